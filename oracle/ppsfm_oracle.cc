@@ -1,0 +1,1097 @@
+// ppsfm_oracle.cc — CPU oracle for the line-lifted absolute-pose RANSAC path.
+//
+// TEST INFRASTRUCTURE ONLY (see ppsfm_oracle.h).  Dependency-free C++17 restatement of the
+// reference's CPU path; every function cites the reference file:line it follows
+// (paths relative to the upstream repository colmap/privacy_preserving_sfm).
+//
+// Build: g++ -O2 -ffp-contract=off -shared -fPIC   (no FMA contraction: the reference is built
+// for baseline x86-64, CMakeLists.txt has no -march flag, so every mul/add rounds separately).
+//
+// PARITY: scoring / support / sampler / RANSAC loop follow in-tree reference code 1:1.
+// P6L + re3q3 call Eigen in the reference (absent here): elimination, LU and the companion-matrix
+// eigenvalue step are restated from the published algorithms (Francis double-shift QR on the
+// Hessenberg companion matrix, EISPACK `hqr` lineage, as used by Eigen::RealSchur) — pinned by the
+// reference's known-answer properties only; bit-level parity with an Eigen build is UNPINNED.
+// The two `rand()`-driven degenerate fallbacks (absolute_pose.cc:128-134, re3q3.h:39-64) use a
+// FIXED generic matrix instead of C rand() so that results are reproducible.
+
+#include "ppsfm_oracle.h"
+
+#include <algorithm>
+#include <cfloat>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <numeric>
+#include <random>
+#include <vector>
+
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// util/random.{h,cc}: one std::mt19937, default seed 0 (random.h:46), lazily created (:90-92).
+// ---------------------------------------------------------------------------------------------
+std::mt19937* g_prng = nullptr;
+
+std::mt19937& Prng() {
+  if (g_prng == nullptr) g_prng = new std::mt19937(0u);
+  return *g_prng;
+}
+
+// util/random.h:88-97 RandomInteger<uint32_t>
+uint32_t RandomInteger(uint32_t lo, uint32_t hi) {
+  std::uniform_int_distribution<uint32_t> distribution(lo, hi);
+  return distribution(Prng());
+}
+
+// optim/random_sampler.cc:40-62 — persistent permutation, partial Fisher-Yates of the first k.
+struct RandomSampler {
+  size_t k;
+  std::vector<size_t> idxs;
+  explicit RandomSampler(size_t num_samples) : k(num_samples) {}
+  void Initialize(size_t total) {
+    idxs.resize(total);
+    std::iota(idxs.begin(), idxs.end(), 0);
+  }
+  // util/random.h:120-128 Shuffle(num_to_shuffle, &elems)
+  void Sample(size_t* out) {
+    const uint32_t last = static_cast<uint32_t>(idxs.size() - 1);
+    for (uint32_t i = 0; i < static_cast<uint32_t>(k); ++i) {
+      const uint32_t j = RandomInteger(i, last);
+      std::swap(idxs[i], idxs[j]);
+    }
+    for (size_t i = 0; i < k; ++i) out[i] = idxs[i];
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Small dense helpers (stand-ins for the Eigen calls of the reference).
+// Matrices are row-major double[r][c] unless stated.
+// ---------------------------------------------------------------------------------------------
+
+// Eigen 3x3 determinant (cofactor expansion along the first row).
+inline double Det3(const double m[3][3]) {
+  const double h0 = m[0][0] * (m[1][1] * m[2][2] - m[1][2] * m[2][1]);
+  const double h1 = m[0][1] * (m[1][0] * m[2][2] - m[1][2] * m[2][0]);
+  const double h2 = m[0][2] * (m[1][0] * m[2][1] - m[1][1] * m[2][0]);
+  return h0 - h1 + h2;
+}
+
+// Solve A X = B for 3x3 A with PARTIAL (row) pivoting; B is 3 x ncols, overwritten by X.
+// Stand-in for Eigen::PartialPivLU<Matrix3d>::solve (absolute_pose.cc:137).
+template <int NC>
+void SolvePartialPiv3(double A[3][3], double B[3][NC]) {
+  for (int k = 0; k < 3; ++k) {
+    int piv = k;
+    double best = std::fabs(A[k][k]);
+    for (int i = k + 1; i < 3; ++i) {
+      const double v = std::fabs(A[i][k]);
+      if (v > best) {
+        best = v;
+        piv = i;
+      }
+    }
+    if (piv != k) {
+      for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[piv][j]);
+      for (int j = 0; j < NC; ++j) std::swap(B[k][j], B[piv][j]);
+    }
+    for (int i = k + 1; i < 3; ++i) {
+      const double f = A[i][k] / A[k][k];
+      A[i][k] = f;
+      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
+      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
+    }
+  }
+  for (int j = 0; j < NC; ++j) {
+    B[2][j] = B[2][j] / A[2][2];
+    B[1][j] = (B[1][j] - A[1][2] * B[2][j]) / A[1][1];
+    B[0][j] = (B[0][j] - A[0][1] * B[1][j] - A[0][2] * B[2][j]) / A[0][0];
+  }
+}
+
+// Solve A X = B for 3x3 A with FULL pivoting (Eigen::FullPivLU, which is what MatrixBase::lu()
+// returns — re3q3.h:71,75,79).  B is 3 x NC, overwritten by X.
+template <int NC>
+void SolveFullPiv3(double A[3][3], double B[3][NC]) {
+  int colperm[3] = {0, 1, 2};
+  for (int k = 0; k < 3; ++k) {
+    int pr = k, pc = k;
+    double best = -1.0;
+    for (int j = k; j < 3; ++j) {  // column-major scan, first maximum wins
+      for (int i = k; i < 3; ++i) {
+        const double v = std::fabs(A[i][j]);
+        if (v > best) {
+          best = v;
+          pr = i;
+          pc = j;
+        }
+      }
+    }
+    if (pr != k) {
+      for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[pr][j]);
+      for (int j = 0; j < NC; ++j) std::swap(B[k][j], B[pr][j]);
+    }
+    if (pc != k) {
+      for (int i = 0; i < 3; ++i) std::swap(A[i][k], A[i][pc]);
+      std::swap(colperm[k], colperm[pc]);
+    }
+    for (int i = k + 1; i < 3; ++i) {
+      const double f = A[i][k] / A[k][k];
+      A[i][k] = f;
+      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
+      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
+    }
+  }
+  double X[3][NC];
+  for (int j = 0; j < NC; ++j) {
+    const double y2 = B[2][j] / A[2][2];
+    const double y1 = (B[1][j] - A[1][2] * y2) / A[1][1];
+    const double y0 = (B[0][j] - A[0][1] * y1 - A[0][2] * y2) / A[0][0];
+    X[colperm[0]][j] = y0;
+    X[colperm[1]][j] = y1;
+    X[colperm[2]][j] = y2;
+  }
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < NC; ++j) B[i][j] = X[i][j];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Polynomial helpers: p[k] is the coefficient of x^k.
+// ---------------------------------------------------------------------------------------------
+// out (degree da+db) = a * b ; out[k] accumulates a[i]*b[k-i] for increasing i.
+template <int DA, int DB>
+inline void PolyMul(const double* a, const double* b, double* out) {
+  for (int k = 0; k <= DA + DB; ++k) {
+    double acc = 0.0;
+    bool first = true;
+    for (int i = 0; i <= DA; ++i) {
+      const int j = k - i;
+      if (j < 0 || j > DB) continue;
+      const double t = a[i] * b[j];
+      if (first) {
+        acc = t;
+        first = false;
+      } else {
+        acc = acc + t;
+      }
+    }
+    out[k] = acc;
+  }
+}
+template <int D>
+inline void PolyAdd(double* acc, const double* b) {
+  for (int k = 0; k <= D; ++k) acc[k] = acc[k] + b[k];
+}
+template <int D>
+inline void PolySub(double* acc, const double* b) {
+  for (int k = 0; k <= D; ++k) acc[k] = acc[k] - b[k];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Eigenvalues of the 8x8 companion matrix (re3q3.h:152-165: Eigen::EigenSolver<Matrix8d>).
+// Real Schur form by Francis double-shift QR on an upper-Hessenberg matrix (EISPACK hqr /
+// JAMA lineage, the algorithm inside Eigen::RealSchur); eigenvalues are read off the
+// quasi-triangular diagonal top-to-bottom, which fixes the ORDER of the returned roots.
+// Only the active window is updated (sufficient for eigenvalues; window values are identical).
+// ---------------------------------------------------------------------------------------------
+constexpr int kN = 8;
+
+struct Hqr8 {
+  double T[kN][kN];
+
+  // Householder vector for a 3- or 2-vector (Eigen makeHouseholder): returns tau, beta, ess[].
+  static void MakeHouseholder(const double* v, int n, double* ess, double* tau, double* beta) {
+    double tail_sq = 0.0;
+    for (int i = 1; i < n; ++i) tail_sq = tail_sq + v[i] * v[i];
+    const double c0 = v[0];
+    if (tail_sq <= std::numeric_limits<double>::min()) {
+      *tau = 0.0;
+      *beta = c0;
+      for (int i = 0; i < n - 1; ++i) ess[i] = 0.0;
+    } else {
+      double b = std::sqrt(c0 * c0 + tail_sq);
+      if (c0 >= 0.0) b = -b;
+      for (int i = 0; i < n - 1; ++i) ess[i] = v[i + 1] / (c0 - b);
+      *tau = (b - c0) / b;
+      *beta = b;
+    }
+  }
+
+  // rows r0..r0+ne (ne = #ess), columns c_lo..c_hi :  M <- (I - tau [1;ess][1;ess]^T) M
+  void ApplyLeft(int r0, int ne, const double* ess, double tau, int c_lo, int c_hi) {
+    if (tau == 0.0) return;
+    for (int j = c_lo; j <= c_hi; ++j) {
+      double tmp = ess[0] * T[r0 + 1][j];
+      if (ne == 2) tmp = tmp + ess[1] * T[r0 + 2][j];
+      tmp = tmp + T[r0][j];
+      T[r0][j] = T[r0][j] - tau * tmp;
+      T[r0 + 1][j] = T[r0 + 1][j] - (tau * ess[0]) * tmp;
+      if (ne == 2) T[r0 + 2][j] = T[r0 + 2][j] - (tau * ess[1]) * tmp;
+    }
+  }
+  // columns c0..c0+ne, rows r_lo..r_hi :  M <- M (I - tau [1;ess][1;ess]^T)
+  void ApplyRight(int c0, int ne, const double* ess, double tau, int r_lo, int r_hi) {
+    if (tau == 0.0) return;
+    for (int i = r_lo; i <= r_hi; ++i) {
+      double tmp = T[i][c0 + 1] * ess[0];
+      if (ne == 2) tmp = tmp + T[i][c0 + 2] * ess[1];
+      tmp = tmp + T[i][c0];
+      T[i][c0] = T[i][c0] - tau * tmp;
+      T[i][c0 + 1] = T[i][c0 + 1] - (tau * tmp) * ess[0];
+      if (ne == 2) T[i][c0 + 2] = T[i][c0 + 2] - (tau * tmp) * ess[1];
+    }
+  }
+
+  // Returns false if the iteration limit (40 per row) is hit.
+  bool Reduce() {
+    // Overall scaling by the largest magnitude (RealSchur::compute).
+    double scale = 0.0;
+    for (int i = 0; i < kN; ++i)
+      for (int j = 0; j < kN; ++j) scale = std::max(scale, std::fabs(T[i][j]));
+    if (!(scale > 0.0) || !std::isfinite(scale)) return std::isfinite(scale);
+    for (int i = 0; i < kN; ++i)
+      for (int j = 0; j < kN; ++j) T[i][j] = T[i][j] / scale;
+
+    // The input is already upper Hessenberg (companion matrix) — no Householder reduction needed.
+    double norm = 0.0;
+    for (int j = 0; j < kN; ++j)
+      for (int i = 0; i < std::min(kN, j + 2); ++i) norm = norm + std::fabs(T[i][j]);
+
+    const int max_iters = 40 * kN;
+    int iu = kN - 1, iter = 0, total_iter = 0;
+    double exshift = 0.0;
+    const double eps = std::numeric_limits<double>::epsilon();
+    bool ok = true;
+    if (norm != 0.0) {
+      while (iu >= 0) {
+        // findSmallSubdiagEntry
+        int il = iu;
+        while (il > 0) {
+          const double s = std::fabs(T[il - 1][il - 1]) + std::fabs(T[il][il]);
+          if (std::fabs(T[il][il - 1]) <= eps * s) break;
+          --il;
+        }
+        if (il == iu) {  // one real root
+          T[iu][iu] = T[iu][iu] + exshift;
+          if (iu > 0) T[iu][iu - 1] = 0.0;
+          --iu;
+          iter = 0;
+        } else if (il == iu - 1) {  // 2x2 block: split if its eigenvalues are real
+          const double p = 0.5 * (T[iu - 1][iu - 1] - T[iu][iu]);
+          const double q = p * p + T[iu][iu - 1] * T[iu - 1][iu];
+          T[iu][iu] = T[iu][iu] + exshift;
+          T[iu - 1][iu - 1] = T[iu - 1][iu - 1] + exshift;
+          if (q >= 0.0) {
+            const double z = std::sqrt(std::fabs(q));
+            // Givens rotation G with G^T [a; b] = [r; 0], a = p +- z, b = T[iu][iu-1].
+            const double a = (p >= 0.0) ? (p + z) : (p - z);
+            const double b = T[iu][iu - 1];
+            double c, s;
+            if (b == 0.0) {
+              c = (a < 0.0) ? -1.0 : 1.0;
+              s = 0.0;
+            } else if (a == 0.0) {
+              c = 0.0;
+              s = (b < 0.0) ? 1.0 : -1.0;
+            } else if (std::fabs(a) > std::fabs(b)) {
+              const double t = b / a;
+              double u = std::sqrt(1.0 + t * t);
+              if (a < 0.0) u = -u;
+              c = 1.0 / u;
+              s = -t * c;
+            } else {
+              const double t = a / b;
+              double u = std::sqrt(1.0 + t * t);
+              if (b < 0.0) u = -u;
+              s = -1.0 / u;
+              c = -t * s;
+            }
+            // rows (iu-1, iu) <- G^T rows  (x' = c x - s y ; y' = s x + c y), columns iu-1..iu
+            for (int j = iu - 1; j <= iu; ++j) {
+              const double x = T[iu - 1][j], y = T[iu][j];
+              T[iu - 1][j] = c * x - s * y;
+              T[iu][j] = s * x + c * y;
+            }
+            // columns (iu-1, iu) <- columns G, rows il..iu
+            for (int i = iu - 1; i <= iu; ++i) {
+              const double x = T[i][iu - 1], y = T[i][iu];
+              T[i][iu - 1] = c * x - s * y;
+              T[i][iu] = s * x + c * y;
+            }
+            T[iu][iu - 1] = 0.0;
+          }
+          if (iu > 1) T[iu - 1][iu - 2] = 0.0;
+          iu -= 2;
+          iter = 0;
+        } else {
+          // computeShift
+          double sh0 = T[iu][iu];
+          double sh1 = T[iu - 1][iu - 1];
+          double sh2 = T[iu][iu - 1] * T[iu - 1][iu];
+          if (iter == 10) {  // Wilkinson's ad hoc shift
+            exshift = exshift + sh0;
+            for (int i = 0; i <= iu; ++i) T[i][i] = T[i][i] - sh0;
+            const double s = std::fabs(T[iu][iu - 1]) + std::fabs(T[iu - 1][iu - 2]);
+            sh0 = 0.75 * s;
+            sh1 = 0.75 * s;
+            sh2 = -0.4375 * s * s;
+          }
+          if (iter == 30) {  // MATLAB's ad hoc shift
+            double s = (sh1 - sh0) / 2.0;
+            s = s * s + sh2;
+            if (s > 0.0) {
+              s = std::sqrt(s);
+              if (sh1 < sh0) s = -s;
+              s = s + (sh1 - sh0) / 2.0;
+              s = sh0 - sh2 / s;
+              exshift = exshift + s;
+              for (int i = 0; i <= iu; ++i) T[i][i] = T[i][i] - s;
+              sh0 = sh1 = sh2 = 0.964;
+            }
+          }
+          ++iter;
+          ++total_iter;
+          if (total_iter > max_iters) {
+            ok = false;
+            break;
+          }
+          // initFrancisQRStep: look for two consecutive small sub-diagonal elements
+          int im;
+          double v[3] = {0.0, 0.0, 0.0};
+          for (im = iu - 2; im >= il; --im) {
+            const double Tmm = T[im][im];
+            const double r = sh0 - Tmm;
+            const double s = sh1 - Tmm;
+            v[0] = (r * s - sh2) / T[im + 1][im] + T[im][im + 1];
+            v[1] = T[im + 1][im + 1] - Tmm - r - s;
+            v[2] = T[im + 2][im + 1];
+            if (im == il) break;
+            const double lhs = T[im][im - 1] * (std::fabs(v[1]) + std::fabs(v[2]));
+            const double rhs = v[0] * (std::fabs(T[im - 1][im - 1]) + std::fabs(Tmm) +
+                                       std::fabs(T[im + 1][im + 1]));
+            if (std::fabs(lhs) < eps * rhs) break;
+          }
+          // performFrancisQRStep
+          for (int k = im; k <= iu - 2; ++k) {
+            const bool first = (k == im);
+            double w[3];
+            if (first) {
+              w[0] = v[0];
+              w[1] = v[1];
+              w[2] = v[2];
+            } else {
+              w[0] = T[k][k - 1];
+              w[1] = T[k + 1][k - 1];
+              w[2] = T[k + 2][k - 1];
+            }
+            double ess[2], tau, beta;
+            MakeHouseholder(w, 3, ess, &tau, &beta);
+            if (beta != 0.0) {
+              if (first && k > il)
+                T[k][k - 1] = -T[k][k - 1];
+              else if (!first)
+                T[k][k - 1] = beta;
+              ApplyLeft(k, 2, ess, tau, k, iu);
+              ApplyRight(k, 2, ess, tau, il, std::min(iu, k + 3));
+            }
+          }
+          {
+            double w[2] = {T[iu - 1][iu - 2], T[iu][iu - 2]};
+            double ess[1], tau, beta;
+            MakeHouseholder(w, 2, ess, &tau, &beta);
+            if (beta != 0.0) {
+              T[iu - 1][iu - 2] = beta;
+              ApplyLeft(iu - 1, 1, ess, tau, iu - 1, iu);
+              ApplyRight(iu - 1, 1, ess, tau, il, iu);
+            }
+          }
+          for (int i = im + 2; i <= iu; ++i) {
+            T[i][i - 2] = 0.0;
+            if (i > im + 2) T[i][i - 3] = 0.0;
+          }
+        }
+      }
+    }
+    for (int i = 0; i < kN; ++i)
+      for (int j = 0; j < kN; ++j) T[i][j] = T[i][j] * scale;
+    return ok;
+  }
+
+  // EigenSolver::compute eigenvalue extraction; returns count (8) and fills re/im.
+  void Eigenvalues(double* re, double* im) const {
+    int i = 0;
+    while (i < kN) {
+      if (i == kN - 1 || T[i + 1][i] == 0.0) {
+        re[i] = T[i][i];
+        im[i] = 0.0;
+        ++i;
+      } else {
+        const double p = 0.5 * (T[i][i] - T[i + 1][i + 1]);
+        double t0 = T[i + 1][i];
+        double t1 = T[i][i + 1];
+        const double maxval = std::max(std::fabs(p), std::max(std::fabs(t0), std::fabs(t1)));
+        t0 = t0 / maxval;
+        t1 = t1 / maxval;
+        const double p0 = p / maxval;
+        const double z = maxval * std::sqrt(std::fabs(p0 * p0 + t0 * t1));
+        re[i] = T[i + 1][i + 1] + p;
+        im[i] = z;
+        re[i + 1] = T[i + 1][i + 1] + p;
+        im[i + 1] = -z;
+        i += 2;
+      }
+    }
+  }
+};
+
+// c[0] x^8 + c[1] x^7 + ... + c[8]  ->  all eigenvalues of the companion matrix (re3q3.h:152-165)
+bool Poly8Roots(const double* c, double* re, double* im) {
+  Hqr8 h;
+  for (int i = 0; i < kN; ++i)
+    for (int j = 0; j < kN; ++j) h.T[i][j] = 0.0;
+  for (int j = 0; j < kN; ++j) h.T[0][j] = -c[j + 1] / c[0];
+  for (int i = 1; i < kN; ++i) h.T[i][i - 1] = 1.0;
+  const bool ok = h.Reduce();
+  h.Eigenvalues(re, im);
+  return ok;
+}
+
+// ---------------------------------------------------------------------------------------------
+// re3q3  (lib/re3q3/re3q3/re3q3.h:16-200)
+// coeffs[k][m], monomial order x^2 xy xz y^2 yz z^2 x y z 1.
+// ---------------------------------------------------------------------------------------------
+
+// Fixed generic change of variables replacing the reference's rand()-driven one (re3q3.h:41-42).
+const double kVarChangeA[3][4] = {
+    // rotation of unit quaternion (0.42,-0.31,0.56,0.64)/|.| ; translation (0.3,-0.5,0.8)/|.|
+    {-0.45264637943155561, -0.88862107060359552, 0.073917846740986226, 0.30304576336566319},
+    {0.19122225569950785, -0.015767801546650473, 0.98142010645776834, -0.5050762722761053},
+    {-0.8709450637742292, 0.45837099527970276, 0.1770613638646179, 0.80812203564176865}};
+
+int Re3q3Impl(double coeffs[3][10], double solutions[3][8], bool try_var_change) {
+  // Choose the elimination variable by the largest |det| of the quadratic block (:19-37).
+  double Ax[3][3], Ay[3][3], Az[3][3];
+  for (int k = 0; k < 3; ++k) {
+    Ax[k][0] = coeffs[k][3]; Ax[k][1] = coeffs[k][5]; Ax[k][2] = coeffs[k][4];  // y^2 z^2 yz
+    Ay[k][0] = coeffs[k][0]; Ay[k][1] = coeffs[k][5]; Ay[k][2] = coeffs[k][2];  // x^2 z^2 xz
+    Az[k][0] = coeffs[k][3]; Az[k][1] = coeffs[k][0]; Az[k][2] = coeffs[k][1];  // y^2 x^2 yx
+  }
+  const double detx = std::fabs(Det3(Ax));
+  const double dety = std::fabs(Det3(Ay));
+  const double detz = std::fabs(Det3(Az));
+  int elim_var = 1;
+  double det = detx;
+  if (det < dety) { det = dety; elim_var = 2; }
+  if (det < detz) { det = detz; elim_var = 3; }
+
+  if (try_var_change && det < 1e-10) {
+    // Affine change of variables v = A[:, :3] v' + A[:, 3]  (:39-64): every quadric
+    // q(v) = [v;1]^T Q [v;1] becomes q'(v') with Q' = G^T Q G, G = [A; 0 0 0 1].
+    const double(*A)[4] = kVarChangeA;
+    double G[4][4] = {{A[0][0], A[0][1], A[0][2], A[0][3]},
+                      {A[1][0], A[1][1], A[1][2], A[1][3]},
+                      {A[2][0], A[2][1], A[2][2], A[2][3]},
+                      {0.0, 0.0, 0.0, 1.0}};
+    double c2[3][10];
+    for (int k = 0; k < 3; ++k) {
+      const double* c = coeffs[k];
+      const double Q[4][4] = {{c[0], 0.5 * c[1], 0.5 * c[2], 0.5 * c[6]},
+                              {0.5 * c[1], c[3], 0.5 * c[4], 0.5 * c[7]},
+                              {0.5 * c[2], 0.5 * c[4], c[5], 0.5 * c[8]},
+                              {0.5 * c[6], 0.5 * c[7], 0.5 * c[8], c[9]}};
+      double QG[4][4], Qp[4][4];
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          double s = 0.0;
+          for (int l = 0; l < 4; ++l) s = s + Q[i][l] * G[l][j];
+          QG[i][j] = s;
+        }
+      for (int i = 0; i < 4; ++i)
+        for (int j = 0; j < 4; ++j) {
+          double s = 0.0;
+          for (int l = 0; l < 4; ++l) s = s + G[l][i] * QG[l][j];
+          Qp[i][j] = s;
+        }
+      c2[k][0] = Qp[0][0];
+      c2[k][1] = Qp[0][1] + Qp[1][0];
+      c2[k][2] = Qp[0][2] + Qp[2][0];
+      c2[k][3] = Qp[1][1];
+      c2[k][4] = Qp[1][2] + Qp[2][1];
+      c2[k][5] = Qp[2][2];
+      c2[k][6] = Qp[0][3] + Qp[3][0];
+      c2[k][7] = Qp[1][3] + Qp[3][1];
+      c2[k][8] = Qp[2][3] + Qp[3][2];
+      c2[k][9] = Qp[3][3];
+    }
+    const int n = Re3q3Impl(c2, solutions, false);
+    for (int s = 0; s < n; ++s) {  // revert (:60-62)
+      const double x = solutions[0][s], y = solutions[1][s], z = solutions[2][s];
+      for (int i = 0; i < 3; ++i)
+        solutions[i][s] = A[i][0] * x + A[i][1] * y + A[i][2] * z + A[i][3];
+    }
+    return n;
+  }
+
+  // Column order so that the eliminated variable plays the role of "x" (:68-80).
+  // P columns: [x^2, xy, xz, x, y, z, 1] in the permuted naming.
+  static const int kCols[3][7] = {{0, 1, 2, 6, 7, 8, 9},   // eliminate x
+                                  {3, 1, 4, 7, 6, 8, 9},   // eliminate y (x<->y)
+                                  {5, 4, 2, 8, 7, 6, 9}};  // eliminate z (x<->z)
+  double A[3][3], P[3][7];
+  for (int k = 0; k < 3; ++k) {
+    for (int j = 0; j < 3; ++j)
+      A[k][j] = (elim_var == 1) ? Ax[k][j] : (elim_var == 2) ? Ay[k][j] : Az[k][j];
+    for (int j = 0; j < 7; ++j) P[k][j] = coeffs[k][kCols[elim_var - 1][j]];
+  }
+  SolveFullPiv3<7>(A, P);
+  for (int k = 0; k < 3; ++k)
+    for (int j = 0; j < 7; ++j) P[k][j] = -P[k][j];
+
+  // Now (naming after the permutation)
+  //   y^2 = py0 y + pz0 z + p10,  z^2 = py1 y + pz1 z + p11,  yz = py2 y + pz2 z + p12
+  // with polynomial coefficients in x (index = power of x).
+  double py[3][2], pz[3][2], p1[3][3];
+  for (int i = 0; i < 3; ++i) {
+    py[i][0] = P[i][4]; py[i][1] = P[i][1];
+    pz[i][0] = P[i][5]; pz[i][1] = P[i][2];
+    p1[i][0] = P[i][6]; p1[i][1] = P[i][3]; p1[i][2] = P[i][0];
+  }
+
+  // Hidden-variable resultant: M(x) [y z 1]^T = 0 from the three syzygies
+  //   z*(y^2) - y*(yz) = 0,   z*(yz) - y*(z^2) = 0,   (y^2)(z^2) - (yz)^2 = 0     (:84-137)
+  double m1y[3], m1z[3], m11[4], m2y[3], m2z[3], m21[4], m3y[4], m3z[4], m31[5];
+  double t2[3], t3[4];
+  // row 1
+  PolyMul<1, 1>(pz[0], py[1], m1y);
+  PolyMul<1, 1>(pz[2], py[2], t2); PolySub<2>(m1y, t2);
+  PolySub<2>(m1y, p1[2]);
+  PolyMul<1, 1>(py[0], pz[2], m1z);
+  PolyMul<1, 1>(pz[0], pz[1], t2); PolyAdd<2>(m1z, t2);
+  PolyMul<1, 1>(py[2], pz[0], t2); PolySub<2>(m1z, t2);
+  PolyMul<1, 1>(pz[2], pz[2], t2); PolySub<2>(m1z, t2);
+  PolyAdd<2>(m1z, p1[0]);
+  PolyMul<1, 2>(py[0], p1[2], m11);
+  PolyMul<1, 2>(pz[0], p1[1], t3); PolyAdd<3>(m11, t3);
+  PolyMul<1, 2>(py[2], p1[0], t3); PolySub<3>(m11, t3);
+  PolyMul<1, 2>(pz[2], p1[2], t3); PolySub<3>(m11, t3);
+  // row 2
+  PolyMul<1, 1>(py[2], py[2], m2y);
+  PolyMul<1, 1>(pz[2], py[1], t2); PolyAdd<2>(m2y, t2);
+  PolyMul<1, 1>(py[1], py[0], t2); PolySub<2>(m2y, t2);
+  PolyMul<1, 1>(pz[1], py[2], t2); PolySub<2>(m2y, t2);
+  PolySub<2>(m2y, p1[1]);
+  PolyMul<1, 1>(py[2], pz[2], m2z);
+  PolyMul<1, 1>(py[1], pz[0], t2); PolySub<2>(m2z, t2);
+  PolyAdd<2>(m2z, p1[2]);
+  PolyMul<1, 2>(py[2], p1[2], m21);
+  PolyMul<1, 2>(pz[2], p1[1], t3); PolyAdd<3>(m21, t3);
+  PolyMul<1, 2>(py[1], p1[0], t3); PolySub<3>(m21, t3);
+  PolyMul<1, 2>(pz[1], p1[2], t3); PolySub<3>(m21, t3);
+  // row 3: alpha y^2 + beta yz + gamma z^2 + (linear part), reduced once more
+  double al[3], be[3], ga[3];
+  PolyMul<1, 1>(py[0], py[1], al);
+  PolyMul<1, 1>(py[2], py[2], t2); PolySub<2>(al, t2);
+  PolyMul<1, 1>(py[0], pz[1], be);
+  PolyMul<1, 1>(pz[0], py[1], t2); PolyAdd<2>(be, t2);
+  PolyMul<1, 1>(py[2], pz[2], t2); PolySub<2>(be, t2); PolySub<2>(be, t2);
+  PolyMul<1, 1>(pz[0], pz[1], ga);
+  PolyMul<1, 1>(pz[2], pz[2], t2); PolySub<2>(ga, t2);
+  PolyMul<2, 1>(al, py[0], m3y);
+  PolyMul<2, 1>(be, py[2], t3); PolyAdd<3>(m3y, t3);
+  PolyMul<2, 1>(ga, py[1], t3); PolyAdd<3>(m3y, t3);
+  PolyMul<1, 2>(py[0], p1[1], t3); PolyAdd<3>(m3y, t3);
+  PolyMul<1, 2>(py[1], p1[0], t3); PolyAdd<3>(m3y, t3);
+  PolyMul<1, 2>(py[2], p1[2], t3); PolySub<3>(m3y, t3); PolySub<3>(m3y, t3);
+  PolyMul<2, 1>(al, pz[0], m3z);
+  PolyMul<2, 1>(be, pz[2], t3); PolyAdd<3>(m3z, t3);
+  PolyMul<2, 1>(ga, pz[1], t3); PolyAdd<3>(m3z, t3);
+  PolyMul<1, 2>(pz[0], p1[1], t3); PolyAdd<3>(m3z, t3);
+  PolyMul<1, 2>(pz[1], p1[0], t3); PolyAdd<3>(m3z, t3);
+  PolyMul<1, 2>(pz[2], p1[2], t3); PolySub<3>(m3z, t3); PolySub<3>(m3z, t3);
+  double t4[5];
+  PolyMul<2, 2>(al, p1[0], m31);
+  PolyMul<2, 2>(be, p1[2], t4); PolyAdd<4>(m31, t4);
+  PolyMul<2, 2>(ga, p1[1], t4); PolyAdd<4>(m31, t4);
+  PolyMul<2, 2>(p1[0], p1[1], t4); PolyAdd<4>(m31, t4);
+  PolyMul<2, 2>(p1[2], p1[2], t4); PolySub<4>(m31, t4);
+
+  // det M(x): degree 8 (:139-150)
+  double d[9], u6[7], w6[7], u5[6], w5[6], t8[9];
+  PolyMul<2, 4>(m2z, m31, u6);
+  PolyMul<3, 3>(m21, m3z, w6); PolySub<6>(u6, w6);
+  PolyMul<2, 6>(m1y, u6, d);
+  PolyMul<2, 4>(m2y, m31, u6);
+  PolyMul<3, 3>(m21, m3y, w6); PolySub<6>(u6, w6);
+  PolyMul<2, 6>(m1z, u6, t8); PolySub<8>(d, t8);
+  PolyMul<2, 3>(m2y, m3z, u5);
+  PolyMul<2, 3>(m2z, m3y, w5); PolySub<5>(u5, w5);
+  PolyMul<3, 5>(m11, u5, t8); PolyAdd<8>(d, t8);
+
+  double c[9];
+  for (int k = 0; k <= 8; ++k) c[k] = d[8 - k];  // c[0] = leading coefficient
+
+  double re[8], im[8];
+  Poly8Roots(c, re, im);
+
+  int root_cnt = 0;
+  for (int i = 0; i < 8; ++i) {
+    if (std::fabs(im[i]) > 1e-8) continue;  // (:173)
+    const double xs1 = re[i];
+    const double xs2 = xs1 * xs1;
+    const double xs3 = xs1 * xs2;
+    const double xs4 = xs1 * xs3;
+    (void)xs4;
+    const double A00 = m1y[2] * xs2 + m1y[1] * xs1 + m1y[0];
+    const double A01 = m1z[2] * xs2 + m1z[1] * xs1 + m1z[0];
+    const double A02 = m11[3] * xs3 + m11[2] * xs2 + m11[1] * xs1 + m11[0];
+    const double A10 = m2y[2] * xs2 + m2y[1] * xs1 + m2y[0];
+    const double A11 = m2z[2] * xs2 + m2z[1] * xs1 + m2z[0];
+    const double A12 = m21[3] * xs3 + m21[2] * xs2 + m21[1] * xs1 + m21[0];
+    solutions[0][root_cnt] = xs1;
+    solutions[1][root_cnt] = (A12 * A01 - A02 * A11) / (A00 * A11 - A10 * A01);
+    solutions[2][root_cnt] = (A12 * A00 - A02 * A10) / (A01 * A10 - A11 * A00);
+    ++root_cnt;
+  }
+  if (elim_var == 2) {
+    for (int s = 0; s < root_cnt; ++s) std::swap(solutions[0][s], solutions[1][s]);
+  } else if (elim_var == 3) {
+    for (int s = 0; s < root_cnt; ++s) std::swap(solutions[0][s], solutions[2][s]);
+  }
+  return root_cnt;
+}
+
+// ---------------------------------------------------------------------------------------------
+// P6L  (src/estimators/absolute_pose.cc:46-162)
+// ---------------------------------------------------------------------------------------------
+// Fixed substitute for Eigen's setRandom() in the degenerate-translation-block branch (:128-134).
+const double kMixA[3][3] = {{0.680375, -0.211234, 0.566198},
+                            {0.596880, 0.823295, -0.604897},
+                            {-0.329554, 0.536459, -0.444451}};
+
+int P6LEstimate(const double lines[6][3], const uint8_t aligned[6], const double points[6][3],
+                double models[8][12]) {
+  bool all_aligned = true;
+  for (int i = 0; i < 6; ++i) all_aligned = all_aligned && (aligned[i] != 0);
+  if (all_aligned) return 0;  // (:87-97)
+
+  // l^T t + kron(X^T, l^T) vec(R) = 0  (:101-123), vec(R) column-major.
+  double tt[3][9], Rc[3][9];
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < 3; ++k)
+      for (int j = 0; j < 3; ++j) {
+        tt[i][3 * k + j] = points[i][k] * lines[i][j];
+        Rc[i][3 * k + j] = points[i + 3][k] * lines[i + 3][j];
+      }
+
+  // B = [l0 l1 l2] (columns); |det| test (:126-134)
+  double B[3][3], L1[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) {
+      B[r][c] = lines[c][r];
+      L1[r][c] = lines[c + 3][r];
+    }
+  const double det_tt = std::fabs(Det3(B));
+  if (det_tt < 1e-10) {
+    double tt2[3][9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 9; ++j) {
+        const double s = kMixA[i][0] * Rc[0][j] + kMixA[i][1] * Rc[1][j] + kMixA[i][2] * Rc[2][j];
+        tt2[i][j] = tt[i][j] + s;
+      }
+    std::memcpy(tt, tt2, sizeof(tt));
+    double B2[3][3];
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 3; ++c) {
+        const double s = L1[r][0] * kMixA[c][0] + L1[r][1] * kMixA[c][1] + L1[r][2] * kMixA[c][2];
+        B2[r][c] = B[r][c] + s;
+      }
+    std::memcpy(B, B2, sizeof(B));
+  }
+
+  // tt <- B^-T tt  (:137)
+  double Bt[3][3];
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) Bt[r][c] = B[c][r];
+  SolvePartialPiv3<9>(Bt, tt);
+  // Rc <- Rc - L1^T tt  (:138)
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 9; ++j) {
+      const double s = L1[0][i] * tt[0][j] + L1[1][i] * tt[1][j] + L1[2][i] * tt[2][j];
+      Rc[i][j] = Rc[i][j] - s;
+    }
+
+  // rotation_to_e3q3 (:46-62): Cayley parametrisation turns each linear form into a quadric.
+  double coeffs[3][10];
+  for (int k = 0; k < 3; ++k) {
+    const double* r = Rc[k];
+    coeffs[k][0] = r[0] - r[4] - r[8];
+    coeffs[k][1] = 2 * r[1] + 2 * r[3];
+    coeffs[k][2] = 2 * r[2] + 2 * r[6];
+    coeffs[k][3] = r[4] - r[0] - r[8];
+    coeffs[k][4] = 2 * r[5] + 2 * r[7];
+    coeffs[k][5] = r[8] - r[4] - r[0];
+    coeffs[k][6] = 2 * r[5] - 2 * r[7];
+    coeffs[k][7] = 2 * r[6] - 2 * r[2];
+    coeffs[k][8] = 2 * r[1] - 2 * r[3];
+    coeffs[k][9] = r[0] + r[4] + r[8];
+  }
+
+  double sols[3][8];
+  const int n_sols = Re3q3Impl(coeffs, sols, true);
+
+  for (int s = 0; s < n_sols; ++s) {
+    // cayley_param (:64-75), R row-major here
+    const double c0 = sols[0][s], c1 = sols[1][s], c2 = sols[2][s];
+    double R[3][3];
+    R[0][0] = c0 * c0 - c1 * c1 - c2 * c2 + 1;
+    R[0][1] = 2 * c0 * c1 - 2 * c2;
+    R[0][2] = 2 * c1 + 2 * c0 * c2;
+    R[1][0] = 2 * c2 + 2 * c0 * c1;
+    R[1][1] = c1 * c1 - c0 * c0 - c2 * c2 + 1;
+    R[1][2] = 2 * c1 * c2 - 2 * c0;
+    R[2][0] = 2 * c0 * c2 - 2 * c1;
+    R[2][1] = 2 * c0 + 2 * c1 * c2;
+    R[2][2] = c2 * c2 - c1 * c1 - c0 * c0 + 1;
+    const double nrm = 1 + c0 * c0 + c1 * c1 + c2 * c2;
+    double* m = models[s];
+    for (int c = 0; c < 3; ++c)
+      for (int r = 0; r < 3; ++r) m[3 * c + r] = R[r][c] / nrm;
+    // t = -tt * vec(R)  (:154)
+    for (int i = 0; i < 3; ++i) {
+      double acc = (-tt[i][0]) * m[0];
+      for (int j = 1; j < 9; ++j) acc = acc + (-tt[i][j]) * m[j];
+      m[9 + i] = acc;
+    }
+  }
+  return n_sols;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Scoring (src/estimators/utils.cc:40-89) and support (src/optim/support_measurement.cc:36-60)
+// ---------------------------------------------------------------------------------------------
+void LineResiduals(const double* lines, const double* points, size_t n, const double* m,
+                   double* res) {
+  const double P_00 = m[0], P_10 = m[1], P_20 = m[2];
+  const double P_01 = m[3], P_11 = m[4], P_21 = m[5];
+  const double P_02 = m[6], P_12 = m[7], P_22 = m[8];
+  const double P_03 = m[9], P_13 = m[10], P_23 = m[11];
+  for (size_t i = 0; i < n; ++i) {
+    const double X_0 = points[3 * i + 0];
+    const double X_1 = points[3 * i + 1];
+    const double X_2 = points[3 * i + 2];
+    const double px_2 = P_20 * X_0 + P_21 * X_1 + P_22 * X_2 + P_23;
+    if (px_2 > std::numeric_limits<double>::epsilon()) {
+      const double px_0 = P_00 * X_0 + P_01 * X_1 + P_02 * X_2 + P_03;
+      const double px_1 = P_10 * X_0 + P_11 * X_1 + P_12 * X_2 + P_13;
+      const double l_0 = lines[3 * i + 0];
+      const double l_1 = lines[3 * i + 1];
+      const double l_2 = lines[3 * i + 2];
+      const double inv_px_2 = 1.0 / px_2;
+      const double r = px_0 * l_0 * inv_px_2 + px_1 * l_1 * inv_px_2 + l_2;
+      res[i] = r * r;
+    } else {
+      res[i] = std::numeric_limits<double>::max();
+    }
+  }
+}
+
+struct Support {
+  size_t num_inliers = 0;
+  double residual_sum = std::numeric_limits<double>::max();  // support_measurement.h:51-52
+};
+
+Support EvaluateSupport(const double* res, size_t n, double max_residual) {
+  Support s;
+  s.num_inliers = 0;
+  s.residual_sum = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (res[i] <= max_residual) {
+      s.num_inliers += 1;
+      s.residual_sum += res[i];
+    }
+  }
+  return s;
+}
+
+bool CompareSupport(const Support& a, const Support& b) {  // support_measurement.cc:52-60
+  if (a.num_inliers > b.num_inliers) return true;
+  return a.num_inliers == b.num_inliers && a.residual_sum < b.residual_sum;
+}
+
+// src/optim/ransac.h:158-176
+size_t ComputeNumTrials(size_t num_inliers, size_t num_samples, double confidence,
+                        double multiplier) {
+  const double inlier_ratio = num_inliers / static_cast<double>(num_samples);
+  const double nom = 1 - confidence;
+  if (nom <= 0) return std::numeric_limits<size_t>::max();
+  const double denom = 1 - std::pow(inlier_ratio, 6);
+  if (denom <= 0) return 1;
+  return static_cast<size_t>(std::ceil(std::log(nom) / std::log(denom) * multiplier));
+}
+
+// src/optim/ransac.h:144-156 (constructor) + :178-278 (Estimate)
+void RansacP6L(const double* lines, const uint8_t* aligned, const double* points, size_t n,
+               const orc_ransac_options& opt_in, orc_ransac_report* report, uint8_t* mask,
+               bool adaptive) {
+  orc_ransac_options opt = opt_in;
+  {
+    const size_t kNumSamples = 100000;
+    const size_t dyn = ComputeNumTrials(static_cast<size_t>(opt.min_inlier_ratio * kNumSamples),
+                                        kNumSamples, opt.confidence,
+                                        opt.dyn_num_trials_multiplier);
+    opt.max_num_trials = std::min<uint64_t>(opt.max_num_trials, dyn);
+  }
+  std::memset(report, 0, sizeof(*report));
+  report->best_trial = -1;
+  report->best_model_idx = -1;
+  report->residual_sum = std::numeric_limits<double>::max();
+  if (n < 6) return;
+
+  Support best;
+  double best_model[12] = {0};
+  bool abort = false;
+  const double max_residual = opt.max_error * opt.max_error;
+  std::vector<double> residuals(n);
+
+  RandomSampler sampler(6);
+  sampler.Initialize(n);
+
+  size_t max_num_trials = opt.max_num_trials;
+  size_t dyn_max_num_trials = max_num_trials;
+  size_t num_trials = 0;
+  uint64_t scored = 0;
+  for (num_trials = 0; num_trials < max_num_trials; ++num_trials) {
+    if (abort) {
+      num_trials += 1;
+      break;
+    }
+    size_t idx[6];
+    sampler.Sample(idx);
+    double l6[6][3], p6[6][3];
+    uint8_t a6[6];
+    for (int i = 0; i < 6; ++i) {
+      for (int j = 0; j < 3; ++j) {
+        l6[i][j] = lines[3 * idx[i] + j];
+        p6[i][j] = points[3 * idx[i] + j];
+      }
+      a6[i] = aligned ? aligned[idx[i]] : 0;
+    }
+    double models[8][12];
+    const int nm = P6LEstimate(l6, a6, p6, models);
+    for (int m = 0; m < nm; ++m) {
+      LineResiduals(lines, points, n, models[m], residuals.data());
+      ++scored;
+      const Support s = EvaluateSupport(residuals.data(), n, max_residual);
+      if (CompareSupport(s, best)) {
+        best = s;
+        std::memcpy(best_model, models[m], sizeof(best_model));
+        report->best_trial = static_cast<int64_t>(num_trials);
+        report->best_model_idx = m;
+        if (adaptive)
+          dyn_max_num_trials = ComputeNumTrials(best.num_inliers, n, opt.confidence,
+                                                opt.dyn_num_trials_multiplier);
+      }
+      if (adaptive && num_trials >= dyn_max_num_trials && num_trials >= opt.min_num_trials) {
+        abort = true;
+        break;
+      }
+    }
+  }
+  report->num_trials = num_trials;
+  report->num_inliers = best.num_inliers;
+  report->residual_sum = best.residual_sum;
+  report->num_models_scored = scored;
+  std::memcpy(report->model, best_model, sizeof(best_model));
+  if (best.num_inliers < 6) return;
+  report->success = 1;
+  if (mask != nullptr) {
+    LineResiduals(lines, points, n, best_model, residuals.data());
+    for (size_t i = 0; i < n; ++i) mask[i] = residuals[i] <= max_residual ? 1 : 0;
+  }
+}
+
+}  // namespace
+
+// =============================================================================================
+// C interface
+// =============================================================================================
+extern "C" {
+
+void orc_set_prng_seed(uint32_t seed) {
+  delete g_prng;
+  g_prng = new std::mt19937(seed);
+}
+
+uint32_t orc_prng_peek(void) {
+  std::mt19937 copy = Prng();
+  return static_cast<uint32_t>(copy());
+}
+
+void orc_line_residuals(const double* lines, const double* points, size_t n, const double* model,
+                        double* residuals_out) {
+  LineResiduals(lines, points, n, model, residuals_out);
+}
+
+void orc_inlier_support(const double* residuals, size_t n, double max_residual,
+                        uint64_t* num_inliers, double* residual_sum) {
+  const Support s = EvaluateSupport(residuals, n, max_residual);
+  *num_inliers = s.num_inliers;
+  *residual_sum = s.residual_sum;
+}
+
+void orc_mestimator_support(const double* residuals, size_t n, double max_residual,
+                            uint64_t* num_inliers, double* score) {
+  uint64_t cnt = 0;
+  double sc = 0;
+  for (size_t i = 0; i < n; ++i) {
+    if (residuals[i] <= max_residual) {
+      cnt += 1;
+      sc += residuals[i];
+    } else {
+      sc += max_residual;
+    }
+  }
+  *num_inliers = cnt;
+  *score = sc;
+}
+
+uint64_t orc_compute_num_trials(uint64_t num_inliers, uint64_t num_samples, double confidence,
+                                double num_trials_multiplier) {
+  return ComputeNumTrials(num_inliers, num_samples, confidence, num_trials_multiplier);
+}
+
+void orc_sample_table(size_t n, size_t num_trials, uint32_t* table_out) {
+  RandomSampler sampler(6);
+  sampler.Initialize(n);
+  for (size_t t = 0; t < num_trials; ++t) {
+    size_t idx[6];
+    sampler.Sample(idx);
+    for (int i = 0; i < 6; ++i) table_out[6 * t + i] = static_cast<uint32_t>(idx[i]);
+  }
+}
+
+int orc_re3q3(const double* coeffs, double* solutions) {
+  double c[3][10], s[3][8];
+  std::memcpy(c, coeffs, sizeof(c));
+  std::memset(s, 0, sizeof(s));
+  const int n = Re3q3Impl(c, s, true);
+  for (int k = 0; k < 8; ++k)
+    for (int i = 0; i < 3; ++i) solutions[3 * k + i] = s[i][k];
+  return n;
+}
+
+int orc_poly8_all_roots(const double* c, double* re_im_out) {
+  double re[8], im[8];
+  const bool ok = Poly8Roots(c, re, im);
+  for (int i = 0; i < 8; ++i) {
+    re_im_out[2 * i] = re[i];
+    re_im_out[2 * i + 1] = im[i];
+  }
+  return ok ? 8 : -1;
+}
+
+int orc_poly8_real_roots(const double* c, double* roots_out) {
+  double re[8], im[8];
+  Poly8Roots(c, re, im);
+  int n = 0;
+  for (int i = 0; i < 8; ++i)
+    if (!(std::fabs(im[i]) > 1e-8)) roots_out[n++] = re[i];
+  return n;
+}
+
+int orc_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double* points6,
+                     double* models_out) {
+  double l[6][3], p[6][3], m[8][12];
+  std::memcpy(l, lines6, sizeof(l));
+  std::memcpy(p, points6, sizeof(p));
+  const int n = P6LEstimate(l, aligned6, p, m);
+  std::memcpy(models_out, m, sizeof(double) * 12 * static_cast<size_t>(n));
+  return n;
+}
+
+void orc_rotation_matrix_to_quaternion(const double* R, double* q) {
+  // Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl):
+  // Ken Shoemake's trace-branch algorithm.  R is column-major: R(r,c) = R[3c + r].
+  auto at = [&](int r, int c) { return R[3 * c + r]; };
+  double t = at(0, 0) + at(1, 1) + at(2, 2);
+  double w, v[3];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    w = 0.5 * t;
+    t = 0.5 / t;
+    v[0] = (at(2, 1) - at(1, 2)) * t;
+    v[1] = (at(0, 2) - at(2, 0)) * t;
+    v[2] = (at(1, 0) - at(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (at(1, 1) > at(0, 0)) i = 1;
+    if (at(2, 2) > at(i, i)) i = 2;
+    const int j = (i + 1) % 3;
+    const int k = (j + 1) % 3;
+    t = std::sqrt(at(i, i) - at(j, j) - at(k, k) + 1.0);
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    w = (at(k, j) - at(j, k)) * t;
+    v[j] = (at(j, i) + at(i, j)) * t;
+    v[k] = (at(k, i) + at(i, k)) * t;
+  }
+  q[0] = w;
+  q[1] = v[0];
+  q[2] = v[1];
+  q[3] = v[2];
+}
+
+void orc_ransac_p6l(const double* lines, const uint8_t* aligned, const double* points, size_t n,
+                    const orc_ransac_options* options, orc_ransac_report* report,
+                    uint8_t* inlier_mask) {
+  RansacP6L(lines, aligned, points, n, *options, report, inlier_mask, true);
+}
+
+int orc_estimate_absolute_pose_from_lines(const double* lines, const uint8_t* aligned,
+                                          const double* points, size_t n,
+                                          const orc_ransac_options* options, double* qvec,
+                                          double* tvec, uint64_t* num_inliers,
+                                          uint8_t* inlier_mask, orc_ransac_report* report_out) {
+  // src/estimators/pose.cc:52-94
+  orc_ransac_report report;
+  std::vector<uint8_t> mask(n, 0);
+  RansacP6L(lines, aligned, points, n, *options, &report, mask.data(), true);
+  if (report_out) *report_out = report;
+  *num_inliers = report.num_inliers;
+  // report.inlier_mask is empty unless success; callers index it only when num_inliers > 0.
+  if (inlier_mask) std::memcpy(inlier_mask, mask.data(), n);
+  if (*num_inliers == 0) return 0;
+  size_t num_aligned_inliers = 0;
+  for (size_t i = 0; i < n; ++i)
+    if (mask[i] && aligned && aligned[i]) num_aligned_inliers += 1;
+  if (num_aligned_inliers > *num_inliers * 0.9) return 0;
+  orc_rotation_matrix_to_quaternion(report.model, qvec);
+  tvec[0] = report.model[9];
+  tvec[1] = report.model[10];
+  tvec[2] = report.model[11];
+  for (int i = 0; i < 4; ++i)
+    if (std::isnan(qvec[i])) return 0;
+  for (int i = 0; i < 3; ++i)
+    if (std::isnan(tvec[i])) return 0;
+  return 1;
+}
+
+uint64_t orc_ransac_p6l_fixed_trials(const double* lines, const uint8_t* aligned,
+                                     const double* points, size_t n, double max_error,
+                                     uint64_t num_trials, orc_ransac_report* report) {
+  orc_ransac_options opt;
+  opt.max_error = max_error;
+  opt.min_inlier_ratio = 0.0;  // constructor cap becomes SIZE_MAX-like (denom = 1 -> log(1)=0)
+  opt.confidence = 0.99999;
+  opt.dyn_num_trials_multiplier = 3.0;
+  opt.min_num_trials = num_trials;
+  opt.max_num_trials = num_trials;
+  orc_ransac_report local;
+  // min_inlier_ratio = 0 makes ComputeNumTrials divide by log(1) = 0 -> +inf -> cast UB; avoid it
+  // by using a tiny ratio whose cap far exceeds any realistic num_trials.
+  opt.min_inlier_ratio = 0.01;
+  RansacP6L(lines, aligned, points, n, opt, report ? report : &local, nullptr, false);
+  return (report ? report : &local)->num_models_scored;
+}
+
+}  // extern "C"
