@@ -879,7 +879,16 @@ void RansacP6L(const double* lines, const uint8_t* aligned, const double* points
     double models[8][12];
     const int nm = P6LEstimate(l6, a6, p6, models);
     for (int m = 0; m < nm; ++m) {
-      LineResiduals(lines, points, n, models[m], residuals.data());
+      // P6LEstimator::Residuals (absolute_pose.cc:165-174) first copies every line into a fresh
+      // std::vector<Eigen::Vector3d> (emplace_back without reserve) — restated so that the CPU
+      // baseline pays the same per-model allocation + copy as the reference.
+      {
+        struct V3 { double v[3]; };
+        std::vector<V3> line_params;
+        for (size_t i = 0; i < n; ++i)
+          line_params.emplace_back(V3{{lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]}});
+        LineResiduals(&line_params[0].v[0], points, n, models[m], residuals.data());
+      }
       ++scored;
       const Support s = EvaluateSupport(residuals.data(), n, max_residual);
       if (CompareSupport(s, best)) {

@@ -1,0 +1,78 @@
+// bench_kernels.cu — measurement helpers used by bench.py (not on the product path):
+//   * FP64 issue-rate micro-benchmarks (the roofline denominator of the scoring kernel: FP64
+//     peak is not in MEASURED_PEAKS.json, SURVEY.md §8d asks the builder to measure it)
+//   * an L2 flush (writes a buffer larger than the 126 MB L2)
+#include "common.h"
+
+namespace {
+
+template <bool kFused>
+__global__ void __launch_bounds__(256) fp64_rate_kernel(double* out, int iters, double a,
+                                                        double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+  double x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  for (int i = 0; i < iters; ++i) {
+    if (kFused) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    } else {
+      x0 = __dmul_rn(x0, a); x1 = __dadd_rn(x1, b); x2 = __dmul_rn(x2, a); x3 = __dadd_rn(x3, b);
+      x4 = __dmul_rn(x4, a); x5 = __dadd_rn(x5, b); x6 = __dmul_rn(x6, a); x7 = __dadd_rn(x7, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+
+}  // namespace
+
+extern "C" {
+
+// Returns FP64 instruction throughput in 1e12 thread-instructions per second:
+// *dfma_tips for DFMA (x2 = TFLOP/s), *dmuladd_tips for an unfused DMUL/DADD mix.
+int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips) {
+  if (!ctx) return PPSFM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int blocks = ctx->num_sms * 8, threads = 256, iters = 8192;
+  double* d = nullptr;
+  PPSFM_CUDA(ctx, cudaMalloc(&d, sizeof(double) * blocks * threads));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best[2] = {0, 0};
+  for (int mode = 0; mode < 2; ++mode) {
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(a, ctx->stream);
+      if (mode == 0)
+        fp64_rate_kernel<true><<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+      else
+        fp64_rate_kernel<false><<<blocks, threads, 0, ctx->stream>>>(d, iters, 1.0000001, 1e-9);
+      cudaEventRecord(b, ctx->stream);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      const double ops = (double)blocks * threads * iters * 8.0;
+      const double tips = ops / (ms * 1e-3) / 1e12;
+      if (rep > 0 && tips > best[mode]) best[mode] = tips;
+    }
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  PPSFM_CUDA(ctx, cudaGetLastError());
+  if (dfma_tips) *dfma_tips = best[0];
+  if (dmuladd_tips) *dmuladd_tips = best[1];
+  return PPSFM_OK;
+}
+
+// Evicts L2 by writing `bytes` (>= 256 MB recommended) on the context stream; blocking.
+int ppsfm_bench_l2_flush(ppsfm_ctx* ctx, size_t bytes) {
+  if (!ctx) return PPSFM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  static thread_local ppsfm::DevBuf buf;
+  PPSFM_CUDA(ctx, buf.reserve(bytes));
+  PPSFM_CUDA(ctx, cudaMemsetAsync(buf.p, 1, bytes, ctx->stream));
+  PPSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return PPSFM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,112 @@
+// common.h — context, error handling and device-buffer helpers shared by the translation units
+// of libppsfm_b200.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/ppsfm_b200.h"
+
+namespace ppsfm {
+
+// Growable device / pinned-host buffers (never shrink; freed with the context).
+struct DevBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+struct PinBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t reserve(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 4 + 256;
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  template <typename T>
+  T* as() const { return static_cast<T*>(p); }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+};
+
+}  // namespace ppsfm
+
+// Correspondence set resident in HBM.
+struct ppsfm_corr {
+  size_t n = 0;
+  double* corr6 = nullptr;    // n x 6 interleaved (l0,l1,l2,X0,X1,X2): 48 B per correspondence
+  uint8_t* aligned = nullptr; // n bytes
+  std::vector<uint8_t> aligned_host;  // host copy for the aligned-inlier test (pose.cc:71-83)
+};
+
+struct ppsfm_ctx {
+  int device = 0;
+  int num_sms = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[8] = {nullptr};
+  std::string last_error;
+  std::mt19937 prng{0u};  // util/random.h:46 kDefaultPRNGSeed = 0
+
+  // RANSAC scratch
+  ppsfm::DevBuf d_samples, d_models, d_num_models, d_cmodels, d_msrc, d_K, d_part_cnt,
+      d_part_sum, d_cnt, d_sum, d_eidx, d_emodels, d_rbuf, d_esum, d_ecnt, d_mask, d_tmp_corr,
+      d_tmp_aligned;
+  ppsfm::PinBuf h_samples, h_num_models, h_cnt, h_sum, h_eidx, h_emodels, h_esum, h_ecnt, h_mask,
+      h_K, h_stage;
+  ppsfm_ransac_timing timing{};
+
+  // BA state lives in ba.cu (opaque here)
+  void* ba_state = nullptr;
+};
+
+namespace ppsfm {
+
+inline int fail(ppsfm_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->last_error = buf;
+  return code;
+}
+
+#define PPSFM_CUDA(ctx, expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess)                                                                 \
+      return ::ppsfm::fail((ctx), PPSFM_ERR_CUDA, "%s:%d %s -> %s", __FILE__, __LINE__,    \
+                           #expr, cudaGetErrorString(_e));                                 \
+  } while (0)
+
+}  // namespace ppsfm

@@ -1,0 +1,379 @@
+// ransac_kernels.cu — sm_100a kernels of the absolute-pose RANSAC path.
+//   * p6l_solve_kernel        one thread per hypothesis (P6L + re3q3)         [A3, A4]
+//   * model_offsets_kernel    exclusive scan of per-trial model counts -> compact model ids
+//   * score_kernel            (32-model group) x (correspondence segment) tiles; correspondence
+//                             tiles are staged in shared memory by the TMA bulk-copy engine
+//                             (cp.async.bulk + mbarrier) and broadcast to the 8 warps   [A5, A8]
+//   * reduce_parts_kernel     per-model combination of the per-segment partial supports
+//   * exact_residual_kernel / seq_support_kernel: index-order (reference-order) supports
+//     and inlier mask for the few candidate models that can become "best"
+//
+// Compiled with --fmad=false: every FP64 operation rounds separately, in the order the reference
+// evaluates it (src/estimators/utils.cc:64-88), so residuals, masks and supports are bit-exact.
+#include <cfloat>
+#include <cstdint>
+
+#include "p6l_device.cuh"
+#include "ransac_kernels.h"
+
+namespace ppsfm {
+
+// ------------------------------------------------------------------------------------------
+// Correspondence packing: (lines n x 3, points n x 3) -> corr6 n x 6 (48-byte records).
+// ------------------------------------------------------------------------------------------
+__global__ void pack_corr_kernel(const double* __restrict__ lines,
+                                 const double* __restrict__ points, size_t n,
+                                 double* __restrict__ corr6) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i >= n * 3) return;
+  const size_t r = i / 3, c = i % 3;
+  corr6[r * 6 + c] = lines[i];
+  corr6[r * 6 + 3 + c] = points[i];
+}
+
+void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
+                      cudaStream_t s) {
+  const int threads = 256;
+  const size_t total = n * 3;
+  pack_corr_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(lines, points,
+                                                                                    n, corr6);
+}
+
+// ------------------------------------------------------------------------------------------
+// P6L solve: one thread per hypothesis.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(64)
+p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ aligned,
+                 const uint32_t* __restrict__ samples, int num_trials,
+                 double* __restrict__ models_out, int* __restrict__ num_models_out) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= num_trials) return;
+  double lines[6][3], points[6][3];
+  bool all_aligned = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const uint32_t idx = samples[6 * (size_t)t + i];
+    const double* c = corr6 + 6 * (size_t)idx;
+    lines[i][0] = c[0]; lines[i][1] = c[1]; lines[i][2] = c[2];
+    points[i][0] = c[3]; points[i][1] = c[4]; points[i][2] = c[5];
+    all_aligned = all_aligned && (aligned != nullptr && aligned[idx] != 0);
+  }
+  double models[8][12];
+  const int n = dev::p6l_estimate(lines, all_aligned, points, models);
+  num_models_out[t] = n;
+  double* out = models_out + (size_t)t * 96;
+  for (int m = 0; m < n; ++m)
+    for (int j = 0; j < 12; ++j) out[m * 12 + j] = models[m][j];
+}
+
+void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
+                      int num_trials, double* models_out, int* num_models_out, cudaStream_t s) {
+  if (num_trials <= 0) return;
+  const int threads = 64;
+  p6l_solve_kernel<<<(num_trials + threads - 1) / threads, threads, 0, s>>>(
+      corr6, aligned, samples, num_trials, models_out, num_models_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Exclusive scan of model counts (single block; H <= a few 10^5).
+// offsets[t] = first compact id of trial t; offsets[H] = K.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+model_offsets_kernel(const int* __restrict__ num_models, int num_trials,
+                     int* __restrict__ offsets) {
+  __shared__ int warp_sums[32];
+  __shared__ int carry_s;
+  const int tid = threadIdx.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  if (tid == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < num_trials; base += 1024) {
+    const int t = base + tid;
+    const int v = (t < num_trials) ? num_models[t] : 0;
+    int x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, x, d);
+      if (lane >= d) x += y;
+    }
+    if (lane == 31) warp_sums[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const int y = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += y;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const int carry = carry_s;
+    const int incl = x + (warp > 0 ? warp_sums[warp - 1] : 0) + carry;
+    if (t < num_trials) offsets[t] = incl - v;
+    __syncthreads();
+    if (tid == 1023) carry_s = incl;
+    __syncthreads();
+  }
+  if (tid == 0) offsets[num_trials] = carry_s;
+}
+
+void launch_model_offsets(const int* num_models, int num_trials, int* offsets, cudaStream_t s) {
+  model_offsets_kernel<<<1, 1024, 0, s>>>(num_models, num_trials, offsets);
+}
+
+// ------------------------------------------------------------------------------------------
+// TMA bulk copy + mbarrier helpers (sm_90+/sm_100a PTX).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* dst, const void* src, uint32_t bytes,
+                                              uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(dst)),
+      "l"(src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------
+// Scoring kernel.  Thread <-> model (12 doubles in registers), warp <-> 32 consecutive compact
+// models, block <-> 8 warps sharing one correspondence segment.  Every lane walks the segment in
+// index order, so each per-segment partial sum is an index-order sum.
+// ------------------------------------------------------------------------------------------
+constexpr int kScoreThreads = 256;
+constexpr int kTile = 128;    // correspondences per shared-memory tile (6 KB)
+constexpr int kStages = 4;
+
+__device__ __forceinline__ void score_one(const double* __restrict__ c, const double (&P)[12],
+                                          const double max_residual, unsigned& cnt, double& sum) {
+  // src/estimators/utils.cc:64-88 — same operations, same order, no contraction.
+  const double2* c2 = reinterpret_cast<const double2*>(c);  // 48-byte records, 16-B aligned
+  const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
+  const double l_0 = v0.x, l_1 = v0.y, l_2 = v1.x;
+  const double X_0 = v1.y, X_1 = v2.x, X_2 = v2.y;
+  const double px_2 = P[2] * X_0 + P[5] * X_1 + P[8] * X_2 + P[11];
+  if (px_2 > DBL_EPSILON) {
+    const double px_0 = P[0] * X_0 + P[3] * X_1 + P[6] * X_2 + P[9];
+    const double px_1 = P[1] * X_0 + P[4] * X_1 + P[7] * X_2 + P[10];
+    const double inv_px_2 = 1.0 / px_2;
+    const double res = px_0 * l_0 * inv_px_2 + px_1 * l_1 * inv_px_2 + l_2;
+    const double r2 = res * res;
+    // src/optim/support_measurement.cc:42-47
+    if (r2 <= max_residual) {
+      cnt += 1;
+      sum += r2;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kScoreThreads)
+score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__ models,
+             const int* __restrict__ offsets, int num_trials, int seg_len, double max_residual,
+             int kcap, unsigned* __restrict__ part_cnt, double* __restrict__ part_sum) {
+  __shared__ __align__(128) double tile[kStages][kTile * 6];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+
+  const int K = offsets[num_trials];
+  const int mbase = blockIdx.x * kScoreThreads;
+  if (mbase >= K) return;
+  const int seg = blockIdx.y;
+  const int i0 = seg * seg_len;
+  const int i1 = min(n, i0 + seg_len);
+  const int k = mbase + threadIdx.x;
+
+  // Locate (trial, m) of compact model k: largest t with offsets[t] <= k.
+  double P[12];
+  if (k < K) {
+    int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offsets[mid] <= k) lo = mid; else hi = mid;
+    }
+    const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) P[j] = src[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) P[j] = 0.0;  // px_2 = 0 -> never counted
+  }
+
+  const int len = max(0, i1 - i0);
+  const int num_tiles = (len + kTile - 1) / kTile;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages && s < num_tiles; ++s) {
+      const int cnt_s = min(kTile, len - s * kTile);
+      const uint32_t bytes = (uint32_t)cnt_s * 48u;
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + s * kTile) * 6, bytes, &full_bar[s]);
+    }
+  }
+
+  unsigned cnt = 0;
+  double sum = 0.0;
+  for (int t = 0; t < num_tiles; ++t) {
+    const int s = t % kStages;
+    const uint32_t parity = (uint32_t)((t / kStages) & 1);
+    mbar_wait(&full_bar[s], parity);
+    const int cnt_t = min(kTile, len - t * kTile);
+    const double* tp = &tile[s][0];
+    int j = 0;
+    for (; j + 4 <= cnt_t; j += 4) {
+      score_one(tp + (j + 0) * 6, P, max_residual, cnt, sum);
+      score_one(tp + (j + 1) * 6, P, max_residual, cnt, sum);
+      score_one(tp + (j + 2) * 6, P, max_residual, cnt, sum);
+      score_one(tp + (j + 3) * 6, P, max_residual, cnt, sum);
+    }
+    for (; j < cnt_t; ++j) score_one(tp + j * 6, P, max_residual, cnt, sum);
+    __syncthreads();  // everyone is done reading stage s
+    if (threadIdx.x == 0 && t + kStages < num_tiles) {
+      const int tn = t + kStages;
+      const int cnt_n = min(kTile, len - tn * kTile);
+      const uint32_t bytes = (uint32_t)cnt_n * 48u;
+      fence_proxy_async();
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
+    }
+  }
+  if (k < K) {
+    part_cnt[(size_t)seg * kcap + k] = cnt;
+    part_sum[(size_t)seg * kcap + k] = sum;
+  }
+}
+
+__global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt,
+                                    const double* __restrict__ part_sum, int num_segs, int kcap,
+                                    const int* __restrict__ offsets, int num_trials,
+                                    unsigned* __restrict__ cnt_out, double* __restrict__ sum_out) {
+  const int K = offsets[num_trials];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  unsigned c = 0;
+  double s = 0.0;
+  for (int g = 0; g < num_segs; ++g) {
+    c += part_cnt[(size_t)g * kcap + k];
+    s += part_sum[(size_t)g * kcap + k];
+  }
+  cnt_out[k] = c;
+  sum_out[k] = s;
+}
+
+void launch_score(const double* corr6, int n, const double* models, const int* offsets,
+                  int num_trials, int num_segs, int seg_len, double max_residual, int kcap,
+                  unsigned* part_cnt, double* part_sum, unsigned* cnt_out, double* sum_out,
+                  cudaStream_t s) {
+  if (num_trials <= 0) return;
+  dim3 grid((kcap + kScoreThreads - 1) / kScoreThreads, num_segs);
+  score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
+                                              max_residual, kcap, part_cnt, part_sum);
+  reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, part_sum, num_segs, kcap,
+                                                         offsets, num_trials, cnt_out, sum_out);
+}
+
+// ------------------------------------------------------------------------------------------
+// Exact (reference-order) support for a handful of models.
+// ------------------------------------------------------------------------------------------
+__global__ void exact_residual_kernel(const double* __restrict__ corr6, int n,
+                                      const double* __restrict__ emodels, int num_e,
+                                      double max_residual, double* __restrict__ rbuf,
+                                      uint8_t* __restrict__ mask) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* c = corr6 + (size_t)i * 6;
+  const double l_0 = c[0], l_1 = c[1], l_2 = c[2];
+  const double X_0 = c[3], X_1 = c[4], X_2 = c[5];
+  for (int e = 0; e < num_e; ++e) {
+    const double* P = emodels + (size_t)e * 12;
+    const double px_2 = P[2] * X_0 + P[5] * X_1 + P[8] * X_2 + P[11];
+    double r2;
+    if (px_2 > DBL_EPSILON) {
+      const double px_0 = P[0] * X_0 + P[3] * X_1 + P[6] * X_2 + P[9];
+      const double px_1 = P[1] * X_0 + P[4] * X_1 + P[7] * X_2 + P[10];
+      const double inv_px_2 = 1.0 / px_2;
+      const double res = px_0 * l_0 * inv_px_2 + px_1 * l_1 * inv_px_2 + l_2;
+      r2 = res * res;
+    } else {
+      r2 = DBL_MAX;
+    }
+    rbuf[(size_t)e * n + i] = r2;
+    if (mask != nullptr) mask[(size_t)e * n + i] = (r2 <= max_residual) ? 1 : 0;
+  }
+}
+
+// One warp per model: index-order sum of the inlier residuals (support_measurement.cc:42-47).
+__global__ void seq_support_kernel(const double* __restrict__ rbuf, int n, int num_e,
+                                   double max_residual, unsigned long long* __restrict__ ecnt,
+                                   double* __restrict__ esum) {
+  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (e >= num_e) return;
+  const int lane = threadIdx.x & 31;
+  const double* r = rbuf + (size_t)e * n;
+  unsigned long long cnt = 0;
+  double sum = 0.0;
+  double next = (lane < n) ? r[lane] : DBL_MAX;
+  for (int base = 0; base < n; base += 32) {
+    const double v = next;
+    const int ni = base + 32 + lane;
+    next = (ni < n) ? r[ni] : DBL_MAX;
+    const bool inl = (base + lane < n) && (v <= max_residual);
+    unsigned m = __ballot_sync(0xffffffffu, inl);
+    cnt += __popc(m);
+    while (m) {
+      const int b = __ffs(m) - 1;
+      m &= m - 1;
+      sum += __shfl_sync(0xffffffffu, v, b);
+    }
+  }
+  if (lane == 0) {
+    ecnt[e] = cnt;
+    esum[e] = sum;
+  }
+}
+
+void launch_exact(const double* corr6, int n, const double* emodels, int num_e,
+                  double max_residual, double* rbuf, uint8_t* mask, unsigned long long* ecnt,
+                  double* esum, cudaStream_t s) {
+  if (num_e <= 0 || n <= 0) return;
+  exact_residual_kernel<<<(n + 255) / 256, 256, 0, s>>>(corr6, n, emodels, num_e, max_residual,
+                                                        rbuf, mask);
+  if (ecnt != nullptr) {
+    const int warps_per_block = 4;
+    seq_support_kernel<<<(num_e + warps_per_block - 1) / warps_per_block, warps_per_block * 32,
+                         0, s>>>(rbuf, n, num_e, max_residual, ecnt, esum);
+  }
+}
+
+}  // namespace ppsfm

@@ -1,0 +1,167 @@
+"""GPU parity tests of the absolute-pose RANSAC path: CUDA (through the C-ABI) vs the CPU oracle.
+
+Bar: bit-exact residuals, supports, inlier masks, winning (trial, model) indices, models and PRNG
+state; these are integer / IEEE-double-without-contraction computations.
+"""
+import numpy as np
+import pytest
+
+from privacy_preserving_sfm_b200 import RANSACOptions, synthetic as S
+import privacy_preserving_sfm_b200 as pp
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_opts(O, o):
+    return O.make_options(o.max_error, o.min_inlier_ratio, o.confidence,
+                          o.dyn_num_trials_multiplier, o.min_num_trials, o.max_num_trials)
+
+
+def test_sample_table_matches_oracle(ctx, oracle):
+    for n, h in [(6, 10), (7, 33), (1000, 500), (50000, 2000)]:
+        ctx.set_prng_seed(0)
+        oracle.set_prng_seed(0)
+        a = ctx.sample_table(n, h)
+        b = oracle.sample_table(n, h)
+        assert np.array_equal(a, b)
+        assert ctx.prng_peek() == oracle.prng_peek()
+
+
+def test_line_residuals_bit_exact(ctx, oracle):
+    sc = S.make_abs_pose_scene(n=4099, seed=3)
+    rng = np.random.default_rng(5)
+    models = [S.model_from_pose(sc["R"], sc["t"])]
+    for _ in range(6):
+        models.append(S.model_from_pose(S.random_rotation(rng), rng.uniform(-1, 1, 3)))
+    models = np.array(models)
+    thr = (12 / 1000.0) ** 2
+    res, cnt, sm = ctx.line_residuals(sc["lines"], sc["points"], models, thr)
+    for k in range(len(models)):
+        r = oracle.line_residuals(sc["lines"], sc["points"], models[k])
+        assert np.array_equal(res[k], r)           # bit-exact, incl. DBL_MAX behind the camera
+        c, s = oracle.inlier_support(r, thr)
+        assert int(cnt[k]) == c
+        assert sm[k] == s                           # index-order sum, bit-exact
+
+
+def test_line_residuals_empty_and_ragged(ctx, oracle):
+    sc = S.make_abs_pose_scene(n=37, seed=4)
+    m = S.model_from_pose(sc["R"], sc["t"])[None, :]
+    res, cnt, sm = ctx.line_residuals(sc["lines"][:0], sc["points"][:0], m, 1e-4)
+    assert res.shape == (1, 0) and cnt[0] == 0 and sm[0] == 0.0
+    for n in (1, 31, 32, 33, 37):
+        res, cnt, sm = ctx.line_residuals(sc["lines"][:n], sc["points"][:n], m, 1e-4)
+        r = oracle.line_residuals(sc["lines"][:n], sc["points"][:n], m[0])
+        assert np.array_equal(res[0], r)
+        assert (int(cnt[0]), sm[0]) == oracle.inlier_support(r, 1e-4)
+
+
+def test_p6l_solve_batch_bit_exact(ctx, oracle):
+    sc = S.make_abs_pose_scene(n=3000, seed=7)
+    ctx.set_prng_seed(1)
+    table = ctx.sample_table(3000, 600)
+    models, nm = ctx.p6l_solve_batch(sc["lines"], sc["aligned"], sc["points"], table)
+    tot = 0
+    for t in range(table.shape[0]):
+        idx = table[t]
+        ref = oracle.p6l_estimate(sc["lines"][idx], sc["aligned"][idx], sc["points"][idx])
+        assert nm[t] == len(ref), f"trial {t}"
+        assert np.array_equal(models[t, :nm[t]], ref), f"trial {t}"
+        tot += nm[t]
+    assert tot > 1000
+
+
+def test_p6l_recovers_generating_pose(ctx):
+    probs = S.make_p6l_minimal_problems(200, seed=11)
+    est = pp.P6LEstimator(ctx)
+    errs = []
+    for p in probs:
+        sols = est.Estimate(p["lines"], p["points"])
+        gt = np.hstack([p["R"], p["t"][:, None]])
+        errs.append(min(np.abs(s - gt).max() for s in sols))
+    assert np.median(errs) < 1e-10 and max(errs) < 1e-6
+
+
+def test_p6l_all_aligned_returns_no_model(ctx):
+    p = S.make_p6l_minimal_problems(1, seed=2)[0]
+    est = pp.P6LEstimator(ctx)
+    assert est.Estimate((p["lines"], np.ones(6, np.uint8)), p["points"]) == []
+
+
+@pytest.mark.parametrize("n,opts,cases", [
+    (2000, dict(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999, min_num_trials=100,
+                max_num_trials=10000), [(0.3, 1), (0.7, 2), (0.05, 3)]),   # mapper settings
+    (5000, dict(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999, min_num_trials=3000,
+                max_num_trials=3000), [(0.3, 1), (0.9, 2)]),               # fixed trial count
+    (1500, dict(max_error=0.012, min_inlier_ratio=0.1, confidence=0.99, min_num_trials=0,
+                max_num_trials=2**64 - 1), [(0.5, 1), (0.7, 2), (1.0, 3)]),  # defaults, early abort
+    (800, dict(max_error=0.012, min_inlier_ratio=0.3, confidence=0.9999, min_num_trials=0,
+               max_num_trials=2**64 - 1), [(0.35, 4), (0.6, 5)]),          # several waves
+])
+def test_ransac_matches_oracle(ctx, oracle, n, opts, cases):
+    for inlier_ratio, seed in cases:
+        sc = S.make_abs_pose_scene(n=n, inlier_ratio=inlier_ratio, seed=seed)
+        o = RANSACOptions(**opts)
+        ctx.set_prng_seed(0)
+        oracle.set_prng_seed(0)
+        rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+        oref, omask = oracle.ransac_p6l(sc["lines"], sc["aligned"], sc["points"],
+                                        _oracle_opts(oracle, o))
+        tag = f"n={n} ratio={inlier_ratio}"
+        assert rep.success == oref.success, tag
+        assert rep.num_trials == oref.num_trials, tag
+        assert rep.num_inliers == oref.num_inliers, tag
+        assert rep.residual_sum == oref.residual_sum, tag
+        assert (rep.best_trial, rep.best_model_idx) == (oref.best_trial, oref.best_model_idx), tag
+        assert list(rep.model) == list(oref.model), tag
+        assert rep.num_models_scored == oref.num_models_scored, tag
+        if rep.success:
+            assert np.array_equal(mask, omask), tag
+        assert ctx.prng_peek() == oracle.prng_peek(), tag   # same number of PRNG draws
+
+
+def test_ransac_too_few_samples(ctx):
+    sc = S.make_abs_pose_scene(n=5, seed=9)
+    rep, _ = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"],
+                            RANSACOptions(max_error=0.01))
+    assert rep.success == 0 and rep.num_trials == 0
+
+
+def test_estimate_absolute_pose_from_lines(ctx, oracle):
+    sc = S.make_abs_pose_scene(n=4000, inlier_ratio=0.4, seed=21)
+    o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                      min_num_trials=100, max_num_trials=10000)
+    ctx.set_prng_seed(0)
+    oracle.set_prng_seed(0)
+    ok, q, t, ninl, mask = pp.EstimateAbsolutePoseFromLines(
+        o, (sc["lines"], sc["aligned"]), sc["points"], ctx=ctx)
+    ok2, q2, t2, ninl2, mask2, _ = oracle.estimate_absolute_pose_from_lines(
+        sc["lines"], sc["aligned"], sc["points"], _oracle_opts(oracle, o))
+    assert ok and ok2
+    assert np.array_equal(q, q2) and np.array_equal(t, t2)
+    assert ninl == ninl2 and np.array_equal(mask, mask2)
+    # and it is the right pose: rotation angle error < 0.2 deg, translation < 1e-2
+    Rgt = sc["R"]
+    Rest = S.quat_to_rotmat(q / np.linalg.norm(q))
+    ang = np.degrees(np.arccos(np.clip((np.trace(Rest.T @ Rgt) - 1) / 2, -1, 1)))
+    assert ang < 0.2 and np.linalg.norm(t - sc["t"]) < 1e-2
+
+
+def test_estimate_rejects_mostly_aligned_inliers(ctx, oracle):
+    sc = S.make_abs_pose_scene(n=2000, inlier_ratio=0.5, aligned_fraction=0.97, seed=5)
+    o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                      min_num_trials=100, max_num_trials=2000)
+    ctx.set_prng_seed(0)
+    oracle.set_prng_seed(0)
+    ok, *_ = pp.EstimateAbsolutePoseFromLines(o, (sc["lines"], sc["aligned"]), sc["points"],
+                                              ctx=ctx)
+    ok2, *_ = oracle.estimate_absolute_pose_from_lines(sc["lines"], sc["aligned"], sc["points"],
+                                                       _oracle_opts(oracle, o))
+    assert ok == ok2 and not ok      # pose.cc:71-83
+
+
+def test_options_check(ctx):
+    with pytest.raises(pp.PpsfmError):
+        pp.RANSAC_P6L(RANSACOptions(max_error=0.0), ctx)
+    with pytest.raises(pp.PpsfmError):
+        pp.RANSAC_P6L(RANSACOptions(max_error=1.0, min_num_trials=5, max_num_trials=4), ctx)
