@@ -272,7 +272,8 @@ def run_b200(args):
     out = {
         "metric": "ransac_hypotheses_per_sec", "value": value, "unit": "hypotheses/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak",
+        "ms_per_step": 1e3 * total / args.steps, "ms_min": 1e3 * min(step_s),
+        "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "absolute-pose P6L RANSAC, 50k lifted-line correspondences x 10k "
                                "hypotheses per GPU per step (BASELINE.json configs[1])",
@@ -282,7 +283,8 @@ def run_b200(args):
                    "parallelism": f"{world} independent hypothesis batches (one per GPU), "
                                   "no data-path collective"},
         "e2e": {"value": e2e_value, "unit": "hypotheses/s", "h2d_bytes_per_step": int(h2d),
-                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_total / args.steps},
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_total / args.steps,
+                "ms_min": 1e3 * min(e2e_s), "ms_median": 1e3 * float(np.median(e2e_s))},
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": roofline,

@@ -63,12 +63,6 @@ struct Support {
   double residual_sum = std::numeric_limits<double>::max();  // support_measurement.h:51-52
 };
 
-// InlierSupportMeasurer::Compare, src/optim/support_measurement.cc:52-60
-inline bool Better(const Support& a, const Support& b) {
-  if (a.num_inliers > b.num_inliers) return true;
-  return a.num_inliers == b.num_inliers && a.residual_sum < b.residual_sum;
-}
-
 float EventMs(cudaEvent_t a, cudaEvent_t b) {
   float ms = 0.f;
   cudaEventElapsedTime(&ms, a, b);
@@ -122,6 +116,8 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   const size_t max_num_trials = opt.max_num_trials;
   size_t dyn_max_num_trials = max_num_trials;
   Support best;
+  bool have_best = false;       // false while `best` is the initial {0, DBL_MAX}
+  bool best_sum_known = true;   // residual_sum of `best` is an exact index-order sum
   double best_model[12] = {0};
   bool abort = false;
   bool finished = false;
@@ -161,12 +157,9 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     int num_segs, seg_len;
     ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);
     PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
-    PPSFM_CUDA(ctx, ctx->d_part_sum.reserve(sizeof(double) * (size_t)num_segs * kcap));
     PPSFM_CUDA(ctx, ctx->d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
-    PPSFM_CUDA(ctx, ctx->d_sum.reserve(sizeof(double) * (size_t)kcap));
     PPSFM_CUDA(ctx, ctx->h_num_models.reserve(sizeof(int) * ((size_t)H + 1)));
     PPSFM_CUDA(ctx, ctx->h_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
-    PPSFM_CUDA(ctx, ctx->h_sum.reserve(sizeof(double) * (size_t)kcap));
 
     // ---- solve + score on the GPU
     PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, hs, sizeof(uint32_t) * 6 * (size_t)H,
@@ -178,8 +171,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
     launch_score(corr->corr6, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
                  num_segs, seg_len, max_residual, kcap, ctx->d_part_cnt.as<unsigned>(),
-                 ctx->d_part_sum.as<double>(), ctx->d_cnt.as<unsigned>(),
-                 ctx->d_sum.as<double>(), st);
+                 ctx->d_cnt.as<unsigned>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
     ctx->timing.kernel_launches += 4;
     ctx->timing.score_launches += 1;
@@ -199,49 +191,59 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     total_ms += EventMs(ctx->ev[0], ctx->ev[2]);
     ctx->timing.score_pairs += (uint64_t)K * n;
 
-    // ---- pass 1 (counts only): candidates that tie or beat the running best count.
+    // ---- pass 1 (counts only): models that beat or tie the running best count.  Only a TIE
+    // needs residual sums (InlierSupportMeasurer::Compare, support_measurement.cc:52-60), and
+    // those must be index-order sums to match the reference bit for bit.
     std::vector<int> cand;
+    bool has_tie = false;
     {
       size_t b = best.num_inliers;
+      bool have = have_best;
       for (int k = 0; k < K; ++k) {
-        if (h_cnt[k] >= b) {
+        const size_t c = h_cnt[k];
+        if (!have || c > b) {
           cand.push_back(k);
-          b = h_cnt[k];
+          b = c;
+          have = true;
+        } else if (c == b) {
+          cand.push_back(k);
+          has_tie = true;
         }
       }
     }
-    // ---- exact (index-order) supports for the candidates
+    auto model_src = [&](int k) -> size_t {
+      const int t = int(std::upper_bound(h_off, h_off + H + 1, k) - h_off) - 1;
+      return (size_t)t * 96 + (size_t)(k - h_off[t]) * 12;
+    };
     const int E = (int)cand.size();
-    std::vector<double> cand_sum(E), cand_models((size_t)E * 12);
-    std::vector<unsigned long long> cand_cnt(E);
-    if (E > 0) {
-      PPSFM_CUDA(ctx, ctx->h_eidx.reserve(sizeof(double) * 12 * (size_t)E));
-      PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double) * (size_t)E));
-      PPSFM_CUDA(ctx, ctx->h_ecnt.reserve(sizeof(unsigned long long) * (size_t)E));
-      // gather candidate models (device -> host, tiny) then process in batches
-      double* hm = ctx->h_eidx.as<double>();
-      for (int e = 0; e < E; ++e) {
-        const int k = cand[e];
-        const int t = int(std::upper_bound(h_off, h_off + H + 1, k) - h_off) - 1;
-        const size_t src = (size_t)t * 96 + (size_t)(k - h_off[t]) * 12;
-        PPSFM_CUDA(ctx, cudaMemcpyAsync(hm + (size_t)e * 12, ctx->d_models.as<double>() + src,
-                                        sizeof(double) * 12, cudaMemcpyDeviceToHost, st));
-      }
-      PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
-      std::memcpy(cand_models.data(), hm, sizeof(double) * 12 * (size_t)E);
+    std::vector<double> cand_sum;
+    if (has_tie) {
+      // exact (index-order) supports for every candidate of this wave (+ the carried best)
+      const bool carry = have_best && !best_sum_known;
+      const int EE = E + (carry ? 1 : 0);
+      cand_sum.resize(EE);
+      PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double) * (size_t)EE));
+      PPSFM_CUDA(ctx, ctx->h_ecnt.reserve(sizeof(unsigned long long) * (size_t)EE));
       const int kBatch = 32;
       PPSFM_CUDA(ctx, ctx->d_emodels.reserve(sizeof(double) * 12 * kBatch));
       PPSFM_CUDA(ctx, ctx->d_rbuf.reserve(sizeof(double) * (size_t)kBatch * n));
       PPSFM_CUDA(ctx, ctx->d_ecnt.reserve(sizeof(unsigned long long) * kBatch));
       PPSFM_CUDA(ctx, ctx->d_esum.reserve(sizeof(double) * kBatch));
-      for (int e0 = 0; e0 < E; e0 += kBatch) {
-        const int ne = std::min(kBatch, E - e0);
-        PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_emodels.p, hm + (size_t)e0 * 12,
-                                        sizeof(double) * 12 * ne, cudaMemcpyHostToDevice, st));
+      for (int e0 = 0; e0 < EE; e0 += kBatch) {
+        const int ne = std::min(kBatch, EE - e0);
+        for (int e = e0; e < e0 + ne; ++e) {
+          double* dst = ctx->d_emodels.as<double>() + (size_t)(e - e0) * 12;
+          if (e < E)
+            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_models.as<double>() + model_src(cand[e]),
+                                            sizeof(double) * 12, cudaMemcpyDeviceToDevice, st));
+          else
+            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, best_model, sizeof(double) * 12,
+                                            cudaMemcpyHostToDevice, st));
+        }
         PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
         launch_exact(corr->corr6, (int)n, ctx->d_emodels.as<double>(), ne, max_residual,
-                     ctx->d_rbuf.as<double>(), nullptr,
-                     ctx->d_ecnt.as<unsigned long long>(), ctx->d_esum.as<double>(), st);
+                     ctx->d_rbuf.as<double>(), nullptr, ctx->d_ecnt.as<unsigned long long>(),
+                     ctx->d_esum.as<double>(), st);
         PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
         ctx->timing.kernel_launches += 2;
         PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_esum.as<double>() + e0, ctx->d_esum.p,
@@ -254,11 +256,15 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
         ctx->timing.exact_ms += ems;
         total_ms += ems;
       }
-      for (int e = 0; e < E; ++e) {
+      for (int e = 0; e < EE; ++e) {
         cand_sum[e] = ctx->h_esum.as<double>()[e];
-        cand_cnt[e] = ctx->h_ecnt.as<unsigned long long>()[e];
-        if (cand_cnt[e] != h_cnt[cand[e]])
+        const size_t want = e < E ? (size_t)h_cnt[cand[e]] : best.num_inliers;
+        if (ctx->h_ecnt.as<unsigned long long>()[e] != want)
           return fail(ctx, PPSFM_ERR_CUDA, "internal: exact/segmented inlier counts differ");
+      }
+      if (carry) {
+        best.residual_sum = cand_sum[E];
+        best_sum_known = true;
       }
     }
 
@@ -266,7 +272,8 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     // `abort` set at trial t means: samples were drawn for trials 0..t, and the loop reports
     // num_trials = t + 2 (the `if (abort) { num_trials += 1; break; }` at the top of the next
     // iteration) unless t + 1 already equals max_num_trials.
-    size_t ci = 0;  // cursor into cand
+    size_t ci = 0;       // cursor into cand
+    int best_k = -1;     // compact id of the best model if it was set in this wave
     for (size_t trial = t_begin; trial < t_end && !abort; ++trial) {
       const int lt = (int)(trial - t_begin);
       const int k0 = h_off[lt], k1 = h_off[lt + 1];
@@ -274,12 +281,28 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
         ++scored;
         while (ci < cand.size() && cand[ci] < k) ++ci;
         if (ci < cand.size() && cand[ci] == k) {
-          Support s;
-          s.num_inliers = h_cnt[k];
-          s.residual_sum = cand_sum[ci];
-          if (Better(s, best)) {
-            best = s;
-            std::memcpy(best_model, &cand_models[ci * 12], sizeof(best_model));
+          const size_t c = h_cnt[k];
+          bool better;
+          if (!have_best) {
+            better = true;  // {c, sum} vs the initial {0, DBL_MAX}: more inliers, or 0 < DBL_MAX
+          } else if (c > best.num_inliers) {
+            better = true;
+          } else if (c == best.num_inliers) {
+            // tie: both sums are index-order exact here (has_tie forced the exact pass)
+            better = cand_sum[ci] < best.residual_sum;
+          } else {
+            better = false;
+          }
+          if (better) {
+            have_best = true;
+            best.num_inliers = c;
+            if (has_tie) {
+              best.residual_sum = cand_sum[ci];
+              best_sum_known = true;
+            } else {
+              best_sum_known = false;
+            }
+            best_k = k;
             report->best_trial = (int64_t)trial;
             report->best_model_idx = k - k0;
             dyn_max_num_trials = ComputeNumTrials(best.num_inliers, n, opt.confidence,
@@ -298,55 +321,88 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
         }
       }
     }
+    if (best_k >= 0) {  // the best model changed in this wave: bring its 12 doubles to the host
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(best_model, ctx->d_models.as<double>() + model_src(best_k),
+                                      sizeof(best_model), cudaMemcpyDeviceToHost, st));
+      PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+    }
     t_begin = t_end;
   }
 
   report->num_trials = reported_trials;
   report->num_inliers = best.num_inliers;
-  report->residual_sum = best.residual_sum;
   report->num_models_scored = scored;
   std::memcpy(report->model, best_model, sizeof(best_model));
-  ctx->timing.total_ms = total_ms;
-  if (best.num_inliers < 6) return PPSFM_OK;  // src/optim/ransac.h:255-259
-  report->success = 1;
 
-  // Inlier mask of the best model (src/optim/ransac.h:265-275).
-  if (inlier_mask != nullptr) {
+  // Support + inlier mask of the best model in reference (index) order
+  // (src/optim/ransac.h:251-275: the reference also rescans the best model once more).
+  if (have_best) {
     PPSFM_CUDA(ctx, ctx->d_emodels.reserve(sizeof(double) * 12));
     PPSFM_CUDA(ctx, ctx->d_rbuf.reserve(sizeof(double) * n));
     PPSFM_CUDA(ctx, ctx->d_mask.reserve(n));
     PPSFM_CUDA(ctx, ctx->h_mask.reserve(n));
+    PPSFM_CUDA(ctx, ctx->d_ecnt.reserve(sizeof(unsigned long long)));
+    PPSFM_CUDA(ctx, ctx->d_esum.reserve(sizeof(double)));
+    PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double)));
+    PPSFM_CUDA(ctx, ctx->h_ecnt.reserve(sizeof(unsigned long long)));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_emodels.p, best_model, sizeof(best_model),
                                     cudaMemcpyHostToDevice, st));
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+    const bool want_mask = inlier_mask != nullptr && best.num_inliers >= 6;
     launch_exact(corr->corr6, (int)n, ctx->d_emodels.as<double>(), 1, max_residual,
-                 ctx->d_rbuf.as<double>(), ctx->d_mask.as<uint8_t>(), nullptr, nullptr, st);
+                 ctx->d_rbuf.as<double>(), want_mask ? ctx->d_mask.as<uint8_t>() : nullptr,
+                 ctx->d_ecnt.as<unsigned long long>(), ctx->d_esum.as<double>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    ctx->timing.kernel_launches += 1;
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_mask.p, ctx->d_mask.p, n, cudaMemcpyDeviceToHost, st));
+    ctx->timing.kernel_launches += 2;
+    if (want_mask)
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_mask.p, ctx->d_mask.p, n, cudaMemcpyDeviceToHost, st));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_esum.p, ctx->d_esum.p, sizeof(double),
+                                    cudaMemcpyDeviceToHost, st));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ecnt.p, ctx->d_ecnt.p, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, st));
     PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
-    std::memcpy(inlier_mask, ctx->h_mask.p, n);
+    if (ctx->h_ecnt.as<unsigned long long>()[0] != best.num_inliers)
+      return fail(ctx, PPSFM_ERR_CUDA, "internal: exact/segmented inlier counts differ");
+    best.residual_sum = ctx->h_esum.as<double>()[0];
+    if (want_mask) std::memcpy(inlier_mask, ctx->h_mask.p, n);
     const float ems = EventMs(ctx->ev[3], ctx->ev[4]);
     ctx->timing.exact_ms += ems;
-    ctx->timing.total_ms += ems;
+    total_ms += ems;
   }
+  report->residual_sum = best.residual_sum;
+  ctx->timing.total_ms = total_ms;
+  PPSFM_CUDA(ctx, cudaGetLastError());
+  if (best.num_inliers < 6) return PPSFM_OK;  // src/optim/ransac.h:255-259
+  report->success = 1;
   return PPSFM_OK;
 }
 
+// Copies a host correspondence set to HBM and packs it into 48-byte records.  With
+// `use_ctx_buffers` the device storage is the context's growable scratch (no cudaMalloc /
+// cudaFree on the per-call path); otherwise the set owns its allocation (resident handles).
 int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, const double* points,
-               size_t n, ppsfm_corr** out) {
+               size_t n, bool use_ctx_buffers, ppsfm_corr** out) {
   if (!ctx || !out || (n > 0 && (!lines || !points)))
     return fail(ctx, PPSFM_ERR_INVALID, "null argument");
   ppsfm_corr* c = new ppsfm_corr();
   c->n = n;
+  c->owns = !use_ctx_buffers;
   cudaStream_t st = ctx->stream;
   if (n > 0) {
-    cudaError_t e = cudaMalloc(&c->corr6, sizeof(double) * 6 * n);
-    if (e == cudaSuccess) e = cudaMalloc(&c->aligned, n);
+    cudaError_t e;
+    if (use_ctx_buffers) {
+      e = ctx->d_corr6.reserve(sizeof(double) * 6 * n);
+      if (e == cudaSuccess) e = ctx->d_aligned.reserve(n);
+      c->corr6 = ctx->d_corr6.as<double>();
+      c->aligned = ctx->d_aligned.as<uint8_t>();
+    } else {
+      e = cudaMalloc(&c->corr6, sizeof(double) * 6 * n);
+      if (e == cudaSuccess) e = cudaMalloc(&c->aligned, n);
+    }
     if (e != cudaSuccess) {
-      if (c->corr6) cudaFree(c->corr6);
+      if (c->owns && c->corr6) cudaFree(c->corr6);
       delete c;
-      return fail(ctx, PPSFM_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+      return fail(ctx, PPSFM_ERR_CUDA, "device allocation: %s", cudaGetErrorString(e));
     }
     PPSFM_CUDA(ctx, ctx->d_tmp_corr.reserve(sizeof(double) * 6 * n));
     double* tl = ctx->d_tmp_corr.as<double>();
@@ -355,13 +411,12 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
     PPSFM_CUDA(ctx, cudaMemcpyAsync(tp, points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
     if (aligned) {
       PPSFM_CUDA(ctx, cudaMemcpyAsync(c->aligned, aligned, n, cudaMemcpyHostToDevice, st));
-      c->aligned_host.assign(aligned, aligned + n);
     } else {
       PPSFM_CUDA(ctx, cudaMemsetAsync(c->aligned, 0, n, st));
-      c->aligned_host.assign(n, 0);
     }
     launch_pack_corr(tl, tp, n, c->corr6, st);
-    PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+    // no synchronisation here: later work is queued on the same stream; the host buffers must
+    // stay valid until the call that consumes the set returns (all entry points are blocking)
   }
   *out = c;
   return PPSFM_OK;
@@ -369,8 +424,10 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
 
 void FreeCorr(ppsfm_corr* c) {
   if (!c) return;
-  if (c->corr6) cudaFree(c->corr6);
-  if (c->aligned) cudaFree(c->aligned);
+  if (c->owns) {
+    if (c->corr6) cudaFree(c->corr6);
+    if (c->aligned) cudaFree(c->aligned);
+  }
   delete c;
 }
 
@@ -451,7 +508,7 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
                             &ctx->d_msrc, &ctx->d_K, &ctx->d_part_cnt, &ctx->d_part_sum,
                             &ctx->d_cnt, &ctx->d_sum, &ctx->d_eidx, &ctx->d_emodels, &ctx->d_rbuf,
                             &ctx->d_esum, &ctx->d_ecnt, &ctx->d_mask, &ctx->d_tmp_corr,
-                            &ctx->d_tmp_aligned};
+                            &ctx->d_tmp_aligned, &ctx->d_corr6, &ctx->d_aligned};
   for (auto* b : dbufs) b->release();
   ppsfm::PinBuf* pbufs[] = {&ctx->h_samples, &ctx->h_num_models, &ctx->h_cnt, &ctx->h_sum,
                             &ctx->h_eidx, &ctx->h_emodels, &ctx->h_esum, &ctx->h_ecnt,
@@ -501,7 +558,10 @@ int ppsfm_sample_table(ppsfm_ctx* ctx, size_t n, size_t num_trials, uint32_t* ta
 int ppsfm_corr_upload(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned,
                       const double* points, size_t n, ppsfm_corr** out) {
   if (ctx) cudaSetDevice(ctx->device);
-  return UploadCorr(ctx, lines, aligned, points, n, out);
+  int rc = UploadCorr(ctx, lines, aligned, points, n, false, out);
+  if (rc == PPSFM_OK && cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+    rc = fail(ctx, PPSFM_ERR_CUDA, "upload failed");
+  return rc;
 }
 
 void ppsfm_corr_free(ppsfm_ctx* ctx, ppsfm_corr* corr) {
@@ -519,10 +579,12 @@ int ppsfm_ransac_p6l_resident(ppsfm_ctx* ctx, const ppsfm_corr* corr,
 int ppsfm_ransac_p6l(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned,
                      const double* points, size_t n, const ppsfm_ransac_options* options,
                      ppsfm_ransac_report* report, uint8_t* inlier_mask) {
+  if (ctx) cudaSetDevice(ctx->device);
   ppsfm_corr* corr = nullptr;
-  int rc = ppsfm_corr_upload(ctx, lines, aligned, points, n, &corr);
+  int rc = UploadCorr(ctx, lines, aligned, points, n, true, &corr);
   if (rc != PPSFM_OK) return rc;
   rc = RansacResident(ctx, corr, options, report, inlier_mask);
+  if (ctx) cudaStreamSynchronize(ctx->stream);
   FreeCorr(corr);
   return rc;
 }
@@ -568,8 +630,9 @@ int ppsfm_p6l_solve_batch(ppsfm_ctx* ctx, const double* lines, const uint8_t* al
     return fail(ctx, PPSFM_ERR_INVALID, "null argument");
   for (size_t i = 0; i < 6 * num_samples; ++i)
     if (sample_idx[i] >= n) return fail(ctx, PPSFM_ERR_INVALID, "sample index out of range");
+  cudaSetDevice(ctx->device);
   ppsfm_corr* corr = nullptr;
-  int rc = ppsfm_corr_upload(ctx, lines, aligned, points, n, &corr);
+  int rc = UploadCorr(ctx, lines, aligned, points, n, true, &corr);
   if (rc != PPSFM_OK) return rc;
   cudaStream_t st = ctx->stream;
   const size_t H = num_samples;
@@ -607,8 +670,9 @@ int ppsfm_line_residuals(ppsfm_ctx* ctx, const double* lines, const double* poin
     }
     return PPSFM_OK;
   }
+  cudaSetDevice(ctx->device);
   ppsfm_corr* corr = nullptr;
-  int rc = ppsfm_corr_upload(ctx, lines, nullptr, points, n, &corr);
+  int rc = UploadCorr(ctx, lines, nullptr, points, n, true, &corr);
   if (rc != PPSFM_OK) return rc;
   cudaStream_t st = ctx->stream;
   auto body = [&]() -> int {

@@ -11,6 +11,7 @@
 // Compiled with --fmad=false: every FP64 operation rounds separately, in the order the reference
 // evaluates it (src/estimators/utils.cc:64-88), so residuals, masks and supports are bit-exact.
 #include <cfloat>
+#include <cmath>
 #include <cstdint>
 
 #include "p6l_device.cuh"
@@ -173,32 +174,38 @@ constexpr int kScoreThreads = 256;
 constexpr int kTile = 128;    // correspondences per shared-memory tile (6 KB)
 constexpr int kStages = 4;
 
+// Inlier COUNT only: residual sums are needed solely to break count-ties and are then computed
+// in reference (index) order by the exact kernels below.  The two comparisons are done on the
+// bit patterns with integer instructions so that they do not occupy the FP64 pipe:
+//   px_2 > DBL_EPSILON        <=>  (int64)bits(px_2) > (int64)bits(eps)     (NaN: see below)
+//   res * res <= max_residual  <=>  bits(|res|) <= bits(r_max)  with r_max the largest double whose
+//                                  rounded square is <= max_residual (rounding is monotone)
+// A NaN px_2 passes the first test only to produce a NaN residual, which fails the second: the
+// pair is not counted, exactly as with the floating-point comparisons of the reference.
 __device__ __forceinline__ void score_one(const double* __restrict__ c, const double (&P)[12],
-                                          const double max_residual, unsigned& cnt, double& sum) {
+                                          const long long eps_bits,
+                                          const unsigned long long rmax_bits, unsigned& cnt) {
   // src/estimators/utils.cc:64-88 — same operations, same order, no contraction.
   const double2* c2 = reinterpret_cast<const double2*>(c);  // 48-byte records, 16-B aligned
   const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
   const double l_0 = v0.x, l_1 = v0.y, l_2 = v1.x;
   const double X_0 = v1.y, X_1 = v2.x, X_2 = v2.y;
   const double px_2 = P[2] * X_0 + P[5] * X_1 + P[8] * X_2 + P[11];
-  if (px_2 > DBL_EPSILON) {
+  if (__double_as_longlong(px_2) > eps_bits) {
     const double px_0 = P[0] * X_0 + P[3] * X_1 + P[6] * X_2 + P[9];
     const double px_1 = P[1] * X_0 + P[4] * X_1 + P[7] * X_2 + P[10];
     const double inv_px_2 = 1.0 / px_2;
     const double res = px_0 * l_0 * inv_px_2 + px_1 * l_1 * inv_px_2 + l_2;
-    const double r2 = res * res;
-    // src/optim/support_measurement.cc:42-47
-    if (r2 <= max_residual) {
-      cnt += 1;
-      sum += r2;
-    }
+    const unsigned long long ares =
+        (unsigned long long)__double_as_longlong(res) & 0x7fffffffffffffffull;
+    if (ares <= rmax_bits) cnt += 1;  // src/optim/support_measurement.cc:42-45
   }
 }
 
 __global__ void __launch_bounds__(kScoreThreads)
 score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__ models,
-             const int* __restrict__ offsets, int num_trials, int seg_len, double max_residual,
-             int kcap, unsigned* __restrict__ part_cnt, double* __restrict__ part_sum) {
+             const int* __restrict__ offsets, int num_trials, int seg_len, double r_max,
+             int kcap, unsigned* __restrict__ part_cnt) {
   __shared__ __align__(128) double tile[kStages][kTile * 6];
   __shared__ __align__(8) uint64_t full_bar[kStages];
 
@@ -243,7 +250,8 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
   }
 
   unsigned cnt = 0;
-  double sum = 0.0;
+  const long long eps_bits = __double_as_longlong(DBL_EPSILON);
+  const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
   for (int t = 0; t < num_tiles; ++t) {
     const int s = t % kStages;
     const uint32_t parity = (uint32_t)((t / kStages) & 1);
@@ -252,12 +260,12 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
     const double* tp = &tile[s][0];
     int j = 0;
     for (; j + 4 <= cnt_t; j += 4) {
-      score_one(tp + (j + 0) * 6, P, max_residual, cnt, sum);
-      score_one(tp + (j + 1) * 6, P, max_residual, cnt, sum);
-      score_one(tp + (j + 2) * 6, P, max_residual, cnt, sum);
-      score_one(tp + (j + 3) * 6, P, max_residual, cnt, sum);
+      score_one(tp + (j + 0) * 6, P, eps_bits, rmax_bits, cnt);
+      score_one(tp + (j + 1) * 6, P, eps_bits, rmax_bits, cnt);
+      score_one(tp + (j + 2) * 6, P, eps_bits, rmax_bits, cnt);
+      score_one(tp + (j + 3) * 6, P, eps_bits, rmax_bits, cnt);
     }
-    for (; j < cnt_t; ++j) score_one(tp + j * 6, P, max_residual, cnt, sum);
+    for (; j < cnt_t; ++j) score_one(tp + j * 6, P, eps_bits, rmax_bits, cnt);
     __syncthreads();  // everyone is done reading stage s
     if (threadIdx.x == 0 && t + kStages < num_tiles) {
       const int tn = t + kStages;
@@ -268,39 +276,43 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
       bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
     }
   }
-  if (k < K) {
-    part_cnt[(size_t)seg * kcap + k] = cnt;
-    part_sum[(size_t)seg * kcap + k] = sum;
-  }
+  if (k < K) part_cnt[(size_t)seg * kcap + k] = cnt;
 }
 
-__global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt,
-                                    const double* __restrict__ part_sum, int num_segs, int kcap,
+__global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
                                     const int* __restrict__ offsets, int num_trials,
-                                    unsigned* __restrict__ cnt_out, double* __restrict__ sum_out) {
+                                    unsigned* __restrict__ cnt_out) {
   const int K = offsets[num_trials];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   unsigned c = 0;
-  double s = 0.0;
-  for (int g = 0; g < num_segs; ++g) {
-    c += part_cnt[(size_t)g * kcap + k];
-    s += part_sum[(size_t)g * kcap + k];
-  }
+  for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + k];
   cnt_out[k] = c;
-  sum_out[k] = s;
+}
+
+// Largest double r with fl(r * r) <= max_residual (host; IEEE multiplication is monotone).
+double inlier_abs_threshold(double max_residual) {
+  if (!(max_residual >= 0.0)) return -1.0;  // nothing is an inlier (bits compare fails)
+  if (max_residual == INFINITY) return DBL_MAX;
+  double r = sqrt(max_residual);
+  while (r * r > max_residual) r = nextafter(r, 0.0);
+  for (;;) {
+    const double up = nextafter(r, INFINITY);
+    if (up * up <= max_residual) r = up; else break;
+  }
+  return r;
 }
 
 void launch_score(const double* corr6, int n, const double* models, const int* offsets,
                   int num_trials, int num_segs, int seg_len, double max_residual, int kcap,
-                  unsigned* part_cnt, double* part_sum, unsigned* cnt_out, double* sum_out,
-                  cudaStream_t s) {
+                  unsigned* part_cnt, unsigned* cnt_out, cudaStream_t s) {
   if (num_trials <= 0) return;
+  const double r_max = inlier_abs_threshold(max_residual);
   dim3 grid((kcap + kScoreThreads - 1) / kScoreThreads, num_segs);
   score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
-                                              max_residual, kcap, part_cnt, part_sum);
-  reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, part_sum, num_segs, kcap,
-                                                         offsets, num_trials, cnt_out, sum_out);
+                                              r_max, kcap, part_cnt);
+  reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
+                                                         num_trials, cnt_out);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -333,31 +345,65 @@ __global__ void exact_residual_kernel(const double* __restrict__ corr6, int n,
   }
 }
 
-// One warp per model: index-order sum of the inlier residuals (support_measurement.cc:42-47).
-__global__ void seq_support_kernel(const double* __restrict__ rbuf, int n, int num_e,
-                                   double max_residual, unsigned long long* __restrict__ ecnt,
-                                   double* __restrict__ esum) {
-  const int e = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+// One block per model: index-order sum of the inlier residuals (support_measurement.cc:42-47).
+// 256 threads compact the inlier residuals of a 2048-wide chunk into shared memory in index
+// order (ballot + popc prefix), then one thread adds them sequentially — the additions must
+// round exactly like the reference's serial loop, so only the compaction is parallel.
+constexpr int kSeqThreads = 256;
+constexpr int kSeqChunk = 2048;
+__global__ void __launch_bounds__(kSeqThreads)
+seq_support_kernel(const double* __restrict__ rbuf, int n, int num_e, double max_residual,
+                   unsigned long long* __restrict__ ecnt, double* __restrict__ esum) {
+  __shared__ double buf[kSeqChunk];
+  __shared__ int warp_cnt[kSeqThreads / 32];
+  const int e = blockIdx.x;
   if (e >= num_e) return;
-  const int lane = threadIdx.x & 31;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const double* r = rbuf + (size_t)e * n;
   unsigned long long cnt = 0;
   double sum = 0.0;
-  double next = (lane < n) ? r[lane] : DBL_MAX;
-  for (int base = 0; base < n; base += 32) {
-    const double v = next;
-    const int ni = base + 32 + lane;
-    next = (ni < n) ? r[ni] : DBL_MAX;
-    const bool inl = (base + lane < n) && (v <= max_residual);
-    unsigned m = __ballot_sync(0xffffffffu, inl);
-    cnt += __popc(m);
-    while (m) {
-      const int b = __ffs(m) - 1;
-      m &= m - 1;
-      sum += __shfl_sync(0xffffffffu, v, b);
+  for (int base = 0; base < n; base += kSeqChunk) {
+    double v[8];
+    unsigned bal[8];
+    int wtotal = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int i = base + warp * 256 + it * 32 + lane;
+      v[it] = (i < n) ? r[i] : DBL_MAX;
+      const bool inl = (i < n) && (v[it] <= max_residual);
+      bal[it] = __ballot_sync(0xffffffffu, inl);
+      wtotal += __popc(bal[it]);
     }
+    if (lane == 0) warp_cnt[warp] = wtotal;
+    __syncthreads();
+    int off = 0, total = 0;
+#pragma unroll
+    for (int w = 0; w < kSeqThreads / 32; ++w) {
+      const int c = warp_cnt[w];
+      if (w < warp) off += c;
+      total += c;
+    }
+    const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      if ((bal[it] >> lane) & 1u) buf[off + __popc(bal[it] & lt)] = v[it];
+      off += __popc(bal[it]);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      int i = 0;
+      for (; i + 8 <= total; i += 8) {
+        const double a0 = buf[i], a1 = buf[i + 1], a2 = buf[i + 2], a3 = buf[i + 3];
+        const double a4 = buf[i + 4], a5 = buf[i + 5], a6 = buf[i + 6], a7 = buf[i + 7];
+        sum += a0; sum += a1; sum += a2; sum += a3;
+        sum += a4; sum += a5; sum += a6; sum += a7;
+      }
+      for (; i < total; ++i) sum += buf[i];
+      cnt += (unsigned long long)total;
+    }
+    __syncthreads();
   }
-  if (lane == 0) {
+  if (tid == 0) {
     ecnt[e] = cnt;
     esum[e] = sum;
   }
@@ -370,9 +416,7 @@ void launch_exact(const double* corr6, int n, const double* emodels, int num_e,
   exact_residual_kernel<<<(n + 255) / 256, 256, 0, s>>>(corr6, n, emodels, num_e, max_residual,
                                                         rbuf, mask);
   if (ecnt != nullptr) {
-    const int warps_per_block = 4;
-    seq_support_kernel<<<(num_e + warps_per_block - 1) / warps_per_block, warps_per_block * 32,
-                         0, s>>>(rbuf, n, num_e, max_residual, ecnt, esum);
+    seq_support_kernel<<<num_e, kSeqThreads, 0, s>>>(rbuf, n, num_e, max_residual, ecnt, esum);
   }
 }
 
