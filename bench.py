@@ -301,7 +301,116 @@ def run_b200(args):
             "sample": f"2000 of {N_HYP} hypotheses ({scored} models) on all {N_CORR} "
                       f"correspondences, {dt:.1f} s; oracle restatement of the reference's serial "
                       "RANSAC loop (the reference needs Eigen/Ceres, absent here)"}
+    if not args.no_ba and world == 1:
+        out["ba"] = run_ba_b200(args, ctx, world, rank, dist)
     print(json.dumps(out), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# Secondary metric: line-reprojection bundle adjustment, BASELINE.json configs[3]
+# (500 cameras / 200k points / 2M observations), LM iterations per second.
+# ------------------------------------------------------------------------------------------------
+BA_CAMS, BA_POINTS, BA_OBS_PER_POINT, BA_ITERS = 500, 200000, 10, 10
+BA_BYTES_PER_OBS = 216.0  # SURVEY.md §8(d), materialised Jacobian: 56 B read + 160 B written
+
+
+def make_ba_problem():
+    from privacy_preserving_sfm_b200 import synthetic as S
+    sc = S.make_ba_scene(num_cams=BA_CAMS, num_points=BA_POINTS, obs_per_point=BA_OBS_PER_POINT,
+                         seed=S.SCENE_SEED)
+    flags = np.zeros(BA_CAMS, np.uint8)
+    flags[0] = 1   # image 0: constant pose; image 1: constant tvec[0]
+    flags[1] = 2   # (src/sfm/incremental_mapper.cc:907-926)
+    return sc, flags
+
+
+def run_ba_b200(args, ctx, world, rank, dist):
+    from privacy_preserving_sfm_b200 import bundle_adjustment as ba
+    sc, flags = make_ba_problem()
+    arr_args = (sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                sc["obs_line"], [1], [sc["cam_params"]])
+    # global-BA options of the reference (src/controllers/incremental_mapper.cc:221-243) with a
+    # fixed number of LM iterations so that every step does the same work
+    opts = ba.default_solver_options(loss_type=0, max_num_iterations=BA_ITERS,
+                                     gradient_tolerance=0.0, function_tolerance=0.0,
+                                     parameter_tolerance=0.0)
+    arrays = ba.BaArrays(*arr_args, pose_flags=flags)
+    prob = ba.ResidentProblem(ctx, arrays, opts)
+    for _ in range(max(1, args.warmup)):
+        prob.reset()
+        prob.run()
+    times, iters, jac_s, jac_n, launches = [], 0, 0.0, 0, 0
+    summ = None
+    for _ in range(args.steps):
+        prob.reset()
+        ctx.bench_l2_flush()
+        t0 = time.perf_counter()
+        ok, summ = prob.run()
+        times.append(time.perf_counter() - t0)
+        iters += summ.num_iterations
+        jac_s += summ.jacobian_time_s
+        jac_n += summ.jacobian_launches
+        launches += summ.kernel_launches
+    prob.free()
+    total = float(sum(times))
+    value = iters / total
+    # end to end: host arrays in, host arrays out (assembly + H2D + solve + D2H)
+    e2e_t, e2e_it = [], 0
+    nbytes_in = sum(a.nbytes for a in (arrays.qvecs, arrays.tvecs, arrays.points, arrays.obs_image,
+                                       arrays.obs_point, arrays.obs_line))
+    nbytes_out = arrays.qvecs.nbytes + arrays.tvecs.nbytes + arrays.points.nbytes
+    for i in range(max(2, min(args.steps, 3)) + 1):
+        a2 = ba.BaArrays(*arr_args, pose_flags=flags)
+        t0 = time.perf_counter()
+        ok, s2 = ba.solve_arrays(ctx, a2, opts)
+        dt = time.perf_counter() - t0
+        if i > 0:   # first call is warm-up
+            e2e_t.append(dt)
+            e2e_it += s2.num_iterations
+    hbm_peak, peak_kind = peaks()
+    K = len(sc["obs_cam"])
+    jac_avg_s = jac_s / max(1, jac_n)
+    achieved = BA_BYTES_PER_OBS * K / jac_avg_s / 1e9
+    out = {
+        "metric": "ba_lm_iterations_per_sec", "value": value, "unit": "LM iterations/s",
+        "ms_per_iteration": 1e3 * total / max(1, iters), "steps": args.steps,
+        "iterations_per_step": iters / max(1, args.steps), "dtype": "f64",
+        "config": {"workload": "line-reprojection BA, 500 cams / 200k points / 2M observations "
+                               "(BASELINE.json configs[3]), PINHOLE, TRIVIAL loss, gauge: cam 0 "
+                               "constant, cam 1 tvec[0] constant", "cameras": BA_CAMS,
+                   "points": BA_POINTS, "observations": int(K),
+                   "lm_iterations_per_solve": BA_ITERS, "l2": "flushed between timed solves"},
+        "e2e": {"value": e2e_it / sum(e2e_t), "unit": "LM iterations/s",
+                "ms_per_solve": 1e3 * float(np.mean(e2e_t)), "h2d_bytes_per_step": int(nbytes_in),
+                "d2h_bytes_per_step": int(nbytes_out)},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "ba_linearize_kernel<true> (Jacobian build)", "bound": "hbm",
+                     "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                     "frac": achieved / hbm_peak, "peak_source": peak_kind,
+                     "bytes_per_obs": BA_BYTES_PER_OBS, "avg_launch_ms": 1e3 * jac_avg_s,
+                     "traffic": None},
+        "result": {"initial_cost": summ.initial_cost, "final_cost": summ.final_cost,
+                   "successful_steps": summ.num_successful_steps,
+                   "unsuccessful_steps": summ.num_unsuccessful_steps},
+    }
+    if not args.no_cpu_baseline and world == 1:
+        out["cpu_baseline"] = ba_cpu_reference_run(sc, flags, 2)
+    return out
+
+
+def ba_cpu_reference_run(sc, flags, iters):
+    """Oracle restatement of the reference's Ceres path on all host threads (the reference uses
+    hardware_concurrency when residuals >= 50000, src/optim/bundle_adjustment.cc:288-301)."""
+    import oracle as O
+    a = O.BaArrays(sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                   sc["obs_line"], [1], [sc["cam_params"]], pose_flags=flags)
+    t0 = time.perf_counter()
+    ok, s = O.ba_solve(a, O.ba_default_options(max_num_iterations=iters, num_threads=-1))
+    dt = time.perf_counter() - t0
+    n = s.num_successful_steps + s.num_unsuccessful_steps
+    return {"value": n / dt, "unit": "LM iterations/s", "cores": os.cpu_count(), "kind": "port",
+            "sample": f"{n} LM iterations of the same 500-camera problem, {dt:.1f} s; oracle "
+                      "restatement (dense Schur + Cholesky) of the reference's Ceres path"}
 
 
 def main():

@@ -139,6 +139,119 @@ int ppsfm_ransac_p6l_resident(ppsfm_ctx* ctx, const ppsfm_corr* corr,
                               uint8_t* inlier_mask);
 void ppsfm_get_ransac_timing(const ppsfm_ctx* ctx, ppsfm_ransac_timing* out);
 
+/* =============================================================================================
+ * Line-reprojection bundle adjustment
+ * ============================================================================================= */
+#define PPSFM_BA_MAX_TRACE 128
+
+typedef struct ppsfm_ba ppsfm_ba; /* a BA problem resident in HBM */
+
+/* The problem BundleAdjuster::SetUp builds from a Reconstruction + BundleAdjustmentConfig
+ * (src/optim/bundle_adjustment.cc:326-542), flattened to arrays.  qvecs / tvecs / points are
+ * updated IN PLACE like Image::Qvec/Tvec and Point3D::XYZ (:357-359).
+ *   pose_flags[i]: bit0 = constant pose (config.HasConstantPose or !refine_extrinsics -> the
+ *                  BundleAdjustmentConstantPoseLineCostFunction branch :383-398, and images added
+ *                  by AddPointToProblem :450-487); bit1..3 = tvec[0..2] constant
+ *                  (config.ConstantTvec -> SubsetParameterization :425-432)
+ *   point_const[p]: ParameterizePoints :530-542 (partial tracks, ConstantPoints)
+ *   camera_model:  COLMAP ids 0 SIMPLE_PINHOLE, 1 PINHOLE, 2 SIMPLE_RADIAL, 3 RADIAL, 4 OPENCV
+ *                  (src/base/camera_models.h:189-248); intrinsics are constant (refine_* = false,
+ *                  the defaults of src/optim/bundle_adjustment.h:57-63). */
+typedef struct {
+  int32_t num_images;
+  double* qvecs;               /* num_images x 4 (w,x,y,z) */
+  double* tvecs;               /* num_images x 3 */
+  const uint8_t* pose_flags;   /* may be NULL (= all variable) */
+  const int32_t* image_camera; /* index into cameras */
+  int32_t num_cameras;
+  const int32_t* camera_model;
+  const double* camera_params; /* num_cameras x 12, zero padded */
+  int32_t num_points;
+  double* points;              /* num_points x 3 */
+  const uint8_t* point_const;  /* may be NULL */
+  int64_t num_obs;
+  const int32_t* obs_image;
+  const int32_t* obs_point;
+  const double* obs_line;      /* num_obs x 3, ||(a,b)|| = 1 */
+} ppsfm_ba_problem;
+
+/* BundleAdjustmentOptions (src/optim/bundle_adjustment.h:49-100) + the ceres::Solver::Options
+ * fields the reference sets (src/controllers/incremental_mapper.cc:196-243). */
+typedef struct {
+  int32_t loss_type; /* LossFunctionType: 0 TRIVIAL, 1 SOFT_L1, 2 CAUCHY */
+  double loss_scale;
+  int32_t max_num_iterations;
+  double function_tolerance;
+  double gradient_tolerance;
+  double parameter_tolerance;
+  int32_t max_num_consecutive_invalid_steps;
+  double initial_trust_region_radius;
+  double max_trust_region_radius;
+  double min_trust_region_radius;
+  double min_relative_decrease;
+  double min_lm_diagonal;
+  double max_lm_diagonal;
+  int32_t jacobi_scaling;
+  int32_t num_threads; /* ignored (kept for layout parity with the CPU oracle) */
+} ppsfm_ba_options;
+
+/* The fields of ceres::Solver::Summary the reference reads / prints
+ * (src/optim/bundle_adjustment.cc:544-598, src/sfm/incremental_mapper.cc:860-861). */
+typedef struct {
+  double initial_cost;
+  double final_cost;
+  int32_t num_successful_steps;
+  int32_t num_unsuccessful_steps;
+  int32_t termination_type; /* 0 CONVERGENCE, 1 NO_CONVERGENCE, 2 FAILURE */
+  int64_t num_residuals;
+  int64_t num_residuals_reduced;
+  int32_t num_effective_parameters_reduced;
+  double total_time_s;
+  double jacobian_time_s;       /* device time of the Jacobian-build kernel (CUDA events) */
+  double linear_solver_time_s;  /* host wall time of reduced system + Cholesky + back-subst. */
+  double final_gradient_max_norm;
+  int32_t trace_len;
+  double trace_cost[PPSFM_BA_MAX_TRACE];
+  double trace_radius[PPSFM_BA_MAX_TRACE];
+  int32_t trace_accepted[PPSFM_BA_MAX_TRACE];
+  int32_t jacobian_launches;
+  int64_t kernel_launches;
+} ppsfm_ba_summary;
+
+void ppsfm_ba_options_default(ppsfm_ba_options* opt);
+
+/* BundleAdjuster::Solve (src/optim/bundle_adjustment.cc:260-320).  Returns PPSFM_OK (true) or
+ * PPSFM_NO_SOLUTION (zero residuals, :269-271). */
+int ppsfm_ba_solve(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                   const ppsfm_ba_options* options, ppsfm_ba_summary* summary);
+
+/* Resident variant: upload once, run (repeatedly, after ppsfm_ba_reset), download. */
+int ppsfm_ba_create(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                    const ppsfm_ba_options* options, ppsfm_ba** out);
+int ppsfm_ba_run(ppsfm_ba* ba, ppsfm_ba_summary* summary);
+int ppsfm_ba_reset(ppsfm_ba* ba);
+int ppsfm_ba_download(ppsfm_ba* ba, const ppsfm_ba_problem* problem);
+void ppsfm_ba_free(ppsfm_ba* ba);
+
+/* RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213, options pose.h:84-108) with constant
+ * intrinsics.  Returns PPSFM_OK when summary.IsSolutionUsable(), else PPSFM_NO_SOLUTION. */
+int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
+                                          const double* lines, const double* points, size_t n,
+                                          int camera_model, const double* camera_params,
+                                          double gradient_tolerance, int max_num_iterations,
+                                          double loss_function_scale, double* qvec, double* tvec,
+                                          ppsfm_ba_summary* summary);
+
+/* Test hooks (parity tests only).
+ * ppsfm_ba_linearize: per observation residual[2], tangent Jacobians jac_cam[2x6] (rotation via
+ * ceres::QuaternionParameterization | translation) and jac_point[2x3], loss-corrected, unscaled —
+ * the counterpart of BundleAdjustmentLineCostFunction + AutoDiff (src/base/cost_functions.h:46-106).
+ * ppsfm_dense_cholesky_solve: the reduced-camera-system solver on a host matrix. */
+int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                       const ppsfm_ba_options* options, double* residuals, double* jac_cam,
+                       double* jac_point, double* cost);
+int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const double* b, double* x);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

@@ -212,3 +212,180 @@ def ransac_p6l_fixed_trials(lines, aligned, points, max_error, num_trials):
     scored = lib().orc_ransac_p6l_fixed_trials(lp, ap, pp, lines.shape[0], max_error, num_trials,
                                                C.byref(rep))
     return int(scored), rep
+
+
+# ---------------------------------------------------------------------------------------------
+# Bundle adjustment oracle (ba_oracle.h)
+# ---------------------------------------------------------------------------------------------
+_i32p = C.POINTER(C.c_int32)
+BA_MAX_TRACE = 128
+
+
+class BaProblem(C.Structure):
+    _fields_ = [("num_images", C.c_int32), ("qvecs", _dp), ("tvecs", _dp), ("pose_flags", _u8p),
+                ("image_camera", _i32p), ("num_cameras", C.c_int32), ("camera_model", _i32p),
+                ("camera_params", _dp), ("num_points", C.c_int32), ("points", _dp),
+                ("point_const", _u8p), ("num_obs", C.c_int64), ("obs_image", _i32p),
+                ("obs_point", _i32p), ("obs_line", _dp)]
+
+
+class BaOptions(C.Structure):
+    _fields_ = [("loss_type", C.c_int32), ("loss_scale", C.c_double),
+                ("max_num_iterations", C.c_int32), ("function_tolerance", C.c_double),
+                ("gradient_tolerance", C.c_double), ("parameter_tolerance", C.c_double),
+                ("max_num_consecutive_invalid_steps", C.c_int32),
+                ("initial_trust_region_radius", C.c_double),
+                ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
+                ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
+                ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
+                ("num_threads", C.c_int32)]
+
+
+class BaSummary(C.Structure):
+    _fields_ = [("initial_cost", C.c_double), ("final_cost", C.c_double),
+                ("num_successful_steps", C.c_int32), ("num_unsuccessful_steps", C.c_int32),
+                ("termination_type", C.c_int32), ("num_residuals", C.c_int64),
+                ("num_residuals_reduced", C.c_int64),
+                ("num_effective_parameters_reduced", C.c_int32), ("total_time_s", C.c_double),
+                ("jacobian_time_s", C.c_double), ("linear_solver_time_s", C.c_double),
+                ("final_gradient_max_norm", C.c_double), ("trace_len", C.c_int32),
+                ("trace_cost", C.c_double * BA_MAX_TRACE),
+                ("trace_radius", C.c_double * BA_MAX_TRACE),
+                ("trace_accepted", C.c_int32 * BA_MAX_TRACE)]
+
+
+_ba_ready = False
+
+
+def _ba_lib():
+    global _ba_ready
+    L = lib()
+    if not _ba_ready:
+        L.orc_ba_options_default.argtypes = [C.POINTER(BaOptions)]
+        L.orc_ba_solve.argtypes = [C.POINTER(BaProblem), C.POINTER(BaOptions),
+                                   C.POINTER(BaSummary)]
+        L.orc_ba_solve.restype = C.c_int
+        L.orc_line_cost.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_line_cost_tangent.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_ba_cost.argtypes = [C.POINTER(BaProblem), C.POINTER(BaOptions)]
+        L.orc_ba_cost.restype = C.c_double
+        L.orc_quaternion_plus.argtypes = [_dp, _dp, _dp]
+        L.orc_refine_absolute_pose.argtypes = [_dp, _dp, _u8p, C.c_size_t, C.c_int, _dp,
+                                               C.c_double, C.c_int, C.c_double, _dp, _dp,
+                                               C.POINTER(BaSummary)]
+        L.orc_refine_absolute_pose.restype = C.c_int
+        _ba_ready = True
+    return L
+
+
+def ba_default_options(**kw):
+    o = BaOptions()
+    _ba_lib().orc_ba_options_default(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+class BaArrays:
+    """Owns contiguous numpy buffers of a BA problem and the ctypes struct pointing at them."""
+
+    def __init__(self, qvecs, tvecs, points, obs_image, obs_point, obs_line, camera_model,
+                 camera_params, image_camera=None, pose_flags=None, point_const=None,
+                 struct_cls=None):
+        self.qvecs = np.ascontiguousarray(qvecs, dtype=np.float64).copy()
+        self.tvecs = np.ascontiguousarray(tvecs, dtype=np.float64).copy()
+        self.points = np.ascontiguousarray(points, dtype=np.float64).copy()
+        ni, npnt = self.qvecs.shape[0], self.points.shape[0]
+        self.obs_image = np.ascontiguousarray(obs_image, dtype=np.int32)
+        self.obs_point = np.ascontiguousarray(obs_point, dtype=np.int32)
+        self.obs_line = np.ascontiguousarray(obs_line, dtype=np.float64)
+        self.camera_model = np.ascontiguousarray(np.atleast_1d(camera_model), dtype=np.int32)
+        cp = np.atleast_2d(np.asarray(camera_params, dtype=np.float64))
+        self.camera_params = np.zeros((cp.shape[0], 12))
+        self.camera_params[:, :cp.shape[1]] = cp
+        self.image_camera = np.ascontiguousarray(
+            image_camera if image_camera is not None else np.zeros(ni), dtype=np.int32)
+        self.pose_flags = np.ascontiguousarray(
+            pose_flags if pose_flags is not None else np.zeros(ni), dtype=np.uint8)
+        self.point_const = np.ascontiguousarray(
+            point_const if point_const is not None else np.zeros(npnt), dtype=np.uint8)
+        cls = struct_cls or BaProblem
+        p = cls()
+        p.num_images = ni
+        p.qvecs = self.qvecs.ctypes.data_as(_dp)
+        p.tvecs = self.tvecs.ctypes.data_as(_dp)
+        p.pose_flags = self.pose_flags.ctypes.data_as(_u8p)
+        p.image_camera = self.image_camera.ctypes.data_as(_i32p)
+        p.num_cameras = self.camera_model.shape[0]
+        p.camera_model = self.camera_model.ctypes.data_as(_i32p)
+        p.camera_params = self.camera_params.ctypes.data_as(_dp)
+        p.num_points = npnt
+        p.points = self.points.ctypes.data_as(_dp)
+        p.point_const = self.point_const.ctypes.data_as(_u8p)
+        p.num_obs = self.obs_image.shape[0]
+        p.obs_image = self.obs_image.ctypes.data_as(_i32p)
+        p.obs_point = self.obs_point.ctypes.data_as(_i32p)
+        p.obs_line = self.obs_line.ctypes.data_as(_dp)
+        self.struct = p
+
+
+def ba_solve(arrays, options):
+    s = BaSummary()
+    ok = _ba_lib().orc_ba_solve(C.byref(arrays.struct), C.byref(options), C.byref(s))
+    return bool(ok), s
+
+
+def ba_cost(arrays, options):
+    return float(_ba_lib().orc_ba_cost(C.byref(arrays.struct), C.byref(options)))
+
+
+def line_cost(model, cam_params, line, q, t, X):
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r, jq, jt, jx = np.zeros(2), np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 3))
+    _ba_lib().orc_line_cost(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                            r.ctypes.data_as(_dp), jq.ctypes.data_as(_dp),
+                            jt.ctypes.data_as(_dp), jx.ctypes.data_as(_dp))
+    return r, jq, jt, jx
+
+
+def line_cost_tangent(model, cam_params, line, q, t, X):
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r, jc, jx = np.zeros(2), np.zeros((2, 6)), np.zeros((2, 3))
+    _ba_lib().orc_line_cost_tangent(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                                    r.ctypes.data_as(_dp), jc.ctypes.data_as(_dp),
+                                    jx.ctypes.data_as(_dp))
+    return r, jc, jx
+
+
+def quaternion_plus(q, delta):
+    q, qp = _d(q)
+    delta, dp_ = _d(delta)
+    out = np.zeros(4)
+    _ba_lib().orc_quaternion_plus(qp, dp_, out.ctypes.data_as(_dp))
+    return out
+
+
+def refine_absolute_pose(lines, points, mask, model, cam_params, qvec, tvec,
+                         gradient_tolerance=1.0, max_num_iterations=100, loss_scale=1.0):
+    lines, lp = _d(lines)
+    points, pp = _d(points)
+    mask, mp = _u8(mask)
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    q = np.array(qvec, dtype=np.float64)
+    t = np.array(tvec, dtype=np.float64)
+    s = BaSummary()
+    ok = _ba_lib().orc_refine_absolute_pose(
+        lp, pp, mp, lines.shape[0], model, cam.ctypes.data_as(_dp), gradient_tolerance,
+        max_num_iterations, loss_scale, q.ctypes.data_as(_dp), t.ctypes.data_as(_dp), C.byref(s))
+    return bool(ok), q, t, s

@@ -1,4 +1,762 @@
-// ba_host.cu — line-reprojection bundle adjustment (host side). Filled in below.
-#include "common.h"
+// ba_host.cu — host side of the line-reprojection bundle adjustment: problem assembly on the
+// SoA boundary, the trust-region Levenberg-Marquardt loop and the C-ABI entry points.
+//
+// Replaces BundleAdjuster::Solve (src/optim/bundle_adjustment.cc:260-320) incl. the part the
+// reference delegates to ceres::Solve (:306), and RefineAbsolutePoseFromLines
+// (src/estimators/pose.cc:96-213).  The minimiser follows Ceres' documented trust-region LM:
+// Jacobi column scaling from the initial Jacobian, LM diagonal clamp(diag(J^T J)) / radius,
+// Schur elimination of the points, step-quality ratio, radius update
+// (SURVEY.md Appendix A); the control flow runs on the host, every array stays in HBM.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <numeric>
+#include <vector>
 
-extern "C" void ppsfm_ba_state_free(ppsfm_ctx* ctx) { (void)ctx; }
+#include "ba_kernels.h"
+#include "common.h"
+#include "dense_chol.h"
+
+namespace ppsfm {
+
+struct BaState {
+  ppsfm_ctx* ctx = nullptr;
+  BaDev d;
+  ppsfm_ba_options opt{};
+  std::vector<void*> allocs;
+  // host copies needed to write results back in the caller's order
+  int C = 0, P = 0;
+  int64_t num_obs_in = 0;
+  double *q0 = nullptr, *t0 = nullptr, *X0 = nullptr;  // initial state (for reset)
+  PinBuf h_scalars;
+  int64_t launches = 0;
+  double lin_ms = 0, lin_launches = 0;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // multi-GPU
+  int rank = 0, world = 1;
+  void* comm = nullptr;  // ncclComm_t
+};
+
+namespace {
+
+template <typename T>
+cudaError_t DevAlloc(BaState* st, T** p, size_t count) {
+  void* v = nullptr;
+  cudaError_t e = cudaMalloc(&v, std::max<size_t>(1, count) * sizeof(T));
+  if (e == cudaSuccess) {
+    st->allocs.push_back(v);
+    *p = static_cast<T*>(v);
+  }
+  return e;
+}
+
+template <typename T>
+cudaError_t Upload(BaState* st, T** p, const std::vector<T>& h) {
+  cudaError_t e = DevAlloc(st, p, h.size());
+  if (e != cudaSuccess) return e;
+  if (!h.empty())
+    e = cudaMemcpyAsync(*p, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice,
+                        st->ctx->stream);
+  return e;
+}
+
+double Secs(std::chrono::steady_clock::time_point a) {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+}
+
+}  // namespace
+
+void BaFree(BaState* st) {
+  if (!st) return;
+  for (void* p : st->allocs) cudaFree(p);
+  st->h_scalars.release();
+  if (st->ev0) cudaEventDestroy(st->ev0);
+  if (st->ev1) cudaEventDestroy(st->ev1);
+  delete st;
+}
+
+// Assembly: what BundleAdjuster::SetUp / AddImageToProblem / AddPointToProblem /
+// ParameterizeCameras / ParameterizePoints (bundle_adjustment.cc:326-542) do with a ceres::Problem,
+// on the SoA boundary: drop residual blocks whose parameter blocks are all constant, number the
+// variable camera blocks, record the per-dimension tangent masks (constant pose, constant
+// tvec components = SubsetParameterization), order observations point-major and build the
+// camera-major index.
+int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options* opt,
+             int rank, int world, BaState** out) {
+  if (!ctx || !pb || !opt || !out) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
+  const int C = pb->num_images, P = pb->num_points;
+  const int64_t O = pb->num_obs;
+  if (C < 0 || P < 0 || O < 0) return fail(ctx, PPSFM_ERR_INVALID, "negative size");
+  for (int64_t o = 0; o < O; ++o) {
+    if (pb->obs_image[o] < 0 || pb->obs_image[o] >= C || pb->obs_point[o] < 0 ||
+        pb->obs_point[o] >= P)
+      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld references a missing image/point",
+                  (long long)o);
+    const double* l = pb->obs_line + 3 * o;
+    // CHECK_NEAR(line.head<2>().norm(), 1.0, 1e-6)  (bundle_adjustment.cc:374)
+    if (std::fabs(std::sqrt(l[0] * l[0] + l[1] * l[1]) - 1.0) > 1e-6)
+      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld: line normal is not unit length",
+                  (long long)o);
+  }
+  for (int i = 0; i < C; ++i) {
+    const int cam = pb->image_camera[i];
+    if (cam < 0 || cam >= pb->num_cameras)
+      return fail(ctx, PPSFM_ERR_INVALID, "image %d references a missing camera", i);
+    const int m = pb->camera_model[cam];
+    if (m < 0 || m > 4)
+      return fail(ctx, PPSFM_ERR_INVALID,
+                  "camera model %d not supported (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, "
+                  "RADIAL, OPENCV are)", m);
+  }
+  BaState* st = new BaState();
+  st->ctx = ctx;
+  st->opt = *opt;
+  st->C = C;
+  st->P = P;
+  st->num_obs_in = O;
+  st->rank = rank;
+  st->world = world;
+  cudaStream_t s = ctx->stream;
+
+  std::vector<uint8_t> pt_var(P, 1), cam_const(C, 0);
+  if (pb->point_const) for (int i = 0; i < P; ++i) pt_var[i] = pb->point_const[i] ? 0 : 1;
+  if (pb->pose_flags) for (int i = 0; i < C; ++i) cam_const[i] = pb->pose_flags[i] & 1;
+  // this rank's share: points are dealt round-robin in blocks (all observations of a point stay
+  // together); cameras are replicated
+  auto mine = [&](int p) { return world == 1 || (p % world) == rank; };
+
+  std::vector<int64_t> pt_start(P + 1, 0);
+  std::vector<uint8_t> cam_used(C, 0);
+  for (int64_t o = 0; o < O; ++o) {
+    const int ci = pb->obs_image[o], pi = pb->obs_point[o];
+    if (cam_const[ci] && !pt_var[pi]) continue;
+    cam_used[ci] = 1;  // global property: identical on every rank
+    if (!mine(pi)) continue;
+    pt_start[pi + 1]++;
+  }
+  for (int i = 0; i < P; ++i) pt_start[i + 1] += pt_start[i];
+  const int64_t K = pt_start[P];
+  std::vector<int> obs_cam(K), obs_pt(K);
+  std::vector<double> obs_line(3 * (size_t)K);
+  {
+    std::vector<int64_t> fill(pt_start.begin(), pt_start.end() - 1);
+    for (int64_t o = 0; o < O; ++o) {
+      const int ci = pb->obs_image[o], pi = pb->obs_point[o];
+      if ((cam_const[ci] && !pt_var[pi]) || !mine(pi)) continue;
+      const int64_t k = fill[pi]++;
+      obs_cam[k] = ci;
+      obs_pt[k] = pi;
+      obs_line[k] = pb->obs_line[3 * o];
+      obs_line[K + k] = pb->obs_line[3 * o + 1];
+      obs_line[2 * K + k] = pb->obs_line[3 * o + 2];
+    }
+  }
+  std::vector<int> cam_block(C, -1), block_img;
+  std::vector<uint8_t> cam_mask(C, 0);
+  std::vector<double> q(pb->qvecs, pb->qvecs + 4 * (size_t)C), t(pb->tvecs, pb->tvecs + 3 * (size_t)C);
+  for (int i = 0; i < C; ++i) {
+    if (cam_const[i] || !cam_used[i]) continue;
+    cam_block[i] = (int)block_img.size();
+    block_img.push_back(i);
+    const uint8_t f = pb->pose_flags ? pb->pose_flags[i] : 0;
+    uint8_t m = 0x07;
+    for (int k = 0; k < 3; ++k)
+      if (!(f & (2 << k))) m |= (uint8_t)(8 << k);
+    cam_mask[i] = m;
+    // image.NormalizeQvec()  (bundle_adjustment.cc:355)
+    double nrm = 0;
+    for (int k = 0; k < 4; ++k) nrm += q[4 * i + k] * q[4 * i + k];
+    nrm = std::sqrt(nrm);
+    if (nrm > 0) for (int k = 0; k < 4; ++k) q[4 * i + k] /= nrm;
+  }
+  const int NB = (int)block_img.size();
+  // a point takes part on this rank only if it has kept observations here
+  for (int i = 0; i < P; ++i)
+    if (pt_start[i + 1] == pt_start[i]) pt_var[i] = 0;
+  // camera-major index
+  std::vector<int64_t> cam_start(NB + 1, 0);
+  for (int64_t k = 0; k < K; ++k) {
+    const int b = cam_block[obs_cam[k]];
+    if (b >= 0) cam_start[b + 1]++;
+  }
+  for (int b = 0; b < NB; ++b) cam_start[b + 1] += cam_start[b];
+  std::vector<int> cam_obs(cam_start[NB]);
+  {
+    std::vector<int64_t> fill(cam_start.begin(), cam_start.end() - 1);
+    for (int64_t k = 0; k < K; ++k) {
+      const int b = cam_block[obs_cam[k]];
+      if (b >= 0) cam_obs[fill[b]++] = (int)k;
+    }
+  }
+  std::vector<int> img_model(C);
+  std::vector<double> img_params(12 * (size_t)C, 0.0);
+  for (int i = 0; i < C; ++i) {
+    const int cam = pb->image_camera[i];
+    img_model[i] = pb->camera_model[cam];
+    std::memcpy(&img_params[12 * (size_t)i], pb->camera_params + 12 * (size_t)cam, 12 * sizeof(double));
+  }
+
+  BaDev& d = st->d;
+  d.C = C; d.P = P; d.NB = NB; d.K = K; d.n = 6 * NB; d.ld = chol_ld(6 * NB);
+  std::vector<double> X(pb->points, pb->points + 3 * (size_t)P);
+  cudaError_t e = cudaSuccess;
+#define BA_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+  BA_TRY(Upload(st, &d.obs_cam, obs_cam));
+  BA_TRY(Upload(st, &d.obs_pt, obs_pt));
+  BA_TRY(Upload(st, &d.obs_line, obs_line));
+  BA_TRY(Upload(st, &d.pt_start, pt_start));
+  BA_TRY(Upload(st, &d.cam_obs, cam_obs));
+  BA_TRY(Upload(st, &d.cam_start, cam_start));
+  BA_TRY(Upload(st, &d.block_img, block_img));
+  BA_TRY(Upload(st, &d.cam_block, cam_block));
+  BA_TRY(Upload(st, &d.cam_mask, cam_mask));
+  BA_TRY(Upload(st, &d.img_model, img_model));
+  BA_TRY(Upload(st, &d.img_params, img_params));
+  BA_TRY(Upload(st, &d.pt_var, pt_var));
+  BA_TRY(Upload(st, &d.q, q));
+  BA_TRY(Upload(st, &d.t, t));
+  BA_TRY(Upload(st, &d.X, X));
+  BA_TRY(Upload(st, &st->q0, q));
+  BA_TRY(Upload(st, &st->t0, t));
+  BA_TRY(Upload(st, &st->X0, X));
+  BA_TRY(DevAlloc(st, &d.qn, 4 * (size_t)C));
+  BA_TRY(DevAlloc(st, &d.tn, 3 * (size_t)C));
+  BA_TRY(DevAlloc(st, &d.Xn, 3 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.r, 2 * (size_t)K));
+  BA_TRY(DevAlloc(st, &d.Jc, 12 * (size_t)K));
+  BA_TRY(DevAlloc(st, &d.Jp, 6 * (size_t)K));
+  BA_TRY(DevAlloc(st, &d.cam_scale, 6 * (size_t)NB));
+  BA_TRY(DevAlloc(st, &d.pt_scale, 3 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.U, 36 * (size_t)NB));
+  BA_TRY(DevAlloc(st, &d.gc, 6 * (size_t)NB));
+  BA_TRY(DevAlloc(st, &d.V, 6 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.Vinv, 6 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.S, (size_t)d.ld * d.ld));
+  BA_TRY(DevAlloc(st, &d.dc, (size_t)std::max(1, d.n)));
+  BA_TRY(DevAlloc(st, &d.dp, 3 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.chol_status, 1));
+  d.num_partials = (int)std::max<int64_t>((K + 255) / 256, (P + 255) / 256) + 1;
+  BA_TRY(DevAlloc(st, &d.partials, 3 * (size_t)d.num_partials));
+  BA_TRY(DevAlloc(st, &d.scalars, kNumScalars));
+  BA_TRY(cudaMemsetAsync(d.scalars, 0, sizeof(double) * kNumScalars, s));
+  BA_TRY(st->h_scalars.reserve(sizeof(double) * kNumScalars));
+  BA_TRY(cudaEventCreate(&st->ev0));
+  BA_TRY(cudaEventCreate(&st->ev1));
+  BA_TRY(cudaStreamSynchronize(s));
+#undef BA_TRY
+  if (e != cudaSuccess) {
+    BaFree(st);
+    return fail(ctx, PPSFM_ERR_CUDA, "BA setup: %s", cudaGetErrorString(e));
+  }
+  *out = st;
+  return PPSFM_OK;
+}
+
+namespace {
+
+// Sum-reduction across ranks (NCCL all-reduce over NVLink); identity for a single GPU.
+int AllReduceSum(BaState* st, double* dev, size_t count);
+int AllReduceMax(BaState* st, double* dev, size_t count);
+
+struct Scalars {
+  double v[kNumScalars];
+};
+
+int FetchScalars(BaState* st, Scalars* out) {
+  ppsfm_ctx* ctx = st->ctx;
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(st->h_scalars.p, st->d.scalars, sizeof(double) * kNumScalars,
+                                  cudaMemcpyDeviceToHost, ctx->stream));
+  PPSFM_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  std::memcpy(out->v, st->h_scalars.p, sizeof(out->v));
+  return PPSFM_OK;
+}
+
+}  // namespace
+
+// The LM loop (mirrors ceres::internal::TrustRegionMinimizer with LevenbergMarquardtStrategy).
+int BaRun(BaState* st, ppsfm_ba_summary* sum) {
+  ppsfm_ctx* ctx = st->ctx;
+  cudaStream_t s = ctx->stream;
+  const ppsfm_ba_options& opt = st->opt;
+  BaDev& d = st->d;
+  const auto t_start = std::chrono::steady_clock::now();
+  std::memset(sum, 0, sizeof(*sum));
+  sum->num_residuals = 2 * st->num_obs_in;
+  sum->num_residuals_reduced = 2 * d.K;  // this rank's share when sharded
+  st->launches = 0;
+  st->lin_ms = 0;
+  st->lin_launches = 0;
+  if (st->num_obs_in == 0) return PPSFM_NO_SOLUTION;  // bundle_adjustment.cc:269-271
+  const BaLoss loss{opt.loss_type, opt.loss_scale};
+  Scalars sc;
+
+  auto linearize = [&](const double* q, const double* t, const double* X, bool jac) -> int {
+    if (jac) PPSFM_CUDA(ctx, cudaEventRecord(st->ev0, s));
+    st->launches += launch_linearize(d, q, t, X, jac, loss, s);
+    if (jac) {
+      PPSFM_CUDA(ctx, cudaEventRecord(st->ev1, s));
+      PPSFM_CUDA(ctx, cudaEventSynchronize(st->ev1));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, st->ev0, st->ev1);
+      st->lin_ms += ms;
+      st->lin_launches += 1;
+    }
+    return PPSFM_OK;
+  };
+  auto normal_equations = [&]() -> int {
+    st->launches += launch_normal_equations(d, s);
+    if (st->world > 1) {  // cameras are replicated: U, g_c are sums over all ranks' observations
+      int rc = AllReduceSum(st, d.U, 36 * (size_t)d.NB);
+      if (rc == PPSFM_OK) rc = AllReduceSum(st, d.gc, 6 * (size_t)d.NB);
+      if (rc != PPSFM_OK) return rc;
+    }
+    return PPSFM_OK;
+  };
+  auto cost_and_gradient = [&](double* cost, double* gmax) -> int {
+    st->launches += launch_gradient_max_norm(d, s);
+    if (st->world > 1) {
+      int rc = AllReduceSum(st, d.scalars + kCost, 1);
+      if (rc == PPSFM_OK) rc = AllReduceMax(st, d.scalars + kGradMax, 1);
+      if (rc != PPSFM_OK) return rc;
+    }
+    int rc = FetchScalars(st, &sc);
+    if (rc != PPSFM_OK) return rc;
+    *cost = sc.v[kCost];
+    *gmax = sc.v[kGradMax];
+    return PPSFM_OK;
+  };
+
+  int eff = 0;
+  {
+    std::vector<uint8_t> mask(d.C), pv(d.P);
+    PPSFM_CUDA(ctx, cudaMemcpy(mask.data(), d.cam_mask, d.C, cudaMemcpyDeviceToHost));
+    PPSFM_CUDA(ctx, cudaMemcpy(pv.data(), d.pt_var, d.P, cudaMemcpyDeviceToHost));
+    for (uint8_t m : mask) eff += __builtin_popcount(m);
+    for (uint8_t v : pv) eff += v ? 3 : 0;
+  }
+  sum->num_effective_parameters_reduced = eff;
+
+  // unit scales, first linearisation
+  {
+    std::vector<double> ones(std::max<size_t>(6 * (size_t)d.NB, 3 * (size_t)d.P), 1.0);
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(d.cam_scale, ones.data(), sizeof(double) * 6 * d.NB,
+                                    cudaMemcpyHostToDevice, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(d.pt_scale, ones.data(), sizeof(double) * 3 * d.P,
+                                    cudaMemcpyHostToDevice, s));
+    PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+  }
+  int rc = linearize(d.q, d.t, d.X, true);
+  if (rc != PPSFM_OK) return rc;
+  rc = normal_equations();
+  if (rc != PPSFM_OK) return rc;
+  if (opt.jacobi_scaling) {
+    st->launches += launch_jacobi_scales(d, s);
+    rc = linearize(d.q, d.t, d.X, true);
+    if (rc != PPSFM_OK) return rc;
+    rc = normal_equations();
+    if (rc != PPSFM_OK) return rc;
+  }
+  double cost = 0, gmax = 0;
+  rc = cost_and_gradient(&cost, &gmax);
+  if (rc != PPSFM_OK) return rc;
+  sum->initial_cost = cost;
+
+  int tl = 0;
+  auto trace = [&](double c, double radius, int acc) {
+    if (tl < PPSFM_BA_MAX_TRACE) {
+      sum->trace_cost[tl] = c;
+      sum->trace_radius[tl] = radius;
+      sum->trace_accepted[tl] = acc;
+      ++tl;
+    }
+  };
+  double radius = opt.initial_trust_region_radius;
+  double decrease_factor = 2.0;
+  trace(cost, radius, 1);
+  sum->termination_type = 1;
+  int invalid = 0;
+  bool done = eff == 0 || gmax <= opt.gradient_tolerance;
+  if (done) sum->termination_type = 0;
+  double solver_s = 0;
+
+  for (int iter = 0; !done && iter < opt.max_num_iterations; ++iter) {
+    const auto t_lin = std::chrono::steady_clock::now();
+    // --- reduced camera system + dense Cholesky
+    st->launches += launch_build_reduced_system(d, radius, opt.min_lm_diagonal,
+                                                opt.max_lm_diagonal, s);
+    if (st->world > 1) {
+      // rank 0 contributed blockdiag(U + D) and -g_c; every rank its points' Schur products
+      rc = AllReduceSum(st, d.S, (size_t)d.ld * (d.n + 1));
+      if (rc != PPSFM_OK) return rc;
+    }
+    int chol_failed = 0;
+    if (d.n > 0) {
+      st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_status, s);
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(&chol_failed, d.chol_status, sizeof(int),
+                                      cudaMemcpyDeviceToHost, s));
+    }
+    st->launches += launch_backsubstitute_and_update(d, s);
+    if (st->world > 1) {
+      rc = AllReduceSum(st, d.scalars + kModelChange, 3);  // model change, step^2, x^2
+      if (rc != PPSFM_OK) return rc;
+    }
+    // candidate cost
+    st->launches += launch_linearize(d, d.qn, d.tn, d.Xn, false, loss, s);
+    if (st->world > 1) {
+      rc = AllReduceSum(st, d.scalars + kCost, 1);
+      if (rc != PPSFM_OK) return rc;
+    }
+    rc = FetchScalars(st, &sc);
+    if (rc != PPSFM_OK) return rc;
+    solver_s += Secs(t_lin);
+    const double model_cost_change = sc.v[kModelChange];
+    const double cost_new = sc.v[kCost];
+    const double step_norm = std::sqrt(sc.v[kStepSq]), x_norm = std::sqrt(sc.v[kXSq]);
+
+    if (chol_failed || !(model_cost_change > 0.0)) {
+      ++sum->num_unsuccessful_steps;
+      if (++invalid >= opt.max_num_consecutive_invalid_steps) {
+        sum->termination_type = 2;
+        trace(cost, radius, 0);
+        break;
+      }
+      radius = radius / decrease_factor;  // LevenbergMarquardtStrategy::StepIsInvalid
+      decrease_factor *= 2.0;
+      trace(cost, radius, 0);
+      continue;
+    }
+    invalid = 0;
+    if (step_norm <= opt.parameter_tolerance * (x_norm + opt.parameter_tolerance)) {
+      sum->termination_type = 0;
+      break;
+    }
+    const double cost_change = cost - cost_new;
+    if (std::fabs(cost_change) <= opt.function_tolerance * cost) {
+      sum->termination_type = 0;
+      break;
+    }
+    const double relative_decrease = cost_change / model_cost_change;
+    if (relative_decrease > opt.min_relative_decrease) {
+      const double tmp = 2.0 * relative_decrease - 1.0;
+      radius = radius / std::max(1.0 / 3.0, 1.0 - tmp * tmp * tmp);
+      radius = std::min(opt.max_trust_region_radius, radius);
+      decrease_factor = 2.0;
+      std::swap(d.q, d.qn);
+      std::swap(d.t, d.tn);
+      std::swap(d.X, d.Xn);
+      rc = linearize(d.q, d.t, d.X, true);
+      if (rc != PPSFM_OK) return rc;
+      rc = normal_equations();
+      if (rc != PPSFM_OK) return rc;
+      rc = cost_and_gradient(&cost, &gmax);
+      if (rc != PPSFM_OK) return rc;
+      ++sum->num_successful_steps;
+      trace(cost, radius, 1);
+      if (gmax <= opt.gradient_tolerance) {
+        sum->termination_type = 0;
+        done = true;
+      }
+    } else {
+      radius = radius / decrease_factor;
+      decrease_factor *= 2.0;
+      ++sum->num_unsuccessful_steps;
+      trace(cost, radius, 0);
+      if (radius < opt.min_trust_region_radius) {
+        sum->termination_type = 0;
+        done = true;
+      }
+    }
+  }
+  PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+  PPSFM_CUDA(ctx, cudaGetLastError());
+  sum->final_cost = cost;
+  sum->final_gradient_max_norm = gmax;
+  sum->trace_len = tl;
+  sum->total_time_s = Secs(t_start);
+  sum->linear_solver_time_s = solver_s;
+  sum->jacobian_time_s = st->lin_ms * 1e-3;
+  sum->jacobian_launches = (int32_t)st->lin_launches;
+  sum->kernel_launches = st->launches;
+  return PPSFM_OK;
+}
+
+int BaDownload(BaState* st, const ppsfm_ba_problem* pb) {
+  ppsfm_ctx* ctx = st->ctx;
+  cudaStream_t s = ctx->stream;
+  const BaDev& d = st->d;
+  // poses of every image (constant ones come back unchanged); points owned by this rank
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->qvecs, d.q, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToHost, s));
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->tvecs, d.t, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToHost, s));
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->points, d.X, sizeof(double) * 3 * d.P, cudaMemcpyDeviceToHost, s));
+  PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+  return PPSFM_OK;
+}
+
+int BaReset(BaState* st) {
+  ppsfm_ctx* ctx = st->ctx;
+  cudaStream_t s = ctx->stream;
+  BaDev& d = st->d;
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(d.q, st->q0, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToDevice, s));
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(d.t, st->t0, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToDevice, s));
+  PPSFM_CUDA(ctx, cudaMemcpyAsync(d.X, st->X0, sizeof(double) * 3 * d.P, cudaMemcpyDeviceToDevice, s));
+  PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+  return PPSFM_OK;
+}
+
+namespace {
+int AllReduceSum(BaState* st, double*, size_t) {
+  return fail(st->ctx, PPSFM_ERR_NCCL, "multi-GPU BA requires ppsfm_comm_init (not initialised)");
+}
+int AllReduceMax(BaState* st, double*, size_t) {
+  return fail(st->ctx, PPSFM_ERR_NCCL, "multi-GPU BA requires ppsfm_comm_init (not initialised)");
+}
+}  // namespace
+
+}  // namespace ppsfm
+
+// ============================================================================================
+// C-ABI
+// ============================================================================================
+using namespace ppsfm;
+
+extern "C" {
+
+void ppsfm_ba_state_free(ppsfm_ctx* ctx) { (void)ctx; }
+
+void ppsfm_ba_options_default(ppsfm_ba_options* o) {
+  if (!o) return;
+  // BundleAdjustmentOptions() (src/optim/bundle_adjustment.h:49-93) + ceres::Solver::Options
+  o->loss_type = 0;
+  o->loss_scale = 1.0;
+  o->max_num_iterations = 100;
+  o->function_tolerance = 0.0;
+  o->gradient_tolerance = 0.0;
+  o->parameter_tolerance = 0.0;
+  o->max_num_consecutive_invalid_steps = 10;
+  o->initial_trust_region_radius = 1e4;
+  o->max_trust_region_radius = 1e16;
+  o->min_trust_region_radius = 1e-32;
+  o->min_relative_decrease = 1e-3;
+  o->min_lm_diagonal = 1e-6;
+  o->max_lm_diagonal = 1e32;
+  o->jacobi_scaling = 1;
+  o->num_threads = -1;
+}
+
+int ppsfm_ba_create(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                    const ppsfm_ba_options* options, ppsfm_ba** out) {
+  if (!ctx) return PPSFM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  BaState* st = nullptr;
+  const int rc = BaCreate(ctx, problem, options, 0, 1, &st);
+  if (out) *out = reinterpret_cast<ppsfm_ba*>(st);
+  return rc;
+}
+
+int ppsfm_ba_run(ppsfm_ba* ba, ppsfm_ba_summary* summary) {
+  BaState* st = reinterpret_cast<BaState*>(ba);
+  if (!st || !summary) return PPSFM_ERR_INVALID;
+  cudaSetDevice(st->ctx->device);
+  return BaRun(st, summary);
+}
+
+int ppsfm_ba_reset(ppsfm_ba* ba) {
+  BaState* st = reinterpret_cast<BaState*>(ba);
+  if (!st) return PPSFM_ERR_INVALID;
+  cudaSetDevice(st->ctx->device);
+  return BaReset(st);
+}
+
+int ppsfm_ba_download(ppsfm_ba* ba, const ppsfm_ba_problem* problem) {
+  BaState* st = reinterpret_cast<BaState*>(ba);
+  if (!st || !problem) return PPSFM_ERR_INVALID;
+  cudaSetDevice(st->ctx->device);
+  return BaDownload(st, problem);
+}
+
+void ppsfm_ba_free(ppsfm_ba* ba) {
+  BaState* st = reinterpret_cast<BaState*>(ba);
+  if (!st) return;
+  cudaSetDevice(st->ctx->device);
+  BaFree(st);
+}
+
+int ppsfm_ba_solve(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                   const ppsfm_ba_options* options, ppsfm_ba_summary* summary) {
+  ppsfm_ba* ba = nullptr;
+  int rc = ppsfm_ba_create(ctx, problem, options, &ba);
+  if (rc != PPSFM_OK) return rc;
+  rc = ppsfm_ba_run(ba, summary);
+  if (rc == PPSFM_OK) {
+    const int rc2 = ppsfm_ba_download(ba, problem);
+    if (rc2 != PPSFM_OK) rc = rc2;
+  }
+  ppsfm_ba_free(ba);
+  return rc;
+}
+
+// Test hook: residuals and tangent-space Jacobian blocks of every observation at the current
+// state, unscaled, with the loss correction of `options` (row-major 2, 2x6, 2x3 per observation,
+// in the order of the input observations; all-constant blocks come back as zeros).
+int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
+                       const ppsfm_ba_options* options, double* residuals, double* jac_cam,
+                       double* jac_point, double* cost) {
+  ppsfm_ba* ba = nullptr;
+  int rc = ppsfm_ba_create(ctx, problem, options, &ba);
+  if (rc != PPSFM_OK) return rc;
+  BaState* st = reinterpret_cast<BaState*>(ba);
+  BaDev& d = st->d;
+  cudaStream_t s = ctx->stream;
+  auto body = [&]() -> int {
+    std::vector<double> ones(std::max<size_t>(6 * (size_t)d.NB, 3 * (size_t)d.P), 1.0);
+    PPSFM_CUDA(ctx, cudaMemcpy(d.cam_scale, ones.data(), sizeof(double) * 6 * d.NB,
+                               cudaMemcpyHostToDevice));
+    PPSFM_CUDA(ctx, cudaMemcpy(d.pt_scale, ones.data(), sizeof(double) * 3 * d.P,
+                               cudaMemcpyHostToDevice));
+    launch_linearize(d, d.q, d.t, d.X, true, BaLoss{options->loss_type, options->loss_scale}, s);
+    const int64_t K = d.K;
+    std::vector<double> r(2 * (size_t)K), jc(12 * (size_t)K), jp(6 * (size_t)K);
+    std::vector<int> oc(K), op(K);
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(r.data(), d.r, sizeof(double) * 2 * K, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(jc.data(), d.Jc, sizeof(double) * 12 * K, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(jp.data(), d.Jp, sizeof(double) * 6 * K, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(oc.data(), d.obs_cam, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(op.data(), d.obs_pt, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
+    double c = 0;
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(&c, d.scalars + kCost, sizeof(double), cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+    PPSFM_CUDA(ctx, cudaGetLastError());
+    if (cost) *cost = c;
+    // kept observations are point-major and stable in input order: replay the same filter
+    const int64_t O = problem->num_obs;
+    std::vector<int64_t> next(problem->num_points + 1, 0);
+    std::vector<int64_t> pt_start(problem->num_points + 1, 0);
+    auto kept = [&](int64_t o) {
+      const int ci = problem->obs_image[o], pi = problem->obs_point[o];
+      const bool cc = problem->pose_flags && (problem->pose_flags[ci] & 1);
+      const bool pc = problem->point_const && problem->point_const[pi];
+      return !(cc && pc);
+    };
+    for (int64_t o = 0; o < O; ++o)
+      if (kept(o)) pt_start[problem->obs_point[o] + 1]++;
+    for (int i = 0; i < problem->num_points; ++i) pt_start[i + 1] += pt_start[i];
+    std::copy(pt_start.begin(), pt_start.end(), next.begin());
+    for (int64_t o = 0; o < O; ++o) {
+      double* ro = residuals + 2 * o;
+      double* co = jac_cam + 12 * o;
+      double* po = jac_point + 6 * o;
+      if (!kept(o)) {
+        std::fill(ro, ro + 2, 0.0);
+        std::fill(co, co + 12, 0.0);
+        std::fill(po, po + 6, 0.0);
+        continue;
+      }
+      const int64_t k = next[problem->obs_point[o]]++;
+      for (int i = 0; i < 2; ++i) ro[i] = r[(size_t)i * K + k];
+      for (int i = 0; i < 12; ++i) co[i] = jc[(size_t)i * K + k];
+      for (int i = 0; i < 6; ++i) po[i] = jp[(size_t)i * K + k];
+    }
+    return PPSFM_OK;
+  };
+  rc = body();
+  ppsfm_ba_free(ba);
+  return rc;
+}
+
+// Test hook: solves A x = b for a dense SPD matrix (row-major n x n, host) with the reduced-
+// camera-system solver (dense_chol.cu).  Returns PPSFM_NO_SOLUTION if A is not positive definite.
+int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const double* b,
+                               double* x) {
+  if (!ctx || !A || !b || !x || n <= 0) return fail(ctx, PPSFM_ERR_INVALID, "bad argument");
+  cudaSetDevice(ctx->device);
+  const int ld = chol_ld(n);
+  std::vector<double> h((size_t)ld * ld, 0.0);
+  for (int i = 0; i < n; ++i)
+    for (int j = 0; j <= i; ++j) h[(size_t)i * ld + j] = A[(size_t)i * n + j];
+  for (int j = 0; j < n; ++j) h[(size_t)n * ld + j] = b[j];
+  double *dA = nullptr, *dx = nullptr;
+  int* dst = nullptr;
+  PPSFM_CUDA(ctx, cudaMalloc(&dA, sizeof(double) * h.size()));
+  PPSFM_CUDA(ctx, cudaMalloc(&dx, sizeof(double) * n));
+  PPSFM_CUDA(ctx, cudaMalloc(&dst, sizeof(int)));
+  cudaStream_t s = ctx->stream;
+  int status = 0;
+  auto body = [&]() -> int {
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(dA, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s));
+    chol_solve_bordered(dA, n, ld, dx, dst, s);
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(&status, dst, sizeof(int), cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+    PPSFM_CUDA(ctx, cudaGetLastError());
+    return PPSFM_OK;
+  };
+  int rc = body();
+  cudaFree(dA);
+  cudaFree(dx);
+  cudaFree(dst);
+  if (rc == PPSFM_OK && status) rc = PPSFM_NO_SOLUTION;
+  return rc;
+}
+
+// RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213) with constant intrinsics
+// (refine_focal_length = refine_extra_params = false, the defaults of pose.h:84-101).
+int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
+                                          const double* lines, const double* points, size_t n,
+                                          int camera_model, const double* camera_params,
+                                          double gradient_tolerance, int max_num_iterations,
+                                          double loss_function_scale, double* qvec, double* tvec,
+                                          ppsfm_ba_summary* summary) {
+  if (!ctx || !inlier_mask || !lines || !points || !qvec || !tvec || !camera_params)
+    return fail(ctx, PPSFM_ERR_INVALID, "null argument");
+  if (camera_model < 0 || camera_model > 4)
+    return fail(ctx, PPSFM_ERR_INVALID, "camera model %d not supported", camera_model);
+  // AbsolutePoseRefinementOptions::Check (pose.h:103-107)
+  if (gradient_tolerance < 0 || max_num_iterations < 0 || loss_function_scale < 0)
+    return fail(ctx, PPSFM_ERR_INVALID, "AbsolutePoseRefinementOptions::Check failed");
+  std::vector<int32_t> oi, op;
+  std::vector<double> ol, pts;
+  for (size_t i = 0; i < n; ++i) {
+    if (!inlier_mask[i]) continue;
+    oi.push_back(0);
+    op.push_back((int32_t)(pts.size() / 3));
+    for (int k = 0; k < 3; ++k) {
+      ol.push_back(lines[3 * i + k]);
+      pts.push_back(points[3 * i + k]);
+    }
+  }
+  const int np = (int)(pts.size() / 3);
+  ppsfm_ba_summary local;
+  ppsfm_ba_summary* sum = summary ? summary : &local;
+  std::memset(sum, 0, sizeof(*sum));
+  if (np == 0) return PPSFM_OK;  // empty problem: Ceres converges immediately, "usable"
+  // *qvec = NormalizeQuaternion(*qvec)  (pose.cc:143)
+  const double nrm = std::sqrt(qvec[0] * qvec[0] + qvec[1] * qvec[1] + qvec[2] * qvec[2] + qvec[3] * qvec[3]);
+  if (nrm > 0) for (int k = 0; k < 4; ++k) qvec[k] /= nrm;
+  std::vector<uint8_t> pc(np, 1);
+  uint8_t flags = 0;
+  int32_t icam = 0, model = camera_model;
+  double params[12] = {0};
+  const int nparams[5] = {3, 4, 4, 5, 8};
+  for (int k = 0; k < nparams[camera_model]; ++k) params[k] = camera_params[k];
+  ppsfm_ba_problem pb;
+  pb.num_images = 1; pb.qvecs = qvec; pb.tvecs = tvec; pb.pose_flags = &flags;
+  pb.image_camera = &icam; pb.num_cameras = 1; pb.camera_model = &model;
+  pb.camera_params = params; pb.num_points = np; pb.points = pts.data();
+  pb.point_const = pc.data(); pb.num_obs = np; pb.obs_image = oi.data();
+  pb.obs_point = op.data(); pb.obs_line = ol.data();
+  ppsfm_ba_options o;
+  ppsfm_ba_options_default(&o);
+  o.loss_type = 2;  // ceres::CauchyLoss(options.loss_function_scale)  (pose.cc:106-107)
+  o.loss_scale = loss_function_scale;
+  o.gradient_tolerance = gradient_tolerance;
+  o.max_num_iterations = max_num_iterations;
+  o.function_tolerance = 1e-6;   // ceres::Solver::Options defaults: pose.cc:187-190 overrides
+  o.parameter_tolerance = 1e-8;  // only gradient_tolerance / max_num_iterations / solver type
+  const int rc = ppsfm_ba_solve(ctx, &pb, &o, sum);
+  if (rc != PPSFM_OK) return rc;
+  return sum->termination_type != 2 ? PPSFM_OK : PPSFM_NO_SOLUTION;  // IsSolutionUsable()
+}
+
+}  // extern "C"

@@ -1,0 +1,667 @@
+// ba_kernels.cu — sm_100a kernels of the line-reprojection bundle adjustment.
+//
+// Replaces what the reference delegates to Ceres (src/optim/bundle_adjustment.cc:306):
+//   ba_linearize_kernel      residual of BundleAdjustmentLineCostFunction
+//                            (src/base/cost_functions.h:62-100) with ANALYTIC 2x6 / 2x3 Jacobian
+//                            blocks in the tangent space of ceres::QuaternionParameterization,
+//                            robust-loss correction and Jacobi column scaling fused in
+//   ba_point_normal_kernel   V_p = sum J_p^T J_p, g_p          (one thread per point)
+//   ba_camera_normal_kernel  U_c = sum J_c^T J_c, g_c          (one CTA per camera, shuffles)
+//   ba_schur_kernel          S -= W V^-1 W^T, rhs += W V^-1 g_p (one warp per point)
+//   ba_backsub_kernel        dp = -V^-1 (g_p + W^T dc), model cost change, candidate points
+//   ba_camera_update_kernel  candidate poses via QuaternionParameterization::Plus
+// Observation data is stored SoA over the (point-major) observation index so that every warp
+// access is a coalesced 256-byte line.
+#include <cfloat>
+#include <cstdint>
+
+#include "ba_kernels.h"
+
+namespace ppsfm {
+
+namespace {
+
+constexpr int kThreads = 256;
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// Sums `v` over the CTA (blockDim.x multiple of 32, <= 1024); result valid in thread 0.
+__device__ __forceinline__ double block_sum(double v, double* smem /* >= 32 */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();
+  if (lane == 0) smem[warp] = v;
+  __syncthreads();
+  double r = 0.0;
+  if (warp == 0) {
+    const int nw = (blockDim.x + 31) >> 5;
+    r = (lane < nw) ? smem[lane] : 0.0;
+    r = warp_sum(r);
+  }
+  return r;
+}
+
+// CameraModel::WorldToImage (src/base/camera_models.h) and its 2x2 Jacobian d(x,y)/d(u,v).
+template <bool JAC>
+__device__ __forceinline__ void world_to_image(int model, const double* __restrict__ p, double u,
+                                               double v, double& x, double& y, double& xu,
+                                               double& xv, double& yu, double& yv) {
+  switch (model) {
+    case 0: {  // SIMPLE_PINHOLE f, cx, cy
+      x = p[0] * u + p[1];
+      y = p[0] * v + p[2];
+      if (JAC) { xu = p[0]; xv = 0.0; yu = 0.0; yv = p[0]; }
+      break;
+    }
+    case 1: {  // PINHOLE fx, fy, cx, cy
+      x = p[0] * u + p[2];
+      y = p[1] * v + p[3];
+      if (JAC) { xu = p[0]; xv = 0.0; yu = 0.0; yv = p[1]; }
+      break;
+    }
+    case 2:    // SIMPLE_RADIAL f, cx, cy, k
+    case 3: {  // RADIAL f, cx, cy, k1, k2
+      const double k1 = p[3], k2 = (model == 3) ? p[4] : 0.0;
+      const double u2 = u * u, v2 = v * v, r2 = u2 + v2;
+      const double radial = k1 * r2 + k2 * r2 * r2;
+      x = p[0] * (u + u * radial) + p[1];
+      y = p[0] * (v + v * radial) + p[2];
+      if (JAC) {
+        const double g = 2.0 * (k1 + 2.0 * k2 * r2);  // d radial / d(r2) * 2
+        xu = p[0] * (1.0 + radial + u * u * g);
+        xv = p[0] * (u * v * g);
+        yu = xv;
+        yv = p[0] * (1.0 + radial + v * v * g);
+      }
+      break;
+    }
+    default: {  // 4: OPENCV fx, fy, cx, cy, k1, k2, p1, p2
+      const double k1 = p[4], k2 = p[5], p1 = p[6], p2 = p[7];
+      const double u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
+      const double radial = k1 * r2 + k2 * r2 * r2;
+      const double du = u * radial + 2.0 * p1 * uv + p2 * (r2 + 2.0 * u2);
+      const double dv = v * radial + 2.0 * p2 * uv + p1 * (r2 + 2.0 * v2);
+      x = p[0] * (u + du) + p[2];
+      y = p[1] * (v + dv) + p[3];
+      if (JAC) {
+        const double g = 2.0 * (k1 + 2.0 * k2 * r2);
+        const double duu = radial + u2 * g + 2.0 * p1 * v + 6.0 * p2 * u;
+        const double duv = uv * g + 2.0 * p1 * u + 2.0 * p2 * v;
+        const double dvu = uv * g + 2.0 * p2 * v + 2.0 * p1 * u;
+        const double dvv = radial + v2 * g + 2.0 * p2 * u + 6.0 * p1 * v;
+        xu = p[0] * (1.0 + duu);
+        xv = p[0] * duv;
+        yu = p[1] * dvu;
+        yv = p[1] * (1.0 + dvv);
+      }
+      break;
+    }
+  }
+}
+
+// ceres loss functions (TrivialLoss, SoftLOneLoss, CauchyLoss): rho(s) and rho'(s).
+// rho'' <= 0 for all three, so the Triggs corrector reduces to scaling by sqrt(rho').
+__device__ __forceinline__ void eval_loss(BaLoss loss, double s, double& rho0, double& rho1) {
+  if (loss.type == 0) {
+    rho0 = s;
+    rho1 = 1.0;
+    return;
+  }
+  const double b = loss.scale * loss.scale, c = 1.0 / b;
+  const double sum = 1.0 + s * c;
+  if (loss.type == 1) {
+    const double tmp = sqrt(sum);
+    rho0 = 2.0 * b * (tmp - 1.0);
+    rho1 = fmax(DBL_MIN, 1.0 / tmp);
+  } else {
+    const double inv = 1.0 / sum;
+    rho0 = b * log(sum);
+    rho1 = fmax(DBL_MIN, inv);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Linearisation: one thread per observation.
+// Algorithmic HBM traffic (materialised variant): read line 24 + cam 4 + pt 4 +
+// point 24 B, write r 16 + J_c 96 + J_p 48 B = 216 B per observation.
+// ------------------------------------------------------------------------------------------
+template <bool JAC>
+__global__ void __launch_bounds__(kThreads)
+ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restrict__ t,
+                    const double* __restrict__ X, BaLoss loss, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int64_t K = d.K;
+  const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  double cost = 0.0;
+  if (k < K) {
+    const int ci = d.obs_cam[k], pi = d.obs_pt[k];
+    const double a = d.obs_line[k], b = d.obs_line[K + k], c = d.obs_line[2 * K + k];
+    const double4 qq = *reinterpret_cast<const double4*>(q + 4 * (size_t)ci);
+    const double qw = qq.x, qx = qq.y, qy = qq.z, qz = qq.w;
+    const double X0 = X[3 * (size_t)pi], X1 = X[3 * (size_t)pi + 1], X2 = X[3 * (size_t)pi + 2];
+    // ceres::UnitQuaternionRotatePoint
+    const double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy;
+    const double t7 = qx * qz, t8 = -qy * qy, t9 = qy * qz, t1 = -qz * qz;
+    const double R00 = 2.0 * (t8 + t1), R01 = 2.0 * (t6 - t4), R02 = 2.0 * (t3 + t7);
+    const double R10 = 2.0 * (t4 + t6), R11 = 2.0 * (t5 + t1), R12 = 2.0 * (t9 - t2);
+    const double R20 = 2.0 * (t7 - t3), R21 = 2.0 * (t2 + t9), R22 = 2.0 * (t5 + t8);
+    const double pr0 = R00 * X0 + R01 * X1 + R02 * X2 + X0;
+    const double pr1 = R10 * X0 + R11 * X1 + R12 * X2 + X1;
+    const double pr2 = R20 * X0 + R21 * X1 + R22 * X2 + X2;
+    const double p0 = pr0 + t[3 * (size_t)ci], p1 = pr1 + t[3 * (size_t)ci + 1];
+    const double p2 = pr2 + t[3 * (size_t)ci + 2];
+    const double iz = 1.0 / p2;
+    const double u = p0 * iz, v = p1 * iz;
+    const double alpha = a * u + b * v + c;
+    const double lu = u - alpha * a, lv = v - alpha * b;
+    const int model = d.img_model[ci];
+    const double* cp = d.img_params + 12 * (size_t)ci;
+    double x1, y1, x2, y2, d1xu = 0, d1xv = 0, d1yu = 0, d1yv = 0, d2xu = 0, d2xv = 0, d2yu = 0,
+                           d2yv = 0;
+    world_to_image<JAC>(model, cp, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
+    world_to_image<JAC>(model, cp, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+    double r0 = x1 - x2, r1 = y1 - y2;
+    const double sq = r0 * r0 + r1 * r1;
+    double rho0, rho1;
+    eval_loss(loss, sq, rho0, rho1);
+    cost = 0.5 * rho0;
+    if (JAC) {
+      const double sr = sqrt(rho1);
+      // d r / d(u,v) = D1 - D2 (I - n n^T)
+      const double m00 = 1.0 - a * a, m01 = -a * b, m11 = 1.0 - b * b;
+      const double E00 = d1xu - (d2xu * m00 + d2xv * m01), E01 = d1xv - (d2xu * m01 + d2xv * m11);
+      const double E10 = d1yu - (d2yu * m00 + d2yv * m01), E11 = d1yv - (d2yu * m01 + d2yv * m11);
+      // d r / d p  (p = R X + t)
+      double G[2][3];
+      G[0][0] = E00 * iz; G[0][1] = E01 * iz; G[0][2] = -(E00 * u + E01 * v) * iz;
+      G[1][0] = E10 * iz; G[1][1] = E11 * iz; G[1][2] = -(E10 * u + E11 * v) * iz;
+      const int blk = d.cam_block[ci];
+      const unsigned mask = blk >= 0 ? d.cam_mask[ci] : 0u;
+      const bool pvar = d.pt_var[pi] != 0;
+      double cs[6], ps[3];
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        cs[j] = ((mask >> j) & 1u) ? sr * d.cam_scale[6 * (size_t)blk + j] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 3; ++j) ps[j] = pvar ? sr * d.pt_scale[3 * (size_t)pi + j] : 0.0;
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        const double g0 = G[row][0], g1 = G[row][1], g2 = G[row][2];
+        // rotation (left perturbation q_delta * q, angle 2|delta|): d p / d delta = -2 [R X]_x
+        d.Jc[(6 * row + 0) * K + k] = cs[0] * 2.0 * (g2 * pr1 - g1 * pr2);
+        d.Jc[(6 * row + 1) * K + k] = cs[1] * 2.0 * (g0 * pr2 - g2 * pr0);
+        d.Jc[(6 * row + 2) * K + k] = cs[2] * 2.0 * (g1 * pr0 - g0 * pr1);
+        d.Jc[(6 * row + 3) * K + k] = cs[3] * g0;
+        d.Jc[(6 * row + 4) * K + k] = cs[4] * g1;
+        d.Jc[(6 * row + 5) * K + k] = cs[5] * g2;
+        // point: G R   (R = I + R..)
+        d.Jp[(3 * row + 0) * K + k] = ps[0] * (g0 * (R00 + 1.0) + g1 * R10 + g2 * R20);
+        d.Jp[(3 * row + 1) * K + k] = ps[1] * (g0 * R01 + g1 * (R11 + 1.0) + g2 * R21);
+        d.Jp[(3 * row + 2) * K + k] = ps[2] * (g0 * R02 + g1 * R12 + g2 * (R22 + 1.0));
+      }
+      d.r[k] = sr * r0;
+      d.r[K + k] = sr * r1;
+    }
+  }
+  const double total = block_sum(cost, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = total;
+}
+
+// Deterministic final reduction: channel ch sums partials[ch * stride .. + count).
+__global__ void __launch_bounds__(1024)
+reduce_partials_kernel(const double* __restrict__ partials, int count, int stride, int nch,
+                       double* __restrict__ scalars, int first_scalar, int accumulate) {
+  __shared__ double red[32];
+  for (int ch = 0; ch < nch; ++ch) {
+    double s = 0.0;
+    for (int i = threadIdx.x; i < count; i += blockDim.x) s += partials[(size_t)ch * stride + i];
+    const double tot = block_sum(s, red);
+    if (threadIdx.x == 0) {
+      if (accumulate) scalars[first_scalar + ch] += tot; else scalars[first_scalar + ch] = tot;
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Normal-equation blocks.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads) ba_point_normal_kernel(BaDev d) {
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  if (p >= d.P) return;
+  const int64_t K = d.K;
+  double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
+  for (int64_t k = d.pt_start[p]; k < d.pt_start[p + 1]; ++k) {
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const double j0 = d.Jp[(3 * row) * K + k], j1 = d.Jp[(3 * row + 1) * K + k];
+      const double j2 = d.Jp[(3 * row + 2) * K + k], rr = d.r[row * K + k];
+      v00 += j0 * j0; v01 += j0 * j1; v02 += j0 * j2;
+      v11 += j1 * j1; v12 += j1 * j2; v22 += j2 * j2;
+      g0 += j0 * rr; g1 += j1 * rr; g2 += j2 * rr;
+    }
+  }
+  const int P = d.P;
+  d.V[p] = v00; d.V[P + p] = v01; d.V[2 * P + p] = v02;
+  d.V[3 * P + p] = v11; d.V[4 * P + p] = v12; d.V[5 * P + p] = v22;
+  d.gp[p] = g0; d.gp[P + p] = g1; d.gp[2 * P + p] = g2;
+}
+
+__global__ void __launch_bounds__(128) ba_camera_normal_kernel(BaDev d) {
+  __shared__ double red[32];
+  const int b = blockIdx.x;
+  const int64_t K = d.K;
+  double u[21], g[6];
+#pragma unroll
+  for (int i = 0; i < 21; ++i) u[i] = 0.0;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) g[i] = 0.0;
+  for (int64_t i = d.cam_start[b] + threadIdx.x; i < d.cam_start[b + 1]; i += blockDim.x) {
+    const int64_t k = d.cam_obs[i];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      double j[6];
+#pragma unroll
+      for (int a = 0; a < 6; ++a) j[a] = d.Jc[(6 * row + a) * K + k];
+      const double rr = d.r[row * K + k];
+      int idx = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+#pragma unroll
+        for (int c = a; c < 6; ++c) u[idx++] += j[a] * j[c];
+        g[a] += j[a] * rr;
+      }
+    }
+  }
+  int idx = 0;
+  for (int a = 0; a < 6; ++a) {
+    for (int c = a; c < 6; ++c) {
+      const double tot = block_sum(u[idx++], red);
+      if (threadIdx.x == 0) {
+        d.U[36 * (size_t)b + 6 * a + c] = tot;
+        d.U[36 * (size_t)b + 6 * c + a] = tot;
+      }
+    }
+    const double tg = block_sum(g[a], red);
+    if (threadIdx.x == 0) d.gc[6 * (size_t)b + a] = tg;
+  }
+}
+
+__global__ void ba_jacobi_scales_kernel(BaDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < 6 * d.NB) {
+    const int b = i / 6, a = i % 6;
+    d.cam_scale[i] = 1.0 / (1.0 + sqrt(d.U[36 * (size_t)b + 7 * a]));
+  }
+  const int j = i - 6 * d.NB;
+  if (j >= 0 && j < 3 * d.P) {
+    const int p = j / 3, a = j % 3;
+    const int vi = (a == 0) ? 0 : (a == 1 ? 3 : 5);
+    d.pt_scale[j] = 1.0 / (1.0 + sqrt(d.V[(size_t)vi * d.P + p]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Reduced camera system.
+// ------------------------------------------------------------------------------------------
+__global__ void ba_init_reduced_kernel(BaDev d, double radius, double min_diag, double max_diag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over NB * 36
+  if (i >= 36 * d.NB) return;
+  const int b = i / 36, a = (i % 36) / 6, c = i % 6;
+  const unsigned mask = d.cam_mask[d.block_img[b]];
+  const bool on_a = (mask >> a) & 1u, on_c = (mask >> c) & 1u;
+  double v = d.U[i];
+  if (a == c) v += fmin(fmax(v, min_diag), max_diag) / radius;
+  if (!on_a || !on_c) v = (a == c) ? 1.0 : 0.0;
+  d.S[(size_t)(6 * b + a) * d.ld + 6 * b + c] = v;
+  if (c == 0) d.S[(size_t)d.n * d.ld + 6 * b + a] = on_a ? -d.gc[6 * (size_t)b + a] : 0.0;
+}
+
+// One warp per point.  With T_ef = J_p,e V^-1 J_p,f^T (2x2), the block contributed to camera
+// pair (e, f) is  J_c,e^T T_ef J_c,f  (6x6); only blocks with block(e) >= block(f) are written
+// (lower triangle), by double-precision atomics into the L2-resident S.
+__global__ void __launch_bounds__(kThreads)
+ba_schur_kernel(BaDev d, double radius, double min_diag, double max_diag) {
+  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (warp >= d.P) return;
+  const int p = warp;
+  const int P = d.P;
+  const int64_t K = d.K;
+  if (!d.pt_var[p]) {
+    if (lane < 6) d.Vinv[(size_t)lane * P + p] = 0.0;
+    return;
+  }
+  // damped V and its inverse (symmetric 3x3, adjugate / determinant)
+  double a = d.V[p], b = d.V[P + p], c = d.V[2 * P + p];
+  double e = d.V[3 * P + p], f = d.V[4 * P + p], i = d.V[5 * P + p];
+  a += fmin(fmax(a, min_diag), max_diag) / radius;
+  e += fmin(fmax(e, min_diag), max_diag) / radius;
+  i += fmin(fmax(i, min_diag), max_diag) / radius;
+  const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
+  const double det = a * c00 + b * c01 + c * c02;
+  double w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
+  if (fabs(det) > 0.0) {
+    const double id = 1.0 / det;
+    w00 = c00 * id; w01 = c01 * id; w02 = c02 * id;
+    w11 = (a * i - c * c) * id; w12 = (b * c - a * f) * id; w22 = (a * e - b * b) * id;
+  }
+  if (lane == 0) {
+    d.Vinv[p] = w00; d.Vinv[P + p] = w01; d.Vinv[2 * P + p] = w02;
+    d.Vinv[3 * P + p] = w11; d.Vinv[4 * P + p] = w12; d.Vinv[5 * P + p] = w22;
+  }
+  const double g0 = d.gp[p], g1 = d.gp[P + p], g2 = d.gp[2 * P + p];
+  const double vg0 = w00 * g0 + w01 * g1 + w02 * g2;
+  const double vg1 = w01 * g0 + w11 * g1 + w12 * g2;
+  const double vg2 = w02 * g0 + w12 * g1 + w22 * g2;
+  const int64_t k0 = d.pt_start[p];
+  const int m = (int)(d.pt_start[p + 1] - k0);
+  double* rhs = d.S + (size_t)d.n * d.ld;
+  // rhs += W V^-1 g_p
+  for (int eo = lane; eo < m; eo += 32) {
+    const int64_t k = k0 + eo;
+    const int bi = d.cam_block[d.obs_cam[k]];
+    if (bi < 0) continue;
+    double y[2];
+#pragma unroll
+    for (int row = 0; row < 2; ++row)
+      y[row] = d.Jp[(3 * row) * K + k] * vg0 + d.Jp[(3 * row + 1) * K + k] * vg1 +
+               d.Jp[(3 * row + 2) * K + k] * vg2;
+#pragma unroll
+    for (int a2 = 0; a2 < 6; ++a2)
+      atomicAdd(&rhs[6 * bi + a2], d.Jc[a2 * K + k] * y[0] + d.Jc[(6 + a2) * K + k] * y[1]);
+  }
+  // S -= sum over ordered pairs
+  for (int idx = lane; idx < m * m; idx += 32) {
+    const int eo = idx / m, fo = idx % m;
+    const int64_t ke = k0 + eo, kf = k0 + fo;
+    const int bi = d.cam_block[d.obs_cam[ke]], bj = d.cam_block[d.obs_cam[kf]];
+    if (bi < 0 || bj < 0 || bi < bj) continue;
+    // Y_e = J_p,e V^-1 (2x3)
+    double Y[2][3], T[2][2];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const double j0 = d.Jp[(3 * row) * K + ke], j1 = d.Jp[(3 * row + 1) * K + ke];
+      const double j2 = d.Jp[(3 * row + 2) * K + ke];
+      Y[row][0] = j0 * w00 + j1 * w01 + j2 * w02;
+      Y[row][1] = j0 * w01 + j1 * w11 + j2 * w12;
+      Y[row][2] = j0 * w02 + j1 * w12 + j2 * w22;
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < 2; ++s2) {
+      const double j0 = d.Jp[(3 * s2) * K + kf], j1 = d.Jp[(3 * s2 + 1) * K + kf];
+      const double j2 = d.Jp[(3 * s2 + 2) * K + kf];
+      T[0][s2] = Y[0][0] * j0 + Y[0][1] * j1 + Y[0][2] * j2;
+      T[1][s2] = Y[1][0] * j0 + Y[1][1] * j1 + Y[1][2] * j2;
+    }
+    double Jf[2][6];
+#pragma unroll
+    for (int c2 = 0; c2 < 6; ++c2) {
+      Jf[0][c2] = d.Jc[c2 * K + kf];
+      Jf[1][c2] = d.Jc[(6 + c2) * K + kf];
+    }
+    double* blk = d.S + (size_t)(6 * bi) * d.ld + 6 * bj;
+#pragma unroll
+    for (int a2 = 0; a2 < 6; ++a2) {
+      const double e0 = d.Jc[a2 * K + ke], e1 = d.Jc[(6 + a2) * K + ke];
+      const double h0 = e0 * T[0][0] + e1 * T[1][0];  // (J_c,e^T T)[a][0]
+      const double h1 = e0 * T[0][1] + e1 * T[1][1];
+#pragma unroll
+      for (int c2 = 0; c2 < 6; ++c2)
+        atomicAdd(&blk[(size_t)a2 * d.ld + c2], -(h0 * Jf[0][c2] + h1 * Jf[1][c2]));
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Back-substitution, model cost change, candidate state.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+ba_backsub_kernel(BaDev d, double* __restrict__ partials, int stride) {
+  __shared__ double red[32];
+  const int p = blockIdx.x * kThreads + threadIdx.x;
+  const int P = d.P;
+  const int64_t K = d.K;
+  double model = 0.0, step_sq = 0.0, x_sq = 0.0;
+  if (p < P) {
+    const int64_t k0 = d.pt_start[p], k1 = d.pt_start[p + 1];
+    double acc0 = d.gp[p], acc1 = d.gp[P + p], acc2 = d.gp[2 * P + p];
+    for (int64_t k = k0; k < k1; ++k) {
+      const int b = d.cam_block[d.obs_cam[k]];
+      if (b < 0) continue;
+      double u0 = 0.0, u1 = 0.0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        const double dca = d.dc[6 * b + a];
+        u0 += d.Jc[a * K + k] * dca;
+        u1 += d.Jc[(6 + a) * K + k] * dca;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const double v = d.Jp[c * K + k] * u0 + d.Jp[(3 + c) * K + k] * u1;
+        if (c == 0) acc0 += v; else if (c == 1) acc1 += v; else acc2 += v;
+      }
+    }
+    const double w00 = d.Vinv[p], w01 = d.Vinv[P + p], w02 = d.Vinv[2 * P + p];
+    const double w11 = d.Vinv[3 * P + p], w12 = d.Vinv[4 * P + p], w22 = d.Vinv[5 * P + p];
+    const double dp0 = -(w00 * acc0 + w01 * acc1 + w02 * acc2);
+    const double dp1 = -(w01 * acc0 + w11 * acc1 + w12 * acc2);
+    const double dp2 = -(w02 * acc0 + w12 * acc1 + w22 * acc2);
+    d.dp[p] = dp0; d.dp[P + p] = dp1; d.dp[2 * P + p] = dp2;
+    // model_cost_change = -sum (J d) . (r + J d / 2)
+    for (int64_t k = k0; k < k1; ++k) {
+      const int b = d.cam_block[d.obs_cam[k]];
+#pragma unroll
+      for (int row = 0; row < 2; ++row) {
+        double m = d.Jp[(3 * row) * K + k] * dp0 + d.Jp[(3 * row + 1) * K + k] * dp1 +
+                   d.Jp[(3 * row + 2) * K + k] * dp2;
+        if (b >= 0) {
+#pragma unroll
+          for (int a = 0; a < 6; ++a) m += d.Jc[(6 * row + a) * K + k] * d.dc[6 * b + a];
+        }
+        model -= m * (d.r[row * K + k] + 0.5 * m);
+      }
+    }
+    // candidate point
+    const double x0 = d.X[3 * (size_t)p], x1 = d.X[3 * (size_t)p + 1], x2 = d.X[3 * (size_t)p + 2];
+    const double s0 = dp0 * d.pt_scale[3 * (size_t)p], s1 = dp1 * d.pt_scale[3 * (size_t)p + 1];
+    const double s2 = dp2 * d.pt_scale[3 * (size_t)p + 2];
+    d.Xn[3 * (size_t)p] = x0 + s0;
+    d.Xn[3 * (size_t)p + 1] = x1 + s1;
+    d.Xn[3 * (size_t)p + 2] = x2 + s2;
+    if (d.pt_var[p]) {
+      step_sq = s0 * s0 + s1 * s1 + s2 * s2;
+      x_sq = x0 * x0 + x1 * x1 + x2 * x2;
+    }
+  }
+  const double tm = block_sum(model, red);
+  const double ts = block_sum(step_sq, red);
+  const double tx = block_sum(x_sq, red);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x] = tm;
+    partials[stride + blockIdx.x] = ts;
+    partials[2 * stride + blockIdx.x] = tx;
+  }
+}
+
+// ceres::QuaternionParameterization::Plus
+__device__ __forceinline__ void quaternion_plus(const double* x, const double* delta, double* out) {
+  const double nd = sqrt(delta[0] * delta[0] + delta[1] * delta[1] + delta[2] * delta[2]);
+  if (nd > 0.0) {
+    const double s = sin(nd) / nd;
+    const double q0 = cos(nd), q1 = s * delta[0], q2 = s * delta[1], q3 = s * delta[2];
+    out[0] = q0 * x[0] - q1 * x[1] - q2 * x[2] - q3 * x[3];
+    out[1] = q0 * x[1] + q1 * x[0] + q2 * x[3] - q3 * x[2];
+    out[2] = q0 * x[2] - q1 * x[3] + q2 * x[0] + q3 * x[1];
+    out[3] = q0 * x[3] + q1 * x[2] - q2 * x[1] + q3 * x[0];
+  } else {
+    out[0] = x[0]; out[1] = x[1]; out[2] = x[2]; out[3] = x[3];
+  }
+}
+
+// single CTA (cameras are few): candidate poses + camera part of step / x norms
+__global__ void __launch_bounds__(kThreads) ba_camera_update_kernel(BaDev d) {
+  __shared__ double red[32];
+  double step_sq = 0.0, x_sq = 0.0;
+  for (int i = threadIdx.x; i < d.C; i += kThreads) {
+    const int b = d.cam_block[i];
+    double qv[4], tv[3];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qv[k] = d.q[4 * (size_t)i + k];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) tv[k] = d.t[3 * (size_t)i + k];
+    if (b < 0) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) d.qn[4 * (size_t)i + k] = qv[k];
+#pragma unroll
+      for (int k = 0; k < 3; ++k) d.tn[3 * (size_t)i + k] = tv[k];
+      continue;
+    }
+    double dl[6], qp[4];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) dl[a] = d.dc[6 * b + a] * d.cam_scale[6 * (size_t)b + a];
+    quaternion_plus(qv, dl, qp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      d.qn[4 * (size_t)i + k] = qp[k];
+      step_sq += (qp[k] - qv[k]) * (qp[k] - qv[k]);
+      x_sq += qv[k] * qv[k];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      d.tn[3 * (size_t)i + k] = tv[k] + dl[3 + k];
+      step_sq += dl[3 + k] * dl[3 + k];
+      x_sq += tv[k] * tv[k];
+    }
+  }
+  const double ts = block_sum(step_sq, red);
+  const double tx = block_sum(x_sq, red);
+  if (threadIdx.x == 0) {
+    d.scalars[kStepSq] = ts;
+    d.scalars[kXSq] = tx;
+  }
+}
+
+__device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
+  atomicMax(reinterpret_cast<unsigned long long*>(addr),
+            (unsigned long long)__double_as_longlong(v));
+}
+
+// gradient of the unscaled problem: g = g_scaled / scale (J_s = J diag(scale)); max |x - Plus(x, -g)|
+__global__ void ba_gradient_max_kernel(BaDev d) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double m = 0.0;
+  if (i < d.NB) {
+    const int img = d.block_img[i];
+    double g[6];
+#pragma unroll
+    for (int a = 0; a < 6; ++a) g[a] = d.gc[6 * (size_t)i + a] / d.cam_scale[6 * (size_t)i + a];
+    const double nd[3] = {-g[0], -g[1], -g[2]};
+    double qv[4], qp[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) qv[k] = d.q[4 * (size_t)img + k];
+    quaternion_plus(qv, nd, qp);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) m = fmax(m, fabs(qp[k] - qv[k]));
+#pragma unroll
+    for (int a = 3; a < 6; ++a) m = fmax(m, fabs(g[a]));
+  }
+  const int p = i - d.NB;
+  if (p >= 0 && p < d.P) {
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+      m = fmax(m, fabs(d.gp[(size_t)a * d.P + p] / d.pt_scale[3 * (size_t)p + a]));
+  }
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0.0) atomic_max_nonneg(&d.scalars[kGradMax], m);
+}
+
+}  // namespace
+
+// ============================================================================================
+int launch_linearize(const BaDev& d, const double* q, const double* t, const double* X,
+                     bool jacobians, BaLoss loss, cudaStream_t s) {
+  const int blocks = (int)((d.K + kThreads - 1) / kThreads);
+  if (blocks == 0) {
+    cudaMemsetAsync(d.scalars + kCost, 0, sizeof(double), s);
+    return 0;
+  }
+  if (jacobians)
+    ba_linearize_kernel<true><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials);
+  else
+    ba_linearize_kernel<false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials);
+  reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
+                                            kCost, 0);
+  return 2;
+}
+
+int launch_normal_equations(const BaDev& d, cudaStream_t s) {
+  int n = 0;
+  if (d.P > 0) {
+    ba_point_normal_kernel<<<(d.P + kThreads - 1) / kThreads, kThreads, 0, s>>>(d);
+    ++n;
+  }
+  if (d.NB > 0) {
+    ba_camera_normal_kernel<<<d.NB, 128, 0, s>>>(d);
+    ++n;
+  }
+  return n;
+}
+
+int launch_jacobi_scales(const BaDev& d, cudaStream_t s) {
+  const int total = 6 * d.NB + 3 * d.P;
+  if (total == 0) return 0;
+  ba_jacobi_scales_kernel<<<(total + 255) / 256, 256, 0, s>>>(d);
+  return 1;
+}
+
+int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,
+                                cudaStream_t s) {
+  int n = 0;
+  cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.ld * d.ld, s);
+  if (d.NB > 0) {
+    ba_init_reduced_kernel<<<(36 * d.NB + 255) / 256, 256, 0, s>>>(d, radius, min_diag, max_diag);
+    ++n;
+  }
+  if (d.P > 0) {
+    const int64_t threads = (int64_t)d.P * 32;
+    ba_schur_kernel<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
+        d, radius, min_diag, max_diag);
+    ++n;
+  }
+  return n;
+}
+
+int launch_backsubstitute_and_update(const BaDev& d, cudaStream_t s) {
+  int n = 0;
+  ba_camera_update_kernel<<<1, kThreads, 0, s>>>(d);
+  ++n;
+  const int blocks = (d.P + kThreads - 1) / kThreads;
+  if (blocks > 0) {
+    ba_backsub_kernel<<<blocks, kThreads, 0, s>>>(d, d.partials, d.num_partials);
+    // model change overwrites, step / x norms accumulate on top of the camera part
+    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
+                                              kModelChange, 0);
+    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials + d.num_partials, blocks,
+                                              d.num_partials, 2, d.scalars, kStepSq, 1);
+    n += 3;
+  } else {
+    cudaMemsetAsync(d.scalars + kModelChange, 0, sizeof(double), s);
+  }
+  return n;
+}
+
+int launch_gradient_max_norm(const BaDev& d, cudaStream_t s) {
+  cudaMemsetAsync(d.scalars + kGradMax, 0, sizeof(double), s);
+  const int total = d.NB + d.P;
+  if (total == 0) return 0;
+  ba_gradient_max_kernel<<<(total + 255) / 256, 256, 0, s>>>(d);
+  return 1;
+}
+
+}  // namespace ppsfm

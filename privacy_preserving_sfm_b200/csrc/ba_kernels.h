@@ -1,0 +1,79 @@
+// ba_kernels.h — device-side data model and launch wrappers of the bundle-adjustment kernels.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+namespace ppsfm {
+
+// All arrays live in HBM.  K = kept observations (point-major), C = images, P = points,
+// NB = camera blocks (images with a variable pose that have observations).
+struct BaDev {
+  int C = 0, P = 0, NB = 0, n = 0, ld = 0;
+  int64_t K = 0;
+  // static structure
+  int* obs_cam = nullptr;       // [K] image index
+  int* obs_pt = nullptr;        // [K] point index
+  double* obs_line = nullptr;   // [3][K] SoA
+  int64_t* pt_start = nullptr;  // [P+1] first observation of every point
+  int* cam_obs = nullptr;       // [K] observation ids grouped by camera block
+  int64_t* cam_start = nullptr; // [NB+1]
+  int* block_img = nullptr;     // [NB] image index of a block
+  int* cam_block = nullptr;     // [C] block index or -1 (constant pose)
+  uint8_t* cam_mask = nullptr;  // [C] bit a set = tangent dim a (rot 0..2, trans 3..5) is free
+  int* img_model = nullptr;     // [C] COLMAP camera model id
+  double* img_params = nullptr; // [C][12] intrinsics (constant)
+  uint8_t* pt_var = nullptr;    // [P]
+  // state
+  double* q = nullptr;   // [C][4]
+  double* t = nullptr;   // [C][3]
+  double* X = nullptr;   // [P][3]
+  double* qn = nullptr;  // candidate
+  double* tn = nullptr;
+  double* Xn = nullptr;
+  // linearisation (scaled by the Jacobi column scales, loss-corrected), SoA over K
+  double* r = nullptr;    // [2][K]
+  double* Jc = nullptr;   // [12][K]: row-major 2x6 [rot | trans]
+  double* Jp = nullptr;   // [6][K]:  row-major 2x3
+  double* cam_scale = nullptr;  // [NB][6]
+  double* pt_scale = nullptr;   // [P][3]
+  // normal equations
+  double* U = nullptr;    // [NB][36]
+  double* gc = nullptr;   // [NB][6]
+  double* V = nullptr;    // [6][P] symmetric (00 01 02 11 12 22), SoA
+  double* gp = nullptr;   // [3][P]
+  double* Vinv = nullptr; // [6][P]
+  double* S = nullptr;    // [ld][ld] bordered reduced camera matrix (row n = rhs)
+  double* dc = nullptr;   // [n]
+  double* dp = nullptr;   // [3][P]
+  int* chol_status = nullptr;
+  // reductions
+  double* partials = nullptr;  // scratch for block partial sums
+  int num_partials = 0;
+  double* scalars = nullptr;   // [16] device scalars
+};
+
+enum BaScalar { kCost = 0, kModelChange = 1, kStepSq = 2, kXSq = 3, kGradMax = 4, kNumScalars = 16 };
+
+struct BaLoss {
+  int type;      // 0 TRIVIAL, 1 SOFT_L1, 2 CAUCHY
+  double scale;
+};
+
+// residuals (+ Jacobians) at (q, t, X) given as pointers so that the candidate state can be
+// evaluated; cost = 0.5 sum rho(|r|^2) is left in scalars[kCost].  Returns #launches.
+int launch_linearize(const BaDev& d, const double* q, const double* t, const double* X,
+                     bool jacobians, BaLoss loss, cudaStream_t s);
+// U, gc, V, gp from the stored linearisation.
+int launch_normal_equations(const BaDev& d, cudaStream_t s);
+// Jacobi scales 1 / (1 + sqrt(diag)) from U, V (computed with unit scales).
+int launch_jacobi_scales(const BaDev& d, cudaStream_t s);
+// S = blockdiag(U + D_c^2) - W (V + D_p^2)^-1 W^T (lower triangle), row n = rhs; stores Vinv.
+int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,
+                                cudaStream_t s);
+// dp from dc, model cost change, candidate state, step / x norms (scalars).
+int launch_backsubstitute_and_update(const BaDev& d, cudaStream_t s);
+// max |x - Plus(x, -g)| over all blocks -> scalars[kGradMax]
+int launch_gradient_max_norm(const BaDev& d, cudaStream_t s);
+
+}  // namespace ppsfm

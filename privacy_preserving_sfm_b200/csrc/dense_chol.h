@@ -1,0 +1,14 @@
+// dense_chol.h — dense FP64 Cholesky solve of the reduced camera system (dense_chol.cu).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ppsfm {
+
+// Leading dimension (multiple of 64) for an n x n system with its right-hand side as row n.
+int chol_ld(int n);
+// A: ld x ld row-major; rows [0,n) lower triangle of the SPD matrix, row n = rhs^T, rest zero.
+// On return x (n doubles, device) holds the solution and A the factor.  *status (device int)
+// becomes 1 if a non-positive pivot was met.  Asynchronous; returns the number of launches.
+int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaStream_t s);
+
+}  // namespace ppsfm

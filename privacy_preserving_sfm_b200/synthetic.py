@@ -136,8 +136,16 @@ def make_ba_scene(num_cams=100, num_points=30000, obs_per_point=10, focal=1000.0
         tvecs[i] = -R @ centers[i]
     points = rng.uniform(-1, 1, size=(num_points, 3))
     # visibility: obs_per_point distinct cameras per point
-    keys = rng.random((num_points, num_cams))
-    cam_idx = np.argsort(keys, axis=1)[:, :obs_per_point].astype(np.int32)
+    cam_idx = np.empty((num_points, obs_per_point), dtype=np.int32)
+    chunk = max(1, (1 << 24) // max(1, num_cams))      # bound the key matrix to ~128 MB
+    for lo in range(0, num_points, chunk):
+        hi = min(num_points, lo + chunk)
+        keys = rng.random((hi - lo, num_cams))
+        if obs_per_point < num_cams:
+            part = np.argpartition(keys, obs_per_point - 1, axis=1)[:, :obs_per_point]
+        else:
+            part = np.tile(np.arange(num_cams), (hi - lo, 1))
+        cam_idx[lo:hi] = part
     cam_idx.sort(axis=1)
     obs_cam = cam_idx.reshape(-1)
     obs_pt = np.repeat(np.arange(num_points, dtype=np.int32), obs_per_point)
