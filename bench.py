@@ -389,6 +389,12 @@ def run_ba_b200(args, ctx, world, rank, dist):
                      "frac": achieved / hbm_peak, "peak_source": peak_kind,
                      "bytes_per_obs": BA_BYTES_PER_OBS, "avg_launch_ms": 1e3 * jac_avg_s,
                      "traffic": None},
+        "phase_ms_per_iteration": {
+            "jacobian_build": 1e3 * jac_avg_s,
+            "reduced_system": 1e3 * summ.schur_time_s / max(1, summ.num_iterations),
+            "cholesky_solve": 1e3 * summ.cholesky_time_s / max(1, summ.num_iterations),
+            "backsubstitution_and_candidate_cost":
+                1e3 * summ.backsub_time_s / max(1, summ.num_iterations)},
         "result": {"initial_cost": summ.initial_cost, "final_cost": summ.final_cost,
                    "successful_steps": summ.num_successful_steps,
                    "unsuccessful_steps": summ.num_unsuccessful_steps},

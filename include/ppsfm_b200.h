@@ -216,6 +216,10 @@ typedef struct {
   int32_t trace_accepted[PPSFM_BA_MAX_TRACE];
   int32_t jacobian_launches;
   int64_t kernel_launches;
+  /* device time (CUDA events) of the phases of the linear solve, summed over iterations */
+  double schur_time_s;     /* reduced camera system assembly */
+  double cholesky_time_s;  /* dense factorisation + triangular solves */
+  double backsub_time_s;   /* back-substitution, model cost, candidate state + cost */
 } ppsfm_ba_summary;
 
 void ppsfm_ba_options_default(ppsfm_ba_options* opt);

@@ -61,7 +61,9 @@ class BaSummary(C.Structure):
                 ("trace_cost", C.c_double * BA_MAX_TRACE),
                 ("trace_radius", C.c_double * BA_MAX_TRACE),
                 ("trace_accepted", C.c_int32 * BA_MAX_TRACE),
-                ("jacobian_launches", C.c_int32), ("kernel_launches", C.c_int64)]
+                ("jacobian_launches", C.c_int32), ("kernel_launches", C.c_int64),
+                ("schur_time_s", C.c_double), ("cholesky_time_s", C.c_double),
+                ("backsub_time_s", C.c_double)]
 
     def IsSolutionUsable(self):
         return self.termination_type != 2

@@ -33,6 +33,7 @@ struct BaState {
   int64_t launches = 0;
   double lin_ms = 0, lin_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t evp[4] = {nullptr, nullptr, nullptr, nullptr};  // phase marks of one LM iteration
   // multi-GPU
   int rank = 0, world = 1;
   void* comm = nullptr;  // ncclComm_t
@@ -73,6 +74,8 @@ void BaFree(BaState* st) {
   st->h_scalars.release();
   if (st->ev0) cudaEventDestroy(st->ev0);
   if (st->ev1) cudaEventDestroy(st->ev1);
+  for (auto& e : st->evp)
+    if (e) cudaEventDestroy(e);
   delete st;
 }
 
@@ -236,6 +239,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.S, (size_t)d.ld * d.ld));
   BA_TRY(DevAlloc(st, &d.dc, (size_t)std::max(1, d.n)));
   BA_TRY(DevAlloc(st, &d.dp, 3 * (size_t)P));
+  BA_TRY(DevAlloc(st, &d.u, 2 * (size_t)K));
   BA_TRY(DevAlloc(st, &d.chol_status, 1));
   d.num_partials = (int)std::max<int64_t>((K + 255) / 256, (P + 255) / 256) + 1;
   BA_TRY(DevAlloc(st, &d.partials, 3 * (size_t)d.num_partials));
@@ -244,6 +248,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(st->h_scalars.reserve(sizeof(double) * kNumScalars));
   BA_TRY(cudaEventCreate(&st->ev0));
   BA_TRY(cudaEventCreate(&st->ev1));
+  for (auto& ev : st->evp) BA_TRY(cudaEventCreate(&ev));
   BA_TRY(cudaStreamSynchronize(s));
 #undef BA_TRY
   if (e != cudaSuccess) {
@@ -384,6 +389,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   for (int iter = 0; !done && iter < opt.max_num_iterations; ++iter) {
     const auto t_lin = std::chrono::steady_clock::now();
     // --- reduced camera system + dense Cholesky
+    PPSFM_CUDA(ctx, cudaEventRecord(st->evp[0], s));
     st->launches += launch_build_reduced_system(d, radius, opt.min_lm_diagonal,
                                                 opt.max_lm_diagonal, s);
     if (st->world > 1) {
@@ -391,12 +397,14 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       rc = AllReduceSum(st, d.S, (size_t)d.ld * (d.n + 1));
       if (rc != PPSFM_OK) return rc;
     }
+    PPSFM_CUDA(ctx, cudaEventRecord(st->evp[1], s));
     int chol_failed = 0;
     if (d.n > 0) {
       st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_status, s);
       PPSFM_CUDA(ctx, cudaMemcpyAsync(&chol_failed, d.chol_status, sizeof(int),
                                       cudaMemcpyDeviceToHost, s));
     }
+    PPSFM_CUDA(ctx, cudaEventRecord(st->evp[2], s));
     st->launches += launch_backsubstitute_and_update(d, s);
     if (st->world > 1) {
       rc = AllReduceSum(st, d.scalars + kModelChange, 3);  // model change, step^2, x^2
@@ -408,9 +416,19 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       rc = AllReduceSum(st, d.scalars + kCost, 1);
       if (rc != PPSFM_OK) return rc;
     }
+    PPSFM_CUDA(ctx, cudaEventRecord(st->evp[3], s));
     rc = FetchScalars(st, &sc);
     if (rc != PPSFM_OK) return rc;
     solver_s += Secs(t_lin);
+    {
+      float m01 = 0, m12 = 0, m23 = 0;
+      cudaEventElapsedTime(&m01, st->evp[0], st->evp[1]);
+      cudaEventElapsedTime(&m12, st->evp[1], st->evp[2]);
+      cudaEventElapsedTime(&m23, st->evp[2], st->evp[3]);
+      sum->schur_time_s += 1e-3 * m01;
+      sum->cholesky_time_s += 1e-3 * m12;
+      sum->backsub_time_s += 1e-3 * m23;
+    }
     const double model_cost_change = sc.v[kModelChange];
     const double cost_new = sc.v[kCost];
     const double step_norm = std::sqrt(sc.v[kStepSq]), x_norm = std::sqrt(sc.v[kXSq]);

@@ -420,53 +420,46 @@ ba_schur_kernel(BaDev d, double radius, double min_diag, double max_diag) {
 // ------------------------------------------------------------------------------------------
 // Back-substitution, model cost change, candidate state.
 // ------------------------------------------------------------------------------------------
+// (1) one thread per observation: u = J_c dc (kept for the model-cost pass), and the point-side
+//     accumulation acc_p += J_p^T u by atomics (acc is pre-loaded with g_p; lives in d.dp).
+__global__ void __launch_bounds__(kThreads) ba_backsub_accum_kernel(BaDev d) {
+  const int64_t K = d.K;
+  const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (k >= K) return;
+  const int b = d.cam_block[d.obs_cam[k]];
+  double u0 = 0.0, u1 = 0.0;
+  if (b >= 0) {
+#pragma unroll
+    for (int a = 0; a < 6; ++a) {
+      const double dca = d.dc[6 * b + a];
+      u0 += d.Jc[a * K + k] * dca;
+      u1 += d.Jc[(6 + a) * K + k] * dca;
+    }
+    const int p = d.obs_pt[k];
+    const int P = d.P;
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+      atomicAdd(&d.dp[(size_t)c * P + p], d.Jp[c * K + k] * u0 + d.Jp[(3 + c) * K + k] * u1);
+  }
+  d.u[k] = u0;
+  d.u[K + k] = u1;
+}
+
+// (2) one thread per point: dp = -V^-1 acc, candidate point, step / x norm partials.
 __global__ void __launch_bounds__(kThreads)
-ba_backsub_kernel(BaDev d, double* __restrict__ partials, int stride) {
+ba_point_step_kernel(BaDev d, double* __restrict__ partials, int stride) {
   __shared__ double red[32];
   const int p = blockIdx.x * kThreads + threadIdx.x;
   const int P = d.P;
-  const int64_t K = d.K;
-  double model = 0.0, step_sq = 0.0, x_sq = 0.0;
+  double step_sq = 0.0, x_sq = 0.0;
   if (p < P) {
-    const int64_t k0 = d.pt_start[p], k1 = d.pt_start[p + 1];
-    double acc0 = d.gp[p], acc1 = d.gp[P + p], acc2 = d.gp[2 * P + p];
-    for (int64_t k = k0; k < k1; ++k) {
-      const int b = d.cam_block[d.obs_cam[k]];
-      if (b < 0) continue;
-      double u0 = 0.0, u1 = 0.0;
-#pragma unroll
-      for (int a = 0; a < 6; ++a) {
-        const double dca = d.dc[6 * b + a];
-        u0 += d.Jc[a * K + k] * dca;
-        u1 += d.Jc[(6 + a) * K + k] * dca;
-      }
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        const double v = d.Jp[c * K + k] * u0 + d.Jp[(3 + c) * K + k] * u1;
-        if (c == 0) acc0 += v; else if (c == 1) acc1 += v; else acc2 += v;
-      }
-    }
+    const double acc0 = d.dp[p], acc1 = d.dp[P + p], acc2 = d.dp[2 * P + p];
     const double w00 = d.Vinv[p], w01 = d.Vinv[P + p], w02 = d.Vinv[2 * P + p];
     const double w11 = d.Vinv[3 * P + p], w12 = d.Vinv[4 * P + p], w22 = d.Vinv[5 * P + p];
     const double dp0 = -(w00 * acc0 + w01 * acc1 + w02 * acc2);
     const double dp1 = -(w01 * acc0 + w11 * acc1 + w12 * acc2);
     const double dp2 = -(w02 * acc0 + w12 * acc1 + w22 * acc2);
     d.dp[p] = dp0; d.dp[P + p] = dp1; d.dp[2 * P + p] = dp2;
-    // model_cost_change = -sum (J d) . (r + J d / 2)
-    for (int64_t k = k0; k < k1; ++k) {
-      const int b = d.cam_block[d.obs_cam[k]];
-#pragma unroll
-      for (int row = 0; row < 2; ++row) {
-        double m = d.Jp[(3 * row) * K + k] * dp0 + d.Jp[(3 * row + 1) * K + k] * dp1 +
-                   d.Jp[(3 * row + 2) * K + k] * dp2;
-        if (b >= 0) {
-#pragma unroll
-          for (int a = 0; a < 6; ++a) m += d.Jc[(6 * row + a) * K + k] * d.dc[6 * b + a];
-        }
-        model -= m * (d.r[row * K + k] + 0.5 * m);
-      }
-    }
-    // candidate point
     const double x0 = d.X[3 * (size_t)p], x1 = d.X[3 * (size_t)p + 1], x2 = d.X[3 * (size_t)p + 2];
     const double s0 = dp0 * d.pt_scale[3 * (size_t)p], s1 = dp1 * d.pt_scale[3 * (size_t)p + 1];
     const double s2 = dp2 * d.pt_scale[3 * (size_t)p + 2];
@@ -478,14 +471,34 @@ ba_backsub_kernel(BaDev d, double* __restrict__ partials, int stride) {
       x_sq = x0 * x0 + x1 * x1 + x2 * x2;
     }
   }
-  const double tm = block_sum(model, red);
   const double ts = block_sum(step_sq, red);
   const double tx = block_sum(x_sq, red);
   if (threadIdx.x == 0) {
-    partials[blockIdx.x] = tm;
     partials[stride + blockIdx.x] = ts;
     partials[2 * stride + blockIdx.x] = tx;
   }
+}
+
+// (3) one thread per observation: model_cost_change = -sum (J d) . (r + J d / 2)
+__global__ void __launch_bounds__(kThreads)
+ba_model_cost_kernel(BaDev d, double* __restrict__ partials) {
+  __shared__ double red[32];
+  const int64_t K = d.K;
+  const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  double model = 0.0;
+  if (k < K) {
+    const int p = d.obs_pt[k];
+    const int P = d.P;
+    const double dp0 = d.dp[p], dp1 = d.dp[P + p], dp2 = d.dp[2 * P + p];
+#pragma unroll
+    for (int row = 0; row < 2; ++row) {
+      const double m = d.u[row * K + k] + d.Jp[(3 * row) * K + k] * dp0 +
+                       d.Jp[(3 * row + 1) * K + k] * dp1 + d.Jp[(3 * row + 2) * K + k] * dp2;
+      model -= m * (d.r[row * K + k] + 0.5 * m);
+    }
+  }
+  const double tm = block_sum(model, red);
+  if (threadIdx.x == 0) partials[blockIdx.x] = tm;
 }
 
 // ceres::QuaternionParameterization::Plus
@@ -641,15 +654,19 @@ int launch_backsubstitute_and_update(const BaDev& d, cudaStream_t s) {
   int n = 0;
   ba_camera_update_kernel<<<1, kThreads, 0, s>>>(d);
   ++n;
-  const int blocks = (d.P + kThreads - 1) / kThreads;
-  if (blocks > 0) {
-    ba_backsub_kernel<<<blocks, kThreads, 0, s>>>(d, d.partials, d.num_partials);
-    // model change overwrites, step / x norms accumulate on top of the camera part
-    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
-                                              kModelChange, 0);
-    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials + d.num_partials, blocks,
+  const int pblocks = (d.P + kThreads - 1) / kThreads;
+  const int oblocks = (int)((d.K + kThreads - 1) / kThreads);
+  if (pblocks > 0 && oblocks > 0) {
+    cudaMemcpyAsync(d.dp, d.gp, sizeof(double) * 3 * (size_t)d.P, cudaMemcpyDeviceToDevice, s);
+    ba_backsub_accum_kernel<<<oblocks, kThreads, 0, s>>>(d);
+    ba_point_step_kernel<<<pblocks, kThreads, 0, s>>>(d, d.partials, d.num_partials);
+    // step / x norms accumulate on top of the camera part written by ba_camera_update_kernel
+    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials + d.num_partials, pblocks,
                                               d.num_partials, 2, d.scalars, kStepSq, 1);
-    n += 3;
+    ba_model_cost_kernel<<<oblocks, kThreads, 0, s>>>(d, d.partials);
+    reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, oblocks, d.num_partials, 1, d.scalars,
+                                              kModelChange, 0);
+    n += 5;
   } else {
     cudaMemsetAsync(d.scalars + kModelChange, 0, sizeof(double), s);
   }

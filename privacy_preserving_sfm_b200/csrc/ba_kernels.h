@@ -46,6 +46,7 @@ struct BaDev {
   double* S = nullptr;    // [ld][ld] bordered reduced camera matrix (row n = rhs)
   double* dc = nullptr;   // [n]
   double* dp = nullptr;   // [3][P]
+  double* u = nullptr;    // [2][K] J_c dc per observation (back-substitution scratch)
   int* chol_status = nullptr;
   // reductions
   double* partials = nullptr;  // scratch for block partial sums

@@ -21,77 +21,77 @@ namespace ppsfm {
 
 constexpr int NB = 64;
 
-// Unblocked Cholesky of a 64x64 block held in shared memory (row-major, stride NB+1).
-// 256 threads.  Returns via *ok (shared) whether all pivots were positive.
-__device__ void factor_diag_smem(double (*D)[NB + 1], int kb, int* ok) {
-  const int tid = threadIdx.x;
-  for (int j = 0; j < kb; ++j) {
-    __syncthreads();
-    const double d = D[j][j];
-    if (tid == 0 && !(d > 0.0)) *ok = 0;
-    const double sd = sqrt(d > 0.0 ? d : 1.0);
-    __syncthreads();
-    // scale column j
-    for (int i = j + tid; i < kb; i += blockDim.x) D[i][j] = (i == j) ? sd : D[i][j] / sd;
-    __syncthreads();
-    // rank-1 update of the trailing lower part
-    const int rem = kb - j - 1;
-    for (int idx = tid; idx < rem * rem; idx += blockDim.x) {
-      const int r = j + 1 + idx / rem, c = j + 1 + idx % rem;
-      if (c <= r) D[r][c] -= D[r][j] * D[c][j];
-    }
-  }
-  __syncthreads();
-}
-
-// Panel step k: rows of tile `blockIdx.x + first_tile` (below the diagonal block), or the
-// diagonal block itself for the CTA that owns it (blockIdx.x == 0 writes it back).
-__global__ void __launch_bounds__(256)
+// Panel step, 64 threads per CTA, thread r owns matrix row r in REGISTERS (fully unrolled):
+//   1. every CTA re-factors the 64x64 diagonal block (left-looking; row j is broadcast from shared
+//      memory, 4 independent accumulators hide the DFMA latency) — cheaper than a launch + sync;
+//   2. X L^T = A for its own 64-row tile by per-row forward substitution (no synchronisation).
+// A partial last block is padded with the identity.  CTA 0 writes the factored block back.
+__global__ void __launch_bounds__(NB)
 chol_panel_kernel(double* __restrict__ A, int ld, int n, int k0, int* __restrict__ status) {
-  extern __shared__ __align__(16) double dyn_smem[];
-  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);
-  double (*T)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));
+  __shared__ double D[NB][NB + 1];
   __shared__ int ok;
-  const int tid = threadIdx.x;
+  const int r = threadIdx.x;
   const int kb = min(NB, n - k0);
-  if (tid == 0) ok = 1;
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx % NB;
-    D[r][c] = (r < kb && c < kb && c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  factor_diag_smem(D, kb, &ok);
-  if (blockIdx.x == 0) {
-    for (int idx = tid; idx < kb * kb; idx += blockDim.x) {
-      const int r = idx / kb, c = idx % kb;
-      if (c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = D[r][c];
-    }
-    if (tid == 0 && !ok) atomicExch(status, 1);
-  }
-  // my row tile: rows r0 .. r0+63 (all < ld), columns k0 .. k0+kb-1
   const int r0 = k0 + kb + blockIdx.x * NB;
-  if (r0 >= ld) return;
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx % NB;
-    T[r][c] = (c < kb && r0 + r < ld) ? A[(size_t)(r0 + r) * ld + k0 + c] : 0.0;
-  }
-  __syncthreads();
-  // X L^T = T  -> forward substitution along the columns, 4 threads per row
+  if (r == 0) ok = 1;
+  double drow[NB];
   {
-    const int r = tid >> 2, q = tid & 3;
-    for (int j = 0; j < kb; ++j) {
-      double s = 0.0;
-      for (int p = q; p < j; p += 4) s += T[r][p] * D[j][p];
-      s += __shfl_xor_sync(0xffffffffu, s, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2);
-      if (q == 0) T[r][j] = (T[r][j] - s) / D[j][j];
-      __syncwarp();
-    }
+    const double* src = A + (size_t)(k0 + r) * ld + k0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      drow[c] = (r < kb) ? ((c <= r) ? src[c] : 0.0) : ((c == r) ? 1.0 : 0.0);
   }
   __syncthreads();
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx % NB;
-    if (c < kb && r0 + r < ld) A[(size_t)(r0 + r) * ld + k0 + c] = T[r][c];
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int p = 0; p < j; ++p) acc[p & 3] += drow[p] * D[j][p];
+    double sj = drow[j] - ((acc[0] + acc[1]) + (acc[2] + acc[3]));
+    if (r == j) {
+      if (!(sj > 0.0)) {
+        ok = 0;
+        sj = 1.0;
+      }
+      drow[j] = sqrt(sj);
+      D[j][j] = drow[j];
+    }
+    __syncthreads();
+    if (r > j) {
+      drow[j] = sj / D[j][j];
+      D[r][j] = drow[j];
+    }
+    __syncthreads();
+  }
+  if (blockIdx.x == 0) {
+    if (r < kb) {
+      double* dst = A + (size_t)(k0 + r) * ld + k0;
+#pragma unroll
+      for (int c = 0; c < NB; ++c)
+        if (c <= r) dst[c] = drow[c];
+    }
+    if (r == 0 && !ok) atomicExch(status, 1);
+  }
+  if (r0 >= ld) return;
+  const bool live = r0 + r < ld;
+  double trow[NB];
+  {
+    const double* src = A + (size_t)(r0 + (live ? r : 0)) * ld + k0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c) trow[c] = (live && c < kb) ? src[c] : 0.0;
+  }
+#pragma unroll
+  for (int j = 0; j < NB; ++j) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+    for (int p = 0; p < j; ++p) acc[p & 3] += trow[p] * D[j][p];
+    trow[j] = (trow[j] - ((acc[0] + acc[1]) + (acc[2] + acc[3]))) / D[j][j];
+  }
+  if (live) {
+    double* dst = A + (size_t)(r0 + r) * ld + k0;
+#pragma unroll
+    for (int c = 0; c < NB; ++c)
+      if (c < kb) dst[c] = trow[c];
   }
 }
 
@@ -147,44 +147,48 @@ chol_update_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_til
   }
 }
 
-// Backward substitution step for block k (descending): every CTA re-solves
-// x_k = L_kk^-T y_k in shared memory; CTA j < k applies y_j -= L[k][j]^T x_k, CTA k stores x_k.
-__global__ void __launch_bounds__(256)
-chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, int k0, double* __restrict__ y) {
+// Backward substitution L^T x = y in ONE persistent CTA: for each 64-block from the bottom,
+// warp 0 solves the diagonal block column by column (no reductions: after x_i is known the
+// remaining entries are updated), then all 1024 threads apply y[0:k0] -= L[k0:k0+kb, 0:k0]^T x_k
+// with coalesced reads of the L rows.
+__global__ void __launch_bounds__(1024)
+chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ y) {
   __shared__ double D[NB][NB + 1];
   __shared__ double xk[NB];
   const int tid = threadIdx.x;
-  const int kb = min(NB, n - k0);
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx % NB;
-    D[r][c] = (r < kb && c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-  }
-  if (tid < NB) xk[tid] = (tid < kb) ? y[k0 + tid] : 0.0;
-  __syncthreads();
-  if (tid < 32) {  // one warp: sequential over rows from the bottom
-    for (int i = kb - 1; i >= 0; --i) {
-      double s = 0.0;
-      for (int p = i + 1 + tid; p < kb; p += 32) s += D[p][i] * xk[p];
-#pragma unroll
-      for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
-      if (tid == 0) xk[i] = (xk[i] - s) / D[i][i];
-      __syncwarp();
+  const int nblk = (n + NB - 1) / NB;
+  for (int b = nblk - 1; b >= 0; --b) {
+    const int k0 = b * NB;
+    const int kb = min(NB, n - k0);
+    for (int idx = tid; idx < NB * NB; idx += 1024) {
+      const int r = idx >> 6, c = idx & 63;
+      D[r][c] = (r < kb && c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
     }
-  }
-  __syncthreads();
-  const int j = blockIdx.x;  // tile column (0 .. k0/NB), the last one stores x_k
-  if (j * NB == k0) {
+    if (tid < NB) xk[tid] = (tid < kb) ? y[k0 + tid] : 0.0;
+    __syncthreads();
+    if (tid < 32) {
+      double v0 = xk[tid], v1 = xk[tid + 32];  // lane owns entries tid and tid + 32
+      for (int i = kb - 1; i >= 0; --i) {
+        const double mine = (i < 32) ? v0 : v1;
+        const double xi = __shfl_sync(0xffffffffu, mine, i & 31) / D[i][i];
+        if (tid == (i & 31)) { if (i < 32) v0 = xi; else v1 = xi; }
+        if (tid < i) v0 -= D[i][tid] * xi;
+        if (tid + 32 < i) v1 -= D[i][tid + 32] * xi;
+      }
+      xk[tid] = v0;
+      xk[tid + 32] = v1;
+    }
+    __syncthreads();
     if (tid < kb) y[k0 + tid] = xk[tid];
-    return;
+    for (int c = tid; c < k0; c += 1024) {
+      double s = 0.0;
+      const double* col = A + (size_t)k0 * ld + c;
+#pragma unroll 8
+      for (int r = 0; r < kb; ++r) s += col[(size_t)r * ld] * xk[r];
+      y[c] -= s;
+    }
+    __syncthreads();
   }
-  // y_j[c] -= sum_r L[k0 + r][j*NB + c] * xk[r]
-  const int c = tid & 63, part = tid >> 6;  // 4 partial sums per column
-  double s = 0.0;
-  for (int r = part; r < kb; r += 4) s += A[(size_t)(k0 + r) * ld + j * NB + c] * xk[r];
-  __shared__ double red[4][NB];
-  red[part][c] = s;
-  __syncthreads();
-  if (part == 0) y[j * NB + c] -= red[0][c] + red[1][c] + red[2][c] + red[3][c];
 }
 
 __global__ void chol_extract_y_kernel(const double* __restrict__ A, int ld, int n,
@@ -198,12 +202,9 @@ int chol_ld(int n) { return ((n + 1 + NB - 1) / NB) * NB; }
 // Factor + solve.  A: ld x ld (see header).  x: n doubles (device).  status: device int, set to
 // 1 if a non-positive pivot was met.  Asynchronous on `s`; returns the number of launches.
 int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaStream_t s) {
-  constexpr int kPanelSmem = 2 * NB * (NB + 1) * (int)sizeof(double);
   constexpr int kUpdateSmem = 2 * NB * (NB + 4) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(chol_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kPanelSmem);
     cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kUpdateSmem);
     attr_set = true;
@@ -216,7 +217,7 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaSt
     // row tiles below the diagonal block (they include the rhs row); for the last, partial
     // block the remaining rows (rhs + padding) start unaligned and fit in one guarded tile
     const int tiles = (ld - r0 + NB - 1) / NB;
-    chol_panel_kernel<<<tiles > 0 ? tiles : 1, 256, kPanelSmem, s>>>(A, ld, n, k0, status);
+    chol_panel_kernel<<<tiles > 0 ? tiles : 1, NB, 0, s>>>(A, ld, n, k0, status);
     ++launches;
     if (r0 < ld && kb == NB) {
       const int nt = (ld - r0) / NB;
@@ -229,11 +230,8 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaSt
   }
   chol_extract_y_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, ld, n, x);
   ++launches;
-  const int nblk = (n + NB - 1) / NB;
-  for (int b = nblk - 1; b >= 0; --b) {
-    chol_backsolve_kernel<<<b + 1, 256, 0, s>>>(A, ld, n, b * NB, x);
-    ++launches;
-  }
+  chol_backsolve_kernel<<<1, 1024, 0, s>>>(A, ld, n, x);
+  ++launches;
   return launches;
 }
 

@@ -1,0 +1,183 @@
+// adaptor_test.cc — exercises the header-only C++ adaptor (privacy_preserving_sfm_b200/cpp/
+// ppsfm_adaptor.h) the way IncrementalMapper uses the reference API
+// (src/sfm/incremental_mapper.cc:673-735, 907-930).  Inputs / outputs are flat binary files so
+// that the pytest driver can compare against the CPU oracle.
+//   adaptor_test pose <in.bin> <out.bin>
+//   adaptor_test ba   <in.bin> <out.bin>
+#include <cstdio>
+#include <cmath>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "ppsfm_adaptor.h"
+
+using namespace ppsfm;
+
+static std::vector<double> ReadDoubles(FILE* f, size_t n) {
+  std::vector<double> v(n);
+  if (n && fread(v.data(), sizeof(double), n, f) != n) std::abort();
+  return v;
+}
+static int64_t ReadI64(FILE* f) {
+  int64_t v;
+  if (fread(&v, sizeof(v), 1, f) != 1) std::abort();
+  return v;
+}
+
+// --- minimal stand-ins for colmap::Camera / Image / Point3D / Track / Reconstruction ------------
+struct TestCamera {
+  int model_id = 1;
+  std::vector<double> params;
+  int ModelId() const { return model_id; }
+  size_t NumParams() const { return params.size(); }
+  const double* ParamsData() const { return params.data(); }
+  double* ParamsData() { return params.data(); }
+};
+struct TestImage {
+  camera_t camera_id = 1;
+  Vector4d qvec{};
+  Vector3d tvec{};
+  FeatureLines lines;
+  camera_t CameraId() const { return camera_id; }
+  void NormalizeQvec() {
+    double n = 0;
+    for (int k = 0; k < 4; ++k) n += qvec[k] * qvec[k];
+    n = std::sqrt(n);
+    if (n > 0) for (int k = 0; k < 4; ++k) qvec[k] /= n;
+  }
+  Vector4d& Qvec() { return qvec; }
+  Vector3d& Tvec() { return tvec; }
+  const FeatureLines& Lines() const { return lines; }
+};
+struct TrackElement { image_t image_id; uint32_t line_idx; };
+struct TestTrack {
+  std::vector<TrackElement> elements;
+  size_t Length() const { return elements.size(); }
+  const std::vector<TrackElement>& Elements() const { return elements; }
+};
+struct TestPoint3D {
+  Vector3d xyz{};
+  TestTrack track;
+  Vector3d& XYZ() { return xyz; }
+  TestTrack& Track() { return track; }
+};
+struct TestReconstruction {
+  std::unordered_map<camera_t, TestCamera> cameras;
+  std::unordered_map<image_t, TestImage> images;
+  std::unordered_map<point3D_t, TestPoint3D> points;
+  TestCamera& Camera(camera_t id) { return cameras.at(id); }
+  TestImage& Image(image_t id) { return images.at(id); }
+  TestPoint3D& Point3D(point3D_t id) { return points.at(id); }
+};
+
+static int RunPose(const char* in, const char* out) {
+  FILE* f = fopen(in, "rb");
+  if (!f) return 2;
+  const size_t n = (size_t)ReadI64(f);
+  const std::vector<double> lines = ReadDoubles(f, 3 * n), pts = ReadDoubles(f, 3 * n),
+                            al = ReadDoubles(f, n);
+  fclose(f);
+  FeatureLines lines2D(n);
+  std::vector<Vector3d> points3D(n);
+  for (size_t i = 0; i < n; ++i) {
+    lines2D[i] = FeatureLine(Vector3d{lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]}, al[i] != 0);
+    points3D[i] = Vector3d{pts[3 * i], pts[3 * i + 1], pts[3 * i + 2]};
+  }
+  // mapper options, src/sfm/incremental_mapper.cc:673-681
+  RANSACOptions options;
+  options.max_error = 12.0 / 1000.0;
+  options.min_inlier_ratio = 0.25;
+  options.min_num_trials = 100;
+  options.max_num_trials = 10000;
+  options.confidence = 0.99999;
+  SetPRNGSeed(0);
+  Vector4d qvec;
+  Vector3d tvec;
+  size_t num_inliers = 0;
+  std::vector<char> mask;
+  const bool ok = EstimateAbsolutePoseFromLines(options, lines2D, points3D, &qvec, &tvec,
+                                                &num_inliers, &mask);
+  Vector4d q_ref = qvec;
+  Vector3d t_ref = tvec;
+  bool ok_ref = false;
+  if (ok) {
+    std::vector<Vector3d> l3(n);
+    for (size_t i = 0; i < n; ++i) l3[i] = lines2D[i].Line();
+    TestCamera cam;
+    cam.params = {1000.0, 1000.0, 500.0, 500.0};
+    AbsolutePoseRefinementOptions ro;
+    ro.print_summary = false;
+    ok_ref = RefineAbsolutePoseFromLines(ro, mask, l3, points3D, &q_ref, &t_ref, &cam);
+  }
+  // also the estimator concept on the first 6 correspondences
+  std::vector<FeatureLine> x6(lines2D.begin(), lines2D.begin() + 6);
+  std::vector<Vector3d> y6(points3D.begin(), points3D.begin() + 6);
+  const std::vector<Matrix3x4d> models = P6LEstimator::Estimate(x6, y6);
+  FILE* g = fopen(out, "wb");
+  const double hdr[4] = {ok ? 1.0 : 0.0, (double)num_inliers, ok_ref ? 1.0 : 0.0, (double)models.size()};
+  fwrite(hdr, sizeof(double), 4, g);
+  fwrite(qvec.data(), sizeof(double), 4, g);
+  fwrite(tvec.data(), sizeof(double), 3, g);
+  fwrite(q_ref.data(), sizeof(double), 4, g);
+  fwrite(t_ref.data(), sizeof(double), 3, g);
+  std::vector<double> m(n, 0.0);
+  for (size_t i = 0; i < mask.size(); ++i) m[i] = mask[i] ? 1.0 : 0.0;
+  fwrite(m.data(), sizeof(double), n, g);
+  fclose(g);
+  return 0;
+}
+
+static int RunBA(const char* in, const char* out) {
+  FILE* f = fopen(in, "rb");
+  if (!f) return 2;
+  const int C = (int)ReadI64(f), P = (int)ReadI64(f);
+  const int64_t O = ReadI64(f);
+  const std::vector<double> q = ReadDoubles(f, 4 * C), t = ReadDoubles(f, 3 * C),
+                            X = ReadDoubles(f, 3 * P), oc = ReadDoubles(f, O), op = ReadDoubles(f, O),
+                            ol = ReadDoubles(f, 3 * O), cam = ReadDoubles(f, 4);
+  fclose(f);
+  TestReconstruction rec;
+  rec.cameras[1].params = cam;
+  for (int i = 0; i < C; ++i) {
+    TestImage& im = rec.images[i + 1];
+    im.qvec = Vector4d{q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]};
+    im.tvec = Vector3d{t[3 * i], t[3 * i + 1], t[3 * i + 2]};
+  }
+  for (int p = 0; p < P; ++p) rec.points[p + 100].xyz = Vector3d{X[3 * p], X[3 * p + 1], X[3 * p + 2]};
+  for (int64_t o = 0; o < O; ++o) {
+    TestImage& im = rec.images[(image_t)oc[o] + 1];
+    const point3D_t pid = (point3D_t)op[o] + 100;
+    im.lines.emplace_back(Vector3d{ol[3 * o], ol[3 * o + 1], ol[3 * o + 2]}, false, pid);
+    rec.points[pid].track.elements.push_back({(image_t)oc[o] + 1, (uint32_t)im.lines.size() - 1});
+  }
+  // IncrementalMapper::AdjustGlobalBundle (src/sfm/incremental_mapper.cc:893-939)
+  BundleAdjustmentOptions options;
+  options.solver_options.max_num_iterations = 20;
+  options.solver_options.gradient_tolerance = 1e-4;
+  options.print_summary = false;
+  BundleAdjustmentConfig config;
+  for (int i = 0; i < C; ++i) config.AddImage(i + 1);
+  config.SetConstantPose(1);
+  config.SetConstantTvec(2, {0});
+  BundleAdjuster<TestReconstruction> adjuster(options, config);
+  const bool ok = adjuster.Solve(&rec);
+  FILE* g = fopen(out, "wb");
+  const double hdr[4] = {ok ? 1.0 : 0.0, adjuster.Summary().initial_cost,
+                         adjuster.Summary().final_cost,
+                         (double)(adjuster.Summary().num_successful_steps +
+                                  adjuster.Summary().num_unsuccessful_steps)};
+  fwrite(hdr, sizeof(double), 4, g);
+  for (int i = 0; i < C; ++i) fwrite(rec.images[i + 1].qvec.data(), sizeof(double), 4, g);
+  for (int i = 0; i < C; ++i) fwrite(rec.images[i + 1].tvec.data(), sizeof(double), 3, g);
+  for (int p = 0; p < P; ++p) fwrite(rec.points[p + 100].xyz.data(), sizeof(double), 3, g);
+  fclose(g);
+  return 0;
+}
+
+int main(int argc, char** argv) {
+  if (argc != 4) return 1;
+  if (std::string(argv[1]) == "pose") return RunPose(argv[2], argv[3]);
+  if (std::string(argv[1]) == "ba") return RunBA(argv[2], argv[3]);
+  return 1;
+}

@@ -119,7 +119,7 @@ def _compare_solutions(a, b, s, s2, tol_pose=1e-8, tol_cost=1e-9):
 def test_ba_solve_matches_oracle(ctx, oracle, loss, scale):
     sc = _scene(num_cams=10, num_points=400, obs=5, seed=21)
     a, b = _both(oracle, sc, pose_flags=_gauge_flags(10))
-    kw = dict(loss_type=loss, loss_scale=scale, max_num_iterations=30, gradient_tolerance=1e-6)
+    kw = dict(loss_type=loss, loss_scale=scale, max_num_iterations=30, gradient_tolerance=1e-2)
     ok, s = ba.solve_arrays(ctx, a, ba.default_solver_options(**kw))
     ok2, s2 = oracle.ba_solve(b, oracle.ba_default_options(num_threads=1, **kw))
     assert ok and ok2
