@@ -256,6 +256,27 @@ int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
                        double* jac_point, double* cost);
 int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const double* b, double* x);
 
+/* =============================================================================================
+ * Multi-GPU (one process / context per GPU).  The only data-path collective of the path is the
+ * all-reduce of the reduced camera system in bundle adjustment: points are dealt
+ * round-robin to ranks (p % world == rank, with all their observations), cameras are replicated,
+ * every LM iteration all-reduces U, g_c, the bordered reduced matrix and four scalars over
+ * NCCL / NVLink; the dense solve is replicated.  After ppsfm_comm_init every ppsfm_ba_* call on
+ * that context is collective: all ranks pass the SAME problem and get the same result back.
+ * The 128-byte id comes from rank 0 (ppsfm_comm_get_unique_id) and is distributed by the host
+ * application (torch.distributed / MPI / a file).
+ * ============================================================================================= */
+int ppsfm_comm_get_unique_id(ppsfm_ctx* ctx, char* id128);
+int ppsfm_comm_init(ppsfm_ctx* ctx, int world_size, int rank, const char* id128);
+void ppsfm_comm_destroy(ppsfm_ctx* ctx);
+int ppsfm_comm_rank(const ppsfm_ctx* ctx);
+int ppsfm_comm_world_size(const ppsfm_ctx* ctx);
+/* in-place sum all-reduce of a host buffer (staged through HBM); test / bench helper */
+int ppsfm_comm_allreduce_sum_host(ppsfm_ctx* ctx, double* host, size_t count);
+/* host-only shard accounting: out[4] = {kept observations on `rank`, owned points with
+ * observations, camera blocks, kept observations in total} */
+int ppsfm_ba_shard_stats(const ppsfm_ba_problem* problem, int rank, int world, int64_t* out);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

@@ -117,6 +117,13 @@ def load_library():
                                             C.POINTER(RansacReport), _u8p]
     L.ppsfm_get_ransac_timing.argtypes = [vp, C.POINTER(RansacTiming)]
     L.ppsfm_get_ransac_timing.restype = None
+    L.ppsfm_comm_get_unique_id.argtypes = [vp, C.c_char_p]
+    L.ppsfm_comm_init.argtypes = [vp, C.c_int, C.c_int, C.c_char_p]
+    L.ppsfm_comm_destroy.argtypes = [vp]
+    L.ppsfm_comm_destroy.restype = None
+    L.ppsfm_comm_rank.argtypes = [vp]
+    L.ppsfm_comm_world_size.argtypes = [vp]
+    L.ppsfm_comm_allreduce_sum_host.argtypes = [vp, _dp, C.c_size_t]
     L.ppsfm_bench_fp64_peak.argtypes = [vp, _dp, _dp]
     L.ppsfm_bench_l2_flush.argtypes = [vp, C.c_size_t]
     _lib = L
@@ -265,6 +272,34 @@ class Context:
             t.ctypes.data_as(_dp), C.byref(ninl), mask.ctypes.data_as(_u8p), C.byref(rep)),
             allow_no_solution=True)
         return rc == PPSFM_OK, q, t, int(ninl.value), mask, rep
+
+    # -- multi-GPU ---------------------------------------------------------------------------
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        self._check(self._L.ppsfm_comm_get_unique_id(self._h, buf))
+        return buf.raw
+
+    def comm_init(self, world_size, rank, unique_id):
+        self._check(self._L.ppsfm_comm_init(self._h, world_size, rank, unique_id))
+
+    def comm_init_from_torch(self, dist):
+        """Initialises the NCCL communicator of this context from an initialised
+        torch.distributed process group (any backend): rank 0's id is broadcast as an object."""
+        rank, world = dist.get_rank(), dist.get_world_size()
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        self.comm_init(world, rank, box[0])
+
+    def comm_rank(self):
+        return int(self._L.ppsfm_comm_rank(self._h))
+
+    def comm_world_size(self):
+        return int(self._L.ppsfm_comm_world_size(self._h))
+
+    def comm_allreduce_sum(self, array):
+        a = np.ascontiguousarray(array, dtype=np.float64).copy()
+        self._check(self._L.ppsfm_comm_allreduce_sum_host(self._h, a.ctypes.data_as(_dp), a.size))
+        return a
 
     def bench_fp64_peak(self):
         a, b = C.c_double(), C.c_double()

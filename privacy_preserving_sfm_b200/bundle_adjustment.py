@@ -98,6 +98,8 @@ def _lib():
         L.ppsfm_ba_linearize.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOptions), _dp, _dp,
                                          _dp, _dp]
         L.ppsfm_dense_cholesky_solve.argtypes = [vp, _dp, C.c_int, _dp, _dp]
+        L.ppsfm_ba_shard_stats.argtypes = [C.POINTER(BaProblem), C.c_int, C.c_int,
+                                           C.POINTER(C.c_int64)]
         _ready = True
     return L
 
@@ -205,6 +207,15 @@ def linearize_arrays(ctx, arrays, solver_options):
                                          r.ctypes.data_as(_dp), jc.ctypes.data_as(_dp),
                                          jp.ctypes.data_as(_dp), C.byref(cost)))
     return r, jc, jp, float(cost.value)
+
+
+def shard_stats(arrays, rank, world):
+    """Host-only: (kept observations on `rank`, owned points, camera blocks, kept obs in total)."""
+    out = (C.c_int64 * 4)()
+    rc = _lib().ppsfm_ba_shard_stats(C.byref(arrays.struct), rank, world, out)
+    if rc != 0:
+        raise PpsfmError(f"ppsfm_ba_shard_stats rc={rc}")
+    return tuple(int(v) for v in out)
 
 
 def dense_cholesky_solve(ctx, A, b):

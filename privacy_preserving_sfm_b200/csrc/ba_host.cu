@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "ba_kernels.h"
+#include "comm.h"
 #include "common.h"
 #include "dense_chol.h"
 
@@ -391,7 +392,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     // --- reduced camera system + dense Cholesky
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[0], s));
     st->launches += launch_build_reduced_system(d, radius, opt.min_lm_diagonal,
-                                                opt.max_lm_diagonal, s);
+                                                opt.max_lm_diagonal, st->rank == 0, s);
     if (st->world > 1) {
       // rank 0 contributed blockdiag(U + D) and -g_c; every rank its points' Schur products
       rc = AllReduceSum(st, d.S, (size_t)d.ld * (d.n + 1));
@@ -405,7 +406,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
                                       cudaMemcpyDeviceToHost, s));
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[2], s));
-    st->launches += launch_backsubstitute_and_update(d, s);
+    st->launches += launch_backsubstitute_and_update(d, st->rank == 0, s);
     if (st->world > 1) {
       rc = AllReduceSum(st, d.scalars + kModelChange, 3);  // model change, step^2, x^2
       if (rc != PPSFM_OK) return rc;
@@ -507,6 +508,14 @@ int BaDownload(BaState* st, const ppsfm_ba_problem* pb) {
   // poses of every image (constant ones come back unchanged); points owned by this rank
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->qvecs, d.q, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToHost, s));
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->tvecs, d.t, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToHost, s));
+  if (st->world > 1) {
+    // every rank moved only its own points: sum the displacements so that all ranks return the
+    // complete point set (X = X0 + sum_r (X_r - X0))
+    launch_axpby(d.Xn, d.X, st->X0, -1.0, 3 * (size_t)d.P, s);
+    const int rc = CommAllReduce(ctx, d.Xn, 3 * (size_t)d.P, false);
+    if (rc != PPSFM_OK) return rc;
+    launch_axpby(d.X, st->X0, d.Xn, 1.0, 3 * (size_t)d.P, s);
+  }
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->points, d.X, sizeof(double) * 3 * d.P, cudaMemcpyDeviceToHost, s));
   PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
   return PPSFM_OK;
@@ -524,11 +533,11 @@ int BaReset(BaState* st) {
 }
 
 namespace {
-int AllReduceSum(BaState* st, double*, size_t) {
-  return fail(st->ctx, PPSFM_ERR_NCCL, "multi-GPU BA requires ppsfm_comm_init (not initialised)");
+int AllReduceSum(BaState* st, double* dev, size_t count) {
+  return CommAllReduce(st->ctx, dev, count, false);
 }
-int AllReduceMax(BaState* st, double*, size_t) {
-  return fail(st->ctx, PPSFM_ERR_NCCL, "multi-GPU BA requires ppsfm_comm_init (not initialised)");
+int AllReduceMax(BaState* st, double* dev, size_t count) {
+  return CommAllReduce(st->ctx, dev, count, true);
 }
 }  // namespace
 
@@ -540,8 +549,6 @@ int AllReduceMax(BaState* st, double*, size_t) {
 using namespace ppsfm;
 
 extern "C" {
-
-void ppsfm_ba_state_free(ppsfm_ctx* ctx) { (void)ctx; }
 
 void ppsfm_ba_options_default(ppsfm_ba_options* o) {
   if (!o) return;
@@ -568,7 +575,7 @@ int ppsfm_ba_create(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
   if (!ctx) return PPSFM_ERR_INVALID;
   cudaSetDevice(ctx->device);
   BaState* st = nullptr;
-  const int rc = BaCreate(ctx, problem, options, 0, 1, &st);
+  const int rc = BaCreate(ctx, problem, options, ctx->rank, ctx->world, &st);
   if (out) *out = reinterpret_cast<ppsfm_ba*>(st);
   return rc;
 }
@@ -613,6 +620,35 @@ int ppsfm_ba_solve(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
   }
   ppsfm_ba_free(ba);
   return rc;
+}
+
+// Host-only: how a problem is dealt to `rank` of `world` ranks (no GPU needed; used by the
+// world_size-2 gloo tests).  out = {kept observations on this rank, points owned by this rank
+// that have kept observations, camera blocks (identical on every rank), kept observations in total}.
+int ppsfm_ba_shard_stats(const ppsfm_ba_problem* pb, int rank, int world, int64_t* out) {
+  if (!pb || !out || world < 1 || rank < 0 || rank >= world) return PPSFM_ERR_INVALID;
+  const int C = pb->num_images, P = pb->num_points;
+  std::vector<uint8_t> cam_used(C, 0), pt_has(P, 0);
+  int64_t local = 0, total = 0;
+  for (int64_t o = 0; o < pb->num_obs; ++o) {
+    const int ci = pb->obs_image[o], pi = pb->obs_point[o];
+    if (ci < 0 || ci >= C || pi < 0 || pi >= P) return PPSFM_ERR_INVALID;
+    const bool cc = pb->pose_flags && (pb->pose_flags[ci] & 1);
+    const bool pc = pb->point_const && pb->point_const[pi];
+    if (cc && pc) continue;
+    cam_used[ci] = 1;
+    ++total;
+    if (world == 1 || (pi % world) == rank) {
+      ++local;
+      pt_has[pi] = 1;
+    }
+  }
+  int64_t blocks = 0, pts = 0;
+  for (int i = 0; i < C; ++i)
+    if (cam_used[i] && !(pb->pose_flags && (pb->pose_flags[i] & 1))) ++blocks;
+  for (int i = 0; i < P; ++i) pts += pt_has[i];
+  out[0] = local; out[1] = pts; out[2] = blocks; out[3] = total;
+  return PPSFM_OK;
 }
 
 // Test hook: residuals and tangent-space Jacobian blocks of every observation at the current

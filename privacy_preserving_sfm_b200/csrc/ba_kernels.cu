@@ -517,7 +517,7 @@ __device__ __forceinline__ void quaternion_plus(const double* x, const double* d
 }
 
 // single CTA (cameras are few): candidate poses + camera part of step / x norms
-__global__ void __launch_bounds__(kThreads) ba_camera_update_kernel(BaDev d) {
+__global__ void __launch_bounds__(kThreads) ba_camera_update_kernel(BaDev d, int count_norms) {
   __shared__ double red[32];
   double step_sq = 0.0, x_sq = 0.0;
   for (int i = threadIdx.x; i < d.C; i += kThreads) {
@@ -553,10 +553,16 @@ __global__ void __launch_bounds__(kThreads) ba_camera_update_kernel(BaDev d) {
   }
   const double ts = block_sum(step_sq, red);
   const double tx = block_sum(x_sq, red);
-  if (threadIdx.x == 0) {
-    d.scalars[kStepSq] = ts;
-    d.scalars[kXSq] = tx;
+  if (threadIdx.x == 0) {  // replicated across ranks: only one rank contributes to the sums
+    d.scalars[kStepSq] = count_norms ? ts : 0.0;
+    d.scalars[kXSq] = count_norms ? tx : 0.0;
   }
+}
+
+__global__ void ba_axpby_kernel(double* __restrict__ out, const double* __restrict__ a,
+                                const double* __restrict__ b, double beta, size_t n) {
+  const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
+  if (i < n) out[i] = a[i] + beta * b[i];
 }
 
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
@@ -634,10 +640,10 @@ int launch_jacobi_scales(const BaDev& d, cudaStream_t s) {
 }
 
 int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,
-                                cudaStream_t s) {
+                                bool include_camera_terms, cudaStream_t s) {
   int n = 0;
   cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.ld * d.ld, s);
-  if (d.NB > 0) {
+  if (d.NB > 0 && include_camera_terms) {
     ba_init_reduced_kernel<<<(36 * d.NB + 255) / 256, 256, 0, s>>>(d, radius, min_diag, max_diag);
     ++n;
   }
@@ -650,9 +656,15 @@ int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, 
   return n;
 }
 
-int launch_backsubstitute_and_update(const BaDev& d, cudaStream_t s) {
+void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,
+                  cudaStream_t s) {
+  if (n == 0) return;
+  ba_axpby_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(out, a, b, beta, n);
+}
+
+int launch_backsubstitute_and_update(const BaDev& d, bool count_camera_norms, cudaStream_t s) {
   int n = 0;
-  ba_camera_update_kernel<<<1, kThreads, 0, s>>>(d);
+  ba_camera_update_kernel<<<1, kThreads, 0, s>>>(d, count_camera_norms ? 1 : 0);
   ++n;
   const int pblocks = (d.P + kThreads - 1) / kThreads;
   const int oblocks = (int)((d.K + kThreads - 1) / kThreads);

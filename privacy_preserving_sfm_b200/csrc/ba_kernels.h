@@ -70,10 +70,15 @@ int launch_normal_equations(const BaDev& d, cudaStream_t s);
 // Jacobi scales 1 / (1 + sqrt(diag)) from U, V (computed with unit scales).
 int launch_jacobi_scales(const BaDev& d, cudaStream_t s);
 // S = blockdiag(U + D_c^2) - W (V + D_p^2)^-1 W^T (lower triangle), row n = rhs; stores Vinv.
+// `include_camera_terms` is false on ranks > 0 of a sharded solve (the replicated camera terms
+// must enter the all-reduced sum once).
 int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,
-                                cudaStream_t s);
+                                bool include_camera_terms, cudaStream_t s);
 // dp from dc, model cost change, candidate state, step / x norms (scalars).
-int launch_backsubstitute_and_update(const BaDev& d, cudaStream_t s);
+int launch_backsubstitute_and_update(const BaDev& d, bool count_camera_norms, cudaStream_t s);
+// out = a + beta * b
+void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,
+                  cudaStream_t s);
 // max |x - Plus(x, -g)| over all blocks -> scalars[kGradMax]
 int launch_gradient_max_norm(const BaDev& d, cudaStream_t s);
 

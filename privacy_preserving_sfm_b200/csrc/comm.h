@@ -1,0 +1,10 @@
+// comm.h — NCCL all-reduce on the context's stream (comm.cu).
+#pragma once
+#include <cstddef>
+
+struct ppsfm_ctx;
+
+namespace ppsfm {
+// In-place all-reduce (sum or max) of `count` doubles in device memory; no-op for world == 1.
+int CommAllReduce(ppsfm_ctx* ctx, double* dev, size_t count, bool max_op);
+}  // namespace ppsfm

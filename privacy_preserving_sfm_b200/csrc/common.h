@@ -85,8 +85,9 @@ struct ppsfm_ctx {
       h_K, h_stage;
   ppsfm_ransac_timing timing{};
 
-  // BA state lives in ba.cu (opaque here)
-  void* ba_state = nullptr;
+  // multi-GPU (comm.cu): NCCL communicator, one rank per context
+  void* comm = nullptr;
+  int rank = 0, world = 1;
 };
 
 namespace ppsfm {

@@ -497,13 +497,13 @@ int ppsfm_ctx_create(int device, ppsfm_ctx** out) {
   return PPSFM_OK;
 }
 
-void ppsfm_ba_state_free(ppsfm_ctx* ctx);  // ba_host.cu
+void ppsfm_comm_destroy(ppsfm_ctx* ctx);  // comm.cu
 
 void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
-  ppsfm_ba_state_free(ctx);
+  ppsfm_comm_destroy(ctx);
   ppsfm::DevBuf* dbufs[] = {&ctx->d_samples, &ctx->d_models, &ctx->d_num_models, &ctx->d_cmodels,
                             &ctx->d_msrc, &ctx->d_K, &ctx->d_part_cnt, &ctx->d_part_sum,
                             &ctx->d_cnt, &ctx->d_sum, &ctx->d_eidx, &ctx->d_emodels, &ctx->d_rbuf,

@@ -1,0 +1,116 @@
+"""Multi-GPU path.
+
+CPU (gloo, world_size 2): the host-side sharding of a BA problem — every kept observation lands
+on exactly one rank, camera blocks are identical on all ranks — and the rendezvous helper.
+GPU (-m gpu, needs >= 2 devices): sharded BA over NCCL gives the single-GPU answer."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+_WORKER = r'''
+import os, sys
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+from privacy_preserving_sfm_b200 import bundle_adjustment as ba, synthetic as S
+
+backend = sys.argv[1]
+dist.init_process_group(backend)
+rank, world = dist.get_rank(), dist.get_world_size()
+sc = S.make_ba_scene(num_cams=9, num_points=401, obs_per_point=5, seed=7)
+flags = np.zeros(9, np.uint8); flags[0] = 1; flags[1] = 2; flags[8] = 1
+pc = (np.arange(401) % 11 == 0).astype(np.uint8)
+args = (sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"], sc["obs_line"],
+        [1], [sc["cam_params"]])
+arr = ba.BaArrays(*args, pose_flags=flags, point_const=pc)
+if backend == "gloo":
+    local, pts, blocks, total = ba.shard_stats(arr, rank, world)
+    t = torch.tensor([local, pts, blocks, total], dtype=torch.int64)
+    s = t.clone(); dist.all_reduce(s)
+    mx = t.clone(); dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+    mn = t.clone(); dist.all_reduce(mn, op=dist.ReduceOp.MIN)
+    one = ba.shard_stats(arr, 0, 1)
+    assert s[0].item() == total == one[0], (s, total, one)        # observations partitioned
+    assert s[1].item() == one[1]                                   # points partitioned
+    assert mx[2].item() == mn[2].item() == one[2]                  # same camera blocks everywhere
+    assert abs(local - total / world) < 0.1 * total                # balanced
+    if rank == 0:
+        print("GLOO_OK")
+else:
+    import privacy_preserving_sfm_b200 as pp
+    torch.cuda.set_device(rank)
+    ctx = pp.Context(rank)
+    ctx.comm_init_from_torch(dist)
+    assert (ctx.comm_rank(), ctx.comm_world_size()) == (rank, world)
+    v = ctx.comm_allreduce_sum(np.array([1.0 + rank, 2.0]))
+    assert np.allclose(v, [sum(1.0 + r for r in range(world)), 2.0 * world])
+    kw = dict(max_num_iterations=15, gradient_tolerance=1e-3)
+    ok, s = ba.solve_arrays(ctx, arr, ba.default_solver_options(**kw))
+    np.save(os.path.join(sys.argv[2], f"q{{rank}}.npy"), arr.qvecs)
+    np.save(os.path.join(sys.argv[2], f"t{{rank}}.npy"), arr.tvecs)
+    np.save(os.path.join(sys.argv[2], f"X{{rank}}.npy"), arr.points)
+    np.save(os.path.join(sys.argv[2], f"c{{rank}}.npy"),
+            np.array([s.initial_cost, s.final_cost, s.num_successful_steps, s.num_unsuccessful_steps]))
+    dist.barrier()
+    if rank == 0:
+        print("NCCL_OK")
+dist.destroy_process_group()
+'''
+
+
+def _launch(backend, nproc, tmp_path, extra=()):
+    script = tmp_path / "worker.py"
+    script.write_text(_WORKER.format(root=ROOT))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
+           "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), backend, *extra]
+    return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+
+
+def test_ba_sharding_partitions_the_problem_gloo_world2(tmp_path):
+    r = _launch("gloo", 2, tmp_path)
+    assert r.returncode == 0 and "GLOO_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+
+
+def test_shard_stats_single_process():
+    from privacy_preserving_sfm_b200 import bundle_adjustment as ba, synthetic as S
+    sc = S.make_ba_scene(num_cams=5, num_points=50, obs_per_point=3, seed=1)
+    arr = ba.BaArrays(sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                      sc["obs_line"], [1], [sc["cam_params"]])
+    tot = ba.shard_stats(arr, 0, 1)
+    assert tot == (150, 50, 5, 150)
+    parts = [ba.shard_stats(arr, r, 3) for r in range(3)]
+    assert sum(p[0] for p in parts) == 150 and sum(p[1] for p in parts) == 50
+    assert all(p[2] == 5 and p[3] == 150 for p in parts)
+
+
+@pytest.mark.gpu
+def test_sharded_ba_matches_single_gpu(tmp_path, ctx):
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    from privacy_preserving_sfm_b200 import bundle_adjustment as ba, synthetic as S
+    out = tmp_path / "out"
+    out.mkdir()
+    r = _launch("nccl", 2, tmp_path, extra=(str(out),))
+    assert r.returncode == 0 and "NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    sc = S.make_ba_scene(num_cams=9, num_points=401, obs_per_point=5, seed=7)
+    flags = np.zeros(9, np.uint8)
+    flags[0], flags[1], flags[8] = 1, 2, 1
+    pc = (np.arange(401) % 11 == 0).astype(np.uint8)
+    arr = ba.BaArrays(sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                      sc["obs_line"], [1], [sc["cam_params"]], pose_flags=flags, point_const=pc)
+    ok, s = ba.solve_arrays(ctx, arr, ba.default_solver_options(max_num_iterations=15,
+                                                                gradient_tolerance=1e-3))
+    for rank in range(2):
+        c = np.load(out / f"c{rank}.npy")
+        assert abs(c[1] - s.final_cost) <= 1e-9 * s.final_cost
+        assert (int(c[2]), int(c[3])) == (s.num_successful_steps, s.num_unsuccessful_steps)
+        assert np.abs(np.load(out / f"q{rank}.npy") - arr.qvecs).max() < 1e-8
+        assert np.abs(np.load(out / f"t{rank}.npy") - arr.tvecs).max() < 1e-8
+        assert np.abs(np.load(out / f"X{rank}.npy") - arr.points).max() < 1e-7
