@@ -242,6 +242,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.dp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.u, 2 * (size_t)K));
   BA_TRY(DevAlloc(st, &d.chol_status, 1));
+  BA_TRY(DevAlloc(st, &d.chol_work, chol_work_doubles(6 * NB)));
   d.num_partials = (int)std::max<int64_t>((K + 255) / 256, (P + 255) / 256) + 1;
   BA_TRY(DevAlloc(st, &d.partials, 3 * (size_t)d.num_partials));
   BA_TRY(DevAlloc(st, &d.scalars, kNumScalars));
@@ -401,7 +402,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[1], s));
     int chol_failed = 0;
     if (d.n > 0) {
-      st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_status, s);
+      st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_work, d.chol_status, s);
       PPSFM_CUDA(ctx, cudaMemcpyAsync(&chol_failed, d.chol_status, sizeof(int),
                                       cudaMemcpyDeviceToHost, s));
     }
@@ -730,16 +731,17 @@ int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const dou
   for (int i = 0; i < n; ++i)
     for (int j = 0; j <= i; ++j) h[(size_t)i * ld + j] = A[(size_t)i * n + j];
   for (int j = 0; j < n; ++j) h[(size_t)n * ld + j] = b[j];
-  double *dA = nullptr, *dx = nullptr;
+  double *dA = nullptr, *dx = nullptr, *dwork = nullptr;
   int* dst = nullptr;
   PPSFM_CUDA(ctx, cudaMalloc(&dA, sizeof(double) * h.size()));
+  PPSFM_CUDA(ctx, cudaMalloc(&dwork, sizeof(double) * chol_work_doubles(n)));
   PPSFM_CUDA(ctx, cudaMalloc(&dx, sizeof(double) * n));
   PPSFM_CUDA(ctx, cudaMalloc(&dst, sizeof(int)));
   cudaStream_t s = ctx->stream;
   int status = 0;
   auto body = [&]() -> int {
     PPSFM_CUDA(ctx, cudaMemcpyAsync(dA, h.data(), sizeof(double) * h.size(), cudaMemcpyHostToDevice, s));
-    chol_solve_bordered(dA, n, ld, dx, dst, s);
+    chol_solve_bordered(dA, n, ld, dx, dwork, dst, s);
     PPSFM_CUDA(ctx, cudaMemcpyAsync(x, dx, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(&status, dst, sizeof(int), cudaMemcpyDeviceToHost, s));
     PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
@@ -749,6 +751,7 @@ int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const dou
   int rc = body();
   cudaFree(dA);
   cudaFree(dx);
+  cudaFree(dwork);
   cudaFree(dst);
   if (rc == PPSFM_OK && status) rc = PPSFM_NO_SOLUTION;
   return rc;

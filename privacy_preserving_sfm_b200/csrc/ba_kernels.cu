@@ -130,7 +130,7 @@ __device__ __forceinline__ void eval_loss(BaLoss loss, double s, double& rho0, d
 // point 24 B, write r 16 + J_c 96 + J_p 48 B = 216 B per observation.
 // ------------------------------------------------------------------------------------------
 template <bool JAC>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 4)  // 64 registers: 4 CTAs / SM hide the gather latency
 ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restrict__ t,
                     const double* __restrict__ X, BaLoss loss, double* __restrict__ partials) {
   __shared__ double red[32];

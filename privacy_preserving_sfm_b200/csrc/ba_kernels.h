@@ -48,6 +48,7 @@ struct BaDev {
   double* dp = nullptr;   // [3][P]
   double* u = nullptr;    // [2][K] J_c dc per observation (back-substitution scratch)
   int* chol_status = nullptr;
+  double* chol_work = nullptr;  // 64x64 scratch of the dense solver
   // reductions
   double* partials = nullptr;  // scratch for block partial sums
   int num_partials = 0;

@@ -21,78 +21,159 @@ namespace ppsfm {
 
 constexpr int NB = 64;
 
-// Panel step, 64 threads per CTA, thread r owns matrix row r in REGISTERS (fully unrolled):
-//   1. every CTA re-factors the 64x64 diagonal block (left-looking; row j is broadcast from shared
-//      memory, 4 independent accumulators hide the DFMA latency) — cheaper than a launch + sync;
-//   2. X L^T = A for its own 64-row tile by per-row forward substitution (no synchronisation).
-// A partial last block is padded with the identity.  CTA 0 writes the factored block back.
-__global__ void __launch_bounds__(NB)
-chol_panel_kernel(double* __restrict__ A, int ld, int n, int k0, int* __restrict__ status) {
-  __shared__ double D[NB][NB + 1];
+// ------------------------------------------------------------------------------------------
+// Diagonal-block kernel (1 CTA, 256 threads): factors the 64x64 diagonal block and inverts its
+// Cholesky factor, so that the panel below becomes a plain matrix product X = A L^-T that runs
+// on the FP64 tensor cores.  Blocked in 16-wide sub-blocks: only the 16x16 factorisations (one
+// warp, rows in registers, shuffles) and their triangular inverses are sequential; panels and
+// trailing updates inside the block use all 256 threads.  A partial last block is padded with
+// the identity.  Outputs: L (lower) written back into A, L^-1 (lower, dense 64x64) into `linv`.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restrict__ linv,
+                 int* __restrict__ status) {
+  extern __shared__ __align__(16) double dyn_smem[];
+  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);  // block -> L
+  double (*Tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L^-1
+  double (*I16)[16][17] =  // inverses of the four 16x16 diagonal sub-blocks
+      reinterpret_cast<double (*)[16][17]>(dyn_smem + 2 * NB * (NB + 1));
   __shared__ int ok;
-  const int r = threadIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int kb = min(NB, n - k0);
-  const int r0 = k0 + kb + blockIdx.x * NB;
-  if (r == 0) ok = 1;
-  double drow[NB];
-  {
-    const double* src = A + (size_t)(k0 + r) * ld + k0;
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      drow[c] = (r < kb) ? ((c <= r) ? src[c] : 0.0) : ((c == r) ? 1.0 : 0.0);
+  if (tid == 0) ok = 1;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    double v = 0.0;
+    if (r < kb && c <= r) v = A[(size_t)(k0 + r) * ld + k0 + c];
+    else if (r >= kb && c == r) v = 1.0;
+    D[r][c] = v;
+    Tm[r][c] = 0.0;
   }
   __syncthreads();
+#pragma unroll 1
+  for (int bk = 0; bk < 4; ++bk) {
+    const int k1 = 16 * bk;
+    if (warp == 0) {
+      // (a)+(b) 16x16 Cholesky with its inverse: lane i (< 16) owns row i of the block (a[]) and
+      // row i of the accumulated elimination transform (m[], starts as e_i).  Applying the
+      // eliminations of step j (scale row j by 1/l_jj, subtract l_ij x row j from rows i > j) to
+      // the identity yields L^-1 — no divisions, no second sequential pass.
+      const int i = lane & 15;
+      double a[16], m[16];
 #pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int p = 0; p < j; ++p) acc[p & 3] += drow[p] * D[j][p];
-    double sj = drow[j] - ((acc[0] + acc[1]) + (acc[2] + acc[3]));
-    if (r == j) {
-      if (!(sj > 0.0)) {
-        ok = 0;
-        sj = 1.0;
+      for (int c = 0; c < 16; ++c) {
+        a[c] = (lane < 16 && c <= i) ? D[k1 + i][k1 + c] : 0.0;
+        m[c] = (c == i) ? 1.0 : 0.0;
       }
-      drow[j] = sqrt(sj);
-      D[j][j] = drow[j];
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        double ajj = __shfl_sync(0xffffffffu, a[j], j);
+        if (!(ajj > 0.0)) {
+          if (lane == 0) ok = 0;
+          ajj = 1.0;
+        }
+        const double inv = rsqrt(ajj);
+        const double lij = (i == j) ? ajj * inv : a[j] * inv;
+        a[j] = (i >= j) ? lij : 0.0;
+        if (i == j) {
+#pragma unroll
+          for (int c = 0; c <= j; ++c) m[c] *= inv;
+        }
+#pragma unroll
+        for (int c = 0; c <= j; ++c) {
+          const double mjc = __shfl_sync(0xffffffffu, m[c], j);
+          if (i > j) m[c] -= a[j] * mjc;
+        }
+#pragma unroll
+        for (int c = j + 1; c < 16; ++c) {
+          const double lcj = __shfl_sync(0xffffffffu, a[j], c);
+          if (i >= c) a[c] -= a[j] * lcj;
+        }
+      }
+      if (lane < 16) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          if (c <= i) D[k1 + i][k1 + c] = a[c];
+          I16[bk][i][c] = (c <= i) ? m[c] : 0.0;
+        }
+      }
     }
     __syncthreads();
-    if (r > j) {
-      drow[j] = sj / D[j][j];
-      D[r][j] = drow[j];
+    const int below = NB - (k1 + 16);  // rows under this sub-block
+    if (below > 0) {
+      // (c) panel: X[r][c] = sum_{p <= c} A[r][k1+p] * I16[c][p]
+      double xv[3];
+      int cnt = 0;
+      for (int idx = tid; idx < below * 16; idx += 256, ++cnt) {
+        const int r = k1 + 16 + idx / 16, c = idx % 16;
+        double acc = 0.0;
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) acc += D[r][k1 + p2] * I16[bk][c][p2];
+        xv[cnt] = acc;
+      }
+      __syncthreads();
+      cnt = 0;
+      for (int idx = tid; idx < below * 16; idx += 256, ++cnt)
+        D[k1 + 16 + idx / 16][k1 + idx % 16] = xv[cnt];
+      __syncthreads();
+      // (d) trailing update inside the block (lower part)
+      for (int idx = tid; idx < below * below; idx += 256) {
+        const int r = k1 + 16 + idx / below, c = k1 + 16 + idx % below;
+        if (c > r) continue;
+        double acc = 0.0;
+#pragma unroll
+        for (int p2 = 0; p2 < 16; ++p2) acc += D[r][k1 + p2] * D[c][k1 + p2];
+        D[r][c] -= acc;
+      }
+      __syncthreads();
+    }
+  }
+  // L^-1 by block forward substitution: Linv[bi][bj] = -I16[bi] * sum_{bk=bj}^{bi-1} L[bi][bk] Linv[bk][bj]
+  for (int idx = tid; idx < 4 * 256; idx += 256) {
+    const int b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
+    Tm[16 * b + r][16 * b + c] = I16[b][r][c];
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int dist = 1; dist < 4; ++dist) {
+    const int nblk = 4 - dist;  // blocks (bi = bj + dist, bj)
+    double tmp[3];
+    int cnt = 0;
+    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
+      double acc = 0.0;
+      for (int p2 = 16 * bj; p2 < 16 * bi; ++p2) acc += D[16 * bi + r][p2] * Tm[p2][16 * bj + c];
+      tmp[cnt] = acc;
+    }
+    // tmp -> scratch region above the diagonal of Tm (unused otherwise): Tm[bj-rows][bi-cols]
+    cnt = 0;
+    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
+      Tm[16 * bj + r][16 * bi + c] = tmp[cnt];
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
+      double acc = 0.0;
+#pragma unroll
+      for (int p2 = 0; p2 < 16; ++p2) acc += I16[bi][r][p2] * Tm[16 * bj + p2][16 * bi + c];
+      tmp[cnt] = -acc;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
+      Tm[16 * bi + r][16 * bj + c] = tmp[cnt];
     }
     __syncthreads();
   }
-  if (blockIdx.x == 0) {
-    if (r < kb) {
-      double* dst = A + (size_t)(k0 + r) * ld + k0;
-#pragma unroll
-      for (int c = 0; c < NB; ++c)
-        if (c <= r) dst[c] = drow[c];
-    }
-    if (r == 0 && !ok) atomicExch(status, 1);
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = D[r][c];
+    linv[idx] = (c <= r) ? Tm[r][c] : 0.0;
   }
-  if (r0 >= ld) return;
-  const bool live = r0 + r < ld;
-  double trow[NB];
-  {
-    const double* src = A + (size_t)(r0 + (live ? r : 0)) * ld + k0;
-#pragma unroll
-    for (int c = 0; c < NB; ++c) trow[c] = (live && c < kb) ? src[c] : 0.0;
-  }
-#pragma unroll
-  for (int j = 0; j < NB; ++j) {
-    double acc[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-    for (int p = 0; p < j; ++p) acc[p & 3] += trow[p] * D[j][p];
-    trow[j] = (trow[j] - ((acc[0] + acc[1]) + (acc[2] + acc[3]))) / D[j][j];
-  }
-  if (live) {
-    double* dst = A + (size_t)(r0 + r) * ld + k0;
-#pragma unroll
-    for (int c = 0; c < NB; ++c)
-      if (c < kb) dst[c] = trow[c];
-  }
+  if (tid == 0 && !ok) atomicExch(status, 1);
 }
 
 // Trailing update with FP64 tensor cores: C(ti, tj) -= X_ti X_tj^T for tiles ti >= tj below /
@@ -104,23 +185,36 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "d"(a), "d"(b));
 }
 
+// One 64x64 output tile per CTA (8 warps; warp w owns rows 8w..8w+7 as eight m8n8k4 accumulators):
+//   kPanel == false: trailing update  C(ti, tj) -= X_ti X_tj^T  for tiles ti >= tj
+//   kPanel == true : panel            X_t = A_t Linv^T           (A_t overwritten in place)
+template <bool kPanel>
 __global__ void __launch_bounds__(256)
-chol_update_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_tile_row) {
-  // linear tile index -> (ti, tj) with tj <= ti, both relative to first_tile_row
-  const int t = blockIdx.x;
-  int ti = (int)floor((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-  while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-  while (ti * (ti + 1) / 2 > t) --ti;
-  const int tj = t - ti * (ti + 1) / 2;
+chol_tile_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_tile_row,
+                 const double* __restrict__ linv) {
+  int ti, tj;
+  if (kPanel) {
+    ti = blockIdx.x;
+    tj = 0;
+  } else {
+    const int t = blockIdx.x;
+    ti = (int)floor((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
+    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+    while (ti * (ti + 1) / 2 > t) --ti;
+    tj = t - ti * (ti + 1) / 2;
+  }
   const int ri = first_tile_row + ti * NB, rj = first_tile_row + tj * NB;
   extern __shared__ __align__(16) double dyn_smem[];
   double (*Xi)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem);
   double (*Xj)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem + NB * (NB + 4));
   const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += blockDim.x) {
-    const int r = idx / NB, c = idx % NB;
-    Xi[r][c] = (c < kb) ? A[(size_t)(ri + r) * ld + k0 + c] : 0.0;
-    Xj[r][c] = (c < kb) ? A[(size_t)(rj + r) * ld + k0 + c] : 0.0;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    Xi[r][c] = (c < kb && ri + r < ld) ? A[(size_t)(ri + r) * ld + k0 + c] : 0.0;
+    if (kPanel)
+      Xj[r][c] = linv[idx];
+    else
+      Xj[r][c] = (c < kb) ? A[(size_t)(rj + r) * ld + k0 + c] : 0.0;
   }
   __syncthreads();
   const int warp = tid >> 5, lane = tid & 31;
@@ -129,6 +223,7 @@ chol_update_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_til
 #pragma unroll
   for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
   const int row = warp * 8 + g;  // A fragment: a = A[row = g][k = q]
+#pragma unroll 4
   for (int kk = 0; kk < NB; kk += 4) {
     const double a = Xi[row][kk + q];
 #pragma unroll
@@ -138,57 +233,59 @@ chol_update_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_til
     }
   }
   // C fragment: c0 = C[g][2q], c1 = C[g][2q+1]
+  if (kPanel) {
+    if (ri + row < ld) {
 #pragma unroll
-  for (int nb = 0; nb < 8; ++nb) {
-    const int c = nb * 8 + 2 * q;
-    double* dst = A + (size_t)(ri + row) * ld + rj + c;
-    if (ti != tj || c <= row) dst[0] -= acc[nb][0];
-    if (ti != tj || c + 1 <= row) dst[1] -= acc[nb][1];
+      for (int nb = 0; nb < 8; ++nb) {
+        const int c = nb * 8 + 2 * q;
+        double* dst = A + (size_t)(ri + row) * ld + k0 + c;
+        if (c < kb) dst[0] = acc[nb][0];
+        if (c + 1 < kb) dst[1] = acc[nb][1];
+      }
+    }
+  } else {
+#pragma unroll
+    for (int nb = 0; nb < 8; ++nb) {
+      const int c = nb * 8 + 2 * q;
+      double* dst = A + (size_t)(ri + row) * ld + rj + c;
+      if (ti != tj || c <= row) dst[0] -= acc[nb][0];
+      if (ti != tj || c + 1 <= row) dst[1] -= acc[nb][1];
+    }
   }
 }
 
-// Backward substitution L^T x = y in ONE persistent CTA: for each 64-block from the bottom,
-// warp 0 solves the diagonal block column by column (no reductions: after x_i is known the
-// remaining entries are updated), then all 1024 threads apply y[0:k0] -= L[k0:k0+kb, 0:k0]^T x_k
-// with coalesced reads of the L rows.
-__global__ void __launch_bounds__(1024)
-chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ y) {
-  __shared__ double D[NB][NB + 1];
-  __shared__ double xk[NB];
-  const int tid = threadIdx.x;
-  const int nblk = (n + NB - 1) / NB;
-  for (int b = nblk - 1; b >= 0; --b) {
-    const int k0 = b * NB;
-    const int kb = min(NB, n - k0);
-    for (int idx = tid; idx < NB * NB; idx += 1024) {
-      const int r = idx >> 6, c = idx & 63;
-      D[r][c] = (r < kb && c <= r) ? A[(size_t)(k0 + r) * ld + k0 + c] : 0.0;
-    }
-    if (tid < NB) xk[tid] = (tid < kb) ? y[k0 + tid] : 0.0;
-    __syncthreads();
-    if (tid < 32) {
-      double v0 = xk[tid], v1 = xk[tid + 32];  // lane owns entries tid and tid + 32
-      for (int i = kb - 1; i >= 0; --i) {
-        const double mine = (i < 32) ? v0 : v1;
-        const double xi = __shfl_sync(0xffffffffu, mine, i & 31) / D[i][i];
-        if (tid == (i & 31)) { if (i < 32) v0 = xi; else v1 = xi; }
-        if (tid < i) v0 -= D[i][tid] * xi;
-        if (tid + 32 < i) v1 -= D[i][tid + 32] * xi;
-      }
-      xk[tid] = v0;
-      xk[tid + 32] = v1;
-    }
-    __syncthreads();
-    if (tid < kb) y[k0 + tid] = xk[tid];
-    for (int c = tid; c < k0; c += 1024) {
-      double s = 0.0;
-      const double* col = A + (size_t)k0 * ld + c;
-#pragma unroll 8
-      for (int r = 0; r < kb; ++r) s += col[(size_t)r * ld] * xk[r];
-      y[c] -= s;
-    }
-    __syncthreads();
+// Backward substitution L^T x = y, one launch per 64-block (descending).  Every CTA recomputes
+// x_b = L_bb^-T y_b from the stored inverse (a 64x64 mat-vec); CTA j < b then applies
+// y_j -= L[b][j]^T x_b on its own 64 columns, CTA b stores x_b.  y and x are distinct buffers.
+__global__ void __launch_bounds__(256)
+chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, int b,
+                      const double* __restrict__ linv_all, double* __restrict__ y,
+                      double* __restrict__ x) {
+  __shared__ double yb[NB], xb[NB], red[4][NB];
+  const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
+  const int k0 = b * NB;
+  const int kb = min(NB, n - k0);
+  const double* linv = linv_all + (size_t)b * NB * NB;
+  if (tid < NB) yb[tid] = (tid < kb) ? y[k0 + tid] : 0.0;
+  __syncthreads();
+  {
+    double s = 0.0;
+    for (int r = part; r < NB; r += 4) s += linv[r * NB + c] * yb[r];  // (L^-1)^T y
+    red[part][c] = s;
   }
+  __syncthreads();
+  if (tid < NB) xb[tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+  __syncthreads();
+  const int j = blockIdx.x;
+  if (j == b) {
+    if (tid < kb) x[k0 + tid] = xb[tid];
+    return;
+  }
+  double s = 0.0;
+  for (int r = part; r < kb; r += 4) s += A[(size_t)(k0 + r) * ld + j * NB + c] * xb[r];
+  red[part][c] = s;
+  __syncthreads();
+  if (part == 0) y[j * NB + c] -= red[0][c] + red[1][c] + red[2][c] + red[3][c];
 }
 
 __global__ void chol_extract_y_kernel(const double* __restrict__ A, int ld, int n,
@@ -198,15 +295,25 @@ __global__ void chol_extract_y_kernel(const double* __restrict__ A, int ld, int 
 }
 
 int chol_ld(int n) { return ((n + 1 + NB - 1) / NB) * NB; }
+size_t chol_work_doubles(int n) {
+  const size_t nblk = (size_t)(n + NB - 1) / NB;
+  return nblk * NB * NB + nblk * NB + NB;  // one L^-1 per diagonal block + y
+}
 
 // Factor + solve.  A: ld x ld (see header).  x: n doubles (device).  status: device int, set to
 // 1 if a non-positive pivot was met.  Asynchronous on `s`; returns the number of launches.
-int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaStream_t s) {
-  constexpr int kUpdateSmem = 2 * NB * (NB + 4) * (int)sizeof(double);
+int chol_solve_bordered(double* A, int n, int ld, double* x, double* linv, int* status,
+                        cudaStream_t s) {
+  constexpr int kTileSmem = 2 * NB * (NB + 4) * (int)sizeof(double);
+  constexpr int kDiagSmem = (2 * NB * (NB + 1) + 4 * 16 * 17) * (int)sizeof(double);
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(chol_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kUpdateSmem);
+    cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kDiagSmem);
+    cudaFuncSetAttribute(chol_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kTileSmem);
+    cudaFuncSetAttribute(chol_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kTileSmem);
     attr_set = true;
   }
   int launches = 0;
@@ -214,24 +321,33 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, int* status, cudaSt
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int kb = (n - k0 < NB) ? (n - k0) : NB;
     const int r0 = k0 + kb;
+    double* linv_k = linv + (size_t)(k0 / NB) * NB * NB;
+    chol_diag_kernel<<<1, 256, kDiagSmem, s>>>(A, ld, n, k0, linv_k, status);
+    ++launches;
     // row tiles below the diagonal block (they include the rhs row); for the last, partial
     // block the remaining rows (rhs + padding) start unaligned and fit in one guarded tile
     const int tiles = (ld - r0 + NB - 1) / NB;
-    chol_panel_kernel<<<tiles > 0 ? tiles : 1, NB, 0, s>>>(A, ld, n, k0, status);
-    ++launches;
+    if (tiles > 0) {
+      chol_tile_kernel<true><<<tiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, linv_k);
+      ++launches;
+    }
     if (r0 < ld && kb == NB) {
       const int nt = (ld - r0) / NB;
       const int ntiles = nt * (nt + 1) / 2;
       if (ntiles > 0) {
-        chol_update_kernel<<<ntiles, 256, kUpdateSmem, s>>>(A, ld, k0, kb, r0);
+        chol_tile_kernel<false><<<ntiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, nullptr);
         ++launches;
       }
     }
   }
-  chol_extract_y_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, ld, n, x);
+  const int nblk = (n + NB - 1) / NB;
+  double* y = linv + (size_t)nblk * NB * NB;  // y = L^-1 rhs (the bordered row), then consumed
+  chol_extract_y_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, ld, n, y);
   ++launches;
-  chol_backsolve_kernel<<<1, 1024, 0, s>>>(A, ld, n, x);
-  ++launches;
+  for (int b = nblk - 1; b >= 0; --b) {
+    chol_backsolve_kernel<<<b + 1, 256, 0, s>>>(A, ld, n, b, linv, y, x);
+    ++launches;
+  }
   return launches;
 }
 
