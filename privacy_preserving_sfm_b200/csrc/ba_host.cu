@@ -217,6 +217,16 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(Upload(st, &d.cam_mask, cam_mask));
   BA_TRY(Upload(st, &d.img_model, img_model));
   BA_TRY(Upload(st, &d.img_params, img_params));
+  {
+    d.num_cameras = pb->num_cameras;
+    std::vector<int> img_cam(pb->image_camera, pb->image_camera + C);
+    std::vector<int> cam_model(pb->camera_model, pb->camera_model + pb->num_cameras);
+    std::vector<double> cam_params(pb->camera_params,
+                                   pb->camera_params + 12 * (size_t)pb->num_cameras);
+    BA_TRY(Upload(st, &d.img_cam, img_cam));
+    BA_TRY(Upload(st, &d.cam_model, cam_model));
+    BA_TRY(Upload(st, &d.cam_params, cam_params));
+  }
   BA_TRY(Upload(st, &d.pt_var, pt_var));
   BA_TRY(Upload(st, &d.q, q));
   BA_TRY(Upload(st, &d.t, t));

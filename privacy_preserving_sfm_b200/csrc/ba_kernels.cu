@@ -129,19 +129,75 @@ __device__ __forceinline__ void eval_loss(BaLoss loss, double s, double& rho0, d
 // Algorithmic HBM traffic (materialised variant): read line 24 + cam 4 + pt 4 +
 // point 24 B, write r 16 + J_c 96 + J_p 48 B = 216 B per observation.
 // ------------------------------------------------------------------------------------------
-template <bool JAC>
-__global__ void __launch_bounds__(kThreads, 4)  // 64 registers: 4 CTAs / SM hide the gather latency
+// Per-image record staged in shared memory by the persistent variant (doubles):
+//   [0..3] q, [4..6] t, [7..12] Jacobi scale x tangent mask (0 = fixed dim / constant pose).
+// Odd stride: lanes that read different images mostly hit different banks.  Intrinsics are
+// staged per CAMERA (8 doubles = OPENCV, the largest supported model) next to it.
+constexpr int kCamRec = 13;
+constexpr int kIntrRec = 9;  // 8 parameters + model id (stored as a double)
+
+template <bool JAC, bool SMEM>
+__global__ void __launch_bounds__(kThreads, 4)  // 64 registers: 4 CTAs / SM
 ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restrict__ t,
-                    const double* __restrict__ X, BaLoss loss, double* __restrict__ partials) {
+                    const double* __restrict__ X, BaLoss loss, double* __restrict__ partials,
+                    int num_chunks) {
   __shared__ double red[32];
+  // [C][kCamRec] image records, [num_cameras][kIntrRec] intrinsics, [C] camera index of an image
+  extern __shared__ __align__(16) double cam_tab[];
+  double* intr_tab = cam_tab + (size_t)d.C * kCamRec;
+  int* tab_cam = reinterpret_cast<int*>(intr_tab + (size_t)d.num_cameras * kIntrRec);
   const int64_t K = d.K;
-  const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  if (SMEM) {
+    for (int idx = threadIdx.x; idx < d.C * kCamRec; idx += kThreads) {
+      const int ci = idx / kCamRec, f = idx - ci * kCamRec;
+      double v;
+      if (f < 4) v = q[4 * (size_t)ci + f];
+      else if (f < 7) v = t[3 * (size_t)ci + (f - 4)];
+      else {
+        const int blk = d.cam_block[ci];
+        const int j = f - 7;
+        v = (JAC && blk >= 0 && ((d.cam_mask[ci] >> j) & 1)) ? d.cam_scale[6 * (size_t)blk + j] : 0.0;
+      }
+      cam_tab[idx] = v;
+    }
+    for (int idx = threadIdx.x; idx < d.num_cameras * kIntrRec; idx += kThreads) {
+      const int cam = idx / kIntrRec, f = idx - cam * kIntrRec;
+      intr_tab[idx] = (f < 8) ? d.cam_params[12 * (size_t)cam + f] : (double)d.cam_model[cam];
+    }
+    for (int ci = threadIdx.x; ci < d.C; ci += kThreads) tab_cam[ci] = d.img_cam[ci];
+    __syncthreads();
+  }
   double cost = 0.0;
-  if (k < K) {
+  for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
+    const int64_t k = (int64_t)chunk * kThreads + threadIdx.x;
+    if (k >= K) continue;
     const int ci = d.obs_cam[k], pi = d.obs_pt[k];
     const double a = d.obs_line[k], b = d.obs_line[K + k], c = d.obs_line[2 * K + k];
-    const double4 qq = *reinterpret_cast<const double4*>(q + 4 * (size_t)ci);
-    const double qw = qq.x, qx = qq.y, qy = qq.z, qz = qq.w;
+    double qw, qx, qy, qz, tx, ty, tz, cs[6], prm[8];
+    int model;
+    if (SMEM) {
+      const double* rec = cam_tab + (size_t)ci * kCamRec;
+      qw = rec[0]; qx = rec[1]; qy = rec[2]; qz = rec[3];
+      tx = rec[4]; ty = rec[5]; tz = rec[6];
+#pragma unroll
+      for (int j = 0; j < 6; ++j) cs[j] = rec[7 + j];
+      const double* irec = intr_tab + (size_t)tab_cam[ci] * kIntrRec;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) prm[j] = irec[j];
+      model = (int)irec[8];
+    } else {
+      const double4 qq = *reinterpret_cast<const double4*>(q + 4 * (size_t)ci);
+      qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
+      tx = t[3 * (size_t)ci]; ty = t[3 * (size_t)ci + 1]; tz = t[3 * (size_t)ci + 2];
+      const int blk = d.cam_block[ci];
+      const unsigned mask = (JAC && blk >= 0) ? d.cam_mask[ci] : 0u;
+#pragma unroll
+      for (int j = 0; j < 6; ++j)
+        cs[j] = ((mask >> j) & 1u) ? d.cam_scale[6 * (size_t)blk + j] : 0.0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) prm[j] = d.img_params[12 * (size_t)ci + j];
+      model = d.img_model[ci];
+    }
     const double X0 = X[3 * (size_t)pi], X1 = X[3 * (size_t)pi + 1], X2 = X[3 * (size_t)pi + 2];
     // ceres::UnitQuaternionRotatePoint
     const double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy;
@@ -152,42 +208,34 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     const double pr0 = R00 * X0 + R01 * X1 + R02 * X2 + X0;
     const double pr1 = R10 * X0 + R11 * X1 + R12 * X2 + X1;
     const double pr2 = R20 * X0 + R21 * X1 + R22 * X2 + X2;
-    const double p0 = pr0 + t[3 * (size_t)ci], p1 = pr1 + t[3 * (size_t)ci + 1];
-    const double p2 = pr2 + t[3 * (size_t)ci + 2];
+    const double p0 = pr0 + tx, p1 = pr1 + ty, p2 = pr2 + tz;
     const double iz = 1.0 / p2;
     const double u = p0 * iz, v = p1 * iz;
     const double alpha = a * u + b * v + c;
     const double lu = u - alpha * a, lv = v - alpha * b;
-    const int model = d.img_model[ci];
-    const double* cp = d.img_params + 12 * (size_t)ci;
     double x1, y1, x2, y2, d1xu = 0, d1xv = 0, d1yu = 0, d1yv = 0, d2xu = 0, d2xv = 0, d2yu = 0,
                            d2yv = 0;
-    world_to_image<JAC>(model, cp, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
-    world_to_image<JAC>(model, cp, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
-    double r0 = x1 - x2, r1 = y1 - y2;
+    world_to_image<JAC>(model, prm, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
+    world_to_image<JAC>(model, prm, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+    const double r0 = x1 - x2, r1 = y1 - y2;
     const double sq = r0 * r0 + r1 * r1;
     double rho0, rho1;
     eval_loss(loss, sq, rho0, rho1);
-    cost = 0.5 * rho0;
+    cost += 0.5 * rho0;
     if (JAC) {
       const double sr = sqrt(rho1);
       // d r / d(u,v) = D1 - D2 (I - n n^T)
       const double m00 = 1.0 - a * a, m01 = -a * b, m11 = 1.0 - b * b;
       const double E00 = d1xu - (d2xu * m00 + d2xv * m01), E01 = d1xv - (d2xu * m01 + d2xv * m11);
       const double E10 = d1yu - (d2yu * m00 + d2yv * m01), E11 = d1yv - (d2yu * m01 + d2yv * m11);
-      // d r / d p  (p = R X + t)
+      // d r / d p  (p = R X + t), pre-multiplied by sqrt(rho')
       double G[2][3];
-      G[0][0] = E00 * iz; G[0][1] = E01 * iz; G[0][2] = -(E00 * u + E01 * v) * iz;
-      G[1][0] = E10 * iz; G[1][1] = E11 * iz; G[1][2] = -(E10 * u + E11 * v) * iz;
-      const int blk = d.cam_block[ci];
-      const unsigned mask = blk >= 0 ? d.cam_mask[ci] : 0u;
+      G[0][0] = sr * E00 * iz; G[0][1] = sr * E01 * iz; G[0][2] = -(G[0][0] * u + G[0][1] * v);
+      G[1][0] = sr * E10 * iz; G[1][1] = sr * E11 * iz; G[1][2] = -(G[1][0] * u + G[1][1] * v);
       const bool pvar = d.pt_var[pi] != 0;
-      double cs[6], ps[3];
+      double ps[3];
 #pragma unroll
-      for (int j = 0; j < 6; ++j)
-        cs[j] = ((mask >> j) & 1u) ? sr * d.cam_scale[6 * (size_t)blk + j] : 0.0;
-#pragma unroll
-      for (int j = 0; j < 3; ++j) ps[j] = pvar ? sr * d.pt_scale[3 * (size_t)pi + j] : 0.0;
+      for (int j = 0; j < 3; ++j) ps[j] = pvar ? d.pt_scale[3 * (size_t)pi + j] : 0.0;
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         const double g0 = G[row][0], g1 = G[row][1], g2 = G[row][2];
@@ -605,15 +653,50 @@ __global__ void ba_gradient_max_kernel(BaDev d) {
 // ============================================================================================
 int launch_linearize(const BaDev& d, const double* q, const double* t, const double* X,
                      bool jacobians, BaLoss loss, cudaStream_t s) {
-  const int blocks = (int)((d.K + kThreads - 1) / kThreads);
-  if (blocks == 0) {
+  const int chunks = (int)((d.K + kThreads - 1) / kThreads);
+  if (chunks == 0) {
     cudaMemsetAsync(d.scalars + kCost, 0, sizeof(double), s);
     return 0;
   }
-  if (jacobians)
-    ba_linearize_kernel<true><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials);
-  else
-    ba_linearize_kernel<false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials);
+  // Persistent CTAs with the per-image table in shared memory when it fits next to 4 CTAs / SM;
+  // otherwise one CTA per chunk gathering from global memory.
+  static int num_sms = 0, max_smem = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncSetAttribute(ba_linearize_kernel<true, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+    cudaFuncSetAttribute(ba_linearize_kernel<false, true>,
+                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
+  }
+  const size_t tab_bytes = (size_t)d.C * (kCamRec * sizeof(double) + sizeof(int)) +
+                           (size_t)d.num_cameras * kIntrRec * sizeof(double) + 16;
+  const bool use_smem = tab_bytes <= (size_t)(max_smem - 2048) && chunks > 2 * num_sms;
+  int blocks = chunks;
+  if (use_smem) {
+    int per_sm = (int)((size_t)(227 * 1024) / (tab_bytes + 1024));
+    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    blocks = num_sms * per_sm;
+    if (blocks > chunks) blocks = chunks;
+  }
+  if (blocks > d.num_partials) blocks = d.num_partials;
+  if (use_smem) {
+    if (jacobians)
+      ba_linearize_kernel<true, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
+                                                                          d.partials, chunks);
+    else
+      ba_linearize_kernel<false, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
+                                                                           d.partials, chunks);
+  } else {
+    if (jacobians)
+      ba_linearize_kernel<true, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
+                                                                   chunks);
+    else
+      ba_linearize_kernel<false, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
+                                                                    chunks);
+  }
   reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
                                             kCost, 0);
   return 2;

@@ -22,7 +22,11 @@ struct BaDev {
   int* cam_block = nullptr;     // [C] block index or -1 (constant pose)
   uint8_t* cam_mask = nullptr;  // [C] bit a set = tangent dim a (rot 0..2, trans 3..5) is free
   int* img_model = nullptr;     // [C] COLMAP camera model id
-  double* img_params = nullptr; // [C][12] intrinsics (constant)
+  double* img_params = nullptr; // [C][12] intrinsics (constant), expanded per image
+  int num_cameras = 0;
+  int* img_cam = nullptr;       // [C] camera index of an image
+  int* cam_model = nullptr;     // [num_cameras]
+  double* cam_params = nullptr; // [num_cameras][12]
   uint8_t* pt_var = nullptr;    // [P]
   // state
   double* q = nullptr;   // [C][4]

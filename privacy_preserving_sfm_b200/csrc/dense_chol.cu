@@ -21,6 +21,7 @@ namespace ppsfm {
 
 constexpr int NB = 64;
 
+
 // ------------------------------------------------------------------------------------------
 // Diagonal-block kernel (1 CTA, 256 threads): factors the 64x64 diagonal block and inverts its
 // Cholesky factor, so that the panel below becomes a plain matrix product X = A L^-T that runs
@@ -29,10 +30,9 @@ constexpr int NB = 64;
 // trailing updates inside the block use all 256 threads.  A partial last block is padded with
 // the identity.  Outputs: L (lower) written back into A, L^-1 (lower, dense 64x64) into `linv`.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restrict__ linv,
-                 int* __restrict__ status) {
-  extern __shared__ __align__(16) double dyn_smem[];
+__device__ void diag_block(double* __restrict__ A, int ld, int n, int k0,
+                           double* __restrict__ linv, int* __restrict__ status,
+                           double* dyn_smem) {
   double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);  // block -> L
   double (*Tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L^-1
   double (*I16)[16][17] =  // inverses of the four 16x16 diagonal sub-blocks
@@ -53,11 +53,14 @@ chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restri
 #pragma unroll 1
   for (int bk = 0; bk < 4; ++bk) {
     const int k1 = 16 * bk;
-    if (warp == 0) {
+    {
       // (a)+(b) 16x16 Cholesky with its inverse: lane i (< 16) owns row i of the block (a[]) and
       // row i of the accumulated elimination transform (m[], starts as e_i).  Applying the
       // eliminations of step j (scale row j by 1/l_jj, subtract l_ij x row j from rows i > j) to
       // the identity yields L^-1 — no divisions, no second sequential pass.
+      // ALL warps execute this redundantly (only warp 0 stores): inside a warp-specialised
+      // branch every shuffle compiles to a ~30-cycle WARPSYNC.COLLECTIVE sequence; in uniform
+      // control flow it is a plain SHFL.  The other warps would idle anyway.
       const int i = lane & 15;
       double a[16], m[16];
 #pragma unroll
@@ -65,36 +68,36 @@ chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restri
         a[c] = (lane < 16 && c <= i) ? D[k1 + i][k1 + c] : 0.0;
         m[c] = (c == i) ? 1.0 : 0.0;
       }
+      bool bad = false;
 #pragma unroll
       for (int j = 0; j < 16; ++j) {
         double ajj = __shfl_sync(0xffffffffu, a[j], j);
-        if (!(ajj > 0.0)) {
-          if (lane == 0) ok = 0;
-          ajj = 1.0;
-        }
+        bad = bad || !(ajj > 0.0);
+        ajj = (ajj > 0.0) ? ajj : 1.0;
         const double inv = rsqrt(ajj);
         const double lij = (i == j) ? ajj * inv : a[j] * inv;
         a[j] = (i >= j) ? lij : 0.0;
-        if (i == j) {
-#pragma unroll
-          for (int c = 0; c <= j; ++c) m[c] *= inv;
-        }
 #pragma unroll
         for (int c = 0; c <= j; ++c) {
-          const double mjc = __shfl_sync(0xffffffffu, m[c], j);
-          if (i > j) m[c] -= a[j] * mjc;
+          const double mc = (i == j) ? m[c] * inv : m[c];
+          const double mjc = __shfl_sync(0xffffffffu, mc, j);
+          m[c] = (i > j) ? mc - a[j] * mjc : mc;
         }
 #pragma unroll
         for (int c = j + 1; c < 16; ++c) {
           const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-          if (i >= c) a[c] -= a[j] * lcj;
+          a[c] = (i >= c) ? a[c] - a[j] * lcj : a[c];
         }
       }
-      if (lane < 16) {
+      __syncthreads();  // all warps are done reading the sub-block
+      if (warp == 0) {
+        if (bad && lane == 0) ok = 0;
+        if (lane < 16) {
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
-          if (c <= i) D[k1 + i][k1 + c] = a[c];
-          I16[bk][i][c] = (c <= i) ? m[c] : 0.0;
+          for (int c = 0; c < 16; ++c) {
+            if (c <= i) D[k1 + i][k1 + c] = a[c];
+            I16[bk][i][c] = (c <= i) ? m[c] : 0.0;
+          }
         }
       }
     }
@@ -173,7 +176,15 @@ chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restri
     if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = D[r][c];
     linv[idx] = (c <= r) ? Tm[r][c] : 0.0;
   }
+  __syncthreads();
   if (tid == 0 && !ok) atomicExch(status, 1);
+}
+
+__global__ void __launch_bounds__(256)
+chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restrict__ linv,
+                 int* __restrict__ status) {
+  extern __shared__ __align__(16) double dyn_smem_diag[];
+  diag_block(A, ld, n, k0, linv, status, dyn_smem_diag);
 }
 
 // Trailing update with FP64 tensor cores: C(ti, tj) -= X_ti X_tj^T for tiles ti >= tj below /
@@ -191,7 +202,8 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 template <bool kPanel>
 __global__ void __launch_bounds__(256)
 chol_tile_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_tile_row,
-                 const double* __restrict__ linv) {
+                 const double* __restrict__ linv, int n, double* __restrict__ linv_next,
+                 int* __restrict__ status) {
   int ti, tj;
   if (kPanel) {
     ti = blockIdx.x;
@@ -251,6 +263,14 @@ chol_tile_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_tile_
       if (ti != tj || c <= row) dst[0] -= acc[nb][0];
       if (ti != tj || c + 1 <= row) dst[1] -= acc[nb][1];
     }
+    // Look-ahead: tile (0, 0) is the next diagonal block.  Its CTA factors (and inverts) it right
+    // away, overlapped with the rest of this trailing update, so the sequential 64x64
+    // factorisation leaves the critical path of the next step.
+    if (blockIdx.x == 0 && linv_next != nullptr && first_tile_row < n) {
+      __threadfence_block();
+      __syncthreads();
+      diag_block(A, ld, n, first_tile_row, linv_next, status, dyn_smem);
+    }
   }
 }
 
@@ -306,37 +326,46 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, double* linv, int* 
                         cudaStream_t s) {
   constexpr int kTileSmem = 2 * NB * (NB + 4) * (int)sizeof(double);
   constexpr int kDiagSmem = (2 * NB * (NB + 1) + 4 * 16 * 17) * (int)sizeof(double);
+  constexpr int kUpdateSmem = kDiagSmem > kTileSmem ? kDiagSmem : kTileSmem;  // look-ahead reuse
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kDiagSmem);
     cudaFuncSetAttribute(chol_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kTileSmem);
+                         kUpdateSmem);
     cudaFuncSetAttribute(chol_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          kTileSmem);
     attr_set = true;
   }
   int launches = 0;
   cudaMemsetAsync(status, 0, sizeof(int), s);
+  bool diag_done = false;  // diagonal block k already factored by the previous update kernel
   for (int k0 = 0; k0 < n; k0 += NB) {
     const int kb = (n - k0 < NB) ? (n - k0) : NB;
     const int r0 = k0 + kb;
     double* linv_k = linv + (size_t)(k0 / NB) * NB * NB;
-    chol_diag_kernel<<<1, 256, kDiagSmem, s>>>(A, ld, n, k0, linv_k, status);
-    ++launches;
+    if (!diag_done) {
+      chol_diag_kernel<<<1, 256, kDiagSmem, s>>>(A, ld, n, k0, linv_k, status);
+      ++launches;
+    }
+    diag_done = false;
     // row tiles below the diagonal block (they include the rhs row); for the last, partial
     // block the remaining rows (rhs + padding) start unaligned and fit in one guarded tile
     const int tiles = (ld - r0 + NB - 1) / NB;
     if (tiles > 0) {
-      chol_tile_kernel<true><<<tiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, linv_k);
+      chol_tile_kernel<true><<<tiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, linv_k, n, nullptr,
+                                                           status);
       ++launches;
     }
     if (r0 < ld && kb == NB) {
       const int nt = (ld - r0) / NB;
       const int ntiles = nt * (nt + 1) / 2;
       if (ntiles > 0) {
-        chol_tile_kernel<false><<<ntiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, nullptr);
+        double* linv_next = (r0 < n) ? linv_k + NB * NB : nullptr;
+        chol_tile_kernel<false><<<ntiles, 256, kUpdateSmem, s>>>(A, ld, k0, kb, r0, nullptr, n,
+                                                                  linv_next, status);
         ++launches;
+        diag_done = (linv_next != nullptr);
       }
     }
   }
