@@ -280,6 +280,8 @@ int ppsfm_ba_shard_stats(const ppsfm_ba_problem* problem, int rank, int world, i
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);
+/* Write-only / read-only HBM bandwidth (GB/s) over a 2 GiB buffer. */
+int ppsfm_bench_hbm_rw_peak(ppsfm_ctx* ctx, double* write_gbs, double* read_gbs);
 /* Evict L2 by writing `bytes` of scratch HBM (blocking). */
 int ppsfm_bench_l2_flush(ppsfm_ctx* ctx, size_t bytes);
 

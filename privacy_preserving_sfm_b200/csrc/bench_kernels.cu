@@ -23,9 +23,64 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// HBM write / read micro-benchmarks: STREAM-style copy peaks mix reads and writes 1:1, but the
+// Jacobian build writes 3x what it reads, so its ceiling is the write-side bandwidth.
+__global__ void __launch_bounds__(256) hbm_write_kernel(double2* __restrict__ out, size_t n,
+                                                        double v) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = make_double2(v, v + (double)i);
+}
+__global__ void __launch_bounds__(256) hbm_read_kernel(const double2* __restrict__ in, size_t n,
+                                                       double* __restrict__ sink) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  double acc = 0.0;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += stride) {
+    const double2 v = in[i];
+    acc += v.x + v.y;
+  }
+  if (acc == 123.456) sink[0] = acc;
+}
+
 }  // namespace
 
 extern "C" {
+
+// Write-only and read-only HBM bandwidth in GB/s over a 2 GiB buffer (best of 3).
+int ppsfm_bench_hbm_rw_peak(ppsfm_ctx* ctx, double* write_gbs, double* read_gbs) {
+  if (!ctx) return PPSFM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const size_t bytes = (size_t)2 << 30, n = bytes / sizeof(double2);
+  double2* buf = nullptr;
+  double* sink = nullptr;
+  PPSFM_CUDA(ctx, cudaMalloc(&buf, bytes));
+  PPSFM_CUDA(ctx, cudaMalloc(&sink, 64));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best[2] = {0, 0};
+  const int blocks = ctx->num_sms * 8;
+  for (int mode = 0; mode < 2; ++mode)
+    for (int rep = 0; rep < 4; ++rep) {
+      cudaEventRecord(a, ctx->stream);
+      if (mode == 0) hbm_write_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, 1.0 + rep);
+      else hbm_read_kernel<<<blocks, 256, 0, ctx->stream>>>(buf, n, sink);
+      cudaEventRecord(b, ctx->stream);
+      cudaEventSynchronize(b);
+      float ms = 0;
+      cudaEventElapsedTime(&ms, a, b);
+      const double gbs = bytes / (ms * 1e-3) / 1e9;
+      if (rep > 0 && gbs > best[mode]) best[mode] = gbs;
+    }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(buf);
+  cudaFree(sink);
+  PPSFM_CUDA(ctx, cudaGetLastError());
+  if (write_gbs) *write_gbs = best[0];
+  if (read_gbs) *read_gbs = best[1];
+  return PPSFM_OK;
+}
 
 // Returns FP64 instruction throughput in 1e12 thread-instructions per second:
 // *dfma_tips for DFMA (x2 = TFLOP/s), *dmuladd_tips for an unfused DMUL/DADD mix.
