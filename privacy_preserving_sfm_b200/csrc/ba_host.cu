@@ -45,7 +45,9 @@ namespace {
 template <typename T>
 cudaError_t DevAlloc(BaState* st, T** p, size_t count) {
   void* v = nullptr;
-  cudaError_t e = cudaMalloc(&v, std::max<size_t>(1, count) * sizeof(T));
+  // stream-ordered pool allocation: after the first solve the context's pool serves these from
+  // cached HBM (no cudaMalloc / cudaFree on the per-call path)
+  cudaError_t e = cudaMallocAsync(&v, std::max<size_t>(1, count) * sizeof(T), st->ctx->stream);
   if (e == cudaSuccess) {
     st->allocs.push_back(v);
     *p = static_cast<T*>(v);
@@ -71,7 +73,8 @@ double Secs(std::chrono::steady_clock::time_point a) {
 
 void BaFree(BaState* st) {
   if (!st) return;
-  for (void* p : st->allocs) cudaFree(p);
+  for (void* p : st->allocs) cudaFreeAsync(p, st->ctx->stream);
+  cudaStreamSynchronize(st->ctx->stream);
   st->h_scalars.release();
   if (st->ev0) cudaEventDestroy(st->ev0);
   if (st->ev1) cudaEventDestroy(st->ev1);
@@ -92,17 +95,6 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   const int C = pb->num_images, P = pb->num_points;
   const int64_t O = pb->num_obs;
   if (C < 0 || P < 0 || O < 0) return fail(ctx, PPSFM_ERR_INVALID, "negative size");
-  for (int64_t o = 0; o < O; ++o) {
-    if (pb->obs_image[o] < 0 || pb->obs_image[o] >= C || pb->obs_point[o] < 0 ||
-        pb->obs_point[o] >= P)
-      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld references a missing image/point",
-                  (long long)o);
-    const double* l = pb->obs_line + 3 * o;
-    // CHECK_NEAR(line.head<2>().norm(), 1.0, 1e-6)  (bundle_adjustment.cc:374)
-    if (std::fabs(std::sqrt(l[0] * l[0] + l[1] * l[1]) - 1.0) > 1e-6)
-      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld: line normal is not unit length",
-                  (long long)o);
-  }
   for (int i = 0; i < C; ++i) {
     const int cam = pb->image_camera[i];
     if (cam < 0 || cam >= pb->num_cameras)
@@ -134,6 +126,19 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   std::vector<uint8_t> cam_used(C, 0);
   for (int64_t o = 0; o < O; ++o) {
     const int ci = pb->obs_image[o], pi = pb->obs_point[o];
+    if (ci < 0 || ci >= C || pi < 0 || pi >= P) {
+      delete st;
+      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld references a missing image/point",
+                  (long long)o);
+    }
+    const double* l = pb->obs_line + 3 * o;
+    // CHECK_NEAR(line.head<2>().norm(), 1.0, 1e-6)  (bundle_adjustment.cc:374)
+    const double n2 = l[0] * l[0] + l[1] * l[1];
+    if (!(n2 > 0.999998 && n2 < 1.000002) && std::fabs(std::sqrt(n2) - 1.0) > 1e-6) {
+      delete st;
+      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld: line normal is not unit length",
+                  (long long)o);
+    }
     if (cam_const[ci] && !pt_var[pi]) continue;
     cam_used[ci] = 1;  // global property: identical on every rank
     if (!mine(pi)) continue;
@@ -237,9 +242,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.qn, 4 * (size_t)C));
   BA_TRY(DevAlloc(st, &d.tn, 3 * (size_t)C));
   BA_TRY(DevAlloc(st, &d.Xn, 3 * (size_t)P));
-  BA_TRY(DevAlloc(st, &d.r, 2 * (size_t)K));
-  BA_TRY(DevAlloc(st, &d.Jc, 12 * (size_t)K));
-  BA_TRY(DevAlloc(st, &d.Jp, 6 * (size_t)K));
+  BA_TRY(DevAlloc(st, &d.J, ba_j_doubles(K)));
   BA_TRY(DevAlloc(st, &d.cam_scale, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.pt_scale, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.U, 36 * (size_t)NB));
@@ -682,11 +685,9 @@ int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
                                cudaMemcpyHostToDevice));
     launch_linearize(d, d.q, d.t, d.X, true, BaLoss{options->loss_type, options->loss_scale}, s);
     const int64_t K = d.K;
-    std::vector<double> r(2 * (size_t)K), jc(12 * (size_t)K), jp(6 * (size_t)K);
+    std::vector<double> J(ba_j_doubles(K));
     std::vector<int> oc(K), op(K);
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(r.data(), d.r, sizeof(double) * 2 * K, cudaMemcpyDeviceToHost, s));
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(jc.data(), d.Jc, sizeof(double) * 12 * K, cudaMemcpyDeviceToHost, s));
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(jp.data(), d.Jp, sizeof(double) * 6 * K, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(J.data(), d.J, sizeof(double) * J.size(), cudaMemcpyDeviceToHost, s));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(oc.data(), d.obs_cam, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(op.data(), d.obs_pt, sizeof(int) * K, cudaMemcpyDeviceToHost, s));
     double c = 0;
@@ -719,9 +720,9 @@ int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
         continue;
       }
       const int64_t k = next[problem->obs_point[o]]++;
-      for (int i = 0; i < 2; ++i) ro[i] = r[(size_t)i * K + k];
-      for (int i = 0; i < 12; ++i) co[i] = jc[(size_t)i * K + k];
-      for (int i = 0; i < 6; ++i) po[i] = jp[(size_t)i * K + k];
+      for (int i = 0; i < 2; ++i) ro[i] = J[ba_jidx(i, k)];
+      for (int i = 0; i < 12; ++i) co[i] = J[ba_jidx(2 + i, k)];
+      for (int i = 0; i < 6; ++i) po[i] = J[ba_jidx(14 + i, k)];
     }
     return PPSFM_OK;
   };

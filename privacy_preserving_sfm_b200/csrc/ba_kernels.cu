@@ -23,6 +23,15 @@ namespace {
 
 constexpr int kThreads = 256;
 
+// Linearisation storage (see BaDev::J): field f of observation k.
+#define JR(row, k) d.J[ba_jidx((row), (k))]
+#define JC(i, k) d.J[ba_jidx(2 + (i), (k))]
+#define JP(i, k) d.J[ba_jidx(14 + (i), (k))]
+
+__device__ __forceinline__ void prefetch_l2(const void* p) {
+  asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
@@ -170,6 +179,18 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
   double cost = 0.0;
   for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
     const int64_t k = (int64_t)chunk * kThreads + threadIdx.x;
+    {
+      // The kernel writes 3x what it reads; demand reads that queue behind the write stream in
+      // DRAM stall the warps.  Pull the inputs of the chunk two iterations ahead into L2 now.
+      const int64_t kp = k + 2 * (int64_t)gridDim.x * kThreads;
+      if (kp < K) {
+        prefetch_l2(d.obs_cam + kp);
+        prefetch_l2(d.obs_pt + kp);
+        prefetch_l2(d.obs_line + kp);
+        prefetch_l2(d.obs_line + K + kp);
+        prefetch_l2(d.obs_line + 2 * K + kp);
+      }
+    }
     if (k >= K) continue;
     const int ci = d.obs_cam[k], pi = d.obs_pt[k];
     const double a = d.obs_line[k], b = d.obs_line[K + k], c = d.obs_line[2 * K + k];
@@ -240,19 +261,19 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
       for (int row = 0; row < 2; ++row) {
         const double g0 = G[row][0], g1 = G[row][1], g2 = G[row][2];
         // rotation (left perturbation q_delta * q, angle 2|delta|): d p / d delta = -2 [R X]_x
-        d.Jc[(6 * row + 0) * K + k] = cs[0] * 2.0 * (g2 * pr1 - g1 * pr2);
-        d.Jc[(6 * row + 1) * K + k] = cs[1] * 2.0 * (g0 * pr2 - g2 * pr0);
-        d.Jc[(6 * row + 2) * K + k] = cs[2] * 2.0 * (g1 * pr0 - g0 * pr1);
-        d.Jc[(6 * row + 3) * K + k] = cs[3] * g0;
-        d.Jc[(6 * row + 4) * K + k] = cs[4] * g1;
-        d.Jc[(6 * row + 5) * K + k] = cs[5] * g2;
+        JC((6 * row + 0), k) = cs[0] * 2.0 * (g2 * pr1 - g1 * pr2);
+        JC((6 * row + 1), k) = cs[1] * 2.0 * (g0 * pr2 - g2 * pr0);
+        JC((6 * row + 2), k) = cs[2] * 2.0 * (g1 * pr0 - g0 * pr1);
+        JC((6 * row + 3), k) = cs[3] * g0;
+        JC((6 * row + 4), k) = cs[4] * g1;
+        JC((6 * row + 5), k) = cs[5] * g2;
         // point: G R   (R = I + R..)
-        d.Jp[(3 * row + 0) * K + k] = ps[0] * (g0 * (R00 + 1.0) + g1 * R10 + g2 * R20);
-        d.Jp[(3 * row + 1) * K + k] = ps[1] * (g0 * R01 + g1 * (R11 + 1.0) + g2 * R21);
-        d.Jp[(3 * row + 2) * K + k] = ps[2] * (g0 * R02 + g1 * R12 + g2 * (R22 + 1.0));
+        JP((3 * row + 0), k) = ps[0] * (g0 * (R00 + 1.0) + g1 * R10 + g2 * R20);
+        JP((3 * row + 1), k) = ps[1] * (g0 * R01 + g1 * (R11 + 1.0) + g2 * R21);
+        JP((3 * row + 2), k) = ps[2] * (g0 * R02 + g1 * R12 + g2 * (R22 + 1.0));
       }
-      d.r[k] = sr * r0;
-      d.r[K + k] = sr * r1;
+      JR(0, k) = sr * r0;
+      JR(1, k) = sr * r1;
     }
   }
   const double total = block_sum(cost, red);
@@ -286,8 +307,8 @@ __global__ void __launch_bounds__(kThreads) ba_point_normal_kernel(BaDev d) {
   for (int64_t k = d.pt_start[p]; k < d.pt_start[p + 1]; ++k) {
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
-      const double j0 = d.Jp[(3 * row) * K + k], j1 = d.Jp[(3 * row + 1) * K + k];
-      const double j2 = d.Jp[(3 * row + 2) * K + k], rr = d.r[row * K + k];
+      const double j0 = JP((3 * row), k), j1 = JP((3 * row + 1), k);
+      const double j2 = JP((3 * row + 2), k), rr = JR(row, k);
       v00 += j0 * j0; v01 += j0 * j1; v02 += j0 * j2;
       v11 += j1 * j1; v12 += j1 * j2; v22 += j2 * j2;
       g0 += j0 * rr; g1 += j1 * rr; g2 += j2 * rr;
@@ -314,8 +335,8 @@ __global__ void __launch_bounds__(128) ba_camera_normal_kernel(BaDev d) {
     for (int row = 0; row < 2; ++row) {
       double j[6];
 #pragma unroll
-      for (int a = 0; a < 6; ++a) j[a] = d.Jc[(6 * row + a) * K + k];
-      const double rr = d.r[row * K + k];
+      for (int a = 0; a < 6; ++a) j[a] = JC((6 * row + a), k);
+      const double rr = JR(row, k);
       int idx = 0;
 #pragma unroll
       for (int a = 0; a < 6; ++a) {
@@ -417,11 +438,11 @@ ba_schur_kernel(BaDev d, double radius, double min_diag, double max_diag) {
     double y[2];
 #pragma unroll
     for (int row = 0; row < 2; ++row)
-      y[row] = d.Jp[(3 * row) * K + k] * vg0 + d.Jp[(3 * row + 1) * K + k] * vg1 +
-               d.Jp[(3 * row + 2) * K + k] * vg2;
+      y[row] = JP((3 * row), k) * vg0 + JP((3 * row + 1), k) * vg1 +
+               JP((3 * row + 2), k) * vg2;
 #pragma unroll
     for (int a2 = 0; a2 < 6; ++a2)
-      atomicAdd(&rhs[6 * bi + a2], d.Jc[a2 * K + k] * y[0] + d.Jc[(6 + a2) * K + k] * y[1]);
+      atomicAdd(&rhs[6 * bi + a2], JC(a2, k) * y[0] + JC((6 + a2), k) * y[1]);
   }
   // S -= sum over ordered pairs
   for (int idx = lane; idx < m * m; idx += 32) {
@@ -433,29 +454,29 @@ ba_schur_kernel(BaDev d, double radius, double min_diag, double max_diag) {
     double Y[2][3], T[2][2];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
-      const double j0 = d.Jp[(3 * row) * K + ke], j1 = d.Jp[(3 * row + 1) * K + ke];
-      const double j2 = d.Jp[(3 * row + 2) * K + ke];
+      const double j0 = JP((3 * row), ke), j1 = JP((3 * row + 1), ke);
+      const double j2 = JP((3 * row + 2), ke);
       Y[row][0] = j0 * w00 + j1 * w01 + j2 * w02;
       Y[row][1] = j0 * w01 + j1 * w11 + j2 * w12;
       Y[row][2] = j0 * w02 + j1 * w12 + j2 * w22;
     }
 #pragma unroll
     for (int s2 = 0; s2 < 2; ++s2) {
-      const double j0 = d.Jp[(3 * s2) * K + kf], j1 = d.Jp[(3 * s2 + 1) * K + kf];
-      const double j2 = d.Jp[(3 * s2 + 2) * K + kf];
+      const double j0 = JP((3 * s2), kf), j1 = JP((3 * s2 + 1), kf);
+      const double j2 = JP((3 * s2 + 2), kf);
       T[0][s2] = Y[0][0] * j0 + Y[0][1] * j1 + Y[0][2] * j2;
       T[1][s2] = Y[1][0] * j0 + Y[1][1] * j1 + Y[1][2] * j2;
     }
     double Jf[2][6];
 #pragma unroll
     for (int c2 = 0; c2 < 6; ++c2) {
-      Jf[0][c2] = d.Jc[c2 * K + kf];
-      Jf[1][c2] = d.Jc[(6 + c2) * K + kf];
+      Jf[0][c2] = JC(c2, kf);
+      Jf[1][c2] = JC((6 + c2), kf);
     }
     double* blk = d.S + (size_t)(6 * bi) * d.ld + 6 * bj;
 #pragma unroll
     for (int a2 = 0; a2 < 6; ++a2) {
-      const double e0 = d.Jc[a2 * K + ke], e1 = d.Jc[(6 + a2) * K + ke];
+      const double e0 = JC(a2, ke), e1 = JC((6 + a2), ke);
       const double h0 = e0 * T[0][0] + e1 * T[1][0];  // (J_c,e^T T)[a][0]
       const double h1 = e0 * T[0][1] + e1 * T[1][1];
 #pragma unroll
@@ -480,14 +501,14 @@ __global__ void __launch_bounds__(kThreads) ba_backsub_accum_kernel(BaDev d) {
 #pragma unroll
     for (int a = 0; a < 6; ++a) {
       const double dca = d.dc[6 * b + a];
-      u0 += d.Jc[a * K + k] * dca;
-      u1 += d.Jc[(6 + a) * K + k] * dca;
+      u0 += JC(a, k) * dca;
+      u1 += JC((6 + a), k) * dca;
     }
     const int p = d.obs_pt[k];
     const int P = d.P;
 #pragma unroll
     for (int c = 0; c < 3; ++c)
-      atomicAdd(&d.dp[(size_t)c * P + p], d.Jp[c * K + k] * u0 + d.Jp[(3 + c) * K + k] * u1);
+      atomicAdd(&d.dp[(size_t)c * P + p], JP(c, k) * u0 + JP((3 + c), k) * u1);
   }
   d.u[k] = u0;
   d.u[K + k] = u1;
@@ -540,9 +561,9 @@ ba_model_cost_kernel(BaDev d, double* __restrict__ partials) {
     const double dp0 = d.dp[p], dp1 = d.dp[P + p], dp2 = d.dp[2 * P + p];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
-      const double m = d.u[row * K + k] + d.Jp[(3 * row) * K + k] * dp0 +
-                       d.Jp[(3 * row + 1) * K + k] * dp1 + d.Jp[(3 * row + 2) * K + k] * dp2;
-      model -= m * (d.r[row * K + k] + 0.5 * m);
+      const double m = d.u[row * K + k] + JP((3 * row), k) * dp0 +
+                       JP((3 * row + 1), k) * dp1 + JP((3 * row + 2), k) * dp2;
+      model -= m * (JR(row, k) + 0.5 * m);
     }
   }
   const double tm = block_sum(model, red);

@@ -35,10 +35,12 @@ struct BaDev {
   double* qn = nullptr;  // candidate
   double* tn = nullptr;
   double* Xn = nullptr;
-  // linearisation (scaled by the Jacobi column scales, loss-corrected), SoA over K
-  double* r = nullptr;    // [2][K]
-  double* Jc = nullptr;   // [12][K]: row-major 2x6 [rot | trans]
-  double* Jp = nullptr;   // [6][K]:  row-major 2x3
+  // linearisation (scaled by the Jacobi column scales, loss-corrected): 20 fields per
+  // observation — residual r (2), J_c row-major 2x6 [rot | trans] (12), J_p row-major 2x3 (6) —
+  // stored "blocked SoA": [chunk of 256 observations][field][256].  Every warp access is still a
+  // coalesced 256-byte line, but one chunk is a single contiguous 40 KB region instead of 20
+  // streams 16 MB apart (DRAM row-buffer locality for the write-heavy Jacobian build).
+  double* J = nullptr;    // [ceil(K/256)][20][256]
   double* cam_scale = nullptr;  // [NB][6]
   double* pt_scale = nullptr;   // [P][3]
   // normal equations
@@ -58,6 +60,12 @@ struct BaDev {
   int num_partials = 0;
   double* scalars = nullptr;   // [16] device scalars
 };
+
+constexpr int kJFields = 20;
+__host__ __device__ inline size_t ba_jidx(int field, int64_t k) {
+  return ((size_t)(k >> 8) * kJFields + (size_t)field) * 256 + (size_t)(k & 255);
+}
+inline size_t ba_j_doubles(int64_t K) { return (size_t)((K + 255) >> 8) * kJFields * 256; }
 
 enum BaScalar { kCost = 0, kModelChange = 1, kStepSq = 2, kXSq = 3, kGradMax = 4, kNumScalars = 16 };
 

@@ -493,6 +493,13 @@ int ppsfm_ctx_create(int device, ppsfm_ctx** out) {
     return PPSFM_ERR_CUDA;
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  {  // keep freed stream-ordered allocations cached in the device pool (BA scratch reuse)
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+      unsigned long long threshold = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+    }
+  }
   *out = ctx;
   return PPSFM_OK;
 }
