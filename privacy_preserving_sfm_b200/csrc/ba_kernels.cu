@@ -16,6 +16,7 @@
 #include <cstdint>
 
 #include "ba_kernels.h"
+#include "common.h"
 
 namespace ppsfm {
 
@@ -30,6 +31,11 @@ constexpr int kThreads = 256;
 
 __device__ __forceinline__ void prefetch_l2(const void* p) {
   asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+}
+
+// J store: plain (write-back, stays in L2) or streaming (evict-first)
+__device__ __forceinline__ void jstore(double* p, double v, int streaming) {
+  if (streaming) __stcs(p, v); else *p = v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -146,16 +152,28 @@ constexpr int kCamRec = 13;
 constexpr int kIntrRec = 9;  // 8 parameters + model id (stored as a double)
 
 template <bool JAC, bool SMEM>
-__global__ void __launch_bounds__(kThreads, 4)  // 64 registers: 4 CTAs / SM
+__global__ void __launch_bounds__(kThreads, 2)  // ~100 live registers: 2 CTAs / SM, no spills
 ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restrict__ t,
                     const double* __restrict__ X, BaLoss loss, double* __restrict__ partials,
-                    int num_chunks) {
+                    int num_chunks, int store_mode) {
   __shared__ double red[32];
   // [C][kCamRec] image records, [num_cameras][kIntrRec] intrinsics, [C] camera index of an image
   extern __shared__ __align__(16) double cam_tab[];
   double* intr_tab = cam_tab + (size_t)d.C * kCamRec;
   int* tab_cam = reinterpret_cast<int*>(intr_tab + (size_t)d.num_cameras * kIntrRec);
   const int64_t K = d.K;
+  // Software pipeline: the streaming inputs (image / point index, line) of this CTA's NEXT chunk
+  // are loaded into registers while the current chunk is computed, and the chunk after that is
+  // pulled into L2 — the kernel writes 3x what it reads, and demand reads that queue behind the
+  // write stream in DRAM would otherwise stall every warp of the SM at the same time.
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  int ci_n = 0, pi_n = 0;
+  double a_n = 0.0, b_n = 0.0, c_n = 0.0;
+  if (k < K) {
+    ci_n = d.obs_cam[k]; pi_n = d.obs_pt[k];
+    a_n = d.obs_line[k]; b_n = d.obs_line[K + k]; c_n = d.obs_line[2 * K + k];
+  }
   if (SMEM) {
     for (int idx = threadIdx.x; idx < d.C * kCamRec; idx += kThreads) {
       const int ci = idx / kCamRec, f = idx - ci * kCamRec;
@@ -178,11 +196,28 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
   }
   double cost = 0.0;
   for (int chunk = blockIdx.x; chunk < num_chunks; chunk += gridDim.x) {
-    const int64_t k = (int64_t)chunk * kThreads + threadIdx.x;
-    {
-      // The kernel writes 3x what it reads; demand reads that queue behind the write stream in
-      // DRAM stall the warps.  Pull the inputs of the chunk two iterations ahead into L2 now.
-      const int64_t kp = k + 2 * (int64_t)gridDim.x * kThreads;
+    const int64_t kc = k;
+    const bool valid = kc < K;
+    const int ci = ci_n, pi = pi_n;
+    const double a = a_n, b = b_n, c = c_n;
+    // gathers of the current observation (L2-resident tables), issued before the next chunk's
+    // streaming loads so that they are first in the queue
+    double X0 = 0.0, X1 = 0.0, X2 = 1.0, ps[3] = {0.0, 0.0, 0.0};
+    if (valid) {
+      X0 = X[3 * (size_t)pi]; X1 = X[3 * (size_t)pi + 1]; X2 = X[3 * (size_t)pi + 2];
+      if (JAC) {  // independent loads (no load -> branch -> load chain), masked afterwards
+        const uint8_t pvar = d.pt_var[pi];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ps[j] = d.pt_scale[3 * (size_t)pi + j];
+#pragma unroll
+        for (int j = 0; j < 3; ++j) ps[j] = pvar ? ps[j] : 0.0;
+      }
+    }
+    k = kc + stride;
+    if (k < K) {
+      ci_n = d.obs_cam[k]; pi_n = d.obs_pt[k];
+      a_n = d.obs_line[k]; b_n = d.obs_line[K + k]; c_n = d.obs_line[2 * K + k];
+      const int64_t kp = k + stride;
       if (kp < K) {
         prefetch_l2(d.obs_cam + kp);
         prefetch_l2(d.obs_pt + kp);
@@ -191,9 +226,7 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
         prefetch_l2(d.obs_line + 2 * K + kp);
       }
     }
-    if (k >= K) continue;
-    const int ci = d.obs_cam[k], pi = d.obs_pt[k];
-    const double a = d.obs_line[k], b = d.obs_line[K + k], c = d.obs_line[2 * K + k];
+    if (!valid) continue;
     double qw, qx, qy, qz, tx, ty, tz, cs[6], prm[8];
     int model;
     if (SMEM) {
@@ -219,7 +252,6 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
       for (int j = 0; j < 8; ++j) prm[j] = d.img_params[12 * (size_t)ci + j];
       model = d.img_model[ci];
     }
-    const double X0 = X[3 * (size_t)pi], X1 = X[3 * (size_t)pi + 1], X2 = X[3 * (size_t)pi + 2];
     // ceres::UnitQuaternionRotatePoint
     const double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy;
     const double t7 = qx * qz, t8 = -qy * qy, t9 = qy * qz, t1 = -qz * qz;
@@ -253,27 +285,23 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
       double G[2][3];
       G[0][0] = sr * E00 * iz; G[0][1] = sr * E01 * iz; G[0][2] = -(G[0][0] * u + G[0][1] * v);
       G[1][0] = sr * E10 * iz; G[1][1] = sr * E11 * iz; G[1][2] = -(G[1][0] * u + G[1][1] * v);
-      const bool pvar = d.pt_var[pi] != 0;
-      double ps[3];
-#pragma unroll
-      for (int j = 0; j < 3; ++j) ps[j] = pvar ? d.pt_scale[3 * (size_t)pi + j] : 0.0;
 #pragma unroll
       for (int row = 0; row < 2; ++row) {
         const double g0 = G[row][0], g1 = G[row][1], g2 = G[row][2];
         // rotation (left perturbation q_delta * q, angle 2|delta|): d p / d delta = -2 [R X]_x
-        JC((6 * row + 0), k) = cs[0] * 2.0 * (g2 * pr1 - g1 * pr2);
-        JC((6 * row + 1), k) = cs[1] * 2.0 * (g0 * pr2 - g2 * pr0);
-        JC((6 * row + 2), k) = cs[2] * 2.0 * (g1 * pr0 - g0 * pr1);
-        JC((6 * row + 3), k) = cs[3] * g0;
-        JC((6 * row + 4), k) = cs[4] * g1;
-        JC((6 * row + 5), k) = cs[5] * g2;
+        jstore(&JC((6 * row + 0), kc), cs[0] * 2.0 * (g2 * pr1 - g1 * pr2), store_mode);
+        jstore(&JC((6 * row + 1), kc), cs[1] * 2.0 * (g0 * pr2 - g2 * pr0), store_mode);
+        jstore(&JC((6 * row + 2), kc), cs[2] * 2.0 * (g1 * pr0 - g0 * pr1), store_mode);
+        jstore(&JC((6 * row + 3), kc), cs[3] * g0, store_mode);
+        jstore(&JC((6 * row + 4), kc), cs[4] * g1, store_mode);
+        jstore(&JC((6 * row + 5), kc), cs[5] * g2, store_mode);
         // point: G R   (R = I + R..)
-        JP((3 * row + 0), k) = ps[0] * (g0 * (R00 + 1.0) + g1 * R10 + g2 * R20);
-        JP((3 * row + 1), k) = ps[1] * (g0 * R01 + g1 * (R11 + 1.0) + g2 * R21);
-        JP((3 * row + 2), k) = ps[2] * (g0 * R02 + g1 * R12 + g2 * (R22 + 1.0));
+        jstore(&JP((3 * row + 0), kc), ps[0] * (g0 * (R00 + 1.0) + g1 * R10 + g2 * R20), store_mode);
+        jstore(&JP((3 * row + 1), kc), ps[1] * (g0 * R01 + g1 * (R11 + 1.0) + g2 * R21), store_mode);
+        jstore(&JP((3 * row + 2), kc), ps[2] * (g0 * R02 + g1 * R12 + g2 * (R22 + 1.0)), store_mode);
       }
-      JR(0, k) = sr * r0;
-      JR(1, k) = sr * r1;
+      jstore(&JR(0, kc), sr * r0, store_mode);
+      jstore(&JR(1, kc), sr * r1, store_mode);
     }
   }
   const double total = block_sum(cost, red);
@@ -679,10 +707,11 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
     cudaMemsetAsync(d.scalars + kCost, 0, sizeof(double), s);
     return 0;
   }
-  // Persistent CTAs with the per-image table in shared memory when it fits next to 4 CTAs / SM;
+  // Persistent CTAs with the per-image table in shared memory when it fits (2 CTAs / SM);
   // otherwise one CTA per chunk gathering from global memory.
-  static int num_sms = 0, max_smem = 0;
+  static int num_sms = 0, max_smem = 0, store_mode = 0;
   if (num_sms == 0) {
+    store_mode = tune_int("PPSFM_BA_J_STREAM", 0);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
@@ -698,7 +727,7 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
   int blocks = chunks;
   if (use_smem) {
     int per_sm = (int)((size_t)(227 * 1024) / (tab_bytes + 1024));
-    per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);
+    per_sm = per_sm < 1 ? 1 : (per_sm > 2 ? 2 : per_sm);
     blocks = num_sms * per_sm;
     if (blocks > chunks) blocks = chunks;
   }
@@ -706,17 +735,17 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
   if (use_smem) {
     if (jacobians)
       ba_linearize_kernel<true, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
-                                                                          d.partials, chunks);
+                                                                          d.partials, chunks, store_mode);
     else
       ba_linearize_kernel<false, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
-                                                                           d.partials, chunks);
+                                                                           d.partials, chunks, store_mode);
   } else {
     if (jacobians)
       ba_linearize_kernel<true, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
-                                                                   chunks);
+                                                                   chunks, store_mode);
     else
       ba_linearize_kernel<false, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
-                                                                    chunks);
+                                                                    chunks, store_mode);
   }
   reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
                                             kCost, 0);

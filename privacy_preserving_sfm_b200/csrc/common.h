@@ -6,6 +6,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <random>
 #include <string>
 #include <vector>
@@ -100,6 +101,13 @@ inline int fail(ppsfm_ctx* ctx, int code, const char* fmt, ...) {
   va_end(ap);
   if (ctx) ctx->last_error = buf;
   return code;
+}
+
+// Development knob read from the environment (kernel variants under measurement); the defaults
+// are the shipped configuration.
+inline int tune_int(const char* name, int dflt) {
+  const char* v = std::getenv(name);
+  return (v && *v) ? std::atoi(v) : dflt;
 }
 
 #define PPSFM_CUDA(ctx, expr)                                                              \
