@@ -2,15 +2,26 @@
 //
 // In the reference this step is hidden inside ceres::Solve (SPARSE_SCHUR / DENSE_SCHUR,
 // src/optim/bundle_adjustment.cc:275-286).  The reduced camera matrix of a BA problem with
-// hundreds of cameras that all share points is dense, so it is factored densely:
-// blocked right-looking Cholesky on the lower triangle, 64-wide panels,
-//   panel kernel : every CTA re-factors the 64x64 diagonal block in shared memory (87 kflop,
-//                  cheaper than a separate launch + sync) and solves its own 64-row tile
-//   update kernel: trailing C_ij -= X_i X_j^T on 64x64 tiles with FP64 tensor-core MMA
-//                  (mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind), the one genuinely dense
-//                  contraction of the path
+// hundreds of cameras that all share points is dense, so it is factored densely.
+//
+// The factorisation of a 3000 x 3000 system is LATENCY bound (47 dependent 64-wide steps), not
+// flop bound (9 GFLOP), so it runs as ONE persistent dataflow kernel instead of ~140 dependent
+// launches:
+//   * the lower triangle is cut into 64x64 tiles; tile (i, j) is one task: accumulate
+//       C = A_ij - sum_{k<j} X_ik X_jk^T        (FP64 tensor-core MMA, mma.sync.m8n8k4.f64 —
+//                                                tcgen05 has no FP64 kind; the one genuinely
+//                                                dense contraction of the path)
+//     then   j == i : L_jj = chol(C)            (16x16 register-resident warp factorisations)
+//            j <  i : X_ij = C L_jj^-T          (blocked triangular solve on the tensor cores)
+//   * tasks are handed out through an atomic ticket in column-major order, so a task only ever
+//     waits for tasks with a smaller ticket (they are running or finished): no deadlock,
+//     whatever the number of resident CTAs;
+//   * a finished tile is published with a release store of its flag; consumers poll with acquire
+//     loads and stream the operand tiles through a cp.async double buffer (left-looking:
+//     accumulators stay in registers, no read-modify-write of the trailing matrix).
 // The right-hand side rides along as an extra matrix row ("bordered" factorisation), which
-// yields y = L^-1 rhs for free; the backward substitution L^T x = y runs block by block.
+// yields y = L^-1 rhs for free; the backward substitution L^T x = y is a second dataflow kernel
+// (one CTA per 64-block, chained by flags).
 //
 // Matrix layout: row-major, leading dimension ld (multiple of 64), rows [0, n) = S (lower
 // triangle referenced), row n = rhs^T, rows (n, ld) zero padding.
@@ -19,124 +30,240 @@
 
 namespace ppsfm {
 
+namespace {
+
 constexpr int NB = 64;
+constexpr int kCS = 68;  // row stride (doubles) of a 64x64 tile in shared memory
+constexpr int kKC = 32;  // k-chunk width of the operand pipeline
+constexpr int kKS = 36;  // row stride (doubles) of a 64x32 chunk in shared memory
+constexpr int kStageDoubles = 64 * kKS;
+constexpr int kFactorSmem = 2 * 2 * kStageDoubles * (int)sizeof(double);  // 73 728 B
+static_assert(2 * 64 * kCS * (int)sizeof(double) <= kFactorSmem, "tile pair must fit the stages");
 
+// ---- PTX helpers ---------------------------------------------------------------------------
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+__device__ __forceinline__ int ld_acquire(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(int* p, int v) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ double2 ld_cg2(const double* p) {
+  double2 v;
+  asm volatile("ld.global.cg.v2.f64 {%0,%1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+  return v;
+}
+__device__ __forceinline__ double ld_cg(const double* p) {
+  double v;
+  asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p));
+  return v;
+}
+// warp shuffle of a double without the convergence bookkeeping nvcc adds around __shfl_sync in
+// warp-specialised code
+__device__ __forceinline__ double shfl_d(double v, int src) {
+  int lo = __double2loint(v), hi = __double2hiint(v);
+  asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(lo) : "r"(src));
+  asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(hi) : "r"(src));
+  return __hiloint2double(hi, lo);
+}
+
+// Work-buffer layout (doubles unless noted): one Lpack and one Linv per 64-block, y/x scratch,
+// then the int flags.
+struct Work {
+  double* lpack;  // [nblk][64*64]  L_jj with its 16x16 diagonal sub-blocks replaced by their inverses
+  double* linv;   // [nblk][64*64]  dense L_jj^-1 (back-substitution)
+  int* flags;     // [0] factor ticket, [1] back-solve ticket, [2 .. 2+T*T) tile flags,
+                  // then [nblk] x flags
+};
+__host__ __device__ inline Work work_layout(double* base, int n) {
+  const size_t nblk = (size_t)(n + NB - 1) / NB;
+  Work w;
+  w.lpack = base;
+  w.linv = base + nblk * NB * NB;
+  w.flags = reinterpret_cast<int*>(base + 2 * nblk * NB * NB);
+  return w;
+}
+inline size_t work_flag_ints(int n) {
+  const size_t T = (size_t)(n + 1 + NB - 1) / NB, nblk = (size_t)(n + NB - 1) / NB;
+  return 2 + T * T + nblk;
+}
 
 // ------------------------------------------------------------------------------------------
-// Diagonal-block kernel (1 CTA, 256 threads): factors the 64x64 diagonal block and inverts its
-// Cholesky factor, so that the panel below becomes a plain matrix product X = A L^-T that runs
-// on the FP64 tensor cores.  Blocked in 16-wide sub-blocks: only the 16x16 factorisations (one
-// warp, rows in registers, shuffles) and their triangular inverses are sequential; panels and
-// trailing updates inside the block use all 256 threads.  A partial last block is padded with
-// the identity.  Outputs: L (lower) written back into A, L^-1 (lower, dense 64x64) into `linv`.
+// 16x16 Cholesky of the diagonal sub-block at (k1, k1) of the tile in shared memory, by ONE warp.
+// Lane i (< 16; the upper half-warp mirrors it) owns row i of the SYMMETRIC block, so the
+// rank-1 update a_ic -= a_ij a_jc / a_jj only needs row j broadcast from lane j — those shuffles
+// do not depend on the reciprocal of the pivot, which is the only long-latency operation on the
+// 16-step dependency chain (the square roots are off the chain).
+// Writes L (lower) back, and rdiag[k1 + j] = 1 / l_jj.
 // ------------------------------------------------------------------------------------------
-__device__ void diag_block(double* __restrict__ A, int ld, int n, int k0,
-                           double* __restrict__ linv, int* __restrict__ status,
-                           double* dyn_smem) {
-  double (*D)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem);  // block -> L
-  double (*Tm)[NB + 1] = reinterpret_cast<double (*)[NB + 1]>(dyn_smem + NB * (NB + 1));  // L^-1
-  double (*I16)[16][17] =  // inverses of the four 16x16 diagonal sub-blocks
-      reinterpret_cast<double (*)[16][17]>(dyn_smem + 2 * NB * (NB + 1));
-  __shared__ int ok;
+__device__ __forceinline__ bool factor16(double* Cs, int k1, double* rdiag, int lane) {
+  const int i = lane & 15;
+  double a[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    const int r0 = i > c ? i : c, c0 = i > c ? c : i;
+    a[c] = Cs[(k1 + r0) * kCS + k1 + c0];
+  }
+  __syncwarp();
+  bool bad = false;
+  double* lrow = Cs + (k1 + i) * kCS + k1;  // every lane has read its row: L can go in place
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    double u[16];
+#pragma unroll
+    for (int c = j; c < 16; ++c) u[c] = shfl_d(a[c], j);
+    double piv = u[j];
+    bad = bad || !(piv > 0.0);
+    piv = (piv > 0.0) ? piv : 1.0;
+    const double rinv = 1.0 / piv;
+    const double t = a[j] * rinv;
+#pragma unroll
+    for (int c = j + 1; c < 16; ++c) a[c] -= t * u[c];
+    const double rs = rsqrt(piv);  // off the chain
+    if (lane < 16 && i >= j) lrow[j] = (i == j) ? piv * rs : a[j] * rs;
+    if (lane == j) rdiag[k1 + j] = rs;
+  }
+  return bad;
+}
+
+// Inverse of the lower-triangular 16x16 block at (k1, k1) (one warp): the eliminations that
+// reduce L to the identity, applied to the identity.  Result (dense, zeros above the diagonal)
+// goes to the 16x16 block at `out`.
+__device__ __forceinline__ void invert16(const double* Cs, int k1, const double* rdiag,
+                                         double* out /* block origin, row stride kCS */,
+                                         int lane) {
+  const int i = lane & 15;
+  double l[16], m[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    l[c] = (c < i) ? Cs[(k1 + i) * kCS + k1 + c] : 0.0;
+    m[c] = (c == i) ? 1.0 : 0.0;
+  }
+  const double ri = rdiag[k1 + i];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) {
+    // row j is final once rows < j have been eliminated from it: scale by 1 / l_jj
+#pragma unroll
+    for (int c = 0; c <= j; ++c) {
+      const double mine = (i == j) ? m[c] * ri : m[c];
+      const double mj = shfl_d(mine, j);
+      m[c] = (i > j) ? mine - l[j] * mj : mine;
+    }
+  }
+  if (lane < 16) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c) out[i * kCS + c] = (c <= i) ? m[c] : 0.0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Diagonal task: Cs (64 x kCS, lower triangle valid) -> L_jj.  kb = number of real rows in this
+// block (< 64 only for the last block, whose tile also carries the right-hand-side row).
+// Publishes L (into A), Lpack (for the triangular solves of the tiles below) and then — off the
+// critical path — the dense inverse for the back-substitution.
+// ------------------------------------------------------------------------------------------
+__device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, int j, double* smem,
+                          const Work& w, int T, int* __restrict__ status) {
+  double* Cs = smem;                                   // [64][kCS]
+  double* Tm = smem + 64 * kCS;                        // [64][kCS] L^-1: 16x16 diagonal blocks
+                                                       // first, the rest after the publish
+  __shared__ double rdiag[NB];
+  __shared__ double rhs_row[NB];
+  __shared__ int s_bad;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int k0 = j * NB;
   const int kb = min(NB, n - k0);
-  if (tid == 0) ok = 1;
+  if (tid == 0) s_bad = 0;
+  if (kb < NB && tid < NB) rhs_row[tid] = (tid < kb) ? Cs[kb * kCS + tid] : 0.0;
+  __syncthreads();
+  // identity padding outside the real block, zeros above the diagonal
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx >> 6, c = idx & 63;
-    double v = 0.0;
-    if (r < kb && c <= r) v = A[(size_t)(k0 + r) * ld + k0 + c];
-    else if (r >= kb && c == r) v = 1.0;
-    D[r][c] = v;
-    Tm[r][c] = 0.0;
+    if (r >= kb || c >= kb) Cs[r * kCS + c] = (r == c) ? 1.0 : 0.0;
+    else if (c > r) Cs[r * kCS + c] = 0.0;
   }
+  for (int idx = tid; idx < NB * kCS; idx += 256) Tm[idx] = 0.0;
   __syncthreads();
 #pragma unroll 1
   for (int bk = 0; bk < 4; ++bk) {
     const int k1 = 16 * bk;
-    {
-      // (a)+(b) 16x16 Cholesky with its inverse: lane i (< 16) owns row i of the block (a[]) and
-      // row i of the accumulated elimination transform (m[], starts as e_i).  Applying the
-      // eliminations of step j (scale row j by 1/l_jj, subtract l_ij x row j from rows i > j) to
-      // the identity yields L^-1 — no divisions, no second sequential pass.
-      // ALL warps execute this redundantly (only warp 0 stores): inside a warp-specialised
-      // branch every shuffle compiles to a ~30-cycle WARPSYNC.COLLECTIVE sequence; in uniform
-      // control flow it is a plain SHFL.  The other warps would idle anyway.
-      const int i = lane & 15;
-      double a[16], m[16];
-#pragma unroll
-      for (int c = 0; c < 16; ++c) {
-        a[c] = (lane < 16 && c <= i) ? D[k1 + i][k1 + c] : 0.0;
-        m[c] = (c == i) ? 1.0 : 0.0;
-      }
-      bool bad = false;
-#pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        double ajj = __shfl_sync(0xffffffffu, a[j], j);
-        bad = bad || !(ajj > 0.0);
-        ajj = (ajj > 0.0) ? ajj : 1.0;
-        const double inv = rsqrt(ajj);
-        const double lij = (i == j) ? ajj * inv : a[j] * inv;
-        a[j] = (i >= j) ? lij : 0.0;
-#pragma unroll
-        for (int c = 0; c <= j; ++c) {
-          const double mc = (i == j) ? m[c] * inv : m[c];
-          const double mjc = __shfl_sync(0xffffffffu, mc, j);
-          m[c] = (i > j) ? mc - a[j] * mjc : mc;
-        }
-#pragma unroll
-        for (int c = j + 1; c < 16; ++c) {
-          const double lcj = __shfl_sync(0xffffffffu, a[j], c);
-          a[c] = (i >= c) ? a[c] - a[j] * lcj : a[c];
-        }
-      }
-      __syncthreads();  // all warps are done reading the sub-block
-      if (warp == 0) {
-        if (bad && lane == 0) ok = 0;
-        if (lane < 16) {
-#pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            if (c <= i) D[k1 + i][k1 + c] = a[c];
-            I16[bk][i][c] = (c <= i) ? m[c] : 0.0;
-          }
-        }
-      }
+    if (warp == 0) {
+      const bool bad = factor16(Cs, k1, rdiag, lane);
+      if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
-    const int below = NB - (k1 + 16);  // rows under this sub-block
+    const int below = NB - (k1 + 16);
     if (below > 0) {
-      // (c) panel: X[r][c] = sum_{p <= c} A[r][k1+p] * I16[c][p]
-      double xv[3];
-      int cnt = 0;
-      for (int idx = tid; idx < below * 16; idx += 256, ++cnt) {
-        const int r = k1 + 16 + idx / 16, c = idx % 16;
-        double acc = 0.0;
+      // panel: row r of X = A_r L^-T by forward substitution, one thread per row
+      if (tid < below) {
+        double* rowp = Cs + (k1 + 16 + tid) * kCS + k1;
+        double x[16];
 #pragma unroll
-        for (int p2 = 0; p2 < 16; ++p2) acc += D[r][k1 + p2] * I16[bk][c][p2];
-        xv[cnt] = acc;
+        for (int c = 0; c < 16; ++c) x[c] = rowp[c];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+          x[c] *= rdiag[k1 + c];
+#pragma unroll
+          for (int p = c + 1; p < 16; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) rowp[c] = x[c];
       }
       __syncthreads();
-      cnt = 0;
-      for (int idx = tid; idx < below * 16; idx += 256, ++cnt)
-        D[k1 + 16 + idx / 16][k1 + idx % 16] = xv[cnt];
-      __syncthreads();
-      // (d) trailing update inside the block (lower part)
-      for (int idx = tid; idx < below * below; idx += 256) {
-        const int r = k1 + 16 + idx / below, c = k1 + 16 + idx % below;
-        if (c > r) continue;
-        double acc = 0.0;
+      // trailing update inside the tile (lower part)
+      const int cnt = below * (below + 1) / 2;
+      for (int idx = tid; idx < cnt; idx += 256) {
+        int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
+        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
+        while (r * (r + 1) / 2 > idx) --r;
+        const int c = idx - r * (r + 1) / 2;
+        const double* xr = Cs + (k1 + 16 + r) * kCS + k1;
+        const double* xc = Cs + (k1 + 16 + c) * kCS + k1;
+        double acc0 = 0.0, acc1 = 0.0;
 #pragma unroll
-        for (int p2 = 0; p2 < 16; ++p2) acc += D[r][k1 + p2] * D[c][k1 + p2];
-        D[r][c] -= acc;
+        for (int p = 0; p < 16; p += 2) {
+          acc0 += xr[p] * xc[p];
+          acc1 += xr[p + 1] * xc[p + 1];
+        }
+        Cs[(k1 + 16 + r) * kCS + k1 + 16 + c] -= acc0 + acc1;
       }
       __syncthreads();
     }
   }
-  // L^-1 by block forward substitution: Linv[bi][bj] = -I16[bi] * sum_{bk=bj}^{bi-1} L[bi][bk] Linv[bk][bj]
-  for (int idx = tid; idx < 4 * 256; idx += 256) {
-    const int b = idx >> 8, r = (idx >> 4) & 15, c = idx & 15;
-    Tm[16 * b + r][16 * b + c] = I16[b][r][c];
+  if (warp < 4) invert16(Cs, 16 * warp, rdiag, Tm + (16 * warp) * kCS + 16 * warp, lane);
+  __syncthreads();
+  // publish: L into A (real rows), Lpack into the work buffer
+  double* lpack = w.lpack + (size_t)j * NB * NB;
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    const double v = Cs[r * kCS + c];
+    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = v;
+    const int br = r >> 4, bc = c >> 4;
+    lpack[idx] = (br == bc) ? Tm[r * kCS + c] : v;
   }
   __syncthreads();
+  if (tid == 0) {
+    if (s_bad) atomicExch(status, 1);
+    __threadfence();
+    st_release(w.flags + 2 + j * T + j, 1);
+  }
+  // ---- off the critical path: dense L^-1 by block forward substitution
+  //      Linv[bi][bj] = -I16[bi] * sum_{bk = bj}^{bi-1} L[bi][bk] Linv[bk][bj]
 #pragma unroll 1
   for (int dist = 1; dist < 4; ++dist) {
     const int nblk = 4 - dist;  // blocks (bi = bj + dist, bj)
@@ -145,14 +272,15 @@ __device__ void diag_block(double* __restrict__ A, int ld, int n, int k0,
     for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
       const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
       double acc = 0.0;
-      for (int p2 = 16 * bj; p2 < 16 * bi; ++p2) acc += D[16 * bi + r][p2] * Tm[p2][16 * bj + c];
+      for (int p2 = 16 * bj; p2 < 16 * bi; ++p2)
+        acc += Cs[(16 * bi + r) * kCS + p2] * Tm[p2 * kCS + 16 * bj + c];
       tmp[cnt] = acc;
     }
-    // tmp -> scratch region above the diagonal of Tm (unused otherwise): Tm[bj-rows][bi-cols]
+    // tmp -> scratch above the diagonal of Tm (unused otherwise): Tm[bj-rows][bi-cols]
     cnt = 0;
     for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
       const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      Tm[16 * bj + r][16 * bi + c] = tmp[cnt];
+      Tm[(16 * bj + r) * kCS + 16 * bi + c] = tmp[cnt];
     }
     __syncthreads();
     cnt = 0;
@@ -160,224 +288,331 @@ __device__ void diag_block(double* __restrict__ A, int ld, int n, int k0,
       const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
       double acc = 0.0;
 #pragma unroll
-      for (int p2 = 0; p2 < 16; ++p2) acc += I16[bi][r][p2] * Tm[16 * bj + p2][16 * bi + c];
+      for (int p2 = 0; p2 < 16; ++p2)
+        acc += Tm[(16 * bi + r) * kCS + 16 * bi + p2] * Tm[(16 * bj + p2) * kCS + 16 * bi + c];
       tmp[cnt] = -acc;
     }
     __syncthreads();
     cnt = 0;
     for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
       const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      Tm[16 * bi + r][16 * bj + c] = tmp[cnt];
+      Tm[(16 * bi + r) * kCS + 16 * bj + c] = tmp[cnt];
     }
     __syncthreads();
   }
+  double* linv = w.linv + (size_t)j * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
     const int r = idx >> 6, c = idx & 63;
-    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = D[r][c];
-    linv[idx] = (c <= r) ? Tm[r][c] : 0.0;
+    linv[idx] = (c <= r) ? Tm[r * kCS + c] : 0.0;
+  }
+  // the right-hand-side row of the last, partial block: y = rhs L^-T
+  if (kb < NB && tid < kb) {
+    double acc = 0.0;
+    for (int p = 0; p <= tid; ++p) acc += rhs_row[p] * Tm[tid * kCS + p];
+    A[(size_t)n * ld + k0 + tid] = acc;
   }
   __syncthreads();
-  if (tid == 0 && !ok) atomicExch(status, 1);
 }
 
-__global__ void __launch_bounds__(256)
-chol_diag_kernel(double* __restrict__ A, int ld, int n, int k0, double* __restrict__ linv,
-                 int* __restrict__ status) {
-  extern __shared__ __align__(16) double dyn_smem_diag[];
-  diag_block(A, ld, n, k0, linv, status, dyn_smem_diag);
-}
-
-// Trailing update with FP64 tensor cores: C(ti, tj) -= X_ti X_tj^T for tiles ti >= tj below /
-// right of the panel.  One CTA (8 warps) per 64x64 tile; warp w owns rows 8w..8w+7 of the tile and
-// all 64 columns as eight m8n8k4 accumulators.
-__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-               : "+d"(c0), "+d"(c1)
-               : "d"(a), "d"(b));
-}
-
-// One 64x64 output tile per CTA (8 warps; warp w owns rows 8w..8w+7 as eight m8n8k4 accumulators):
-//   kPanel == false: trailing update  C(ti, tj) -= X_ti X_tj^T  for tiles ti >= tj
-//   kPanel == true : panel            X_t = A_t Linv^T           (A_t overwritten in place)
-template <bool kPanel>
-__global__ void __launch_bounds__(256)
-chol_tile_kernel(double* __restrict__ A, int ld, int k0, int kb, int first_tile_row,
-                 const double* __restrict__ linv, int n, double* __restrict__ linv_next,
-                 int* __restrict__ status) {
-  int ti, tj;
-  if (kPanel) {
-    ti = blockIdx.x;
-    tj = 0;
-  } else {
-    const int t = blockIdx.x;
-    ti = (int)floor((sqrt(8.0 * t + 1.0) - 1.0) * 0.5);
-    while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-    while (ti * (ti + 1) / 2 > t) --ti;
-    tj = t - ti * (ti + 1) / 2;
-  }
-  const int ri = first_tile_row + ti * NB, rj = first_tile_row + tj * NB;
-  extern __shared__ __align__(16) double dyn_smem[];
-  double (*Xi)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem);
-  double (*Xj)[NB + 4] = reinterpret_cast<double (*)[NB + 4]>(dyn_smem + NB * (NB + 4));
-  const int tid = threadIdx.x;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    Xi[r][c] = (c < kb && ri + r < ld) ? A[(size_t)(ri + r) * ld + k0 + c] : 0.0;
-    if (kPanel)
-      Xj[r][c] = linv[idx];
-    else
-      Xj[r][c] = (c < kb) ? A[(size_t)(rj + r) * ld + k0 + c] : 0.0;
+// ------------------------------------------------------------------------------------------
+// Off-diagonal task: X = C L_jj^-T for the 64x64 tile in Cs, warp-local (warp w owns rows
+// 8w..8w+7), in four 16-column steps:  X_b = (C_b - sum_{b'<b} X_b' L_bb'^T) inv(L_bb)^T.
+// acc[nb] are the tile's C fragments (nb = 8-column block).
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i, int j,
+                                          double (&acc)[8][2], double* smem, const Work& w,
+                                          int T) {
+  double* Xs = smem;             // [64][kCS]: own rows, X blocks as they are produced
+  double* Lp = smem + 64 * kCS;  // [64][kCS]: Lpack_j
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int row = warp * 8 + g;
+  if (tid == 0) {
+    const int* f = w.flags + 2 + j * T + j;
+    while (ld_acquire(f) == 0) __nanosleep(20);
   }
   __syncthreads();
-  const int warp = tid >> 5, lane = tid & 31;
-  const int g = lane >> 2, q = lane & 3;  // mma fragment coordinates
-  double acc[8][2];
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb) acc[nb][0] = acc[nb][1] = 0.0;
-  const int row = warp * 8 + g;  // A fragment: a = A[row = g][k = q]
-#pragma unroll 4
-  for (int kk = 0; kk < NB; kk += 4) {
-    const double a = Xi[row][kk + q];
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const double b = Xj[nb * 8 + g][kk + q];  // B fragment (col-major k x n): B[k = q][n = g]
-      dmma_m8n8k4(acc[nb][0], acc[nb][1], a, b);
+  {
+    const double* src = w.lpack + (size_t)j * NB * NB;
+    for (int p = tid; p < NB * 32; p += 256) {  // 16-byte pieces
+      const int r = p >> 5, s = p & 31;
+      cp_async16(Lp + r * kCS + 2 * s, src + r * NB + 2 * s);
     }
+    cp_async_commit();
+    cp_async_wait<0>();
   }
-  // C fragment: c0 = C[g][2q], c1 = C[g][2q+1]
-  if (kPanel) {
-    if (ri + row < ld) {
+  __syncthreads();
+#pragma unroll
+  for (int b = 0; b < 4; ++b) {
+    double t0[2] = {acc[2 * b][0], acc[2 * b][1]};
+    double t1[2] = {acc[2 * b + 1][0], acc[2 * b + 1][1]};
+#pragma unroll
+    for (int kk = 0; kk < 16 * b; kk += 4) {
+      const double a = -Xs[row * kCS + kk + q];
+      const double b0 = Lp[(16 * b + g) * kCS + kk + q];
+      const double b1 = Lp[(16 * b + 8 + g) * kCS + kk + q];
+      dmma_m8n8k4(t0[0], t0[1], a, b0);
+      dmma_m8n8k4(t1[0], t1[1], a, b1);
+    }
+    // T (C-fragment layout) -> shared memory -> A-fragment layout; rows are warp-private
+    *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 2 * q) = make_double2(t0[0], t0[1]);
+    *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 8 + 2 * q) = make_double2(t1[0], t1[1]);
+    __syncwarp();
+    double x0[2] = {0.0, 0.0}, x1[2] = {0.0, 0.0};
+#pragma unroll
+    for (int kk = 0; kk < 16; kk += 4) {
+      const double a = Xs[row * kCS + 16 * b + kk + q];
+      const double b0 = Lp[(16 * b + g) * kCS + 16 * b + kk + q];
+      const double b1 = Lp[(16 * b + 8 + g) * kCS + 16 * b + kk + q];
+      dmma_m8n8k4(x0[0], x0[1], a, b0);
+      dmma_m8n8k4(x1[0], x1[1], a, b1);
+    }
+    __syncwarp();
+    *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 2 * q) = make_double2(x0[0], x0[1]);
+    *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 8 + 2 * q) = make_double2(x1[0], x1[1]);
+    __syncwarp();
+    double* dst = A + (size_t)(i * NB + row) * ld + j * NB + 16 * b + 2 * q;
+    *reinterpret_cast<double2*>(dst) = make_double2(x0[0], x0[1]);
+    *reinterpret_cast<double2*>(dst + 8) = make_double2(x1[0], x1[1]);
+  }
+  __syncthreads();
+  if (tid == 0) {
+    __threadfence();
+    st_release(w.flags + 2 + i * T + j, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The factorisation kernel: persistent CTAs (256 threads) pulling tile tasks from a ticket.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 3)
+chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ work_base,
+                   int* __restrict__ status) {
+  extern __shared__ __align__(16) double smem[];
+  __shared__ int s_ticket, s_ready;
+  const Work w = work_layout(work_base, n);
+  const int T = ld / NB;
+  const int ncols = (n + NB - 1) / NB;
+  const int ntiles = ncols * T - ncols * (ncols - 1) / 2;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  const int row = warp * 8 + g;
+  int* tile_flags = w.flags + 2;
+
+  for (;;) {
+    __syncthreads();  // previous task is completely done with shared memory
+    if (tid == 0) s_ticket = atomicAdd(w.flags, 1);
+    __syncthreads();
+    const int t = s_ticket;
+    if (t >= ntiles) break;
+    // column-major order, diagonal tile first: column j starts at j*T - j(j-1)/2
+    int j = 0, off = 0;
+    while (j + 1 < ncols && off + (T - j) <= t) {
+      off += T - j;
+      ++j;
+    }
+    const int i = j + (t - off);
+
+    // accumulators start as A_ij; the k loop subtracts X_ik X_jk^T
+    double acc[8][2];
+    {
+      const double* src = A + (size_t)(i * NB + row) * ld + j * NB + 2 * q;
 #pragma unroll
       for (int nb = 0; nb < 8; ++nb) {
-        const int c = nb * 8 + 2 * q;
-        double* dst = A + (size_t)(ri + row) * ld + k0 + c;
-        if (c < kb) dst[0] = acc[nb][0];
-        if (c + 1 < kb) dst[1] = acc[nb][1];
+        const double2 v = ld_cg2(src + 8 * nb);
+        acc[nb][0] = v.x;
+        acc[nb][1] = v.y;
       }
     }
-  } else {
-#pragma unroll
-    for (int nb = 0; nb < 8; ++nb) {
-      const int c = nb * 8 + 2 * q;
-      double* dst = A + (size_t)(ri + row) * ld + rj + c;
-      if (ti != tj || c <= row) dst[0] -= acc[nb][0];
-      if (ti != tj || c + 1 <= row) dst[1] -= acc[nb][1];
-    }
-    // Look-ahead: tile (0, 0) is the next diagonal block.  Its CTA factors (and inverts) it right
-    // away, overlapped with the rest of this trailing update, so the sequential 64x64
-    // factorisation leaves the critical path of the next step.
-    if (blockIdx.x == 0 && linv_next != nullptr && first_tile_row < n) {
-      __threadfence_block();
+    const int nchunks = 2 * j;
+    const bool diag = (i == j);
+    int issued = 0, known_k = 0;  // chunks issued; operand tiles of columns < known_k are ready
+    auto issue = [&](int c) {
+      const int k = c >> 1, half = c & 1, st = c & 1;
+      double* si = smem + (size_t)(st * 2) * kStageDoubles;
+      double* sj = si + kStageDoubles;
+      const double* gi = A + (size_t)(i * NB) * ld + k * NB + half * kKC;
+      const double* gj = A + (size_t)(j * NB) * ld + k * NB + half * kKC;
+      for (int p = tid; p < 64 * 16; p += 256) {
+        const int r = p >> 4, s = p & 15;
+        cp_async16(si + r * kKS + 2 * s, gi + (size_t)r * ld + 2 * s);
+        if (!diag) cp_async16(sj + r * kKS + 2 * s, gj + (size_t)r * ld + 2 * s);
+      }
+      cp_async_commit();
+    };
+    for (int c = 0; c < nchunks; ++c) {
+      // keep up to two chunks in flight; block on a flag only when there is nothing to compute
+      while (issued < nchunks && issued < c + 2) {
+        const int k = issued >> 1;
+        if (k >= known_k) {
+          const bool must = (issued == c);
+          if (tid == 0) {
+            const int* fi = tile_flags + i * T + k;
+            const int* fj = tile_flags + j * T + k;
+            int ok = (ld_acquire(fi) != 0) && (ld_acquire(fj) != 0);
+            while (!ok && must) {
+              __nanosleep(20);
+              ok = (ld_acquire(fi) != 0) && (ld_acquire(fj) != 0);
+            }
+            s_ready = ok;
+          }
+          __syncthreads();
+          const int ok = s_ready;
+          __syncthreads();
+          if (!ok) break;
+          known_k = k + 1;
+        }
+        issue(issued);
+        ++issued;
+      }
+      if (issued - c - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
       __syncthreads();
-      diag_block(A, ld, n, first_tile_row, linv_next, status, dyn_smem);
+      const int st = c & 1;
+      const double* Xi = smem + (size_t)(st * 2) * kStageDoubles;
+      const double* Xj = diag ? Xi : Xi + kStageDoubles;
+#pragma unroll
+      for (int kk = 0; kk < kKC; kk += 4) {
+        const double a = -Xi[row * kKS + kk + q];
+#pragma unroll
+        for (int nb = 0; nb < 8; ++nb) {
+          const double b = Xj[(nb * 8 + g) * kKS + kk + q];
+          dmma_m8n8k4(acc[nb][0], acc[nb][1], a, b);
+        }
+      }
+      __syncthreads();  // stage st may be overwritten
+    }
+    if (diag) {
+      // C fragments -> shared tile
+#pragma unroll
+      for (int nb = 0; nb < 8; ++nb)
+        *reinterpret_cast<double2*>(smem + row * kCS + nb * 8 + 2 * q) =
+            make_double2(acc[nb][0], acc[nb][1]);
+      __syncthreads();
+      diag_task(A, ld, n, j, smem, w, T, status);
+    } else {
+      trsm_task(A, ld, i, j, acc, smem, w, T);
     }
   }
 }
 
-// Backward substitution L^T x = y, one launch per 64-block (descending).  Every CTA recomputes
-// x_b = L_bb^-T y_b from the stored inverse (a 64x64 mat-vec); CTA j < b then applies
-// y_j -= L[b][j]^T x_b on its own 64 columns, CTA b stores x_b.  y and x are distinct buffers.
+// ------------------------------------------------------------------------------------------
+// Backward substitution L^T x = y as a dataflow kernel: one CTA per 64-block (descending by
+// ticket).  CTA j streams the tiles L[b][j], b > j, through a cp.async double buffer, applies
+// y_j -= L[b][j]^T x_b as soon as x_b is published, then x_j = L_jj^-T y_j.
+// ------------------------------------------------------------------------------------------
+constexpr int kBackSmem = 3 * NB * NB * (int)sizeof(double);
+
 __global__ void __launch_bounds__(256)
-chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, int b,
-                      const double* __restrict__ linv_all, double* __restrict__ y,
+chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ work_base,
                       double* __restrict__ x) {
-  __shared__ double yb[NB], xb[NB], red[4][NB];
+  extern __shared__ __align__(16) double smem[];
+  __shared__ double yj[NB], xb[NB], red[4][NB];
+  __shared__ int s_ticket;
+  const Work w = work_layout(work_base, n);
+  const int T = ld / NB;
+  const int nblk = (n + NB - 1) / NB;
+  int* xflags = w.flags + 2 + T * T;
   const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
-  const int k0 = b * NB;
+  if (tid == 0) s_ticket = atomicAdd(w.flags + 1, 1);
+  __syncthreads();
+  const int j = nblk - 1 - s_ticket;
+  if (j < 0) return;
+  const int k0 = j * NB;
   const int kb = min(NB, n - k0);
-  const double* linv = linv_all + (size_t)b * NB * NB;
-  if (tid < NB) yb[tid] = (tid < kb) ? y[k0 + tid] : 0.0;
+  double* Linv = smem;                 // [64][64]
+  double* stage0 = smem + NB * NB;     // two tile stages
+  auto issue_tile = [&](int b, int st) {
+    double* dst = stage0 + (size_t)st * NB * NB;
+    const double* src = A + (size_t)(b * NB) * ld + k0;
+    for (int p = tid; p < NB * 32; p += 256) {
+      const int r = p >> 5, s = p & 31;
+      cp_async16(dst + r * NB + 2 * s, src + (size_t)r * ld + 2 * s);
+    }
+    cp_async_commit();
+  };
+  {
+    const double* src = w.linv + (size_t)j * NB * NB;
+    for (int p = tid; p < NB * 32; p += 256) cp_async16(Linv + 2 * p, src + 2 * p);
+    cp_async_commit();
+  }
+  if (tid < NB) yj[tid] = (tid < kb) ? ld_cg(A + (size_t)n * ld + k0 + tid) : 0.0;
+  int issued_b = nblk - 1;  // next tile to issue
+  for (int cnt = 0; cnt < 2 && issued_b > j; ++cnt, --issued_b) issue_tile(issued_b, (nblk - 1 - issued_b) & 1);
+  for (int b = nblk - 1; b > j; --b) {
+    const int st = (nblk - 1 - b) & 1;
+    if (tid == 0) {
+      while (ld_acquire(xflags + b) == 0) __nanosleep(20);
+    }
+    // tile b has been issued; at most one younger group is in flight
+    if (issued_b < b - 1) cp_async_wait<1>(); else cp_async_wait<0>();
+    __syncthreads();
+    const int kbb = min(NB, n - b * NB);
+    if (tid < NB) xb[tid] = (tid < kbb) ? ld_cg(x + b * NB + tid) : 0.0;
+    __syncthreads();
+    const double* Lt = stage0 + (size_t)st * NB * NB;
+    double s = 0.0;
+#pragma unroll 4
+    for (int r = part; r < kbb; r += 4) s += Lt[r * NB + c] * xb[r];
+    red[part][c] = s;
+    __syncthreads();
+    if (tid < NB) yj[tid] -= red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    // stage st is free again
+    if (issued_b > j) {
+      issue_tile(issued_b, (nblk - 1 - issued_b) & 1);
+      --issued_b;
+    }
+    __syncthreads();
+  }
+  cp_async_wait<0>();
   __syncthreads();
   {
     double s = 0.0;
-    for (int r = part; r < NB; r += 4) s += linv[r * NB + c] * yb[r];  // (L^-1)^T y
+#pragma unroll 4
+    for (int r = part; r < NB; r += 4) s += Linv[r * NB + c] * yj[r];  // (L^-1)^T y
     red[part][c] = s;
   }
   __syncthreads();
-  if (tid < NB) xb[tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+  if (tid < kb) x[k0 + tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
   __syncthreads();
-  const int j = blockIdx.x;
-  if (j == b) {
-    if (tid < kb) x[k0 + tid] = xb[tid];
-    return;
+  if (tid == 0) {
+    __threadfence();
+    st_release(xflags + j, 1);
   }
-  double s = 0.0;
-  for (int r = part; r < kb; r += 4) s += A[(size_t)(k0 + r) * ld + j * NB + c] * xb[r];
-  red[part][c] = s;
-  __syncthreads();
-  if (part == 0) y[j * NB + c] -= red[0][c] + red[1][c] + red[2][c] + red[3][c];
 }
 
-__global__ void chol_extract_y_kernel(const double* __restrict__ A, int ld, int n,
-                                      double* __restrict__ y) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) y[i] = A[(size_t)n * ld + i];
-}
+}  // namespace
 
 int chol_ld(int n) { return ((n + 1 + NB - 1) / NB) * NB; }
 size_t chol_work_doubles(int n) {
   const size_t nblk = (size_t)(n + NB - 1) / NB;
-  return nblk * NB * NB + nblk * NB + NB;  // one L^-1 per diagonal block + y
+  return 2 * nblk * NB * NB + (work_flag_ints(n) + 1) / 2 + 2;
 }
 
 // Factor + solve.  A: ld x ld (see header).  x: n doubles (device).  status: device int, set to
 // 1 if a non-positive pivot was met.  Asynchronous on `s`; returns the number of launches.
-int chol_solve_bordered(double* A, int n, int ld, double* x, double* linv, int* status,
+int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* status,
                         cudaStream_t s) {
-  constexpr int kTileSmem = 2 * NB * (NB + 4) * (int)sizeof(double);
-  constexpr int kDiagSmem = (2 * NB * (NB + 1) + 4 * 16 * 17) * (int)sizeof(double);
-  constexpr int kUpdateSmem = kDiagSmem > kTileSmem ? kDiagSmem : kTileSmem;  // look-ahead reuse
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(chol_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kDiagSmem);
-    cudaFuncSetAttribute(chol_tile_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kUpdateSmem);
-    cudaFuncSetAttribute(chol_tile_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kTileSmem);
-    attr_set = true;
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kFactorSmem);
+    cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         kBackSmem);
   }
-  int launches = 0;
+  const Work w = work_layout(work, n);
   cudaMemsetAsync(status, 0, sizeof(int), s);
-  bool diag_done = false;  // diagonal block k already factored by the previous update kernel
-  for (int k0 = 0; k0 < n; k0 += NB) {
-    const int kb = (n - k0 < NB) ? (n - k0) : NB;
-    const int r0 = k0 + kb;
-    double* linv_k = linv + (size_t)(k0 / NB) * NB * NB;
-    if (!diag_done) {
-      chol_diag_kernel<<<1, 256, kDiagSmem, s>>>(A, ld, n, k0, linv_k, status);
-      ++launches;
-    }
-    diag_done = false;
-    // row tiles below the diagonal block (they include the rhs row); for the last, partial
-    // block the remaining rows (rhs + padding) start unaligned and fit in one guarded tile
-    const int tiles = (ld - r0 + NB - 1) / NB;
-    if (tiles > 0) {
-      chol_tile_kernel<true><<<tiles, 256, kTileSmem, s>>>(A, ld, k0, kb, r0, linv_k, n, nullptr,
-                                                           status);
-      ++launches;
-    }
-    if (r0 < ld && kb == NB) {
-      const int nt = (ld - r0) / NB;
-      const int ntiles = nt * (nt + 1) / 2;
-      if (ntiles > 0) {
-        double* linv_next = (r0 < n) ? linv_k + NB * NB : nullptr;
-        chol_tile_kernel<false><<<ntiles, 256, kUpdateSmem, s>>>(A, ld, k0, kb, r0, nullptr, n,
-                                                                  linv_next, status);
-        ++launches;
-        diag_done = (linv_next != nullptr);
-      }
-    }
-  }
-  const int nblk = (n + NB - 1) / NB;
-  double* y = linv + (size_t)nblk * NB * NB;  // y = L^-1 rhs (the bordered row), then consumed
-  chol_extract_y_kernel<<<(n + 255) / 256, 256, 0, s>>>(A, ld, n, y);
-  ++launches;
-  for (int b = nblk - 1; b >= 0; --b) {
-    chol_backsolve_kernel<<<b + 1, 256, 0, s>>>(A, ld, n, b, linv, y, x);
-    ++launches;
-  }
-  return launches;
+  cudaMemsetAsync(w.flags, 0, sizeof(int) * work_flag_ints(n), s);
+  const int T = ld / NB;
+  const int ncols = (n + NB - 1) / NB;
+  const int ntiles = ncols * T - ncols * (ncols - 1) / 2;
+  int grid = 3 * num_sms;
+  if (grid > ntiles) grid = ntiles;
+  chol_factor_kernel<<<grid, 256, kFactorSmem, s>>>(A, ld, n, work, status);
+  chol_backsolve_kernel<<<ncols, 256, kBackSmem, s>>>(A, ld, n, work, x);
+  return 2;
 }
 
 }  // namespace ppsfm

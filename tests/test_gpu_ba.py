@@ -34,7 +34,7 @@ def _gauge_flags(n):
     return f
 
 
-@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 130, 600, 1000])
+@pytest.mark.parametrize("n", [1, 5, 16, 17, 63, 64, 65, 127, 128, 130, 192, 600, 1000, 2994])
 def test_dense_cholesky_solve(ctx, n):
     rng = np.random.default_rng(n)
     M = rng.normal(size=(n, n))
