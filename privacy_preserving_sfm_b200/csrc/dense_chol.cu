@@ -82,6 +82,17 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// Optional per-tile event trace (PPSFM_CHOL_TRACE=<file>): 16 timestamp slots per tile.
+#define CHOL_TRACE(slot)                                                          \
+  do {                                                                            \
+    if (trace != nullptr && threadIdx.x == 0) trace[16 * (size_t)(i * T + j) + (slot)] = global_ns(); \
+  } while (0)
+
 // Work-buffer layout (doubles unless noted): one Lpack and one Linv per 64-block, y/x scratch,
 // then the int flags.
 struct Work {
@@ -178,14 +189,19 @@ __device__ __forceinline__ void invert16(const double* Cs, int k1, const double*
 // critical path — the dense inverse for the back-substitution.
 // ------------------------------------------------------------------------------------------
 __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, int j, double* smem,
-                          const Work& w, int T, int* __restrict__ status) {
+                          const Work& w, int T, int* __restrict__ status,
+                          unsigned long long* __restrict__ trace) {
+  const int i = j;
   double* Cs = smem;                                   // [64][kCS]
   double* Tm = smem + 64 * kCS;                        // [64][kCS] L^-1: 16x16 diagonal blocks
                                                        // first, the rest after the publish
   __shared__ double rdiag[NB];
   __shared__ double rhs_row[NB];
   __shared__ int s_bad;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
+  // warp index broadcast from lane 0: the compiler then knows the warp-specialised branches
+  // below are warp-uniform and emits plain SHFL instead of WARPSYNC.COLLECTIVE sequences
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int k0 = j * NB;
   const int kb = min(NB, n - k0);
   if (tid == 0) s_bad = 0;
@@ -199,6 +215,7 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
   }
   for (int idx = tid; idx < NB * kCS; idx += 256) Tm[idx] = 0.0;
   __syncthreads();
+  CHOL_TRACE(4);
 #pragma unroll 1
   for (int bk = 0; bk < 4; ++bk) {
     const int k1 = 16 * bk;
@@ -207,6 +224,7 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
       if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
+    CHOL_TRACE(5 + 2 * bk);
     const int below = NB - (k1 + 16);
     if (below > 0) {
       // panel: row r of X = A_r L^-T by forward substitution, one thread per row
@@ -243,10 +261,12 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
         Cs[(k1 + 16 + r) * kCS + k1 + 16 + c] -= acc0 + acc1;
       }
       __syncthreads();
+      CHOL_TRACE(6 + 2 * bk);
     }
   }
   if (warp < 4) invert16(Cs, 16 * warp, rdiag, Tm + (16 * warp) * kCS + 16 * warp, lane);
   __syncthreads();
+  CHOL_TRACE(13);
   // publish: L into A (real rows), Lpack into the work buffer
   double* lpack = w.lpack + (size_t)j * NB * NB;
   for (int idx = tid; idx < NB * NB; idx += 256) {
@@ -257,11 +277,13 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
     lpack[idx] = (br == bc) ? Tm[r * kCS + c] : v;
   }
   __syncthreads();
+  CHOL_TRACE(14);
   if (tid == 0) {
     if (s_bad) atomicExch(status, 1);
     __threadfence();
     st_release(w.flags + 2 + j * T + j, 1);
   }
+  CHOL_TRACE(2);
   // ---- off the critical path: dense L^-1 by block forward substitution
   //      Linv[bi][bj] = -I16[bi] * sum_{bk = bj}^{bi-1} L[bi][bk] Linv[bk][bj]
 #pragma unroll 1
@@ -321,7 +343,7 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i, int j,
                                           double (&acc)[8][2], double* smem, const Work& w,
-                                          int T) {
+                                          int T, unsigned long long* __restrict__ trace) {
   double* Xs = smem;             // [64][kCS]: own rows, X blocks as they are produced
   double* Lp = smem + 64 * kCS;  // [64][kCS]: Lpack_j
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -380,6 +402,7 @@ __device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i,
     __threadfence();
     st_release(w.flags + 2 + i * T + j, 1);
   }
+  CHOL_TRACE(2);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -387,7 +410,7 @@ __device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i,
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256, 3)
 chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ work_base,
-                   int* __restrict__ status) {
+                   int* __restrict__ status, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double smem[];
   __shared__ int s_ticket, s_ready;
   const Work w = work_layout(work_base, n);
@@ -412,6 +435,7 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
       ++j;
     }
     const int i = j + (t - off);
+    CHOL_TRACE(0);
 
     // accumulators start as A_ij; the k loop subtracts X_ik X_jk^T
     double acc[8][2];
@@ -481,6 +505,7 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
       }
       __syncthreads();  // stage st may be overwritten
     }
+    CHOL_TRACE(1);
     if (diag) {
       // C fragments -> shared tile
 #pragma unroll
@@ -488,9 +513,10 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
         *reinterpret_cast<double2*>(smem + row * kCS + nb * 8 + 2 * q) =
             make_double2(acc[nb][0], acc[nb][1]);
       __syncthreads();
-      diag_task(A, ld, n, j, smem, w, T, status);
+      diag_task(A, ld, n, j, smem, w, T, status, trace);
+      CHOL_TRACE(3);
     } else {
-      trsm_task(A, ld, i, j, acc, smem, w, T);
+      trsm_task(A, ld, i, j, acc, smem, w, T, trace);
     }
   }
 }
@@ -610,8 +636,30 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* 
   const int ntiles = ncols * T - ncols * (ncols - 1) / 2;
   int grid = 3 * num_sms;
   if (grid > ntiles) grid = ntiles;
-  chol_factor_kernel<<<grid, 256, kFactorSmem, s>>>(A, ld, n, work, status);
+  static const char* trace_path = std::getenv("PPSFM_CHOL_TRACE");
+  unsigned long long* trace = nullptr;
+  if (trace_path) {
+    cudaMalloc(&trace, sizeof(unsigned long long) * 16 * (size_t)T * T);
+    cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 16 * (size_t)T * T, s);
+  }
+  chol_factor_kernel<<<grid, 256, kFactorSmem, s>>>(A, ld, n, work, status, trace);
   chol_backsolve_kernel<<<ncols, 256, kBackSmem, s>>>(A, ld, n, work, x);
+  if (trace_path) {  // development aid: dump "i j t0 t1 t2 t3" (ns) per tile
+    std::vector<unsigned long long> h(16 * (size_t)T * T);
+    cudaStreamSynchronize(s);
+    cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
+    cudaFree(trace);
+    if (FILE* f = std::fopen(trace_path, "w")) {
+      for (int i = 0; i < T; ++i)
+        for (int j = 0; j <= i && j < ncols; ++j) {
+          const unsigned long long* e = &h[16 * (size_t)(i * T + j)];
+          std::fprintf(f, "%d %d", i, j);
+          for (int k = 0; k < 16; ++k) std::fprintf(f, " %llu", e[k]);
+          std::fprintf(f, "\n");
+        }
+      std::fclose(f);
+    }
+  }
   return 2;
 }
 
