@@ -65,6 +65,12 @@ cudaError_t Upload(BaState* st, T** p, const std::vector<T>& h) {
   return e;
 }
 
+// allocation callback for build_schur_lists
+void* StateAlloc(void* state, size_t bytes) {
+  char* p = nullptr;
+  return DevAlloc(static_cast<BaState*>(state), &p, bytes) == cudaSuccess ? p : nullptr;
+}
+
 double Secs(std::chrono::steady_clock::time_point a) {
   return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
 }
@@ -251,6 +257,10 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.Vinv, 6 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.S, (size_t)d.ld * d.ld));
+  // zeroed once: the assembly overwrites every lower block and the rhs row each iteration, the
+  // factorisation keeps the padding rows zero
+  BA_TRY(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.ld * d.ld, s));
+  BA_TRY(build_schur_lists(d, &StateAlloc, st, s));
   BA_TRY(DevAlloc(st, &d.dc, (size_t)std::max(1, d.n)));
   BA_TRY(DevAlloc(st, &d.dp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.u, 2 * (size_t)K));

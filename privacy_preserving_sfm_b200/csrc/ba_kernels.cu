@@ -7,7 +7,7 @@
 //                            robust-loss correction and Jacobi column scaling fused in
 //   ba_point_normal_kernel   V_p = sum J_p^T J_p, g_p          (one thread per point)
 //   ba_camera_normal_kernel  U_c = sum J_c^T J_c, g_c          (one CTA per camera, shuffles)
-//   ba_schur_kernel          S -= W V^-1 W^T, rhs += W V^-1 g_p (one warp per point)
+//   (reduced camera system: ba_schur.cu)
 //   ba_backsub_kernel        dp = -V^-1 (g_p + W^T dc), model cost change, candidate points
 //   ba_camera_update_kernel  candidate poses via QuaternionParameterization::Plus
 // Observation data is stored SoA over the (point-major) observation index so that every warp
@@ -403,118 +403,6 @@ __global__ void ba_jacobi_scales_kernel(BaDev d) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Reduced camera system.
-// ------------------------------------------------------------------------------------------
-__global__ void ba_init_reduced_kernel(BaDev d, double radius, double min_diag, double max_diag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // over NB * 36
-  if (i >= 36 * d.NB) return;
-  const int b = i / 36, a = (i % 36) / 6, c = i % 6;
-  const unsigned mask = d.cam_mask[d.block_img[b]];
-  const bool on_a = (mask >> a) & 1u, on_c = (mask >> c) & 1u;
-  double v = d.U[i];
-  if (a == c) v += fmin(fmax(v, min_diag), max_diag) / radius;
-  if (!on_a || !on_c) v = (a == c) ? 1.0 : 0.0;
-  d.S[(size_t)(6 * b + a) * d.ld + 6 * b + c] = v;
-  if (c == 0) d.S[(size_t)d.n * d.ld + 6 * b + a] = on_a ? -d.gc[6 * (size_t)b + a] : 0.0;
-}
-
-// One warp per point.  With T_ef = J_p,e V^-1 J_p,f^T (2x2), the block contributed to camera
-// pair (e, f) is  J_c,e^T T_ef J_c,f  (6x6); only blocks with block(e) >= block(f) are written
-// (lower triangle), by double-precision atomics into the L2-resident S.
-__global__ void __launch_bounds__(kThreads)
-ba_schur_kernel(BaDev d, double radius, double min_diag, double max_diag) {
-  const int warp = (blockIdx.x * kThreads + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (warp >= d.P) return;
-  const int p = warp;
-  const int P = d.P;
-  const int64_t K = d.K;
-  if (!d.pt_var[p]) {
-    if (lane < 6) d.Vinv[(size_t)lane * P + p] = 0.0;
-    return;
-  }
-  // damped V and its inverse (symmetric 3x3, adjugate / determinant)
-  double a = d.V[p], b = d.V[P + p], c = d.V[2 * P + p];
-  double e = d.V[3 * P + p], f = d.V[4 * P + p], i = d.V[5 * P + p];
-  a += fmin(fmax(a, min_diag), max_diag) / radius;
-  e += fmin(fmax(e, min_diag), max_diag) / radius;
-  i += fmin(fmax(i, min_diag), max_diag) / radius;
-  const double c00 = e * i - f * f, c01 = c * f - b * i, c02 = b * f - c * e;
-  const double det = a * c00 + b * c01 + c * c02;
-  double w00 = 0, w01 = 0, w02 = 0, w11 = 0, w12 = 0, w22 = 0;
-  if (fabs(det) > 0.0) {
-    const double id = 1.0 / det;
-    w00 = c00 * id; w01 = c01 * id; w02 = c02 * id;
-    w11 = (a * i - c * c) * id; w12 = (b * c - a * f) * id; w22 = (a * e - b * b) * id;
-  }
-  if (lane == 0) {
-    d.Vinv[p] = w00; d.Vinv[P + p] = w01; d.Vinv[2 * P + p] = w02;
-    d.Vinv[3 * P + p] = w11; d.Vinv[4 * P + p] = w12; d.Vinv[5 * P + p] = w22;
-  }
-  const double g0 = d.gp[p], g1 = d.gp[P + p], g2 = d.gp[2 * P + p];
-  const double vg0 = w00 * g0 + w01 * g1 + w02 * g2;
-  const double vg1 = w01 * g0 + w11 * g1 + w12 * g2;
-  const double vg2 = w02 * g0 + w12 * g1 + w22 * g2;
-  const int64_t k0 = d.pt_start[p];
-  const int m = (int)(d.pt_start[p + 1] - k0);
-  double* rhs = d.S + (size_t)d.n * d.ld;
-  // rhs += W V^-1 g_p
-  for (int eo = lane; eo < m; eo += 32) {
-    const int64_t k = k0 + eo;
-    const int bi = d.cam_block[d.obs_cam[k]];
-    if (bi < 0) continue;
-    double y[2];
-#pragma unroll
-    for (int row = 0; row < 2; ++row)
-      y[row] = JP((3 * row), k) * vg0 + JP((3 * row + 1), k) * vg1 +
-               JP((3 * row + 2), k) * vg2;
-#pragma unroll
-    for (int a2 = 0; a2 < 6; ++a2)
-      atomicAdd(&rhs[6 * bi + a2], JC(a2, k) * y[0] + JC((6 + a2), k) * y[1]);
-  }
-  // S -= sum over ordered pairs
-  for (int idx = lane; idx < m * m; idx += 32) {
-    const int eo = idx / m, fo = idx % m;
-    const int64_t ke = k0 + eo, kf = k0 + fo;
-    const int bi = d.cam_block[d.obs_cam[ke]], bj = d.cam_block[d.obs_cam[kf]];
-    if (bi < 0 || bj < 0 || bi < bj) continue;
-    // Y_e = J_p,e V^-1 (2x3)
-    double Y[2][3], T[2][2];
-#pragma unroll
-    for (int row = 0; row < 2; ++row) {
-      const double j0 = JP((3 * row), ke), j1 = JP((3 * row + 1), ke);
-      const double j2 = JP((3 * row + 2), ke);
-      Y[row][0] = j0 * w00 + j1 * w01 + j2 * w02;
-      Y[row][1] = j0 * w01 + j1 * w11 + j2 * w12;
-      Y[row][2] = j0 * w02 + j1 * w12 + j2 * w22;
-    }
-#pragma unroll
-    for (int s2 = 0; s2 < 2; ++s2) {
-      const double j0 = JP((3 * s2), kf), j1 = JP((3 * s2 + 1), kf);
-      const double j2 = JP((3 * s2 + 2), kf);
-      T[0][s2] = Y[0][0] * j0 + Y[0][1] * j1 + Y[0][2] * j2;
-      T[1][s2] = Y[1][0] * j0 + Y[1][1] * j1 + Y[1][2] * j2;
-    }
-    double Jf[2][6];
-#pragma unroll
-    for (int c2 = 0; c2 < 6; ++c2) {
-      Jf[0][c2] = JC(c2, kf);
-      Jf[1][c2] = JC((6 + c2), kf);
-    }
-    double* blk = d.S + (size_t)(6 * bi) * d.ld + 6 * bj;
-#pragma unroll
-    for (int a2 = 0; a2 < 6; ++a2) {
-      const double e0 = JC(a2, ke), e1 = JC((6 + a2), ke);
-      const double h0 = e0 * T[0][0] + e1 * T[1][0];  // (J_c,e^T T)[a][0]
-      const double h1 = e0 * T[0][1] + e1 * T[1][1];
-#pragma unroll
-      for (int c2 = 0; c2 < 6; ++c2)
-        atomicAdd(&blk[(size_t)a2 * d.ld + c2], -(h0 * Jf[0][c2] + h1 * Jf[1][c2]));
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------
 // Back-substitution, model cost change, candidate state.
 // ------------------------------------------------------------------------------------------
 // (1) one thread per observation: u = J_c dc (kept for the model-cost pass), and the point-side
@@ -770,23 +658,6 @@ int launch_jacobi_scales(const BaDev& d, cudaStream_t s) {
   if (total == 0) return 0;
   ba_jacobi_scales_kernel<<<(total + 255) / 256, 256, 0, s>>>(d);
   return 1;
-}
-
-int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,
-                                bool include_camera_terms, cudaStream_t s) {
-  int n = 0;
-  cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.ld * d.ld, s);
-  if (d.NB > 0 && include_camera_terms) {
-    ba_init_reduced_kernel<<<(36 * d.NB + 255) / 256, 256, 0, s>>>(d, radius, min_diag, max_diag);
-    ++n;
-  }
-  if (d.P > 0) {
-    const int64_t threads = (int64_t)d.P * 32;
-    ba_schur_kernel<<<(unsigned)((threads + kThreads - 1) / kThreads), kThreads, 0, s>>>(
-        d, radius, min_diag, max_diag);
-    ++n;
-  }
-  return n;
 }
 
 void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,

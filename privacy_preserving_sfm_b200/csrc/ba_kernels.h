@@ -49,6 +49,16 @@ struct BaDev {
   double* V = nullptr;    // [6][P] symmetric (00 01 02 11 12 22), SoA
   double* gp = nullptr;   // [3][P]
   double* Vinv = nullptr; // [6][P]
+  double* Lv = nullptr;   // [P][9] inverse Cholesky factor of the damped V (6) and h = L^-1 g_p (3)
+  double* Zrec = nullptr; // [K][24] per observation: Z = J_c^T J_p L^-T (6x3 row-major), z = Z h (6)
+  // Schur gather lists (static structure, ba_schur.cu): observation pairs grouped by camera pair
+  int sch_npairs = 0, sch_nchunks = 0, sch_nmulti = 0;
+  int2* sch_ent = nullptr;          // [entries] (e, f), sorted by camera pair (i >= j), then e
+  int64_t* sch_pair_start = nullptr;  // [npairs + 1]
+  int* sch_pair_chunk = nullptr;    // [npairs + 1] first chunk (<= 128 entries) of a pair
+  int* sch_chunk_pair = nullptr;    // [nchunks]
+  int* sch_multi = nullptr;         // [nmulti] pairs that span several chunks
+  double* sch_partial = nullptr;    // [nchunks][48] chunk sums of those pairs
   double* S = nullptr;    // [ld][ld] bordered reduced camera matrix (row n = rhs)
   double* dc = nullptr;   // [n]
   double* dp = nullptr;   // [3][P]
@@ -82,7 +92,12 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
 int launch_normal_equations(const BaDev& d, cudaStream_t s);
 // Jacobi scales 1 / (1 + sqrt(diag)) from U, V (computed with unit scales).
 int launch_jacobi_scales(const BaDev& d, cudaStream_t s);
+// One-time structure set-up of the reduced-system assembly (gather lists, record storage);
+// alloc(ctx, bytes) returns device memory owned by the problem (nullptr on failure).
+cudaError_t build_schur_lists(BaDev& d, void* (*alloc)(void*, size_t), void* alloc_ctx,
+                              cudaStream_t s);
 // S = blockdiag(U + D_c^2) - W (V + D_p^2)^-1 W^T (lower triangle), row n = rhs; stores Vinv.
+// Every block of the lower triangle and the rhs row are overwritten (no memset needed).
 // `include_camera_terms` is false on ranks > 0 of a sharded solve (the replicated camera terms
 // must enter the all-reduced sum once).
 int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, double max_diag,

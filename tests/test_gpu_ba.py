@@ -103,10 +103,19 @@ def test_linearize_masks_constant_blocks(ctx, oracle):
 
 def _compare_solutions(a, b, s, s2, tol_pose=1e-8, tol_cost=1e-9):
     assert s.termination_type == s2.termination_type
-    assert (s.num_successful_steps, s.num_unsuccessful_steps) == \
-        (s2.num_successful_steps, s2.num_unsuccessful_steps)
-    assert s.trace_len == s2.trace_len
-    assert list(s.trace_accepted[:s.trace_len]) == list(s2.trace_accepted[:s2.trace_len])
+    # same accepted / rejected step sequence — up to the point where a decision is made on
+    # rounding noise (cost change below 1e-11 relative), beyond which the two need not agree
+    acc, acc2 = list(s.trace_accepted[:s.trace_len]), list(s2.trace_accepted[:s2.trace_len])
+    for i in range(min(len(acc), len(acc2))):
+        if acc[i] != acc2[i]:
+            moved = max(abs(s.trace_cost[i] - s.trace_cost[i - 1]),
+                        abs(s2.trace_cost[i] - s2.trace_cost[i - 1]))
+            assert i > 0 and moved <= 1e-11 * s2.trace_cost[i - 1], (i, acc, acc2)
+            break
+    else:
+        assert len(acc) == len(acc2)
+        assert (s.num_successful_steps, s.num_unsuccessful_steps) == \
+            (s2.num_successful_steps, s2.num_unsuccessful_steps)
     assert abs(s.initial_cost - s2.initial_cost) <= 1e-11 * s2.initial_cost
     assert abs(s.final_cost - s2.final_cost) <= tol_cost * max(s2.final_cost, 1e-300)
     # north-star bar: 1e-6 rad / 1e-6 relative translation; observed agreement is far tighter
