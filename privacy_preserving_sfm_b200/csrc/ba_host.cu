@@ -252,6 +252,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.cam_scale, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.pt_scale, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.U, 36 * (size_t)NB));
+  BA_TRY(DevAlloc(st, &d.Upart, 4 * 27 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.gc, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.V, 6 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));

@@ -5,8 +5,8 @@
 //                            (src/base/cost_functions.h:62-100) with ANALYTIC 2x6 / 2x3 Jacobian
 //                            blocks in the tangent space of ceres::QuaternionParameterization,
 //                            robust-loss correction and Jacobi column scaling fused in
-//   ba_point_normal_kernel   V_p = sum J_p^T J_p, g_p          (one thread per point)
-//   ba_camera_normal_kernel  U_c = sum J_c^T J_c, g_c          (one CTA per camera, shuffles)
+//   ba_point_normal_kernel   V_p = sum J_p^T J_p, g_p          (thread per observation, segmented)
+//   ba_camera_normal_kernel  U_c = sum J_c^T J_c, g_c          (4 CTAs per camera, shuffles)
 //   (reduced camera system: ba_schur.cu)
 //   ba_backsub_kernel        dp = -V^-1 (g_p + W^T dc), model cost change, candidate points
 //   ba_camera_update_kernel  candidate poses via QuaternionParameterization::Plus
@@ -327,37 +327,76 @@ reduce_partials_kernel(const double* __restrict__ partials, int count, int strid
 // ------------------------------------------------------------------------------------------
 // Normal-equation blocks.
 // ------------------------------------------------------------------------------------------
+// V_p = sum J_p^T J_p, g_p = sum J_p^T r.  One thread per observation (coalesced reads of the
+// blocked-SoA linearisation); the observations of a point are contiguous, so the per-point sums
+// are a segmented warp reduction.  Segments that lie inside one warp batch are stored directly;
+// the (at most two per batch) that cross a batch boundary are added atomically into the zeroed
+// arrays — two partials commute, so the result is reproducible for tracks of <= 32 observations.
 __global__ void __launch_bounds__(kThreads) ba_point_normal_kernel(BaDev d) {
-  const int p = blockIdx.x * kThreads + threadIdx.x;
-  if (p >= d.P) return;
   const int64_t K = d.K;
-  double v00 = 0, v01 = 0, v02 = 0, v11 = 0, v12 = 0, v22 = 0, g0 = 0, g1 = 0, g2 = 0;
-  for (int64_t k = d.pt_start[p]; k < d.pt_start[p + 1]; ++k) {
+  const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
+  const int lane = threadIdx.x & 31;
+  int pid = -1;
+  double v[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) v[i] = 0.0;
+  if (k < K) {
+    pid = d.obs_pt[k];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
       const double j0 = JP((3 * row), k), j1 = JP((3 * row + 1), k);
       const double j2 = JP((3 * row + 2), k), rr = JR(row, k);
-      v00 += j0 * j0; v01 += j0 * j1; v02 += j0 * j2;
-      v11 += j1 * j1; v12 += j1 * j2; v22 += j2 * j2;
-      g0 += j0 * rr; g1 += j1 * rr; g2 += j2 * rr;
+      v[0] += j0 * j0; v[1] += j0 * j1; v[2] += j0 * j2;
+      v[3] += j1 * j1; v[4] += j1 * j2; v[5] += j2 * j2;
+      v[6] += j0 * rr; v[7] += j1 * rr; v[8] += j2 * rr;
     }
   }
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int other = __shfl_down_sync(0xffffffffu, pid, off);
+    const bool take = (lane + off < 32) && (other == pid);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+      const double t = __shfl_down_sync(0xffffffffu, v[i], off);
+      if (take) v[i] += t;
+    }
+  }
+  const int prev = __shfl_up_sync(0xffffffffu, pid, 1);
+  const bool head = pid >= 0 && (lane == 0 || prev != pid);
+  if (!head) return;
+  const int64_t batch_end = (k - lane) + 32;  // one past the last observation of the warp batch
+  const bool whole = d.pt_start[pid] == k && d.pt_start[pid + 1] <= batch_end;
   const int P = d.P;
-  d.V[p] = v00; d.V[P + p] = v01; d.V[2 * P + p] = v02;
-  d.V[3 * P + p] = v11; d.V[4 * P + p] = v12; d.V[5 * P + p] = v22;
-  d.gp[p] = g0; d.gp[P + p] = g1; d.gp[2 * P + p] = g2;
+  if (whole) {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) d.V[(size_t)i * P + pid] = v[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) d.gp[(size_t)i * P + pid] = v[6 + i];
+  } else {
+#pragma unroll
+    for (int i = 0; i < 6; ++i) atomicAdd(&d.V[(size_t)i * P + pid], v[i]);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) atomicAdd(&d.gp[(size_t)i * P + pid], v[6 + i]);
+  }
 }
 
+// U_c = sum J_c^T J_c, g_c = sum J_c^T r: kCamSplit CTAs per camera block, each reduces its part
+// of the camera's observation list (gather through cam_obs) into 27 partial sums; the partials are
+// added in a fixed order by ba_camera_reduce_kernel.
+constexpr int kCamSplit = 4;
 __global__ void __launch_bounds__(128) ba_camera_normal_kernel(BaDev d) {
   __shared__ double red[32];
-  const int b = blockIdx.x;
+  const int b = blockIdx.x / kCamSplit, part = blockIdx.x % kCamSplit;
   const int64_t K = d.K;
   double u[21], g[6];
 #pragma unroll
   for (int i = 0; i < 21; ++i) u[i] = 0.0;
 #pragma unroll
   for (int i = 0; i < 6; ++i) g[i] = 0.0;
-  for (int64_t i = d.cam_start[b] + threadIdx.x; i < d.cam_start[b + 1]; i += blockDim.x) {
+  const int64_t c0 = d.cam_start[b], c1 = d.cam_start[b + 1];
+  const int64_t len = (c1 - c0 + kCamSplit - 1) / kCamSplit;
+  const int64_t i0 = c0 + part * len, i1 = (i0 + len < c1) ? (i0 + len) : c1;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += blockDim.x) {
     const int64_t k = d.cam_obs[i];
 #pragma unroll
     for (int row = 0; row < 2; ++row) {
@@ -374,18 +413,38 @@ __global__ void __launch_bounds__(128) ba_camera_normal_kernel(BaDev d) {
       }
     }
   }
-  int idx = 0;
-  for (int a = 0; a < 6; ++a) {
-    for (int c = a; c < 6; ++c) {
-      const double tot = block_sum(u[idx++], red);
-      if (threadIdx.x == 0) {
-        d.U[36 * (size_t)b + 6 * a + c] = tot;
-        d.U[36 * (size_t)b + 6 * c + a] = tot;
-      }
-    }
-    const double tg = block_sum(g[a], red);
-    if (threadIdx.x == 0) d.gc[6 * (size_t)b + a] = tg;
+  double* out = d.Upart + 27 * (size_t)blockIdx.x;
+#pragma unroll
+  for (int i = 0; i < 21; ++i) {
+    const double tot = block_sum(u[i], red);
+    if (threadIdx.x == 0) out[i] = tot;
   }
+#pragma unroll
+  for (int a = 0; a < 6; ++a) {
+    const double tg = block_sum(g[a], red);
+    if (threadIdx.x == 0) out[21 + a] = tg;
+  }
+}
+
+__global__ void ba_camera_reduce_kernel(BaDev d) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  const int b = t / 27, i = t - 27 * b;
+  if (b >= d.NB) return;
+  double s = 0.0;
+#pragma unroll
+  for (int part = 0; part < kCamSplit; ++part) s += d.Upart[27 * ((size_t)b * kCamSplit + part) + i];
+  if (i >= 21) {
+    d.gc[6 * (size_t)b + (i - 21)] = s;
+    return;
+  }
+  int a = 0, rem = i;  // upper-triangle index -> (a, c)
+  while (rem >= 6 - a) {
+    rem -= 6 - a;
+    ++a;
+  }
+  const int c = a + rem;
+  d.U[36 * (size_t)b + 6 * a + c] = s;
+  d.U[36 * (size_t)b + 6 * c + a] = s;
 }
 
 __global__ void ba_jacobi_scales_kernel(BaDev d) {
@@ -643,12 +702,17 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
 int launch_normal_equations(const BaDev& d, cudaStream_t s) {
   int n = 0;
   if (d.P > 0) {
-    ba_point_normal_kernel<<<(d.P + kThreads - 1) / kThreads, kThreads, 0, s>>>(d);
-    ++n;
+    cudaMemsetAsync(d.V, 0, sizeof(double) * 6 * (size_t)d.P, s);
+    cudaMemsetAsync(d.gp, 0, sizeof(double) * 3 * (size_t)d.P, s);
+    if (d.K > 0) {
+      ba_point_normal_kernel<<<(unsigned)((d.K + kThreads - 1) / kThreads), kThreads, 0, s>>>(d);
+      ++n;
+    }
   }
   if (d.NB > 0) {
-    ba_camera_normal_kernel<<<d.NB, 128, 0, s>>>(d);
-    ++n;
+    ba_camera_normal_kernel<<<d.NB * kCamSplit, 128, 0, s>>>(d);
+    ba_camera_reduce_kernel<<<(27 * d.NB + 255) / 256, 256, 0, s>>>(d);
+    n += 2;
   }
   return n;
 }

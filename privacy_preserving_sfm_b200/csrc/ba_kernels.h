@@ -45,6 +45,7 @@ struct BaDev {
   double* pt_scale = nullptr;   // [P][3]
   // normal equations
   double* U = nullptr;    // [NB][36]
+  double* Upart = nullptr; // [NB][4][27] partial sums of the camera normal equations
   double* gc = nullptr;   // [NB][6]
   double* V = nullptr;    // [6][P] symmetric (00 01 02 11 12 22), SoA
   double* gp = nullptr;   // [3][P]

@@ -51,6 +51,15 @@ __device__ __forceinline__ int ld_acquire(const int* p) {
   asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Polling uses RELAXED loads: an acquire load is followed by an L1 invalidation (CCTL.IVALL),
+// and CTAs that spin on flags would invalidate the L1 / stall the LSU of the SM they share with
+// the CTA on the critical path.  One acquire fence after the flag has been seen orders the data.
+__device__ __forceinline__ int ld_relaxed(const int* p) {
+  int v;
+  asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -115,71 +124,51 @@ inline size_t work_flag_ints(int n) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 16x16 Cholesky of the diagonal sub-block at (k1, k1) of the tile in shared memory, by ONE warp.
-// Lane i (< 16; the upper half-warp mirrors it) owns row i of the SYMMETRIC block, so the
-// rank-1 update a_ic -= a_ij a_jc / a_jj only needs row j broadcast from lane j — those shuffles
-// do not depend on the reciprocal of the pivot, which is the only long-latency operation on the
-// 16-step dependency chain (the square roots are off the chain).
+// 8x8 Cholesky of the diagonal sub-block at (k1, k1) of the tile in shared memory, by ONE warp.
+// The symmetric block is spread over the warp, two elements per lane: lane (r, c) = (lane >> 3,
+// lane & 7) holds A[r][c] and A[r+4][c].  A pivot step then needs only four shuffles (pivot,
+// row element a_jc, column elements a_rj and a_(r+4)j) and two FMAs per lane, so the warp's
+// instruction stream stays far below the length of the dependency chain
+// shuffle -> reciprocal -> multiply -> FMA (~110 cycles per pivot; measured on B200: DFMA 8,
+// SHFL.64 26, reciprocal 58 cycles).  Square roots are taken once, after the eight steps.
 // Writes L (lower) back, and rdiag[k1 + j] = 1 / l_jj.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool factor16(double* Cs, int k1, double* rdiag, int lane) {
-  const int i = lane & 15;
-  double a[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const int r0 = i > c ? i : c, c0 = i > c ? c : i;
-    a[c] = Cs[(k1 + r0) * kCS + k1 + c0];
+__device__ __forceinline__ bool factor8(double* Cs, int k1, double* rdiag, int lane) {
+  const int r = lane >> 3, c = lane & 7;
+  double e0, e1;
+  {
+    const int r0 = r > c ? r : c, c0 = r > c ? c : r;
+    const int r1 = r + 4 > c ? r + 4 : c, c1 = r + 4 > c ? c : r + 4;
+    e0 = Cs[(k1 + r0) * kCS + k1 + c0];
+    e1 = Cs[(k1 + r1) * kCS + k1 + c1];
   }
   __syncwarp();
   bool bad = false;
-  double* lrow = Cs + (k1 + i) * kCS + k1;  // every lane has read its row: L can go in place
+  double l0 = 0.0, l1 = 0.0, pv = 1.0;  // column c of the factor (unscaled) and its pivot
 #pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    double u[16];
-#pragma unroll
-    for (int c = j; c < 16; ++c) u[c] = shfl_d(a[c], j);
-    double piv = u[j];
+  for (int j = 0; j < 8; ++j) {
+    const int jl = (j & 3) << 3;
+    const double src = (j < 4) ? e0 : e1;  // row j lives in slot j >> 2 of lanes (j & 3, *)
+    double piv = shfl_d(src, jl | j);
+    const double u = shfl_d(src, jl | c);          // a_jc
+    const double t0 = shfl_d(e0, (r << 3) | j);    // a_rj
+    const double t1 = shfl_d(e1, (r << 3) | j);    // a_(r+4)j
     bad = bad || !(piv > 0.0);
     piv = (piv > 0.0) ? piv : 1.0;
-    const double rinv = 1.0 / piv;
-    const double t = a[j] * rinv;
-#pragma unroll
-    for (int c = j + 1; c < 16; ++c) a[c] -= t * u[c];
-    const double rs = rsqrt(piv);  // off the chain
-    if (lane < 16 && i >= j) lrow[j] = (i == j) ? piv * rs : a[j] * rs;
-    if (lane == j) rdiag[k1 + j] = rs;
-  }
-  return bad;
-}
-
-// Inverse of the lower-triangular 16x16 block at (k1, k1) (one warp): the eliminations that
-// reduce L to the identity, applied to the identity.  Result (dense, zeros above the diagonal)
-// goes to the 16x16 block at `out`.
-__device__ __forceinline__ void invert16(const double* Cs, int k1, const double* rdiag,
-                                         double* out /* block origin, row stride kCS */,
-                                         int lane) {
-  const int i = lane & 15;
-  double l[16], m[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    l[c] = (c < i) ? Cs[(k1 + i) * kCS + k1 + c] : 0.0;
-    m[c] = (c == i) ? 1.0 : 0.0;
-  }
-  const double ri = rdiag[k1 + i];
-#pragma unroll
-  for (int j = 0; j < 16; ++j) {
-    // row j is final once rows < j have been eliminated from it: scale by 1 / l_jj
-#pragma unroll
-    for (int c = 0; c <= j; ++c) {
-      const double mine = (i == j) ? m[c] * ri : m[c];
-      const double mj = shfl_d(mine, j);
-      m[c] = (i > j) ? mine - l[j] * mj : mine;
+    if (c == j) {
+      l0 = e0;
+      l1 = e1;
+      pv = piv;
     }
+    const double sc = u * (1.0 / piv);
+    e0 -= t0 * sc;
+    e1 -= t1 * sc;
   }
-  if (lane < 16) {
-#pragma unroll
-    for (int c = 0; c < 16; ++c) out[i * kCS + c] = (c <= i) ? m[c] : 0.0;
-  }
+  const double rs = rsqrt(pv);
+  if (r >= c) Cs[(k1 + r) * kCS + k1 + c] = l0 * rs;
+  Cs[(k1 + r + 4) * kCS + k1 + c] = l1 * rs;  // r + 4 >= c for the rows that matter; the
+  if (r == 0) rdiag[k1 + c] = rs;             // entries above the diagonal are never read
+  return bad;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -205,76 +194,120 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
   const int k0 = j * NB;
   const int kb = min(NB, n - k0);
   if (tid == 0) s_bad = 0;
-  if (kb < NB && tid < NB) rhs_row[tid] = (tid < kb) ? Cs[kb * kCS + tid] : 0.0;
-  __syncthreads();
-  // identity padding outside the real block, zeros above the diagonal
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    if (r >= kb || c >= kb) Cs[r * kCS + c] = (r == c) ? 1.0 : 0.0;
-    else if (c > r) Cs[r * kCS + c] = 0.0;
+  if (kb < NB) {
+    // last, partial block: keep the right-hand-side row aside, pad with the identity
+    if (tid < NB) rhs_row[tid] = (tid < kb) ? Cs[kb * kCS + tid] : 0.0;
+    __syncthreads();
+    for (int idx = tid; idx < NB * NB; idx += 256) {
+      const int r = idx >> 6, c = idx & 63;
+      if (r >= kb || c >= kb) Cs[r * kCS + c] = (r == c) ? 1.0 : 0.0;
+    }
   }
-  for (int idx = tid; idx < NB * kCS; idx += 256) Tm[idx] = 0.0;
+  // (only the lower triangle of Cs is ever read; Tm is fully written before it is read)
   __syncthreads();
   CHOL_TRACE(4);
+  const int g = lane >> 2, q = lane & 3;  // mma fragment coordinates
 #pragma unroll 1
-  for (int bk = 0; bk < 4; ++bk) {
-    const int k1 = 16 * bk;
+  for (int bk = 0; bk < 8; ++bk) {
+    const int k1 = 8 * bk;
     if (warp == 0) {
-      const bool bad = factor16(Cs, k1, rdiag, lane);
+      const bool bad = factor8(Cs, k1, rdiag, lane);
       if (bad && lane == 0) s_bad = 1;
     }
     __syncthreads();
-    CHOL_TRACE(5 + 2 * bk);
-    const int below = NB - (k1 + 16);
+    const int below = NB - (k1 + 8);
     if (below > 0) {
       // panel: row r of X = A_r L^-T by forward substitution, one thread per row
       if (tid < below) {
-        double* rowp = Cs + (k1 + 16 + tid) * kCS + k1;
-        double x[16];
+        double* rowp = Cs + (k1 + 8 + tid) * kCS + k1;
+        double x[8];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) x[c] = rowp[c];
+        for (int c = 0; c < 8; ++c) x[c] = rowp[c];
 #pragma unroll
-        for (int c = 0; c < 16; ++c) {
+        for (int c = 0; c < 8; ++c) {
           x[c] *= rdiag[k1 + c];
 #pragma unroll
-          for (int p = c + 1; p < 16; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
+          for (int p = c + 1; p < 8; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
         }
 #pragma unroll
-        for (int c = 0; c < 16; ++c) rowp[c] = x[c];
+        for (int c = 0; c < 8; ++c) rowp[c] = x[c];
       }
       __syncthreads();
-      // trailing update inside the tile (lower part)
-      const int cnt = below * (below + 1) / 2;
-      for (int idx = tid; idx < cnt; idx += 256) {
-        int r = (int)((sqrtf(8.0f * idx + 1.0f) - 1.0f) * 0.5f);
-        while ((r + 1) * (r + 2) / 2 <= idx) ++r;
-        while (r * (r + 1) / 2 > idx) --r;
-        const int c = idx - r * (r + 1) / 2;
-        const double* xr = Cs + (k1 + 16 + r) * kCS + k1;
-        const double* xc = Cs + (k1 + 16 + c) * kCS + k1;
-        double acc0 = 0.0, acc1 = 0.0;
+      // trailing update inside the tile on the FP64 tensor cores: 8x8 output tiles (lower
+      // part), C -= X_ti X_tj^T with k = 8 (two m8n8k4 steps)
+      const int nb = below >> 3;
+      const int ntile = nb * (nb + 1) / 2;
+      const double* X = Cs + (k1 + 8) * kCS + k1;
+      for (int t = warp; t < ntile; t += 8) {
+        int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+        while (ti * (ti + 1) / 2 > t) --ti;
+        const int tj = t - ti * (ti + 1) / 2;
+        double* cp = Cs + (k1 + 8 + 8 * ti + g) * kCS + k1 + 8 + 8 * tj + 2 * q;
+        double2 cv = *reinterpret_cast<double2*>(cp);
+        const double a0 = -X[(8 * ti + g) * kCS + q], a1 = -X[(8 * ti + g) * kCS + 4 + q];
+        const double b0 = X[(8 * tj + g) * kCS + q], b1 = X[(8 * tj + g) * kCS + 4 + q];
+        dmma_m8n8k4(cv.x, cv.y, a0, b0);
+        dmma_m8n8k4(cv.x, cv.y, a1, b1);
+        *reinterpret_cast<double2*>(cp) = cv;
+      }
+      __syncthreads();
+    }
+    if (bk & 1) CHOL_TRACE(5 + bk - 1);
+  }
+  // Inverses of the 16x16 diagonal sub-blocks (what the triangular solves of the tiles below
+  // use): 8x8 inverses by forward substitution, one thread per column, then
+  // inv([A 0; B C]) = [inv A, 0; -inv(C) B inv(A), inv C].
+  if (tid < 64) {
+    const int blk = tid >> 3, c = tid & 7, o = 8 * blk;
+    double m[8];
 #pragma unroll
-        for (int p = 0; p < 16; p += 2) {
-          acc0 += xr[p] * xc[p];
-          acc1 += xr[p + 1] * xc[p + 1];
-        }
-        Cs[(k1 + 16 + r) * kCS + k1 + 16 + c] -= acc0 + acc1;
+    for (int i = 0; i < 8; ++i) m[i] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      if (i >= c) {
+        double acc = (i == c) ? 1.0 : 0.0;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < i && k >= c) acc -= Cs[(o + i) * kCS + o + k] * m[k];
+        m[i] = acc * rdiag[o + i];
       }
-      __syncthreads();
-      CHOL_TRACE(6 + 2 * bk);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) Tm[(o + i) * kCS + o + c] = m[i];
+    // upper-right 8x8 of the 16-block this 8-block belongs to is zero
+    if ((blk & 1) == 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) Tm[(o + i) * kCS + o + 8 + c] = 0.0;
     }
   }
-  if (warp < 4) invert16(Cs, 16 * warp, rdiag, Tm + (16 * warp) * kCS + 16 * warp, lane);
+  __syncthreads();
+  {
+    // lower-left 8x8 of each 16-block: T = B inv(A) (into scratch right of the tile's 16-block
+    // row, Tm columns [48, 56) are free until the dense inverse is assembled), then -inv(C) T
+    const int blk = tid >> 6, r = (tid >> 3) & 7, c = tid & 7, o = 16 * blk;
+    double acc = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc += Cs[(o + 8 + r) * kCS + o + k] * Tm[(o + k) * kCS + o + c];
+    __syncthreads();
+    double* scratch = Tm + (size_t)(o + r) * kCS + ((blk == 3) ? 0 : 56);  // outside block `blk`
+    scratch[c] = acc;
+    __syncthreads();
+    double res = 0.0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+      res -= Tm[(o + 8 + r) * kCS + o + 8 + k] * Tm[(size_t)(o + k) * kCS + ((blk == 3) ? 0 : 56) + c];
+    __syncthreads();
+    Tm[(o + 8 + r) * kCS + o + c] = res;
+  }
   __syncthreads();
   CHOL_TRACE(13);
-  // publish: L into A (real rows), Lpack into the work buffer
+  // publish Lpack (what the triangular solves of the tiles below need), then raise the flag
   double* lpack = w.lpack + (size_t)j * NB * NB;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    const double v = Cs[r * kCS + c];
-    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = v;
-    const int br = r >> 4, bc = c >> 4;
-    lpack[idx] = (br == bc) ? Tm[r * kCS + c] : v;
+  for (int idx = tid; idx < NB * NB / 2; idx += 256) {
+    const int r = idx >> 5, c = (idx & 31) * 2;
+    const double* src = (((r >> 4) == (c >> 4)) ? Tm : Cs) + r * kCS + c;
+    *reinterpret_cast<double2*>(lpack + r * NB + c) = *reinterpret_cast<const double2*>(src);
   }
   __syncthreads();
   CHOL_TRACE(14);
@@ -284,7 +317,12 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
     st_release(w.flags + 2 + j * T + j, 1);
   }
   CHOL_TRACE(2);
-  // ---- off the critical path: dense L^-1 by block forward substitution
+  // ---- off the critical path: L into A (read by the back-substitution kernel), then the dense
+  //      L^-1 by block forward substitution
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, c = idx & 63;
+    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = Cs[r * kCS + c];
+  }
   //      Linv[bi][bj] = -I16[bi] * sum_{bk = bj}^{bi-1} L[bi][bk] Linv[bk][bj]
 #pragma unroll 1
   for (int dist = 1; dist < 4; ++dist) {
@@ -351,7 +389,8 @@ __device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i,
   const int row = warp * 8 + g;
   if (tid == 0) {
     const int* f = w.flags + 2 + j * T + j;
-    while (ld_acquire(f) == 0) __nanosleep(20);
+    while (ld_relaxed(f) == 0) __nanosleep(40);
+    fence_acquire();
   }
   __syncthreads();
   {
@@ -473,11 +512,12 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
           if (tid == 0) {
             const int* fi = tile_flags + i * T + k;
             const int* fj = tile_flags + j * T + k;
-            int ok = (ld_acquire(fi) != 0) && (ld_acquire(fj) != 0);
+            int ok = (ld_relaxed(fi) != 0) && (ld_relaxed(fj) != 0);
             while (!ok && must) {
-              __nanosleep(20);
-              ok = (ld_acquire(fi) != 0) && (ld_acquire(fj) != 0);
+              __nanosleep(40);
+              ok = (ld_relaxed(fi) != 0) && (ld_relaxed(fj) != 0);
             }
+            if (ok) fence_acquire();
             s_ready = ok;
           }
           __syncthreads();
@@ -567,7 +607,8 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   for (int b = nblk - 1; b > j; --b) {
     const int st = (nblk - 1 - b) & 1;
     if (tid == 0) {
-      while (ld_acquire(xflags + b) == 0) __nanosleep(20);
+      while (ld_relaxed(xflags + b) == 0) __nanosleep(20);
+      fence_acquire();
     }
     // tile b has been issued; at most one younger group is in flight
     if (issued_b < b - 1) cp_async_wait<1>(); else cp_async_wait<0>();
