@@ -111,6 +111,8 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
                   "camera model %d not supported (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, "
                   "RADIAL, OPENCV are)", m);
   }
+  static const bool timing = tune_int("PPSFM_BA_TIMING", 0) != 0;
+  const auto t_create = std::chrono::steady_clock::now();
   BaState* st = new BaState();
   st->ctx = ctx;
   st->opt = *opt;
@@ -121,60 +123,55 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   st->world = world;
   cudaStream_t s = ctx->stream;
 
-  std::vector<uint8_t> pt_var(P, 1), cam_const(C, 0);
-  if (pb->point_const) for (int i = 0; i < P; ++i) pt_var[i] = pb->point_const[i] ? 0 : 1;
-  if (pb->pose_flags) for (int i = 0; i < C; ++i) cam_const[i] = pb->pose_flags[i] & 1;
-  // this rank's share: points are dealt round-robin in blocks (all observations of a point stay
-  // together); cameras are replicated
-  auto mine = [&](int p) { return world == 1 || (p % world) == rank; };
-
-  std::vector<int64_t> pt_start(P + 1, 0);
-  std::vector<uint8_t> cam_used(C, 0);
-  for (int64_t o = 0; o < O; ++o) {
-    const int ci = pb->obs_image[o], pi = pb->obs_point[o];
-    if (ci < 0 || ci >= C || pi < 0 || pi >= P) {
-      delete st;
+  BaDev& d = st->d;
+  d.C = C; d.P = P;
+  cudaError_t e = cudaSuccess;
+#define BA_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
+  // ---- raw arrays to HBM, assembly on the device (ba_assembly.cu)
+  BaRaw raw;
+  raw.C = C; raw.P = P; raw.O = O;
+  std::vector<uint8_t> flags_h(std::max(C, 1), 0), pconst_h(std::max(P, 1), 0);
+  if (pb->pose_flags) std::copy(pb->pose_flags, pb->pose_flags + C, flags_h.begin());
+  if (pb->point_const)
+    for (int i = 0; i < P; ++i) pconst_h[i] = pb->point_const[i] ? 1 : 0;
+  std::vector<void*> raw_tmp;
+  auto raw_upload = [&](const void* src, size_t bytes) -> void* {
+    void* p = nullptr;
+    BA_TRY(cudaMallocAsync(&p, std::max<size_t>(bytes, 16), s));
+    if (e == cudaSuccess) raw_tmp.push_back(p);
+    if (e == cudaSuccess && bytes > 0)
+      e = cudaMemcpyAsync(p, src, bytes, cudaMemcpyHostToDevice, s);
+    return p;
+  };
+  raw.obs_image = (const int*)raw_upload(pb->obs_image, sizeof(int32_t) * (size_t)O);
+  raw.obs_point = (const int*)raw_upload(pb->obs_point, sizeof(int32_t) * (size_t)O);
+  raw.obs_line = (const double*)raw_upload(pb->obs_line, sizeof(double) * 3 * (size_t)O);
+  raw.pose_flags = (const uint8_t*)raw_upload(flags_h.data(), (size_t)C);
+  raw.point_const = (const uint8_t*)raw_upload(pconst_h.data(), (size_t)P);
+  std::vector<uint8_t> cam_used(std::max(C, 1), 0);
+  int64_t bad_index = -1, bad_norm = -1;
+  BA_TRY(ba_assemble_points(d, raw, rank, world, &StateAlloc, st, s, cam_used.data(), &bad_index,
+                            &bad_norm));
+  if (e == cudaSuccess && (bad_index >= 0 || bad_norm >= 0)) {
+    for (void* p : raw_tmp) cudaFreeAsync(p, s);
+    BaFree(st);
+    // the reference walks the observations in order: report the first violation it would meet
+    if (bad_index >= 0 && (bad_norm < 0 || bad_index <= bad_norm))
       return fail(ctx, PPSFM_ERR_INVALID, "observation %lld references a missing image/point",
-                  (long long)o);
-    }
-    const double* l = pb->obs_line + 3 * o;
-    // CHECK_NEAR(line.head<2>().norm(), 1.0, 1e-6)  (bundle_adjustment.cc:374)
-    const double n2 = l[0] * l[0] + l[1] * l[1];
-    if (!(n2 > 0.999998 && n2 < 1.000002) && std::fabs(std::sqrt(n2) - 1.0) > 1e-6) {
-      delete st;
-      return fail(ctx, PPSFM_ERR_INVALID, "observation %lld: line normal is not unit length",
-                  (long long)o);
-    }
-    if (cam_const[ci] && !pt_var[pi]) continue;
-    cam_used[ci] = 1;  // global property: identical on every rank
-    if (!mine(pi)) continue;
-    pt_start[pi + 1]++;
+                  (long long)bad_index);
+    return fail(ctx, PPSFM_ERR_INVALID, "observation %lld: line normal is not unit length",
+                (long long)bad_norm);
   }
-  for (int i = 0; i < P; ++i) pt_start[i + 1] += pt_start[i];
-  const int64_t K = pt_start[P];
-  std::vector<int> obs_cam(K), obs_pt(K);
-  std::vector<double> obs_line(3 * (size_t)K);
-  {
-    std::vector<int64_t> fill(pt_start.begin(), pt_start.end() - 1);
-    for (int64_t o = 0; o < O; ++o) {
-      const int ci = pb->obs_image[o], pi = pb->obs_point[o];
-      if ((cam_const[ci] && !pt_var[pi]) || !mine(pi)) continue;
-      const int64_t k = fill[pi]++;
-      obs_cam[k] = ci;
-      obs_pt[k] = pi;
-      obs_line[k] = pb->obs_line[3 * o];
-      obs_line[K + k] = pb->obs_line[3 * o + 1];
-      obs_line[2 * K + k] = pb->obs_line[3 * o + 2];
-    }
-  }
+  for (void* p : raw_tmp) cudaFreeAsync(p, s);
+  const int64_t K = d.K;
   std::vector<int> cam_block(C, -1), block_img;
   std::vector<uint8_t> cam_mask(C, 0);
   std::vector<double> q(pb->qvecs, pb->qvecs + 4 * (size_t)C), t(pb->tvecs, pb->tvecs + 3 * (size_t)C);
   for (int i = 0; i < C; ++i) {
-    if (cam_const[i] || !cam_used[i]) continue;
+    if ((flags_h[i] & 1) || !cam_used[i]) continue;
     cam_block[i] = (int)block_img.size();
     block_img.push_back(i);
-    const uint8_t f = pb->pose_flags ? pb->pose_flags[i] : 0;
+    const uint8_t f = flags_h[i];
     uint8_t m = 0x07;
     for (int k = 0; k < 3; ++k)
       if (!(f & (2 << k))) m |= (uint8_t)(8 << k);
@@ -186,24 +183,6 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     if (nrm > 0) for (int k = 0; k < 4; ++k) q[4 * i + k] /= nrm;
   }
   const int NB = (int)block_img.size();
-  // a point takes part on this rank only if it has kept observations here
-  for (int i = 0; i < P; ++i)
-    if (pt_start[i + 1] == pt_start[i]) pt_var[i] = 0;
-  // camera-major index
-  std::vector<int64_t> cam_start(NB + 1, 0);
-  for (int64_t k = 0; k < K; ++k) {
-    const int b = cam_block[obs_cam[k]];
-    if (b >= 0) cam_start[b + 1]++;
-  }
-  for (int b = 0; b < NB; ++b) cam_start[b + 1] += cam_start[b];
-  std::vector<int> cam_obs(cam_start[NB]);
-  {
-    std::vector<int64_t> fill(cam_start.begin(), cam_start.end() - 1);
-    for (int64_t k = 0; k < K; ++k) {
-      const int b = cam_block[obs_cam[k]];
-      if (b >= 0) cam_obs[fill[b]++] = (int)k;
-    }
-  }
   std::vector<int> img_model(C);
   std::vector<double> img_params(12 * (size_t)C, 0.0);
   for (int i = 0; i < C; ++i) {
@@ -211,20 +190,15 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     img_model[i] = pb->camera_model[cam];
     std::memcpy(&img_params[12 * (size_t)i], pb->camera_params + 12 * (size_t)cam, 12 * sizeof(double));
   }
-
-  BaDev& d = st->d;
-  d.C = C; d.P = P; d.NB = NB; d.K = K; d.n = 6 * NB; d.ld = chol_ld(6 * NB);
-  std::vector<double> X(pb->points, pb->points + 3 * (size_t)P);
-  cudaError_t e = cudaSuccess;
-#define BA_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
-  BA_TRY(Upload(st, &d.obs_cam, obs_cam));
-  BA_TRY(Upload(st, &d.obs_pt, obs_pt));
-  BA_TRY(Upload(st, &d.obs_line, obs_line));
-  BA_TRY(Upload(st, &d.pt_start, pt_start));
-  BA_TRY(Upload(st, &d.cam_obs, cam_obs));
-  BA_TRY(Upload(st, &d.cam_start, cam_start));
-  BA_TRY(Upload(st, &d.block_img, block_img));
+  d.NB = NB; d.n = 6 * NB; d.ld = chol_ld(6 * NB);
   BA_TRY(Upload(st, &d.cam_block, cam_block));
+  BA_TRY(ba_assemble_cameras(d, &StateAlloc, st, s));
+  if (timing) {
+    cudaStreamSynchronize(s);
+    std::fprintf(stderr, "[ba] upload + device assembly %.2f ms\n", 1e3 * Secs(t_create));
+  }
+  std::vector<double> X(pb->points, pb->points + 3 * (size_t)P);
+  BA_TRY(Upload(st, &d.block_img, block_img));
   BA_TRY(Upload(st, &d.cam_mask, cam_mask));
   BA_TRY(Upload(st, &d.img_model, img_model));
   BA_TRY(Upload(st, &d.img_params, img_params));
@@ -238,7 +212,6 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     BA_TRY(Upload(st, &d.cam_model, cam_model));
     BA_TRY(Upload(st, &d.cam_params, cam_params));
   }
-  BA_TRY(Upload(st, &d.pt_var, pt_var));
   BA_TRY(Upload(st, &d.q, q));
   BA_TRY(Upload(st, &d.t, t));
   BA_TRY(Upload(st, &d.X, X));
@@ -257,6 +230,10 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.V, 6 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.Vinv, 6 * (size_t)P));
+  if (timing) {
+    cudaStreamSynchronize(s);
+    std::fprintf(stderr, "[ba] + uploads %.2f ms\n", 1e3 * Secs(t_create));
+  }
   BA_TRY(DevAlloc(st, &d.S, (size_t)d.ld * d.ld));
   // zeroed once: the assembly overwrites every lower block and the rhs row each iteration, the
   // factorisation keeps the padding rows zero
@@ -281,6 +258,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     BaFree(st);
     return fail(ctx, PPSFM_ERR_CUDA, "BA setup: %s", cudaGetErrorString(e));
   }
+  if (timing) std::fprintf(stderr, "[ba] + structure build, create total %.2f ms\n", 1e3 * Secs(t_create));
   *out = st;
   return PPSFM_OK;
 }
@@ -635,15 +613,24 @@ void ppsfm_ba_free(ppsfm_ba* ba) {
 
 int ppsfm_ba_solve(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
                    const ppsfm_ba_options* options, ppsfm_ba_summary* summary) {
+  static const bool timing = tune_int("PPSFM_BA_TIMING", 0) != 0;
+  const auto t0 = std::chrono::steady_clock::now();
   ppsfm_ba* ba = nullptr;
   int rc = ppsfm_ba_create(ctx, problem, options, &ba);
   if (rc != PPSFM_OK) return rc;
+  const double t_create = Secs(t0);
   rc = ppsfm_ba_run(ba, summary);
+  const double t_run = Secs(t0);
   if (rc == PPSFM_OK) {
     const int rc2 = ppsfm_ba_download(ba, problem);
     if (rc2 != PPSFM_OK) rc = rc2;
   }
+  const double t_down = Secs(t0);
   ppsfm_ba_free(ba);
+  if (timing)
+    std::fprintf(stderr, "[ba] solve: create %.2f, run %.2f, download %.2f, free %.2f ms\n",
+                 1e3 * t_create, 1e3 * (t_run - t_create), 1e3 * (t_down - t_run),
+                 1e3 * (Secs(t0) - t_down));
   return rc;
 }
 

@@ -72,6 +72,23 @@ struct BaDev {
   double* scalars = nullptr;   // [16] device scalars
 };
 
+// Device copies of the caller's arrays (input order), consumed by the assembly (ba_assembly.cu).
+struct BaRaw {
+  int C = 0, P = 0;
+  int64_t O = 0;
+  const int* obs_image = nullptr;       // [O]
+  const int* obs_point = nullptr;       // [O]
+  const double* obs_line = nullptr;     // [O][3]
+  const uint8_t* pose_flags = nullptr;  // [C] (zeros if the caller passed none)
+  const uint8_t* point_const = nullptr; // [P]
+};
+cudaError_t ba_assemble_points(BaDev& d, const BaRaw& raw, int rank, int world,
+                               void* (*alloc)(void*, size_t), void* alloc_ctx, cudaStream_t s,
+                               uint8_t* cam_used_host, int64_t* first_bad_index,
+                               int64_t* first_bad_norm);
+cudaError_t ba_assemble_cameras(BaDev& d, void* (*alloc)(void*, size_t), void* alloc_ctx,
+                                cudaStream_t s);
+
 constexpr int kJFields = 20;
 __host__ __device__ inline size_t ba_jidx(int field, int64_t k) {
   return ((size_t)(k >> 8) * kJFields + (size_t)field) * 256 + (size_t)(k & 255);
