@@ -277,6 +277,36 @@ int ppsfm_comm_allreduce_sum_host(ppsfm_ctx* ctx, double* host, size_t count);
  * observations, camera blocks, kept observations in total} */
 int ppsfm_ba_shard_stats(const ppsfm_ba_problem* problem, int rank, int world, int64_t* out);
 
+/* =============================================================================================
+ * Four-view initialisation from lifted lines with known gravity (host code, no GPU needed):
+ * replaces init::initialize_reconstruction (src/init/initializer.h:103-108, initializer.cc:57-215)
+ * and, underneath, FourView2dEstimator / PlanarOffsetEstimator (src/init/sfm2d.h:48-100,
+ * src/init/initializer.h:62-101) run by ransac_lib::LocallyOptimizedMSAC
+ * (lib/RansacLib/RansacLib/ransac.h:127-271).
+ *   lines    [4][n][3]  (a, b, c) per image in normalised camera coordinates, same track order
+ *   aligned  [4][n]     FeatureLine::IsAligned (the aligned / unaligned split must agree)
+ *   gravity  [4][3]     gravity direction per image
+ *   poses_out[4][12]    row-major 3x4 [R | t]
+ * Returns PPSFM_OK, PPSFM_NO_SOLUTION (the reference's `false`) or PPSFM_ERR_INVALID where the
+ * reference CHECK-aborts (initializer.cc:83, 99-104).
+ * ============================================================================================= */
+typedef struct ppsfm_init_options {   /* init::InitOptions, src/init/initializer.h:49-58 */
+  double min_tri_angle;
+  double min_num_inliers;
+  double max_error;
+} ppsfm_init_options;
+typedef struct ppsfm_init_report {
+  int32_t num_aligned, num_unaligned;
+  int32_t inliers_2d, inliers_3d;
+  uint32_t iterations_2d, iterations_3d;
+  double mean_tri_angle_deg;
+} ppsfm_init_report;
+void ppsfm_init_options_default(ppsfm_init_options* options);
+int ppsfm_initialize_reconstruction(const double* lines, const uint8_t* aligned, size_t n,
+                                    const double* gravity, const ppsfm_init_options* options,
+                                    double* poses_out, double* inlier_ratio,
+                                    ppsfm_init_report* report);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

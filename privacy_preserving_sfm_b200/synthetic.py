@@ -183,3 +183,78 @@ def quat_mul(a, b):
                      aw * bx + ax * bw + ay * bz - az * by,
                      aw * by - ax * bz + ay * bw + az * bx,
                      aw * bz + ax * by - ay * bx + az * bw])
+
+
+def _rotation_between(a, b):
+    """Minimal rotation taking direction a onto b (Eigen::Quaterniond::FromTwoVectors)."""
+    a, b = a / np.linalg.norm(a), b / np.linalg.norm(b)
+    v, c = np.cross(a, b), float(a @ b)
+    K = np.array([[0, -v[2], v[1]], [v[2], 0, -v[0]], [-v[1], v[0], 0]])
+    return np.eye(3) + K + K @ K / (1.0 + c)
+
+
+def make_init_scene(num_points=100, num_aligned=50, num_outliers=0, seed=SCENE_SEED,
+                    tilt_deg=0.0):
+    """Four-view initialisation scene after the reference's own test recipe
+    (src/init/initializer_test.cc:44-137): camera 0 = identity, |t_1| = 1, upright cameras (rotation
+    about the gravity axis y), points uniform in [-1, 1]^2 x [0, 1] in front of all cameras,
+    `num_aligned` gravity-aligned lines l = normalize(x~ x g) and the rest through random normals,
+    outliers = one view's point replaced by a random one.  ``tilt_deg > 0`` additionally rotates
+    every camera frame by a random rotation of up to that angle (gravity no longer along the
+    camera y axis; the scene keeps all points in front of the gravity-aligned cameras, which is
+    what the bearing sign convention of initializer.cc:87-89 assumes).
+    Returns lines [4, n, 3], aligned [4, n], gravity [4, 3], poses [4, 3, 4] (ground truth)."""
+    rng = np.random.default_rng(seed)
+    ey = np.array([0.0, 1.0, 0.0])
+    while True:
+        cams, tilts = [], []
+        for i in range(4):
+            P = np.zeros((3, 4))
+            if i == 0:
+                P[:, :3] = np.eye(3)
+            else:
+                a = rng.uniform(-np.pi, np.pi)
+                P[:, :3] = np.array([[np.cos(a), 0, np.sin(a)], [0, 1, 0],
+                                     [-np.sin(a), 0, np.cos(a)]])
+                P[:, 3] = rng.uniform(-1, 1, 3)
+            if i == 1:
+                P[:, 3] /= np.linalg.norm(P[:, 3])
+            cams.append(P)
+            axis = rng.normal(size=3)
+            axis /= np.linalg.norm(axis)
+            ang = np.deg2rad(tilt_deg) * rng.uniform(0.3, 1.0)
+            K = np.array([[0, -axis[2], axis[1]], [axis[2], 0, -axis[0]], [-axis[1], axis[0], 0]])
+            tilts.append(np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * K @ K)
+        X = rng.uniform(-1, 1, (num_points, 3))
+        X[:, 2] = np.abs(X[:, 2])
+        Xh = np.concatenate([X, np.ones((num_points, 1))], axis=1)
+        z = [Xh @ P.T for P in cams]
+        ok = all((zi[:, 2] > 1e-3).all() for zi in z)
+        if ok and tilt_deg > 0:   # depth in the gravity-aligned frame Rg Q P X
+            for zi, Q in zip(z, tilts):
+                Rg = _rotation_between(Q @ ey, ey)
+                ok = ok and ((zi @ (Rg @ Q).T)[:, 2] > 1e-3).all()
+        if ok:
+            break
+    x = [zi[:, :2] / zi[:, 2:3] for zi in z]
+    order = rng.permutation(num_points)
+    for i in range(num_outliers):
+        x[rng.integers(0, 4)][order[i]] = rng.uniform(-1, 1, 2)
+    is_aligned = rng.permutation(num_points) < num_aligned
+    lines = np.zeros((4, num_points, 3))
+    gravity = np.zeros((4, 3))
+    poses = np.stack(cams)
+    for i in range(4):
+        g = cams[i][:, 1].copy()
+        xh = np.concatenate([x[i], np.ones((num_points, 1))], axis=1)
+        nrm = np.where(is_aligned[:, None], g[None, :], rng.uniform(-1, 1, (num_points, 3)))
+        l = np.cross(xh, nrm)
+        lines[i] = l / np.linalg.norm(l, axis=1, keepdims=True)
+        gravity[i] = g
+        if tilt_deg > 0:
+            Q = tilts[i]
+            lines[i] = lines[i] @ Q.T
+            gravity[i] = Q @ g
+            poses[i] = Q @ poses[i]
+    aligned = np.repeat(is_aligned[None, :].astype(np.uint8), 4, axis=0)
+    return lines, aligned, gravity, poses
