@@ -144,8 +144,10 @@ def test_gauge_and_constant_blocks(oracle):
                         sc["obs_line"], [1], [sc["cam_params"]], pose_flags=flags, point_const=pc)
     ok, s2 = oracle.ba_solve(b, oracle.ba_default_options(max_num_iterations=20, num_threads=4,
                                                           gradient_tolerance=1e-6))
-    assert abs(s2.final_cost - s.final_cost) <= 1e-10 * s.final_cost
-    assert np.abs(a.points - b.points).max() < 1e-9
+    # (thread-order dependent summation: the runs may stop one LM step apart at the 1e-6 gradient
+    # tolerance, so compare at the accuracy that tolerance implies, not at rounding level)
+    assert abs(s2.final_cost - s.final_cost) <= 1e-8 * s.final_cost
+    assert np.abs(a.points - b.points).max() < 1e-6
 
 
 def test_no_residuals_returns_false(oracle):
