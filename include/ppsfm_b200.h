@@ -307,6 +307,41 @@ int ppsfm_initialize_reconstruction(const double* lines, const uint8_t* aligned,
                                     double* poses_out, double* inlier_ratio,
                                     ppsfm_init_report* report);
 
+/* =============================================================================================
+ * Observation / point filters that follow every bundle adjustment, on a
+ * track-major view of the reconstruction: the observations of point p are
+ * [track_start[p], track_start[p+1]) in track order.  Replaces Reconstruction::FilterPoints3D
+ * (src/base/reconstruction.cc:425-440 = FilterPoints3DWithLargeReprojectionError :650-719 followed
+ * by FilterPoints3DWithSmallTriangulationAngle :594-648) and
+ * Reconstruction::FilterObservationsWithNegativeDepth (:442-460).  Outputs are delete masks the
+ * caller applies to its Reconstruction (DeleteObservation / DeletePoint3D) and the value the
+ * reference returns (num_filtered); point_error [P] is in/out (Point3D::SetError for survivors).
+ * ============================================================================================= */
+typedef struct ppsfm_filter_problem {
+  int32_t num_images;
+  const double* qvecs;           /* [num_images][4] (w, x, y, z) */
+  const double* tvecs;           /* [num_images][3] */
+  const int32_t* image_camera;   /* [num_images] */
+  int32_t num_cameras;
+  const int32_t* camera_model;   /* COLMAP model id (0..4) */
+  const double* camera_params;   /* [num_cameras][12] */
+  const int32_t* camera_width;   /* Camera::Width() */
+  const int32_t* camera_height;
+  int32_t num_points;
+  const double* points;          /* [num_points][3] */
+  const int64_t* track_start;    /* [num_points + 1] */
+  int64_t num_obs;
+  const int32_t* obs_image;      /* [num_obs] */
+  const double* obs_line;        /* [num_obs][3], |(a, b)| = 1 */
+  const uint8_t* obs_aligned;    /* [num_obs] FeatureLine::IsAligned */
+} ppsfm_filter_problem;
+int ppsfm_filter_points3d(ppsfm_ctx* ctx, const ppsfm_filter_problem* problem,
+                          double max_reproj_error, double min_tri_angle_deg, uint8_t* obs_deleted,
+                          uint8_t* point_deleted, double* point_error, size_t* num_filtered);
+int ppsfm_filter_observations_with_negative_depth(ppsfm_ctx* ctx,
+                                                  const ppsfm_filter_problem* problem,
+                                                  uint8_t* obs_deleted, size_t* num_filtered);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

@@ -389,3 +389,31 @@ def refine_absolute_pose(lines, points, mask, model, cam_params, qvec, tvec,
         lp, pp, mp, lines.shape[0], model, cam.ctypes.data_as(_dp), gradient_tolerance,
         max_num_iterations, loss_scale, q.ctypes.data_as(_dp), t.ctypes.data_as(_dp), C.byref(s))
     return bool(ok), q, t, s
+
+
+# ---- post-BA filters (filter_oracle.cc) ------------------------------------------------------
+def filter_points3d(problem, max_reproj_error, min_tri_angle, point_error=None):
+    """problem: privacy_preserving_sfm_b200.filters.FilterProblem (same struct layout).
+    Returns (num_filtered, obs_deleted, point_deleted, point_error, squared_errors)."""
+    L = lib()
+    O, P = len(problem.obs_image), len(problem.points)
+    od, pd = np.zeros(max(O, 1), np.uint8), np.zeros(max(P, 1), np.uint8)
+    pe = np.full(max(P, 1), -1.0) if point_error is None else np.array(point_error, np.float64)
+    sq = np.full(max(O, 1), -1.0)
+    nf = C.c_uint64(0)
+    L.orc_filter_points3d.argtypes = [C.c_void_p, C.c_double, C.c_double, _u8p, _u8p, _dp,
+                                      C.POINTER(C.c_uint64), _dp]
+    L.orc_filter_points3d(C.byref(problem.struct), max_reproj_error, min_tri_angle,
+                          od.ctypes.data_as(_u8p), pd.ctypes.data_as(_u8p),
+                          pe.ctypes.data_as(_dp), C.byref(nf), sq.ctypes.data_as(_dp))
+    return nf.value, od[:O], pd[:P], pe[:P], sq[:O]
+
+
+def filter_negative_depth(problem):
+    L = lib()
+    O = len(problem.obs_image)
+    od = np.zeros(max(O, 1), np.uint8)
+    nf = C.c_uint64(0)
+    L.orc_filter_negative_depth.argtypes = [C.c_void_p, _u8p, C.POINTER(C.c_uint64)]
+    L.orc_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p), C.byref(nf))
+    return nf.value, od[:O]
