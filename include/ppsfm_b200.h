@@ -342,6 +342,34 @@ int ppsfm_filter_observations_with_negative_depth(ppsfm_ctx* ctx,
                                                   const ppsfm_filter_problem* problem,
                                                   uint8_t* obs_deleted, size_t* num_filtered);
 
+/* =============================================================================================
+ * Batched robust line triangulation: EstimateTriangulation
+ * (src/estimators/triangulation.h:143-147, triangulation.cc:118-149) for every track of a
+ * track-major problem (ppsfm_filter_problem; `points` is not read, num_points = number of
+ * tracks).  LORANSAC over the 3-combinations of a track in lexicographic order
+ * (src/optim/loransac.h:91-234, combination_sampler.cc:41-70), multi-view point from lines
+ * (src/base/triangulation.cc:41-57), squared angular or line-reprojection residuals.
+ * exhaustive_threshold: tracks up to this length get min_num_trials = C(n, 3)
+ * (src/sfm/incremental_triangulator.cc:527-531).  Outputs: xyz [T][3], success [T],
+ * inlier_mask [O], num_trials [T] (may be NULL).
+ * ============================================================================================= */
+typedef struct ppsfm_triangulation_options {
+  double min_tri_angle;          /* radians */
+  int32_t residual_type;         /* 0 ANGULAR_ERROR (max_error in radians), 1 REPROJECTION_ERROR (pixels) */
+  double max_error;              /* RANSACOptions */
+  double min_inlier_ratio;
+  double confidence;
+  double dyn_num_trials_multiplier;
+  uint64_t min_num_trials;
+  uint64_t max_num_trials;
+  int32_t exhaustive_threshold;
+} ppsfm_triangulation_options;
+void ppsfm_triangulation_options_default(ppsfm_triangulation_options* options);
+int ppsfm_estimate_triangulation_batch(ppsfm_ctx* ctx, const ppsfm_filter_problem* tracks,
+                                       const ppsfm_triangulation_options* options, double* xyz,
+                                       uint8_t* success, uint8_t* inlier_mask,
+                                       uint32_t* num_trials);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

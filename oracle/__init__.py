@@ -417,3 +417,19 @@ def filter_negative_depth(problem):
     L.orc_filter_negative_depth.argtypes = [C.c_void_p, _u8p, C.POINTER(C.c_uint64)]
     L.orc_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p), C.byref(nf))
     return nf.value, od[:O]
+
+
+# ---- batched line triangulation (triangulation_oracle.cc) -------------------------------------
+def estimate_triangulation_batch(tracks, options):
+    """tracks: filters.FilterProblem, options: triangulation.EstimateTriangulationOptions (same
+    struct layouts).  Returns (success, xyz, inlier_mask, num_trials)."""
+    L = lib()
+    T, O = len(tracks.points), len(tracks.obs_image)
+    xyz = np.zeros((max(T, 1), 3))
+    ok, mask = np.zeros(max(T, 1), np.uint8), np.zeros(max(O, 1), np.uint8)
+    nt = np.zeros(max(T, 1), np.uint32)
+    L.orc_estimate_triangulation_batch.argtypes = [C.c_void_p, C.c_void_p, _dp, _u8p, _u8p, _u32p]
+    L.orc_estimate_triangulation_batch(C.byref(tracks.struct), C.byref(options),
+                                       xyz.ctypes.data_as(_dp), ok.ctypes.data_as(_u8p),
+                                       mask.ctypes.data_as(_u8p), nt.ctypes.data_as(_u32p))
+    return ok[:T].astype(bool), xyz[:T], mask[:O].astype(bool), nt[:T]
