@@ -5,20 +5,22 @@
 // hundreds of cameras that all share points is dense, so it is factored densely.
 //
 // The factorisation of a 3000 x 3000 system is LATENCY bound (47 dependent 64-wide steps), not
-// flop bound (9 GFLOP), so it runs as ONE persistent dataflow kernel instead of ~140 dependent
-// launches:
-//   * the lower triangle is cut into 64x64 tiles; tile (i, j) is one task: accumulate
-//       C = A_ij - sum_{k<j} X_ik X_jk^T        (FP64 tensor-core MMA, mma.sync.m8n8k4.f64 —
-//                                                tcgen05 has no FP64 kind; the one genuinely
-//                                                dense contraction of the path)
-//     then   j == i : L_jj = chol(C)            (16x16 register-resident warp factorisations)
-//            j <  i : X_ij = C L_jj^-T          (blocked triangular solve on the tensor cores)
-//   * tasks are handed out through an atomic ticket in column-major order, so a task only ever
-//     waits for tasks with a smaller ticket (they are running or finished): no deadlock,
-//     whatever the number of resident CTAs;
-//   * a finished tile is published with a release store of its flag; consumers poll with acquire
-//     loads and stream the operand tiles through a cp.async double buffer (left-looking:
-//     accumulators stay in registers, no read-modify-write of the trailing matrix).
+// flop bound (9 GFLOP = 0.3 ms of FP64 tensor-core time), so it runs as ONE persistent dataflow
+// kernel with two roles:
+//   * HELPER CTAs pull 64x64 tile tasks (i, j) from an atomic ticket in column-major order and
+//     accumulate  C = A_ij - sum_k X_ik X_jk^T  left-looking (accumulators stay in registers,
+//     operand tiles stream through a 3-stage cp.async pipeline; FP64 tensor-core MMA
+//     mma.sync.m8n8k4.f64 — tcgen05 has no FP64 kind).  Tiles with i >= j + 2 are then finished
+//     by the blocked triangular solve X_ij = C L_jj^-T on the tensor cores; the diagonal and
+//     sub-diagonal tiles are only PRE-accumulated (all terms that do not depend on the previous
+//     column step) and handed to the walker.
+//   * ONE WALKER CTA, alone on its SM, walks down the diagonal and keeps the whole dependency
+//     chain  L_jj = chol(C_jj)  ->  X_(j+1)j = C_(j+1)j L_jj^-T  ->  C_(j+1)(j+1) -= X X^T  in
+//     shared memory and registers: no flag round trip, no global-memory latency and no
+//     co-resident tensor-core traffic on the critical path.
+// A task only ever waits for tasks with a smaller ticket or for the walker, and the walker is the
+// first CTA that starts, so there is no deadlock whatever the number of resident CTAs.  Finished
+// tiles are published with release stores; consumers poll with relaxed loads and one acquire fence.
 // The right-hand side rides along as an extra matrix row ("bordered" factorisation), which
 // yields y = L^-1 rhs for free; the backward substitution L^T x = y is a second dataflow kernel
 // (one CTA per 64-block, chained by flags).
@@ -36,9 +38,10 @@ constexpr int NB = 64;
 constexpr int kCS = 68;  // row stride (doubles) of a 64x64 tile in shared memory
 constexpr int kKC = 32;  // k-chunk width of the operand pipeline
 constexpr int kKS = 36;  // row stride (doubles) of a 64x32 chunk in shared memory
+constexpr int kStages = 3;
 constexpr int kStageDoubles = 64 * kKS;
-constexpr int kFactorSmem = 2 * 2 * kStageDoubles * (int)sizeof(double);  // 73 728 B
-static_assert(2 * 64 * kCS * (int)sizeof(double) <= kFactorSmem, "tile pair must fit the stages");
+constexpr int kFactorSmem = kStages * 2 * kStageDoubles * (int)sizeof(double);  // 110 592 B
+static_assert(3 * 64 * kCS * (int)sizeof(double) <= kFactorSmem, "walker needs three tiles");
 
 // ---- PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -102,25 +105,39 @@ __device__ __forceinline__ unsigned long long global_ns() {
     if (trace != nullptr && threadIdx.x == 0) trace[16 * (size_t)(i * T + j) + (slot)] = global_ns(); \
   } while (0)
 
-// Work-buffer layout (doubles unless noted): one Lpack and one Linv per 64-block, y/x scratch,
-// then the int flags.
+__device__ __forceinline__ unsigned smid() {
+  unsigned v;
+  asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
+  return v;
+}
+// Work buffer: Lpack per 64-block (L_jj with its 16x16 diagonal sub-blocks replaced by their
+// inverses: what the triangular solves and the back-substitution need), then the int flags:
+// [0] factor ticket, [1] back-solve ticket, [2] role word, [3] walker SM id + 1,
+// [4, 4+T*T) tile flags (X_ij final; for i == j: Lpack_j published), [.., +T*T) pre flags
+// (diagonal / sub-diagonal tile pre-accumulated), then [nblk] x flags.
 struct Work {
-  double* lpack;  // [nblk][64*64]  L_jj with its 16x16 diagonal sub-blocks replaced by their inverses
-  double* linv;   // [nblk][64*64]  dense L_jj^-1 (back-substitution)
-  int* flags;     // [0] factor ticket, [1] back-solve ticket, [2 .. 2+T*T) tile flags,
-                  // then [nblk] x flags
+  double* lpack;
+  int* flags;
+  int *tile, *pre, *xf;
 };
 __host__ __device__ inline Work work_layout(double* base, int n) {
-  const size_t nblk = (size_t)(n + NB - 1) / NB;
+  const size_t nblk = (size_t)(n + NB - 1) / NB, T = (size_t)(n + 1 + NB - 1) / NB;
   Work w;
   w.lpack = base;
-  w.linv = base + nblk * NB * NB;
-  w.flags = reinterpret_cast<int*>(base + 2 * nblk * NB * NB);
+  w.flags = reinterpret_cast<int*>(base + nblk * NB * NB);
+  w.tile = w.flags + 4;
+  w.pre = w.tile + T * T;
+  w.xf = w.pre + T * T;
   return w;
 }
 inline size_t work_flag_ints(int n) {
   const size_t T = (size_t)(n + 1 + NB - 1) / NB, nblk = (size_t)(n + NB - 1) / NB;
-  return 2 + T * T + nblk;
+  return 4 + 2 * T * T + nblk;
+}
+
+__device__ __forceinline__ void wait_flag(const int* f) {
+  while (ld_relaxed(f) == 0) __nanosleep(40);
+  fence_acquire();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -172,88 +189,111 @@ __device__ __forceinline__ bool factor8(double* Cs, int k1, double* rdiag, int l
 }
 
 // ------------------------------------------------------------------------------------------
-// Diagonal task: Cs (64 x kCS, lower triangle valid) -> L_jj.  kb = number of real rows in this
-// block (< 64 only for the last block, whose tile also carries the right-hand-side row).
-// Publishes L (into A), Lpack (for the triangular solves of the tiles below) and then — off the
-// critical path — the dense inverse for the back-substitution.
+// In-place factorisation of the 64x64 tile in Cs (lower triangle valid): L overwrites the lower
+// triangle, the inverses of the four 16x16 diagonal sub-blocks go to the diagonal blocks of Tm.
+// Eight rounds: 8x8 factor (warp 0) -> panel rows by forward substitution -> trailing update on
+// the tensor cores.  All 256 threads call it.
 // ------------------------------------------------------------------------------------------
-__device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, int j, double* smem,
-                          const Work& w, int T, int* __restrict__ status,
-                          unsigned long long* __restrict__ trace) {
-  const int i = j;
-  double* Cs = smem;                                   // [64][kCS]
-  double* Tm = smem + 64 * kCS;                        // [64][kCS] L^-1: 16x16 diagonal blocks
-                                                       // first, the rest after the publish
-  __shared__ double rdiag[NB];
-  __shared__ double rhs_row[NB];
-  __shared__ int s_bad;
+// 64x64 tile global (leading dimension ld) -> shared (stride kCS), asynchronously
+__device__ __forceinline__ void tile_prefetch(double* dst, const double* src, int ld) {
+  for (int p = threadIdx.x; p < NB * 32; p += 256) {
+    const int r = p >> 5, s = p & 31;
+    cp_async16(dst + r * kCS + 2 * s, src + (size_t)r * ld + 2 * s);
+  }
+  cp_async_commit();
+}
+
+// Optional hook: while the block is being factored the walker wants the next tile it needs
+// (pre-accumulated by the helpers) in shared memory as early as possible; thread 0 polls the
+// tile's flag once per round and the CTA issues the cp.async prefetch as soon as it is up.
+struct PrefetchHook {
+  const int* flag = nullptr;  // nullptr: nothing to prefetch
+  double* dst = nullptr;
+  const double* src = nullptr;
+  int ld = 0;
+  bool issued = false;
+};
+
+__device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int* s_bad,
+                                     PrefetchHook* hook) {
+  __shared__ int s_hook;
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index broadcast from lane 0: the compiler then knows the warp-specialised branches
   // below are warp-uniform and emits plain SHFL instead of WARPSYNC.COLLECTIVE sequences
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int k0 = j * NB;
-  const int kb = min(NB, n - k0);
-  if (tid == 0) s_bad = 0;
-  if (kb < NB) {
-    // last, partial block: keep the right-hand-side row aside, pad with the identity
-    if (tid < NB) rhs_row[tid] = (tid < kb) ? Cs[kb * kCS + tid] : 0.0;
-    __syncthreads();
-    for (int idx = tid; idx < NB * NB; idx += 256) {
-      const int r = idx >> 6, c = idx & 63;
-      if (r >= kb || c >= kb) Cs[r * kCS + c] = (r == c) ? 1.0 : 0.0;
-    }
-  }
-  // (only the lower triangle of Cs is ever read; Tm is fully written before it is read)
-  __syncthreads();
-  CHOL_TRACE(4);
   const int g = lane >> 2, q = lane & 3;  // mma fragment coordinates
+  if (warp == 0) {
+    const bool bad = factor8(Cs, 0, rdiag, lane);
+    if (bad && lane == 0) *s_bad = 1;
+  }
+  const bool want = hook->flag != nullptr && !hook->issued;
+  if (want && tid == 32) {  // (warp 1 idles during the first 8x8 factor)
+    s_hook = ld_relaxed(hook->flag) != 0;
+    if (s_hook) fence_acquire();
+  }
+  __syncthreads();
 #pragma unroll 1
-  for (int bk = 0; bk < 8; ++bk) {
+  for (int bk = 0; bk < 7; ++bk) {
     const int k1 = 8 * bk;
-    if (warp == 0) {
-      const bool bad = factor8(Cs, k1, rdiag, lane);
-      if (bad && lane == 0) s_bad = 1;
+    const int below = NB - (k1 + 8);
+    if (want && !hook->issued && s_hook) {
+      tile_prefetch(hook->dst, hook->src, hook->ld);
+      hook->issued = true;
+    }
+    // panel: row r of X = A_r L^-T by forward substitution, one thread per row
+    if (tid < below) {
+      double* rowp = Cs + (k1 + 8 + tid) * kCS + k1;
+      double x[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) x[c] = rowp[c];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        x[c] *= rdiag[k1 + c];
+#pragma unroll
+        for (int p = c + 1; p < 8; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) rowp[c] = x[c];
     }
     __syncthreads();
-    const int below = NB - (k1 + 8);
-    if (below > 0) {
-      // panel: row r of X = A_r L^-T by forward substitution, one thread per row
-      if (tid < below) {
-        double* rowp = Cs + (k1 + 8 + tid) * kCS + k1;
-        double x[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) x[c] = rowp[c];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          x[c] *= rdiag[k1 + c];
-#pragma unroll
-          for (int p = c + 1; p < 8; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) rowp[c] = x[c];
-      }
-      __syncthreads();
-      // trailing update inside the tile on the FP64 tensor cores: 8x8 output tiles (lower
-      // part), C -= X_ti X_tj^T with k = 8 (two m8n8k4 steps)
-      const int nb = below >> 3;
-      const int ntile = nb * (nb + 1) / 2;
-      const double* X = Cs + (k1 + 8) * kCS + k1;
-      for (int t = warp; t < ntile; t += 8) {
-        int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-        while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-        while (ti * (ti + 1) / 2 > t) --ti;
-        const int tj = t - ti * (ti + 1) / 2;
-        double* cp = Cs + (k1 + 8 + 8 * ti + g) * kCS + k1 + 8 + 8 * tj + 2 * q;
-        double2 cv = *reinterpret_cast<double2*>(cp);
-        const double a0 = -X[(8 * ti + g) * kCS + q], a1 = -X[(8 * ti + g) * kCS + 4 + q];
-        const double b0 = X[(8 * tj + g) * kCS + q], b1 = X[(8 * tj + g) * kCS + 4 + q];
-        dmma_m8n8k4(cv.x, cv.y, a0, b0);
-        dmma_m8n8k4(cv.x, cv.y, a1, b1);
-        *reinterpret_cast<double2*>(cp) = cv;
-      }
-      __syncthreads();
+    // (s_hook is only written between the two barriers of a round and read after the second one,
+    // so every thread takes the same prefetch decision)
+    if (want && !hook->issued && tid == 255) {
+      s_hook = ld_relaxed(hook->flag) != 0;
+      if (s_hook) fence_acquire();
     }
-    if (bk & 1) CHOL_TRACE(5 + bk - 1);
+    // trailing update inside the tile on the FP64 tensor cores: 8x8 output tiles (lower part),
+    // C -= X_ti X_tj^T with k = 8 (two m8n8k4 steps).  Look-ahead: warp 0 updates the next
+    // diagonal 8x8 block first and factors it right away, the other warps do the rest.
+    const int nb = below >> 3;
+    const int ntile = nb * (nb + 1) / 2;
+    const double* X = Cs + (k1 + 8) * kCS + k1;
+    auto update_tile = [&](int t) {
+      int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
+      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
+      while (ti * (ti + 1) / 2 > t) --ti;
+      const int tj = t - ti * (ti + 1) / 2;
+      double* cp = Cs + (k1 + 8 + 8 * ti + g) * kCS + k1 + 8 + 8 * tj + 2 * q;
+      double2 cv = *reinterpret_cast<double2*>(cp);
+      const double a0 = -X[(8 * ti + g) * kCS + q], a1 = -X[(8 * ti + g) * kCS + 4 + q];
+      const double b0 = X[(8 * tj + g) * kCS + q], b1 = X[(8 * tj + g) * kCS + 4 + q];
+      dmma_m8n8k4(cv.x, cv.y, a0, b0);
+      dmma_m8n8k4(cv.x, cv.y, a1, b1);
+      *reinterpret_cast<double2*>(cp) = cv;
+    };
+    if (warp == 0) {
+      update_tile(0);
+      __syncwarp();
+      const bool bad = factor8(Cs, k1 + 8, rdiag, lane);
+      if (bad && lane == 0) *s_bad = 1;
+    } else {
+      for (int t = warp; t < ntile; t += 7) update_tile(t);
+    }
+    __syncthreads();
+  }
+  if (want && !hook->issued && s_hook) {
+    tile_prefetch(hook->dst, hook->src, hook->ld);
+    hook->issued = true;
   }
   // Inverses of the 16x16 diagonal sub-blocks (what the triangular solves of the tiles below
   // use): 8x8 inverses by forward substitution, one thread per column, then
@@ -301,108 +341,18 @@ __device__ __noinline__ void diag_task(double* __restrict__ A, int ld, int n, in
     Tm[(o + 8 + r) * kCS + o + c] = res;
   }
   __syncthreads();
-  CHOL_TRACE(13);
-  // publish Lpack (what the triangular solves of the tiles below need), then raise the flag
-  double* lpack = w.lpack + (size_t)j * NB * NB;
-  for (int idx = tid; idx < NB * NB / 2; idx += 256) {
-    const int r = idx >> 5, c = (idx & 31) * 2;
-    const double* src = (((r >> 4) == (c >> 4)) ? Tm : Cs) + r * kCS + c;
-    *reinterpret_cast<double2*>(lpack + r * NB + c) = *reinterpret_cast<const double2*>(src);
-  }
-  __syncthreads();
-  CHOL_TRACE(14);
-  if (tid == 0) {
-    if (s_bad) atomicExch(status, 1);
-    __threadfence();
-    st_release(w.flags + 2 + j * T + j, 1);
-  }
-  CHOL_TRACE(2);
-  // ---- off the critical path: L into A (read by the back-substitution kernel), then the dense
-  //      L^-1 by block forward substitution
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    if (r < kb && c <= r) A[(size_t)(k0 + r) * ld + k0 + c] = Cs[r * kCS + c];
-  }
-  //      Linv[bi][bj] = -I16[bi] * sum_{bk = bj}^{bi-1} L[bi][bk] Linv[bk][bj]
-#pragma unroll 1
-  for (int dist = 1; dist < 4; ++dist) {
-    const int nblk = 4 - dist;  // blocks (bi = bj + dist, bj)
-    double tmp[3];
-    int cnt = 0;
-    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
-      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      double acc = 0.0;
-      for (int p2 = 16 * bj; p2 < 16 * bi; ++p2)
-        acc += Cs[(16 * bi + r) * kCS + p2] * Tm[p2 * kCS + 16 * bj + c];
-      tmp[cnt] = acc;
-    }
-    // tmp -> scratch above the diagonal of Tm (unused otherwise): Tm[bj-rows][bi-cols]
-    cnt = 0;
-    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
-      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      Tm[(16 * bj + r) * kCS + 16 * bi + c] = tmp[cnt];
-    }
-    __syncthreads();
-    cnt = 0;
-    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
-      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      double acc = 0.0;
-#pragma unroll
-      for (int p2 = 0; p2 < 16; ++p2)
-        acc += Tm[(16 * bi + r) * kCS + 16 * bi + p2] * Tm[(16 * bj + p2) * kCS + 16 * bi + c];
-      tmp[cnt] = -acc;
-    }
-    __syncthreads();
-    cnt = 0;
-    for (int idx = tid; idx < nblk * 256; idx += 256, ++cnt) {
-      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, c = idx & 15;
-      Tm[(16 * bi + r) * kCS + 16 * bj + c] = tmp[cnt];
-    }
-    __syncthreads();
-  }
-  double* linv = w.linv + (size_t)j * NB * NB;
-  for (int idx = tid; idx < NB * NB; idx += 256) {
-    const int r = idx >> 6, c = idx & 63;
-    linv[idx] = (c <= r) ? Tm[r * kCS + c] : 0.0;
-  }
-  // the right-hand-side row of the last, partial block: y = rhs L^-T
-  if (kb < NB && tid < kb) {
-    double acc = 0.0;
-    for (int p = 0; p <= tid; ++p) acc += rhs_row[p] * Tm[tid * kCS + p];
-    A[(size_t)n * ld + k0 + tid] = acc;
-  }
-  __syncthreads();
 }
 
 // ------------------------------------------------------------------------------------------
-// Off-diagonal task: X = C L_jj^-T for the 64x64 tile in Cs, warp-local (warp w owns rows
-// 8w..8w+7), in four 16-column steps:  X_b = (C_b - sum_{b'<b} X_b' L_bb'^T) inv(L_bb)^T.
-// acc[nb] are the tile's C fragments (nb = 8-column block).
+// X = C L^-T for a 64x64 tile, warp-local (warp w owns rows 8w..8w+7), in four 16-column steps:
+//   X_b = (C_b - sum_{b'<b} X_b' L_bb'^T) inv(L_bb)^T.
+// acc[nb] holds the tile's C fragments on entry and X's on exit; Lp = Lpack in shared memory;
+// Xs receives X (row-major, stride kCS) as it is produced.
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i, int j,
-                                          double (&acc)[8][2], double* smem, const Work& w,
-                                          int T, unsigned long long* __restrict__ trace) {
-  double* Xs = smem;             // [64][kCS]: own rows, X blocks as they are produced
-  double* Lp = smem + 64 * kCS;  // [64][kCS]: Lpack_j
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+__device__ __forceinline__ void trsm_core(double (&acc)[8][2], double* Xs, const double* Lp) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int row = warp * 8 + g;
-  if (tid == 0) {
-    const int* f = w.flags + 2 + j * T + j;
-    while (ld_relaxed(f) == 0) __nanosleep(40);
-    fence_acquire();
-  }
-  __syncthreads();
-  {
-    const double* src = w.lpack + (size_t)j * NB * NB;
-    for (int p = tid; p < NB * 32; p += 256) {  // 16-byte pieces
-      const int r = p >> 5, s = p & 31;
-      cp_async16(Lp + r * kCS + 2 * s, src + r * NB + 2 * s);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-  }
-  __syncthreads();
 #pragma unroll
   for (int b = 0; b < 4; ++b) {
     double t0[2] = {acc[2 * b][0], acc[2 * b][1]};
@@ -432,26 +382,226 @@ __device__ __forceinline__ void trsm_task(double* __restrict__ A, int ld, int i,
     *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 2 * q) = make_double2(x0[0], x0[1]);
     *reinterpret_cast<double2*>(Xs + row * kCS + 16 * b + 8 + 2 * q) = make_double2(x1[0], x1[1]);
     __syncwarp();
-    double* dst = A + (size_t)(i * NB + row) * ld + j * NB + 16 * b + 2 * q;
-    *reinterpret_cast<double2*>(dst) = make_double2(x0[0], x0[1]);
-    *reinterpret_cast<double2*>(dst + 8) = make_double2(x1[0], x1[1]);
+    acc[2 * b][0] = x0[0]; acc[2 * b][1] = x0[1];
+    acc[2 * b + 1][0] = x1[0]; acc[2 * b + 1][1] = x1[1];
   }
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    st_release(w.flags + 2 + i * T + j, 1);
+}
+
+// fragments <-> global / shared tiles (warp w rows 8w..8w+7; fragment nb = columns 8nb+2q, +1)
+__device__ __forceinline__ void frag_store_global(const double (&acc)[8][2], double* tile, int ld) {
+  const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) * 8 + (lane >> 2), q = lane & 3;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+    *reinterpret_cast<double2*>(tile + (size_t)row * ld + 8 * nb + 2 * q) =
+        make_double2(acc[nb][0], acc[nb][1]);
+}
+__device__ __forceinline__ void frag_load_smem(double (&acc)[8][2], const double* tile) {
+  const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) * 8 + (lane >> 2), q = lane & 3;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb) {
+    const double2 v = *reinterpret_cast<const double2*>(tile + row * kCS + 8 * nb + 2 * q);
+    acc[nb][0] = v.x;
+    acc[nb][1] = v.y;
   }
-  CHOL_TRACE(2);
+}
+__device__ __forceinline__ void frag_store_smem(const double (&acc)[8][2], double* tile) {
+  const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) * 8 + (lane >> 2), q = lane & 3;
+#pragma unroll
+  for (int nb = 0; nb < 8; ++nb)
+    *reinterpret_cast<double2*>(tile + row * kCS + 8 * nb + 2 * q) = make_double2(acc[nb][0], acc[nb][1]);
 }
 
 // ------------------------------------------------------------------------------------------
-// The factorisation kernel: persistent CTAs (256 threads) pulling tile tasks from a ticket.
+// The walker: diagonal and sub-diagonal tiles, one column after the other.
+// Shared memory: Cs (current diagonal tile -> L -> Lpack), Tm (block inverses, then X of the
+// sub-diagonal tile), Ps (prefetch buffer for the pre-accumulated tiles the helpers hand over).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256, 3)
+__device__ void walker(double* __restrict__ A, int ld, int n, double* smem, const Work& w, int T,
+                       int ncols, int* __restrict__ status,
+                       unsigned long long* __restrict__ trace) {
+  double* Cs = smem;
+  double* Tm = smem + 64 * kCS;
+  double* Ps = smem + 2 * 64 * kCS;
+  __shared__ double rdiag[NB], rhs_row[NB];
+  __shared__ int s_bad, s_poll;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, q = lane & 3;
+  if (tid == 0) s_bad = 0;
+  int pending_diag = -1, pending_tile = -1;  // flags to raise (by warp 1) once their stores are ordered
+  // C_00
+  if (tid == 0) wait_flag(w.pre + 0);
+  __syncthreads();
+  tile_prefetch(Cs, A, ld);
+  cp_async_wait<0>();
+  __syncthreads();
+  for (int j = 0; j < ncols; ++j) {
+    const int k0 = j * NB;
+    const int kb = min(NB, n - k0);
+    const bool has_row = j + 1 < T;      // a tile row below (it may be the right-hand-side row only)
+    const bool has_next = j + 1 < ncols; // a next diagonal block
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 1] = global_ns();
+    // the pre-accumulated sub-diagonal tile is prefetched into Ps while the diagonal block is
+    // factored, as soon as the helpers have it ready
+    PrefetchHook hook;
+    if (has_row) {
+      hook.flag = w.pre + (j + 1) * T + j;
+      hook.dst = Ps;
+      hook.src = A + (size_t)(k0 + NB) * ld + k0;
+      hook.ld = ld;
+    }
+    // raise the flags of the previous column now: warp 1 idles during the first 8x8 factor anyway
+    if (warp == 1 && lane == 0 && (pending_diag >= 0 || pending_tile >= 0)) {
+      __threadfence();
+      if (pending_diag >= 0) st_release(w.tile + pending_diag, 1);
+      if (pending_tile >= 0) st_release(w.tile + pending_tile, 1);
+    }
+    pending_diag = pending_tile = -1;
+    if (kb < NB) {
+      // last, partial block: keep the right-hand-side row aside, pad with the identity
+      if (tid < NB) rhs_row[tid] = (tid < kb) ? Cs[kb * kCS + tid] : 0.0;
+      __syncthreads();
+      for (int idx = tid; idx < NB * NB; idx += 256) {
+        const int r = idx >> 6, c = idx & 63;
+        if (r >= kb || c >= kb) Cs[r * kCS + c] = (r == c) ? 1.0 : 0.0;
+      }
+      __syncthreads();
+    }
+    potrf64(Cs, Tm, rdiag, &s_bad, &hook);
+    // Cs := Lpack (diagonal 16x16 blocks <- their inverses)
+    for (int idx = tid; idx < 4 * 256; idx += 256) {
+      const int b = idx >> 8, r = 16 * b + ((idx >> 4) & 15), c = 16 * b + (idx & 15);
+      Cs[r * kCS + c] = Tm[r * kCS + c];
+    }
+    __syncthreads();
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 2] = global_ns();
+    if (kb < NB) {
+      // y = rhs L^-T for the right-hand-side row of the last block: column-oriented substitution
+      // with the blocked factor (off-diagonal blocks = L, diagonal blocks = inverses)
+      if (tid < NB) {
+        // v = rhs (thread c owns entry c); four 16-blocks
+        double v = rhs_row[tid];
+        for (int b = 0; b < 4; ++b) {
+          // x_b = v_b inv(L_bb)^T : x_c = sum_{p <= c, p in block} v_p I[c][p]
+          __syncwarp();
+          if ((tid >> 4) == b) rhs_row[tid] = v;
+          __threadfence_block();
+          asm volatile("bar.sync 1, 64;");
+          double x = 0.0;
+          if ((tid >> 4) == b)
+            for (int p = 16 * b; p <= tid; ++p) x += rhs_row[p] * Cs[tid * kCS + p];
+          asm volatile("bar.sync 1, 64;");
+          if ((tid >> 4) == b) rhs_row[tid] = x;
+          asm volatile("bar.sync 1, 64;");
+          // v_c -= sum_{p in block b} x_p L[c][p] for the later blocks
+          if ((tid >> 4) > b)
+            for (int p = 16 * b; p < 16 * b + 16; ++p) v -= rhs_row[p] * Cs[tid * kCS + p];
+          if ((tid >> 4) == b) v = x;
+        }
+        if (tid < kb) A[(size_t)n * ld + k0 + tid] = v;
+      }
+      __syncthreads();
+    }
+    // publish Lpack_j (the helpers' triangular solves and the back-substitution read it)
+    {
+      double* lpack = w.lpack + (size_t)j * NB * NB;
+      for (int idx = tid; idx < NB * NB / 2; idx += 256) {
+        const int r = idx >> 5, c = (idx & 31) * 2;
+        *reinterpret_cast<double2*>(lpack + r * NB + c) =
+            *reinterpret_cast<const double2*>(Cs + r * kCS + c);
+      }
+      pending_diag = j * T + j;
+    }
+    if (!has_row) {
+      __syncthreads();
+      break;
+    }
+    // sub-diagonal tile: X = C L^-T, kept in Tm for the update of the next diagonal tile
+    if (!hook.issued) {
+      if (tid == 0) wait_flag(w.pre + (j + 1) * T + j);
+      __syncthreads();
+      tile_prefetch(Ps, A + (size_t)(k0 + NB) * ld + k0, ld);
+    }
+    cp_async_wait<0>();
+    __syncthreads();
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 4] = global_ns();
+    // Lpack_j is needed by the helpers' triangular solves of this column, which head the chain
+    // that produces the walker's inputs of the NEXT column: publish it now (costs warp 1 one
+    // membar of latency inside the solve below) instead of at the top of the next iteration
+    if (tid == 32 && pending_diag >= 0) {
+      __threadfence();
+      st_release(w.tile + pending_diag, 1);
+    }
+    pending_diag = -1;
+    double acc[8][2];
+    frag_load_smem(acc, Ps);
+    // the pre-accumulated next diagonal tile follows into Ps: start the copy before the solve if
+    // the helpers are done with it, otherwise right after
+    bool next_issued = false;
+    if (has_next) {
+      if (tid == 0) {
+        s_poll = ld_relaxed(w.pre + (j + 1) * T + (j + 1)) != 0;
+        if (s_poll) fence_acquire();
+      }
+      __syncthreads();  // (also: every warp has its fragments, Ps may be overwritten)
+      if (s_poll) {
+        tile_prefetch(Ps, A + (size_t)(k0 + NB) * ld + k0 + NB, ld);
+        next_issued = true;
+      }
+    }
+    trsm_core(acc, Tm, Cs);
+    frag_store_global(acc, A + (size_t)(k0 + NB) * ld + k0, ld);
+    pending_tile = (j + 1) * T + j;
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 5] = global_ns();
+    if (!has_next) {
+      __syncthreads();
+      break;
+    }
+    if (!next_issued) {
+      if (tid == 0) wait_flag(w.pre + (j + 1) * T + (j + 1));
+      __syncthreads();
+      tile_prefetch(Ps, A + (size_t)(k0 + NB) * ld + k0 + NB, ld);
+    }
+    // next diagonal tile: C -= X X^T (the one term the helpers could not pre-accumulate); only
+    // the 36 lower 8x8 blocks, dealt round-robin to the warps
+    cp_async_wait<0>();
+    __syncthreads();  // X complete in Tm, pre-accumulated tile complete in Ps, Lpack stores issued
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 6] = global_ns();
+#pragma unroll 1
+    for (int e = warp; e < 36; e += 8) {
+      int bi = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+      while ((bi + 1) * (bi + 2) / 2 <= e) ++bi;
+      while (bi * (bi + 1) / 2 > e) --bi;
+      const int bj = e - bi * (bi + 1) / 2;
+      double2 cv = *reinterpret_cast<const double2*>(Ps + (8 * bi + g) * kCS + 8 * bj + 2 * q);
+#pragma unroll
+      for (int kk = 0; kk < NB; kk += 4) {
+        const double a = -Tm[(8 * bi + g) * kCS + kk + q];
+        const double b = Tm[(8 * bj + g) * kCS + kk + q];
+        dmma_m8n8k4(cv.x, cv.y, a, b);
+      }
+      *reinterpret_cast<double2*>(Cs + (8 * bi + g) * kCS + 8 * bj + 2 * q) = cv;
+    }
+    __syncthreads();
+    if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 7] = global_ns();
+  }
+  // flags of the last column
+  if (tid == 0) {
+    if (s_bad) atomicExch(status, 1);
+    __threadfence();
+    if (pending_diag >= 0) st_release(w.tile + pending_diag, 1);
+    if (pending_tile >= 0) st_release(w.tile + pending_tile, 1);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// The factorisation kernel: persistent CTAs (256 threads); the first one to start is the walker,
+// the others pull tile tasks from a ticket.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256, 2)
 chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ work_base,
                    int* __restrict__ status, unsigned long long* __restrict__ trace) {
   extern __shared__ __align__(16) double smem[];
-  __shared__ int s_ticket, s_ready;
+  __shared__ int s_ticket, s_ready, s_role;
   const Work w = work_layout(work_base, n);
   const int T = ld / NB;
   const int ncols = (n + NB - 1) / NB;
@@ -459,7 +609,23 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   const int row = warp * 8 + g;
-  int* tile_flags = w.flags + 2;
+
+  if (tid == 0) {
+    s_role = atomicCAS(w.flags + 2, 0, 1) == 0 ? 1 : 0;
+    if (s_role) {
+      st_release(w.flags + 3, (int)smid() + 1);
+    } else {
+      int ws;
+      while ((ws = ld_relaxed(w.flags + 3)) == 0) __nanosleep(40);
+      if (ws == (int)smid() + 1) s_role = 2;  // shares the walker's SM: leave it alone
+    }
+  }
+  __syncthreads();
+  if (s_role == 2) return;
+  if (s_role == 1) {
+    walker(A, ld, n, smem, w, T, ncols, status, trace);
+    return;
+  }
 
   for (;;) {
     __syncthreads();  // previous task is completely done with shared memory
@@ -474,7 +640,12 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
       ++j;
     }
     const int i = j + (t - off);
-    CHOL_TRACE(0);
+    if (trace && tid == 0) trace[16 * (size_t)(i * T + j)] = global_ns();
+    const bool diag = (i == j);
+    const bool pre_only = (i - j) <= 1;  // finished by the walker
+    // terms the task accumulates: k < j, except that the last one of a diagonal tile needs the
+    // sub-diagonal tile of the previous column, which the walker produces and applies itself
+    const int nk = diag ? (j > 0 ? j - 1 : 0) : j;
 
     // accumulators start as A_ij; the k loop subtracts X_ik X_jk^T
     double acc[8][2];
@@ -487,11 +658,10 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
         acc[nb][1] = v.y;
       }
     }
-    const int nchunks = 2 * j;
-    const bool diag = (i == j);
+    const int nchunks = 2 * nk;
     int issued = 0, known_k = 0;  // chunks issued; operand tiles of columns < known_k are ready
     auto issue = [&](int c) {
-      const int k = c >> 1, half = c & 1, st = c & 1;
+      const int k = c >> 1, half = c & 1, st = c % kStages;
       double* si = smem + (size_t)(st * 2) * kStageDoubles;
       double* sj = si + kStageDoubles;
       const double* gi = A + (size_t)(i * NB) * ld + k * NB + half * kKC;
@@ -504,14 +674,14 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
       cp_async_commit();
     };
     for (int c = 0; c < nchunks; ++c) {
-      // keep up to two chunks in flight; block on a flag only when there is nothing to compute
-      while (issued < nchunks && issued < c + 2) {
+      // keep up to kStages chunks in flight; block on a flag only when there is nothing to compute
+      while (issued < nchunks && issued < c + kStages) {
         const int k = issued >> 1;
         if (k >= known_k) {
           const bool must = (issued == c);
           if (tid == 0) {
-            const int* fi = tile_flags + i * T + k;
-            const int* fj = tile_flags + j * T + k;
+            const int* fi = w.tile + i * T + k;
+            const int* fj = w.tile + j * T + k;
             int ok = (ld_relaxed(fi) != 0) && (ld_relaxed(fj) != 0);
             while (!ok && must) {
               __nanosleep(40);
@@ -529,9 +699,12 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
         issue(issued);
         ++issued;
       }
-      if (issued - c - 1 >= 1) cp_async_wait<1>(); else cp_async_wait<0>();
+      const int in_flight = issued - c - 1;  // groups younger than chunk c
+      if (in_flight >= 2) cp_async_wait<2>();
+      else if (in_flight == 1) cp_async_wait<1>();
+      else cp_async_wait<0>();
       __syncthreads();
-      const int st = c & 1;
+      const int st = c % kStages;
       const double* Xi = smem + (size_t)(st * 2) * kStageDoubles;
       const double* Xj = diag ? Xi : Xi + kStageDoubles;
 #pragma unroll
@@ -545,18 +718,38 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
       }
       __syncthreads();  // stage st may be overwritten
     }
-    CHOL_TRACE(1);
-    if (diag) {
-      // C fragments -> shared tile
-#pragma unroll
-      for (int nb = 0; nb < 8; ++nb)
-        *reinterpret_cast<double2*>(smem + row * kCS + nb * 8 + 2 * q) =
-            make_double2(acc[nb][0], acc[nb][1]);
+    if (trace && tid == 0) trace[16 * (size_t)(i * T + j) + 3] = global_ns();
+    if (pre_only) {
+      // hand the pre-accumulated tile to the walker (in place)
+      if (nchunks > 0) frag_store_global(acc, A + (size_t)(i * NB) * ld + j * NB, ld);
       __syncthreads();
-      diag_task(A, ld, n, j, smem, w, T, status, trace);
-      CHOL_TRACE(3);
-    } else {
-      trsm_task(A, ld, i, j, acc, smem, w, T, trace);
+      if (tid == 0) {
+        __threadfence();
+        st_release(w.pre + i * T + j, 1);
+      }
+      continue;
+    }
+    // X = C L_jj^-T with the published Lpack_j
+    double* Xs = smem;             // [64][kCS]
+    double* Lp = smem + 64 * kCS;  // [64][kCS]
+    if (tid == 0) wait_flag(w.tile + j * T + j);
+    __syncthreads();
+    {
+      const double* src = w.lpack + (size_t)j * NB * NB;
+      for (int p = tid; p < NB * 32; p += 256) {  // 16-byte pieces
+        const int r = p >> 5, s = p & 31;
+        cp_async16(Lp + r * kCS + 2 * s, src + r * NB + 2 * s);
+      }
+      cp_async_commit();
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    trsm_core(acc, Xs, Lp);
+    frag_store_global(acc, A + (size_t)(i * NB) * ld + j * NB, ld);
+    __syncthreads();
+    if (tid == 0) {
+      __threadfence();
+      st_release(w.tile + i * T + j, 1);
     }
   }
 }
@@ -564,7 +757,8 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
 // ------------------------------------------------------------------------------------------
 // Backward substitution L^T x = y as a dataflow kernel: one CTA per 64-block (descending by
 // ticket).  CTA j streams the tiles L[b][j], b > j, through a cp.async double buffer, applies
-// y_j -= L[b][j]^T x_b as soon as x_b is published, then x_j = L_jj^-T y_j.
+// y_j -= L[b][j]^T x_b as soon as x_b is published, then solves L_jj^T x_j = y_j with the blocked
+// factor Lpack_j (four 16-wide steps: off-diagonal blocks of L, inverses on the diagonal).
 // ------------------------------------------------------------------------------------------
 constexpr int kBackSmem = 3 * NB * NB * (int)sizeof(double);
 
@@ -575,9 +769,8 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   __shared__ double yj[NB], xb[NB], red[4][NB];
   __shared__ int s_ticket;
   const Work w = work_layout(work_base, n);
-  const int T = ld / NB;
   const int nblk = (n + NB - 1) / NB;
-  int* xflags = w.flags + 2 + T * T;
+  int* xflags = w.xf;
   const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
   if (tid == 0) s_ticket = atomicAdd(w.flags + 1, 1);
   __syncthreads();
@@ -585,7 +778,7 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   if (j < 0) return;
   const int k0 = j * NB;
   const int kb = min(NB, n - k0);
-  double* Linv = smem;                 // [64][64]
+  double* Lp = smem;                   // [64][64] Lpack_j
   double* stage0 = smem + NB * NB;     // two tile stages
   auto issue_tile = [&](int b, int st) {
     double* dst = stage0 + (size_t)st * NB * NB;
@@ -597,8 +790,8 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
     cp_async_commit();
   };
   {
-    const double* src = w.linv + (size_t)j * NB * NB;
-    for (int p = tid; p < NB * 32; p += 256) cp_async16(Linv + 2 * p, src + 2 * p);
+    const double* src = w.lpack + (size_t)j * NB * NB;
+    for (int p = tid; p < NB * 32; p += 256) cp_async16(Lp + 2 * p, src + 2 * p);
     cp_async_commit();
   }
   if (tid < NB) yj[tid] = (tid < kb) ? ld_cg(A + (size_t)n * ld + k0 + tid) : 0.0;
@@ -606,10 +799,7 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   for (int cnt = 0; cnt < 2 && issued_b > j; ++cnt, --issued_b) issue_tile(issued_b, (nblk - 1 - issued_b) & 1);
   for (int b = nblk - 1; b > j; --b) {
     const int st = (nblk - 1 - b) & 1;
-    if (tid == 0) {
-      while (ld_relaxed(xflags + b) == 0) __nanosleep(20);
-      fence_acquire();
-    }
+    if (tid == 0) wait_flag(xflags + b);
     // tile b has been issued; at most one younger group is in flight
     if (issued_b < b - 1) cp_async_wait<1>(); else cp_async_wait<0>();
     __syncthreads();
@@ -632,14 +822,25 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   }
   cp_async_wait<0>();
   __syncthreads();
-  {
-    double s = 0.0;
-#pragma unroll 4
-    for (int r = part; r < NB; r += 4) s += Linv[r * NB + c] * yj[r];  // (L^-1)^T y
-    red[part][c] = s;
+  // L_jj^T x = y by 16-blocks, last block first (threads 0..63, thread c owns entry c):
+  //   x_b = inv(L_bb)^T (y_b - sum_{b' > b} L_b'b^T x_b')
+  if (tid < NB) {
+    double v = yj[tid];
+    for (int b = 3; b >= 0; --b) {
+      if ((tid >> 4) == b) yj[tid] = v;
+      asm volatile("bar.sync 1, 64;");
+      double xv = 0.0;
+      if ((tid >> 4) == b)
+        for (int r = tid; r < 16 * b + 16; ++r) xv += Lp[r * NB + tid] * yj[r];  // inverse block, transposed
+      asm volatile("bar.sync 1, 64;");
+      if ((tid >> 4) == b) yj[tid] = xv;
+      asm volatile("bar.sync 1, 64;");
+      if ((tid >> 4) < b)
+        for (int r = 16 * b; r < 16 * b + 16; ++r) v -= Lp[r * NB + tid] * yj[r];
+      if ((tid >> 4) == b) v = xv;
+    }
+    if (tid < kb) x[k0 + tid] = v;
   }
-  __syncthreads();
-  if (tid < kb) x[k0 + tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
   __syncthreads();
   if (tid == 0) {
     __threadfence();
@@ -652,7 +853,7 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
 int chol_ld(int n) { return ((n + 1 + NB - 1) / NB) * NB; }
 size_t chol_work_doubles(int n) {
   const size_t nblk = (size_t)(n + NB - 1) / NB;
-  return 2 * nblk * NB * NB + (work_flag_ints(n) + 1) / 2 + 2;
+  return nblk * NB * NB + (work_flag_ints(n) + 1) / 2 + 2;
 }
 
 // Factor + solve.  A: ld x ld (see header).  x: n doubles (device).  status: device int, set to
@@ -675,8 +876,8 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* 
   const int T = ld / NB;
   const int ncols = (n + NB - 1) / NB;
   const int ntiles = ncols * T - ncols * (ncols - 1) / 2;
-  int grid = 3 * num_sms;
-  if (grid > ntiles) grid = ntiles;
+  int grid = 2 * num_sms;
+  if (grid > ntiles + 2) grid = ntiles + 2;  // walker + (possibly) the CTA that leaves its SM
   static const char* trace_path = std::getenv("PPSFM_CHOL_TRACE");
   unsigned long long* trace = nullptr;
   if (trace_path) {
@@ -685,7 +886,7 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* 
   }
   chol_factor_kernel<<<grid, 256, kFactorSmem, s>>>(A, ld, n, work, status, trace);
   chol_backsolve_kernel<<<ncols, 256, kBackSmem, s>>>(A, ld, n, work, x);
-  if (trace_path) {  // development aid: dump "i j t0 t1 t2 t3" (ns) per tile
+  if (trace_path) {  // development aid: dump "i j t0..t15" (ns) per tile
     std::vector<unsigned long long> h(16 * (size_t)T * T);
     cudaStreamSynchronize(s);
     cudaMemcpy(h.data(), trace, sizeof(unsigned long long) * h.size(), cudaMemcpyDeviceToHost);
