@@ -12,10 +12,13 @@
 //   ba_point_damp_kernel   thread / point        L^-1, (V + D)^-1, h = L^-1 g_p
 //   ba_zbuild_kernel       thread / observation  192-byte records [Z_e | Z_e h] (coalesced through
 //                                                shared memory)
-//   ba_schur_gather_kernel warp / chunk of <= 128 list entries: each lane accumulates whole 6x6
-//                          products of its entries in registers, a shuffle reduce-scatter leaves 3
-//                          of the 42 sums on every even lane, which writes S (no read-modify-write,
-//                          no memset of the 72 MB matrix, bit-reproducible)
+//   ba_schur_gather_kernel warp / chunk of <= 128 list entries of one camera pair; ONE FP64
+//                          tensor-core MMA (mma.sync.m8n8k4.f64) per entry accumulates
+//                          [Z_e | z_e] (6x4, padded to 8x4) x [Z_f | 1{e=f}]^T into the warp's 8x8
+//                          accumulator fragment: the two 192-byte records are one coalesced load
+//                          each, the kernel needs ~40 registers, and the sums land directly in the
+//                          lanes that store them (no read-modify-write, no memset of the 72 MB
+//                          matrix, bit-reproducible)
 //   ba_schur_multi_kernel  only for camera pairs that span several chunks (few cameras, many
 //                          points): ordered sum of the chunk partials
 // The former one-warp-per-point kernel issued 36 FP64 atomics per camera pair (396 M per
@@ -36,7 +39,7 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kChunk = 128;  // list entries per warp task
-constexpr int kRec = 24;     // doubles per observation record: Z (6x3 row-major), z = Z h (6)
+constexpr int kRec = 24;     // doubles per observation record: rows [Z_a0 Z_a1 Z_a2 z_a], a = 0..5
 
 __device__ __forceinline__ int tri(int i) { return i * (i + 1) / 2; }
 
@@ -171,7 +174,7 @@ ba_point_damp_kernel(BaDev d, double radius, double min_diag, double max_diag) {
   lv[8] = m20 * g0 + m21 * g1 + m22 * g2;
 }
 
-// One thread per observation: record [Z | z].  The 192-byte records of a warp are contiguous
+// One thread per observation: record rows [Z_a | z_a] (6 x 4, the A operand of the gather MMA).  The 192-byte records of a warp are contiguous
 // (6 KB); they are transposed through shared memory so that the warp stores full 512-byte rows.
 constexpr int kZThreads = 128;
 __global__ void __launch_bounds__(kZThreads) ba_zbuild_kernel(BaDev d) {
@@ -203,8 +206,8 @@ __global__ void __launch_bounds__(kZThreads) ba_zbuild_kernel(BaDev d) {
       const double z0 = w0 * m00;                          // Z = W M^T
       const double z1 = w0 * m10 + w1 * m11;
       const double z2 = w0 * m20 + w1 * m21 + w2 * m22;
-      rec[3 * a] = z0; rec[3 * a + 1] = z1; rec[3 * a + 2] = z2;
-      rec[18 + a] = z0 * h0 + z1 * h1 + z2 * h2;
+      rec[4 * a] = z0; rec[4 * a + 1] = z1; rec[4 * a + 2] = z2;
+      rec[4 * a + 3] = z0 * h0 + z1 * h1 + z2 * h2;
     }
   }
   double* st = stage[warp];
@@ -219,27 +222,6 @@ __global__ void __launch_bounds__(kZThreads) ba_zbuild_kernel(BaDev d) {
     const int idx = i * 32 + lane;  // linear index into the warp's 32 x 24 doubles
     if (idx < nvalid) out[idx] = st[(idx / kRec) * (kRec + 1) + (idx % kRec)];
   }
-}
-
-// reduce-scatter over the warp: v[0..47] summed across lanes; afterwards lane L (even) holds the
-// totals of indices base(L) .. base(L)+2 in v[0..2], base(L) = 24 b4 + 12 b3 + 6 b2 + 3 b1.
-__device__ __forceinline__ void warp_reduce_scatter48(double (&v)[48], int lane) {
-#define PPSFM_RS_STEP(H, BIT)                                            \
-  {                                                                      \
-    const bool up = (lane & (BIT)) != 0;                                 \
-    _Pragma("unroll") for (int i = 0; i < (H); ++i) {                    \
-      const double send = up ? v[i] : v[i + (H)];                        \
-      const double keep = up ? v[i + (H)] : v[i];                        \
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, (BIT));           \
-    }                                                                    \
-  }
-  PPSFM_RS_STEP(24, 16)
-  PPSFM_RS_STEP(12, 8)
-  PPSFM_RS_STEP(6, 4)
-  PPSFM_RS_STEP(3, 2)
-#undef PPSFM_RS_STEP
-#pragma unroll
-  for (int i = 0; i < 3; ++i) v[i] += __shfl_xor_sync(0xffffffffu, v[i], 1);
 }
 
 // value `idx` (0..35 = S block element a*6+c, 36..41 = rhs element) of camera pair (bi, bj):
@@ -272,13 +254,21 @@ __device__ __forceinline__ void schur_store(const BaDev& d, int bi, int bj, int 
   d.S[(size_t)(6 * bi + a) * d.ld + 6 * bj + c] = v;
 }
 
-constexpr int kGThreads = 128;
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+constexpr int kGThreads = 256;
+constexpr int kUnroll = 8;  // entries whose record loads are in flight together, per warp
+
 __global__ void __launch_bounds__(kGThreads)
 ba_schur_gather_kernel(BaDev d, double radius, double min_diag, double max_diag,
                        int include_cam) {
   const int w = (int)(((int64_t)blockIdx.x * kGThreads + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
-  if (w >= d.sch_nchunks) return;  // whole warps leave: the shuffles below stay converged
+  if (w >= d.sch_nchunks) return;  // whole warps leave: the collectives below stay converged
   const int pair = d.sch_chunk_pair[w];
   const int c0 = d.sch_pair_chunk[pair], c1 = d.sch_pair_chunk[pair + 1];
   const int64_t begin = d.sch_pair_start[pair] + (int64_t)(w - c0) * kChunk;
@@ -288,49 +278,54 @@ ba_schur_gather_kernel(BaDev d, double radius, double min_diag, double max_diag,
   while (tri(bi + 1) <= pair) ++bi;
   while (tri(bi) > pair) --bi;
   const int bj = pair - tri(bi);
-  double v[48];
+  // MMA fragment coordinates: A[m = g][k = q], B[k = q][n = g], C[m = g][n = 2q, 2q+1]
+  const int g = lane >> 2, q = lane & 3;
+  const bool a_lane = lane < 24;            // rows 0..5 of [Z | z]: record element `lane`
+  const bool b_lane = lane < 24 && q != 3;  // Z_f[n = g][k = q]
+  const bool one_lane = lane == 27;         // B[k = 3][n = 6] = 1 for e == f: column 6 sums z_e
+  double acc0 = 0.0, acc1 = 0.0;
+  const int n = (int)(end - begin);
+  const int lc = lane < 24 ? lane : 23;  // record element this lane loads (clamped: loads are
+                                         // unconditional so that they can all be in flight)
+  const double* __restrict__ Z = d.Zrec;
+  int2 ef_next = make_int2(0, 0);
+  if (lane < n) ef_next = d.sch_ent[begin + lane];
+  for (int base = 0; base < n; base += 32) {
+    const int2 ef = ef_next;
+    if (base + 32 + lane < n) ef_next = d.sch_ent[begin + base + 32 + lane];
+    const int m = min(32, n - base);
+    for (int j0 = 0; j0 < m; j0 += kUnroll) {
+      int ke[kUnroll], kf[kUnroll];
+      double av[kUnroll], bv[kUnroll];
 #pragma unroll
-  for (int i = 0; i < 48; ++i) v[i] = 0.0;
-  for (int64_t idx = begin + lane; idx < end; idx += 32) {
-    const int2 ef = d.sch_ent[idx];
-    const double2* ze = reinterpret_cast<const double2*>(d.Zrec + (size_t)ef.x * kRec);
-    const double2* zf = reinterpret_cast<const double2*>(d.Zrec + (size_t)ef.y * kRec);
-    double E[18], F[18];
+      for (int u = 0; u < kUnroll; ++u) {  // (dead slots read entry (0, 0): valid addresses)
+        ke[u] = __shfl_sync(0xffffffffu, ef.x, (j0 + u) & 31);
+        kf[u] = __shfl_sync(0xffffffffu, ef.y, (j0 + u) & 31);
+      }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const double2 x = ze[i];
-      E[2 * i] = x.x; E[2 * i + 1] = x.y;
-    }
+      for (int u = 0; u < kUnroll; ++u) {
+        av[u] = Z[(size_t)ke[u] * kRec + lc];
+        bv[u] = Z[(size_t)kf[u] * kRec + lc];
+      }
 #pragma unroll
-    for (int i = 0; i < 9; ++i) {
-      const double2 x = zf[i];
-      F[2 * i] = x.x; F[2 * i + 1] = x.y;
-    }
-#pragma unroll
-    for (int a = 0; a < 6; ++a)
-#pragma unroll
-      for (int c = 0; c < 6; ++c)
-        v[6 * a + c] += E[3 * a] * F[3 * c] + E[3 * a + 1] * F[3 * c + 1] + E[3 * a + 2] * F[3 * c + 2];
-    if (ef.x == ef.y) {  // only in diagonal pairs: right-hand side W V^-1 g_p
-#pragma unroll
-      for (int i = 0; i < 3; ++i) {
-        const double2 x = ze[9 + i];
-        v[36 + 2 * i] += x.x;
-        v[36 + 2 * i + 1] += x.y;
+      for (int u = 0; u < kUnroll; ++u) {
+        const bool live = j0 + u < m;
+        const double a = (live && a_lane) ? av[u] : 0.0;
+        const double b = (live && b_lane) ? bv[u] : ((live && one_lane && ke[u] == kf[u]) ? 1.0 : 0.0);
+        dmma_m8n8k4(acc0, acc1, a, b);
       }
     }
   }
-  warp_reduce_scatter48(v, lane);
-  if (lane & 1) return;
-  const int base = ((lane >> 4) & 1) * 24 + ((lane >> 3) & 1) * 12 + ((lane >> 2) & 1) * 6 +
-                   ((lane >> 1) & 1) * 3;
-  if (c1 - c0 == 1) {
+  if (g >= 6) return;
+  // lane (g, q) holds the sums of row g, columns 2q and 2q + 1 (column 6 = right-hand side)
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
-      schur_store(d, bi, bj, base + i, v[i], radius, min_diag, max_diag, include_cam);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 3; ++i) d.sch_partial[(size_t)w * 48 + base + i] = v[i];
+  for (int v = 0; v < 2; ++v) {
+    const int col = 2 * q + v;
+    const int idx = col < 6 ? 6 * g + col : (col == 6 ? 36 + g : -1);
+    if (idx < 0) continue;
+    const double sum = v ? acc1 : acc0;
+    if (c1 - c0 == 1) schur_store(d, bi, bj, idx, sum, radius, min_diag, max_diag, include_cam);
+    else d.sch_partial[(size_t)w * 48 + idx] = sum;
   }
 }
 
