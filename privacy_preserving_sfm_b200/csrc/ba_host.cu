@@ -34,6 +34,11 @@ struct BaState {
   int64_t launches = 0;
   double lin_ms = 0, lin_launches = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // Jacobian-build timing without a host sync per launch: a ring of event pairs, read back when
+  // the solve is over
+  static constexpr int kLinEvents = 64;
+  cudaEvent_t lin_ev[2 * kLinEvents] = {nullptr};
+  int lin_pending = 0;
   cudaEvent_t evp[4] = {nullptr, nullptr, nullptr, nullptr};  // phase marks of one LM iteration
   // multi-GPU
   int rank = 0, world = 1;
@@ -82,6 +87,8 @@ void BaFree(BaState* st) {
   for (void* p : st->allocs) cudaFreeAsync(p, st->ctx->stream);
   cudaStreamSynchronize(st->ctx->stream);
   st->h_scalars.release();
+  for (auto& e : st->lin_ev)
+    if (e) cudaEventDestroy(e);
   if (st->ev0) cudaEventDestroy(st->ev0);
   if (st->ev1) cudaEventDestroy(st->ev1);
   for (auto& e : st->evp)
@@ -301,17 +308,30 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   const BaLoss loss{opt.loss_type, opt.loss_scale};
   Scalars sc;
 
-  auto linearize = [&](const double* q, const double* t, const double* X, bool jac) -> int {
-    if (jac) PPSFM_CUDA(ctx, cudaEventRecord(st->ev0, s));
-    st->launches += launch_linearize(d, q, t, X, jac, loss, s);
-    if (jac) {
-      PPSFM_CUDA(ctx, cudaEventRecord(st->ev1, s));
-      PPSFM_CUDA(ctx, cudaEventSynchronize(st->ev1));
+  auto drain_lin_events = [&]() {  // (the stream must have passed the recorded events)
+    for (int i = 0; i < st->lin_pending; ++i) {
       float ms = 0;
-      cudaEventElapsedTime(&ms, st->ev0, st->ev1);
-      st->lin_ms += ms;
-      st->lin_launches += 1;
+      if (cudaEventElapsedTime(&ms, st->lin_ev[2 * i], st->lin_ev[2 * i + 1]) == cudaSuccess) {
+        st->lin_ms += ms;
+        st->lin_launches += 1;
+      }
     }
+    st->lin_pending = 0;
+  };
+  auto linearize = [&](const double* q, const double* t, const double* X, bool jac) -> int {
+    int slot = -1;
+    if (jac) {
+      if (st->lin_pending == BaState::kLinEvents) {
+        PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+        drain_lin_events();
+      }
+      slot = st->lin_pending++;
+      for (int k = 0; k < 2; ++k)
+        if (!st->lin_ev[2 * slot + k]) PPSFM_CUDA(ctx, cudaEventCreate(&st->lin_ev[2 * slot + k]));
+      PPSFM_CUDA(ctx, cudaEventRecord(st->lin_ev[2 * slot], s));
+    }
+    st->launches += launch_linearize(d, q, t, X, jac, loss, s);
+    if (jac) PPSFM_CUDA(ctx, cudaEventRecord(st->lin_ev[2 * slot + 1], s));
     return PPSFM_OK;
   };
   auto normal_equations = [&]() -> int {
@@ -493,6 +513,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   }
   PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
   PPSFM_CUDA(ctx, cudaGetLastError());
+  drain_lin_events();
   sum->final_cost = cost;
   sum->final_gradient_max_norm = gmax;
   sum->trace_len = tl;

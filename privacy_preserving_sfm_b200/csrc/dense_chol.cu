@@ -757,10 +757,10 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
 // ------------------------------------------------------------------------------------------
 // Backward substitution L^T x = y as a dataflow kernel: one CTA per 64-block (descending by
 // ticket).  CTA j streams the tiles L[b][j], b > j, through a cp.async double buffer, applies
-// y_j -= L[b][j]^T x_b as soon as x_b is published, then solves L_jj^T x_j = y_j with the blocked
-// factor Lpack_j (four 16-wide steps: off-diagonal blocks of L, inverses on the diagonal).
+// y_j -= L[b][j]^T x_b as soon as x_b is published, then x_j = L_jj^-T y_j with the dense inverse
+// it assembled from the blocked factor Lpack_j while it was waiting.
 // ------------------------------------------------------------------------------------------
-constexpr int kBackSmem = 3 * NB * NB * (int)sizeof(double);
+constexpr int kBackSmem = 4 * NB * NB * (int)sizeof(double);
 
 __global__ void __launch_bounds__(256)
 chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __restrict__ work_base,
@@ -779,7 +779,8 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   const int k0 = j * NB;
   const int kb = min(NB, n - k0);
   double* Lp = smem;                   // [64][64] Lpack_j
-  double* stage0 = smem + NB * NB;     // two tile stages
+  double* Li = smem + NB * NB;         // [64][64] dense L_jj^-1, built while waiting for x
+  double* stage0 = smem + 2 * NB * NB; // two tile stages
   auto issue_tile = [&](int b, int st) {
     double* dst = stage0 + (size_t)st * NB * NB;
     const double* src = A + (size_t)(b * NB) * ld + k0;
@@ -797,6 +798,54 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   if (tid < NB) yj[tid] = (tid < kb) ? ld_cg(A + (size_t)n * ld + k0 + tid) : 0.0;
   int issued_b = nblk - 1;  // next tile to issue
   for (int cnt = 0; cnt < 2 && issued_b > j; ++cnt, --issued_b) issue_tile(issued_b, (nblk - 1 - issued_b) & 1);
+  // Dense inverse of the diagonal block from the blocked factor (diagonal 16x16 blocks of Lpack
+  // are the inverses I_b, off-diagonal blocks are L), by block forward substitution
+  //   Linv[bi][bj] = -I_bi * sum_{bk = bj}^{bi-1} L[bi][bk] Linv[bk][bj].
+  // Every CTA but the first one of the chain has to wait for x anyway, so this is free.
+  if (issued_b < nblk - 2) cp_async_wait<2>();       // Lpack is the oldest group
+  else if (issued_b < nblk - 1) cp_async_wait<1>();
+  else cp_async_wait<0>();
+  __syncthreads();
+  for (int idx = tid; idx < NB * NB; idx += 256) {
+    const int r = idx >> 6, cc = idx & 63;
+    Li[idx] = ((r >> 4) == (cc >> 4)) ? Lp[idx] : 0.0;
+  }
+  __syncthreads();
+#pragma unroll 1
+  for (int dist = 1; dist < 4; ++dist) {
+    const int nb = 4 - dist;  // blocks (bi = bj + dist, bj)
+    double tmp[3];
+    int cnt = 0;
+    for (int idx = tid; idx < nb * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, cc = idx & 15;
+      double acc = 0.0;
+      for (int p2 = 16 * bj; p2 < 16 * bi; ++p2) acc += Lp[(16 * bi + r) * NB + p2] * Li[p2 * NB + 16 * bj + cc];
+      tmp[cnt] = acc;
+    }
+    // tmp -> scratch above the diagonal of Li (unused otherwise): Li[bj-rows][bi-cols]
+    cnt = 0;
+    for (int idx = tid; idx < nb * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, cc = idx & 15;
+      Li[(16 * bj + r) * NB + 16 * bi + cc] = tmp[cnt];
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int idx = tid; idx < nb * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, cc = idx & 15;
+      double acc = 0.0;
+#pragma unroll
+      for (int p2 = 0; p2 < 16; ++p2)
+        acc += Lp[(16 * bi + r) * NB + 16 * bi + p2] * Li[(16 * bj + p2) * NB + 16 * bi + cc];
+      tmp[cnt] = -acc;
+    }
+    __syncthreads();
+    cnt = 0;
+    for (int idx = tid; idx < nb * 256; idx += 256, ++cnt) {
+      const int bj = idx >> 8, bi = bj + dist, r = (idx >> 4) & 15, cc = idx & 15;
+      Li[(16 * bi + r) * NB + 16 * bj + cc] = tmp[cnt];
+    }
+    __syncthreads();
+  }
   for (int b = nblk - 1; b > j; --b) {
     const int st = (nblk - 1 - b) & 1;
     if (tid == 0) wait_flag(xflags + b);
@@ -822,25 +871,16 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   }
   cp_async_wait<0>();
   __syncthreads();
-  // L_jj^T x = y by 16-blocks, last block first (threads 0..63, thread c owns entry c):
-  //   x_b = inv(L_bb)^T (y_b - sum_{b' > b} L_b'b^T x_b')
-  if (tid < NB) {
-    double v = yj[tid];
-    for (int b = 3; b >= 0; --b) {
-      if ((tid >> 4) == b) yj[tid] = v;
-      asm volatile("bar.sync 1, 64;");
-      double xv = 0.0;
-      if ((tid >> 4) == b)
-        for (int r = tid; r < 16 * b + 16; ++r) xv += Lp[r * NB + tid] * yj[r];  // inverse block, transposed
-      asm volatile("bar.sync 1, 64;");
-      if ((tid >> 4) == b) yj[tid] = xv;
-      asm volatile("bar.sync 1, 64;");
-      if ((tid >> 4) < b)
-        for (int r = 16 * b; r < 16 * b + 16; ++r) v -= Lp[r * NB + tid] * yj[r];
-      if ((tid >> 4) == b) v = xv;
-    }
-    if (tid < kb) x[k0 + tid] = v;
+  {
+    double s = 0.0;
+#pragma unroll 4
+    for (int r = part; r < NB; r += 4)
+      if (r >= c) s += Li[r * NB + c] * yj[r];  // (L^-1)^T y: lower triangle only (the upper
+                                                 // off-diagonal blocks hold scratch)
+    red[part][c] = s;
   }
+  __syncthreads();
+  if (tid < kb) x[k0 + tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
   __syncthreads();
   if (tid == 0) {
     __threadfence();
