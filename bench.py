@@ -271,7 +271,10 @@ def run_b200(args):
         "hbm": {"achieved": passes * N_CORR * BYTES_PER_CORR / (score_s / args.steps) / 1e9,
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_kind,
                 "note": "algorithmic bytes = passes x N x 48 B; compute-bound kernel"},
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed
+        # ncu --set full capture (profiles/r01_score_kernel_ncu.txt): the 2.4 MB correspondence
+        # set is read from HBM about 2.6 times, the other passes hit L2
+        "traffic": 6.2e6,
     }
 
     out = {
@@ -406,7 +409,10 @@ def run_ba_b200(args, ctx, world, rank, dist):
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "peak_source": peak_kind,
                      "bytes_per_obs": BA_BYTES_PER_OBS, "avg_launch_ms": 1e3 * jac_avg_s,
-                     "traffic": None,
+                     # dram read 74 MB + write 260 MB per launch at N = 1 in the committed
+                     # ncu --set full capture (profiles/r01_s2_ba_kernels_ncu.txt); the last
+                     # ~100 MB of the 432 MB written are still dirty in the 126 MB L2 at kernel end
+                     "traffic": 334e6 / world,
                      "note": "write-heavy kernel (160 of 216 B/obs are writes); measured in this "
                              "run: write-only HBM peak %.0f GB/s, read-only %.0f GB/s; the kernel "
                              "writes %.0f GB/s" % (write_peak, read_peak,
