@@ -104,6 +104,11 @@ class ClockSampler:
 
 
 def dist_setup(n_gpus):
+    # keep stdout to the one JSON line: NCCL prints its version banner there at NCCL_DEBUG=VERSION
+    # and WARN, so the variable is removed unless PPSFM_NCCL_DEBUG asks for a level
+    os.environ.pop("NCCL_DEBUG", None)
+    if os.environ.get("PPSFM_NCCL_DEBUG"):
+        os.environ["NCCL_DEBUG"] = os.environ["PPSFM_NCCL_DEBUG"]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))

@@ -242,6 +242,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     std::fprintf(stderr, "[ba] + uploads %.2f ms\n", 1e3 * Secs(t_create));
   }
   BA_TRY(DevAlloc(st, &d.S, (size_t)d.ld * d.ld));
+  if (world > 1) BA_TRY(DevAlloc(st, &d.Spacked, packed_lower_doubles(d.n) + 1));
   // zeroed once: the assembly overwrites every lower block and the rhs row each iteration, the
   // factorisation keeps the padding rows zero
   BA_TRY(cudaMemsetAsync(d.S, 0, sizeof(double) * (size_t)d.ld * d.ld, s));
@@ -418,8 +419,12 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
                                                 opt.max_lm_diagonal, st->rank == 0, s);
     if (st->world > 1) {
       // rank 0 contributed blockdiag(U + D) and -g_c; every rank its points' Schur products
-      rc = AllReduceSum(st, d.S, (size_t)d.ld * (d.n + 1));
+      // (only the lower triangle and the rhs row are referenced: pack, reduce half the bytes)
+      launch_pack_lower(d.S, d.n, d.ld, d.Spacked, s);
+      rc = AllReduceSum(st, d.Spacked, packed_lower_doubles(d.n));
       if (rc != PPSFM_OK) return rc;
+      launch_unpack_lower(d.S, d.n, d.ld, d.Spacked, s);
+      st->launches += 2;
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[1], s));
     int chol_failed = 0;

@@ -330,7 +330,6 @@ constexpr int kCamSplit = 4;
 __global__ void __launch_bounds__(128) ba_camera_normal_kernel(BaDev d) {
   __shared__ double red[32];
   const int b = blockIdx.x / kCamSplit, part = blockIdx.x % kCamSplit;
-  const int64_t K = d.K;
   double u[21], g[6];
 #pragma unroll
   for (int i = 0; i < 21; ++i) u[i] = 0.0;
@@ -552,6 +551,24 @@ __global__ void ba_axpby_kernel(double* __restrict__ out, const double* __restri
   if (i < n) out[i] = a[i] + beta * b[i];
 }
 
+// Lower triangle (rows 0..n-1, columns 0..r) plus the right-hand-side row n of the bordered
+// reduced matrix <-> packed buffer: the multi-GPU all-reduce then moves half the bytes.
+// Row r starts at r (r + 1) / 2; the rhs row (n entries) follows the triangle.
+__global__ void __launch_bounds__(kThreads)
+ba_pack_lower_kernel(const double* __restrict__ S, int n, int ld, double* __restrict__ packed) {
+  const int r = blockIdx.x;  // 0..n (row n = rhs)
+  const int len = r < n ? r + 1 : n;
+  const size_t off = r < n ? (size_t)r * (r + 1) / 2 : (size_t)n * (n + 1) / 2;
+  for (int c = threadIdx.x; c < len; c += kThreads) packed[off + c] = S[(size_t)r * ld + c];
+}
+__global__ void __launch_bounds__(kThreads)
+ba_unpack_lower_kernel(double* __restrict__ S, int n, int ld, const double* __restrict__ packed) {
+  const int r = blockIdx.x;
+  const int len = r < n ? r + 1 : n;
+  const size_t off = r < n ? (size_t)r * (r + 1) / 2 : (size_t)n * (n + 1) / 2;
+  for (int c = threadIdx.x; c < len; c += kThreads) S[(size_t)r * ld + c] = packed[off + c];
+}
+
 __device__ __forceinline__ void atomic_max_nonneg(double* addr, double v) {
   atomicMax(reinterpret_cast<unsigned long long*>(addr),
             (unsigned long long)__double_as_longlong(v));
@@ -665,6 +682,14 @@ int launch_jacobi_scales(const BaDev& d, cudaStream_t s) {
   if (total == 0) return 0;
   ba_jacobi_scales_kernel<<<(total + 255) / 256, 256, 0, s>>>(d);
   return 1;
+}
+
+size_t packed_lower_doubles(int n) { return (size_t)n * (n + 1) / 2 + (size_t)n; }
+void launch_pack_lower(const double* S, int n, int ld, double* packed, cudaStream_t s) {
+  if (n > 0) ba_pack_lower_kernel<<<n + 1, kThreads, 0, s>>>(S, n, ld, packed);
+}
+void launch_unpack_lower(double* S, int n, int ld, const double* packed, cudaStream_t s) {
+  if (n > 0) ba_unpack_lower_kernel<<<n + 1, kThreads, 0, s>>>(S, n, ld, packed);
 }
 
 void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,

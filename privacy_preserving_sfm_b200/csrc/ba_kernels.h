@@ -61,6 +61,7 @@ struct BaDev {
   int* sch_multi = nullptr;         // [nmulti] pairs that span several chunks
   double* sch_partial = nullptr;    // [nchunks][48] chunk sums of those pairs
   double* S = nullptr;    // [ld][ld] bordered reduced camera matrix (row n = rhs)
+  double* Spacked = nullptr;  // multi-GPU: packed lower triangle + rhs for the all-reduce
   double* dc = nullptr;   // [n]
   double* dp = nullptr;   // [3][P]
   double* u = nullptr;    // [2][K] J_c dc per observation (back-substitution scratch)
@@ -122,6 +123,10 @@ int launch_build_reduced_system(const BaDev& d, double radius, double min_diag, 
                                 bool include_camera_terms, cudaStream_t s);
 // dp from dc, model cost change, candidate state, step / x norms (scalars).
 int launch_backsubstitute_and_update(const BaDev& d, bool count_camera_norms, cudaStream_t s);
+// lower triangle + rhs row of the bordered reduced matrix <-> packed buffer (multi-GPU all-reduce)
+size_t packed_lower_doubles(int n);
+void launch_pack_lower(const double* S, int n, int ld, double* packed, cudaStream_t s);
+void launch_unpack_lower(double* S, int n, int ld, const double* packed, cudaStream_t s);
 // out = a + beta * b
 void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,
                   cudaStream_t s);

@@ -49,11 +49,6 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
                : "+d"(c0), "+d"(c1)
                : "d"(a), "d"(b));
 }
-__device__ __forceinline__ int ld_acquire(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 // Polling uses RELAXED loads: an acquire load is followed by an L1 invalidation (CCTL.IVALL),
 // and CTAs that spin on flags would invalidate the L1 / stall the LSU of the SM they share with
 // the CTA on the critical path.  One acquire fence after the flag has been seen orders the data.
@@ -94,17 +89,12 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+// (optional per-tile event trace: PPSFM_CHOL_TRACE=<file>, 16 timestamp slots per tile)
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Optional per-tile event trace (PPSFM_CHOL_TRACE=<file>): 16 timestamp slots per tile.
-#define CHOL_TRACE(slot)                                                          \
-  do {                                                                            \
-    if (trace != nullptr && threadIdx.x == 0) trace[16 * (size_t)(i * T + j) + (slot)] = global_ns(); \
-  } while (0)
-
 __device__ __forceinline__ unsigned smid() {
   unsigned v;
   asm volatile("mov.u32 %0, %%smid;" : "=r"(v));
