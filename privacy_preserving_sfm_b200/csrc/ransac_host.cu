@@ -155,7 +155,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, ctx->d_num_models.reserve(sizeof(int) * (size_t)H));
     PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);
+    ChooseSegments(ctx, (int)n, (kcap + 511) / 512, &num_segs, &seg_len);  // 512 models per CTA
     PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
     PPSFM_CUDA(ctx, ctx->d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
     PPSFM_CUDA(ctx, ctx->h_num_models.reserve(sizeof(int) * ((size_t)H + 1)));
@@ -169,7 +169,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
                      ctx->d_models.as<double>(), ctx->d_num_models.as<int>(), st);
     launch_model_offsets(ctx->d_num_models.as<int>(), H, ctx->d_msrc.as<int>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    launch_score(corr->corr6, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
+    launch_score(corr->corr6, corr->bounds, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
                  num_segs, seg_len, max_residual, kcap, ctx->d_part_cnt.as<unsigned>(),
                  ctx->d_cnt.as<unsigned>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -393,11 +393,14 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
     if (use_ctx_buffers) {
       e = ctx->d_corr6.reserve(sizeof(double) * 6 * n);
       if (e == cudaSuccess) e = ctx->d_aligned.reserve(n);
+      if (e == cudaSuccess) e = ctx->d_bounds.reserve(4 * sizeof(double));
       c->corr6 = ctx->d_corr6.as<double>();
       c->aligned = ctx->d_aligned.as<uint8_t>();
+      c->bounds = ctx->d_bounds.as<double>();
     } else {
       e = cudaMalloc(&c->corr6, sizeof(double) * 6 * n);
       if (e == cudaSuccess) e = cudaMalloc(&c->aligned, n);
+      if (e == cudaSuccess) e = cudaMalloc(&c->bounds, 4 * sizeof(double));
     }
     if (e != cudaSuccess) {
       if (c->owns && c->corr6) cudaFree(c->corr6);
@@ -414,7 +417,7 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
     } else {
       PPSFM_CUDA(ctx, cudaMemsetAsync(c->aligned, 0, n, st));
     }
-    launch_pack_corr(tl, tp, n, c->corr6, st);
+    launch_pack_corr(tl, tp, n, c->corr6, c->bounds, st);
     // no synchronisation here: later work is queued on the same stream; the host buffers must
     // stay valid until the call that consumes the set returns (all entry points are blocking)
   }
@@ -427,6 +430,7 @@ void FreeCorr(ppsfm_corr* c) {
   if (c->owns) {
     if (c->corr6) cudaFree(c->corr6);
     if (c->aligned) cudaFree(c->aligned);
+    if (c->bounds) cudaFree(c->bounds);
   }
   delete c;
 }

@@ -24,20 +24,43 @@ namespace ppsfm {
 // ------------------------------------------------------------------------------------------
 __global__ void pack_corr_kernel(const double* __restrict__ lines,
                                  const double* __restrict__ points, size_t n,
-                                 double* __restrict__ corr6) {
+                                 double* __restrict__ corr6, double* __restrict__ bounds) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
-  if (i >= n * 3) return;
-  const size_t r = i / 3, c = i % 3;
-  corr6[r * 6 + c] = lines[i];
-  corr6[r * 6 + 3 + c] = points[i];
+  unsigned long long bx = 0, bl = 0, b2 = 0;  // bit patterns of |X|, of |l_0| / |l_1|, of |l_2|
+  if (i < n * 3) {
+    const size_t r = i / 3, c = i % 3;
+    const double l = lines[i], x = points[i];
+    corr6[r * 6 + c] = l;
+    corr6[r * 6 + 3 + c] = x;
+    bx = (unsigned long long)__double_as_longlong(fabs(x));
+    if (c < 2) bl = (unsigned long long)__double_as_longlong(fabs(l));
+    else b2 = (unsigned long long)__double_as_longlong(fabs(l));
+  }
+  // bounds[0] = max |X_k|, [1] = max(|l_0|, |l_1|), [2] = max |l_2| over the set (non-negative doubles order
+  // like their bit patterns; a NaN input yields a NaN bound, which disables the fast path)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long ox = __shfl_xor_sync(0xffffffffu, bx, o);
+    const unsigned long long ol = __shfl_xor_sync(0xffffffffu, bl, o);
+    const unsigned long long o2 = __shfl_xor_sync(0xffffffffu, b2, o);
+    bx = ox > bx ? ox : bx;
+    bl = ol > bl ? ol : bl;
+    b2 = o2 > b2 ? o2 : b2;
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(reinterpret_cast<unsigned long long*>(bounds), bx);
+    atomicMax(reinterpret_cast<unsigned long long*>(bounds) + 1, bl);
+    atomicMax(reinterpret_cast<unsigned long long*>(bounds) + 2, b2);
+  }
 }
 
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
-                      cudaStream_t s) {
+                      double* bounds, cudaStream_t s) {
   const int threads = 256;
   const size_t total = n * 3;
+  cudaMemsetAsync(bounds, 0, 3 * sizeof(double), s);
   pack_corr_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(lines, points,
-                                                                                    n, corr6);
+                                                                                    n, corr6, bounds);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -202,35 +225,121 @@ __device__ __forceinline__ void score_one(const double* __restrict__ c, const do
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Filtered evaluation.  The reference arithmetic above costs ~33 FP64-pipe instructions per
+// (model, correspondence) pair, a third of them in the IEEE division.  The inlier COUNT only needs
+// the sign of |res| - r_max, and for pz > 0
+//     |res| <= r_max   <=>   |px l_0 + py l_1 + l_2 pz| <= r_max pz,
+// so almost every pair can be decided without any division: projections with FMA chains,
+//     d = |fma(l_2, pz, fma(py, l_1, px l_0))| - r_max pz,
+// and a rigorous bound on the difference between d / pz and the reference's |res| - r_max:
+//     band = k0 + k1 pz,   k0 = 2^-40 (B_x + B_y) Lmax,   k1 = 2^-40 (L2max + r_max + B_z (...)),
+// built from per-model sums B_* = sum_k |P_*k| max|X| + |P_*3| and the maxima of the correspondence
+// set (2^-40 leaves a factor > 2^9 over all rounding and cancellation errors of both evaluations).
+// A pair is decided here only if |pz| >= 2^-30 B_z (which settles the cheirality test
+// pz > DBL_EPSILON either way) and, in front of the camera, |d| > band; otherwise — about one pair in 10^8 — the reference arithmetic
+// above decides.  Counts are therefore still bit-identical to the reference; the fast path costs
+// 15 FP64-pipe instructions and no MUFU.
+// ------------------------------------------------------------------------------------------
+struct FastConsts {
+  int zmin_hi;          // high word of the threshold on |pz| (INT_MAX: never use the fast path)
+  double k0, k1;        // band = k0 + k1 pz
+  double rmax;
+};
+
+struct Corr {  // one correspondence, read once from shared memory for all models of the thread
+  double l_0, l_1, l_2, X_0, X_1, X_2;
+};
+__device__ __forceinline__ Corr load_corr(const double* __restrict__ c) {
+  const double2* c2 = reinterpret_cast<const double2*>(c);  // 48-byte records, 16-B aligned
+  const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
+  return Corr{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
+}
+
+// returns false if the pair could not be decided (the caller then runs the reference arithmetic)
+__device__ __forceinline__ bool score_fast(const Corr& c, const double (&P)[12],
+                                           const FastConsts& fc, unsigned& cnt) {
+  const double pz = fma(P[8], c.X_2, fma(P[5], c.X_1, fma(P[2], c.X_0, P[11])));
+  const double px = fma(P[6], c.X_2, fma(P[3], c.X_1, fma(P[0], c.X_0, P[9])));
+  const double py = fma(P[7], c.X_2, fma(P[4], c.X_1, fma(P[1], c.X_0, P[10])));
+  const double num = fma(c.l_2, pz, fma(py, c.l_1, px * c.l_0));
+  const double d = fabs(num) - fc.rmax * pz;   // pz < 0: d > 0, "not an inlier", as it must be
+  const double band = fma(fc.k1, fabs(pz), fc.k0);
+  // The three tests run on the HIGH words with 32-bit integer compares (strict '>' on the high
+  // words implies '>' on the doubles; the bounds have a factor 2^9 to spare):
+  //   |pz| > zmin (cheirality settled either way),  |d| > band,  |d| finite
+  const int pz_hi = __double2hiint(pz) & 0x7fffffff;
+  const int d_hi = __double2hiint(d);
+  const int ad_hi = d_hi & 0x7fffffff;
+  const bool decided = pz_hi > fc.zmin_hi && ad_hi > __double2hiint(band) && ad_hi < 0x7ff00000;
+  cnt += decided ? ((unsigned)d_hi >> 31) : 0u;  // d < 0: inlier
+  return decided;
+}
+
+// per-model constants of the filter
+__device__ __forceinline__ FastConsts fast_consts(const double (&P)[12], const double* bounds,
+                                                  double r_max, bool live) {
+  FastConsts fc;
+  const double xmax = bounds[0], lmax = bounds[1], l2max = bounds[2];
+  const double bx = (fabs(P[0]) + fabs(P[3]) + fabs(P[6])) * xmax + fabs(P[9]);
+  const double by = (fabs(P[1]) + fabs(P[4]) + fabs(P[7])) * xmax + fabs(P[10]);
+  const double bz = (fabs(P[2]) + fabs(P[5]) + fabs(P[8])) * xmax + fabs(P[11]);
+  // |d_exact - d| <= 8u [(B_x + B_y) Lmax + (L2max + r_max) B_z] (u = 2^-53) for the fused
+  // evaluation, and the reference's |res| - r_max times pz differs from d_exact by at most the
+  // same plus 8u (|num| + r_max pz) <= 16u (...): everything is below
+  //   2^-40 [(B_x + B_y) Lmax + (L2max + r_max) B_z]  +  2^-40 (L2max + r_max) pz
+  const double zmin = bz * 0x1p-30;
+  fc.k0 = ((bx + by) * lmax + (l2max + r_max) * bz) * 0x1p-40;
+  fc.k1 = (l2max + r_max) * 0x1p-40;
+  fc.rmax = r_max;
+  // usable only for normal, finite constants and a non-negative r_max (a negative one means
+  // "nothing is an inlier"); otherwise every pair takes the reference path
+  const bool usable = zmin >= 0x1p-900 && zmin < 0x1p900 && fc.k0 < 0x1p900 && fc.k1 < 0x1p900 &&
+                      r_max >= 0.0 && live;
+  fc.zmin_hi = usable ? __double2hiint(zmin) : 0x7fffffff;
+  return fc;
+}
+
+// Thread <-> kModelsPerThread models (12 doubles each in registers); every correspondence read
+// from shared memory is used for all of them (a broadcast LDS.128 costs four 128-byte wavefronts
+// whatever the number of distinct addresses: 12 wavefronts per correspondence and warp).
+constexpr int kModelsPerThread = 1;  // (2 halves the LDS wavefronts but costs occupancy: slower)
+constexpr int kModelsPerCta = kScoreThreads * kModelsPerThread;
+
 __global__ void __launch_bounds__(kScoreThreads)
 score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__ models,
              const int* __restrict__ offsets, int num_trials, int seg_len, double r_max,
-             int kcap, unsigned* __restrict__ part_cnt) {
+             int kcap, unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
   __shared__ __align__(128) double tile[kStages][kTile * 6];
   __shared__ __align__(8) uint64_t full_bar[kStages];
 
   const int K = offsets[num_trials];
-  const int mbase = blockIdx.x * kScoreThreads;
+  const int mbase = blockIdx.x * kModelsPerCta;
   if (mbase >= K) return;
   const int seg = blockIdx.y;
   const int i0 = seg * seg_len;
   const int i1 = min(n, i0 + seg_len);
-  const int k = mbase + threadIdx.x;
 
   // Locate (trial, m) of compact model k: largest t with offsets[t] <= k.
-  double P[12];
-  if (k < K) {
-    int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (offsets[mid] <= k) lo = mid; else hi = mid;
+  double P[kModelsPerThread][12];
+  int kk[kModelsPerThread];
+#pragma unroll
+  for (int v = 0; v < kModelsPerThread; ++v) {
+    const int k = mbase + v * kScoreThreads + threadIdx.x;
+    kk[v] = k;
+    if (k < K) {
+      int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= k) lo = mid; else hi = mid;
+      }
+      const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) P[v][j] = src[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) P[v][j] = 0.0;  // px_2 = 0 -> never counted
     }
-    const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) P[j] = src[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 12; ++j) P[j] = 0.0;  // px_2 = 0 -> never counted
   }
 
   const int len = max(0, i1 - i0);
@@ -249,7 +358,13 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
     }
   }
 
-  unsigned cnt = 0;
+  unsigned cnt[kModelsPerThread];
+  FastConsts fc[kModelsPerThread];
+#pragma unroll
+  for (int v = 0; v < kModelsPerThread; ++v) {
+    cnt[v] = 0;
+    fc[v] = fast_consts(P[v], bounds, r_max, kk[v] < K);
+  }
   const long long eps_bits = __double_as_longlong(DBL_EPSILON);
   const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
   for (int t = 0; t < num_tiles; ++t) {
@@ -259,13 +374,36 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
     const int cnt_t = min(kTile, len - t * kTile);
     const double* tp = &tile[s][0];
     int j = 0;
-    for (; j + 4 <= cnt_t; j += 4) {
-      score_one(tp + (j + 0) * 6, P, eps_bits, rmax_bits, cnt);
-      score_one(tp + (j + 1) * 6, P, eps_bits, rmax_bits, cnt);
-      score_one(tp + (j + 2) * 6, P, eps_bits, rmax_bits, cnt);
-      score_one(tp + (j + 3) * 6, P, eps_bits, rmax_bits, cnt);
+#pragma unroll 1
+    constexpr int kGroup = 4 / kModelsPerThread;  // pairs per unrolled group
+    for (; j + kGroup <= cnt_t; j += kGroup) {
+      unsigned pend = 0;  // undecided (pair, model) combinations of this group (about 1 in 10^8)
+#pragma unroll
+      for (int u = 0; u < kGroup; ++u) {
+        const Corr c = load_corr(tp + (j + u) * 6);
+#pragma unroll
+        for (int v = 0; v < kModelsPerThread; ++v)
+          pend |= score_fast(c, P[v], fc[v], cnt[v]) ? 0u : (1u << (u * kModelsPerThread + v));
+      }
+      if (pend != 0) {
+#pragma unroll 1
+        for (int b = 0; b < kGroup * kModelsPerThread; ++b)
+          if ((pend >> b) & 1u) {
+            const double* cp = tp + (j + b / kModelsPerThread) * 6;
+#pragma unroll
+            for (int v = 0; v < kModelsPerThread; ++v)
+              if (b % kModelsPerThread == v) score_one(cp, P[v], eps_bits, rmax_bits, cnt[v]);
+          }
+      }
     }
-    for (; j < cnt_t; ++j) score_one(tp + j * 6, P, eps_bits, rmax_bits, cnt);
+#pragma unroll 1
+    for (; j < cnt_t; ++j) {
+      const Corr c = load_corr(tp + j * 6);
+#pragma unroll
+      for (int v = 0; v < kModelsPerThread; ++v)
+        if (!score_fast(c, P[v], fc[v], cnt[v]))
+          score_one(tp + j * 6, P[v], eps_bits, rmax_bits, cnt[v]);
+    }
     __syncthreads();  // everyone is done reading stage s
     if (threadIdx.x == 0 && t + kStages < num_tiles) {
       const int tn = t + kStages;
@@ -276,7 +414,9 @@ score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__
       bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
     }
   }
-  if (k < K) part_cnt[(size_t)seg * kcap + k] = cnt;
+#pragma unroll
+  for (int v = 0; v < kModelsPerThread; ++v)
+    if (kk[v] < K) part_cnt[(size_t)seg * kcap + kk[v]] = cnt[v];
 }
 
 __global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
@@ -303,14 +443,15 @@ double inlier_abs_threshold(double max_residual) {
   return r;
 }
 
-void launch_score(const double* corr6, int n, const double* models, const int* offsets,
-                  int num_trials, int num_segs, int seg_len, double max_residual, int kcap,
-                  unsigned* part_cnt, unsigned* cnt_out, cudaStream_t s) {
+void launch_score(const double* corr6, const double* bounds, int n, const double* models,
+                  const int* offsets, int num_trials, int num_segs, int seg_len,
+                  double max_residual, int kcap, unsigned* part_cnt, unsigned* cnt_out,
+                  cudaStream_t s) {
   if (num_trials <= 0) return;
   const double r_max = inlier_abs_threshold(max_residual);
-  dim3 grid((kcap + kScoreThreads - 1) / kScoreThreads, num_segs);
+  dim3 grid((kcap + kModelsPerCta - 1) / kModelsPerCta, num_segs);
   score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
-                                              r_max, kcap, part_cnt);
+                                              r_max, kcap, part_cnt, bounds);
   reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
                                                          num_trials, cnt_out);
 }

@@ -7,16 +7,18 @@
 
 namespace ppsfm {
 
+// bounds (device, 3 doubles): max |X_k|, max(|l_0|, |l_1|), max |l_2| over the set (score filter)
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
-                      cudaStream_t s);
+                      double* bounds, cudaStream_t s);
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s);
 void launch_model_offsets(const int* num_models, int num_trials, int* offsets, cudaStream_t s);
 // Inlier counts of every compact model.  part_cnt: num_segs x kcap scratch; cnt_out: kcap
 // (first K valid).
-void launch_score(const double* corr6, int n, const double* models, const int* offsets,
-                  int num_trials, int num_segs, int seg_len, double max_residual, int kcap,
-                  unsigned* part_cnt, unsigned* cnt_out, cudaStream_t s);
+void launch_score(const double* corr6, const double* bounds, int n, const double* models,
+                  const int* offsets, int num_trials, int num_segs, int seg_len,
+                  double max_residual, int kcap, unsigned* part_cnt, unsigned* cnt_out,
+                  cudaStream_t s);
 // Largest double r with fl(r*r) <= max_residual.
 double inlier_abs_threshold(double max_residual);
 // rbuf: num_e x n residuals; mask (optional): num_e x n; ecnt/esum (optional): num_e.
