@@ -155,7 +155,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, ctx->d_num_models.reserve(sizeof(int) * (size_t)H));
     PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, (kcap + 511) / 512, &num_segs, &seg_len);  // 512 models per CTA
+    ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);  // 256 models per CTA
     PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
     PPSFM_CUDA(ctx, ctx->d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
     PPSFM_CUDA(ctx, ctx->h_num_models.reserve(sizeof(int) * ((size_t)H + 1)));
