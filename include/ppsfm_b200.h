@@ -106,6 +106,12 @@ int ppsfm_line_residuals(ppsfm_ctx* ctx, const double* lines, const double* poin
                          double* residuals_out, uint64_t* num_inliers_out,
                          double* residual_sum_out);
 
+/* Test hook: the same inlier counts through the count-only scoring kernel of the RANSAC loop
+ * (division-free filter + reference fallback), for tests that aim at the filter's edge cases. */
+int ppsfm_score_models(ppsfm_ctx* ctx, const double* lines, const double* points, size_t n,
+                       const double* models, size_t num_models, double max_residual,
+                       uint32_t* counts_out);
+
 /* ---- A3 + A4: batched minimal solver -------------------------------------------------------
  * P6LEstimator::Estimate (src/estimators/absolute_pose.cc:79-162) incl. re3q3
  * (lib/re3q3/re3q3/re3q3.h:16-200) for H samples of 6 correspondences, one thread per

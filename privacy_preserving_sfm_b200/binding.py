@@ -217,6 +217,19 @@ class Context:
             cnt.ctypes.data_as(_u64p), sm.ctypes.data_as(_dp)))
         return res, cnt, sm
 
+    def score_models(self, lines, points, models, max_residual):
+        """Inlier counts through the RANSAC scoring kernel (test hook)."""
+        lines, lp = _d(lines)
+        points, pp = _d(points)
+        models, mp = _d(np.asarray(models, dtype=np.float64).reshape(-1, 12))
+        cnt = np.zeros(models.shape[0], dtype=np.uint32)
+        self._L.ppsfm_score_models.argtypes = [C.c_void_p, _dp, _dp, C.c_size_t, _dp, C.c_size_t,
+                                               C.c_double, _u32p]
+        self._check(self._L.ppsfm_score_models(self._h, lp, pp, lines.shape[0], mp,
+                                               models.shape[0], max_residual,
+                                               cnt.ctypes.data_as(_u32p)))
+        return cnt
+
     def p6l_solve_batch(self, lines, aligned, points, sample_idx):
         lines, lp = _d(lines)
         points, pp = _d(points)

@@ -669,6 +669,57 @@ int ppsfm_p6l_solve_batch(ppsfm_ctx* ctx, const double* lines, const uint8_t* al
   return rc;
 }
 
+// Test hook: inlier counts of `num_models` models through the RANSAC scoring kernel (the filtered
+// count-only path with its reference fallback), so that tests can aim at the filter's edge cases
+// directly.  Same result as num_inliers_out of ppsfm_line_residuals, by construction.
+int ppsfm_score_models(ppsfm_ctx* ctx, const double* lines, const double* points, size_t n,
+                       const double* models, size_t num_models, double max_residual,
+                       uint32_t* counts_out) {
+  if (!ctx || !models || !counts_out) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
+  if (n == 0 || num_models == 0) {
+    for (size_t k = 0; k < num_models; ++k) counts_out[k] = 0;
+    return PPSFM_OK;
+  }
+  if (n > 0x7fffffffull || num_models > (1u << 24)) return fail(ctx, PPSFM_ERR_INVALID, "too large");
+  cudaSetDevice(ctx->device);
+  ppsfm_corr* corr = nullptr;
+  int rc = UploadCorr(ctx, lines, nullptr, points, n, true, &corr);
+  if (rc != PPSFM_OK) return rc;
+  cudaStream_t st = ctx->stream;
+  const int H = (int)num_models, kcap = 8 * H;
+  auto body = [&]() -> int {
+    // one model per trial: slot 0 of every 8-model group, offsets = 0, 1, 2, ...
+    std::vector<double> hm((size_t)H * 96, 0.0);
+    std::vector<int> hoff(H + 1);
+    for (int k = 0; k < H; ++k) {
+      std::copy(models + 12 * (size_t)k, models + 12 * (size_t)k + 12, hm.begin() + 96 * (size_t)k);
+      hoff[k] = k;
+    }
+    hoff[H] = H;
+    int num_segs, seg_len;
+    ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);
+    PPSFM_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * hm.size()));
+    PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
+    PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
+    PPSFM_CUDA(ctx, ctx->d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_models.p, hm.data(), sizeof(double) * hm.size(),
+                                    cudaMemcpyHostToDevice, st));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_msrc.p, hoff.data(), sizeof(int) * hoff.size(),
+                                    cudaMemcpyHostToDevice, st));
+    launch_score(corr->corr6, corr->bounds, (int)n, ctx->d_models.as<double>(),
+                 ctx->d_msrc.as<int>(), H, num_segs, seg_len, max_residual, kcap,
+                 ctx->d_part_cnt.as<unsigned>(), ctx->d_cnt.as<unsigned>(), st);
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(counts_out, ctx->d_cnt.p, sizeof(unsigned) * (size_t)H,
+                                    cudaMemcpyDeviceToHost, st));
+    PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+    PPSFM_CUDA(ctx, cudaGetLastError());
+    return PPSFM_OK;
+  };
+  rc = body();
+  FreeCorr(corr);
+  return rc;
+}
+
 int ppsfm_line_residuals(ppsfm_ctx* ctx, const double* lines, const double* points, size_t n,
                          const double* models, size_t num_models, double max_residual,
                          double* residuals_out, uint64_t* num_inliers_out,

@@ -11,6 +11,7 @@
 // Compiled with --fmad=false: every FP64 operation rounds separately, in the order the reference
 // evaluates it (src/estimators/utils.cc:64-88), so residuals, masks and supports are bit-exact.
 #include <cfloat>
+#include <cstring>
 #include <cmath>
 #include <cstdint>
 
@@ -205,6 +206,11 @@ constexpr int kStages = 4;
 //                                  rounded square is <= max_residual (rounding is monotone)
 // A NaN px_2 passes the first test only to produce a NaN residual, which fails the second: the
 // pair is not counted, exactly as with the floating-point comparisons of the reference.
+// With max_residual >= DBL_MAX (RANSACOptions::max_error = inf) the reference also counts the
+// pairs that fail the cheirality test (their residual is DBL_MAX, utils.cc:85-86); r_max is
+// DBL_MAX exactly then (inlier_abs_threshold), which flags the case.
+constexpr unsigned long long kAllInliers = 0x7fefffffffffffffull;  // bits(DBL_MAX)
+
 __device__ __forceinline__ void score_one(const double* __restrict__ c, const double (&P)[12],
                                           const long long eps_bits,
                                           const unsigned long long rmax_bits, unsigned& cnt) {
@@ -214,6 +220,10 @@ __device__ __forceinline__ void score_one(const double* __restrict__ c, const do
   const double l_0 = v0.x, l_1 = v0.y, l_2 = v1.x;
   const double X_0 = v1.y, X_1 = v2.x, X_2 = v2.y;
   const double px_2 = P[2] * X_0 + P[5] * X_1 + P[8] * X_2 + P[11];
+  if (rmax_bits == kAllInliers && !(px_2 > DBL_EPSILON)) {
+    cnt += 1;  // residual DBL_MAX <= max_residual
+    return;
+  }
   if (__double_as_longlong(px_2) > eps_bits) {
     const double px_0 = P[0] * X_0 + P[3] * X_1 + P[6] * X_2 + P[9];
     const double px_1 = P[1] * X_0 + P[4] * X_1 + P[7] * X_2 + P[10];
@@ -295,7 +305,7 @@ __device__ __forceinline__ FastConsts fast_consts(const double (&P)[12], const d
   // usable only for normal, finite constants and a non-negative r_max (a negative one means
   // "nothing is an inlier"); otherwise every pair takes the reference path
   const bool usable = zmin >= 0x1p-900 && zmin < 0x1p900 && fc.k0 < 0x1p900 && fc.k1 < 0x1p900 &&
-                      r_max >= 0.0 && live;
+                      r_max >= 0.0 && r_max < DBL_MAX && live;
   fc.zmin_hi = usable ? __double2hiint(zmin) : 0x7fffffff;
   return fc;
 }
@@ -428,16 +438,25 @@ __global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int n
   cnt_out[k] = c;
 }
 
-// Largest double r with fl(r * r) <= max_residual (host; IEEE multiplication is monotone).
+// Largest double r with fl(r * r) <= max_residual (host).  IEEE multiplication is monotone, so
+// the predicate is monotone in r and a bisection over the bit patterns of the non-negative doubles
+// finds the boundary in 63 steps — also where r * r underflows (a step-by-step search from
+// sqrt(max_residual) would walk through all denormals for max_residual = 0).
 double inlier_abs_threshold(double max_residual) {
   if (!(max_residual >= 0.0)) return -1.0;  // nothing is an inlier (bits compare fails)
-  if (max_residual == INFINITY) return DBL_MAX;
-  double r = sqrt(max_residual);
-  while (r * r > max_residual) r = nextafter(r, 0.0);
-  for (;;) {
-    const double up = nextafter(r, INFINITY);
-    if (up * up <= max_residual) r = up; else break;
+  auto ok = [&](unsigned long long bits) {
+    double r;
+    std::memcpy(&r, &bits, sizeof(r));
+    return r * r <= max_residual;
+  };
+  unsigned long long lo = 0, hi = 0x7fefffffffffffffull;  // +0 .. DBL_MAX; ok(lo) always holds
+  if (ok(hi)) return DBL_MAX;
+  while (hi - lo > 1) {
+    const unsigned long long mid = lo + (hi - lo) / 2;
+    if (ok(mid)) lo = mid; else hi = mid;
   }
+  double r;
+  std::memcpy(&r, &lo, sizeof(r));
   return r;
 }
 

@@ -165,3 +165,42 @@ def test_options_check(ctx):
         pp.RANSAC_P6L(RANSACOptions(max_error=0.0), ctx)
     with pytest.raises(pp.PpsfmError):
         pp.RANSAC_P6L(RANSACOptions(max_error=1.0, min_num_trials=5, max_num_trials=4), ctx)
+
+
+def test_score_filter_edge_cases(ctx, oracle):
+    """The count-only scoring kernel decides almost every pair with a division-free filter and
+    falls back to the reference arithmetic inside an error band.  Aim at the band: residuals that
+    equal the threshold exactly (and its neighbours), points on / next to the camera plane, huge
+    and tiny magnitudes, NaN / inf inputs — counts must stay bit-identical to the reference."""
+    rng = np.random.default_rng(77)
+    n, k = 4096, 300
+    R = np.stack([S.random_rotation(rng) for _ in range(k)])
+    t = rng.uniform(-1, 1, (k, 3))
+    models = np.concatenate([R.transpose(0, 2, 1).reshape(k, 9), t], axis=1)   # column-major 3x4
+    X = rng.uniform(-3, 3, (n, 3))
+    th = rng.uniform(0, 2 * np.pi, n)
+    lines = np.stack([np.cos(th), np.sin(th), rng.uniform(-1, 1, n)], axis=1)
+    # points exactly on / next to the camera plane of model 0 (pz = 0, +-eps, +-tiny)
+    r3, t3 = R[0][2], t[0][2]
+    base = X[:64] - np.outer((X[:64] @ r3 + t3), r3)            # pz ~ 0 up to rounding
+    X[:64] = base
+    X[64:96] = base[:32] + np.outer(2.0 ** -np.arange(20, 52), r3)
+    X[96:128] = base[:32] - np.outer(2.0 ** -np.arange(20, 52), r3)
+    X[128] *= 1e150
+    X[129] *= 1e-150
+    X[130, 0] = np.nan
+    X[131, 1] = np.inf
+    lines[132, 2] = np.nan
+    lines[133] *= 1e100
+    res, cnt_ref, _ = ctx.line_residuals(lines, X, models, 1e-4)
+    # thresholds that hit residuals exactly: r_max^2 = a residual of model 1, and its neighbours
+    finite = np.sort(res[1][np.isfinite(res[1]) & (res[1] < 1.0)])
+    for thr in [1e-4, finite[len(finite) // 2], np.nextafter(finite[len(finite) // 2], 0.0),
+                np.nextafter(finite[len(finite) // 3], 1.0), 0.0, 1e-300, 1e300, np.inf]:
+        _, want, _ = ctx.line_residuals(lines, X, models, thr, want_residuals=False)
+        got = ctx.score_models(lines, X, models, thr)
+        assert np.array_equal(got.astype(np.uint64), want), thr
+        # and against the CPU oracle for a few models
+        for m in (0, 1, 7):
+            r_cpu = oracle.line_residuals(lines, X, models[m])
+            assert int((r_cpu <= thr).sum()) == int(got[m])
