@@ -51,56 +51,87 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled DURING the timed region.
+
+    NVML (nvidia_ml_py) is polled from a thread every 5 ms: the timed region of the RANSAC leg is
+    tens of milliseconds, shorter than nvidia-smi's start-up, so a subprocess sampler misses it.
+    The main thread sits in blocking C-ABI calls (GIL released) while the sampler runs.  If NVML
+    cannot be loaded, one synchronous nvidia-smi query is taken at stop()."""
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40),
+               ("sw_thermal_slowdown", 0x20), ("sw_power_cap", 0x4))
 
     def __init__(self, index):
         self.index = index
-        self.proc = None
-        self.lines = []
+        self.sm, self.mask, self.max_mhz = [], 0, None
+        self.h = self.nv = self.th = None
+        self.run = False
+
+    def _handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        self.nv = pynvml
+        try:   # NVML indices ignore CUDA_VISIBLE_DEVICES: go through the device UUID
+            import torch
+            uuid = "GPU-" + str(torch.cuda.get_device_properties(self.index).uuid)
+            return pynvml.nvmlDeviceGetHandleByUUID(uuid)
+        except Exception:
+            return pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _sample(self):
+        nv = self.nv
+        self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+        try:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+        except Exception:
+            self.mask |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+
+    def _loop(self):
+        while self.run:
+            try:
+                self._sample()
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(self.index)],
-                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            self.h = self._handle()
+            self.max_mhz = float(self.nv.nvmlDeviceGetMaxClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            self.run = True
+            self.th = threading.Thread(target=self._loop, daemon=True)
             self.th.start()
         except Exception:
-            self.proc = None
+            self.h = None
 
-    def _read(self):
-        for ln in self.proc.stdout:
-            self.lines.append(ln.strip())
+    def _smi_once(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        try:
+            out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits",
+                                  "-i", str(self.index)], capture_output=True, text=True,
+                                 timeout=20).stdout.strip().splitlines()[0]
+            f = [x.strip() for x in out.split(",")]
+            self.sm.append(float(f[0]))
+            self.max_mhz = float(f[1])
+            for (name, bit), v in zip(self.REASONS, f[2:6]):
+                if v.lower().startswith("active"):
+                    self.mask |= bit
+            return "nvidia-smi (one sample after the timed region)"
+        except Exception:
+            return "unavailable"
 
     def stop(self):
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
-            if len(f) < 9:
-                continue
-            try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-            except ValueError:
-                continue
-            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown",
-                                "sw_power_cap"], f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None,
-                "sm_max_mhz": float(max(mx)) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        source = "nvml"
+        if self.th is not None:
+            self.run = False
+            self.th.join(timeout=1)
+        if not self.sm:
+            source = self._smi_once()
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None,
+                "sm_max_mhz": self.max_mhz,
+                "reasons": [n for n, bit in self.REASONS if self.mask & bit],
+                "samples": len(self.sm), "source": source}
 
 
 def dist_setup(n_gpus):
@@ -355,6 +386,8 @@ def run_ba_b200(args, ctx, world, rank, dist):
         prob.run()
     times, iters, jac_s, jac_n, launches = [], 0, 0.0, 0, 0
     summ = None
+    sampler = ClockSampler(int(os.environ.get("LOCAL_RANK", 0)))
+    sampler.start()
     for _ in range(args.steps):
         prob.reset()
         ctx.bench_l2_flush()
@@ -367,6 +400,7 @@ def run_ba_b200(args, ctx, world, rank, dist):
         jac_s += summ.jacobian_time_s
         jac_n += summ.jacobian_launches
         launches += summ.kernel_launches
+    ba_clocks = sampler.stop()
     prob.free()
     total = float(sum(times))
     if dist is not None:
@@ -410,7 +444,7 @@ def run_ba_b200(args, ctx, world, rank, dist):
         "e2e": {"value": e2e_it / sum(e2e_t), "unit": "LM iterations/s",
                 "ms_per_solve": 1e3 * float(np.mean(e2e_t)), "h2d_bytes_per_step": int(nbytes_in),
                 "d2h_bytes_per_step": int(nbytes_out)},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "clocks": ba_clocks,
         "roofline": {"kernel": "ba_linearize_kernel<true> (Jacobian build)", "bound": "hbm",
                      "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                      "frac": achieved / hbm_peak, "peak_source": peak_kind,

@@ -66,6 +66,8 @@ struct PinBuf {
 struct ppsfm_corr {
   size_t n = 0;
   double* corr6 = nullptr;    // n x 6 interleaved (l0,l1,l2,X0,X1,X2): 48 B per correspondence
+  float* corr6f = nullptr;    // ceil(n/2) x 12: the same rounded to float, two correspondences
+                              // a, b per record (l0a,l0b,l1a,l1b,l2a,l2b,X0a,X0b,...) — score filter
   uint8_t* aligned = nullptr; // n bytes
   double* bounds = nullptr;   // 3 doubles: max |X_k|, max(|l_0|, |l_1|), max |l_2| (score filter)
   bool owns = true;           // false: storage belongs to the context's scratch buffers
@@ -82,7 +84,7 @@ struct ppsfm_ctx {
   // RANSAC scratch
   ppsfm::DevBuf d_samples, d_models, d_num_models, d_cmodels, d_msrc, d_K, d_part_cnt,
       d_part_sum, d_cnt, d_sum, d_eidx, d_emodels, d_rbuf, d_esum, d_ecnt, d_mask, d_tmp_corr,
-      d_tmp_aligned, d_corr6, d_aligned, d_bounds;
+      d_tmp_aligned, d_corr6, d_aligned, d_bounds, d_corr6f;
   ppsfm::PinBuf h_samples, h_num_models, h_cnt, h_sum, h_eidx, h_emodels, h_esum, h_ecnt, h_mask,
       h_K, h_stage;
   ppsfm_ransac_timing timing{};

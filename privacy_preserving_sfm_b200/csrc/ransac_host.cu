@@ -79,6 +79,7 @@ static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap_blocks, int* nu
   int segs = (target_blocks + kcap_blocks - 1) / std::max(1, kcap_blocks);
   // model blocks beyond K exit immediately; on average half the capacity is live.
   segs = std::max(1, std::min(segs * 2, 64));
+  segs = std::max(1, std::min(ppsfm::tune_int("PPSFM_SCORE_SEGS", segs), 256));
   int len = (n + segs - 1) / segs;
   len = std::max(256, ((len + 127) / 128) * 128);
   segs = (n + len - 1) / len;
@@ -169,7 +170,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
                      ctx->d_models.as<double>(), ctx->d_num_models.as<int>(), st);
     launch_model_offsets(ctx->d_num_models.as<int>(), H, ctx->d_msrc.as<int>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    launch_score(corr->corr6, corr->bounds, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
+    launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
                  num_segs, seg_len, max_residual, kcap, ctx->d_part_cnt.as<unsigned>(),
                  ctx->d_cnt.as<unsigned>(), st);
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
@@ -394,6 +395,8 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
       e = ctx->d_corr6.reserve(sizeof(double) * 6 * n);
       if (e == cudaSuccess) e = ctx->d_aligned.reserve(n);
       if (e == cudaSuccess) e = ctx->d_bounds.reserve(4 * sizeof(double));
+      if (e == cudaSuccess) e = ctx->d_corr6f.reserve(sizeof(float) * 12 * ((n + 1) / 2));
+      c->corr6f = ctx->d_corr6f.as<float>();
       c->corr6 = ctx->d_corr6.as<double>();
       c->aligned = ctx->d_aligned.as<uint8_t>();
       c->bounds = ctx->d_bounds.as<double>();
@@ -401,9 +404,14 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
       e = cudaMalloc(&c->corr6, sizeof(double) * 6 * n);
       if (e == cudaSuccess) e = cudaMalloc(&c->aligned, n);
       if (e == cudaSuccess) e = cudaMalloc(&c->bounds, 4 * sizeof(double));
+      if (e == cudaSuccess) e = cudaMalloc(&c->corr6f, sizeof(float) * 12 * ((n + 1) / 2));
     }
     if (e != cudaSuccess) {
-      if (c->owns && c->corr6) cudaFree(c->corr6);
+      if (c->owns) {
+        if (c->corr6) cudaFree(c->corr6);
+        if (c->aligned) cudaFree(c->aligned);
+        if (c->bounds) cudaFree(c->bounds);
+      }
       delete c;
       return fail(ctx, PPSFM_ERR_CUDA, "device allocation: %s", cudaGetErrorString(e));
     }
@@ -417,7 +425,7 @@ int UploadCorr(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned, cons
     } else {
       PPSFM_CUDA(ctx, cudaMemsetAsync(c->aligned, 0, n, st));
     }
-    launch_pack_corr(tl, tp, n, c->corr6, c->bounds, st);
+    launch_pack_corr(tl, tp, n, c->corr6, c->corr6f, c->bounds, st);
     // no synchronisation here: later work is queued on the same stream; the host buffers must
     // stay valid until the call that consumes the set returns (all entry points are blocking)
   }
@@ -431,6 +439,7 @@ void FreeCorr(ppsfm_corr* c) {
     if (c->corr6) cudaFree(c->corr6);
     if (c->aligned) cudaFree(c->aligned);
     if (c->bounds) cudaFree(c->bounds);
+    if (c->corr6f) cudaFree(c->corr6f);
   }
   delete c;
 }
@@ -519,7 +528,8 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
                             &ctx->d_msrc, &ctx->d_K, &ctx->d_part_cnt, &ctx->d_part_sum,
                             &ctx->d_cnt, &ctx->d_sum, &ctx->d_eidx, &ctx->d_emodels, &ctx->d_rbuf,
                             &ctx->d_esum, &ctx->d_ecnt, &ctx->d_mask, &ctx->d_tmp_corr,
-                            &ctx->d_tmp_aligned, &ctx->d_corr6, &ctx->d_aligned};
+                            &ctx->d_tmp_aligned, &ctx->d_corr6, &ctx->d_aligned, &ctx->d_bounds,
+                            &ctx->d_corr6f};
   for (auto* b : dbufs) b->release();
   ppsfm::PinBuf* pbufs[] = {&ctx->h_samples, &ctx->h_num_models, &ctx->h_cnt, &ctx->h_sum,
                             &ctx->h_eidx, &ctx->h_emodels, &ctx->h_esum, &ctx->h_ecnt,
@@ -706,7 +716,7 @@ int ppsfm_score_models(ppsfm_ctx* ctx, const double* lines, const double* points
                                     cudaMemcpyHostToDevice, st));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_msrc.p, hoff.data(), sizeof(int) * hoff.size(),
                                     cudaMemcpyHostToDevice, st));
-    launch_score(corr->corr6, corr->bounds, (int)n, ctx->d_models.as<double>(),
+    launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, ctx->d_models.as<double>(),
                  ctx->d_msrc.as<int>(), H, num_segs, seg_len, max_residual, kcap,
                  ctx->d_part_cnt.as<unsigned>(), ctx->d_cnt.as<unsigned>(), st);
     PPSFM_CUDA(ctx, cudaMemcpyAsync(counts_out, ctx->d_cnt.p, sizeof(unsigned) * (size_t)H,

@@ -17,6 +17,7 @@
 
 #include "p6l_device.cuh"
 #include "ransac_kernels.h"
+#include "common.h"
 
 namespace ppsfm {
 
@@ -25,7 +26,8 @@ namespace ppsfm {
 // ------------------------------------------------------------------------------------------
 __global__ void pack_corr_kernel(const double* __restrict__ lines,
                                  const double* __restrict__ points, size_t n,
-                                 double* __restrict__ corr6, double* __restrict__ bounds) {
+                                 double* __restrict__ corr6, float* __restrict__ corr6f,
+                                 double* __restrict__ bounds) {
   const size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x;
   unsigned long long bx = 0, bl = 0, b2 = 0;  // bit patterns of |X|, of |l_0| / |l_1|, of |l_2|
   if (i < n * 3) {
@@ -33,6 +35,10 @@ __global__ void pack_corr_kernel(const double* __restrict__ lines,
     const double l = lines[i], x = points[i];
     corr6[r * 6 + c] = l;
     corr6[r * 6 + 3 + c] = x;
+    // float copy for the first stage of the score filter: record r / 2, slot r % 2
+    float* f = corr6f + (r >> 1) * 12 + (r & 1);
+    f[2 * c] = __double2float_rn(l);
+    f[6 + 2 * c] = __double2float_rn(x);
     bx = (unsigned long long)__double_as_longlong(fabs(x));
     if (c < 2) bl = (unsigned long long)__double_as_longlong(fabs(l));
     else b2 = (unsigned long long)__double_as_longlong(fabs(l));
@@ -56,12 +62,15 @@ __global__ void pack_corr_kernel(const double* __restrict__ lines,
 }
 
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
-                      double* bounds, cudaStream_t s) {
+                      float* corr6f, double* bounds, cudaStream_t s) {
   const int threads = 256;
   const size_t total = n * 3;
+  if (n == 0) return;
   cudaMemsetAsync(bounds, 0, 3 * sizeof(double), s);
+  if (n & 1) cudaMemsetAsync(corr6f + (n >> 1) * 12, 0, 12 * sizeof(float), s);  // empty slot
   pack_corr_kernel<<<(unsigned)((total + threads - 1) / threads), threads, 0, s>>>(lines, points,
-                                                                                    n, corr6, bounds);
+                                                                                    n, corr6, corr6f,
+                                                                                    bounds);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -231,7 +240,10 @@ __device__ __forceinline__ void score_one(const double* __restrict__ c, const do
     const double res = px_0 * l_0 * inv_px_2 + px_1 * l_1 * inv_px_2 + l_2;
     const unsigned long long ares =
         (unsigned long long)__double_as_longlong(res) & 0x7fffffffffffffffull;
-    if (ares <= rmax_bits) cnt += 1;  // src/optim/support_measurement.cc:42-45
+    // UNSIGNED compare: the compiler may take |res| through the FP64 pipe, which turns a NaN into
+    // the canonical negative one — it must still fail.  A negative r_max (NaN / negative
+    // max_residual: nothing is an inlier) has the sign bit set and is tested for separately.
+    if (ares <= rmax_bits && (long long)rmax_bits >= 0) cnt += 1;  // support_measurement.cc:42-45
   }
 }
 
@@ -460,15 +472,422 @@ double inlier_abs_threshold(double max_residual) {
   return r;
 }
 
-void launch_score(const double* corr6, const double* bounds, int n, const double* models,
-                  const int* offsets, int num_trials, int num_segs, int seg_len,
-                  double max_residual, int kcap, unsigned* part_cnt, unsigned* cnt_out,
-                  cudaStream_t s) {
+// ------------------------------------------------------------------------------------------
+// Scoring kernel, second form.  Differences from score_kernel above (kept for A/B timing):
+//   * the band is a per-model CONSTANT, k0 + k1 B_z + r_max 2^-50 >= k0 + k1 |pz|, and the test on
+//     |pz| is gone: a pair is decided iff |d| > band.  "Not an inlier" (d > band) is then right
+//     whichever way the reference's cheirality test px_2 > DBL_EPSILON falls, because a failed
+//     test also means "not counted"; "inlier" (d < -band) implies r_max pz > band, hence
+//     pz > 2^-50 + 2^-39 B_z, and the reference's own px_2 (within 2^-50 B_z of pz) is above
+//     DBL_EPSILON = 2^-52.  No overflow test either: the per-model constants are only usable when
+//     every intermediate is bounded by 2^940.
+//   * 13 FP64-pipe instructions per pair (9 projection FMAs, 3 for the numerator, 1 for d), one
+//     LOP + one chained ISETP + one LEA.HI of integer work; the group's predicate is tested once
+//     and a failed group is redone pair by pair (filter, then reference arithmetic).
+//   * no CTA-wide barrier in the tile loop: every warp counts itself off on a shared-memory
+//     counter when it is done with a stage and the last one re-arms the stage's TMA copy, so the
+//     warps of a CTA drift apart by up to kStages tiles instead of meeting every 128
+//     correspondences in the same phase of the instruction stream.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ int filter_band_hi(const double (&P)[12], const double* bounds,
+                                              double r_max, bool live) {
+  if (!live) return -1;  // P = 0: d = +0 is "decided", its sign bit is 0 — never counted, never slow
+  const double xmax = bounds[0], lmax = bounds[1], l2max = bounds[2];
+  const double bx = (fabs(P[0]) + fabs(P[3]) + fabs(P[6])) * xmax + fabs(P[9]);
+  const double by = (fabs(P[1]) + fabs(P[4]) + fabs(P[7])) * xmax + fabs(P[10]);
+  const double bz = (fabs(P[2]) + fabs(P[5]) + fabs(P[8])) * xmax + fabs(P[11]);
+  const double scale = (bx + by) * lmax + (l2max + r_max) * bz;   // >= |num| + r_max |pz|
+  const double band = (scale + (l2max + r_max) * bz) * 0x1p-40 + r_max * 0x1p-50;
+  const bool usable = band >= 0x1p-900 && band < 0x1p900 && r_max >= 0.0 && r_max < DBL_MAX;
+  return usable ? __double2hiint(band) : 0x7fffffff;
+}
+
+template <int OFF>
+__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a), "=d"(b) : "r"(addr), "n"(OFF));
+}
+
+// d = |px l_0 + py l_1 + pz l_2| - r_max pz for the correspondence at shared address addr + OFF
+template <int OFF>
+__device__ __forceinline__ int filter_d_hi(uint32_t addr, const double (&P)[12], double neg_rmax) {
+  double l_0, l_1, l_2, X_0, X_1, X_2;
+  lds_f64x2<OFF>(addr, l_0, l_1);
+  lds_f64x2<OFF + 16>(addr, l_2, X_0);
+  lds_f64x2<OFF + 32>(addr, X_1, X_2);
+  const double pz = fma(P[8], X_2, fma(P[5], X_1, fma(P[2], X_0, P[11])));
+  const double px = fma(P[6], X_2, fma(P[3], X_1, fma(P[0], X_0, P[9])));
+  const double py = fma(P[7], X_2, fma(P[4], X_1, fma(P[1], X_0, P[10])));
+  const double num = fma(l_2, pz, fma(py, l_1, px * l_0));
+  return __double2hiint(fma(neg_rmax, pz, fabs(num)));
+}
+
+template <int G, int U = 0>
+__device__ __forceinline__ void filter_group(uint32_t addr, const double (&P)[12], double neg_rmax,
+                                             int band_hi, bool& ok, unsigned& gcnt) {
+  if constexpr (U < G) {
+    const int d_hi = filter_d_hi<U * 48>(addr, P, neg_rmax);
+    ok = ok && (d_hi & 0x7fffffff) > band_hi;
+    gcnt += (unsigned)d_hi >> 31;  // d < 0: inlier
+    filter_group<G, U + 1>(addr, P, neg_rmax, band_hi, ok, gcnt);
+  }
+}
+
+// one pair, filter first and the reference arithmetic if undecided (rare path, not unrolled)
+__device__ __forceinline__ void score_checked(uint32_t addr, const double* __restrict__ c,
+                                              const double (&P)[12], double neg_rmax, int band_hi,
+                                              long long eps_bits, unsigned long long rmax_bits,
+                                              unsigned& cnt) {
+  const int d_hi = filter_d_hi<0>(addr, P, neg_rmax);
+  if ((d_hi & 0x7fffffff) > band_hi) cnt += (unsigned)d_hi >> 31;
+  else score_one(c, P, eps_bits, rmax_bits, cnt);
+}
+
+constexpr int kScoreWarps = kScoreThreads / 32;
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(kScoreThreads, MINB)
+score_kernel_v2(const double* __restrict__ corr6, int n, const double* __restrict__ models,
+                const int* __restrict__ offsets, int num_trials, int seg_len, double r_max,
+                int kcap, unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
+  __shared__ __align__(128) double tile[kStages][kTile * 6];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ unsigned done[kStages];   // warps that have finished with the stage
+
+  const int K = offsets[num_trials];
+  const int mbase = blockIdx.x * kScoreThreads;
+  if (mbase >= K) return;
+  const int seg = blockIdx.y;
+  const int i0 = seg * seg_len;
+  const int i1 = min(n, i0 + seg_len);
+
+  double P[12];
+  const int k = mbase + threadIdx.x;
+  if (k < K) {
+    int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (offsets[mid] <= k) lo = mid; else hi = mid;
+    }
+    const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
+#pragma unroll
+    for (int j = 0; j < 12; ++j) P[j] = src[j];
+  } else {
+#pragma unroll
+    for (int j = 0; j < 12; ++j) P[j] = 0.0;
+  }
+
+  const int len = max(0, i1 - i0);
+  const int num_tiles = (len + kTile - 1) / kTile;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages && s < num_tiles; ++s) {
+      const uint32_t bytes = (uint32_t)min(kTile, len - s * kTile) * 48u;
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + s * kTile) * 6, bytes, &full_bar[s]);
+    }
+  }
+
+  const int band_hi = filter_band_hi(P, bounds, r_max, k < K);
+  const double neg_rmax = -r_max;
+  const long long eps_bits = __double_as_longlong(DBL_EPSILON);
+  const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
+  const uint32_t tile_addr = smem_u32(&tile[0][0]);
+  unsigned cnt = 0;
+  for (int t = 0; t < num_tiles; ++t) {
+    const int s = t % kStages;
+    mbar_wait(&full_bar[s], (uint32_t)((t / kStages) & 1));
+    const int cnt_t = min(kTile, len - t * kTile);
+    const double* tp = &tile[s][0];
+    const uint32_t ta = tile_addr + (uint32_t)s * (kTile * 48);
+    int j = 0;
+#pragma unroll 1
+    for (; j + G <= cnt_t; j += G) {
+      bool ok = true;
+      unsigned gcnt = 0;
+      filter_group<G>(ta + (uint32_t)j * 48u, P, neg_rmax, band_hi, ok, gcnt);
+      if (ok) {
+        cnt += gcnt;
+      } else {  // some pair of the group is undecided (about one pair in 10^8)
+#pragma unroll 1
+        for (int u = 0; u < G; ++u)
+          score_checked(ta + (uint32_t)(j + u) * 48u, tp + (j + u) * 6, P, neg_rmax, band_hi,
+                        eps_bits, rmax_bits, cnt);
+      }
+    }
+#pragma unroll 1
+    for (; j < cnt_t; ++j)
+      score_checked(ta + (uint32_t)j * 48u, tp + j * 6, P, neg_rmax, band_hi, eps_bits, rmax_bits,
+                    cnt);
+    // this warp is done with stage s; the last warp of the CTA to get here refills it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(&done[s], 1u) == kScoreWarps - 1) {
+        done[s] = 0;
+        const int tn = t + kStages;
+        if (tn < num_tiles) {
+          const uint32_t bytes = (uint32_t)min(kTile, len - tn * kTile) * 48u;
+          __threadfence_block();
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
+        }
+      }
+    }
+  }
+  if (k < K) part_cnt[(size_t)seg * kcap + k] = cnt;
+}
+
+// ------------------------------------------------------------------------------------------
+// Scoring kernel, third form: a FLOAT first stage in front of the FP64 filter.
+//
+// The sign of d = |px l_0 + py l_1 + pz l_2| - r_max pz is all the count needs, and for all but a
+// few pairs in a million it is already certain in single precision.  The first stage evaluates d
+// on float copies of the model and of the correspondences, two correspondences per lane with the
+// packed FFMA2 of sm_100 (13 FMAs per pair -> 6.5 FFMA2; the FP64 pipe runs a DFMA warp
+// instruction every other cycle, FFMA2 does two FMAs per lane at that rate), and decides the pair
+// iff |d_32| > band_32:
+//   inputs rounded to float (relative 2^-24 each), three FMA chains of depth 3, the numerator
+//   chain and the final FMA give  |d_32 - d| <= 10 * 2^-24 * S,  S = (B_x + B_y) Lmax +
+//   (L2max + r_max) B_z >= |num| + r_max |pz|;  band_32 = 2^-20 S + band_64 + 2^-60 leaves a factor
+//   1.6 on that, adds the FP64 band (distance between the exact d and the reference's own
+//   evaluation, see filter_band_hi) and covers float underflow: the stage is used only when all
+//   inputs are below 2^40 in magnitude, so that an absolute error of 2^-150 (input or
+//   intermediate flushed / rounded in the subnormal range) reaches d with a factor < 2^80.
+// Everything else — a group in which some pair is undecided, models or sets outside the float
+// range — goes through score_slow: the FP64 filter and then the reference arithmetic, on the
+// double correspondences read from global memory (L2-resident), with the model reloaded from
+// global memory so that the hot loop carries only the float model.
+// ------------------------------------------------------------------------------------------
+constexpr int kTileR = 128;  // float records (= 256 correspondences, 6 KB) per stage
+
+__device__ __forceinline__ int filter32_band_bits(const double (&P)[12], const double* bounds,
+                                                  double r_max, bool live) {
+  if (!live) return -1;  // P = 0: d = +0, "decided" (band -1), sign bit 0
+  const double xmax = bounds[0], lmax = bounds[1], l2max = bounds[2];
+  const double bx = (fabs(P[0]) + fabs(P[3]) + fabs(P[6])) * xmax + fabs(P[9]);
+  const double by = (fabs(P[1]) + fabs(P[4]) + fabs(P[7])) * xmax + fabs(P[10]);
+  const double bz = (fabs(P[2]) + fabs(P[5]) + fabs(P[8])) * xmax + fabs(P[11]);
+  double pmax = 0.0;
+#pragma unroll
+  for (int j = 0; j < 12; ++j) pmax = fmax(pmax, fabs(P[j]));
+  const double scale = (bx + by) * lmax + (l2max + r_max) * bz;
+  const double band64 = (scale + (l2max + r_max) * bz) * 0x1p-40 + r_max * 0x1p-50;
+  const double band = scale * 0x1p-20 + band64 + 0x1p-60;
+  // (comparisons are false for NaN; fmax drops a NaN entry of P but then B_* is NaN)
+  const bool usable = xmax < 0x1p40 && lmax < 0x1p40 && l2max < 0x1p40 && pmax < 0x1p40 &&
+                      r_max >= 0.0 && r_max < 0x1p40 && scale < 0x1p80 && band < 0x1p80;
+  return usable ? __float_as_int(__double2float_ru(band)) : 0x7fffffff;
+}
+
+template <int OFF>
+__device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4+%5];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(addr), "n"(OFF));
+  return v;
+}
+
+template <int G, int U = 0>
+__device__ __forceinline__ void filter32_group(uint32_t addr, const float2 (&Pf)[12], float2 nr,
+                                               int band, bool& ok, unsigned& gcnt) {
+  if constexpr (U < G) {
+    const float4 v0 = lds_f32x4<U * 48>(addr), v1 = lds_f32x4<U * 48 + 16>(addr),
+                 v2 = lds_f32x4<U * 48 + 32>(addr);
+    const float2 l_0 = make_float2(v0.x, v0.y), l_1 = make_float2(v0.z, v0.w);
+    const float2 l_2 = make_float2(v1.x, v1.y), X_0 = make_float2(v1.z, v1.w);
+    const float2 X_1 = make_float2(v2.x, v2.y), X_2 = make_float2(v2.z, v2.w);
+    const float2 pz = __ffma2_rn(Pf[8], X_2, __ffma2_rn(Pf[5], X_1, __ffma2_rn(Pf[2], X_0, Pf[11])));
+    const float2 px = __ffma2_rn(Pf[6], X_2, __ffma2_rn(Pf[3], X_1, __ffma2_rn(Pf[0], X_0, Pf[9])));
+    const float2 py = __ffma2_rn(Pf[7], X_2, __ffma2_rn(Pf[4], X_1, __ffma2_rn(Pf[1], X_0, Pf[10])));
+    float2 num = __ffma2_rn(l_2, pz, __ffma2_rn(py, l_1, __fmul2_rn(px, l_0)));
+    num.x = fabsf(num.x);
+    num.y = fabsf(num.y);
+    const float2 d = __ffma2_rn(nr, pz, num);
+    const int da = __float_as_int(d.x), db = __float_as_int(d.y);
+    ok = ok && (da & 0x7fffffff) > band && (db & 0x7fffffff) > band;
+    gcnt += ((unsigned)da >> 31) + ((unsigned)db >> 31);  // d < 0: inlier
+    filter32_group<G, U + 1>(addr, Pf, nr, band, ok, gcnt);
+  }
+}
+
+// `count` correspondences from global memory against the model at Psrc: FP64 filter, then the
+// reference arithmetic.  Not inlined: nothing of the caller's state is passed by reference.
+__device__ __noinline__ unsigned score_slow(const double* __restrict__ c, int count,
+                                            const double* __restrict__ Psrc,
+                                            const double* __restrict__ bounds, double r_max) {
+  double P[12];
+#pragma unroll
+  for (int j = 0; j < 12; ++j) P[j] = Psrc[j];
+  const int band_hi = filter_band_hi(P, bounds, r_max, true);
+  const double neg_rmax = -r_max;
+  const long long eps_bits = __double_as_longlong(DBL_EPSILON);
+  const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
+  unsigned cnt = 0;
+#pragma unroll 1
+  for (int u = 0; u < count; ++u, c += 6) {
+    const double l_0 = c[0], l_1 = c[1], l_2 = c[2], X_0 = c[3], X_1 = c[4], X_2 = c[5];
+    const double pz = fma(P[8], X_2, fma(P[5], X_1, fma(P[2], X_0, P[11])));
+    const double px = fma(P[6], X_2, fma(P[3], X_1, fma(P[0], X_0, P[9])));
+    const double py = fma(P[7], X_2, fma(P[4], X_1, fma(P[1], X_0, P[10])));
+    const double num = fma(l_2, pz, fma(py, l_1, px * l_0));
+    const int d_hi = __double2hiint(fma(neg_rmax, pz, fabs(num)));
+    if ((d_hi & 0x7fffffff) > band_hi) cnt += (unsigned)d_hi >> 31;
+    else score_one(c, P, eps_bits, rmax_bits, cnt);
+  }
+  return cnt;
+}
+
+template <int G, int MINB>
+__global__ void __launch_bounds__(kScoreThreads, MINB)
+score_kernel_v3(const double* __restrict__ corr6, const float* __restrict__ corr6f, int n,
+                const double* __restrict__ models, const int* __restrict__ offsets,
+                int num_trials, int seg_len, double r_max, int kcap,
+                unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
+  __shared__ __align__(128) float tile[kStages][kTileR * 12];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
+  __shared__ unsigned done[kStages];  // warps that have finished with the stage
+
+  const int K = offsets[num_trials];
+  const int mbase = blockIdx.x * kScoreThreads;
+  if (mbase >= K) return;
+  const int seg = blockIdx.y;
+  const int i0 = seg * seg_len;  // even: seg_len is a multiple of 128
+  const int i1 = min(n, i0 + seg_len);
+  const int len = max(0, i1 - i0);
+  const int nrec = len >> 1;  // full records; an odd last correspondence goes through score_slow
+  const int num_tiles = (nrec + kTileR - 1) / kTileR;
+  const float* recs = corr6f + (size_t)(i0 >> 1) * 12;
+
+  const int k = mbase + threadIdx.x;
+  const double* src = nullptr;
+  float2 Pf[12];
+  int band = -1;
+  {
+    double P[12];
+    if (k < K) {
+      int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
+      while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets[mid] <= k) lo = mid; else hi = mid;
+      }
+      src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
+#pragma unroll
+      for (int j = 0; j < 12; ++j) P[j] = src[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < 12; ++j) P[j] = 0.0;
+    }
+    band = filter32_band_bits(P, bounds, r_max, k < K);
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+      const float f = __double2float_rn(P[j]);
+      Pf[j] = make_float2(f, f);
+    }
+  }
+  const float nrf = -__double2float_rn(r_max);
+  const float2 nr = make_float2(nrf, nrf);
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages && s < num_tiles; ++s) {
+      const uint32_t bytes = (uint32_t)min(kTileR, nrec - s * kTileR) * 48u;
+      mbar_arrive_expect_tx(&full_bar[s], bytes);
+      bulk_copy_g2s(&tile[s][0], recs + (size_t)s * kTileR * 12, bytes, &full_bar[s]);
+    }
+  }
+
+  const uint32_t tile_addr = smem_u32(&tile[0][0]);
+  unsigned cnt = 0;
+  for (int t = 0; t < num_tiles; ++t) {
+    const int s = t % kStages;
+    mbar_wait(&full_bar[s], (uint32_t)((t / kStages) & 1));
+    const int cnt_t = min(kTileR, nrec - t * kTileR);
+    const uint32_t ta = tile_addr + (uint32_t)s * (kTileR * 48);
+    const double* gc = corr6 + (size_t)(i0 + 2 * t * kTileR) * 6;  // the tile's doubles (slow path)
+    int j = 0;
+#pragma unroll 1
+    for (; j + G <= cnt_t; j += G) {
+      bool ok = true;
+      unsigned gcnt = 0;
+      filter32_group<G>(ta + (uint32_t)j * 48u, Pf, nr, band, ok, gcnt);
+      if (ok) cnt += gcnt;
+      else cnt += score_slow(gc + (size_t)j * 12, 2 * G, src, bounds, r_max);
+    }
+    if (j < cnt_t && src != nullptr)  // ragged end of the set
+      cnt += score_slow(gc + (size_t)j * 12, 2 * (cnt_t - j), src, bounds, r_max);
+    // this warp is done with stage s; the last warp of the CTA to get here refills it
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) {
+      __threadfence_block();
+      if (atomicAdd(&done[s], 1u) == kScoreWarps - 1) {
+        done[s] = 0;
+        const int tn = t + kStages;
+        if (tn < num_tiles) {
+          const uint32_t bytes = (uint32_t)min(kTileR, nrec - tn * kTileR) * 48u;
+          __threadfence_block();
+          fence_proxy_async();
+          mbar_arrive_expect_tx(&full_bar[s], bytes);
+          bulk_copy_g2s(&tile[s][0], recs + (size_t)tn * kTileR * 12, bytes, &full_bar[s]);
+        }
+      }
+    }
+  }
+  if (k < K) {
+    if (len & 1) cnt += score_slow(corr6 + (size_t)(i1 - 1) * 6, 1, src, bounds, r_max);
+    part_cnt[(size_t)seg * kcap + k] = cnt;
+  }
+}
+
+void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
+                  const double* models, const int* offsets, int num_trials, int num_segs,
+                  int seg_len, double max_residual, int kcap, unsigned* part_cnt,
+                  unsigned* cnt_out, cudaStream_t s) {
   if (num_trials <= 0) return;
   const double r_max = inlier_abs_threshold(max_residual);
   dim3 grid((kcap + kModelsPerCta - 1) / kModelsPerCta, num_segs);
-  score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
-                                              r_max, kcap, part_cnt, bounds);
+#define PPSFM_SCORE_V2(G, MINB)                                                                \
+  score_kernel_v2<G, MINB><<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, \
+                                                          seg_len, r_max, kcap, part_cnt, bounds)
+#define PPSFM_SCORE_V3(G, MINB)                                                              \
+  score_kernel_v3<G, MINB><<<grid, kScoreThreads, 0, s>>>(corr6, corr6f, n, models, offsets, \
+                                                          num_trials, seg_len, r_max, kcap,  \
+                                                          part_cnt, bounds)
+  switch (tune_int("PPSFM_SCORE_VARIANT", 13)) {
+    case 0:
+      score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
+                                                  r_max, kcap, part_cnt, bounds);
+      break;
+    case 2: PPSFM_SCORE_V2(8, 2); break;
+    case 4: PPSFM_SCORE_V2(8, 3); break;
+    case 5: PPSFM_SCORE_V2(4, 4); break;
+    case 10: PPSFM_SCORE_V3(2, 2); break;
+    case 11: PPSFM_SCORE_V3(4, 2); break;
+    case 12: PPSFM_SCORE_V3(2, 3); break;
+    case 13: PPSFM_SCORE_V3(4, 3); break;
+    case 14: PPSFM_SCORE_V3(2, 4); break;
+    case 15: PPSFM_SCORE_V3(4, 4); break;
+    case 16: PPSFM_SCORE_V3(8, 2); break;
+    case 17: PPSFM_SCORE_V3(1, 4); break;
+    default: PPSFM_SCORE_V2(4, 2); break;
+  }
+#undef PPSFM_SCORE_V2
+#undef PPSFM_SCORE_V3
   reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
                                                          num_trials, cnt_out);
 }

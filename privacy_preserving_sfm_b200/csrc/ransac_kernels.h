@@ -8,14 +8,16 @@
 namespace ppsfm {
 
 // bounds (device, 3 doubles): max |X_k|, max(|l_0|, |l_1|), max |l_2| over the set (score filter)
+// corr6f (device, ceil(n/2) x 12 floats): the set rounded to float, two correspondences per record
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
-                      double* bounds, cudaStream_t s);
+                      float* corr6f, double* bounds, cudaStream_t s);
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s);
 void launch_model_offsets(const int* num_models, int num_trials, int* offsets, cudaStream_t s);
 // Inlier counts of every compact model.  part_cnt: num_segs x kcap scratch; cnt_out: kcap
 // (first K valid).
-void launch_score(const double* corr6, const double* bounds, int n, const double* models,
+void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
+                  const double* models,
                   const int* offsets, int num_trials, int num_segs, int seg_len,
                   double max_residual, int kcap, unsigned* part_cnt, unsigned* cnt_out,
                   cudaStream_t s);

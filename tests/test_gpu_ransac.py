@@ -167,13 +167,7 @@ def test_options_check(ctx):
         pp.RANSAC_P6L(RANSACOptions(max_error=1.0, min_num_trials=5, max_num_trials=4), ctx)
 
 
-def test_score_filter_edge_cases(ctx, oracle):
-    """The count-only scoring kernel decides almost every pair with a division-free filter and
-    falls back to the reference arithmetic inside an error band.  Aim at the band: residuals that
-    equal the threshold exactly (and its neighbours), points on / next to the camera plane, huge
-    and tiny magnitudes, NaN / inf inputs — counts must stay bit-identical to the reference."""
-    rng = np.random.default_rng(77)
-    n, k = 4096, 300
+def _filter_case(rng, n=4096, k=300):
     R = np.stack([S.random_rotation(rng) for _ in range(k)])
     t = rng.uniform(-1, 1, (k, 3))
     models = np.concatenate([R.transpose(0, 2, 1).reshape(k, 9), t], axis=1)   # column-major 3x4
@@ -186,21 +180,59 @@ def test_score_filter_edge_cases(ctx, oracle):
     X[:64] = base
     X[64:96] = base[:32] + np.outer(2.0 ** -np.arange(20, 52), r3)
     X[96:128] = base[:32] - np.outer(2.0 ** -np.arange(20, 52), r3)
+    return models, lines, X
+
+
+def _check_counts(ctx, oracle, lines, X, models, tag, oracle_models=(0, 1, 7)):
+    res, _, _ = ctx.line_residuals(lines, X, models, 1e-4)
+    # thresholds that hit residuals exactly: r_max^2 = a residual of model 1, and its neighbours
+    finite = np.sort(res[1][np.isfinite(res[1]) & (res[1] < 1.0)])
+    thrs = [1e-4, 0.0, 1e-300, 1e300, np.inf]
+    if len(finite) > 3:
+        thrs += [finite[len(finite) // 2], np.nextafter(finite[len(finite) // 2], 0.0),
+                 np.nextafter(finite[len(finite) // 3], 1.0)]
+    for thr in thrs:
+        _, want, _ = ctx.line_residuals(lines, X, models, thr, want_residuals=False)
+        got = ctx.score_models(lines, X, models, thr)
+        assert np.array_equal(got.astype(np.uint64), want), (tag, thr)
+        # and against the CPU oracle for a few models
+        for m in oracle_models:
+            r_cpu = oracle.line_residuals(lines, X, models[m])
+            assert int((r_cpu <= thr).sum()) == int(got[m]), (tag, thr, m)
+
+
+def test_score_filter_edge_cases(ctx, oracle):
+    """The count-only scoring kernel decides almost every pair with division-free filters (a float
+    stage, then an FP64 stage) and falls back to the reference arithmetic inside their error
+    bands.  Aim at the bands: residuals that equal the threshold exactly (and its neighbours),
+    points on / next to the camera plane, magnitudes at and beyond the float stage's range, odd
+    and tiny set sizes, NaN / inf inputs — counts must stay bit-identical to the reference."""
+    rng = np.random.default_rng(77)
+    models, lines, X = _filter_case(rng)
+    _check_counts(ctx, oracle, lines, X, models, "clean")            # both filter stages active
+    for n_odd in (1, 2, 3, 255, 257, 1001):                           # ragged ends of the pairing
+        _check_counts(ctx, oracle, lines[:n_odd], X[:n_odd], models, "n=%d" % n_odd, (1,))
+    # magnitudes: the scene scaled up to the float stage's limit and beyond, and down into and
+    # below the float subnormal range (residuals are invariant under a common scale of X and t)
+    for e in (20, 36, 39, 45, 200, -20, -40, -60, -200):
+        sc = 2.0 ** e
+        m2 = models.copy()
+        m2[:, 9:] *= sc
+        _check_counts(ctx, oracle, lines, X * sc, m2, "scale 2^%d" % e, (1,))
+    # a set with non-finite and extreme entries: every filter stage must stand down
     X[128] *= 1e150
     X[129] *= 1e-150
     X[130, 0] = np.nan
     X[131, 1] = np.inf
     lines[132, 2] = np.nan
     lines[133] *= 1e100
-    res, cnt_ref, _ = ctx.line_residuals(lines, X, models, 1e-4)
-    # thresholds that hit residuals exactly: r_max^2 = a residual of model 1, and its neighbours
-    finite = np.sort(res[1][np.isfinite(res[1]) & (res[1] < 1.0)])
-    for thr in [1e-4, finite[len(finite) // 2], np.nextafter(finite[len(finite) // 2], 0.0),
-                np.nextafter(finite[len(finite) // 3], 1.0), 0.0, 1e-300, 1e300, np.inf]:
-        _, want, _ = ctx.line_residuals(lines, X, models, thr, want_residuals=False)
-        got = ctx.score_models(lines, X, models, thr)
-        assert np.array_equal(got.astype(np.uint64), want), thr
-        # and against the CPU oracle for a few models
-        for m in (0, 1, 7):
-            r_cpu = oracle.line_residuals(lines, X, models[m])
-            assert int((r_cpu <= thr).sum()) == int(got[m])
+    _check_counts(ctx, oracle, lines, X, models, "dirty")
+    # models with non-finite / huge / zero entries next to ordinary ones
+    m3 = models.copy()
+    m3[3, 4] = np.nan
+    m3[4, 11] = np.inf
+    m3[5] *= 1e60
+    m3[6] = 0.0
+    m3[8] *= 1e-60
+    models_c, lines_c, X_c = _filter_case(np.random.default_rng(78))
+    _check_counts(ctx, oracle, lines_c, X_c, m3, "odd models", (1, 5, 6))
