@@ -379,6 +379,8 @@ int ppsfm_estimate_triangulation_batch(ppsfm_ctx* ctx, const ppsfm_filter_proble
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);
+/* Packed float FMA (FFMA2) rate in 1e12 FMAs/s: the ceiling of the score filter's float stage. */
+int ppsfm_bench_fp32_peak(ppsfm_ctx* ctx, double* ffma_tips);
 /* Write-only / read-only HBM bandwidth (GB/s) over a 2 GiB buffer. */
 int ppsfm_bench_hbm_rw_peak(ppsfm_ctx* ctx, double* write_gbs, double* read_gbs);
 /* Evict L2 by writing `bytes` of scratch HBM (blocking). */

@@ -125,6 +125,7 @@ def load_library():
     L.ppsfm_comm_world_size.argtypes = [vp]
     L.ppsfm_comm_allreduce_sum_host.argtypes = [vp, _dp, C.c_size_t]
     L.ppsfm_bench_fp64_peak.argtypes = [vp, _dp, _dp]
+    L.ppsfm_bench_fp32_peak.argtypes = [vp, _dp]
     L.ppsfm_bench_l2_flush.argtypes = [vp, C.c_size_t]
     L.ppsfm_bench_hbm_rw_peak.argtypes = [vp, _dp, _dp]
     _lib = L
@@ -319,6 +320,11 @@ class Context:
         a, b = C.c_double(), C.c_double()
         self._check(self._L.ppsfm_bench_fp64_peak(self._h, C.byref(a), C.byref(b)))
         return float(a.value), float(b.value)
+
+    def bench_fp32_peak(self):
+        a = C.c_double()
+        self._check(self._L.ppsfm_bench_fp32_peak(self._h, C.byref(a)))
+        return float(a.value)
 
     def bench_hbm_rw_peak(self):
         a, b = C.c_double(), C.c_double()

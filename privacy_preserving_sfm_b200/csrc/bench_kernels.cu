@@ -23,6 +23,24 @@ __global__ void __launch_bounds__(256) fp64_rate_kernel(double* out, int iters, 
   out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
 }
 
+// Packed float FMA rate (FFMA2: two FMAs per lane and instruction — the form the float stage of
+// the score filter is built from), 8 independent accumulator pairs per thread.
+__global__ void __launch_bounds__(256) fp32_rate_kernel(float* out, int iters, float a, float b) {
+  float2 x[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) x[i] = make_float2(threadIdx.x * 1e-3f + i, threadIdx.x * 2e-3f - i);
+  const float2 av = make_float2(a + threadIdx.x * 1e-9f, a - threadIdx.x * 1e-9f);
+  const float2 bv = make_float2(b + threadIdx.x * 1e-9f, b);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x[i] = __ffma2_rn(x[i], av, bv);
+  }
+  float r = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += x[i].x + x[i].y;
+  out[blockIdx.x * blockDim.x + threadIdx.x] = r;
+}
+
 // HBM write / read micro-benchmarks: STREAM-style copy peaks mix reads and writes 1:1, but the
 // Jacobian build writes 3x what it reads, so its ceiling is the write-side bandwidth.
 __global__ void __launch_bounds__(256) hbm_write_kernel(double2* __restrict__ out, size_t n,
@@ -116,6 +134,36 @@ int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tip
   PPSFM_CUDA(ctx, cudaGetLastError());
   if (dfma_tips) *dfma_tips = best[0];
   if (dmuladd_tips) *dmuladd_tips = best[1];
+  return PPSFM_OK;
+}
+
+// Returns the packed float FMA throughput in 1e12 FMAs per second (x2 = TFLOP/s FP32).
+int ppsfm_bench_fp32_peak(ppsfm_ctx* ctx, double* ffma_tips) {
+  if (!ctx) return PPSFM_ERR_INVALID;
+  cudaSetDevice(ctx->device);
+  const int blocks = ctx->num_sms * 8, threads = 256, iters = 8192;
+  float* d = nullptr;
+  PPSFM_CUDA(ctx, cudaMalloc(&d, sizeof(float) * blocks * threads));
+  cudaEvent_t a, b;
+  cudaEventCreate(&a);
+  cudaEventCreate(&b);
+  double best = 0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(a, ctx->stream);
+    fp32_rate_kernel<<<blocks, threads, 0, ctx->stream>>>(d, iters, 0.9999999f, 1e-6f);
+    cudaEventRecord(b, ctx->stream);
+    cudaEventSynchronize(b);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, a, b);
+    const double fmas = (double)blocks * threads * iters * 16.0;
+    const double tips = fmas / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tips > best) best = tips;
+  }
+  cudaEventDestroy(a);
+  cudaEventDestroy(b);
+  cudaFree(d);
+  PPSFM_CUDA(ctx, cudaGetLastError());
+  if (ffma_tips) *ffma_tips = best;
   return PPSFM_OK;
 }
 

@@ -88,6 +88,22 @@ struct ppsfm_ctx {
   ppsfm::PinBuf h_samples, h_num_models, h_cnt, h_sum, h_eidx, h_emodels, h_esum, h_ecnt, h_mask,
       h_K, h_stage;
   ppsfm_ransac_timing timing{};
+  // RANSAC wave pipeline (ransac_host.cu RansacResident): per-wave buffers and events, a
+  // high-priority stream for the sample copies / solve kernels / exact kernels
+  static constexpr int kWaveSlots = 4;
+  struct WaveSlot {
+    ppsfm::DevBuf d_samples, d_models, d_num_models, d_off, d_part_cnt, d_cnt;
+    ppsfm::PinBuf h_samples, h_off, h_cnt;
+    cudaEvent_t ev[5] = {nullptr};  // solve begin / end, score begin / end, results on the host
+    cudaStream_t solve_stream = nullptr;  // high priority: the waves' solve kernels overlap
+  } wave[kWaveSlots];
+  cudaStream_t stream_hi = nullptr;
+  cudaStream_t stream_copy = nullptr;  // result copies, so that scoring kernels run back to back
+  cudaEvent_t ev_sync = nullptr;
+  // index-order support + mask of the current best model, computed ahead of the end of the loop
+  ppsfm::DevBuf d_fmodel, d_frbuf, d_fmask, d_fcnt, d_fsum;
+  ppsfm::PinBuf h_fmask, h_fres;
+  cudaEvent_t ev_final[3] = {nullptr};  // kernel begin / end, results on the host
 
   // multi-GPU (comm.cu): NCCL communicator, one rank per context
   void* comm = nullptr;

@@ -7,6 +7,7 @@
 // waves, and the loop-carried logic (best-so-far, dyn_max_num_trials, abort inside the model
 // loop) is replayed literally on the host over per-model supports.
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstring>
@@ -87,7 +88,24 @@ static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap_blocks, int* nu
   *seg_len = len;
 }
 
+// One wave of the trial loop: trials [t_begin, t_end), its buffers (a slot of ctx->wave) and the
+// generator state before its samples were drawn (needed to rewind after an abort).
+struct Wave {
+  size_t t_begin = 0, t_end = 0;
+  int H = 0, kcap = 0, slot = 0;
+  std::mt19937 prng_at_start;
+};
+
 // Runs trials [0, ...) of the RANSAC loop on a resident correspondence set.
+//
+// The loop is a software pipeline over waves of trials.  issue(w) draws the wave's samples on the
+// host and queues copy + solve on the high-priority stream and the scoring kernel on the main
+// stream; consume(w) waits for the wave's counts and replays the reference's sequential loop
+// over them.  Up to kWaveSlots waves are in flight, so the host work of the next waves (sampling,
+// replay) and their latency-bound solve kernels run under the scoring kernel of the current one.
+// Waves are issued ahead only over trials the loop is certain to reach (below min_num_trials, or
+// below the current dynamic bound once a best model exists), so a call that stops inside its
+// first wave pays nothing for the pipeline.
 int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_options* opt_in,
                    ppsfm_ransac_report* report, uint8_t* inlier_mask) {
   if (!ctx || !corr || !opt_in || !report) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
@@ -124,72 +142,170 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   bool finished = false;
   size_t reported_trials = max_num_trials;
   uint64_t scored = 0;
+  float total_ms = 0.f;
 
   HostSampler sampler;
   sampler.Initialize(n);
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->stream;      // scoring kernels, result copies
+  cudaStream_t hi = ctx->stream_hi;   // exact (tie / final) kernels; the waves' sample copies and
+                                      // solve kernels go to their slot's own high-priority stream
+  // the correspondence set may still be in flight on the main stream (upload + pack)
+  PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev_sync, st));
+  PPSFM_CUDA(ctx, cudaStreamWaitEvent(hi, ctx->ev_sync, 0));
+  for (auto& sl : ctx->wave) PPSFM_CUDA(ctx, cudaStreamWaitEvent(sl.solve_stream, ctx->ev_sync, 0));
 
-  // Wave schedule: the first wave covers at least min_num_trials (and a floor that fills the
-  // GPU); later waves run up to the current dyn_max_num_trials.
+  const bool trace = ppsfm::tune_int("PPSFM_RANSAC_TRACE", 0) != 0;
+  const auto host_t0 = std::chrono::steady_clock::now();
+  auto host_ms = [&]() {
+    return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - host_t0)
+        .count();
+  };
+  if (trace) PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));  // GPU time base
+  // On every exit path the streams are drained: speculative waves may still be running.
+  struct Drain {
+    ppsfm_ctx* c;
+    ~Drain() {
+      for (auto& sl : c->wave) cudaStreamSynchronize(sl.solve_stream);
+      cudaStreamSynchronize(c->stream);
+      cudaStreamSynchronize(c->stream_hi);
+      cudaStreamSynchronize(c->stream_copy);
+    }
+  } drain{ctx};
+
+  // ---- wave schedule.  A "plan" is the range the reference loop is currently bound to reach
+  // (at least min_num_trials and a floor that fills the GPU, at most the dynamic bound); it is
+  // cut into kChunks waves so that the pipeline has something to overlap.
   const size_t kWaveFloor = 1024;
   const size_t kWaveCap = 1u << 17;
-  size_t t_begin = 0;
-  float total_ms = 0.f;
-  while (!finished && t_begin < max_num_trials) {
-    size_t want_end = std::max<size_t>(opt.min_num_trials, t_begin + kWaveFloor);
-    if (dyn_max_num_trials != std::numeric_limits<size_t>::max())
-      want_end = std::max(want_end, std::min(dyn_max_num_trials + 1, max_num_trials));
-    size_t t_end = std::min(max_num_trials, want_end);
-    t_end = std::min(t_end, t_begin + kWaveCap);
-    const int H = static_cast<int>(t_end - t_begin);
-    const int kcap = 8 * H;
+  const size_t kChunks = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", 4));
+  size_t t_issue = 0;      // first trial not yet issued
+  size_t plan_end = 0, plan_chunk = 0;
+  // Wave sizes grow geometrically inside a plan (x3 from a tenth of the span): the first wave is
+  // the only one whose sampling and solve latency nothing can hide, and the scoring of each wave
+  // has to cover the solve latency of the next.  PPSFM_RANSAC_CHUNKS=1 keeps the plan whole.
+  auto next_wave_range = [&](size_t* t_end_out) {
+    if (t_issue >= plan_end) {
+      size_t want_end = std::max<size_t>(opt.min_num_trials, t_issue + kWaveFloor);
+      if (dyn_max_num_trials != std::numeric_limits<size_t>::max())
+        want_end = std::max(want_end, std::min(dyn_max_num_trials + 1, max_num_trials));
+      plan_end = std::min(max_num_trials, want_end);
+      const size_t span = plan_end - t_issue;
+      plan_chunk = kChunks <= 1 ? kWaveCap
+                                : std::min(kWaveCap, std::max(kWaveFloor, (span / 10 + 255) / 256 * 256));
+    }
+    size_t t_end = std::min(plan_end, t_issue + plan_chunk);
+    if (plan_end - t_end < plan_chunk) t_end = std::min(plan_end, t_issue + kWaveCap);
+    plan_chunk = std::min(kWaveCap, plan_chunk * 3);
+    *t_end_out = t_end;
+  };
 
-    // ---- sample on the host (A7), keep a PRNG snapshot for the rewind after an abort
-    const std::mt19937 prng_at_wave_start = ctx->prng;
-    PPSFM_CUDA(ctx, ctx->h_samples.reserve(sizeof(uint32_t) * 6 * (size_t)H));
-    uint32_t* hs = ctx->h_samples.as<uint32_t>();
+  auto issue = [&](Wave& w) -> int {
+    auto& sl = ctx->wave[w.slot];
+    cudaStream_t hs_stream = sl.solve_stream;
+    const int H = w.H, kcap = w.kcap;
+    w.prng_at_start = ctx->prng;
+    const double trace_t0 = trace ? host_ms() : 0.0;
+    // ---- sample on the host (A7)
+    PPSFM_CUDA(ctx, sl.h_samples.reserve(sizeof(uint32_t) * 6 * (size_t)H));
+    uint32_t* hs = sl.h_samples.as<uint32_t>();
     for (int t = 0; t < H; ++t) sampler.Sample(ctx->prng, hs + 6 * (size_t)t);
-
     // ---- device buffers
-    PPSFM_CUDA(ctx, ctx->d_samples.reserve(sizeof(uint32_t) * 6 * (size_t)H));
-    PPSFM_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * 96 * (size_t)H));
-    PPSFM_CUDA(ctx, ctx->d_num_models.reserve(sizeof(int) * (size_t)H));
-    PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
+    PPSFM_CUDA(ctx, sl.d_samples.reserve(sizeof(uint32_t) * 6 * (size_t)H));
+    PPSFM_CUDA(ctx, sl.d_models.reserve(sizeof(double) * 96 * (size_t)H));
+    PPSFM_CUDA(ctx, sl.d_num_models.reserve(sizeof(int) * (size_t)H));
+    PPSFM_CUDA(ctx, sl.d_off.reserve(sizeof(int) * ((size_t)H + 1)));
     int num_segs, seg_len;
     ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);  // 256 models per CTA
-    PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
-    PPSFM_CUDA(ctx, ctx->d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
-    PPSFM_CUDA(ctx, ctx->h_num_models.reserve(sizeof(int) * ((size_t)H + 1)));
-    PPSFM_CUDA(ctx, ctx->h_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
-
-    // ---- solve + score on the GPU
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, hs, sizeof(uint32_t) * 6 * (size_t)H,
-                                    cudaMemcpyHostToDevice, st));
-    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));
-    launch_p6l_solve(corr->corr6, corr->aligned, ctx->d_samples.as<uint32_t>(), H,
-                     ctx->d_models.as<double>(), ctx->d_num_models.as<int>(), st);
-    launch_model_offsets(ctx->d_num_models.as<int>(), H, ctx->d_msrc.as<int>(), st);
-    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[1], st));
-    launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, ctx->d_models.as<double>(), ctx->d_msrc.as<int>(), H,
-                 num_segs, seg_len, max_residual, kcap, ctx->d_part_cnt.as<unsigned>(),
-                 ctx->d_cnt.as<unsigned>(), st);
-    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[2], st));
+    PPSFM_CUDA(ctx, sl.d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
+    PPSFM_CUDA(ctx, sl.d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
+    PPSFM_CUDA(ctx, sl.h_off.reserve(sizeof(int) * ((size_t)H + 1)));
+    PPSFM_CUDA(ctx, sl.h_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
+    // ---- copy + solve on the slot's high-priority stream
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.d_samples.p, hs, sizeof(uint32_t) * 6 * (size_t)H,
+                                    cudaMemcpyHostToDevice, hs_stream));
+    PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[0], hs_stream));
+    launch_p6l_solve(corr->corr6, corr->aligned, sl.d_samples.as<uint32_t>(), H,
+                     sl.d_models.as<double>(), sl.d_num_models.as<int>(), hs_stream);
+    launch_model_offsets(sl.d_num_models.as<int>(), H, sl.d_off.as<int>(), hs_stream);
+    PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[1], hs_stream));
+    // ---- score on the main stream, results to the host
+    PPSFM_CUDA(ctx, cudaStreamWaitEvent(st, sl.ev[1], 0));
+    PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[2], st));
+    launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, sl.d_models.as<double>(),
+                 sl.d_off.as<int>(), H, num_segs, seg_len, max_residual, kcap,
+                 sl.d_part_cnt.as<unsigned>(), sl.d_cnt.as<unsigned>(), st);
+    PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[3], st));
+    // results to the host on the copy stream: the next wave's scoring kernel follows directly
+    cudaStream_t cp = ctx->stream_copy;
+    PPSFM_CUDA(ctx, cudaStreamWaitEvent(cp, sl.ev[3], 0));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_off.p, sl.d_off.p, sizeof(int) * ((size_t)H + 1),
+                                    cudaMemcpyDeviceToHost, cp));
+    // (K is not known on the host yet: all kcap counts travel, 32 B per trial)
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_cnt.p, sl.d_cnt.p, sizeof(unsigned) * (size_t)kcap,
+                                    cudaMemcpyDeviceToHost, cp));
+    PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[4], cp));
     ctx->timing.kernel_launches += 4;
     ctx->timing.score_launches += 1;
-    int* h_off = ctx->h_num_models.as<int>();
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(h_off, ctx->d_msrc.p, sizeof(int) * ((size_t)H + 1),
-                                    cudaMemcpyDeviceToHost, st));
-    PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+    if (trace)
+      fprintf(stderr, "[ransac] issue   trials %zu..%zu host %.3f -> %.3f ms\n", w.t_begin, w.t_end,
+              trace_t0, host_ms());
+    return PPSFM_OK;
+  };
+
+  // ---- index-order support (+ mask) of the best model, src/optim/ransac.h:251-275.  Launched as
+  // soon as a wave has changed the best model, on the high-priority stream, so that it runs under
+  // the scoring of the following waves; if the best model is still the same at the end of the loop
+  // the result is simply picked up.
+  const bool mask_wanted = inlier_mask != nullptr;
+  bool final_valid = false;      // a launch for the CURRENT best model is in flight / done
+  bool final_has_mask = false;
+  auto launch_final = [&]() -> int {
+    PPSFM_CUDA(ctx, ctx->d_fmodel.reserve(sizeof(double) * 12));
+    PPSFM_CUDA(ctx, ctx->d_frbuf.reserve(sizeof(double) * n));
+    PPSFM_CUDA(ctx, ctx->d_fmask.reserve(n));
+    PPSFM_CUDA(ctx, ctx->h_fmask.reserve(n));
+    PPSFM_CUDA(ctx, ctx->d_fcnt.reserve(sizeof(unsigned long long)));
+    PPSFM_CUDA(ctx, ctx->d_fsum.reserve(sizeof(double)));
+    PPSFM_CUDA(ctx, ctx->h_fres.reserve(16));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_fmodel.p, best_model, sizeof(best_model),
+                                    cudaMemcpyHostToDevice, hi));
+    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev_final[0], hi));
+    final_has_mask = mask_wanted && best.num_inliers >= 6;
+    launch_exact(corr->corr6, (int)n, ctx->d_fmodel.as<double>(), 1, max_residual,
+                 ctx->d_frbuf.as<double>(), final_has_mask ? ctx->d_fmask.as<uint8_t>() : nullptr,
+                 ctx->d_fcnt.as<unsigned long long>(), ctx->d_fsum.as<double>(), hi);
+    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev_final[1], hi));
+    ctx->timing.kernel_launches += 2;
+    if (final_has_mask)
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_fmask.p, ctx->d_fmask.p, n, cudaMemcpyDeviceToHost, hi));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_fres.p, ctx->d_fsum.p, sizeof(double),
+                                    cudaMemcpyDeviceToHost, hi));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_fres.as<char>() + 8, ctx->d_fcnt.p,
+                                    sizeof(unsigned long long), cudaMemcpyDeviceToHost, hi));
+    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev_final[2], hi));
+    final_valid = true;
+    return PPSFM_OK;
+  };
+
+  auto consume = [&](Wave& w) -> int {
+    auto& sl = ctx->wave[w.slot];
+    const int H = w.H;
+    const size_t t_begin = w.t_begin, t_end = w.t_end;
+    const double trace_t0 = trace ? host_ms() : 0.0;
+    PPSFM_CUDA(ctx, cudaEventSynchronize(sl.ev[4]));
+    if (trace)
+      fprintf(stderr,
+              "[ransac] consume trials %zu..%zu host wait %.3f -> %.3f ms | gpu solve %.3f..%.3f "
+              "score %.3f..%.3f results %.3f\n",
+              w.t_begin, w.t_end, trace_t0, host_ms(), EventMs(ctx->ev[0], sl.ev[0]),
+              EventMs(ctx->ev[0], sl.ev[1]), EventMs(ctx->ev[0], sl.ev[2]),
+              EventMs(ctx->ev[0], sl.ev[3]), EventMs(ctx->ev[0], sl.ev[4]));
+    int* h_off = sl.h_off.as<int>();
+    unsigned* h_cnt = sl.h_cnt.as<unsigned>();
     const int K = h_off[H];
-    unsigned* h_cnt = ctx->h_cnt.as<unsigned>();
-    if (K > 0) {
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(h_cnt, ctx->d_cnt.p, sizeof(unsigned) * (size_t)K,
-                                      cudaMemcpyDeviceToHost, st));
-      PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
-    }
-    ctx->timing.solve_ms += EventMs(ctx->ev[0], ctx->ev[1]);
-    ctx->timing.score_ms += EventMs(ctx->ev[1], ctx->ev[2]);
-    total_ms += EventMs(ctx->ev[0], ctx->ev[2]);
+    ctx->timing.solve_ms += EventMs(sl.ev[0], sl.ev[1]);
+    ctx->timing.score_ms += EventMs(sl.ev[2], sl.ev[3]);
+    total_ms += EventMs(sl.ev[0], sl.ev[1]) + EventMs(sl.ev[2], sl.ev[3]);
     ctx->timing.score_pairs += (uint64_t)K * n;
 
     // ---- pass 1 (counts only): models that beat or tie the running best count.  Only a TIE
@@ -235,24 +351,24 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
         for (int e = e0; e < e0 + ne; ++e) {
           double* dst = ctx->d_emodels.as<double>() + (size_t)(e - e0) * 12;
           if (e < E)
-            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, ctx->d_models.as<double>() + model_src(cand[e]),
-                                            sizeof(double) * 12, cudaMemcpyDeviceToDevice, st));
+            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, sl.d_models.as<double>() + model_src(cand[e]),
+                                            sizeof(double) * 12, cudaMemcpyDeviceToDevice, hi));
           else
             PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, best_model, sizeof(double) * 12,
-                                            cudaMemcpyHostToDevice, st));
+                                            cudaMemcpyHostToDevice, hi));
         }
-        PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
+        PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], hi));
         launch_exact(corr->corr6, (int)n, ctx->d_emodels.as<double>(), ne, max_residual,
                      ctx->d_rbuf.as<double>(), nullptr, ctx->d_ecnt.as<unsigned long long>(),
-                     ctx->d_esum.as<double>(), st);
-        PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
+                     ctx->d_esum.as<double>(), hi);
+        PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[4], hi));
         ctx->timing.kernel_launches += 2;
         PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_esum.as<double>() + e0, ctx->d_esum.p,
-                                        sizeof(double) * ne, cudaMemcpyDeviceToHost, st));
+                                        sizeof(double) * ne, cudaMemcpyDeviceToHost, hi));
         PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ecnt.as<unsigned long long>() + e0, ctx->d_ecnt.p,
                                         sizeof(unsigned long long) * ne, cudaMemcpyDeviceToHost,
-                                        st));
-        PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+                                        hi));
+        PPSFM_CUDA(ctx, cudaStreamSynchronize(hi));
         const float ems = EventMs(ctx->ev[3], ctx->ev[4]);
         ctx->timing.exact_ms += ems;
         total_ms += ems;
@@ -314,8 +430,9 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
           abort = true;
           const size_t t_abort = trial;
           reported_trials = (t_abort + 1 < max_num_trials) ? t_abort + 2 : max_num_trials;
-          // the reference drew samples for trials 0..t_abort only: rewind the generator
-          ctx->prng = prng_at_wave_start;
+          // the reference drew samples for trials 0..t_abort only: rewind the generator to the
+          // start of this wave (later waves may have been sampled ahead) and skip forward
+          ctx->prng = w.prng_at_start;
           HostSampler::Skip(ctx->prng, n, t_abort + 1 - t_begin);
           finished = true;
           break;
@@ -323,12 +440,46 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       }
     }
     if (best_k >= 0) {  // the best model changed in this wave: bring its 12 doubles to the host
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(best_model, ctx->d_models.as<double>() + model_src(best_k),
-                                      sizeof(best_model), cudaMemcpyDeviceToHost, st));
-      PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(best_model, sl.d_models.as<double>() + model_src(best_k),
+                                      sizeof(best_model), cudaMemcpyDeviceToHost, hi));
+      PPSFM_CUDA(ctx, cudaStreamSynchronize(hi));
+      const int rc = launch_final();
+      if (rc != PPSFM_OK) return rc;
     }
-    t_begin = t_end;
+    return PPSFM_OK;
+  };
+
+  // ---- the pipeline
+  constexpr int kSlots = ppsfm_ctx::kWaveSlots;
+  Wave waves[kSlots];
+  int head = 0, in_flight = 0;  // waves[head] is the oldest wave in flight
+  size_t num_issued = 0;
+  auto certain_to_reach = [&](size_t t) {
+    return t < opt.min_num_trials || (have_best && t <= dyn_max_num_trials);
+  };
+  while (!finished) {
+    // issue: always when nothing is in flight, ahead only over trials certain to be reached
+    while (in_flight < kSlots && t_issue < max_num_trials &&
+           (in_flight == 0 || certain_to_reach(t_issue))) {
+      Wave& w = waves[(head + in_flight) % kSlots];
+      w.slot = (head + in_flight) % kSlots;
+      w.t_begin = t_issue;
+      next_wave_range(&w.t_end);
+      w.H = static_cast<int>(w.t_end - w.t_begin);
+      w.kcap = 8 * w.H;
+      const int rc = issue(w);
+      if (rc != PPSFM_OK) return rc;
+      t_issue = w.t_end;
+      ++in_flight;
+      ++num_issued;
+    }
+    if (in_flight == 0) break;  // all trials done
+    const int rc = consume(waves[head]);
+    if (rc != PPSFM_OK) return rc;
+    head = (head + 1) % kSlots;
+    --in_flight;
   }
+  (void)num_issued;
 
   report->num_trials = reported_trials;
   report->num_inliers = best.num_inliers;
@@ -338,35 +489,23 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   // Support + inlier mask of the best model in reference (index) order
   // (src/optim/ransac.h:251-275: the reference also rescans the best model once more).
   if (have_best) {
-    PPSFM_CUDA(ctx, ctx->d_emodels.reserve(sizeof(double) * 12));
-    PPSFM_CUDA(ctx, ctx->d_rbuf.reserve(sizeof(double) * n));
-    PPSFM_CUDA(ctx, ctx->d_mask.reserve(n));
-    PPSFM_CUDA(ctx, ctx->h_mask.reserve(n));
-    PPSFM_CUDA(ctx, ctx->d_ecnt.reserve(sizeof(unsigned long long)));
-    PPSFM_CUDA(ctx, ctx->d_esum.reserve(sizeof(double)));
-    PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double)));
-    PPSFM_CUDA(ctx, ctx->h_ecnt.reserve(sizeof(unsigned long long)));
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_emodels.p, best_model, sizeof(best_model),
-                                    cudaMemcpyHostToDevice, st));
-    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], st));
-    const bool want_mask = inlier_mask != nullptr && best.num_inliers >= 6;
-    launch_exact(corr->corr6, (int)n, ctx->d_emodels.as<double>(), 1, max_residual,
-                 ctx->d_rbuf.as<double>(), want_mask ? ctx->d_mask.as<uint8_t>() : nullptr,
-                 ctx->d_ecnt.as<unsigned long long>(), ctx->d_esum.as<double>(), st);
-    PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[4], st));
-    ctx->timing.kernel_launches += 2;
-    if (want_mask)
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_mask.p, ctx->d_mask.p, n, cudaMemcpyDeviceToHost, st));
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_esum.p, ctx->d_esum.p, sizeof(double),
-                                    cudaMemcpyDeviceToHost, st));
-    PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->h_ecnt.p, ctx->d_ecnt.p, sizeof(unsigned long long),
-                                    cudaMemcpyDeviceToHost, st));
-    PPSFM_CUDA(ctx, cudaStreamSynchronize(st));
-    if (ctx->h_ecnt.as<unsigned long long>()[0] != best.num_inliers)
+    if (!final_valid) {
+      const int rc = launch_final();
+      if (rc != PPSFM_OK) return rc;
+    }
+    const double trace_t0 = trace ? host_ms() : 0.0;
+    PPSFM_CUDA(ctx, cudaEventSynchronize(ctx->ev_final[2]));
+    if (trace)
+      fprintf(stderr, "[ransac] final   host wait %.3f -> %.3f ms | gpu exact %.3f..%.3f\n",
+              trace_t0, host_ms(), EventMs(ctx->ev[0], ctx->ev_final[0]),
+              EventMs(ctx->ev[0], ctx->ev_final[1]));
+    unsigned long long fcnt;
+    std::memcpy(&fcnt, ctx->h_fres.as<char>() + 8, sizeof(fcnt));
+    if (fcnt != best.num_inliers)
       return fail(ctx, PPSFM_ERR_CUDA, "internal: exact/segmented inlier counts differ");
-    best.residual_sum = ctx->h_esum.as<double>()[0];
-    if (want_mask) std::memcpy(inlier_mask, ctx->h_mask.p, n);
-    const float ems = EventMs(ctx->ev[3], ctx->ev[4]);
+    std::memcpy(&best.residual_sum, ctx->h_fres.p, sizeof(double));
+    if (final_has_mask) std::memcpy(inlier_mask, ctx->h_fmask.p, n);
+    const float ems = EventMs(ctx->ev_final[0], ctx->ev_final[1]);
     ctx->timing.exact_ms += ems;
     total_ms += ems;
   }
@@ -506,6 +645,22 @@ int ppsfm_ctx_create(int device, ppsfm_ctx** out) {
     return PPSFM_ERR_CUDA;
   }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  {
+    int lo = 0, hi = 0;  // numerically lowest value = greatest priority
+    cudaDeviceGetStreamPriorityRange(&lo, &hi);
+    if (cudaStreamCreateWithPriority(&ctx->stream_hi, cudaStreamNonBlocking, hi) != cudaSuccess) {
+      cudaStreamDestroy(ctx->stream);
+      delete ctx;
+      return PPSFM_ERR_CUDA;
+    }
+    cudaStreamCreateWithPriority(&ctx->stream_copy, cudaStreamNonBlocking, hi);
+    cudaEventCreateWithFlags(&ctx->ev_sync, cudaEventDisableTiming);
+    for (auto& ev : ctx->ev_final) cudaEventCreate(&ev);
+    for (auto& sl : ctx->wave) {
+      for (auto& ev : sl.ev) cudaEventCreate(&ev);
+      cudaStreamCreateWithPriority(&sl.solve_stream, cudaStreamNonBlocking, hi);
+    }
+  }
   {  // keep freed stream-ordered allocations cached in the device pool (BA scratch reuse)
     cudaMemPool_t pool;
     if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -523,6 +678,7 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->stream_hi) cudaStreamSynchronize(ctx->stream_hi);
   ppsfm_comm_destroy(ctx);
   ppsfm::DevBuf* dbufs[] = {&ctx->d_samples, &ctx->d_models, &ctx->d_num_models, &ctx->d_cmodels,
                             &ctx->d_msrc, &ctx->d_K, &ctx->d_part_cnt, &ctx->d_part_sum,
@@ -537,6 +693,27 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
   for (auto* b : pbufs) b->release();
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  for (auto& sl : ctx->wave) {
+    ppsfm::DevBuf* d[] = {&sl.d_samples, &sl.d_models, &sl.d_num_models, &sl.d_off,
+                          &sl.d_part_cnt, &sl.d_cnt};
+    for (auto* b : d) b->release();
+    ppsfm::PinBuf* h[] = {&sl.h_samples, &sl.h_off, &sl.h_cnt};
+    for (auto* b : h) b->release();
+    for (auto& ev : sl.ev)
+      if (ev) cudaEventDestroy(ev);
+    if (sl.solve_stream) cudaStreamDestroy(sl.solve_stream);
+  }
+  if (ctx->ev_sync) cudaEventDestroy(ctx->ev_sync);
+  for (auto& ev : ctx->ev_final)
+    if (ev) cudaEventDestroy(ev);
+  {
+    ppsfm::DevBuf* d[] = {&ctx->d_fmodel, &ctx->d_frbuf, &ctx->d_fmask, &ctx->d_fcnt, &ctx->d_fsum};
+    for (auto* b : d) b->release();
+    ctx->h_fmask.release();
+    ctx->h_fres.release();
+  }
+  if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);
+  if (ctx->stream_copy) cudaStreamDestroy(ctx->stream_copy);
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }

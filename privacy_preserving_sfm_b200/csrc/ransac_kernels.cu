@@ -1,9 +1,10 @@
 // ransac_kernels.cu — sm_100a kernels of the absolute-pose RANSAC path.
 //   * p6l_solve_kernel        one thread per hypothesis (P6L + re3q3)         [A3, A4]
 //   * model_offsets_kernel    exclusive scan of per-trial model counts -> compact model ids
-//   * score_kernel            (32-model group) x (correspondence segment) tiles; correspondence
-//                             tiles are staged in shared memory by the TMA bulk-copy engine
-//                             (cp.async.bulk + mbarrier) and broadcast to the 8 warps   [A5, A8]
+//   * score_kernel            (256-model block) x (correspondence segment) tiles; inlier counts
+//                             through a float filter -> FP64 filter -> reference arithmetic
+//                             cascade; correspondence tiles are staged in shared memory by the
+//                             TMA bulk-copy engine (cp.async.bulk + mbarrier)          [A5, A8]
 //   * reduce_parts_kernel     per-model combination of the per-segment partial supports
 //   * exact_residual_kernel / seq_support_kernel: index-order (reference-order) supports
 //     and inlier mask for the few candidate models that can become "best"
@@ -17,7 +18,6 @@
 
 #include "p6l_device.cuh"
 #include "ransac_kernels.h"
-#include "common.h"
 
 namespace ppsfm {
 
@@ -199,17 +199,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Scoring kernel.  Thread <-> model (12 doubles in registers), warp <-> 32 consecutive compact
-// models, block <-> 8 warps sharing one correspondence segment.  Every lane walks the segment in
-// index order, so each per-segment partial sum is an index-order sum.
+// Scoring kernel.  Thread <-> model, warp <-> 32 consecutive compact models, block <-> 8 warps
+// sharing one correspondence segment; grid = model blocks x segments, per-segment counts are
+// combined by reduce_parts_kernel.
+//
+// Inlier COUNT only: residual sums are needed solely to break count-ties and are then computed in
+// reference (index) order by the exact kernels below.  The count of a (model, correspondence)
+// pair is decided by a cascade of three evaluations, each exact about what it decides:
+//   1. float stage   d_32 = |px l_0 + py l_1 + pz l_2| - r_max pz on float copies, packed FFMA2;
+//                    decides iff |d_32| > band_32                     (all but ~1e-5 of the pairs)
+//   2. FP64 stage    the same d with FMA chains in double; decides iff |d| > band_64
+//   3. reference     src/estimators/utils.cc:64-88 operation by operation (score_one)
+// Stage 3 is the definition of the result; stages 1 and 2 only ever answer where their error
+// bounds prove that stage 3 would answer the same, so the counts are bit-identical to the
+// reference's.  For pz > 0:  |res| <= r_max  <=>  |px l_0 + py l_1 + l_2 pz| <= r_max pz, which
+// needs no division; the bands bound the distance between d and the reference's own
+// (|res| - r_max) pz, rounding and cancellation included (derivations at filter_band_hi and
+// filter32_band_bits).
 // ------------------------------------------------------------------------------------------
 constexpr int kScoreThreads = 256;
-constexpr int kTile = 128;    // correspondences per shared-memory tile (6 KB)
+constexpr int kScoreWarps = kScoreThreads / 32;
 constexpr int kStages = 4;
 
-// Inlier COUNT only: residual sums are needed solely to break count-ties and are then computed
-// in reference (index) order by the exact kernels below.  The two comparisons are done on the
-// bit patterns with integer instructions so that they do not occupy the FP64 pipe:
+// Stage 3.  The two comparisons are done on the bit patterns with integer instructions:
 //   px_2 > DBL_EPSILON        <=>  (int64)bits(px_2) > (int64)bits(eps)     (NaN: see below)
 //   res * res <= max_residual  <=>  bits(|res|) <= bits(r_max)  with r_max the largest double whose
 //                                  rounded square is <= max_residual (rounding is monotone)
@@ -248,246 +260,22 @@ __device__ __forceinline__ void score_one(const double* __restrict__ c, const do
 }
 
 // ------------------------------------------------------------------------------------------
-// Filtered evaluation.  The reference arithmetic above costs ~33 FP64-pipe instructions per
-// (model, correspondence) pair, a third of them in the IEEE division.  The inlier COUNT only needs
-// the sign of |res| - r_max, and for pz > 0
-//     |res| <= r_max   <=>   |px l_0 + py l_1 + l_2 pz| <= r_max pz,
-// so almost every pair can be decided without any division: projections with FMA chains,
-//     d = |fma(l_2, pz, fma(py, l_1, px l_0))| - r_max pz,
-// and a rigorous bound on the difference between d / pz and the reference's |res| - r_max:
-//     band = k0 + k1 pz,   k0 = 2^-40 (B_x + B_y) Lmax,   k1 = 2^-40 (L2max + r_max + B_z (...)),
-// built from per-model sums B_* = sum_k |P_*k| max|X| + |P_*3| and the maxima of the correspondence
-// set (2^-40 leaves a factor > 2^9 over all rounding and cancellation errors of both evaluations).
-// A pair is decided here only if |pz| >= 2^-30 B_z (which settles the cheirality test
-// pz > DBL_EPSILON either way) and, in front of the camera, |d| > band; otherwise — about one pair in 10^8 — the reference arithmetic
-// above decides.  Counts are therefore still bit-identical to the reference; the fast path costs
-// 15 FP64-pipe instructions and no MUFU.
-// ------------------------------------------------------------------------------------------
-struct FastConsts {
-  int zmin_hi;          // high word of the threshold on |pz| (INT_MAX: never use the fast path)
-  double k0, k1;        // band = k0 + k1 pz
-  double rmax;
-};
-
-struct Corr {  // one correspondence, read once from shared memory for all models of the thread
-  double l_0, l_1, l_2, X_0, X_1, X_2;
-};
-__device__ __forceinline__ Corr load_corr(const double* __restrict__ c) {
-  const double2* c2 = reinterpret_cast<const double2*>(c);  // 48-byte records, 16-B aligned
-  const double2 v0 = c2[0], v1 = c2[1], v2 = c2[2];
-  return Corr{v0.x, v0.y, v1.x, v1.y, v2.x, v2.y};
-}
-
-// returns false if the pair could not be decided (the caller then runs the reference arithmetic)
-__device__ __forceinline__ bool score_fast(const Corr& c, const double (&P)[12],
-                                           const FastConsts& fc, unsigned& cnt) {
-  const double pz = fma(P[8], c.X_2, fma(P[5], c.X_1, fma(P[2], c.X_0, P[11])));
-  const double px = fma(P[6], c.X_2, fma(P[3], c.X_1, fma(P[0], c.X_0, P[9])));
-  const double py = fma(P[7], c.X_2, fma(P[4], c.X_1, fma(P[1], c.X_0, P[10])));
-  const double num = fma(c.l_2, pz, fma(py, c.l_1, px * c.l_0));
-  const double d = fabs(num) - fc.rmax * pz;   // pz < 0: d > 0, "not an inlier", as it must be
-  const double band = fma(fc.k1, fabs(pz), fc.k0);
-  // The three tests run on the HIGH words with 32-bit integer compares (strict '>' on the high
-  // words implies '>' on the doubles; the bounds have a factor 2^9 to spare):
-  //   |pz| > zmin (cheirality settled either way),  |d| > band,  |d| finite
-  const int pz_hi = __double2hiint(pz) & 0x7fffffff;
-  const int d_hi = __double2hiint(d);
-  const int ad_hi = d_hi & 0x7fffffff;
-  const bool decided = pz_hi > fc.zmin_hi && ad_hi > __double2hiint(band) && ad_hi < 0x7ff00000;
-  cnt += decided ? ((unsigned)d_hi >> 31) : 0u;  // d < 0: inlier
-  return decided;
-}
-
-// per-model constants of the filter
-__device__ __forceinline__ FastConsts fast_consts(const double (&P)[12], const double* bounds,
-                                                  double r_max, bool live) {
-  FastConsts fc;
-  const double xmax = bounds[0], lmax = bounds[1], l2max = bounds[2];
-  const double bx = (fabs(P[0]) + fabs(P[3]) + fabs(P[6])) * xmax + fabs(P[9]);
-  const double by = (fabs(P[1]) + fabs(P[4]) + fabs(P[7])) * xmax + fabs(P[10]);
-  const double bz = (fabs(P[2]) + fabs(P[5]) + fabs(P[8])) * xmax + fabs(P[11]);
-  // |d_exact - d| <= 8u [(B_x + B_y) Lmax + (L2max + r_max) B_z] (u = 2^-53) for the fused
-  // evaluation, and the reference's |res| - r_max times pz differs from d_exact by at most the
-  // same plus 8u (|num| + r_max pz) <= 16u (...): everything is below
-  //   2^-40 [(B_x + B_y) Lmax + (L2max + r_max) B_z]  +  2^-40 (L2max + r_max) pz
-  const double zmin = bz * 0x1p-30;
-  fc.k0 = ((bx + by) * lmax + (l2max + r_max) * bz) * 0x1p-40;
-  fc.k1 = (l2max + r_max) * 0x1p-40;
-  fc.rmax = r_max;
-  // usable only for normal, finite constants and a non-negative r_max (a negative one means
-  // "nothing is an inlier"); otherwise every pair takes the reference path
-  const bool usable = zmin >= 0x1p-900 && zmin < 0x1p900 && fc.k0 < 0x1p900 && fc.k1 < 0x1p900 &&
-                      r_max >= 0.0 && r_max < DBL_MAX && live;
-  fc.zmin_hi = usable ? __double2hiint(zmin) : 0x7fffffff;
-  return fc;
-}
-
-// Thread <-> kModelsPerThread models (12 doubles each in registers); every correspondence read
-// from shared memory is used for all of them (a broadcast LDS.128 costs four 128-byte wavefronts
-// whatever the number of distinct addresses: 12 wavefronts per correspondence and warp).
-constexpr int kModelsPerThread = 1;  // 2 halves the shared-memory wavefronts but needs 114
-                                     // registers (16 warps / SM): measured slower (3.07 vs 2.74 ms)
-constexpr int kModelsPerCta = kScoreThreads * kModelsPerThread;
-
-__global__ void __launch_bounds__(kScoreThreads)
-score_kernel(const double* __restrict__ corr6, int n, const double* __restrict__ models,
-             const int* __restrict__ offsets, int num_trials, int seg_len, double r_max,
-             int kcap, unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
-  __shared__ __align__(128) double tile[kStages][kTile * 6];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-
-  const int K = offsets[num_trials];
-  const int mbase = blockIdx.x * kModelsPerCta;
-  if (mbase >= K) return;
-  const int seg = blockIdx.y;
-  const int i0 = seg * seg_len;
-  const int i1 = min(n, i0 + seg_len);
-
-  // Locate (trial, m) of compact model k: largest t with offsets[t] <= k.
-  double P[kModelsPerThread][12];
-  int kk[kModelsPerThread];
-#pragma unroll
-  for (int v = 0; v < kModelsPerThread; ++v) {
-    const int k = mbase + v * kScoreThreads + threadIdx.x;
-    kk[v] = k;
-    if (k < K) {
-      int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
-      while (hi - lo > 1) {
-        const int mid = (lo + hi) >> 1;
-        if (offsets[mid] <= k) lo = mid; else hi = mid;
-      }
-      const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
-#pragma unroll
-      for (int j = 0; j < 12; ++j) P[v][j] = src[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < 12; ++j) P[v][j] = 0.0;  // px_2 = 0 -> never counted
-    }
-  }
-
-  const int len = max(0, i1 - i0);
-  const int num_tiles = (len + kTile - 1) / kTile;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) mbar_init(&full_bar[s], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages && s < num_tiles; ++s) {
-      const int cnt_s = min(kTile, len - s * kTile);
-      const uint32_t bytes = (uint32_t)cnt_s * 48u;
-      mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + s * kTile) * 6, bytes, &full_bar[s]);
-    }
-  }
-
-  unsigned cnt[kModelsPerThread];
-  FastConsts fc[kModelsPerThread];
-#pragma unroll
-  for (int v = 0; v < kModelsPerThread; ++v) {
-    cnt[v] = 0;
-    fc[v] = fast_consts(P[v], bounds, r_max, kk[v] < K);
-  }
-  const long long eps_bits = __double_as_longlong(DBL_EPSILON);
-  const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
-  for (int t = 0; t < num_tiles; ++t) {
-    const int s = t % kStages;
-    const uint32_t parity = (uint32_t)((t / kStages) & 1);
-    mbar_wait(&full_bar[s], parity);
-    const int cnt_t = min(kTile, len - t * kTile);
-    const double* tp = &tile[s][0];
-    int j = 0;
-#pragma unroll 1
-    constexpr int kGroup = 4 / kModelsPerThread;  // pairs per unrolled group
-    for (; j + kGroup <= cnt_t; j += kGroup) {
-      unsigned pend = 0;  // undecided (pair, model) combinations of this group (about 1 in 10^8)
-#pragma unroll
-      for (int u = 0; u < kGroup; ++u) {
-        const Corr c = load_corr(tp + (j + u) * 6);
-#pragma unroll
-        for (int v = 0; v < kModelsPerThread; ++v)
-          pend |= score_fast(c, P[v], fc[v], cnt[v]) ? 0u : (1u << (u * kModelsPerThread + v));
-      }
-      if (pend != 0) {
-#pragma unroll
-        for (int b = 0; b < kGroup * kModelsPerThread; ++b)  // (static indices: P stays in registers)
-          if ((pend >> b) & 1u)
-            score_one(tp + (j + b / kModelsPerThread) * 6, P[b % kModelsPerThread], eps_bits,
-                      rmax_bits, cnt[b % kModelsPerThread]);
-      }
-    }
-#pragma unroll 1
-    for (; j < cnt_t; ++j) {
-      const Corr c = load_corr(tp + j * 6);
-#pragma unroll
-      for (int v = 0; v < kModelsPerThread; ++v)
-        if (!score_fast(c, P[v], fc[v], cnt[v]))
-          score_one(tp + j * 6, P[v], eps_bits, rmax_bits, cnt[v]);
-    }
-    __syncthreads();  // everyone is done reading stage s
-    if (threadIdx.x == 0 && t + kStages < num_tiles) {
-      const int tn = t + kStages;
-      const int cnt_n = min(kTile, len - tn * kTile);
-      const uint32_t bytes = (uint32_t)cnt_n * 48u;
-      fence_proxy_async();
-      mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
-    }
-  }
-#pragma unroll
-  for (int v = 0; v < kModelsPerThread; ++v)
-    if (kk[v] < K) part_cnt[(size_t)seg * kcap + kk[v]] = cnt[v];
-}
-
-__global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
-                                    const int* __restrict__ offsets, int num_trials,
-                                    unsigned* __restrict__ cnt_out) {
-  const int K = offsets[num_trials];
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
-  unsigned c = 0;
-  for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + k];
-  cnt_out[k] = c;
-}
-
-// Largest double r with fl(r * r) <= max_residual (host).  IEEE multiplication is monotone, so
-// the predicate is monotone in r and a bisection over the bit patterns of the non-negative doubles
-// finds the boundary in 63 steps — also where r * r underflows (a step-by-step search from
-// sqrt(max_residual) would walk through all denormals for max_residual = 0).
-double inlier_abs_threshold(double max_residual) {
-  if (!(max_residual >= 0.0)) return -1.0;  // nothing is an inlier (bits compare fails)
-  auto ok = [&](unsigned long long bits) {
-    double r;
-    std::memcpy(&r, &bits, sizeof(r));
-    return r * r <= max_residual;
-  };
-  unsigned long long lo = 0, hi = 0x7fefffffffffffffull;  // +0 .. DBL_MAX; ok(lo) always holds
-  if (ok(hi)) return DBL_MAX;
-  while (hi - lo > 1) {
-    const unsigned long long mid = lo + (hi - lo) / 2;
-    if (ok(mid)) lo = mid; else hi = mid;
-  }
-  double r;
-  std::memcpy(&r, &lo, sizeof(r));
-  return r;
-}
-
-// ------------------------------------------------------------------------------------------
-// Scoring kernel, second form.  Differences from score_kernel above (kept for A/B timing):
-//   * the band is a per-model CONSTANT, k0 + k1 B_z + r_max 2^-50 >= k0 + k1 |pz|, and the test on
-//     |pz| is gone: a pair is decided iff |d| > band.  "Not an inlier" (d > band) is then right
-//     whichever way the reference's cheirality test px_2 > DBL_EPSILON falls, because a failed
-//     test also means "not counted"; "inlier" (d < -band) implies r_max pz > band, hence
-//     pz > 2^-50 + 2^-39 B_z, and the reference's own px_2 (within 2^-50 B_z of pz) is above
-//     DBL_EPSILON = 2^-52.  No overflow test either: the per-model constants are only usable when
-//     every intermediate is bounded by 2^940.
-//   * 13 FP64-pipe instructions per pair (9 projection FMAs, 3 for the numerator, 1 for d), one
-//     LOP + one chained ISETP + one LEA.HI of integer work; the group's predicate is tested once
-//     and a failed group is redone pair by pair (filter, then reference arithmetic).
-//   * no CTA-wide barrier in the tile loop: every warp counts itself off on a shared-memory
-//     counter when it is done with a stage and the last one re-arms the stage's TMA copy, so the
-//     warps of a CTA drift apart by up to kStages tiles instead of meeting every 128
-//     correspondences in the same phase of the instruction stream.
+// Stage 2: FP64 filter.  Projections and numerator with FMA chains,
+//     d = fma(-r_max, pz, |fma(l_2, pz, fma(py, l_1, px l_0))|),
+// 13 FP64-pipe instructions and no division (the reference arithmetic costs ~33, a third of them
+// in the IEEE division).  Per model, with B_* = sum_k |P_*k| max|X| + |P_*3| and the maxima of the
+// correspondence set (pack_corr_kernel):
+//     S = (B_x + B_y) Lmax + (L2max + r_max) B_z  >=  |num| + r_max |pz|,
+//     band_64 = 2^-40 (S + (L2max + r_max) B_z) + 2^-50 r_max.
+// The fused d and the reference's own (|res| - r_max) px_2 each carry at most ~16 roundings of
+// relative size 2^-53 on terms bounded by S, so they differ by less than 2^-48 S: the 2^-40 leaves
+// a factor > 2^7.  A pair is decided iff |d| > band_64 (compared on the high words):
+//   * "not an inlier" (d > band) is right whichever way the reference's cheirality test
+//     px_2 > DBL_EPSILON falls, because a failed test also means "not counted";
+//   * "inlier" (d < -band) implies r_max pz > band, hence pz > 2^-50 + 2^-39 B_z, and the
+//     reference's own px_2 (within 2^-50 B_z of pz) is above DBL_EPSILON = 2^-52.
+// No overflow test: the constants are only usable when every intermediate is below 2^940, and
+// r_max = DBL_MAX ("count everything", see kAllInliers) or a negative / NaN r_max disable it.
 // ------------------------------------------------------------------------------------------
 __device__ __forceinline__ int filter_band_hi(const double (&P)[12], const double* bounds,
                                               double r_max, bool live) {
@@ -502,151 +290,8 @@ __device__ __forceinline__ int filter_band_hi(const double (&P)[12], const doubl
   return usable ? __double2hiint(band) : 0x7fffffff;
 }
 
-template <int OFF>
-__device__ __forceinline__ void lds_f64x2(uint32_t addr, double& a, double& b) {
-  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+%3];" : "=d"(a), "=d"(b) : "r"(addr), "n"(OFF));
-}
-
-// d = |px l_0 + py l_1 + pz l_2| - r_max pz for the correspondence at shared address addr + OFF
-template <int OFF>
-__device__ __forceinline__ int filter_d_hi(uint32_t addr, const double (&P)[12], double neg_rmax) {
-  double l_0, l_1, l_2, X_0, X_1, X_2;
-  lds_f64x2<OFF>(addr, l_0, l_1);
-  lds_f64x2<OFF + 16>(addr, l_2, X_0);
-  lds_f64x2<OFF + 32>(addr, X_1, X_2);
-  const double pz = fma(P[8], X_2, fma(P[5], X_1, fma(P[2], X_0, P[11])));
-  const double px = fma(P[6], X_2, fma(P[3], X_1, fma(P[0], X_0, P[9])));
-  const double py = fma(P[7], X_2, fma(P[4], X_1, fma(P[1], X_0, P[10])));
-  const double num = fma(l_2, pz, fma(py, l_1, px * l_0));
-  return __double2hiint(fma(neg_rmax, pz, fabs(num)));
-}
-
-template <int G, int U = 0>
-__device__ __forceinline__ void filter_group(uint32_t addr, const double (&P)[12], double neg_rmax,
-                                             int band_hi, bool& ok, unsigned& gcnt) {
-  if constexpr (U < G) {
-    const int d_hi = filter_d_hi<U * 48>(addr, P, neg_rmax);
-    ok = ok && (d_hi & 0x7fffffff) > band_hi;
-    gcnt += (unsigned)d_hi >> 31;  // d < 0: inlier
-    filter_group<G, U + 1>(addr, P, neg_rmax, band_hi, ok, gcnt);
-  }
-}
-
-// one pair, filter first and the reference arithmetic if undecided (rare path, not unrolled)
-__device__ __forceinline__ void score_checked(uint32_t addr, const double* __restrict__ c,
-                                              const double (&P)[12], double neg_rmax, int band_hi,
-                                              long long eps_bits, unsigned long long rmax_bits,
-                                              unsigned& cnt) {
-  const int d_hi = filter_d_hi<0>(addr, P, neg_rmax);
-  if ((d_hi & 0x7fffffff) > band_hi) cnt += (unsigned)d_hi >> 31;
-  else score_one(c, P, eps_bits, rmax_bits, cnt);
-}
-
-constexpr int kScoreWarps = kScoreThreads / 32;
-
-template <int G, int MINB>
-__global__ void __launch_bounds__(kScoreThreads, MINB)
-score_kernel_v2(const double* __restrict__ corr6, int n, const double* __restrict__ models,
-                const int* __restrict__ offsets, int num_trials, int seg_len, double r_max,
-                int kcap, unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
-  __shared__ __align__(128) double tile[kStages][kTile * 6];
-  __shared__ __align__(8) uint64_t full_bar[kStages];
-  __shared__ unsigned done[kStages];   // warps that have finished with the stage
-
-  const int K = offsets[num_trials];
-  const int mbase = blockIdx.x * kScoreThreads;
-  if (mbase >= K) return;
-  const int seg = blockIdx.y;
-  const int i0 = seg * seg_len;
-  const int i1 = min(n, i0 + seg_len);
-
-  double P[12];
-  const int k = mbase + threadIdx.x;
-  if (k < K) {
-    int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (offsets[mid] <= k) lo = mid; else hi = mid;
-    }
-    const double* src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
-#pragma unroll
-    for (int j = 0; j < 12; ++j) P[j] = src[j];
-  } else {
-#pragma unroll
-    for (int j = 0; j < 12; ++j) P[j] = 0.0;
-  }
-
-  const int len = max(0, i1 - i0);
-  const int num_tiles = (len + kTile - 1) / kTile;
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      done[s] = 0;
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages && s < num_tiles; ++s) {
-      const uint32_t bytes = (uint32_t)min(kTile, len - s * kTile) * 48u;
-      mbar_arrive_expect_tx(&full_bar[s], bytes);
-      bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + s * kTile) * 6, bytes, &full_bar[s]);
-    }
-  }
-
-  const int band_hi = filter_band_hi(P, bounds, r_max, k < K);
-  const double neg_rmax = -r_max;
-  const long long eps_bits = __double_as_longlong(DBL_EPSILON);
-  const unsigned long long rmax_bits = (unsigned long long)__double_as_longlong(r_max);
-  const uint32_t tile_addr = smem_u32(&tile[0][0]);
-  unsigned cnt = 0;
-  for (int t = 0; t < num_tiles; ++t) {
-    const int s = t % kStages;
-    mbar_wait(&full_bar[s], (uint32_t)((t / kStages) & 1));
-    const int cnt_t = min(kTile, len - t * kTile);
-    const double* tp = &tile[s][0];
-    const uint32_t ta = tile_addr + (uint32_t)s * (kTile * 48);
-    int j = 0;
-#pragma unroll 1
-    for (; j + G <= cnt_t; j += G) {
-      bool ok = true;
-      unsigned gcnt = 0;
-      filter_group<G>(ta + (uint32_t)j * 48u, P, neg_rmax, band_hi, ok, gcnt);
-      if (ok) {
-        cnt += gcnt;
-      } else {  // some pair of the group is undecided (about one pair in 10^8)
-#pragma unroll 1
-        for (int u = 0; u < G; ++u)
-          score_checked(ta + (uint32_t)(j + u) * 48u, tp + (j + u) * 6, P, neg_rmax, band_hi,
-                        eps_bits, rmax_bits, cnt);
-      }
-    }
-#pragma unroll 1
-    for (; j < cnt_t; ++j)
-      score_checked(ta + (uint32_t)j * 48u, tp + j * 6, P, neg_rmax, band_hi, eps_bits, rmax_bits,
-                    cnt);
-    // this warp is done with stage s; the last warp of the CTA to get here refills it
-    __syncwarp();
-    if ((threadIdx.x & 31) == 0) {
-      __threadfence_block();
-      if (atomicAdd(&done[s], 1u) == kScoreWarps - 1) {
-        done[s] = 0;
-        const int tn = t + kStages;
-        if (tn < num_tiles) {
-          const uint32_t bytes = (uint32_t)min(kTile, len - tn * kTile) * 48u;
-          __threadfence_block();
-          fence_proxy_async();
-          mbar_arrive_expect_tx(&full_bar[s], bytes);
-          bulk_copy_g2s(&tile[s][0], corr6 + (size_t)(i0 + tn * kTile) * 6, bytes, &full_bar[s]);
-        }
-      }
-    }
-  }
-  if (k < K) part_cnt[(size_t)seg * kcap + k] = cnt;
-}
-
 // ------------------------------------------------------------------------------------------
-// Scoring kernel, third form: a FLOAT first stage in front of the FP64 filter.
+// Stage 1: float filter, and the kernel.
 //
 // The sign of d = |px l_0 + py l_1 + pz l_2| - r_max pz is all the count needs, and for all but a
 // few pairs in a million it is already certain in single precision.  The first stage evaluates d
@@ -662,9 +307,17 @@ score_kernel_v2(const double* __restrict__ corr6, int n, const double* __restric
 //   inputs are below 2^40 in magnitude, so that an absolute error of 2^-150 (input or
 //   intermediate flushed / rounded in the subnormal range) reaches d with a factor < 2^80.
 // Everything else — a group in which some pair is undecided, models or sets outside the float
-// range — goes through score_slow: the FP64 filter and then the reference arithmetic, on the
-// double correspondences read from global memory (L2-resident), with the model reloaded from
-// global memory so that the hot loop carries only the float model.
+// range — goes through score_slow: stages 2 and 3 on the double correspondences read from global
+// memory (L2-resident), with the model reloaded from global memory so that the hot loop carries
+// only the float model.
+//
+// Correspondence records (48 B, two correspondences) are staged in shared memory by the TMA bulk
+// copy engine (cp.async.bulk + mbarrier), kStages tiles deep.  There is no CTA-wide barrier in the
+// tile loop: every warp counts itself off on a shared-memory counter when it is done with a stage
+// and the last one re-arms the stage's copy, so the warps of a CTA drift apart by up to kStages
+// tiles instead of meeting every tile in the same phase of the instruction stream.
+// Measured on the bench workload (1.9e9 pairs): reference arithmetic with TMA tiles 3.79 ms,
+// + FP64 filter 2.03 ms, + float stage 1.11 ms (profiles/r01_s3_score_variants_*.txt).
 // ------------------------------------------------------------------------------------------
 constexpr int kTileR = 128;  // float records (= 256 correspondences, 6 KB) per stage
 
@@ -748,7 +401,7 @@ __device__ __noinline__ unsigned score_slow(const double* __restrict__ c, int co
 
 template <int G, int MINB>
 __global__ void __launch_bounds__(kScoreThreads, MINB)
-score_kernel_v3(const double* __restrict__ corr6, const float* __restrict__ corr6f, int n,
+score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f, int n,
                 const double* __restrict__ models, const int* __restrict__ offsets,
                 int num_trials, int seg_len, double r_max, int kcap,
                 unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
@@ -854,40 +507,50 @@ score_kernel_v3(const double* __restrict__ corr6, const float* __restrict__ corr
   }
 }
 
+__global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
+                                    const int* __restrict__ offsets, int num_trials,
+                                    unsigned* __restrict__ cnt_out) {
+  const int K = offsets[num_trials];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= K) return;
+  unsigned c = 0;
+  for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + k];
+  cnt_out[k] = c;
+}
+
+// Largest double r with fl(r * r) <= max_residual (host).  IEEE multiplication is monotone, so
+// the predicate is monotone in r and a bisection over the bit patterns of the non-negative doubles
+// finds the boundary in 63 steps — also where r * r underflows (a step-by-step search from
+// sqrt(max_residual) would walk through all denormals for max_residual = 0).
+double inlier_abs_threshold(double max_residual) {
+  if (!(max_residual >= 0.0)) return -1.0;  // nothing is an inlier (bits compare fails)
+  auto ok = [&](unsigned long long bits) {
+    double r;
+    std::memcpy(&r, &bits, sizeof(r));
+    return r * r <= max_residual;
+  };
+  unsigned long long lo = 0, hi = 0x7fefffffffffffffull;  // +0 .. DBL_MAX; ok(lo) always holds
+  if (ok(hi)) return DBL_MAX;
+  while (hi - lo > 1) {
+    const unsigned long long mid = lo + (hi - lo) / 2;
+    if (ok(mid)) lo = mid; else hi = mid;
+  }
+  double r;
+  std::memcpy(&r, &lo, sizeof(r));
+  return r;
+}
+
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
                   const double* models, const int* offsets, int num_trials, int num_segs,
                   int seg_len, double max_residual, int kcap, unsigned* part_cnt,
                   unsigned* cnt_out, cudaStream_t s) {
   if (num_trials <= 0) return;
   const double r_max = inlier_abs_threshold(max_residual);
-  dim3 grid((kcap + kModelsPerCta - 1) / kModelsPerCta, num_segs);
-#define PPSFM_SCORE_V2(G, MINB)                                                                \
-  score_kernel_v2<G, MINB><<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, \
-                                                          seg_len, r_max, kcap, part_cnt, bounds)
-#define PPSFM_SCORE_V3(G, MINB)                                                              \
-  score_kernel_v3<G, MINB><<<grid, kScoreThreads, 0, s>>>(corr6, corr6f, n, models, offsets, \
-                                                          num_trials, seg_len, r_max, kcap,  \
-                                                          part_cnt, bounds)
-  switch (tune_int("PPSFM_SCORE_VARIANT", 13)) {
-    case 0:
-      score_kernel<<<grid, kScoreThreads, 0, s>>>(corr6, n, models, offsets, num_trials, seg_len,
-                                                  r_max, kcap, part_cnt, bounds);
-      break;
-    case 2: PPSFM_SCORE_V2(8, 2); break;
-    case 4: PPSFM_SCORE_V2(8, 3); break;
-    case 5: PPSFM_SCORE_V2(4, 4); break;
-    case 10: PPSFM_SCORE_V3(2, 2); break;
-    case 11: PPSFM_SCORE_V3(4, 2); break;
-    case 12: PPSFM_SCORE_V3(2, 3); break;
-    case 13: PPSFM_SCORE_V3(4, 3); break;
-    case 14: PPSFM_SCORE_V3(2, 4); break;
-    case 15: PPSFM_SCORE_V3(4, 4); break;
-    case 16: PPSFM_SCORE_V3(8, 2); break;
-    case 17: PPSFM_SCORE_V3(1, 4); break;
-    default: PPSFM_SCORE_V2(4, 2); break;
-  }
-#undef PPSFM_SCORE_V2
-#undef PPSFM_SCORE_V3
+  dim3 grid((kcap + kScoreThreads - 1) / kScoreThreads, num_segs);
+  // 4 records (8 correspondences) per unrolled group, 3 CTAs per SM (80 registers): the best of
+  // the (group, occupancy) variants measured, profiles/r01_s3_score_variants_float_stage.txt
+  score_kernel<4, 3><<<grid, kScoreThreads, 0, s>>>(corr6, corr6f, n, models, offsets, num_trials,
+                                                    seg_len, r_max, kcap, part_cnt, bounds);
   reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
                                                          num_trials, cnt_out);
 }
