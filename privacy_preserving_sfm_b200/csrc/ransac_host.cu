@@ -178,11 +178,16 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   const size_t kWaveFloor = 1024;
   const size_t kWaveCap = 1u << 17;
   const size_t kChunks = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", 4));
+  const size_t kFirst = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_FIRST", 3));
+  const size_t kGrowth = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_GROWTH", 100));
   size_t t_issue = 0;      // first trial not yet issued
   size_t plan_end = 0, plan_chunk = 0;
-  // Wave sizes grow geometrically inside a plan (x3 from a tenth of the span): the first wave is
-  // the only one whose sampling and solve latency nothing can hide, and the scoring of each wave
-  // has to cover the solve latency of the next.  PPSFM_RANSAC_CHUNKS=1 keeps the plan whole.
+  // A plan is cut into a first wave of a third of its trials and a second wave with the rest: the
+  // first wave's sampling and solve latency is the one thing nothing can hide, and its scoring has
+  // to cover the solve latency of the second.  Measured on the bench workload (scripts/
+  // plan_sweep.sh; first fraction 1/N, growth factor of the following waves): 1/3 + rest 1.74 ms
+  // per call, 1/8 x2 1.79, 1/10 x3 1.81, 1/5 x4 1.91, whole plan 1.95.  PPSFM_RANSAC_CHUNKS=1 keeps
+  // the plan whole; PPSFM_RANSAC_FIRST / PPSFM_RANSAC_GROWTH change the shape.
   auto next_wave_range = [&](size_t* t_end_out) {
     if (t_issue >= plan_end) {
       size_t want_end = std::max<size_t>(opt.min_num_trials, t_issue + kWaveFloor);
@@ -191,11 +196,11 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       plan_end = std::min(max_num_trials, want_end);
       const size_t span = plan_end - t_issue;
       plan_chunk = kChunks <= 1 ? kWaveCap
-                                : std::min(kWaveCap, std::max(kWaveFloor, (span / 10 + 255) / 256 * 256));
+                                : std::min(kWaveCap, std::max(kWaveFloor, (span / kFirst + 255) / 256 * 256));
     }
     size_t t_end = std::min(plan_end, t_issue + plan_chunk);
     if (plan_end - t_end < plan_chunk) t_end = std::min(plan_end, t_issue + kWaveCap);
-    plan_chunk = std::min(kWaveCap, plan_chunk * 3);
+    plan_chunk = std::min(kWaveCap, plan_chunk * kGrowth);
     *t_end_out = t_end;
   };
 
