@@ -72,10 +72,11 @@ float EventMs(cudaEvent_t a, cudaEvent_t b) {
 
 }  // namespace
 
-// Chooses the segment count so that the scoring grid is a few waves of 148 x 4 resident CTAs.
-static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap_blocks, int* num_segs,
-                           int* seg_len) {
-  const int resident = ctx->num_sms * 4;
+// Chooses the segment count so that the scoring grid is a few waves of the resident CTAs
+// (148 SMs x kScoreCtasPerSm); kcap = model capacity (8 per trial).
+static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap, int* num_segs, int* seg_len) {
+  const int kcap_blocks = (kcap + ppsfm::kScoreModelsPerCta - 1) / ppsfm::kScoreModelsPerCta;
+  const int resident = ctx->num_sms * ppsfm::kScoreCtasPerSm;
   int target_blocks = resident * 4;
   int segs = (target_blocks + kcap_blocks - 1) / std::max(1, kcap_blocks);
   // model blocks beyond K exit immediately; on average half the capacity is live.
@@ -180,6 +181,16 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   const size_t kChunks = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", 4));
   const size_t kFirst = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_FIRST", 3));
   const size_t kGrowth = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_GROWTH", 100));
+  // Hypotheses per warp of the solve kernel: as few as keep all warps resident at once (the
+  // kernel needs 254 registers: 8 warps per SM; 6 leaves room beside a scoring CTA).  Measured on
+  // the bench workload: 8 lanes 0.28 ms per wave, 32 lanes 0.31 ms.
+  const int kSolveLanes = ppsfm::tune_int("PPSFM_SOLVE_LANES", 0);
+  auto solve_lanes = [&](int H) {
+    if (kSolveLanes > 0) return kSolveLanes;
+    int lanes = 8;
+    while (lanes < 32 && (H + lanes - 1) / lanes > ctx->num_sms * 6) lanes *= 2;
+    return lanes;
+  };
   size_t t_issue = 0;      // first trial not yet issued
   size_t plan_end = 0, plan_chunk = 0;
   // A plan is cut into a first wave of a third of its trials and a second wave with the rest: the
@@ -220,7 +231,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, sl.d_num_models.reserve(sizeof(int) * (size_t)H));
     PPSFM_CUDA(ctx, sl.d_off.reserve(sizeof(int) * ((size_t)H + 1)));
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);  // 256 models per CTA
+    ChooseSegments(ctx, (int)n, kcap, &num_segs, &seg_len);
     PPSFM_CUDA(ctx, sl.d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
     PPSFM_CUDA(ctx, sl.d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
     PPSFM_CUDA(ctx, sl.h_off.reserve(sizeof(int) * ((size_t)H + 1)));
@@ -230,7 +241,8 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
                                     cudaMemcpyHostToDevice, hs_stream));
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[0], hs_stream));
     launch_p6l_solve(corr->corr6, corr->aligned, sl.d_samples.as<uint32_t>(), H,
-                     sl.d_models.as<double>(), sl.d_num_models.as<int>(), hs_stream);
+                     sl.d_models.as<double>(), sl.d_num_models.as<int>(), hs_stream,
+                     solve_lanes(H));
     launch_model_offsets(sl.d_num_models.as<int>(), H, sl.d_off.as<int>(), hs_stream);
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[1], hs_stream));
     // ---- score on the main stream, results to the host
@@ -889,7 +901,7 @@ int ppsfm_score_models(ppsfm_ctx* ctx, const double* lines, const double* points
     }
     hoff[H] = H;
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, (kcap + 255) / 256, &num_segs, &seg_len);
+    ChooseSegments(ctx, (int)n, kcap, &num_segs, &seg_len);
     PPSFM_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * hm.size()));
     PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
     PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));

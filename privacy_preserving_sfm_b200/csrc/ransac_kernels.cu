@@ -11,6 +11,7 @@
 //
 // Compiled with --fmad=false: every FP64 operation rounds separately, in the order the reference
 // evaluates it (src/estimators/utils.cc:64-88), so residuals, masks and supports are bit-exact.
+#include <algorithm>
 #include <cfloat>
 #include <cstring>
 #include <cmath>
@@ -79,8 +80,16 @@ void launch_pack_corr(const double* lines, const double* points, size_t n, doubl
 __global__ void __launch_bounds__(64)
 p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ aligned,
                  const uint32_t* __restrict__ samples, int num_trials,
-                 double* __restrict__ models_out, int* __restrict__ num_models_out) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+                 double* __restrict__ models_out, int* __restrict__ num_models_out,
+                 int lanes_per_warp) {
+  // Only the first `lanes_per_warp` lanes of a warp take a hypothesis: the solver's data-dependent
+  // loops (QR iterations, root polishing) diverge between lanes, and the kernel is latency-bound
+  // with the SMs nearly empty, so spreading the hypotheses over more warps shortens every warp's
+  // instruction stream at no cost.
+  const int lane = threadIdx.x & 31;
+  if (lane >= lanes_per_warp) return;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int t = warp * lanes_per_warp + lane;
   if (t >= num_trials) return;
   double lines[6][3], points[6][3];
   bool all_aligned = true;
@@ -101,11 +110,14 @@ p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ a
 }
 
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
-                      int num_trials, double* models_out, int* num_models_out, cudaStream_t s) {
+                      int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
+                      int lanes_per_warp) {
   if (num_trials <= 0) return;
   const int threads = 64;
-  p6l_solve_kernel<<<(num_trials + threads - 1) / threads, threads, 0, s>>>(
-      corr6, aligned, samples, num_trials, models_out, num_models_out);
+  const int lanes = std::max(1, std::min(32, lanes_per_warp));
+  const int warps = (num_trials + lanes - 1) / lanes;
+  p6l_solve_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, s>>>(
+      corr6, aligned, samples, num_trials, models_out, num_models_out, lanes);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -199,9 +211,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Scoring kernel.  Thread <-> model, warp <-> 32 consecutive compact models, block <-> 8 warps
-// sharing one correspondence segment; grid = model blocks x segments, per-segment counts are
-// combined by reduce_parts_kernel.
+// Scoring kernel.  Thread <-> M models (k, k + 256, ...), warp <-> 32 consecutive compact models
+// per slot, block <-> 8 warps sharing one correspondence segment; grid = model blocks x segments,
+// per-segment counts are combined by reduce_parts_kernel.
 //
 // Inlier COUNT only: residual sums are needed solely to break count-ties and are then computed in
 // reference (index) order by the exact kernels below.  The count of a (model, correspondence)
@@ -349,26 +361,31 @@ __device__ __forceinline__ float4 lds_f32x4(uint32_t addr) {
   return v;
 }
 
-template <int G, int U = 0>
-__device__ __forceinline__ void filter32_group(uint32_t addr, const float2 (&Pf)[12], float2 nr,
-                                               int band, bool& ok, unsigned& gcnt) {
+template <int G, int M, int U = 0>
+__device__ __forceinline__ void filter32_group(uint32_t addr, const float2 (&Pf)[M][12], float2 nr,
+                                               const int (&band)[M], bool (&ok)[M],
+                                               unsigned (&gcnt)[M]) {
   if constexpr (U < G) {
     const float4 v0 = lds_f32x4<U * 48>(addr), v1 = lds_f32x4<U * 48 + 16>(addr),
                  v2 = lds_f32x4<U * 48 + 32>(addr);
     const float2 l_0 = make_float2(v0.x, v0.y), l_1 = make_float2(v0.z, v0.w);
     const float2 l_2 = make_float2(v1.x, v1.y), X_0 = make_float2(v1.z, v1.w);
     const float2 X_1 = make_float2(v2.x, v2.y), X_2 = make_float2(v2.z, v2.w);
-    const float2 pz = __ffma2_rn(Pf[8], X_2, __ffma2_rn(Pf[5], X_1, __ffma2_rn(Pf[2], X_0, Pf[11])));
-    const float2 px = __ffma2_rn(Pf[6], X_2, __ffma2_rn(Pf[3], X_1, __ffma2_rn(Pf[0], X_0, Pf[9])));
-    const float2 py = __ffma2_rn(Pf[7], X_2, __ffma2_rn(Pf[4], X_1, __ffma2_rn(Pf[1], X_0, Pf[10])));
-    float2 num = __ffma2_rn(l_2, pz, __ffma2_rn(py, l_1, __fmul2_rn(px, l_0)));
-    num.x = fabsf(num.x);
-    num.y = fabsf(num.y);
-    const float2 d = __ffma2_rn(nr, pz, num);
-    const int da = __float_as_int(d.x), db = __float_as_int(d.y);
-    ok = ok && (da & 0x7fffffff) > band && (db & 0x7fffffff) > band;
-    gcnt += ((unsigned)da >> 31) + ((unsigned)db >> 31);  // d < 0: inlier
-    filter32_group<G, U + 1>(addr, Pf, nr, band, ok, gcnt);
+#pragma unroll
+    for (int m = 0; m < M; ++m) {  // the record is read once for the thread's M models
+      const float2(&P)[12] = Pf[m];
+      const float2 pz = __ffma2_rn(P[8], X_2, __ffma2_rn(P[5], X_1, __ffma2_rn(P[2], X_0, P[11])));
+      const float2 px = __ffma2_rn(P[6], X_2, __ffma2_rn(P[3], X_1, __ffma2_rn(P[0], X_0, P[9])));
+      const float2 py = __ffma2_rn(P[7], X_2, __ffma2_rn(P[4], X_1, __ffma2_rn(P[1], X_0, P[10])));
+      float2 num = __ffma2_rn(l_2, pz, __ffma2_rn(py, l_1, __fmul2_rn(px, l_0)));
+      num.x = fabsf(num.x);
+      num.y = fabsf(num.y);
+      const float2 d = __ffma2_rn(nr, pz, num);
+      const int da = __float_as_int(d.x), db = __float_as_int(d.y);
+      ok[m] = ok[m] && (da & 0x7fffffff) > band[m] && (db & 0x7fffffff) > band[m];
+      gcnt[m] += ((unsigned)da >> 31) + ((unsigned)db >> 31);  // d < 0: inlier
+    }
+    filter32_group<G, M, U + 1>(addr, Pf, nr, band, ok, gcnt);
   }
 }
 
@@ -399,18 +416,18 @@ __device__ __noinline__ unsigned score_slow(const double* __restrict__ c, int co
   return cnt;
 }
 
-template <int G, int MINB>
+template <int G, int M, int MINB>
 __global__ void __launch_bounds__(kScoreThreads, MINB)
 score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f, int n,
-                const double* __restrict__ models, const int* __restrict__ offsets,
-                int num_trials, int seg_len, double r_max, int kcap,
-                unsigned* __restrict__ part_cnt, const double* __restrict__ bounds) {
+             const double* __restrict__ models, const int* __restrict__ offsets, int num_trials,
+             int seg_len, double r_max, int kcap, unsigned* __restrict__ part_cnt,
+             const double* __restrict__ bounds) {
   __shared__ __align__(128) float tile[kStages][kTileR * 12];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ unsigned done[kStages];  // warps that have finished with the stage
 
   const int K = offsets[num_trials];
-  const int mbase = blockIdx.x * kScoreThreads;
+  const int mbase = blockIdx.x * (kScoreThreads * M);
   if (mbase >= K) return;
   const int seg = blockIdx.y;
   const int i0 = seg * seg_len;  // even: seg_len is a multiple of 128
@@ -420,30 +437,33 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
   const int num_tiles = (nrec + kTileR - 1) / kTileR;
   const float* recs = corr6f + (size_t)(i0 >> 1) * 12;
 
-  const int k = mbase + threadIdx.x;
-  const double* src = nullptr;
-  float2 Pf[12];
-  int band = -1;
-  {
+  // thread <-> models mbase + m * 256 + tid, m < M
+  const double* src[M];
+  float2 Pf[M][12];
+  int band[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    const int k = mbase + m * kScoreThreads + threadIdx.x;
     double P[12];
+    src[m] = nullptr;
     if (k < K) {
       int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
         if (offsets[mid] <= k) lo = mid; else hi = mid;
       }
-      src = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
+      src[m] = models + (size_t)lo * 96 + (size_t)(k - offsets[lo]) * 12;
 #pragma unroll
-      for (int j = 0; j < 12; ++j) P[j] = src[j];
+      for (int j = 0; j < 12; ++j) P[j] = src[m][j];
     } else {
 #pragma unroll
       for (int j = 0; j < 12; ++j) P[j] = 0.0;
     }
-    band = filter32_band_bits(P, bounds, r_max, k < K);
+    band[m] = filter32_band_bits(P, bounds, r_max, k < K);
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
       const float f = __double2float_rn(P[j]);
-      Pf[j] = make_float2(f, f);
+      Pf[m][j] = make_float2(f, f);
     }
   }
   const float nrf = -__double2float_rn(r_max);
@@ -466,7 +486,9 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
   }
 
   const uint32_t tile_addr = smem_u32(&tile[0][0]);
-  unsigned cnt = 0;
+  unsigned cnt[M];
+#pragma unroll
+  for (int m = 0; m < M; ++m) cnt[m] = 0;
   for (int t = 0; t < num_tiles; ++t) {
     const int s = t % kStages;
     mbar_wait(&full_bar[s], (uint32_t)((t / kStages) & 1));
@@ -476,14 +498,26 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
     int j = 0;
 #pragma unroll 1
     for (; j + G <= cnt_t; j += G) {
-      bool ok = true;
-      unsigned gcnt = 0;
-      filter32_group<G>(ta + (uint32_t)j * 48u, Pf, nr, band, ok, gcnt);
-      if (ok) cnt += gcnt;
-      else cnt += score_slow(gc + (size_t)j * 12, 2 * G, src, bounds, r_max);
+      bool ok[M];
+      unsigned gcnt[M];
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        ok[m] = true;
+        gcnt[m] = 0;
+      }
+      filter32_group<G, M>(ta + (uint32_t)j * 48u, Pf, nr, band, ok, gcnt);
+#pragma unroll
+      for (int m = 0; m < M; ++m) {
+        if (ok[m]) cnt[m] += gcnt[m];
+        else cnt[m] += score_slow(gc + (size_t)j * 12, 2 * G, src[m], bounds, r_max);
+      }
     }
-    if (j < cnt_t && src != nullptr)  // ragged end of the set
-      cnt += score_slow(gc + (size_t)j * 12, 2 * (cnt_t - j), src, bounds, r_max);
+    if (j < cnt_t) {  // ragged end of the set
+#pragma unroll
+      for (int m = 0; m < M; ++m)
+        if (src[m] != nullptr)
+          cnt[m] += score_slow(gc + (size_t)j * 12, 2 * (cnt_t - j), src[m], bounds, r_max);
+    }
     // this warp is done with stage s; the last warp of the CTA to get here refills it
     __syncwarp();
     if ((threadIdx.x & 31) == 0) {
@@ -501,9 +535,12 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
       }
     }
   }
-  if (k < K) {
-    if (len & 1) cnt += score_slow(corr6 + (size_t)(i1 - 1) * 6, 1, src, bounds, r_max);
-    part_cnt[(size_t)seg * kcap + k] = cnt;
+#pragma unroll
+  for (int m = 0; m < M; ++m) {
+    if (src[m] != nullptr) {
+      if (len & 1) cnt[m] += score_slow(corr6 + (size_t)(i1 - 1) * 6, 1, src[m], bounds, r_max);
+      part_cnt[(size_t)seg * kcap + mbase + m * kScoreThreads + threadIdx.x] = cnt[m];
+    }
   }
 }
 
@@ -546,11 +583,14 @@ void launch_score(const double* corr6, const float* corr6f, const double* bounds
                   unsigned* cnt_out, cudaStream_t s) {
   if (num_trials <= 0) return;
   const double r_max = inlier_abs_threshold(max_residual);
-  dim3 grid((kcap + kScoreThreads - 1) / kScoreThreads, num_segs);
-  // 4 records (8 correspondences) per unrolled group, 3 CTAs per SM (80 registers): the best of
-  // the (group, occupancy) variants measured, profiles/r01_s3_score_variants_float_stage.txt
-  score_kernel<4, 3><<<grid, kScoreThreads, 0, s>>>(corr6, corr6f, n, models, offsets, num_trials,
-                                                    seg_len, r_max, kcap, part_cnt, bounds);
+  // 4 records (8 correspondences) per unrolled group, 2 models per thread (every record read
+  // from shared memory serves both), 2 CTAs per SM (100 registers): the best of the (group,
+  // models per thread, occupancy) variants measured on the bench workload — (4,2,2) 1.085 ms,
+  // (4,1,3) 1.126, (2,2,2) 1.131, (2,2,3) 1.254, (1,3,2) 1.341, (1,2,3) 1.363, (1,2,4) 2.180.
+  constexpr int kG = 4, kM = kScoreModelsPerCta / kScoreThreads, kMinB = kScoreCtasPerSm;
+  const dim3 grid((kcap + kScoreThreads * kM - 1) / (kScoreThreads * kM), num_segs);
+  score_kernel<kG, kM, kMinB><<<grid, kScoreThreads, 0, s>>>(
+      corr6, corr6f, n, models, offsets, num_trials, seg_len, r_max, kcap, part_cnt, bounds);
   reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
                                                          num_trials, cnt_out);
 }

@@ -11,9 +11,15 @@ namespace ppsfm {
 // corr6f (device, ceil(n/2) x 12 floats): the set rounded to float, two correspondences per record
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
                       float* corr6f, double* bounds, cudaStream_t s);
+// lanes_per_warp: how many lanes of each warp take a hypothesis (divergence vs. warp count)
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
-                      int num_trials, double* models_out, int* num_models_out, cudaStream_t s);
+                      int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
+                      int lanes_per_warp = 32);
 void launch_model_offsets(const int* num_models, int num_trials, int* offsets, cudaStream_t s);
+// Shape of the scoring grid (launch_score): models per CTA and resident CTAs per SM, for the
+// callers that choose the segment count.
+constexpr int kScoreModelsPerCta = 512;
+constexpr int kScoreCtasPerSm = 2;
 // Inlier counts of every compact model.  part_cnt: num_segs x kcap scratch; cnt_out: kcap
 // (first K valid).
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
