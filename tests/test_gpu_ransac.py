@@ -120,6 +120,37 @@ def test_ransac_matches_oracle(ctx, oracle, n, opts, cases):
         assert ctx.prng_peek() == oracle.prng_peek(), tag   # same number of PRNG draws
 
 
+@pytest.mark.parametrize("first,growth,chunks", [(10, 2, 4), (3, 100, 4), (4, 3, 4), (3, 100, 1)])
+def test_ransac_wave_pipeline_is_invisible(ctx, oracle, monkeypatch, first, growth, chunks):
+    """The trial loop runs as a pipeline of waves, issued ahead of the replay where the loop is
+    certain to get there.  Whatever the partition: same report, mask and generator state as the
+    serial loop — including an adaptive abort inside a wave while later waves are already sampled
+    and in flight (the generator is rewound to the aborting wave's snapshot)."""
+    monkeypatch.setenv("PPSFM_RANSAC_FIRST", str(first))
+    monkeypatch.setenv("PPSFM_RANSAC_GROWTH", str(growth))
+    monkeypatch.setenv("PPSFM_RANSAC_CHUNKS", str(chunks))
+    for n, ratio, min_trials, max_trials, seed in [
+            (3000, 0.45, 2048, 10000, 1), (3000, 0.5, 2048, 10000, 2), (2500, 0.4, 1200, 10000, 3),
+            (3000, 0.6, 5000, 10000, 4), (2000, 0.35, 0, 10000, 5), (2000, 0.3, 4000, 4000, 6)]:
+        sc = S.make_abs_pose_scene(n=n, inlier_ratio=ratio, seed=seed)
+        o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                          min_num_trials=min_trials, max_num_trials=max_trials)
+        ctx.set_prng_seed(0)
+        oracle.set_prng_seed(0)
+        rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+        oref, omask = oracle.ransac_p6l(sc["lines"], sc["aligned"], sc["points"],
+                                        _oracle_opts(oracle, o))
+        tag = f"n={n} ratio={ratio} min={min_trials}"
+        assert (rep.success, rep.num_trials, rep.num_inliers) == \
+            (oref.success, oref.num_trials, oref.num_inliers), tag
+        assert rep.residual_sum == oref.residual_sum, tag
+        assert (rep.best_trial, rep.best_model_idx) == (oref.best_trial, oref.best_model_idx), tag
+        assert list(rep.model) == list(oref.model), tag
+        assert rep.num_models_scored == oref.num_models_scored, tag
+        assert np.array_equal(mask, omask), tag
+        assert ctx.prng_peek() == oracle.prng_peek(), tag
+
+
 def test_ransac_too_few_samples(ctx):
     sc = S.make_abs_pose_scene(n=5, seed=9)
     rep, _ = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"],
