@@ -422,8 +422,20 @@ def run_ba_b200(args, ctx, world, rank, dist):
     nbytes_in = sum(a.nbytes for a in (arrays.qvecs, arrays.tvecs, arrays.points, arrays.obs_image,
                                        arrays.obs_point, arrays.obs_line))
     nbytes_out = arrays.qvecs.nbytes + arrays.tvecs.nbytes + arrays.points.nbytes
+    # host buffers in pinned memory (as the contract asks of the end-to-end leg); the in-place
+    # outputs (poses, points) are re-initialised before every solve, outside the timed region
+    import torch
+    def pinned(a, dtype):
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=dtype)).pin_memory()
+        return t, t.numpy()
+    keep = {k: pinned(sc[k], np.float64) for k in ("qvecs", "tvecs", "points", "obs_line")}
+    keep.update({k: pinned(sc[k], np.int32) for k in ("obs_cam", "obs_pt")})
     for i in range(max(2, min(args.steps, 3)) + 1):
-        a2 = ba.BaArrays(*arr_args, pose_flags=flags)
+        for k in ("qvecs", "tvecs", "points"):
+            keep[k][1][...] = sc[k]
+        a2 = ba.BaArrays(keep["qvecs"][1], keep["tvecs"][1], keep["points"][1], keep["obs_cam"][1],
+                         keep["obs_pt"][1], keep["obs_line"][1], [1], [sc["cam_params"]],
+                         pose_flags=flags, copy=False)
         t0 = time.perf_counter()
         ok, s2 = ba.solve_arrays(ctx, a2, opts)
         dt = time.perf_counter() - t0

@@ -394,12 +394,6 @@ __device__ __forceinline__ void frag_load_smem(double (&acc)[8][2], const double
     acc[nb][1] = v.y;
   }
 }
-__device__ __forceinline__ void frag_store_smem(const double (&acc)[8][2], double* tile) {
-  const int lane = threadIdx.x & 31, row = (threadIdx.x >> 5) * 8 + (lane >> 2), q = lane & 3;
-#pragma unroll
-  for (int nb = 0; nb < 8; ++nb)
-    *reinterpret_cast<double2*>(tile + row * kCS + 8 * nb + 2 * q) = make_double2(acc[nb][0], acc[nb][1]);
-}
 
 // ------------------------------------------------------------------------------------------
 // The walker: diagonal and sub-diagonal tiles, one column after the other.
