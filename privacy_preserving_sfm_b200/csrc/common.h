@@ -92,11 +92,12 @@ struct ppsfm_ctx {
   // high-priority stream for the sample copies / solve kernels / exact kernels
   static constexpr int kWaveSlots = 4;
   struct WaveSlot {
-    ppsfm::DevBuf d_samples, d_models, d_num_models, d_off, d_part_cnt, d_cnt;
+    ppsfm::DevBuf d_samples, d_models, d_num_models, d_off, d_part_cnt, d_cnt, d_list;
     ppsfm::PinBuf h_samples, h_off, h_cnt;
     cudaEvent_t ev[5] = {nullptr};  // solve begin / end, score begin / end, results on the host
     cudaStream_t solve_stream = nullptr;  // high priority: the waves' solve kernels overlap
   } wave[kWaveSlots];
+  ppsfm::DevBuf d_best_lb;  // best inlier count of the waves scored so far (exact pruning)
   cudaStream_t stream_hi = nullptr;
   cudaStream_t stream_copy = nullptr;  // result copies, so that scoring kernels run back to back
   cudaEvent_t ev_sync = nullptr;

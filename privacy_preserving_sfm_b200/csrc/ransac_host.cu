@@ -94,6 +94,7 @@ static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap, int* num_segs,
 struct Wave {
   size_t t_begin = 0, t_end = 0;
   int H = 0, kcap = 0, slot = 0;
+  int n_first = 0;  // > 0: scored in two phases with exact pruning (launch_score)
   std::mt19937 prng_at_start;
 };
 
@@ -162,6 +163,12 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
         .count();
   };
   if (trace) PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[0], st));  // GPU time base
+  // exact pruning (launch_score): best count of the waves scored so far, kept on the device
+  const bool kPrune = ppsfm::tune_int("PPSFM_RANSAC_PRUNE", 1) != 0;
+  // smallest second phase worth its three extra launches (tests lower it to reach the path)
+  const size_t kPruneMin = (size_t)std::max(128, ppsfm::tune_int("PPSFM_RANSAC_PRUNE_MIN", 2048));
+  PPSFM_CUDA(ctx, ctx->d_best_lb.reserve(sizeof(unsigned)));
+  PPSFM_CUDA(ctx, cudaMemsetAsync(ctx->d_best_lb.p, 0, sizeof(unsigned), st));
   // On every exit path the streams are drained: speculative waves may still be running.
   struct Drain {
     ppsfm_ctx* c;
@@ -185,8 +192,13 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   // kernel needs 254 registers: 8 warps per SM; 6 leaves room beside a scoring CTA).  Measured on
   // the bench workload: 8 lanes 0.28 ms per wave, 32 lanes 0.31 ms.
   const int kSolveLanes = ppsfm::tune_int("PPSFM_SOLVE_LANES", 0);
+  size_t num_issued = 0;   // waves issued so far
   auto solve_lanes = [&](int H) {
     if (kSolveLanes > 0) return kSolveLanes;
+    // later waves solve under the scoring of the previous one: there the small footprint wins
+    // (254 registers per thread — spread over 4x the warps it leaves the scoring kernel one CTA
+    // per SM instead of two: 0.58 instead of 0.40 ms for the first wave's scoring)
+    if (num_issued > 0) return 32;
     int lanes = 8;
     while (lanes < 32 && (H + lanes - 1) / lanes > ctx->num_sms * 6) lanes *= 2;
     return lanes;
@@ -230,12 +242,37 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, sl.d_models.reserve(sizeof(double) * 96 * (size_t)H));
     PPSFM_CUDA(ctx, sl.d_num_models.reserve(sizeof(int) * (size_t)H));
     PPSFM_CUDA(ctx, sl.d_off.reserve(sizeof(int) * ((size_t)H + 1)));
+    // Two-phase scoring with exact pruning for every wave after the first of the call: all
+    // models on the first n_first correspondences, then only those that can still reach the best
+    // count of the earlier waves.  A model with inlier ratio rho is dropped if
+    // rho n_first + (n - n_first) < best; with n_first = n (1 - 0.8 r), r the inlier ratio the
+    // call expects of its best model (min_inlier_ratio, or the best ratio seen so far), that is
+    // every model with rho < r / 5 or so — the bulk of the hypotheses.
+    ppsfm::ScorePrune prune;
+    int n_first = (int)n;
+    if (kPrune) {
+      prune.best_lb = ctx->d_best_lb.as<unsigned>();
+      double r = opt.min_inlier_ratio;
+      if (have_best) r = std::max(r, (double)best.num_inliers / (double)n);
+      const size_t cut = ((size_t)((double)n * (1.0 - 0.8 * std::min(1.0, r))) + 127) / 128 * 128;
+      if (num_issued > 0 && r > 0.0 && cut >= 2 * kPruneMin && cut + kPruneMin <= n) n_first = (int)cut;
+    }
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, kcap, &num_segs, &seg_len);
-    PPSFM_CUDA(ctx, sl.d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));
+    ChooseSegments(ctx, n_first, kcap, &num_segs, &seg_len);
+    int part_segs = num_segs;
+    if (n_first < (int)n) {
+      prune.n_first = n_first;
+      ChooseSegments(ctx, (int)n - n_first, kcap, &prune.num_segs2, &prune.seg_len2);
+      part_segs = std::max(part_segs, prune.num_segs2);
+      PPSFM_CUDA(ctx, sl.d_list.reserve(sizeof(int) * ((size_t)kcap + 1)));
+      prune.list = sl.d_list.as<int>() + 1;
+      prune.list_count = sl.d_list.as<int>();
+    }
+    PPSFM_CUDA(ctx, sl.d_part_cnt.reserve(sizeof(unsigned) * (size_t)part_segs * kcap));
     PPSFM_CUDA(ctx, sl.d_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
-    PPSFM_CUDA(ctx, sl.h_off.reserve(sizeof(int) * ((size_t)H + 1)));
+    PPSFM_CUDA(ctx, sl.h_off.reserve(sizeof(int) * ((size_t)H + 2)));  // + survivor count
     PPSFM_CUDA(ctx, sl.h_cnt.reserve(sizeof(unsigned) * (size_t)kcap));
+    w.n_first = prune.n_first;
     // ---- copy + solve on the slot's high-priority stream
     PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.d_samples.p, hs, sizeof(uint32_t) * 6 * (size_t)H,
                                     cudaMemcpyHostToDevice, hs_stream));
@@ -250,19 +287,22 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[2], st));
     launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, sl.d_models.as<double>(),
                  sl.d_off.as<int>(), H, num_segs, seg_len, max_residual, kcap,
-                 sl.d_part_cnt.as<unsigned>(), sl.d_cnt.as<unsigned>(), st);
+                 sl.d_part_cnt.as<unsigned>(), sl.d_cnt.as<unsigned>(), st, prune);
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[3], st));
     // results to the host on the copy stream: the next wave's scoring kernel follows directly
     cudaStream_t cp = ctx->stream_copy;
     PPSFM_CUDA(ctx, cudaStreamWaitEvent(cp, sl.ev[3], 0));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_off.p, sl.d_off.p, sizeof(int) * ((size_t)H + 1),
                                     cudaMemcpyDeviceToHost, cp));
+    if (prune.n_first > 0)
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_off.as<int>() + H + 1, prune.list_count, sizeof(int),
+                                      cudaMemcpyDeviceToHost, cp));
     // (K is not known on the host yet: all kcap counts travel, 32 B per trial)
     PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_cnt.p, sl.d_cnt.p, sizeof(unsigned) * (size_t)kcap,
                                     cudaMemcpyDeviceToHost, cp));
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[4], cp));
-    ctx->timing.kernel_launches += 4;
-    ctx->timing.score_launches += 1;
+    ctx->timing.kernel_launches += prune.n_first > 0 ? 7 : 4;
+    ctx->timing.score_launches += prune.n_first > 0 ? 2 : 1;
     if (trace)
       fprintf(stderr, "[ransac] issue   trials %zu..%zu host %.3f -> %.3f ms\n", w.t_begin, w.t_end,
               trace_t0, host_ms());
@@ -323,7 +363,10 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     ctx->timing.solve_ms += EventMs(sl.ev[0], sl.ev[1]);
     ctx->timing.score_ms += EventMs(sl.ev[2], sl.ev[3]);
     total_ms += EventMs(sl.ev[0], sl.ev[1]) + EventMs(sl.ev[2], sl.ev[3]);
-    ctx->timing.score_pairs += (uint64_t)K * n;
+    // pairs the scoring kernel actually evaluated (dropped models skip the second phase)
+    ctx->timing.score_pairs += w.n_first > 0 ? (uint64_t)K * w.n_first +
+                                                   (uint64_t)h_off[H + 1] * (n - w.n_first)
+                                             : (uint64_t)K * n;
 
     // ---- pass 1 (counts only): models that beat or tie the running best count.  Only a TIE
     // needs residual sums (InlierSupportMeasurer::Compare, support_measurement.cc:52-60), and
@@ -470,7 +513,6 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   constexpr int kSlots = ppsfm_ctx::kWaveSlots;
   Wave waves[kSlots];
   int head = 0, in_flight = 0;  // waves[head] is the oldest wave in flight
-  size_t num_issued = 0;
   auto certain_to_reach = [&](size_t t) {
     return t < opt.min_num_trials || (have_best && t <= dyn_max_num_trials);
   };
@@ -496,7 +538,6 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     head = (head + 1) % kSlots;
     --in_flight;
   }
-  (void)num_issued;
 
   report->num_trials = reported_trials;
   report->num_inliers = best.num_inliers;
@@ -712,7 +753,7 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
     if (ev) cudaEventDestroy(ev);
   for (auto& sl : ctx->wave) {
     ppsfm::DevBuf* d[] = {&sl.d_samples, &sl.d_models, &sl.d_num_models, &sl.d_off,
-                          &sl.d_part_cnt, &sl.d_cnt};
+                          &sl.d_part_cnt, &sl.d_cnt, &sl.d_list};
     for (auto* b : d) b->release();
     ppsfm::PinBuf* h[] = {&sl.h_samples, &sl.h_off, &sl.h_cnt};
     for (auto* b : h) b->release();
@@ -727,6 +768,7 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
     ppsfm::DevBuf* d[] = {&ctx->d_fmodel, &ctx->d_frbuf, &ctx->d_fmask, &ctx->d_fcnt, &ctx->d_fsum};
     for (auto* b : d) b->release();
     ctx->h_fmask.release();
+    ctx->d_best_lb.release();
     ctx->h_fres.release();
   }
   if (ctx->stream_hi) cudaStreamDestroy(ctx->stream_hi);

@@ -416,19 +416,20 @@ __device__ __noinline__ unsigned score_slow(const double* __restrict__ c, int co
   return cnt;
 }
 
-template <int G, int M, int MINB>
-__global__ void __launch_bounds__(kScoreThreads, MINB)
+template <int G, int M, int MAXREG>
+__global__ void __maxnreg__(MAXREG)
 score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f, int n,
              const double* __restrict__ models, const int* __restrict__ offsets, int num_trials,
              int seg_len, double r_max, int kcap, unsigned* __restrict__ part_cnt,
-             const double* __restrict__ bounds) {
+             const double* __restrict__ bounds, const int* __restrict__ list,
+             const int* __restrict__ list_count) {
+  // list != nullptr: second phase of a pruned wave — slot i of the grid scores model list[i]
   __shared__ __align__(128) float tile[kStages][kTileR * 12];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ unsigned done[kStages];  // warps that have finished with the stage
 
-  const int K = offsets[num_trials];
-  const int mbase = blockIdx.x * (kScoreThreads * M);
-  if (mbase >= K) return;
+  const int K = list ? *list_count : offsets[num_trials];
+  if ((int)blockIdx.x * (kScoreThreads * M) >= K) return;
   const int seg = blockIdx.y;
   const int i0 = seg * seg_len;  // even: seg_len is a multiple of 128
   const int i1 = min(n, i0 + seg_len);
@@ -436,17 +437,35 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
   const int nrec = len >> 1;  // full records; an odd last correspondence goes through score_slow
   const int num_tiles = (nrec + kTileR - 1) / kTileR;
   const float* recs = corr6f + (size_t)(i0 >> 1) * 12;
+  const float nrf = -__double2float_rn(r_max);
+  const float2 nr = make_float2(nrf, nrf);
+  const uint32_t tile_addr = smem_u32(&tile[0][0]);
 
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      done[s] = 0;
+    }
+    mbar_fence_init();
+  }
+  unsigned phase_bits = 0;  // bit s: parity of the next completion of full_bar[s]
+
+  // A CTA takes the model blocks blockIdx.x, blockIdx.x + gridDim.x, ...: one block per CTA in
+  // the first phase (grid sized to the capacity), a short grid walking the survivor list in the
+  // second phase of a pruned wave.  The barriers live across blocks; phase_bits carries on.
+  for (int mbase = blockIdx.x * (kScoreThreads * M); mbase < K;
+       mbase += gridDim.x * (kScoreThreads * M)) {
   // thread <-> models mbase + m * 256 + tid, m < M
   const double* src[M];
   float2 Pf[M][12];
   int band[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) {
-    const int k = mbase + m * kScoreThreads + threadIdx.x;
+    const int slot = mbase + m * kScoreThreads + threadIdx.x;
+    const int k = slot < K ? (list ? list[slot] : slot) : -1;
     double P[12];
     src[m] = nullptr;
-    if (k < K) {
+    if (k >= 0) {
       int lo = 0, hi = num_trials;  // offsets[lo] <= k < offsets[hi]
       while (hi - lo > 1) {
         const int mid = (lo + hi) >> 1;
@@ -459,24 +478,14 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
 #pragma unroll
       for (int j = 0; j < 12; ++j) P[j] = 0.0;
     }
-    band[m] = filter32_band_bits(P, bounds, r_max, k < K);
+    band[m] = filter32_band_bits(P, bounds, r_max, k >= 0);
 #pragma unroll
     for (int j = 0; j < 12; ++j) {
       const float f = __double2float_rn(P[j]);
       Pf[m][j] = make_float2(f, f);
     }
   }
-  const float nrf = -__double2float_rn(r_max);
-  const float2 nr = make_float2(nrf, nrf);
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
-      mbar_init(&full_bar[s], 1);
-      done[s] = 0;
-    }
-    mbar_fence_init();
-  }
-  __syncthreads();
+  __syncthreads();  // barriers initialised / every warp is done with the previous block's tiles
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages && s < num_tiles; ++s) {
       const uint32_t bytes = (uint32_t)min(kTileR, nrec - s * kTileR) * 48u;
@@ -485,13 +494,13 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
     }
   }
 
-  const uint32_t tile_addr = smem_u32(&tile[0][0]);
   unsigned cnt[M];
 #pragma unroll
   for (int m = 0; m < M; ++m) cnt[m] = 0;
   for (int t = 0; t < num_tiles; ++t) {
     const int s = t % kStages;
-    mbar_wait(&full_bar[s], (uint32_t)((t / kStages) & 1));
+    mbar_wait(&full_bar[s], (phase_bits >> s) & 1u);
+    phase_bits ^= 1u << s;
     const int cnt_t = min(kTileR, nrec - t * kTileR);
     const uint32_t ta = tile_addr + (uint32_t)s * (kTileR * 48);
     const double* gc = corr6 + (size_t)(i0 + 2 * t * kTileR) * 6;  // the tile's doubles (slow path)
@@ -542,17 +551,55 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
       part_cnt[(size_t)seg * kcap + mbase + m * kScoreThreads + threadIdx.x] = cnt[m];
     }
   }
+  }  // model blocks
 }
 
+// Per-model combination of the per-segment counts.  best_lb (optional): running maximum of the
+// FINAL counts over everything scored so far in the call (see launch_score).
 __global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
                                     const int* __restrict__ offsets, int num_trials,
-                                    unsigned* __restrict__ cnt_out) {
+                                    unsigned* __restrict__ cnt_out,
+                                    unsigned* __restrict__ best_lb) {
   const int K = offsets[num_trials];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= K) return;
   unsigned c = 0;
   for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + k];
   cnt_out[k] = c;
+  if (best_lb) atomicMax(best_lb, c);
+}
+
+// Second phase of a pruned wave: slot i holds the remaining count of model list[i].
+__global__ void reduce_parts_list_kernel(const unsigned* __restrict__ part_cnt, int num_segs,
+                                         int kcap, const int* __restrict__ list,
+                                         const int* __restrict__ list_count,
+                                         unsigned* __restrict__ cnt_out,
+                                         unsigned* __restrict__ best_lb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= *list_count) return;
+  unsigned c = 0;
+  for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + i];
+  const int k = list[i];
+  c += cnt_out[k];
+  cnt_out[k] = c;
+  atomicMax(best_lb, c);
+}
+
+// Models that can still reach the best count known so far: first-phase count + everything left.
+__global__ void survivors_kernel(const unsigned* __restrict__ cnt_first, int remaining,
+                                 const int* __restrict__ offsets, int num_trials,
+                                 const unsigned* __restrict__ best_lb, int* __restrict__ list,
+                                 int* __restrict__ list_count) {
+  const int K = offsets[num_trials];
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool keep = k < K && cnt_first[k] + (unsigned)remaining >= *best_lb;  // '>=': ties count
+  const unsigned bal = __ballot_sync(0xffffffffu, keep);
+  if (bal == 0) return;
+  const int lane = threadIdx.x & 31;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(list_count, __popc(bal));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  if (keep) list[base + __popc(bal & ((1u << lane) - 1u))] = k;
 }
 
 // Largest double r with fl(r * r) <= max_residual (host).  IEEE multiplication is monotone, so
@@ -577,22 +624,44 @@ double inlier_abs_threshold(double max_residual) {
   return r;
 }
 
+// Exact pruning (prune.best_lb != nullptr).  The replay on the host only ever looks at a model's
+// count to ask whether it beats or ties the best count so far (InlierSupportMeasurer::Compare);
+// a model that cannot reach the best count of the waves scored BEFORE its own can therefore be
+// dropped without changing anything the reference computes.  best_lb is that count, maintained
+// on the device (atomicMax over the final counts of every launch, in stream order), so it is
+// valid even though the host has not consumed those waves yet.  With prune.n_first > 0 the wave
+// is scored in two phases: all models on correspondences [0, n_first), then only the models with
+// first-phase count + (n - n_first) >= best_lb on the rest; dropped models keep their first-phase
+// count, which is below best_lb like their true count.
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
                   const double* models, const int* offsets, int num_trials, int num_segs,
                   int seg_len, double max_residual, int kcap, unsigned* part_cnt,
-                  unsigned* cnt_out, cudaStream_t s) {
+                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune) {
   if (num_trials <= 0) return;
   const double r_max = inlier_abs_threshold(max_residual);
   // 4 records (8 correspondences) per unrolled group, 2 models per thread (every record read
   // from shared memory serves both), 2 CTAs per SM (100 registers): the best of the (group,
   // models per thread, occupancy) variants measured on the bench workload — (4,2,2) 1.085 ms,
   // (4,1,3) 1.126, (2,2,2) 1.131, (2,2,3) 1.254, (1,3,2) 1.341, (1,2,3) 1.363, (1,2,4) 2.180.
-  constexpr int kG = 4, kM = kScoreModelsPerCta / kScoreThreads, kMinB = kScoreCtasPerSm;
-  const dim3 grid((kcap + kScoreThreads * kM - 1) / (kScoreThreads * kM), num_segs);
-  score_kernel<kG, kM, kMinB><<<grid, kScoreThreads, 0, s>>>(
-      corr6, corr6f, n, models, offsets, num_trials, seg_len, r_max, kcap, part_cnt, bounds);
-  reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(part_cnt, num_segs, kcap, offsets,
-                                                         num_trials, cnt_out);
+  constexpr int kG = 4, kM = kScoreModelsPerCta / kScoreThreads, kMinB = kScoreMaxRegs;
+  const int xblocks = (kcap + kScoreThreads * kM - 1) / (kScoreThreads * kM);
+  const bool two_phase = prune.best_lb && prune.n_first > 0 && prune.n_first < n;
+  const int n1 = two_phase ? prune.n_first : n;  // multiple of 128 when two_phase (caller)
+  score_kernel<kG, kM, kMinB><<<dim3(xblocks, num_segs), kScoreThreads, 0, s>>>(
+      corr6, corr6f, n1, models, offsets, num_trials, seg_len, r_max, kcap, part_cnt, bounds,
+      nullptr, nullptr);
+  reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(
+      part_cnt, num_segs, kcap, offsets, num_trials, cnt_out, two_phase ? nullptr : prune.best_lb);
+  if (!two_phase) return;
+  cudaMemsetAsync(prune.list_count, 0, sizeof(int), s);
+  survivors_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(cnt_out, n - n1, offsets, num_trials,
+                                                      prune.best_lb, prune.list, prune.list_count);
+  // (few models survive: a short grid walks the list instead of one mostly empty CTA per block)
+  score_kernel<kG, kM, kMinB><<<dim3(std::min(xblocks, 16), prune.num_segs2), kScoreThreads, 0, s>>>(
+      corr6 + (size_t)n1 * 6, corr6f + (size_t)(n1 / 2) * 12, n - n1, models, offsets, num_trials,
+      prune.seg_len2, r_max, kcap, part_cnt, bounds, prune.list, prune.list_count);
+  reduce_parts_list_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(
+      part_cnt, prune.num_segs2, kcap, prune.list, prune.list_count, cnt_out, prune.best_lb);
 }
 
 // ------------------------------------------------------------------------------------------

@@ -20,13 +20,25 @@ void launch_model_offsets(const int* num_models, int num_trials, int* offsets, c
 // callers that choose the segment count.
 constexpr int kScoreModelsPerCta = 512;
 constexpr int kScoreCtasPerSm = 2;
-// Inlier counts of every compact model.  part_cnt: num_segs x kcap scratch; cnt_out: kcap
-// (first K valid).
+// 96 registers: two scoring CTAs (2 x 256 x 96) and one CTA of the solve kernel (64 x 256) fill
+// the 64 K register file exactly, so a solve running under the scoring of the previous wave does
+// not push a scoring CTA off the SM.
+constexpr int kScoreMaxRegs = 96;
+// Exact pruning state of launch_score (all device pointers; see the comment at launch_score).
+struct ScorePrune {
+  unsigned* best_lb = nullptr;  // running maximum of the final counts; nullptr: no pruning
+  int n_first = 0;              // > 0: two phases, the first over correspondences [0, n_first)
+                                // (a multiple of 128), segments of the second phase below
+  int num_segs2 = 0, seg_len2 = 0;
+  int* list = nullptr;          // kcap survivors of the first phase
+  int* list_count = nullptr;
+};
+// Inlier counts of every compact model.  part_cnt: max(num_segs, num_segs2) x kcap scratch;
+// cnt_out: kcap (first K valid; exact for every model that can matter, see ScorePrune).
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
-                  const double* models,
-                  const int* offsets, int num_trials, int num_segs, int seg_len,
-                  double max_residual, int kcap, unsigned* part_cnt, unsigned* cnt_out,
-                  cudaStream_t s);
+                  const double* models, const int* offsets, int num_trials, int num_segs,
+                  int seg_len, double max_residual, int kcap, unsigned* part_cnt,
+                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune = ScorePrune());
 // Largest double r with fl(r*r) <= max_residual.
 double inlier_abs_threshold(double max_residual);
 // rbuf: num_e x n residuals; mask (optional): num_e x n; ecnt/esum (optional): num_e.

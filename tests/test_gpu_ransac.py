@@ -120,18 +120,26 @@ def test_ransac_matches_oracle(ctx, oracle, n, opts, cases):
         assert ctx.prng_peek() == oracle.prng_peek(), tag   # same number of PRNG draws
 
 
-@pytest.mark.parametrize("first,growth,chunks", [(10, 2, 4), (3, 100, 4), (4, 3, 4), (3, 100, 1)])
-def test_ransac_wave_pipeline_is_invisible(ctx, oracle, monkeypatch, first, growth, chunks):
+@pytest.mark.parametrize("first,growth,chunks,prune_min", [
+    (10, 2, 4, 2048), (3, 100, 4, 2048), (4, 3, 4, 2048), (3, 100, 1, 2048),
+    (10, 2, 4, 128), (3, 100, 4, 128), (5, 2, 4, 256)])
+def test_ransac_wave_pipeline_is_invisible(ctx, oracle, monkeypatch, first, growth, chunks,
+                                           prune_min):
     """The trial loop runs as a pipeline of waves, issued ahead of the replay where the loop is
     certain to get there.  Whatever the partition: same report, mask and generator state as the
     serial loop — including an adaptive abort inside a wave while later waves are already sampled
-    and in flight (the generator is rewound to the aborting wave's snapshot)."""
+    and in flight (the generator is rewound to the aborting wave's snapshot).  Waves after the
+    first are scored in two phases with exact pruning (models that cannot reach the best count of
+    the earlier waves skip the second phase); prune_min lowers the size threshold of that path so
+    that these small sets go through it."""
+    monkeypatch.setenv("PPSFM_RANSAC_PRUNE_MIN", str(prune_min))
     monkeypatch.setenv("PPSFM_RANSAC_FIRST", str(first))
     monkeypatch.setenv("PPSFM_RANSAC_GROWTH", str(growth))
     monkeypatch.setenv("PPSFM_RANSAC_CHUNKS", str(chunks))
     for n, ratio, min_trials, max_trials, seed in [
             (3000, 0.45, 2048, 10000, 1), (3000, 0.5, 2048, 10000, 2), (2500, 0.4, 1200, 10000, 3),
-            (3000, 0.6, 5000, 10000, 4), (2000, 0.35, 0, 10000, 5), (2000, 0.3, 4000, 4000, 6)]:
+            (3000, 0.6, 5000, 10000, 4), (2000, 0.35, 0, 10000, 5), (2000, 0.3, 4000, 4000, 6),
+            (12000, 0.3, 2500, 2500, 7)]:
         sc = S.make_abs_pose_scene(n=n, inlier_ratio=ratio, seed=seed)
         o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
                           min_num_trials=min_trials, max_num_trials=max_trials)
