@@ -72,21 +72,36 @@ float EventMs(cudaEvent_t a, cudaEvent_t b) {
 
 }  // namespace
 
-// Chooses the segment count so that the scoring grid is a few waves of the resident CTAs
-// (148 SMs x kScoreCtasPerSm); kcap = model capacity (8 per trial).
-static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap, int* num_segs, int* seg_len) {
-  const int kcap_blocks = (kcap + ppsfm::kScoreModelsPerCta - 1) / ppsfm::kScoreModelsPerCta;
+// Chooses the segment count so that the LIVE part of the scoring grid (model blocks below K;
+// the blocks above exit at once) is just under a whole number of waves of the resident CTAs
+// (148 SMs x kScoreCtasPerSm): K is only known on the device, so the live block count is
+// estimated from the expected models per trial (3.9 of 8 for P6L, or what the call has seen so
+// far), and the grid is kept 4 % under the wave boundary — a grid of 4.01 waves costs 5.
+static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap, double models_per_trial,
+                           int* num_segs, int* seg_len) {
   const int resident = ctx->num_sms * ppsfm::kScoreCtasPerSm;
-  int target_blocks = resident * 4;
-  int segs = (target_blocks + kcap_blocks - 1) / std::max(1, kcap_blocks);
-  // model blocks beyond K exit immediately; on average half the capacity is live.
-  segs = std::max(1, std::min(segs * 2, 64));
-  segs = std::max(1, std::min(ppsfm::tune_int("PPSFM_SCORE_SEGS", segs), 256));
-  int len = (n + segs - 1) / segs;
-  len = std::max(256, ((len + 127) / 128) * 128);
-  segs = (n + len - 1) / len;
-  *num_segs = std::max(1, segs);
-  *seg_len = len;
+  const double live_models = std::max(1.0, (kcap / 8.0) * models_per_trial);
+  const int live_blocks = (int)std::ceil(live_models / ppsfm::kScoreModelsPerCta);
+  const int forced = ppsfm::tune_int("PPSFM_SCORE_SEGS", 0);
+  int best_segs = 1, best_len = std::max(256, ((n + 127) / 128) * 128);
+  if (forced > 0) {
+    best_len = std::max(256, (((n + forced - 1) / forced + 127) / 128) * 128);
+    best_segs = (n + best_len - 1) / best_len;
+  } else {
+    // the largest grid of at most 4 waves (segments no shorter than 512 correspondences)
+    const int budget = (int)(resident * 4 * 0.96);
+    for (int segs = std::max(1, budget / live_blocks); segs >= 1; --segs) {
+      const int len = std::max(512, (((n + segs - 1) / segs + 127) / 128) * 128);
+      const int real = (n + len - 1) / len;
+      if ((long long)real * live_blocks <= budget || segs == 1) {
+        best_segs = real;
+        best_len = len;
+        break;
+      }
+    }
+  }
+  *num_segs = std::max(1, best_segs);
+  *seg_len = best_len;
 }
 
 // One wave of the trial loop: trials [t_begin, t_end), its buffers (a slot of ctx->wave) and the
@@ -192,7 +207,13 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   // kernel needs 254 registers: 8 warps per SM; 6 leaves room beside a scoring CTA).  Measured on
   // the bench workload: 8 lanes 0.28 ms per wave, 32 lanes 0.31 ms.
   const int kSolveLanes = ppsfm::tune_int("PPSFM_SOLVE_LANES", 0);
+  // CTA size of the solve kernels that run under the previous wave's scoring: 256 threads x 255
+  // registers fill an SM, so the solve sits on ~26 SMs and leaves the others to the scoring
+  // kernel alone; spread out in 64-thread CTAs it shared ~100 SMs with it and cost the scoring
+  // more than it gained (bench step 1.61 ms against 1.70 ms)
+  const int kSolveThreadsLate = ppsfm::tune_int("PPSFM_SOLVE_THREADS_LATE", 256);
   size_t num_issued = 0;   // waves issued so far
+  double models_per_trial = 3.9;  // P6L: 3.8 +- 0.1 on generic data; updated from consumed waves
   auto solve_lanes = [&](int H) {
     if (kSolveLanes > 0) return kSolveLanes;
     // later waves solve under the scoring of the previous one: there the small footprint wins
@@ -258,11 +279,12 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       if (num_issued > 0 && r > 0.0 && cut >= 2 * kPruneMin && cut + kPruneMin <= n) n_first = (int)cut;
     }
     int num_segs, seg_len;
-    ChooseSegments(ctx, n_first, kcap, &num_segs, &seg_len);
+    ChooseSegments(ctx, n_first, kcap, models_per_trial, &num_segs, &seg_len);
     int part_segs = num_segs;
     if (n_first < (int)n) {
       prune.n_first = n_first;
-      ChooseSegments(ctx, (int)n - n_first, kcap, &prune.num_segs2, &prune.seg_len2);
+      // (few models survive: the second phase is sized as if one in eight did)
+      ChooseSegments(ctx, (int)n - n_first, kcap, 1.0, &prune.num_segs2, &prune.seg_len2);
       part_segs = std::max(part_segs, prune.num_segs2);
       PPSFM_CUDA(ctx, sl.d_list.reserve(sizeof(int) * ((size_t)kcap + 1)));
       prune.list = sl.d_list.as<int>() + 1;
@@ -279,7 +301,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[0], hs_stream));
     launch_p6l_solve(corr->corr6, corr->aligned, sl.d_samples.as<uint32_t>(), H,
                      sl.d_models.as<double>(), sl.d_num_models.as<int>(), hs_stream,
-                     solve_lanes(H));
+                     solve_lanes(H), num_issued > 0 ? kSolveThreadsLate : 64);
     launch_model_offsets(sl.d_num_models.as<int>(), H, sl.d_off.as<int>(), hs_stream);
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[1], hs_stream));
     // ---- score on the main stream, results to the host
@@ -360,6 +382,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     int* h_off = sl.h_off.as<int>();
     unsigned* h_cnt = sl.h_cnt.as<unsigned>();
     const int K = h_off[H];
+    if (H >= 256) models_per_trial = std::max(0.25, (double)K / H) * 1.02;
     ctx->timing.solve_ms += EventMs(sl.ev[0], sl.ev[1]);
     ctx->timing.score_ms += EventMs(sl.ev[2], sl.ev[3]);
     total_ms += EventMs(sl.ev[0], sl.ev[1]) + EventMs(sl.ev[2], sl.ev[3]);
@@ -943,7 +966,7 @@ int ppsfm_score_models(ppsfm_ctx* ctx, const double* lines, const double* points
     }
     hoff[H] = H;
     int num_segs, seg_len;
-    ChooseSegments(ctx, (int)n, kcap, &num_segs, &seg_len);
+    ChooseSegments(ctx, (int)n, kcap, 1.0, &num_segs, &seg_len);  // one model per trial here
     PPSFM_CUDA(ctx, ctx->d_models.reserve(sizeof(double) * hm.size()));
     PPSFM_CUDA(ctx, ctx->d_msrc.reserve(sizeof(int) * ((size_t)H + 1)));
     PPSFM_CUDA(ctx, ctx->d_part_cnt.reserve(sizeof(unsigned) * (size_t)num_segs * kcap));

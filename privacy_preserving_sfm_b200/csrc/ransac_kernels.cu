@@ -77,7 +77,7 @@ void launch_pack_corr(const double* lines, const double* points, size_t n, doubl
 // ------------------------------------------------------------------------------------------
 // P6L solve: one thread per hypothesis.
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(64)
+__global__ void __launch_bounds__(256)
 p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ aligned,
                  const uint32_t* __restrict__ samples, int num_trials,
                  double* __restrict__ models_out, int* __restrict__ num_models_out,
@@ -111,9 +111,9 @@ p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ a
 
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
-                      int lanes_per_warp) {
+                      int lanes_per_warp, int threads_per_cta) {
   if (num_trials <= 0) return;
-  const int threads = 64;
+  const int threads = std::max(32, std::min(256, threads_per_cta)) / 32 * 32;
   const int lanes = std::max(1, std::min(32, lanes_per_warp));
   const int warps = (num_trials + lanes - 1) / lanes;
   p6l_solve_kernel<<<(warps * 32 + threads - 1) / threads, threads, 0, s>>>(

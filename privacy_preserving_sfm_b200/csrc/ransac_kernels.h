@@ -14,7 +14,7 @@ void launch_pack_corr(const double* lines, const double* points, size_t n, doubl
 // lanes_per_warp: how many lanes of each warp take a hypothesis (divergence vs. warp count)
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
-                      int lanes_per_warp = 32);
+                      int lanes_per_warp = 32, int threads_per_cta = 64);
 void launch_model_offsets(const int* num_models, int num_trials, int* offsets, cudaStream_t s);
 // Shape of the scoring grid (launch_score): models per CTA and resident CTAs per SM, for the
 // callers that choose the segment count.
