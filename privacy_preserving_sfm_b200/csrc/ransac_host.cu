@@ -468,60 +468,79 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       }
     }
 
-    // ---- pass 2: literal replay of src/optim/ransac.h:213-249 over this wave.
+    // ---- pass 2: replay of src/optim/ransac.h:213-249 over this wave.  The reference visits
+    // every model of every trial; only two kinds of visits change state: a candidate (may become
+    // the best model and lower dyn_max_num_trials) and the first model at which the abort test
+    // `trial >= dyn_max_num_trials && trial >= min_num_trials` holds (checked after every model,
+    // so an empty trial cannot abort).  The replay jumps from one such visit to the next; for a
+    // given bound the abort can only trigger at the first model of the first non-empty trial at
+    // or above it, i.e. at compact index h_off[bound - t_begin].
     // `abort` set at trial t means: samples were drawn for trials 0..t, and the loop reports
     // num_trials = t + 2 (the `if (abort) { num_trials += 1; break; }` at the top of the next
     // iteration) unless t + 1 already equals max_num_trials.
     size_t ci = 0;       // cursor into cand
     int best_k = -1;     // compact id of the best model if it was set in this wave
-    for (size_t trial = t_begin; trial < t_end && !abort; ++trial) {
-      const int lt = (int)(trial - t_begin);
-      const int k0 = h_off[lt], k1 = h_off[lt + 1];
-      for (int k = k0; k < k1; ++k) {
-        ++scored;
-        while (ci < cand.size() && cand[ci] < k) ++ci;
-        if (ci < cand.size() && cand[ci] == k) {
-          const size_t c = h_cnt[k];
-          bool better;
-          if (!have_best) {
-            better = true;  // {c, sum} vs the initial {0, DBL_MAX}: more inliers, or 0 < DBL_MAX
-          } else if (c > best.num_inliers) {
-            better = true;
-          } else if (c == best.num_inliers) {
-            // tie: both sums are index-order exact here (has_tie forced the exact pass)
-            better = cand_sum[ci] < best.residual_sum;
+    int k_done = 0;      // models [0, k_done) of the wave have been visited
+    int abort_model = -1;
+    auto local_trial = [&](int k) { return int(std::upper_bound(h_off, h_off + H + 1, k) - h_off) - 1; };
+    while (true) {
+      const size_t bound = std::max<size_t>(dyn_max_num_trials, opt.min_num_trials);
+      int abort_k = K;
+      if (bound < t_end) abort_k = std::max(k_done, h_off[bound > t_begin ? bound - t_begin : 0]);
+      while (ci < cand.size() && cand[ci] < k_done) ++ci;
+      const int next_cand = ci < cand.size() ? cand[ci] : K;
+      if (next_cand >= K && abort_k >= K) break;
+      int k;
+      if (next_cand <= abort_k) {  // the candidate is visited first (or is the aborting model)
+        k = next_cand;
+        const int lt = local_trial(k);
+        const size_t trial = t_begin + lt;
+        const size_t c = h_cnt[k];
+        bool better;
+        if (!have_best) {
+          better = true;  // {c, sum} vs the initial {0, DBL_MAX}: more inliers, or 0 < DBL_MAX
+        } else if (c > best.num_inliers) {
+          better = true;
+        } else if (c == best.num_inliers) {
+          // tie: both sums are index-order exact here (has_tie forced the exact pass)
+          better = cand_sum[ci] < best.residual_sum;
+        } else {
+          better = false;
+        }
+        if (better) {
+          have_best = true;
+          best.num_inliers = c;
+          if (has_tie) {
+            best.residual_sum = cand_sum[ci];
+            best_sum_known = true;
           } else {
-            better = false;
+            best_sum_known = false;
           }
-          if (better) {
-            have_best = true;
-            best.num_inliers = c;
-            if (has_tie) {
-              best.residual_sum = cand_sum[ci];
-              best_sum_known = true;
-            } else {
-              best_sum_known = false;
-            }
-            best_k = k;
-            report->best_trial = (int64_t)trial;
-            report->best_model_idx = k - k0;
-            dyn_max_num_trials = ComputeNumTrials(best.num_inliers, n, opt.confidence,
-                                                  opt.dyn_num_trials_multiplier);
-          }
+          best_k = k;
+          report->best_trial = (int64_t)trial;
+          report->best_model_idx = k - h_off[lt];
+          dyn_max_num_trials = ComputeNumTrials(best.num_inliers, n, opt.confidence,
+                                                opt.dyn_num_trials_multiplier);
         }
-        if (trial >= dyn_max_num_trials && trial >= opt.min_num_trials) {
-          abort = true;
-          const size_t t_abort = trial;
-          reported_trials = (t_abort + 1 < max_num_trials) ? t_abort + 2 : max_num_trials;
-          // the reference drew samples for trials 0..t_abort only: rewind the generator to the
-          // start of this wave (later waves may have been sampled ahead) and skip forward
-          ctx->prng = w.prng_at_start;
-          HostSampler::Skip(ctx->prng, n, t_abort + 1 - t_begin);
-          finished = true;
-          break;
-        }
+        ++ci;
+        k_done = k + 1;
+        if (!(trial >= dyn_max_num_trials && trial >= opt.min_num_trials)) continue;
+      } else {
+        k = abort_k;
       }
+      // abort right after model k
+      abort = true;
+      abort_model = k;
+      const size_t t_abort = t_begin + local_trial(k);
+      reported_trials = (t_abort + 1 < max_num_trials) ? t_abort + 2 : max_num_trials;
+      // the reference drew samples for trials 0..t_abort only: rewind the generator to the
+      // start of this wave (later waves may have been sampled ahead) and skip forward
+      ctx->prng = w.prng_at_start;
+      HostSampler::Skip(ctx->prng, n, t_abort + 1 - t_begin);
+      finished = true;
+      break;
     }
+    scored += abort_model >= 0 ? (uint64_t)abort_model + 1 : (uint64_t)K;
     if (best_k >= 0) {  // the best model changed in this wave: bring its 12 doubles to the host
       PPSFM_CUDA(ctx, cudaMemcpyAsync(best_model, sl.d_models.as<double>() + model_src(best_k),
                                       sizeof(best_model), cudaMemcpyDeviceToHost, hi));
