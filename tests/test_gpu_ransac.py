@@ -139,7 +139,7 @@ def test_ransac_wave_pipeline_is_invisible(ctx, oracle, monkeypatch, first, grow
     for n, ratio, min_trials, max_trials, seed in [
             (3000, 0.45, 2048, 10000, 1), (3000, 0.5, 2048, 10000, 2), (2500, 0.4, 1200, 10000, 3),
             (3000, 0.6, 5000, 10000, 4), (2000, 0.35, 0, 10000, 5), (2000, 0.3, 4000, 4000, 6),
-            (12000, 0.3, 2500, 2500, 7)]:
+            (12000, 0.3, 2500, 2500, 7), (2001, 0.4, 1500, 10000, 8), (777, 0.5, 1100, 3000, 9)]:
         sc = S.make_abs_pose_scene(n=n, inlier_ratio=ratio, seed=seed)
         o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
                           min_num_trials=min_trials, max_num_trials=max_trials)
