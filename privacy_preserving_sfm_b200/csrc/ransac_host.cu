@@ -197,7 +197,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
 
   // ---- wave schedule.  A "plan" is the range the reference loop is currently bound to reach
   // (at least min_num_trials and a floor that fills the GPU, at most the dynamic bound); it is
-  // cut into kChunks waves so that the pipeline has something to overlap.
+  // cut into waves (next_wave_range) so that the pipeline has something to overlap.
   const size_t kWaveFloor = 1024;
   const size_t kWaveCap = 1u << 17;
   const size_t kChunks = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", 4));
@@ -216,9 +216,8 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   double models_per_trial = 3.9;  // P6L: 3.8 +- 0.1 on generic data; updated from consumed waves
   auto solve_lanes = [&](int H) {
     if (kSolveLanes > 0) return kSolveLanes;
-    // later waves solve under the scoring of the previous one: there the small footprint wins
-    // (254 registers per thread — spread over 4x the warps it leaves the scoring kernel one CTA
-    // per SM instead of two: 0.58 instead of 0.40 ms for the first wave's scoring)
+    // later waves solve under the scoring of the previous one, where their latency is hidden
+    // anyway: full warps, so that the solve occupies as few SMs as possible (kSolveThreadsLate)
     if (num_issued > 0) return 32;
     int lanes = 8;
     while (lanes < 32 && (H + lanes - 1) / lanes > ctx->num_sms * 6) lanes *= 2;

@@ -20,9 +20,8 @@ void launch_model_offsets(const int* num_models, int num_trials, int* offsets, c
 // callers that choose the segment count.
 constexpr int kScoreModelsPerCta = 512;
 constexpr int kScoreCtasPerSm = 2;
-// 96 registers: two scoring CTAs (2 x 256 x 96) and one CTA of the solve kernel (64 x 256) fill
-// the 64 K register file exactly, so a solve running under the scoring of the previous wave does
-// not push a scoring CTA off the SM.
+// 96 registers (the kernel needs 95 - 106 depending on scheduling; no spills at 96): two scoring
+// CTAs (2 x 256 x 96) leave a quarter of the register file to whatever else is on the SM.
 constexpr int kScoreMaxRegs = 96;
 // Exact pruning state of launch_score (all device pointers; see the comment at launch_score).
 struct ScorePrune {
