@@ -316,7 +316,7 @@ def run_b200(args):
                 "peak": hbm_peak, "unit": "GB/s", "peak_source": peak_kind,
                 "note": "algorithmic bytes = passes x N x 48 B; compute-bound kernel"},
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch over all 10k hypotheses in
-        # the committed ncu --set full capture (profiles/r01_s3_score_kernel_ncu.txt): the float
+        # the committed ncu --set full capture (profiles/r01_s6_score_kernel_ncu.txt): the float
         # and double copies of the correspondence set are read from HBM about twice, the other
         # passes hit L2; scaled by the launches per step
         "traffic": 7.4e6 / max(1.0, score_launches / max(1, args.steps)),
