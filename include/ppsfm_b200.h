@@ -83,6 +83,10 @@ const char* ppsfm_version(void);
 /* SetPRNGSeed, src/util/random.cc:38-50 (the context's generator starts at seed 0 like
  * kDefaultPRNGSeed, src/util/random.h:46). */
 void ppsfm_set_prng_seed(ppsfm_ctx* ctx, uint32_t seed);
+/* Host-only self-test (no context, no GPU): the event-driven replay of the reference's trial loop
+ * (src/optim/ransac.h:213-249) used by ppsfm_ransac_p6l against the literal model-by-model loop
+ * on `rounds` random waves.  Returns the number of waves on which they differ (0 = pass). */
+int ppsfm_selftest_replay(uint32_t seed, int rounds);
 /* next raw mt19937 output without advancing (state fingerprint for parity tests) */
 uint32_t ppsfm_prng_peek(const ppsfm_ctx* ctx);
 

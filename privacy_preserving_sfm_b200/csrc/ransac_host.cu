@@ -16,20 +16,12 @@
 
 #include "common.h"
 #include "ransac_kernels.h"
+#include "ransac_replay.h"
 
 namespace ppsfm {
 namespace {
 
-// RANSAC<P6LEstimator>::ComputeNumTrials, src/optim/ransac.h:158-176 (kMinNumSamples = 6)
-size_t ComputeNumTrials(size_t num_inliers, size_t num_samples, double confidence,
-                        double multiplier) {
-  const double inlier_ratio = num_inliers / static_cast<double>(num_samples);
-  const double nom = 1 - confidence;
-  if (nom <= 0) return std::numeric_limits<size_t>::max();
-  const double denom = 1 - std::pow(inlier_ratio, 6);
-  if (denom <= 0) return 1;
-  return static_cast<size_t>(std::ceil(std::log(nom) / std::log(denom) * multiplier));
-}
+using ppsfm::ComputeNumTrials;  // ransac_replay.h
 
 // RandomSampler (src/optim/random_sampler.cc:40-62): persistent permutation, partial
 // Fisher-Yates of the first 6 slots with RandomInteger<uint32_t>(i, n-1).
@@ -57,11 +49,6 @@ struct HostSampler {
         (void)distribution(prng);
       }
   }
-};
-
-struct Support {
-  size_t num_inliers = 0;
-  double residual_sum = std::numeric_limits<double>::max();  // support_measurement.h:51-52
 };
 
 float EventMs(cudaEvent_t a, cudaEvent_t b) {
@@ -150,12 +137,9 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
 
   const double max_residual = opt.max_error * opt.max_error;
   const size_t max_num_trials = opt.max_num_trials;
-  size_t dyn_max_num_trials = max_num_trials;
-  Support best;
-  bool have_best = false;       // false while `best` is the initial {0, DBL_MAX}
-  bool best_sum_known = true;   // residual_sum of `best` is an exact index-order sum
+  ppsfm::ReplayState rs;        // best support so far, dynamic trial bound (ransac_replay.h)
+  rs.dyn_max_num_trials = max_num_trials;
   double best_model[12] = {0};
-  bool abort = false;
   bool finished = false;
   size_t reported_trials = max_num_trials;
   uint64_t scored = 0;
@@ -234,8 +218,8 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   auto next_wave_range = [&](size_t* t_end_out) {
     if (t_issue >= plan_end) {
       size_t want_end = std::max<size_t>(opt.min_num_trials, t_issue + kWaveFloor);
-      if (dyn_max_num_trials != std::numeric_limits<size_t>::max())
-        want_end = std::max(want_end, std::min(dyn_max_num_trials + 1, max_num_trials));
+      if (rs.dyn_max_num_trials != std::numeric_limits<size_t>::max())
+        want_end = std::max(want_end, std::min(rs.dyn_max_num_trials + 1, max_num_trials));
       plan_end = std::min(max_num_trials, want_end);
       const size_t span = plan_end - t_issue;
       plan_chunk = kChunks <= 1 ? kWaveCap
@@ -273,7 +257,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     if (kPrune) {
       prune.best_lb = ctx->d_best_lb.as<unsigned>();
       double r = opt.min_inlier_ratio;
-      if (have_best) r = std::max(r, (double)best.num_inliers / (double)n);
+      if (rs.have_best) r = std::max(r, (double)rs.best_inliers / (double)n);
       const size_t cut = ((size_t)((double)n * (1.0 - 0.8 * std::min(1.0, r))) + 127) / 128 * 128;
       if (num_issued > 0 && r > 0.0 && cut >= 2 * kPruneMin && cut + kPruneMin <= n) n_first = (int)cut;
     }
@@ -348,7 +332,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_fmodel.p, best_model, sizeof(best_model),
                                     cudaMemcpyHostToDevice, hi));
     PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev_final[0], hi));
-    final_has_mask = mask_wanted && best.num_inliers >= 6;
+    final_has_mask = mask_wanted && rs.best_inliers >= 6;
     launch_exact(corr->corr6, (int)n, ctx->d_fmodel.as<double>(), 1, max_residual,
                  ctx->d_frbuf.as<double>(), final_has_mask ? ctx->d_fmask.as<uint8_t>() : nullptr,
                  ctx->d_fcnt.as<unsigned long long>(), ctx->d_fsum.as<double>(), hi);
@@ -394,22 +378,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     // needs residual sums (InlierSupportMeasurer::Compare, support_measurement.cc:52-60), and
     // those must be index-order sums to match the reference bit for bit.
     std::vector<int> cand;
-    bool has_tie = false;
-    {
-      size_t b = best.num_inliers;
-      bool have = have_best;
-      for (int k = 0; k < K; ++k) {
-        const size_t c = h_cnt[k];
-        if (!have || c > b) {
-          cand.push_back(k);
-          b = c;
-          have = true;
-        } else if (c == b) {
-          cand.push_back(k);
-          has_tie = true;
-        }
-      }
-    }
+    const bool has_tie = ppsfm::replay_candidates(h_cnt, K, rs, &cand);
     auto model_src = [&](int k) -> size_t {
       const int t = int(std::upper_bound(h_off, h_off + H + 1, k) - h_off) - 1;
       return (size_t)t * 96 + (size_t)(k - h_off[t]) * 12;
@@ -418,7 +387,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     std::vector<double> cand_sum;
     if (has_tie) {
       // exact (index-order) supports for every candidate of this wave (+ the carried best)
-      const bool carry = have_best && !best_sum_known;
+      const bool carry = rs.have_best && !rs.best_sum_known;
       const int EE = E + (carry ? 1 : 0);
       cand_sum.resize(EE);
       PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double) * (size_t)EE));
@@ -457,89 +426,44 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       }
       for (int e = 0; e < EE; ++e) {
         cand_sum[e] = ctx->h_esum.as<double>()[e];
-        const size_t want = e < E ? (size_t)h_cnt[cand[e]] : best.num_inliers;
+        const size_t want = e < E ? (size_t)h_cnt[cand[e]] : rs.best_inliers;
         if (ctx->h_ecnt.as<unsigned long long>()[e] != want)
           return fail(ctx, PPSFM_ERR_CUDA, "internal: exact/segmented inlier counts differ");
       }
       if (carry) {
-        best.residual_sum = cand_sum[E];
-        best_sum_known = true;
+        rs.best_sum = cand_sum[E];
+        rs.best_sum_known = true;
       }
     }
 
-    // ---- pass 2: replay of src/optim/ransac.h:213-249 over this wave.  The reference visits
-    // every model of every trial; only two kinds of visits change state: a candidate (may become
-    // the best model and lower dyn_max_num_trials) and the first model at which the abort test
-    // `trial >= dyn_max_num_trials && trial >= min_num_trials` holds (checked after every model,
-    // so an empty trial cannot abort).  The replay jumps from one such visit to the next; for a
-    // given bound the abort can only trigger at the first model of the first non-empty trial at
-    // or above it, i.e. at compact index h_off[bound - t_begin].
-    // `abort` set at trial t means: samples were drawn for trials 0..t, and the loop reports
+    // ---- pass 2: replay of src/optim/ransac.h:213-249 over this wave (ransac_replay.h).
+    // An abort at trial t means: samples were drawn for trials 0..t, and the loop reports
     // num_trials = t + 2 (the `if (abort) { num_trials += 1; break; }` at the top of the next
     // iteration) unless t + 1 already equals max_num_trials.
-    size_t ci = 0;       // cursor into cand
-    int best_k = -1;     // compact id of the best model if it was set in this wave
-    int k_done = 0;      // models [0, k_done) of the wave have been visited
-    int abort_model = -1;
-    auto local_trial = [&](int k) { return int(std::upper_bound(h_off, h_off + H + 1, k) - h_off) - 1; };
-    while (true) {
-      const size_t bound = std::max<size_t>(dyn_max_num_trials, opt.min_num_trials);
-      int abort_k = K;
-      if (bound < t_end) abort_k = std::max(k_done, h_off[bound > t_begin ? bound - t_begin : 0]);
-      while (ci < cand.size() && cand[ci] < k_done) ++ci;
-      const int next_cand = ci < cand.size() ? cand[ci] : K;
-      if (next_cand >= K && abort_k >= K) break;
-      int k;
-      if (next_cand <= abort_k) {  // the candidate is visited first (or is the aborting model)
-        k = next_cand;
-        const int lt = local_trial(k);
-        const size_t trial = t_begin + lt;
-        const size_t c = h_cnt[k];
-        bool better;
-        if (!have_best) {
-          better = true;  // {c, sum} vs the initial {0, DBL_MAX}: more inliers, or 0 < DBL_MAX
-        } else if (c > best.num_inliers) {
-          better = true;
-        } else if (c == best.num_inliers) {
-          // tie: both sums are index-order exact here (has_tie forced the exact pass)
-          better = cand_sum[ci] < best.residual_sum;
-        } else {
-          better = false;
-        }
-        if (better) {
-          have_best = true;
-          best.num_inliers = c;
-          if (has_tie) {
-            best.residual_sum = cand_sum[ci];
-            best_sum_known = true;
-          } else {
-            best_sum_known = false;
-          }
-          best_k = k;
-          report->best_trial = (int64_t)trial;
-          report->best_model_idx = k - h_off[lt];
-          dyn_max_num_trials = ComputeNumTrials(best.num_inliers, n, opt.confidence,
-                                                opt.dyn_num_trials_multiplier);
-        }
-        ++ci;
-        k_done = k + 1;
-        if (!(trial >= dyn_max_num_trials && trial >= opt.min_num_trials)) continue;
-      } else {
-        k = abort_k;
-      }
-      // abort right after model k
-      abort = true;
-      abort_model = k;
-      const size_t t_abort = t_begin + local_trial(k);
+    ppsfm::ReplayParams rp;
+    rp.t_begin = t_begin;
+    rp.t_end = t_end;
+    rp.num_samples = n;
+    rp.min_num_trials = opt.min_num_trials;
+    rp.confidence = opt.confidence;
+    rp.multiplier = opt.dyn_num_trials_multiplier;
+    const ppsfm::ReplayOutcome ro =
+        ppsfm::replay_wave(h_off, H, h_cnt, cand, has_tie ? cand_sum.data() : nullptr, rp, &rs);
+    scored += ro.scored;
+    const int best_k = ro.best_k;
+    if (best_k >= 0) {
+      report->best_trial = rs.best_trial;
+      report->best_model_idx = rs.best_model_idx;
+    }
+    if (ro.abort_model >= 0) {
+      const size_t t_abort = ro.t_abort;
       reported_trials = (t_abort + 1 < max_num_trials) ? t_abort + 2 : max_num_trials;
       // the reference drew samples for trials 0..t_abort only: rewind the generator to the
       // start of this wave (later waves may have been sampled ahead) and skip forward
       ctx->prng = w.prng_at_start;
       HostSampler::Skip(ctx->prng, n, t_abort + 1 - t_begin);
       finished = true;
-      break;
     }
-    scored += abort_model >= 0 ? (uint64_t)abort_model + 1 : (uint64_t)K;
     if (best_k >= 0) {  // the best model changed in this wave: bring its 12 doubles to the host
       PPSFM_CUDA(ctx, cudaMemcpyAsync(best_model, sl.d_models.as<double>() + model_src(best_k),
                                       sizeof(best_model), cudaMemcpyDeviceToHost, hi));
@@ -555,7 +479,7 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   Wave waves[kSlots];
   int head = 0, in_flight = 0;  // waves[head] is the oldest wave in flight
   auto certain_to_reach = [&](size_t t) {
-    return t < opt.min_num_trials || (have_best && t <= dyn_max_num_trials);
+    return t < opt.min_num_trials || (rs.have_best && t <= rs.dyn_max_num_trials);
   };
   while (!finished) {
     // issue: always when nothing is in flight, ahead only over trials certain to be reached
@@ -581,13 +505,13 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   }
 
   report->num_trials = reported_trials;
-  report->num_inliers = best.num_inliers;
+  report->num_inliers = rs.best_inliers;
   report->num_models_scored = scored;
   std::memcpy(report->model, best_model, sizeof(best_model));
 
   // Support + inlier mask of the best model in reference (index) order
   // (src/optim/ransac.h:251-275: the reference also rescans the best model once more).
-  if (have_best) {
+  if (rs.have_best) {
     if (!final_valid) {
       const int rc = launch_final();
       if (rc != PPSFM_OK) return rc;
@@ -600,18 +524,18 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
               EventMs(ctx->ev[0], ctx->ev_final[1]));
     unsigned long long fcnt;
     std::memcpy(&fcnt, ctx->h_fres.as<char>() + 8, sizeof(fcnt));
-    if (fcnt != best.num_inliers)
+    if (fcnt != rs.best_inliers)
       return fail(ctx, PPSFM_ERR_CUDA, "internal: exact/segmented inlier counts differ");
-    std::memcpy(&best.residual_sum, ctx->h_fres.p, sizeof(double));
+    std::memcpy(&rs.best_sum, ctx->h_fres.p, sizeof(double));
     if (final_has_mask) std::memcpy(inlier_mask, ctx->h_fmask.p, n);
     const float ems = EventMs(ctx->ev_final[0], ctx->ev_final[1]);
     ctx->timing.exact_ms += ems;
     total_ms += ems;
   }
-  report->residual_sum = best.residual_sum;
+  report->residual_sum = rs.best_sum;
   ctx->timing.total_ms = total_ms;
   PPSFM_CUDA(ctx, cudaGetLastError());
-  if (best.num_inliers < 6) return PPSFM_OK;  // src/optim/ransac.h:255-259
+  if (rs.best_inliers < 6) return PPSFM_OK;  // src/optim/ransac.h:255-259
   report->success = 1;
   return PPSFM_OK;
 }
@@ -819,6 +743,61 @@ void ppsfm_ctx_destroy(ppsfm_ctx* ctx) {
 }
 
 const char* ppsfm_last_error(const ppsfm_ctx* ctx) { return ctx ? ctx->last_error.c_str() : ""; }
+
+// Host-only self-test (no context, no GPU): the event-driven replay RansacResident uses against
+// the literal model-by-model loop, on `rounds` random waves (empty trials, ties, carried best
+// models, aborts at every position).  Returns the number of waves on which they differ.
+int ppsfm_selftest_replay(uint32_t seed, int rounds) {
+  std::mt19937 g(seed);
+  auto uni = [&](int lo, int hi) { return std::uniform_int_distribution<int>(lo, hi)(g); };
+  int mismatches = 0;
+  for (int r = 0; r < rounds; ++r) {
+    const int H = uni(1, 300);
+    const size_t N = (size_t)uni(50, 4000);
+    std::vector<int> off(H + 1, 0);
+    const int empty_pct = uni(0, 60);
+    for (int t = 0; t < H; ++t) off[t + 1] = off[t] + (uni(0, 99) < empty_pct ? 0 : uni(1, 8));
+    const int K = off[H];
+    const int levels = uni(1, 40);  // few distinct counts -> ties
+    const unsigned top = (unsigned)uni(1, (int)N);
+    std::vector<unsigned> cnt(K);
+    for (int k = 0; k < K; ++k) cnt[k] = (unsigned)((uint64_t)uni(0, levels) * top / levels);
+    ppsfm::ReplayParams p;
+    p.t_begin = uni(0, 1) ? 0 : (size_t)uni(1, 5000);
+    p.t_end = p.t_begin + H;
+    p.num_samples = N;
+    p.min_num_trials = uni(0, 2) == 0 ? 0 : (size_t)uni(0, (int)p.t_end + 50);
+    p.confidence = uni(0, 2) == 0 ? 0.9 : (uni(0, 1) ? 0.99 : 0.99999);
+    p.multiplier = uni(0, 1) ? 3.0 : 1.0;
+    ppsfm::ReplayState s0;
+    s0.dyn_max_num_trials = (size_t)uni(1, 20000);
+    if (uni(0, 1)) {  // a best model carried over from earlier waves
+      s0.have_best = true;
+      s0.best_inliers = (size_t)uni(0, (int)N);
+      s0.best_sum = uni(0, 1000) * 1e-3;
+      s0.best_sum_known = uni(0, 1) != 0;
+      s0.dyn_max_num_trials = std::min<size_t>(
+          s0.dyn_max_num_trials, ComputeNumTrials(s0.best_inliers, N, p.confidence, p.multiplier));
+    }
+    std::vector<int> cand;
+    const bool has_tie = ppsfm::replay_candidates(cnt.data(), K, s0, &cand);
+    std::vector<double> sums(cand.size());
+    for (auto& v : sums) v = uni(0, 5) * 0.25;  // equal sums happen too
+    if (has_tie && s0.have_best) s0.best_sum_known = true;  // the tie pass makes it exact
+    const double* cs = has_tie ? sums.data() : nullptr;
+    ppsfm::ReplayState a = s0, b = s0;
+    const ppsfm::ReplayOutcome oa = ppsfm::replay_wave_literal(off.data(), H, cnt.data(), cand, cs, p, &a);
+    const ppsfm::ReplayOutcome ob = ppsfm::replay_wave(off.data(), H, cnt.data(), cand, cs, p, &b);
+    const bool same = oa.best_k == ob.best_k && oa.abort_model == ob.abort_model &&
+                      (oa.abort_model < 0 || oa.t_abort == ob.t_abort) && oa.scored == ob.scored &&
+                      a.have_best == b.have_best && a.best_inliers == b.best_inliers &&
+                      a.best_sum == b.best_sum && a.best_sum_known == b.best_sum_known &&
+                      a.dyn_max_num_trials == b.dyn_max_num_trials &&
+                      a.best_trial == b.best_trial && a.best_model_idx == b.best_model_idx;
+    if (!same) ++mismatches;
+  }
+  return mismatches;
+}
 
 void ppsfm_set_prng_seed(ppsfm_ctx* ctx, uint32_t seed) {
   if (ctx) ctx->prng = std::mt19937(seed);

@@ -44,6 +44,18 @@ def test_host_only_entry_points_work_without_gpu():
     assert o.min_num_trials == 0 and o.max_num_trials == 2 ** 64 - 1
 
 
+def test_event_driven_replay_equals_the_literal_loop():
+    """RansacResident replays the reference's trial loop (src/optim/ransac.h:213-249) over the
+    counts of a wave by jumping between the visits that change state; the library's host-only
+    self-test runs it against the literal model-by-model loop on random waves (empty trials,
+    ties, carried best models; about half of the waves abort, a third of them mid-wave)."""
+    L = pp.load_library()
+    L.ppsfm_selftest_replay.argtypes = [ctypes.c_uint32, ctypes.c_int]
+    L.ppsfm_selftest_replay.restype = ctypes.c_int
+    for seed in (1, 2, 3, 20201017):
+        assert L.ppsfm_selftest_replay(seed, 20000) == 0
+
+
 def test_no_cpu_fallback():
     import torch
     if torch.cuda.is_available():
