@@ -69,11 +69,28 @@ def p6l_case():
     return out
 
 
+def ba_case():
+    sb = S.make_ba_scene(num_cams=6, num_points=200, obs_per_point=4, seed=107)
+    flags = np.zeros(6, np.uint8)
+    flags[0], flags[1] = 1, 2          # camera 0 constant, camera 1 tvec[0] constant
+    a = O.BaArrays(sb["qvecs"], sb["tvecs"], sb["points"], sb["obs_cam"], sb["obs_pt"],
+                   sb["obs_line"], [1], [sb["cam_params"]], pose_flags=flags)
+    ok, s = O.ba_solve(a, O.ba_default_options(num_threads=1, max_num_iterations=20,
+                                               gradient_tolerance=1e-4))
+    state = np.concatenate([a.qvecs.ravel(), a.tvecs.ravel(), a.points.ravel()])
+    return {"ok": bool(ok), "successful_steps": int(s.num_successful_steps),
+            "unsuccessful_steps": int(s.num_unsuccessful_steps),
+            "termination_type": int(s.termination_type),
+            "initial_cost": float(s.initial_cost).hex(), "final_cost": float(s.final_cost).hex(),
+            "state_sha256": hashlib.sha256(state.astype(np.float64).tobytes()).hexdigest()}
+
+
 def main():
     O.build()
     gold = {"ransac": {name: dict(scene=kw, options=list(opt), expect=ransac_case(kw, opt))
                        for name, kw, opt in RANSAC_CASES},
-            "line_residuals": residual_case(), "p6l_estimate": p6l_case()}
+            "line_residuals": residual_case(), "p6l_estimate": p6l_case(),
+            "ba_solve_single_thread": ba_case()}
     with open(os.path.join(HERE, "oracle_vectors.json"), "w") as f:
         json.dump(gold, f, indent=1)
     print("wrote", os.path.join(HERE, "oracle_vectors.json"))
