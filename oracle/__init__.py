@@ -58,6 +58,8 @@ def lib():
         L.orc_sample_table.argtypes = [C.c_size_t, C.c_size_t, _u32p]
         L.orc_re3q3.argtypes = [_dp, _dp]
         L.orc_re3q3.restype = C.c_int
+        L.orc_re3q3_resultant.argtypes = [_dp, _dp, _dp]
+        L.orc_re3q3_backsubstitute.argtypes = [_dp, C.c_double, _dp]
         L.orc_poly8_real_roots.argtypes = [_dp, _dp]
         L.orc_poly8_real_roots.restype = C.c_int
         L.orc_poly8_all_roots.argtypes = [_dp, _dp]
@@ -144,6 +146,23 @@ def re3q3(coeffs):
     sol = np.zeros(24, dtype=np.float64)
     n = lib().orc_re3q3(cp, sol.ctypes.data_as(_dp))
     return sol.reshape(8, 3)[:n].copy()
+
+
+def re3q3_resultant(P):
+    """re3q3.h:84-150 on P (3x7) -> (a[33], c[9])."""
+    P, pp = _d(np.asarray(P, np.float64).reshape(3, 7))
+    a = np.zeros(33)
+    c = np.zeros(9)
+    lib().orc_re3q3_resultant(pp, a.ctypes.data_as(_dp), c.ctypes.data_as(_dp))
+    return a, c
+
+
+def re3q3_backsubstitute(a, x):
+    """re3q3.h:177-188: (y, z) for the root x."""
+    a, ap = _d(np.asarray(a, np.float64).reshape(33))
+    yz = np.zeros(2)
+    lib().orc_re3q3_backsubstitute(ap, float(x), yz.ctypes.data_as(_dp))
+    return yz
 
 
 def poly8_real_roots(c):

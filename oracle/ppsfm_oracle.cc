@@ -77,115 +77,60 @@ inline double Det3(const double m[3][3]) {
   return h0 - h1 + h2;
 }
 
-// Solve A X = B for 3x3 A with PARTIAL (row) pivoting; B is 3 x ncols, overwritten by X.
-// Stand-in for Eigen::PartialPivLU<Matrix3d>::solve (absolute_pose.cc:137).
+// Solve A X = B for 3x3 A: Eigen::PartialPivLU<Matrix3d>(A).solve(B), which is what both
+// `B.transpose().partialPivLu().solve(tt)` (absolute_pose.cc:137) and `Ax.lu().solve(P)`
+// (re3q3.h:71,75,79 -- in Eigen 3 MatrixBase::lu() is a synonym of partialPivLu()) evaluate.
+// Operation order restated from Eigen 3.3's sources (the library itself is absent here, so this
+// is UNPINNED at the bit level): LU/PartialPivLU.h `unblocked_lu` (first maximum of |column| is the
+// pivot, whole rows swapped, multipliers by true division, rank-1 update of the trailing block),
+// then `solve` = row permutation, unit-lower and upper triangular solves by
+// products/TriangularSolverMatrix.h (right-looking per pivot: x_i = b_i * (1 / u_ii), then
+// b_r -= x_i * u_ri for the remaining rows).  B is 3 x NC, overwritten by X.
 template <int NC>
 void SolvePartialPiv3(double A[3][3], double B[3][NC]) {
+  int piv[3];
   for (int k = 0; k < 3; ++k) {
-    int piv = k;
+    int p = k;
     double best = std::fabs(A[k][k]);
     for (int i = k + 1; i < 3; ++i) {
       const double v = std::fabs(A[i][k]);
       if (v > best) {
         best = v;
-        piv = i;
+        p = i;
       }
     }
-    if (piv != k) {
-      for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[piv][j]);
-      for (int j = 0; j < NC; ++j) std::swap(B[k][j], B[piv][j]);
+    piv[k] = p;
+    if (best != 0.0) {
+      if (p != k)
+        for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[p][j]);
+      for (int i = k + 1; i < 3; ++i) A[i][k] = A[i][k] / A[k][k];
     }
-    for (int i = k + 1; i < 3; ++i) {
-      const double f = A[i][k] / A[k][k];
-      A[i][k] = f;
-      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
-      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
-    }
+    for (int i = k + 1; i < 3; ++i)
+      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - A[i][k] * A[k][j];
   }
-  for (int j = 0; j < NC; ++j) {
-    B[2][j] = B[2][j] / A[2][2];
-    B[1][j] = (B[1][j] - A[1][2] * B[2][j]) / A[1][1];
-    B[0][j] = (B[0][j] - A[0][1] * B[1][j] - A[0][2] * B[2][j]) / A[0][0];
+  for (int k = 0; k < 3; ++k)  // dst = P * rhs
+    if (piv[k] != k)
+      for (int j = 0; j < NC; ++j) std::swap(B[k][j], B[piv[k]][j]);
+  for (int i = 0; i < 3; ++i)  // unit lower
+    for (int j = 0; j < NC; ++j) {
+      const double b = B[i][j];
+      for (int r = i + 1; r < 3; ++r) B[r][j] = B[r][j] - b * A[r][i];
+    }
+  for (int i = 2; i >= 0; --i) {  // upper
+    const double a = 1.0 / A[i][i];
+    for (int j = 0; j < NC; ++j) {
+      const double b = B[i][j] * a;
+      B[i][j] = b;
+      for (int r = 0; r < i; ++r) B[r][j] = B[r][j] - b * A[r][i];
+    }
   }
 }
 
-// Solve A X = B for 3x3 A with FULL pivoting (Eigen::FullPivLU, which is what MatrixBase::lu()
-// returns — re3q3.h:71,75,79).  B is 3 x NC, overwritten by X.
-template <int NC>
-void SolveFullPiv3(double A[3][3], double B[3][NC]) {
-  int colperm[3] = {0, 1, 2};
-  for (int k = 0; k < 3; ++k) {
-    int pr = k, pc = k;
-    double best = -1.0;
-    for (int j = k; j < 3; ++j) {  // column-major scan, first maximum wins
-      for (int i = k; i < 3; ++i) {
-        const double v = std::fabs(A[i][j]);
-        if (v > best) {
-          best = v;
-          pr = i;
-          pc = j;
-        }
-      }
-    }
-    if (pr != k) {
-      for (int j = 0; j < 3; ++j) std::swap(A[k][j], A[pr][j]);
-      for (int j = 0; j < NC; ++j) std::swap(B[k][j], B[pr][j]);
-    }
-    if (pc != k) {
-      for (int i = 0; i < 3; ++i) std::swap(A[i][k], A[i][pc]);
-      std::swap(colperm[k], colperm[pc]);
-    }
-    for (int i = k + 1; i < 3; ++i) {
-      const double f = A[i][k] / A[k][k];
-      A[i][k] = f;
-      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
-      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
-    }
-  }
-  double X[3][NC];
-  for (int j = 0; j < NC; ++j) {
-    const double y2 = B[2][j] / A[2][2];
-    const double y1 = (B[1][j] - A[1][2] * y2) / A[1][1];
-    const double y0 = (B[0][j] - A[0][1] * y1 - A[0][2] * y2) / A[0][0];
-    X[colperm[0]][j] = y0;
-    X[colperm[1]][j] = y1;
-    X[colperm[2]][j] = y2;
-  }
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < NC; ++j) B[i][j] = X[i][j];
-}
-
-// ---------------------------------------------------------------------------------------------
-// Polynomial helpers: p[k] is the coefficient of x^k.
-// ---------------------------------------------------------------------------------------------
-// out (degree da+db) = a * b ; out[k] accumulates a[i]*b[k-i] for increasing i.
-template <int DA, int DB>
-inline void PolyMul(const double* a, const double* b, double* out) {
-  for (int k = 0; k <= DA + DB; ++k) {
-    double acc = 0.0;
-    bool first = true;
-    for (int i = 0; i <= DA; ++i) {
-      const int j = k - i;
-      if (j < 0 || j > DB) continue;
-      const double t = a[i] * b[j];
-      if (first) {
-        acc = t;
-        first = false;
-      } else {
-        acc = acc + t;
-      }
-    }
-    out[k] = acc;
-  }
-}
-template <int D>
-inline void PolyAdd(double* acc, const double* b) {
-  for (int k = 0; k <= D; ++k) acc[k] = acc[k] + b[k];
-}
-template <int D>
-inline void PolySub(double* acc, const double* b) {
-  for (int k = 0; k <= D; ++k) acc[k] = acc[k] - b[k];
-}
+// The hidden-variable resultant of re3q3 (re3q3.h:84-150, :177-188) as generated straight-line
+// code: one statement per IEEE operation of the reference's expressions, in their order.
+#define RE3Q3_FN inline
+#include "re3q3_resultant.inc"
+#undef RE3Q3_FN
 
 // ---------------------------------------------------------------------------------------------
 // Eigenvalues of the 8x8 companion matrix (re3q3.h:152-165: Eigen::EigenSolver<Matrix8d>).
@@ -543,92 +488,13 @@ int Re3q3Impl(double coeffs[3][10], double solutions[3][8], bool try_var_change)
       A[k][j] = (elim_var == 1) ? Ax[k][j] : (elim_var == 2) ? Ay[k][j] : Az[k][j];
     for (int j = 0; j < 7; ++j) P[k][j] = coeffs[k][kCols[elim_var - 1][j]];
   }
-  SolveFullPiv3<7>(A, P);
+  SolvePartialPiv3<7>(A, P);  // P = -A.lu().solve(P)  (:71-79)
   for (int k = 0; k < 3; ++k)
     for (int j = 0; j < 7; ++j) P[k][j] = -P[k][j];
 
-  // Now (naming after the permutation)
-  //   y^2 = py0 y + pz0 z + p10,  z^2 = py1 y + pz1 z + p11,  yz = py2 y + pz2 z + p12
-  // with polynomial coefficients in x (index = power of x).
-  double py[3][2], pz[3][2], p1[3][3];
-  for (int i = 0; i < 3; ++i) {
-    py[i][0] = P[i][4]; py[i][1] = P[i][1];
-    pz[i][0] = P[i][5]; pz[i][1] = P[i][2];
-    p1[i][0] = P[i][6]; p1[i][1] = P[i][3]; p1[i][2] = P[i][0];
-  }
-
-  // Hidden-variable resultant: M(x) [y z 1]^T = 0 from the three syzygies
-  //   z*(y^2) - y*(yz) = 0,   z*(yz) - y*(z^2) = 0,   (y^2)(z^2) - (yz)^2 = 0     (:84-137)
-  double m1y[3], m1z[3], m11[4], m2y[3], m2z[3], m21[4], m3y[4], m3z[4], m31[5];
-  double t2[3], t3[4];
-  // row 1
-  PolyMul<1, 1>(pz[0], py[1], m1y);
-  PolyMul<1, 1>(pz[2], py[2], t2); PolySub<2>(m1y, t2);
-  PolySub<2>(m1y, p1[2]);
-  PolyMul<1, 1>(py[0], pz[2], m1z);
-  PolyMul<1, 1>(pz[0], pz[1], t2); PolyAdd<2>(m1z, t2);
-  PolyMul<1, 1>(py[2], pz[0], t2); PolySub<2>(m1z, t2);
-  PolyMul<1, 1>(pz[2], pz[2], t2); PolySub<2>(m1z, t2);
-  PolyAdd<2>(m1z, p1[0]);
-  PolyMul<1, 2>(py[0], p1[2], m11);
-  PolyMul<1, 2>(pz[0], p1[1], t3); PolyAdd<3>(m11, t3);
-  PolyMul<1, 2>(py[2], p1[0], t3); PolySub<3>(m11, t3);
-  PolyMul<1, 2>(pz[2], p1[2], t3); PolySub<3>(m11, t3);
-  // row 2
-  PolyMul<1, 1>(py[2], py[2], m2y);
-  PolyMul<1, 1>(pz[2], py[1], t2); PolyAdd<2>(m2y, t2);
-  PolyMul<1, 1>(py[1], py[0], t2); PolySub<2>(m2y, t2);
-  PolyMul<1, 1>(pz[1], py[2], t2); PolySub<2>(m2y, t2);
-  PolySub<2>(m2y, p1[1]);
-  PolyMul<1, 1>(py[2], pz[2], m2z);
-  PolyMul<1, 1>(py[1], pz[0], t2); PolySub<2>(m2z, t2);
-  PolyAdd<2>(m2z, p1[2]);
-  PolyMul<1, 2>(py[2], p1[2], m21);
-  PolyMul<1, 2>(pz[2], p1[1], t3); PolyAdd<3>(m21, t3);
-  PolyMul<1, 2>(py[1], p1[0], t3); PolySub<3>(m21, t3);
-  PolyMul<1, 2>(pz[1], p1[2], t3); PolySub<3>(m21, t3);
-  // row 3: alpha y^2 + beta yz + gamma z^2 + (linear part), reduced once more
-  double al[3], be[3], ga[3];
-  PolyMul<1, 1>(py[0], py[1], al);
-  PolyMul<1, 1>(py[2], py[2], t2); PolySub<2>(al, t2);
-  PolyMul<1, 1>(py[0], pz[1], be);
-  PolyMul<1, 1>(pz[0], py[1], t2); PolyAdd<2>(be, t2);
-  PolyMul<1, 1>(py[2], pz[2], t2); PolySub<2>(be, t2); PolySub<2>(be, t2);
-  PolyMul<1, 1>(pz[0], pz[1], ga);
-  PolyMul<1, 1>(pz[2], pz[2], t2); PolySub<2>(ga, t2);
-  PolyMul<2, 1>(al, py[0], m3y);
-  PolyMul<2, 1>(be, py[2], t3); PolyAdd<3>(m3y, t3);
-  PolyMul<2, 1>(ga, py[1], t3); PolyAdd<3>(m3y, t3);
-  PolyMul<1, 2>(py[0], p1[1], t3); PolyAdd<3>(m3y, t3);
-  PolyMul<1, 2>(py[1], p1[0], t3); PolyAdd<3>(m3y, t3);
-  PolyMul<1, 2>(py[2], p1[2], t3); PolySub<3>(m3y, t3); PolySub<3>(m3y, t3);
-  PolyMul<2, 1>(al, pz[0], m3z);
-  PolyMul<2, 1>(be, pz[2], t3); PolyAdd<3>(m3z, t3);
-  PolyMul<2, 1>(ga, pz[1], t3); PolyAdd<3>(m3z, t3);
-  PolyMul<1, 2>(pz[0], p1[1], t3); PolyAdd<3>(m3z, t3);
-  PolyMul<1, 2>(pz[1], p1[0], t3); PolyAdd<3>(m3z, t3);
-  PolyMul<1, 2>(pz[2], p1[2], t3); PolySub<3>(m3z, t3); PolySub<3>(m3z, t3);
-  double t4[5];
-  PolyMul<2, 2>(al, p1[0], m31);
-  PolyMul<2, 2>(be, p1[2], t4); PolyAdd<4>(m31, t4);
-  PolyMul<2, 2>(ga, p1[1], t4); PolyAdd<4>(m31, t4);
-  PolyMul<2, 2>(p1[0], p1[1], t4); PolyAdd<4>(m31, t4);
-  PolyMul<2, 2>(p1[2], p1[2], t4); PolySub<4>(m31, t4);
-
-  // det M(x): degree 8 (:139-150)
-  double d[9], u6[7], w6[7], u5[6], w5[6], t8[9];
-  PolyMul<2, 4>(m2z, m31, u6);
-  PolyMul<3, 3>(m21, m3z, w6); PolySub<6>(u6, w6);
-  PolyMul<2, 6>(m1y, u6, d);
-  PolyMul<2, 4>(m2y, m31, u6);
-  PolyMul<3, 3>(m21, m3y, w6); PolySub<6>(u6, w6);
-  PolyMul<2, 6>(m1z, u6, t8); PolySub<8>(d, t8);
-  PolyMul<2, 3>(m2y, m3z, u5);
-  PolyMul<2, 3>(m2z, m3y, w5); PolySub<5>(u5, w5);
-  PolyMul<3, 5>(m11, u5, t8); PolyAdd<8>(d, t8);
-
-  double c[9];
-  for (int k = 0; k <= 8; ++k) c[k] = d[8 - k];  // c[0] = leading coefficient
+  // a11 ... a313 and c(0) ... c(8) = det M(x), literally the reference's expressions (:84-150)
+  double a[33], c[9];
+  re3q3_resultant(P, a, c);
 
   double re[8], im[8];
   Poly8Roots(c, re, im);
@@ -637,19 +503,8 @@ int Re3q3Impl(double coeffs[3][10], double solutions[3][8], bool try_var_change)
   for (int i = 0; i < 8; ++i) {
     if (std::fabs(im[i]) > 1e-8) continue;  // (:173)
     const double xs1 = re[i];
-    const double xs2 = xs1 * xs1;
-    const double xs3 = xs1 * xs2;
-    const double xs4 = xs1 * xs3;
-    (void)xs4;
-    const double A00 = m1y[2] * xs2 + m1y[1] * xs1 + m1y[0];
-    const double A01 = m1z[2] * xs2 + m1z[1] * xs1 + m1z[0];
-    const double A02 = m11[3] * xs3 + m11[2] * xs2 + m11[1] * xs1 + m11[0];
-    const double A10 = m2y[2] * xs2 + m2y[1] * xs1 + m2y[0];
-    const double A11 = m2z[2] * xs2 + m2z[1] * xs1 + m2z[0];
-    const double A12 = m21[3] * xs3 + m21[2] * xs2 + m21[1] * xs1 + m21[0];
-    solutions[0][root_cnt] = xs1;
-    solutions[1][root_cnt] = (A12 * A01 - A02 * A11) / (A00 * A11 - A10 * A01);
-    solutions[2][root_cnt] = (A12 * A00 - A02 * A10) / (A01 * A10 - A11 * A00);
+    solutions[0][root_cnt] = xs1;  // (:177-188)
+    re3q3_backsubstitute(a, xs1, &solutions[1][root_cnt], &solutions[2][root_cnt]);
     ++root_cnt;
   }
   if (elim_var == 2) {
@@ -997,6 +852,21 @@ int orc_poly8_all_roots(const double* c, double* re_im_out) {
     re_im_out[2 * i + 1] = im[i];
   }
   return ok ? 8 : -1;
+}
+
+void orc_re3q3_resultant(const double* P, double* a_out, double* c_out) {
+  double Pm[3][7], a[33], c[9];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 7; ++j) Pm[i][j] = P[7 * i + j];
+  re3q3_resultant(Pm, a, c);
+  for (int i = 0; i < 33; ++i) a_out[i] = a[i];
+  for (int i = 0; i < 9; ++i) c_out[i] = c[i];
+}
+
+void orc_re3q3_backsubstitute(const double* a_in, double x, double* yz_out) {
+  double a[33];
+  for (int i = 0; i < 33; ++i) a[i] = a_in[i];
+  re3q3_backsubstitute(a, x, &yz_out[0], &yz_out[1]);
 }
 
 int orc_poly8_real_roots(const double* c, double* roots_out) {

@@ -9,11 +9,15 @@
  *   - line residual / support / sampler / RANSAC control flow: restated 1:1 from reference
  *     sources that are fully in-tree (no third-party arithmetic) — pinned by construction and
  *     by known-answer tests.
- *   - P6L + re3q3: the reference calls Eigen (determinant, PartialPivLU, FullPivLU,
- *     EigenSolver) which is NOT in /root/reference and not installed; the algorithm is restated
- *     from the published method (EISPACK hqr lineage).  Pinned against the reference's own
- *     known-answer properties (lib/re3q3/test_re3q3.cpp) and numpy.roots; bit-level parity with
- *     an Eigen build is UNPINNED.
+ *   - P6L + re3q3: every expression the reference writes out itself (tt / Rcoeffs rows,
+ *     rotation_to_e3q3, the 33 resultant coefficients a11..a313, c(0)..c(8), A(x), the Cramer
+ *     quotients, cayley_param) is evaluated operation by operation in the reference's order
+ *     (re3q3_resultant.inc is generated from re3q3.h:84-150 and pinned to those expressions by
+ *     tests/golden/re3q3_resultant_vectors.json).  What the reference delegates to Eigen
+ *     (3x3 determinant, PartialPivLU::solve, the 3x3 * 3x9 products, EigenSolver<8x8>) is NOT in
+ *     /root/reference and not installed: restated from Eigen 3.3's algorithms; pinned by the
+ *     reference's known-answer properties (lib/re3q3/test_re3q3.cpp) and numpy.roots; bit-level
+ *     parity with an Eigen build is UNPINNED for exactly those calls.
  *   - BA / pose refinement: Ceres is not in /root/reference; parity UNPINNED (see ba_oracle.h).
  *
  * Layout conventions (shared with include/ppsfm_b200.h):
@@ -79,6 +83,11 @@ void orc_sample_table(size_t n, size_t num_trials, uint32_t* table_out /* num_tr
 /* lib/re3q3/re3q3/re3q3.h:16-200.  coeffs: 3x10 row-major (row = equation, monomial order
  * x^2 xy xz y^2 yz z^2 x y z 1).  solutions: 3x8 column-major (solution k at [3k..3k+2]). */
 int orc_re3q3(const double* coeffs, double* solutions);
+/* re3q3.h:84-150: P (3x7 row-major, after `P = -A.lu().solve(P)`) -> a11..a313 (33) and c(0..8);
+ * re3q3.h:177-188: y, z for a root x.  Hooks for tests/golden/re3q3_resultant_vectors.json, which
+ * holds the REFERENCE's own expressions evaluated in IEEE double by tests/golden/make_re3q3_golden.py. */
+void orc_re3q3_resultant(const double* P, double* a_out, double* c_out);
+void orc_re3q3_backsubstitute(const double* a, double x, double* yz_out);
 /* real roots of c[0] x^8 + ... + c[8] as the re3q3 companion/eigenvalue step returns them
  * (|imag| <= 1e-8, Schur-diagonal order).  Returns the count. */
 int orc_poly8_real_roots(const double* c, double* roots_out);

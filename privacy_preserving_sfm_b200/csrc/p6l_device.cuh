@@ -6,8 +6,10 @@
 // Numerical contract: this translation unit is compiled with --fmad=false and every expression
 // below is evaluated in a fixed order, so that the models are bit-identical to the CPU oracle's
 // (oracle/ppsfm_oracle.cc), which in turn follows the reference's FMA-free x86-64 build.
-// The Eigen calls of the reference (3x3 determinant, PartialPivLU, FullPivLU, EigenSolver<8x8>)
-// are realised as: cofactor determinant, row-pivoted / fully-pivoted Gaussian elimination, and
+// The expressions the reference writes out itself (re3q3.h:84-150, :177-188) are generated code in
+// the reference's own evaluation order (re3q3_resultant.inc).  The Eigen calls of the reference
+// (3x3 determinant, PartialPivLU::solve -- `lu()` is its synonym --, EigenSolver<8x8>) are
+// realised as: cofactor determinant, Eigen 3.3's unblocked row-pivoted LU + triangular solves, and
 // Francis double-shift QR on the (already Hessenberg) companion matrix with eigenvalues read off
 // the real Schur form top-to-bottom.
 #pragma once
@@ -32,118 +34,76 @@ PPSFM_DI void swapd(double& a, double& b) {
   b = t;
 }
 
-// A X = B, 3x3, row pivoting (PartialPivLU::solve, absolute_pose.cc:137)
+// A X = B, 3x3: Eigen::PartialPivLU<Matrix3d>(A).solve(B) -- absolute_pose.cc:137 and
+// re3q3.h:71-79 (`lu()` is Eigen 3's synonym of partialPivLu()).  Operation order of Eigen 3.3's
+// unblocked_lu + permutation + unit-lower / upper triangular solves (x_i = b_i * (1 / u_ii), then
+// b_r -= x_i * u_ri), identical to oracle/ppsfm_oracle.cc SolvePartialPiv3.
 template <int NC>
 __device__ void solve_partial_piv3(double A[3][3], double B[3][NC]) {
-#pragma unroll 1
+  int piv[3];
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    int piv = k;
+    int p = k;
     double best = fabs(A[k][k]);
+#pragma unroll
     for (int i = k + 1; i < 3; ++i) {
       const double v = fabs(A[i][k]);
       if (v > best) {
         best = v;
-        piv = i;
+        p = i;
       }
     }
-    if (piv != k) {
-      for (int j = 0; j < 3; ++j) swapd(A[k][j], A[piv][j]);
-      for (int j = 0; j < NC; ++j) swapd(B[k][j], B[piv][j]);
-    }
-    for (int i = k + 1; i < 3; ++i) {
-      const double f = A[i][k] / A[k][k];
-      A[i][k] = f;
-      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
-      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
-    }
-  }
-  for (int j = 0; j < NC; ++j) {
-    B[2][j] = B[2][j] / A[2][2];
-    B[1][j] = (B[1][j] - A[1][2] * B[2][j]) / A[1][1];
-    B[0][j] = (B[0][j] - A[0][1] * B[1][j] - A[0][2] * B[2][j]) / A[0][0];
-  }
-}
-
-// A X = B, 3x3, full pivoting (MatrixBase::lu() == FullPivLU, re3q3.h:71-79)
-template <int NC>
-__device__ void solve_full_piv3(double A[3][3], double B[3][NC]) {
-  int colperm[3] = {0, 1, 2};
-#pragma unroll 1
-  for (int k = 0; k < 3; ++k) {
-    int pr = k, pc = k;
-    double best = -1.0;
-    for (int j = k; j < 3; ++j) {
-      for (int i = k; i < 3; ++i) {
-        const double v = fabs(A[i][j]);
-        if (v > best) {
-          best = v;
-          pr = i;
-          pc = j;
+    piv[k] = p;
+    if (best != 0.0) {
+#pragma unroll
+      for (int i = k + 1; i < 3; ++i)
+        if (p == i) {
+#pragma unroll
+          for (int j = 0; j < 3; ++j) swapd(A[k][j], A[i][j]);
         }
+#pragma unroll
+      for (int i = k + 1; i < 3; ++i) A[i][k] = A[i][k] / A[k][k];
+    }
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i)
+#pragma unroll
+      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - A[i][k] * A[k][j];
+  }
+#pragma unroll
+  for (int k = 0; k < 2; ++k)  // dst = P * rhs
+#pragma unroll
+    for (int i = k + 1; i < 3; ++i)
+      if (piv[k] == i) {
+#pragma unroll
+        for (int j = 0; j < NC; ++j) swapd(B[k][j], B[i][j]);
       }
+#pragma unroll
+  for (int i = 0; i < 3; ++i)  // unit lower
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const double b = B[i][j];
+#pragma unroll
+      for (int r = i + 1; r < 3; ++r) B[r][j] = B[r][j] - b * A[r][i];
     }
-    if (pr != k) {
-      for (int j = 0; j < 3; ++j) swapd(A[k][j], A[pr][j]);
-      for (int j = 0; j < NC; ++j) swapd(B[k][j], B[pr][j]);
-    }
-    if (pc != k) {
-      for (int i = 0; i < 3; ++i) swapd(A[i][k], A[i][pc]);
-      const int t = colperm[k];
-      colperm[k] = colperm[pc];
-      colperm[pc] = t;
-    }
-    for (int i = k + 1; i < 3; ++i) {
-      const double f = A[i][k] / A[k][k];
-      A[i][k] = f;
-      for (int j = k + 1; j < 3; ++j) A[i][j] = A[i][j] - f * A[k][j];
-      for (int j = 0; j < NC; ++j) B[i][j] = B[i][j] - f * B[k][j];
+#pragma unroll
+  for (int i = 2; i >= 0; --i) {  // upper
+    const double a = 1.0 / A[i][i];
+#pragma unroll
+    for (int j = 0; j < NC; ++j) {
+      const double b = B[i][j] * a;
+      B[i][j] = b;
+#pragma unroll
+      for (int r = 0; r < i; ++r) B[r][j] = B[r][j] - b * A[r][i];
     }
   }
-  double X[3][NC];
-  for (int j = 0; j < NC; ++j) {
-    const double y2 = B[2][j] / A[2][2];
-    const double y1 = (B[1][j] - A[1][2] * y2) / A[1][1];
-    const double y0 = (B[0][j] - A[0][1] * y1 - A[0][2] * y2) / A[0][0];
-    X[colperm[0]][j] = y0;
-    X[colperm[1]][j] = y1;
-    X[colperm[2]][j] = y2;
-  }
-  for (int i = 0; i < 3; ++i)
-    for (int j = 0; j < NC; ++j) B[i][j] = X[i][j];
 }
 
-// ---- polynomial helpers, p[k] = coefficient of x^k ----------------------------------------
-template <int DA, int DB>
-PPSFM_DI void poly_mul(const double* a, const double* b, double* out) {
-#pragma unroll
-  for (int k = 0; k <= DA + DB; ++k) {
-    double acc = 0.0;
-    bool first = true;
-#pragma unroll
-    for (int i = 0; i <= DA; ++i) {
-      const int j = k - i;
-      if (j < 0 || j > DB) continue;
-      const double t = a[i] * b[j];
-      if (first) {
-        acc = t;
-        first = false;
-      } else {
-        acc = acc + t;
-      }
-    }
-    out[k] = acc;
-  }
-}
-template <int D>
-PPSFM_DI void poly_add(double* acc, const double* b) {
-#pragma unroll
-  for (int k = 0; k <= D; ++k) acc[k] = acc[k] + b[k];
-}
-template <int D>
-PPSFM_DI void poly_sub(double* acc, const double* b) {
-#pragma unroll
-  for (int k = 0; k <= D; ++k) acc[k] = acc[k] - b[k];
-}
+// The hidden-variable resultant (re3q3.h:84-150) and the back-substitution for a root
+// (:177-188): generated three-address code, one IEEE operation per statement in the reference's
+// evaluation order (scripts/gen_re3q3_resultant.py); the oracle includes the same text.
+#define RE3Q3_FN __device__ __forceinline__
+#include "re3q3_resultant.inc"
+#undef RE3Q3_FN
 
 // ---- 8x8 Hessenberg QR (Francis double shift), eigenvalues only ------------------------------
 struct Hqr8 {
@@ -429,87 +389,12 @@ __device__ int re3q3_core(const double coeffs[3][10], int elim_var, double solut
     }
     for (int j = 0; j < 7; ++j) P[k][j] = coeffs[k][kRe3q3Cols[elim_var - 1][j]];
   }
-  solve_full_piv3<7>(A, P);
+  solve_partial_piv3<7>(A, P);  // P = -A.lu().solve(P)
   for (int k = 0; k < 3; ++k)
     for (int j = 0; j < 7; ++j) P[k][j] = -P[k][j];
 
-  double py[3][2], pz[3][2], p1[3][3];
-  for (int i = 0; i < 3; ++i) {
-    py[i][0] = P[i][4]; py[i][1] = P[i][1];
-    pz[i][0] = P[i][5]; pz[i][1] = P[i][2];
-    p1[i][0] = P[i][6]; p1[i][1] = P[i][3]; p1[i][2] = P[i][0];
-  }
-
-  double m1y[3], m1z[3], m11[4], m2y[3], m2z[3], m21[4], m3y[4], m3z[4], m31[5];
-  double t2[3], t3[4];
-  // row 1:  z*(y^2) - y*(yz)
-  poly_mul<1, 1>(pz[0], py[1], m1y);
-  poly_mul<1, 1>(pz[2], py[2], t2); poly_sub<2>(m1y, t2);
-  poly_sub<2>(m1y, p1[2]);
-  poly_mul<1, 1>(py[0], pz[2], m1z);
-  poly_mul<1, 1>(pz[0], pz[1], t2); poly_add<2>(m1z, t2);
-  poly_mul<1, 1>(py[2], pz[0], t2); poly_sub<2>(m1z, t2);
-  poly_mul<1, 1>(pz[2], pz[2], t2); poly_sub<2>(m1z, t2);
-  poly_add<2>(m1z, p1[0]);
-  poly_mul<1, 2>(py[0], p1[2], m11);
-  poly_mul<1, 2>(pz[0], p1[1], t3); poly_add<3>(m11, t3);
-  poly_mul<1, 2>(py[2], p1[0], t3); poly_sub<3>(m11, t3);
-  poly_mul<1, 2>(pz[2], p1[2], t3); poly_sub<3>(m11, t3);
-  // row 2:  z*(yz) - y*(z^2)
-  poly_mul<1, 1>(py[2], py[2], m2y);
-  poly_mul<1, 1>(pz[2], py[1], t2); poly_add<2>(m2y, t2);
-  poly_mul<1, 1>(py[1], py[0], t2); poly_sub<2>(m2y, t2);
-  poly_mul<1, 1>(pz[1], py[2], t2); poly_sub<2>(m2y, t2);
-  poly_sub<2>(m2y, p1[1]);
-  poly_mul<1, 1>(py[2], pz[2], m2z);
-  poly_mul<1, 1>(py[1], pz[0], t2); poly_sub<2>(m2z, t2);
-  poly_add<2>(m2z, p1[2]);
-  poly_mul<1, 2>(py[2], p1[2], m21);
-  poly_mul<1, 2>(pz[2], p1[1], t3); poly_add<3>(m21, t3);
-  poly_mul<1, 2>(py[1], p1[0], t3); poly_sub<3>(m21, t3);
-  poly_mul<1, 2>(pz[1], p1[2], t3); poly_sub<3>(m21, t3);
-  // row 3:  (y^2)(z^2) - (yz)^2
-  double al[3], be[3], ga[3];
-  poly_mul<1, 1>(py[0], py[1], al);
-  poly_mul<1, 1>(py[2], py[2], t2); poly_sub<2>(al, t2);
-  poly_mul<1, 1>(py[0], pz[1], be);
-  poly_mul<1, 1>(pz[0], py[1], t2); poly_add<2>(be, t2);
-  poly_mul<1, 1>(py[2], pz[2], t2); poly_sub<2>(be, t2); poly_sub<2>(be, t2);
-  poly_mul<1, 1>(pz[0], pz[1], ga);
-  poly_mul<1, 1>(pz[2], pz[2], t2); poly_sub<2>(ga, t2);
-  poly_mul<2, 1>(al, py[0], m3y);
-  poly_mul<2, 1>(be, py[2], t3); poly_add<3>(m3y, t3);
-  poly_mul<2, 1>(ga, py[1], t3); poly_add<3>(m3y, t3);
-  poly_mul<1, 2>(py[0], p1[1], t3); poly_add<3>(m3y, t3);
-  poly_mul<1, 2>(py[1], p1[0], t3); poly_add<3>(m3y, t3);
-  poly_mul<1, 2>(py[2], p1[2], t3); poly_sub<3>(m3y, t3); poly_sub<3>(m3y, t3);
-  poly_mul<2, 1>(al, pz[0], m3z);
-  poly_mul<2, 1>(be, pz[2], t3); poly_add<3>(m3z, t3);
-  poly_mul<2, 1>(ga, pz[1], t3); poly_add<3>(m3z, t3);
-  poly_mul<1, 2>(pz[0], p1[1], t3); poly_add<3>(m3z, t3);
-  poly_mul<1, 2>(pz[1], p1[0], t3); poly_add<3>(m3z, t3);
-  poly_mul<1, 2>(pz[2], p1[2], t3); poly_sub<3>(m3z, t3); poly_sub<3>(m3z, t3);
-  double t4[5];
-  poly_mul<2, 2>(al, p1[0], m31);
-  poly_mul<2, 2>(be, p1[2], t4); poly_add<4>(m31, t4);
-  poly_mul<2, 2>(ga, p1[1], t4); poly_add<4>(m31, t4);
-  poly_mul<2, 2>(p1[0], p1[1], t4); poly_add<4>(m31, t4);
-  poly_mul<2, 2>(p1[2], p1[2], t4); poly_sub<4>(m31, t4);
-
-  // det M(x)
-  double d[9], u6[7], w6[7], u5[6], w5[6], t8[9];
-  poly_mul<2, 4>(m2z, m31, u6);
-  poly_mul<3, 3>(m21, m3z, w6); poly_sub<6>(u6, w6);
-  poly_mul<2, 6>(m1y, u6, d);
-  poly_mul<2, 4>(m2y, m31, u6);
-  poly_mul<3, 3>(m21, m3y, w6); poly_sub<6>(u6, w6);
-  poly_mul<2, 6>(m1z, u6, t8); poly_sub<8>(d, t8);
-  poly_mul<2, 3>(m2y, m3z, u5);
-  poly_mul<2, 3>(m2z, m3y, w5); poly_sub<5>(u5, w5);
-  poly_mul<3, 5>(m11, u5, t8); poly_add<8>(d, t8);
-
-  double c[9];
-  for (int k = 0; k <= 8; ++k) c[k] = d[8 - k];
+  double a[33], c[9];
+  re3q3_resultant(P, a, c);  // a11 ... a313, c(0) ... c(8)
 
   double re[8], im[8];
   poly8_roots(c, re, im);
@@ -518,17 +403,8 @@ __device__ int re3q3_core(const double coeffs[3][10], int elim_var, double solut
   for (int i = 0; i < 8; ++i) {
     if (fabs(im[i]) > 1e-8) continue;
     const double xs1 = re[i];
-    const double xs2 = xs1 * xs1;
-    const double xs3 = xs1 * xs2;
-    const double A00 = m1y[2] * xs2 + m1y[1] * xs1 + m1y[0];
-    const double A01 = m1z[2] * xs2 + m1z[1] * xs1 + m1z[0];
-    const double A02 = m11[3] * xs3 + m11[2] * xs2 + m11[1] * xs1 + m11[0];
-    const double A10 = m2y[2] * xs2 + m2y[1] * xs1 + m2y[0];
-    const double A11 = m2z[2] * xs2 + m2z[1] * xs1 + m2z[0];
-    const double A12 = m21[3] * xs3 + m21[2] * xs2 + m21[1] * xs1 + m21[0];
     solutions[0][root_cnt] = xs1;
-    solutions[1][root_cnt] = (A12 * A01 - A02 * A11) / (A00 * A11 - A10 * A01);
-    solutions[2][root_cnt] = (A12 * A00 - A02 * A10) / (A01 * A10 - A11 * A00);
+    re3q3_backsubstitute(a, xs1, &solutions[1][root_cnt], &solutions[2][root_cnt]);
     ++root_cnt;
   }
   if (elim_var == 2) {
