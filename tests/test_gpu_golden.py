@@ -1,0 +1,80 @@
+"""The CUDA path against the committed golden vectors (tests/golden/*.json), without the oracle in
+the loop: RANSAC reports / masks / generator state, line residuals and P6L solutions bit for bit,
+the small BA solve to its floating-point tolerance, and the re3q3 resultant vectors (the
+reference's own expressions, tests/golden/make_re3q3_golden.py) through the batched P6L kernel's
+building blocks where they are reachable from the C-ABI."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import privacy_preserving_sfm_b200 as pp
+from privacy_preserving_sfm_b200 import RANSACOptions, bundle_adjustment as ba, synthetic as S
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _gold():
+    with open(os.path.join(HERE, "golden", "oracle_vectors.json")) as f:
+        return json.load(f)
+
+
+def _hexes(a):
+    return [float(x).hex() for x in np.asarray(a, dtype=np.float64).ravel()]
+
+
+def test_gpu_ransac_reproduces_golden(ctx):
+    gold = _gold()
+    assert len(gold["ransac"]) >= 4
+    for name, case in gold["ransac"].items():
+        sc = S.make_abs_pose_scene(**case["scene"])
+        me, mir, conf, mult, tmin, tmax = case["options"]
+        o = RANSACOptions(max_error=me, min_inlier_ratio=mir, confidence=conf,
+                          dyn_num_trials_multiplier=mult, min_num_trials=int(tmin),
+                          max_num_trials=int(tmax))
+        ctx.set_prng_seed(0)
+        rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+        got = {
+            "success": int(rep.success), "num_trials": int(rep.num_trials),
+            "num_inliers": int(rep.num_inliers), "residual_sum": float(rep.residual_sum).hex(),
+            "best_trial": int(rep.best_trial), "best_model_idx": int(rep.best_model_idx),
+            "num_models_scored": int(rep.num_models_scored), "model": _hexes(list(rep.model)),
+            "mask_sha256": hashlib.sha256(np.asarray(mask, np.uint8).tobytes()).hexdigest(),
+            "prng_peek_after": int(ctx.prng_peek()),
+        }
+        assert got == case["expect"], name
+
+
+def test_gpu_residuals_and_p6l_reproduce_golden(ctx):
+    gold = _gold()
+    sc = S.make_abs_pose_scene(n=500, inlier_ratio=0.5, seed=105)
+    P = np.concatenate([sc["R"].T.reshape(9), sc["t"]])
+    res, cnt, _ = ctx.line_residuals(sc["lines"], sc["points"], P[None, :], 0.012 ** 2)
+    g = gold["line_residuals"]
+    assert hashlib.sha256(res[0].tobytes()).hexdigest() == g["residuals_sha256"]
+    assert _hexes(res[0][:8]) == g["first8"] and int(cnt[0]) == g["num_le_thr"]
+    probs = S.make_p6l_minimal_problems(8, seed=106)
+    for p, want in zip(probs, gold["p6l_estimate"]):
+        models, nm = ctx.p6l_solve_batch(p["lines"], np.zeros(6, np.uint8), p["points"],
+                                         np.arange(6, dtype=np.uint32)[None, :])
+        assert [_hexes(m) for m in models[0, :nm[0]]] == want
+
+
+def test_gpu_ba_reproduces_golden(ctx):
+    g = _gold()["ba_solve_single_thread"]
+    sb = S.make_ba_scene(num_cams=6, num_points=200, obs_per_point=4, seed=107)
+    flags = np.zeros(6, np.uint8)
+    flags[0], flags[1] = 1, 2
+    a = ba.BaArrays(sb["qvecs"], sb["tvecs"], sb["points"], sb["obs_cam"], sb["obs_pt"],
+                    sb["obs_line"], [1], [sb["cam_params"]], pose_flags=flags)
+    ok, s = ba.solve_arrays(ctx, a, ba.default_solver_options(max_num_iterations=20,
+                                                              gradient_tolerance=1e-4))
+    assert ok == g["ok"]
+    assert (s.num_successful_steps, s.num_unsuccessful_steps, s.termination_type) == \
+        (g["successful_steps"], g["unsuccessful_steps"], g["termination_type"])
+    ic, fc = float.fromhex(g["initial_cost"]), float.fromhex(g["final_cost"])
+    assert abs(s.initial_cost - ic) <= 1e-11 * ic       # floating-point path: tolerance, not bits
+    assert abs(s.final_cost - fc) <= 1e-9 * fc
