@@ -325,7 +325,11 @@ int ppsfm_initialize_reconstruction(const double* lines, const uint8_t* aligned,
  * by FilterPoints3DWithSmallTriangulationAngle :594-648) and
  * Reconstruction::FilterObservationsWithNegativeDepth (:442-460).  Outputs are delete masks the
  * caller applies to its Reconstruction (DeleteObservation / DeletePoint3D) and the value the
- * reference returns (num_filtered); point_error [P] is in/out (Point3D::SetError for survivors).
+ * reference returns (num_filtered); point_error [P] is in/out (Point3D::SetError for survivors:
+ * error sum / REMAINING track length, :706-713).  The negative-depth filter follows
+ * DeleteObservation's cascade (:255-275): a point whose track is down to <= 3 elements when one
+ * of its observations is deleted goes away as a whole (point_deleted [P], may be NULL; all its
+ * observations are flagged) and its later observations are not counted.
  * ============================================================================================= */
 typedef struct ppsfm_filter_problem {
   int32_t num_images;
@@ -350,7 +354,8 @@ int ppsfm_filter_points3d(ppsfm_ctx* ctx, const ppsfm_filter_problem* problem,
                           uint8_t* point_deleted, double* point_error, size_t* num_filtered);
 int ppsfm_filter_observations_with_negative_depth(ppsfm_ctx* ctx,
                                                   const ppsfm_filter_problem* problem,
-                                                  uint8_t* obs_deleted, size_t* num_filtered);
+                                                  uint8_t* obs_deleted, uint8_t* point_deleted,
+                                                  size_t* num_filtered);
 
 /* =============================================================================================
  * Batched robust line triangulation: EstimateTriangulation

@@ -431,11 +431,14 @@ def filter_points3d(problem, max_reproj_error, min_tri_angle, point_error=None):
 def filter_negative_depth(problem):
     L = lib()
     O = len(problem.obs_image)
+    P = len(problem.points)
     od = np.zeros(max(O, 1), np.uint8)
+    pd = np.zeros(max(P, 1), np.uint8)
     nf = C.c_uint64(0)
-    L.orc_filter_negative_depth.argtypes = [C.c_void_p, _u8p, C.POINTER(C.c_uint64)]
-    L.orc_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p), C.byref(nf))
-    return nf.value, od[:O]
+    L.orc_filter_negative_depth.argtypes = [C.c_void_p, _u8p, _u8p, C.POINTER(C.c_uint64)]
+    L.orc_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p),
+                                pd.ctypes.data_as(_u8p), C.byref(nf))
+    return nf.value, od[:O], pd[:P]
 
 
 # ---- batched line triangulation (triangulation_oracle.cc) -------------------------------------

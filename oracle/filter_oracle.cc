@@ -151,7 +151,7 @@ int orc_filter_points3d(const FilterProblem* pbp, double max_reproj_error, doubl
         total += (uint64_t)len;
       } else {
         total += (uint64_t)nd;
-        point_error[p] = sum / (double)len;
+        point_error[p] = sum / (double)(len - nd);  // after DeleteObservation (:706-713)
       }
     }
     if (!deleted) {
@@ -180,20 +180,45 @@ int orc_filter_points3d(const FilterProblem* pbp, double max_reproj_error, doubl
   return 0;
 }
 
-int orc_filter_negative_depth(const FilterProblem* pbp, uint8_t* obs_deleted, uint64_t* num_filtered) {
+// reconstruction.cc:442-460 with DeleteObservation (:255-275) simulated literally: images in
+// index order, the observations of an image in input order; an observation whose point is gone
+// "has no point" and is skipped.
+int orc_filter_negative_depth(const FilterProblem* pbp, uint8_t* obs_deleted,
+                              uint8_t* point_deleted, uint64_t* num_filtered) {
   const FilterProblem& pb = *pbp;
+  std::vector<int> obs_point((size_t)pb.num_obs);
+  std::vector<int64_t> length((size_t)pb.num_points);
+  std::vector<uint8_t> alive((size_t)pb.num_points, 1);
+  for (int p = 0; p < pb.num_points; ++p) {
+    length[p] = pb.track_start[p + 1] - pb.track_start[p];
+    for (int64_t k = pb.track_start[p]; k < pb.track_start[p + 1]; ++k) obs_point[k] = p;
+  }
+  std::vector<std::vector<int64_t>> by_image((size_t)pb.num_images);
+  for (int64_t k = 0; k < pb.num_obs; ++k) by_image[pb.obs_image[k]].push_back(k);
+  for (int64_t k = 0; k < pb.num_obs; ++k) obs_deleted[k] = 0;
   uint64_t total = 0;
-  for (int p = 0; p < pb.num_points; ++p)
-    for (int64_t k = pb.track_start[p]; k < pb.track_start[p + 1]; ++k) {
-      double R[9];
-      const int img = pb.obs_image[k];
-      RotationOf(pb.qvecs + 4 * (size_t)img, R);
+  for (int img = 0; img < pb.num_images; ++img) {
+    double R[9];
+    RotationOf(pb.qvecs + 4 * (size_t)img, R);
+    for (const int64_t k : by_image[img]) {
+      const int p = obs_point[k];
+      if (!alive[p] || obs_deleted[k]) continue;  // !line.HasPoint3D()
       const double* X = pb.points + 3 * (size_t)p;
       const double pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + pb.tvecs[3 * (size_t)img + 2];
-      const bool del = !(pz >= DBL_EPSILON);
-      obs_deleted[k] = del ? 1 : 0;
-      total += del ? 1 : 0;
+      if (pz >= DBL_EPSILON) continue;            // HasPointPositiveDepth
+      // DeleteObservation
+      if (length[p] <= 3) {
+        alive[p] = 0;                             // DeletePoint3D: every line of the track reset
+        for (int64_t j = pb.track_start[p]; j < pb.track_start[p + 1]; ++j) obs_deleted[j] = 1;
+      } else {
+        length[p] -= 1;
+        obs_deleted[k] = 1;
+      }
+      total += 1;
     }
+  }
+  if (point_deleted)
+    for (int p = 0; p < pb.num_points; ++p) point_deleted[p] = alive[p] ? 0 : 1;
   *num_filtered = total;
   return 0;
 }

@@ -132,7 +132,8 @@ filter_points_kernel(FilterDev d, double max_sq_error, double min_tri_angle_rad)
       filtered = (unsigned long long)len;
     } else {
       filtered = (unsigned long long)nd;
-      d.point_error[p] = sum / (double)len;
+      // SetError after the DeleteObservation calls: the track is already shorter (:706-713)
+      d.point_error[p] = sum / (double)(len - nd);
     }
   }
   if (!deleted) {
@@ -161,18 +162,38 @@ filter_points_kernel(FilterDev d, double max_sq_error, double min_tri_angle_rad)
   if (filtered) atomicAdd(d.num_filtered, filtered);
 }
 
-// FilterObservationsWithNegativeDepth (reconstruction.cc:442-460): thread per observation
-__global__ void filter_depth_kernel(FilterDev d, const int* __restrict__ obs_point) {
-  const int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= d.O) return;
-  double R[9];
-  const int img = d.obs_image[k];
-  rotation_of(d.q + 4 * (size_t)img, R);
-  const double* X = d.X + 3 * (size_t)obs_point[k];
-  const double pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + d.t[3 * (size_t)img + 2];
-  const bool del = !(pz >= DBL_EPSILON);
-  d.obs_deleted[k] = del ? 1 : 0;
-  if (del) atomicAdd(d.num_filtered, 1ull);
+// FilterObservationsWithNegativeDepth (reconstruction.cc:442-460): thread per point.
+// Every negative-depth observation goes through DeleteObservation (:255-275), which deletes the
+// whole point when its track is down to <= 3 elements; the later observations of that point no
+// longer "have a point" and are neither visited nor counted.  Per point with track length len and
+// n negative-depth observations the sequential loop therefore counts min(n, max(1, len - 2))
+// deletions, and the point dies iff n >= max(1, len - 2) -- whatever the image order.
+__global__ void __launch_bounds__(128) filter_depth_kernel(FilterDev d) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= d.P) return;
+  const int64_t k0 = d.track_start[p], k1 = d.track_start[p + 1];
+  const int64_t len = k1 - k0;
+  d.point_deleted[p] = 0;
+  if (len == 0) return;
+  const double* X = d.X + 3 * (size_t)p;
+  int64_t n = 0;
+  for (int64_t k = k0; k < k1; ++k) {
+    double R[9];
+    const int img = d.obs_image[k];
+    rotation_of(d.q + 4 * (size_t)img, R);
+    const double pz = R[6] * X[0] + R[7] * X[1] + R[8] * X[2] + d.t[3 * (size_t)img + 2];
+    const bool del = !(pz >= DBL_EPSILON);
+    d.obs_deleted[k] = del ? 1 : 0;
+    n += del ? 1 : 0;
+  }
+  if (n == 0) return;
+  const int64_t fatal = len - 2 > 1 ? len - 2 : 1;
+  if (n >= fatal) {
+    for (int64_t k = k0; k < k1; ++k) d.obs_deleted[k] = 1;
+    d.point_deleted[p] = 1;
+    n = fatal;
+  }
+  atomicAdd(d.num_filtered, (unsigned long long)n);
 }
 
 struct Uploader {
@@ -250,19 +271,11 @@ int run(ppsfm_ctx* ctx, const ppsfm_filter_problem* pb, bool depth_only, double 
   d.point_deleted = u.up((const uint8_t*)nullptr, (size_t)P);
   d.point_error = u.up(point_error, (size_t)P);
   d.num_filtered = u.up((const unsigned long long*)nullptr, 1);
-  int* obs_point = nullptr;
-  std::vector<int> obs_point_h;
-  if (depth_only) {
-    obs_point_h.resize(O);
-    for (int p = 0; p < P; ++p)
-      for (int64_t k = pb->track_start[p]; k < pb->track_start[p + 1]; ++k) obs_point_h[k] = p;
-    obs_point = u.up(obs_point_h.data(), (size_t)O);
-  }
   PPSFM_CUDA(ctx, u.err);
   PPSFM_CUDA(ctx, cudaMemsetAsync(d.obs_deleted, 0, (size_t)(O ? O : 1), s));
   PPSFM_CUDA(ctx, cudaMemsetAsync(d.num_filtered, 0, sizeof(unsigned long long), s));
   if (depth_only) {
-    if (O > 0) filter_depth_kernel<<<(unsigned)((O + 255) / 256), 256, 0, s>>>(d, obs_point);
+    if (P > 0) filter_depth_kernel<<<(P + 127) / 128, 128, 0, s>>>(d);
   } else {
     if (C > 0) filter_centers_kernel<<<(C + 127) / 128, 128, 0, s>>>(d);
     if (P > 0)
@@ -272,9 +285,9 @@ int run(ppsfm_ctx* ctx, const ppsfm_filter_problem* pb, bool depth_only, double 
   unsigned long long nf = 0;
   if (obs_deleted && O > 0)
     PPSFM_CUDA(ctx, cudaMemcpyAsync(obs_deleted, d.obs_deleted, (size_t)O, cudaMemcpyDeviceToHost, s));
+  if (point_deleted && P > 0)
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(point_deleted, d.point_deleted, (size_t)P, cudaMemcpyDeviceToHost, s));
   if (!depth_only) {
-    if (point_deleted && P > 0)
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(point_deleted, d.point_deleted, (size_t)P, cudaMemcpyDeviceToHost, s));
     if (point_error && P > 0)
       PPSFM_CUDA(ctx, cudaMemcpyAsync(point_error, d.point_error, sizeof(double) * (size_t)P,
                                       cudaMemcpyDeviceToHost, s));
@@ -300,8 +313,10 @@ int ppsfm_filter_points3d(ppsfm_ctx* ctx, const ppsfm_filter_problem* problem,
 
 int ppsfm_filter_observations_with_negative_depth(ppsfm_ctx* ctx,
                                                   const ppsfm_filter_problem* problem,
-                                                  uint8_t* obs_deleted, size_t* num_filtered) {
-  return ppsfm::run(ctx, problem, true, 0.0, 0.0, obs_deleted, nullptr, nullptr, num_filtered);
+                                                  uint8_t* obs_deleted, uint8_t* point_deleted,
+                                                  size_t* num_filtered) {
+  return ppsfm::run(ctx, problem, true, 0.0, 0.0, obs_deleted, point_deleted, nullptr,
+                    num_filtered);
 }
 
 }  // extern "C"

@@ -57,7 +57,7 @@ def _declare(L):
     P = C.POINTER(FilterProblemStruct)
     L.ppsfm_filter_points3d.argtypes = [C.c_void_p, P, C.c_double, C.c_double, _u8p, _u8p, _dp,
                                         C.POINTER(C.c_size_t)]
-    L.ppsfm_filter_observations_with_negative_depth.argtypes = [C.c_void_p, P, _u8p,
+    L.ppsfm_filter_observations_with_negative_depth.argtypes = [C.c_void_p, P, _u8p, _u8p,
                                                                 C.POINTER(C.c_size_t)]
     L._filter_declared = True
 
@@ -77,12 +77,14 @@ def FilterPoints3D(ctx, problem, max_reproj_error, min_tri_angle, point_error=No
 
 
 def FilterObservationsWithNegativeDepth(ctx, problem):
-    """Returns (num_filtered, obs_deleted [O])."""
+    """Returns (num_filtered, obs_deleted [O], point_deleted [P]): DeleteObservation removes the
+    whole point once its track is down to three elements (reconstruction.cc:255-275)."""
     L = binding.load_library()
     _declare(L)
-    O = len(problem.obs_image)
-    od = np.zeros(max(O, 1), np.uint8)
+    O, P = len(problem.obs_image), len(problem.points)
+    od, pd = np.zeros(max(O, 1), np.uint8), np.zeros(max(P, 1), np.uint8)
     nf = C.c_size_t(0)
     ctx._check(L.ppsfm_filter_observations_with_negative_depth(
-        ctx._h, C.byref(problem.struct), od.ctypes.data_as(_u8p), C.byref(nf)))
-    return nf.value, od[:O]
+        ctx._h, C.byref(problem.struct), od.ctypes.data_as(_u8p), pd.ctypes.data_as(_u8p),
+        C.byref(nf)))
+    return nf.value, od[:O], pd[:P]

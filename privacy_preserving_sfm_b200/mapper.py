@@ -155,9 +155,16 @@ class IncrementalMapper:
             return
         pb, obs_image, obs_point = self._track_problem(pid, self.points[pid].copy())
         # FilterObservationsWithNegativeDepth before the adjustment (:904)
-        _, neg = F.FilterObservationsWithNegativeDepth(self.ctx, pb)
+        # (DeleteObservation removes points whose track is down to three views: all their
+        # observations come back flagged)
+        _, neg, dead = F.FilterObservationsWithNegativeDepth(self.ctx, pb)
         self.obs_on[obs_image[neg.astype(bool)], obs_point[neg.astype(bool)]] = False
+        self.has_point[pid[dead.astype(bool)]] = False
+        self.points[pid[dead.astype(bool)]] = np.nan
         keep = ~neg.astype(bool)
+        pid = pid[~dead.astype(bool)]
+        if len(pid) == 0:
+            return
         local_pt = np.searchsorted(pid, obs_point[keep])
         flags = np.ones(len(self.qvec), np.uint8)        # unregistered images: constant, unused
         flags[reg] = 0

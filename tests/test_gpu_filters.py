@@ -64,9 +64,78 @@ def test_filter_points3d_short_and_empty_tracks(ctx, oracle):
 def test_filter_negative_depth_matches_oracle(ctx, oracle):
     pb = _problem(10, 500, 5, seed=21)
     pb.points[::7] -= 20.0 * np.array([0.0, 0.0, 1.0])   # (in place: the struct points here)
-    nf, od = F.FilterObservationsWithNegativeDepth(ctx, pb)
-    nf2, od2 = oracle.filter_negative_depth(pb)
-    assert nf == nf2 and np.array_equal(od, od2) and 0 < nf < len(od)
+    nf, od, pd = F.FilterObservationsWithNegativeDepth(ctx, pb)
+    nf2, od2, pd2 = oracle.filter_negative_depth(pb)
+    assert nf == nf2 and np.array_equal(od, od2) and np.array_equal(pd, pd2)
+    assert 0 < nf < len(od) and pd.any()
+
+
+def test_filter_negative_depth_cascade_hand_computed(ctx, oracle):
+    """DeleteObservation deletes the whole point once its track is down to <= 3 elements
+    (reconstruction.cc:255-275); later observations of that point are not counted.  Camera at the
+    origin looking down +z, hand-made tracks:
+      track 0: 6 views, 2 behind  -> 2 deletions, point survives with 4 views
+      track 1: 5 views, 3 behind  -> deletions at lengths 5, 4, 3: the third removes the point
+      track 2: 5 views, 4 behind  -> same three deletions, the fourth is never visited: 3
+      track 3: 3 views, 1 behind  -> first deletion removes the point: 1
+      track 4: 4 views, 0 behind  -> untouched"""
+    lens, behind = [6, 5, 5, 3, 4], [2, 3, 4, 1, 0]
+    num_img = 6
+    q = np.tile([1.0, 0, 0, 0], (num_img, 1))
+    t = np.zeros((num_img, 3))
+    obs_img, track_start = [], [0]
+    for p, (n, b) in enumerate(zip(lens, behind)):
+        obs_img += list(range(n))
+        track_start.append(track_start[-1] + n)
+    # image i sees a point in front iff z + t_z > 0: give the "behind" views a tvec of -10 in z
+    # for that point only -> use one image set per point by shifting the POINT instead:
+    # points sit at z = 5; views 0..b-1 of track p use images whose t_z = -10 (images 0..3 get
+    # t_z = -10 only through per-track image choice)
+    pts = np.tile([0.0, 0.0, 5.0], (len(lens), 1))
+    t[:, 2] = 0.0
+    # build per-observation images so that the first `b` observations of a track look from
+    # images with negative depth: images 0-3 have t_z = -10, images 4-9 have t_z = 0
+    num_img = 10
+    q = np.tile([1.0, 0, 0, 0], (num_img, 1))
+    t = np.zeros((num_img, 3))
+    t[:4, 2] = -10.0
+    obs_img = []
+    for n, b in zip(lens, behind):
+        obs_img += list(range(b)) + list(range(4, 4 + n - b))
+    O = len(obs_img)
+    lines = np.tile([1.0, 0.0, 0.0], (O, 1))
+    pb = F.FilterProblem(q, t, np.zeros(num_img, np.int32), [1], [[1000.0, 1000.0, 500.0, 500.0]],
+                         [(1000, 1000)], pts, np.array(track_start, np.int64),
+                         np.array(obs_img, np.int32), lines, np.zeros(O, np.uint8))
+    nf, od, pd = F.FilterObservationsWithNegativeDepth(ctx, pb)
+    assert nf == 2 + 3 + 3 + 1 + 0
+    assert list(pd) == [0, 1, 1, 1, 0]
+    ts = track_start
+    assert list(od[ts[0]:ts[1]]) == [1, 1, 0, 0, 0, 0]
+    assert od[ts[1]:ts[4]].all() and not od[ts[4]:].any()
+    nf2, od2, pd2 = oracle.filter_negative_depth(pb)
+    assert nf2 == nf and np.array_equal(od2, od) and np.array_equal(pd2, pd)
+
+
+def test_filter_point_error_uses_remaining_track_length(ctx, oracle):
+    """Point3D::SetError(sum / Track().Length()) runs AFTER the DeleteObservation calls
+    (reconstruction.cc:706-713): mean over the surviving observations.  One point, 6 views on a
+    circle, two of its lines pushed 50 px away: error = mean of the 4 kept line distances."""
+    sc = S.make_ba_scene(num_cams=6, num_points=1, obs_per_point=6, seed=4)
+    order = np.argsort(sc["obs_cam"], kind="stable")
+    line = sc["obs_line"][order].copy()
+    line[1, 2] += 0.05
+    line[4, 2] -= 0.05
+    pb = F.FilterProblem(sc["qvecs_gt"], sc["tvecs_gt"], np.zeros(6, np.int32), [1],
+                         [[1000.0, 1000.0, 500.0, 500.0]], [(1000, 1000)], sc["points_gt"],
+                         np.array([0, 6], np.int64), sc["obs_cam"][order], line,
+                         np.zeros(6, np.uint8))
+    nf, od, pd, pe = F.FilterPoints3D(ctx, pb, 4.0, 1.5)
+    nf2, od2, pd2, pe2, sq = oracle.filter_points3d(pb, 4.0, 1.5)
+    assert nf == 2 and list(od) == [0, 1, 0, 0, 1, 0] and not pd[0]
+    kept = np.sqrt(sq[[0, 2, 3, 5]])
+    assert abs(pe[0] - kept.sum() / 4.0) <= 1e-15 * max(1.0, pe[0])
+    assert pe[0] == pe2[0] and nf == nf2
 
 
 def test_filter_rejects_bad_input(ctx):
