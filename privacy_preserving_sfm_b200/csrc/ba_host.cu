@@ -430,6 +430,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     int chol_failed = 0;
     if (d.n > 0) {
       st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_work, d.chol_status, s);
+      PPSFM_CUDA(ctx, cudaGetLastError());  // a refused launch must not read as "factorised"
       PPSFM_CUDA(ctx, cudaMemcpyAsync(&chol_failed, d.chol_status, sizeof(int),
                                       cudaMemcpyDeviceToHost, s));
     }

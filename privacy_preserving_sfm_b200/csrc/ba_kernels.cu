@@ -616,18 +616,19 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
   }
   // Persistent CTAs with the per-image table in shared memory when it fits (2 CTAs / SM);
   // otherwise one CTA per chunk gathering from global memory.
-  static int num_sms = 0, max_smem = 0, store_mode = 0;
-  if (num_sms == 0) {
-    store_mode = tune_int("PPSFM_BA_J_STREAM", 0);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
-    cudaFuncSetAttribute(ba_linearize_kernel<true, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
-    cudaFuncSetAttribute(ba_linearize_kernel<false, true>,
-                         cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem - 1024);
-  }
+  static PerDevice<> per_device;
+  static const int store_mode = tune_int("PPSFM_BA_J_STREAM", 0);
+  const auto& dev = per_device.get([](const DeviceFacts& f, int&) {
+    cudaError_t e = cudaFuncSetAttribute(ba_linearize_kernel<true, true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         f.max_smem_optin - 1024);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(ba_linearize_kernel<false, true>,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                f.max_smem_optin - 1024);
+  });
+  // (a failed attribute call surfaces as a launch error at the caller's next CUDA check)
+  const int num_sms = dev.facts.num_sms, max_smem = dev.facts.max_smem_optin;
   const size_t tab_bytes = (size_t)d.C * (kCamRec * sizeof(double) + sizeof(int)) +
                            (size_t)d.num_cameras * kIntrRec * sizeof(double) + 16;
   const bool use_smem = tab_bytes <= (size_t)(max_smem - 2048) && chunks > 2 * num_sms;

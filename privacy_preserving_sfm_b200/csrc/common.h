@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include <random>
 #include <string>
 #include <vector>
@@ -129,6 +130,39 @@ inline int tune_int(const char* name, int dflt) {
   const char* v = std::getenv(name);
   return (v && *v) ? std::atoi(v) : dflt;
 }
+
+// Per-device facts and one-time per-device setup.  cudaFuncSetAttribute and the SM count belong to
+// a DEVICE, and the ABI allows one context per device (and per host thread) in one process, so
+// nothing of this kind may live in a process-wide static: each call site owns a PerDevice<> table
+// indexed by the current device, initialised under a std::once_flag per entry.
+constexpr int kMaxDevices = 64;
+struct DeviceFacts {
+  int num_sms = 0;
+  int max_smem_optin = 0;
+};
+template <typename Extra = int>
+struct PerDevice {
+  struct Entry {
+    std::once_flag once;
+    DeviceFacts facts;
+    Extra extra{};
+    cudaError_t err = cudaSuccess;
+  };
+  Entry entries[kMaxDevices];
+  // init(facts, extra) runs once per device (with that device current) and returns a cudaError_t
+  template <typename Init>
+  Entry& get(Init&& init) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    Entry& e = entries[(dev >= 0 && dev < kMaxDevices) ? dev : 0];
+    std::call_once(e.once, [&] {
+      cudaDeviceGetAttribute(&e.facts.num_sms, cudaDevAttrMultiProcessorCount, dev);
+      cudaDeviceGetAttribute(&e.facts.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+      e.err = init(e.facts, e.extra);
+    });
+    return e;
+  }
+};
 
 #define PPSFM_CUDA(ctx, expr)                                                              \
   do {                                                                                     \

@@ -18,8 +18,10 @@
 //     chain  L_jj = chol(C_jj)  ->  X_(j+1)j = C_(j+1)j L_jj^-T  ->  C_(j+1)(j+1) -= X X^T  in
 //     shared memory and registers: no flag round trip, no global-memory latency and no
 //     co-resident tensor-core traffic on the critical path.
-// A task only ever waits for tasks with a smaller ticket or for the walker, and the walker is the
-// first CTA that starts, so there is no deadlock whatever the number of resident CTAs.  Finished
+// A task only ever waits for tasks with a smaller ticket or for the walker, the walker is the
+// first CTA that starts, and at most one CTA (the one that shares the walker's SM) leaves without
+// working, so at least one helper exists and there is no deadlock whatever the number of resident
+// CTAs and whatever else occupies the GPU.  Finished
 // tiles are published with release stores; consumers poll with relaxed loads and one acquire fence.
 // The right-hand side rides along as an extra matrix row ("bordered" factorisation), which
 // yields y = L^-1 rhs for free; the backward substitution L^T x = y is a second dataflow kernel
@@ -601,7 +603,13 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
     } else {
       int ws;
       while ((ws = ld_relaxed(w.flags + 3)) == 0) __nanosleep(40);
-      if (ws == (int)smid() + 1) s_role = 2;  // shares the walker's SM: leave it alone
+      // Shares the walker's SM: leave it alone -- but only ONE CTA may ever leave.  When the
+      // other SMs are busy (another stream, another process) the block scheduler refills the
+      // slot a leaver frees on this very SM, and if every CTA that lands here left, the grid
+      // would drain through that slot and the walker would wait for helpers that no longer
+      // exist.  The grid has at least walker + 2 CTAs, so at least one helper always remains;
+      // a later CTA that lands on the walker's SM stays and works (slower, never stuck).
+      if (ws == (int)smid() + 1 && atomicCAS(w.flags + 2, 1, 2) == 1) s_role = 2;
     }
   }
   __syncthreads();
@@ -884,16 +892,15 @@ size_t chol_work_doubles(int n) {
 // 1 if a non-positive pivot was met.  Asynchronous on `s`; returns the number of launches.
 int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* status,
                         cudaStream_t s) {
-  static int num_sms = 0;
-  if (num_sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(chol_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kFactorSmem);
-    cudaFuncSetAttribute(chol_backsolve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         kBackSmem);
-  }
+  static PerDevice<> per_device;
+  const auto& dev = per_device.get([](const DeviceFacts&, int&) {
+    cudaError_t e = cudaFuncSetAttribute(chol_factor_kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kFactorSmem);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(chol_backsolve_kernel,
+                                cudaFuncAttributeMaxDynamicSharedMemorySize, kBackSmem);
+  });
+  const int num_sms = dev.facts.num_sms;
   const Work w = work_layout(work, n);
   cudaMemsetAsync(status, 0, sizeof(int), s);
   cudaMemsetAsync(w.flags, 0, sizeof(int) * work_flag_ints(n), s);
