@@ -72,6 +72,7 @@ typedef struct {
   uint64_t score_pairs;    /* (model, correspondence) pairs evaluated by the scoring kernel */
   uint64_t score_launches; /* scoring-kernel launches */
   uint64_t kernel_launches; /* all kernels launched by the call */
+  double comm_ms;    /* sharded call: all-reduce of the counts + pruning-bound update */
 } ppsfm_ransac_timing;
 
 /* ---- context -------------------------------------------------------------------------- */
@@ -148,6 +149,25 @@ int ppsfm_ransac_p6l_resident(ppsfm_ctx* ctx, const ppsfm_corr* corr,
                               const ppsfm_ransac_options* options, ppsfm_ransac_report* report,
                               uint8_t* inlier_mask);
 void ppsfm_get_ransac_timing(const ppsfm_ctx* ctx, ppsfm_ransac_timing* out);
+
+/* ---- ONE Estimate call sharded over the GPUs of a communicator (RANSAC row) ----
+ * Collective: after ppsfm_comm_init every rank calls with the SAME correspondence set, options
+ * and generator state (ppsfm_set_prng_seed).  The trials of RANSAC<>::Estimate
+ * (src/optim/ransac.h:178-278) are generated on every rank, the models of each wave are scored
+ * 1/world per GPU, one NCCL all-reduce of the 32-bit inlier counts per wave gives every rank
+ * every count (the exact-pruning bound is raised to the best count over all ranks), and every
+ * rank replays the reference loop (:213-249) over the same counts: report, mask and generator
+ * state are those of the single-GPU call, on every rank.  With world == 1 (or without a
+ * communicator) the calls are the plain ones. */
+int ppsfm_ransac_p6l_sharded(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned,
+                             const double* points, size_t n, const ppsfm_ransac_options* options,
+                             ppsfm_ransac_report* report, uint8_t* inlier_mask);
+int ppsfm_ransac_p6l_resident_sharded(ppsfm_ctx* ctx, const ppsfm_corr* corr,
+                                      const ppsfm_ransac_options* options,
+                                      ppsfm_ransac_report* report, uint8_t* inlier_mask);
+/* host-only shard accounting: of a wave's num_models compact models, how many rank `rank` scores
+ * (blocks of 512 models dealt round-robin to the ranks) */
+uint64_t ppsfm_ransac_shard_models(uint64_t num_models, int rank, int world);
 
 /* =============================================================================================
  * Line-reprojection bundle adjustment

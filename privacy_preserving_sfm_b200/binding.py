@@ -64,7 +64,8 @@ class RansacReport(C.Structure):
 class RansacTiming(C.Structure):
     _fields_ = [("solve_ms", C.c_double), ("score_ms", C.c_double), ("exact_ms", C.c_double),
                 ("total_ms", C.c_double), ("score_pairs", C.c_uint64),
-                ("score_launches", C.c_uint64), ("kernel_launches", C.c_uint64)]
+                ("score_launches", C.c_uint64), ("kernel_launches", C.c_uint64),
+                ("comm_ms", C.c_double)]
 
 
 _dp = C.POINTER(C.c_double)
@@ -115,6 +116,10 @@ def load_library():
     L.ppsfm_corr_free.restype = None
     L.ppsfm_ransac_p6l_resident.argtypes = [vp, vp, C.POINTER(RANSACOptions),
                                             C.POINTER(RansacReport), _u8p]
+    L.ppsfm_ransac_p6l_resident_sharded.argtypes = [vp, vp, C.POINTER(RANSACOptions),
+                                                    C.POINTER(RansacReport), _u8p]
+    L.ppsfm_ransac_p6l_sharded.argtypes = [vp, _dp, _u8p, _dp, C.c_size_t,
+                                           C.POINTER(RANSACOptions), C.POINTER(RansacReport), _u8p]
     L.ppsfm_get_ransac_timing.argtypes = [vp, C.POINTER(RansacTiming)]
     L.ppsfm_get_ransac_timing.restype = None
     L.ppsfm_comm_get_unique_id.argtypes = [vp, C.c_char_p]
@@ -289,6 +294,28 @@ class Context:
         return rc == PPSFM_OK, q, t, int(ninl.value), mask, rep
 
     # -- multi-GPU ---------------------------------------------------------------------------
+    def ransac_p6l_sharded(self, lines, aligned, points, options, want_mask=True):
+        """ONE RANSAC call sharded over the communicator's GPUs (collective: every rank passes the
+        same set, options and generator state and gets the single-GPU call's report back)."""
+        lines, lp = _d(lines)
+        points, pp = _d(points)
+        aligned, ap = _u8(aligned)
+        n = lines.shape[0]
+        rep = RansacReport()
+        mask = np.zeros(n, dtype=np.uint8)
+        self._check(self._L.ppsfm_ransac_p6l_sharded(
+            self._h, lp, ap, pp, n, C.byref(options), C.byref(rep),
+            mask.ctypes.data_as(_u8p) if want_mask else None))
+        return rep, mask
+
+    def ransac_p6l_resident_sharded(self, corr, options, want_mask=True, mask_out=None):
+        rep = RansacReport()
+        mask = mask_out if mask_out is not None else np.zeros(corr.n, dtype=np.uint8)
+        self._check(self._L.ppsfm_ransac_p6l_resident_sharded(
+            self._h, corr._h, C.byref(options), C.byref(rep),
+            mask.ctypes.data_as(_u8p) if want_mask else None))
+        return rep, mask
+
     def comm_unique_id(self):
         buf = C.create_string_buffer(128)
         self._check(self._L.ppsfm_comm_get_unique_id(self._h, buf))
@@ -341,6 +368,14 @@ class Context:
 
 
 _default_ctx = None
+
+
+def ransac_shard_models(num_models, rank, world):
+    """Host-only: models of a wave that `rank` of `world` scores in a sharded RANSAC call."""
+    L = load_library()
+    L.ppsfm_ransac_shard_models.argtypes = [C.c_uint64, C.c_int, C.c_int]
+    L.ppsfm_ransac_shard_models.restype = C.c_uint64
+    return int(L.ppsfm_ransac_shard_models(num_models, rank, world))
 
 
 def default_context():

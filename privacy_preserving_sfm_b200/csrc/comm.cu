@@ -17,7 +17,7 @@ namespace {
 typedef struct ncclComm* ncclComm_t;
 typedef struct { char internal[128]; } ncclUniqueId;
 typedef int ncclResult_t;
-enum { kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };
+enum { kNcclUint32 = 3, kNcclFloat64 = 8, kNcclSum = 0, kNcclMax = 2 };
 
 struct NcclApi {
   void* handle = nullptr;
@@ -69,6 +69,17 @@ int CommAllReduce(ppsfm_ctx* ctx, double* dev, size_t count, bool max_op) {
   if (!a->ok || !ctx->comm) return fail(ctx, PPSFM_ERR_NCCL, "communicator not initialised");
   const ncclResult_t r = a->AllReduce(dev, dev, count, kNcclFloat64, max_op ? kNcclMax : kNcclSum,
                                       (ncclComm_t)ctx->comm, ctx->stream);
+  if (r != 0) return NcclFail(ctx, "ncclAllReduce", r);
+  return PPSFM_OK;
+}
+
+// Sum all-reduce of 32-bit counts on `stream` (the per-wave exchange of a sharded RANSAC call).
+int CommAllReduceU32(ppsfm_ctx* ctx, unsigned* dev, size_t count, cudaStream_t stream) {
+  if (ctx->world <= 1 || count == 0) return PPSFM_OK;
+  NcclApi* a = Api();
+  if (!a->ok || !ctx->comm) return fail(ctx, PPSFM_ERR_NCCL, "communicator not initialised");
+  const ncclResult_t r = a->AllReduce(dev, dev, count, kNcclUint32, kNcclSum,
+                                      (ncclComm_t)ctx->comm, stream);
   if (r != 0) return NcclFail(ctx, "ncclAllReduce", r);
   return PPSFM_OK;
 }

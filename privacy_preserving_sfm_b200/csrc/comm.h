@@ -1,5 +1,7 @@
 // comm.h — NCCL all-reduce on the context's stream (comm.cu).
 #pragma once
+#include <cuda_runtime.h>
+
 #include <cstddef>
 
 struct ppsfm_ctx;
@@ -7,4 +9,6 @@ struct ppsfm_ctx;
 namespace ppsfm {
 // In-place all-reduce (sum or max) of `count` doubles in device memory; no-op for world == 1.
 int CommAllReduce(ppsfm_ctx* ctx, double* dev, size_t count, bool max_op);
+// In-place sum all-reduce of `count` 32-bit counts on `stream`.
+int CommAllReduceU32(ppsfm_ctx* ctx, unsigned* dev, size_t count, cudaStream_t stream);
 }  // namespace ppsfm

@@ -95,7 +95,8 @@ struct ppsfm_ctx {
   struct WaveSlot {
     ppsfm::DevBuf d_samples, d_models, d_num_models, d_off, d_part_cnt, d_cnt, d_list;
     ppsfm::PinBuf h_samples, h_off, h_cnt;
-    cudaEvent_t ev[5] = {nullptr};  // solve begin / end, score begin / end, results on the host
+    cudaEvent_t ev[6] = {nullptr};  // solve begin / end, score begin / end, results on the host,
+                                    // counts exchanged (sharded call)
     cudaStream_t solve_stream = nullptr;  // high priority: the waves' solve kernels overlap
   } wave[kWaveSlots];
   ppsfm::DevBuf d_best_lb;  // best inlier count of the waves scored so far (exact pruning)

@@ -14,6 +14,7 @@
 #include <limits>
 #include <numeric>
 
+#include "comm.h"
 #include "common.h"
 #include "ransac_kernels.h"
 #include "ransac_replay.h"
@@ -65,9 +66,10 @@ float EventMs(cudaEvent_t a, cudaEvent_t b) {
 // estimated from the expected models per trial (3.9 of 8 for P6L, or what the call has seen so
 // far), and the grid is kept 4 % under the wave boundary — a grid of 4.01 waves costs 5.
 static void ChooseSegments(const ppsfm_ctx* ctx, int n, int kcap, double models_per_trial,
-                           int* num_segs, int* seg_len) {
+                           int* num_segs, int* seg_len, int shard_world = 1) {
   const int resident = ctx->num_sms * ppsfm::kScoreCtasPerSm;
-  const double live_models = std::max(1.0, (kcap / 8.0) * models_per_trial);
+  // (a sharded call scores 1 / shard_world of the wave's models on this GPU)
+  const double live_models = std::max(1.0, (kcap / 8.0) * models_per_trial / shard_world);
   const int live_blocks = (int)std::ceil(live_models / ppsfm::kScoreModelsPerCta);
   const int forced = ppsfm::tune_int("PPSFM_SCORE_SEGS", 0);
   int best_segs = 1, best_len = std::max(256, ((n + 127) / 128) * 128);
@@ -110,9 +112,24 @@ struct Wave {
 // Waves are issued ahead only over trials the loop is certain to reach (below min_num_trials, or
 // below the current dynamic bound once a best model exists), so a call that stops inside its
 // first wave pays nothing for the pipeline.
+//
+// sharded = true (RANSAC row): the call is COLLECTIVE over the context's
+// communicator.  Every rank holds the whole correspondence set and the same generator state,
+// draws the same samples and solves every hypothesis of a wave (the solve kernel is latency
+// bound: its time does not depend on the number of hypotheses, and having all models on every
+// rank means no model ever has to travel), but scores only its share of the wave's models (model
+// blocks interleaved over the ranks); one NCCL sum all-reduce of the 32-bit counts per wave gives
+// every rank every count, the pruning bound is raised to the best count over all ranks, and every
+// rank replays the same loop over the same counts -> the same report, mask and generator state
+// as the single-GPU call, on every rank.
 int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_options* opt_in,
-                   ppsfm_ransac_report* report, uint8_t* inlier_mask) {
+                   ppsfm_ransac_report* report, uint8_t* inlier_mask, bool sharded = false) {
   if (!ctx || !corr || !opt_in || !report) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
+  ppsfm::ScoreShard shard;
+  if (sharded && ctx->world > 1) {
+    shard.world = ctx->world;
+    shard.rank = ctx->rank;
+  }
   ppsfm_ransac_options opt = *opt_in;
   // RANSACOptions::Check, src/optim/ransac.h:68-75
   if (!(opt.max_error > 0) || opt.min_inlier_ratio < 0 || opt.min_inlier_ratio > 1 ||
@@ -262,12 +279,13 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       if (num_issued > 0 && r > 0.0 && cut >= 2 * kPruneMin && cut + kPruneMin <= n) n_first = (int)cut;
     }
     int num_segs, seg_len;
-    ChooseSegments(ctx, n_first, kcap, models_per_trial, &num_segs, &seg_len);
+    ChooseSegments(ctx, n_first, kcap, models_per_trial, &num_segs, &seg_len, shard.world);
     int part_segs = num_segs;
     if (n_first < (int)n) {
       prune.n_first = n_first;
       // (few models survive: the second phase is sized as if one in eight did)
-      ChooseSegments(ctx, (int)n - n_first, kcap, 1.0, &prune.num_segs2, &prune.seg_len2);
+      ChooseSegments(ctx, (int)n - n_first, kcap, 1.0, &prune.num_segs2, &prune.seg_len2,
+                     shard.world);
       part_segs = std::max(part_segs, prune.num_segs2);
       PPSFM_CUDA(ctx, sl.d_list.reserve(sizeof(int) * ((size_t)kcap + 1)));
       prune.list = sl.d_list.as<int>() + 1;
@@ -292,11 +310,22 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[2], st));
     launch_score(corr->corr6, corr->corr6f, corr->bounds, (int)n, sl.d_models.as<double>(),
                  sl.d_off.as<int>(), H, num_segs, seg_len, max_residual, kcap,
-                 sl.d_part_cnt.as<unsigned>(), sl.d_cnt.as<unsigned>(), st, prune);
+                 sl.d_part_cnt.as<unsigned>(), sl.d_cnt.as<unsigned>(), st, prune, shard);
     PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[3], st));
+    if (shard.world > 1) {
+      // the wave's one exchange: every rank gets every count; then the pruning bound of the
+      // following waves becomes the best count over all ranks
+      const int rc = ppsfm::CommAllReduceU32(ctx, sl.d_cnt.as<unsigned>(), (size_t)kcap, st);
+      if (rc != PPSFM_OK) return rc;
+      if (kPrune)
+        launch_raise_best_lb(sl.d_cnt.as<unsigned>(), sl.d_off.as<int>(), H,
+                             ctx->d_best_lb.as<unsigned>(), st);
+      PPSFM_CUDA(ctx, cudaEventRecord(sl.ev[5], st));
+      ctx->timing.kernel_launches += 2;
+    }
     // results to the host on the copy stream: the next wave's scoring kernel follows directly
     cudaStream_t cp = ctx->stream_copy;
-    PPSFM_CUDA(ctx, cudaStreamWaitEvent(cp, sl.ev[3], 0));
+    PPSFM_CUDA(ctx, cudaStreamWaitEvent(cp, shard.world > 1 ? sl.ev[5] : sl.ev[3], 0));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(sl.h_off.p, sl.d_off.p, sizeof(int) * ((size_t)H + 1),
                                     cudaMemcpyDeviceToHost, cp));
     if (prune.n_first > 0)
@@ -369,10 +398,15 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
     ctx->timing.solve_ms += EventMs(sl.ev[0], sl.ev[1]);
     ctx->timing.score_ms += EventMs(sl.ev[2], sl.ev[3]);
     total_ms += EventMs(sl.ev[0], sl.ev[1]) + EventMs(sl.ev[2], sl.ev[3]);
+    if (shard.world > 1) {
+      ctx->timing.comm_ms += EventMs(sl.ev[3], sl.ev[5]);
+      total_ms += EventMs(sl.ev[3], sl.ev[5]);
+    }
     // pairs the scoring kernel actually evaluated (dropped models skip the second phase)
-    ctx->timing.score_pairs += w.n_first > 0 ? (uint64_t)K * w.n_first +
+    const uint64_t K_own = ppsfm_ransac_shard_models((uint64_t)K, shard.rank, shard.world);
+    ctx->timing.score_pairs += w.n_first > 0 ? K_own * w.n_first +
                                                    (uint64_t)h_off[H + 1] * (n - w.n_first)
-                                             : (uint64_t)K * n;
+                                             : K_own * n;
 
     // ---- pass 1 (counts only): models that beat or tie the running best count.  Only a TIE
     // needs residual sums (InlierSupportMeasurer::Compare, support_measurement.cc:52-60), and
@@ -861,6 +895,37 @@ int ppsfm_ransac_p6l(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned
   int rc = UploadCorr(ctx, lines, aligned, points, n, true, &corr);
   if (rc != PPSFM_OK) return rc;
   rc = RansacResident(ctx, corr, options, report, inlier_mask);
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  FreeCorr(corr);
+  return rc;
+}
+
+// Host-only: how many of a wave's K compact models rank `rank` of `world` scores in a sharded
+// call (blocks of kScoreModelsPerCta models, block b belongs to rank b % world).
+uint64_t ppsfm_ransac_shard_models(uint64_t num_models, int rank, int world) {
+  if (world <= 1) return num_models;
+  uint64_t own = 0;
+  const uint64_t B = (uint64_t)ppsfm::kScoreModelsPerCta;
+  for (uint64_t b = (uint64_t)rank; b * B < num_models; b += (uint64_t)world)
+    own += std::min<uint64_t>(B, num_models - b * B);
+  return own;
+}
+
+int ppsfm_ransac_p6l_resident_sharded(ppsfm_ctx* ctx, const ppsfm_corr* corr,
+                                      const ppsfm_ransac_options* options,
+                                      ppsfm_ransac_report* report, uint8_t* inlier_mask) {
+  if (ctx) cudaSetDevice(ctx->device);
+  return RansacResident(ctx, corr, options, report, inlier_mask, true);
+}
+
+int ppsfm_ransac_p6l_sharded(ppsfm_ctx* ctx, const double* lines, const uint8_t* aligned,
+                             const double* points, size_t n, const ppsfm_ransac_options* options,
+                             ppsfm_ransac_report* report, uint8_t* inlier_mask) {
+  if (ctx) cudaSetDevice(ctx->device);
+  ppsfm_corr* corr = nullptr;
+  int rc = UploadCorr(ctx, lines, aligned, points, n, true, &corr);
+  if (rc != PPSFM_OK) return rc;
+  rc = RansacResident(ctx, corr, options, report, inlier_mask, true);
   if (ctx) cudaStreamSynchronize(ctx->stream);
   FreeCorr(corr);
   return rc;

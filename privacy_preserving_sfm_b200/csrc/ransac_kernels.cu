@@ -422,14 +422,17 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
              const double* __restrict__ models, const int* __restrict__ offsets, int num_trials,
              int seg_len, double r_max, int kcap, unsigned* __restrict__ part_cnt,
              const double* __restrict__ bounds, const int* __restrict__ list,
-             const int* __restrict__ list_count) {
+             const int* __restrict__ list_count, int shard_world, int shard_rank) {
   // list != nullptr: second phase of a pruned wave — slot i of the grid scores model list[i]
+  // shard_world > 1 (first phase only): ONE call sharded over the GPUs of a communicator; this
+  // rank scores the model blocks b with b % shard_world == shard_rank (K is only known on the
+  // device, so the interleaving is what balances the ranks)
   __shared__ __align__(128) float tile[kStages][kTileR * 12];
   __shared__ __align__(8) uint64_t full_bar[kStages];
   __shared__ unsigned done[kStages];  // warps that have finished with the stage
 
   const int K = list ? *list_count : offsets[num_trials];
-  if ((int)blockIdx.x * (kScoreThreads * M) >= K) return;
+  if ((int)(blockIdx.x * shard_world + shard_rank) * (kScoreThreads * M) >= K) return;
   const int seg = blockIdx.y;
   const int i0 = seg * seg_len;  // even: seg_len is a multiple of 128
   const int i1 = min(n, i0 + seg_len);
@@ -453,8 +456,8 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
   // A CTA takes the model blocks blockIdx.x, blockIdx.x + gridDim.x, ...: one block per CTA in
   // the first phase (grid sized to the capacity), a short grid walking the survivor list in the
   // second phase of a pruned wave.  The barriers live across blocks; phase_bits carries on.
-  for (int mbase = blockIdx.x * (kScoreThreads * M); mbase < K;
-       mbase += gridDim.x * (kScoreThreads * M)) {
+  for (int mbase = (blockIdx.x * shard_world + shard_rank) * (kScoreThreads * M); mbase < K;
+       mbase += gridDim.x * shard_world * (kScoreThreads * M)) {
   // thread <-> models mbase + m * 256 + tid, m < M
   const double* src[M];
   float2 Pf[M][12];
@@ -559,14 +562,35 @@ score_kernel(const double* __restrict__ corr6, const float* __restrict__ corr6f,
 __global__ void reduce_parts_kernel(const unsigned* __restrict__ part_cnt, int num_segs, int kcap,
                                     const int* __restrict__ offsets, int num_trials,
                                     unsigned* __restrict__ cnt_out,
-                                    unsigned* __restrict__ best_lb) {
+                                    unsigned* __restrict__ best_lb, int shard_world,
+                                    int shard_rank, int models_per_block) {
   const int K = offsets[num_trials];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= K) return;
+  if (k >= kcap) return;
+  // sharded call: the counts of the other ranks' models arrive through the all-reduce (sum), so
+  // this rank contributes zeros for them — and for the unused slots above K
+  const bool mine = k < K && (k / models_per_block) % shard_world == shard_rank;
+  if (!mine) {
+    if (shard_world > 1) cnt_out[k] = 0;
+    return;
+  }
   unsigned c = 0;
   for (int g = 0; g < num_segs; ++g) c += part_cnt[(size_t)g * kcap + k];
   cnt_out[k] = c;
   if (best_lb) atomicMax(best_lb, c);
+}
+
+// Sharded call, after the all-reduce of the counts: the pruning bound of the following waves is
+// the best count over ALL ranks' models.
+__global__ void raise_best_lb_kernel(const unsigned* __restrict__ cnt, const int* __restrict__ offsets,
+                                     int num_trials, unsigned* __restrict__ best_lb) {
+  const int K = offsets[num_trials];
+  unsigned m = 0;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x)
+    m = max(m, cnt[k]);
+#pragma unroll
+  for (int s = 16; s > 0; s >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, s));
+  if ((threadIdx.x & 31) == 0 && m > 0) atomicMax(best_lb, m);
 }
 
 // Second phase of a pruned wave: slot i holds the remaining count of model list[i].
@@ -589,10 +613,12 @@ __global__ void reduce_parts_list_kernel(const unsigned* __restrict__ part_cnt, 
 __global__ void survivors_kernel(const unsigned* __restrict__ cnt_first, int remaining,
                                  const int* __restrict__ offsets, int num_trials,
                                  const unsigned* __restrict__ best_lb, int* __restrict__ list,
-                                 int* __restrict__ list_count) {
+                                 int* __restrict__ list_count, int shard_world, int shard_rank,
+                                 int models_per_block) {
   const int K = offsets[num_trials];
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  const bool keep = k < K && cnt_first[k] + (unsigned)remaining >= *best_lb;  // '>=': ties count
+  const bool keep = k < K && (k / models_per_block) % shard_world == shard_rank &&
+                    cnt_first[k] + (unsigned)remaining >= *best_lb;  // '>=': ties count
   const unsigned bal = __ballot_sync(0xffffffffu, keep);
   if (bal == 0) return;
   const int lane = threadIdx.x & 31;
@@ -636,8 +662,10 @@ double inlier_abs_threshold(double max_residual) {
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
                   const double* models, const int* offsets, int num_trials, int num_segs,
                   int seg_len, double max_residual, int kcap, unsigned* part_cnt,
-                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune) {
+                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune,
+                  const ScoreShard& shard) {
   if (num_trials <= 0) return;
+  const int W = shard.world > 1 ? shard.world : 1, R = shard.world > 1 ? shard.rank : 0;
   const double r_max = inlier_abs_threshold(max_residual);
   // 4 records (8 correspondences) per unrolled group, 2 models per thread (every record read
   // from shared memory serves both), 2 CTAs per SM (100 registers): the best of the (group,
@@ -647,21 +675,28 @@ void launch_score(const double* corr6, const float* corr6f, const double* bounds
   const int xblocks = (kcap + kScoreThreads * kM - 1) / (kScoreThreads * kM);
   const bool two_phase = prune.best_lb && prune.n_first > 0 && prune.n_first < n;
   const int n1 = two_phase ? prune.n_first : n;  // multiple of 128 when two_phase (caller)
-  score_kernel<kG, kM, kMinB><<<dim3(xblocks, num_segs), kScoreThreads, 0, s>>>(
+  score_kernel<kG, kM, kMinB><<<dim3((xblocks + W - 1) / W, num_segs), kScoreThreads, 0, s>>>(
       corr6, corr6f, n1, models, offsets, num_trials, seg_len, r_max, kcap, part_cnt, bounds,
-      nullptr, nullptr);
+      nullptr, nullptr, W, R);
   reduce_parts_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(
-      part_cnt, num_segs, kcap, offsets, num_trials, cnt_out, two_phase ? nullptr : prune.best_lb);
+      part_cnt, num_segs, kcap, offsets, num_trials, cnt_out, two_phase ? nullptr : prune.best_lb,
+      W, R, kScoreThreads * kM);
   if (!two_phase) return;
   cudaMemsetAsync(prune.list_count, 0, sizeof(int), s);
   survivors_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(cnt_out, n - n1, offsets, num_trials,
-                                                      prune.best_lb, prune.list, prune.list_count);
+                                                      prune.best_lb, prune.list, prune.list_count,
+                                                      W, R, kScoreThreads * kM);
   // (few models survive: a short grid walks the list instead of one mostly empty CTA per block)
   score_kernel<kG, kM, kMinB><<<dim3(std::min(xblocks, 16), prune.num_segs2), kScoreThreads, 0, s>>>(
       corr6 + (size_t)n1 * 6, corr6f + (size_t)(n1 / 2) * 12, n - n1, models, offsets, num_trials,
-      prune.seg_len2, r_max, kcap, part_cnt, bounds, prune.list, prune.list_count);
+      prune.seg_len2, r_max, kcap, part_cnt, bounds, prune.list, prune.list_count, 1, 0);
   reduce_parts_list_kernel<<<(kcap + 255) / 256, 256, 0, s>>>(
       part_cnt, prune.num_segs2, kcap, prune.list, prune.list_count, cnt_out, prune.best_lb);
+}
+
+void launch_raise_best_lb(const unsigned* cnt, const int* offsets, int num_trials,
+                          unsigned* best_lb, cudaStream_t s) {
+  raise_best_lb_kernel<<<64, 256, 0, s>>>(cnt, offsets, num_trials, best_lb);
 }
 
 // ------------------------------------------------------------------------------------------

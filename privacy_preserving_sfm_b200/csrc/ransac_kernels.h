@@ -32,12 +32,22 @@ struct ScorePrune {
   int* list = nullptr;          // kcap survivors of the first phase
   int* list_count = nullptr;
 };
+// One call sharded over the ranks of a communicator: this rank scores the model
+// blocks b (kScoreModelsPerCta models each) with b % world == rank and writes zeros for the
+// others, so that a sum all-reduce of cnt_out (all kcap slots) gives every rank every count.
+struct ScoreShard {
+  int world = 1, rank = 0;
+};
 // Inlier counts of every compact model.  part_cnt: max(num_segs, num_segs2) x kcap scratch;
 // cnt_out: kcap (first K valid; exact for every model that can matter, see ScorePrune).
 void launch_score(const double* corr6, const float* corr6f, const double* bounds, int n,
                   const double* models, const int* offsets, int num_trials, int num_segs,
                   int seg_len, double max_residual, int kcap, unsigned* part_cnt,
-                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune = ScorePrune());
+                  unsigned* cnt_out, cudaStream_t s, const ScorePrune& prune = ScorePrune(),
+                  const ScoreShard& shard = ScoreShard());
+// best_lb = max(best_lb, max of the first K counts): after the all-reduce of a sharded wave
+void launch_raise_best_lb(const unsigned* cnt, const int* offsets, int num_trials,
+                          unsigned* best_lb, cudaStream_t s);
 // Largest double r with fl(r*r) <= max_residual.
 double inlier_abs_threshold(double max_residual);
 // rbuf: num_e x n residuals; mask (optional): num_e x n; ecnt/esum (optional): num_e.

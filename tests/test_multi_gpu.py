@@ -64,9 +64,56 @@ dist.destroy_process_group()
 '''
 
 
-def _launch(backend, nproc, tmp_path, extra=()):
+_RANSAC_CASES = [
+    # n, inlier ratio, min trials, max trials, scene seed, PRUNE_MIN
+    (3000, 0.45, 2048, 10000, 1, 128),    # several waves, pruned second phases, adaptive abort
+    (12000, 0.3, 2500, 2500, 7, 2048),    # fixed trial count
+    (2000, 0.35, 0, 10000, 5, 128),       # abort inside the first wave
+    (777, 0.5, 1100, 3000, 9, 128),       # ragged sizes
+    (20000, 0.3, 6000, 6000, 11, 2048),   # more than one model block per rank
+]
+
+_RANSAC_WORKER = r'''
+import os, sys, json
+sys.path.insert(0, {root!r})
+import numpy as np
+import torch
+import torch.distributed as dist
+import privacy_preserving_sfm_b200 as pp
+from privacy_preserving_sfm_b200 import RANSACOptions, synthetic as S
+
+dist.init_process_group("nccl")
+rank, world = dist.get_rank(), dist.get_world_size()
+torch.cuda.set_device(rank)
+ctx = pp.Context(rank)
+ctx.comm_init_from_torch(dist)
+out = []
+for n, ratio, tmin, tmax, seed, prune_min in {cases!r}:
+    os.environ["PPSFM_RANSAC_PRUNE_MIN"] = str(prune_min)
+    sc = S.make_abs_pose_scene(n=n, inlier_ratio=ratio, seed=seed)
+    o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                      min_num_trials=tmin, max_num_trials=tmax)
+    ctx.set_prng_seed(0)
+    rep, mask = ctx.ransac_p6l_sharded(sc["lines"], sc["aligned"], sc["points"], o)
+    tm = ctx.ransac_timing()
+    out.append(dict(success=int(rep.success), num_trials=int(rep.num_trials),
+                    num_inliers=int(rep.num_inliers), residual_sum=float(rep.residual_sum).hex(),
+                    best=(int(rep.best_trial), int(rep.best_model_idx)),
+                    model=[float(x).hex() for x in rep.model],
+                    scored=int(rep.num_models_scored), mask=mask.tobytes().hex(),
+                    prng=int(ctx.prng_peek()), pairs=int(tm.score_pairs)))
+with open(os.path.join(sys.argv[1], f"ransac{{rank}}.json"), "w") as f:
+    json.dump(out, f)
+dist.barrier()
+if rank == 0:
+    print("RANSAC_NCCL_OK")
+dist.destroy_process_group()
+'''
+
+
+def _launch(backend, nproc, tmp_path, extra=(), worker=None):
     script = tmp_path / "worker.py"
-    script.write_text(_WORKER.format(root=ROOT))
+    script.write_text(worker if worker is not None else _WORKER.format(root=ROOT))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={nproc}",
            "--master-addr", "127.0.0.1", "--master-port", "29517", str(script), backend, *extra]
     return subprocess.run(cmd, capture_output=True, text=True, timeout=600)
@@ -87,6 +134,56 @@ def test_shard_stats_single_process():
     parts = [ba.shard_stats(arr, r, 3) for r in range(3)]
     assert sum(p[0] for p in parts) == 150 and sum(p[1] for p in parts) == 50
     assert all(p[2] == 5 and p[3] == 150 for p in parts)
+
+
+def test_ransac_shard_accounting():
+    """Host side of the sharded RANSAC call: the model blocks (512 models) are dealt round-robin,
+    every model belongs to exactly one rank, shares differ by at most one block."""
+    import privacy_preserving_sfm_b200 as pp
+    for K in (0, 1, 511, 512, 513, 4000, 37712):
+        for world in (1, 2, 3, 8):
+            own = [pp.binding.ransac_shard_models(K, r, world) for r in range(world)]
+            assert sum(own) == K
+            assert max(own) - min(own) <= 512
+
+
+@pytest.mark.gpu
+def test_sharded_ransac_call_matches_single_gpu(tmp_path, ctx, monkeypatch):
+    """ONE RANSAC call sharded over 2 GPUs: every rank returns the report, mask and
+    generator state of the single-GPU call, bit for bit, and scores about half of the pairs."""
+    import json
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    import privacy_preserving_sfm_b200 as pp
+    from privacy_preserving_sfm_b200 import RANSACOptions, synthetic as S
+    out = tmp_path / "out"
+    out.mkdir()
+    r = _launch("nccl", 2, tmp_path, extra=(str(out),),
+                worker=_RANSAC_WORKER.format(root=ROOT, cases=_RANSAC_CASES))
+    assert r.returncode == 0 and "RANSAC_NCCL_OK" in r.stdout, r.stdout[-2000:] + r.stderr[-4000:]
+    got = [json.load(open(out / f"ransac{rank}.json")) for rank in range(2)]
+    for i, (n, ratio, tmin, tmax, seed, prune_min) in enumerate(_RANSAC_CASES):
+        monkeypatch.setenv("PPSFM_RANSAC_PRUNE_MIN", str(prune_min))
+        sc = S.make_abs_pose_scene(n=n, inlier_ratio=ratio, seed=seed)
+        o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                          min_num_trials=tmin, max_num_trials=tmax)
+        ctx.set_prng_seed(0)
+        rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+        pairs1 = ctx.ransac_timing().score_pairs
+        for rank in range(2):
+            g = got[rank][i]
+            assert g["success"] == rep.success and g["num_trials"] == rep.num_trials, (i, rank)
+            assert g["num_inliers"] == rep.num_inliers, (i, rank)
+            assert g["residual_sum"] == float(rep.residual_sum).hex(), (i, rank)
+            assert tuple(g["best"]) == (rep.best_trial, rep.best_model_idx), (i, rank)
+            assert g["model"] == [float(x).hex() for x in rep.model], (i, rank)
+            assert g["scored"] == rep.num_models_scored, (i, rank)
+            assert g["mask"] == mask.tobytes().hex(), (i, rank)
+            assert g["prng"] == ctx.prng_peek(), (i, rank)
+        if n >= 12000:   # the work is really split: each rank evaluates about half of the pairs
+            assert got[0][i]["pairs"] + got[1][i]["pairs"] <= 1.1 * pairs1
+            assert max(got[0][i]["pairs"], got[1][i]["pairs"]) <= 0.75 * pairs1
 
 
 @pytest.mark.gpu
