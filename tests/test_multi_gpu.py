@@ -102,7 +102,7 @@ for n, ratio, tmin, tmax, seed, prune_min in {cases!r}:
                     model=[float(x).hex() for x in rep.model],
                     scored=int(rep.num_models_scored), mask=mask.tobytes().hex(),
                     prng=int(ctx.prng_peek()), pairs=int(tm.score_pairs)))
-with open(os.path.join(sys.argv[1], f"ransac{{rank}}.json"), "w") as f:
+with open(os.path.join(sys.argv[2], f"ransac{{rank}}.json"), "w") as f:
     json.dump(out, f)
 dist.barrier()
 if rank == 0:
