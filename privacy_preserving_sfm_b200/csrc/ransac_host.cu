@@ -215,8 +215,12 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   const int kSolveThreadsLate = ppsfm::tune_int("PPSFM_SOLVE_THREADS_LATE", 256);
   size_t num_issued = 0;   // waves issued so far
   double models_per_trial = 3.9;  // P6L: 3.8 +- 0.1 on generic data; updated from consumed waves
+  // the first wave of a call is solved eight lanes per hypothesis (p6l_octet.cuh): its latency is
+  // the one thing the pipeline cannot hide; PPSFM_SOLVE_OCTET = 0 never, 2 every wave
+  const int kSolveOctetMode = ppsfm::tune_int("PPSFM_SOLVE_OCTET", 1);
   auto solve_lanes = [&](int H) {
     if (kSolveLanes > 0) return kSolveLanes;
+    if (kSolveOctetMode >= 2 || (kSolveOctetMode == 1 && num_issued == 0)) return ppsfm::kSolveOctet;
     // later waves solve under the scoring of the previous one, where their latency is hidden
     // anyway: full warps, so that the solve occupies as few SMs as possible (kSolveThreadsLate)
     if (num_issued > 0) return 32;
@@ -985,8 +989,11 @@ int ppsfm_p6l_solve_batch(ppsfm_ctx* ctx, const double* lines, const uint8_t* al
     PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_samples.p, sample_idx, sizeof(uint32_t) * 6 * H,
                                     cudaMemcpyHostToDevice, st));
     PPSFM_CUDA(ctx, cudaMemsetAsync(ctx->d_models.p, 0, sizeof(double) * 96 * H, st));
+    // (PPSFM_SOLVE_OCTET >= 2: through the eight-lanes-per-hypothesis kernel — the parity tests
+    // run both and require identical bits)
     launch_p6l_solve(corr->corr6, corr->aligned, ctx->d_samples.as<uint32_t>(), (int)H,
-                     ctx->d_models.as<double>(), ctx->d_num_models.as<int>(), st);
+                     ctx->d_models.as<double>(), ctx->d_num_models.as<int>(), st,
+                     ppsfm::tune_int("PPSFM_SOLVE_OCTET", 1) >= 2 ? ppsfm::kSolveOctet : 32);
     PPSFM_CUDA(ctx, cudaMemcpyAsync(models_out, ctx->d_models.p, sizeof(double) * 96 * H,
                                     cudaMemcpyDeviceToHost, st));
     PPSFM_CUDA(ctx, cudaMemcpyAsync(num_models_out, ctx->d_num_models.p, sizeof(int) * H,

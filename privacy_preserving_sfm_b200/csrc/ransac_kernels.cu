@@ -17,7 +17,7 @@
 #include <cmath>
 #include <cstdint>
 
-#include "p6l_device.cuh"
+#include "p6l_octet.cuh"
 #include "ransac_kernels.h"
 
 namespace ppsfm {
@@ -109,10 +109,48 @@ p6l_solve_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ a
     for (int j = 0; j < 12; ++j) out[m * 12 + j] = models[m][j];
 }
 
+// ------------------------------------------------------------------------------------------
+// P6L solve, eight lanes per hypothesis (p6l_octet.cuh): the latency-critical variant for the
+// head of a call.  Bit-identical models.
+// ------------------------------------------------------------------------------------------
+constexpr int kOctetThreads = 64;
+__global__ void __launch_bounds__(kOctetThreads)
+p6l_solve_octet_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ aligned,
+                       const uint32_t* __restrict__ samples, int num_trials,
+                       double* __restrict__ models_out, int* __restrict__ num_models_out) {
+  __shared__ double Tsm[kOctetThreads / 8][8 * dev::Octet::kLd];
+  const int oct = threadIdx.x >> 3;
+  const int t = blockIdx.x * (kOctetThreads / 8) + oct;
+  if (t >= num_trials) return;  // whole octets leave
+  dev::Octet o;
+  o.T = Tsm[oct];
+  o.sub = threadIdx.x & 7;
+  o.mask = 0xffu << ((threadIdx.x & 31) & ~7);
+  double lines[6][3], points[6][3];
+  bool all_aligned = true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    const uint32_t idx = samples[6 * (size_t)t + i];
+    const double* c = corr6 + 6 * (size_t)idx;
+    lines[i][0] = c[0]; lines[i][1] = c[1]; lines[i][2] = c[2];
+    points[i][0] = c[3]; points[i][1] = c[4]; points[i][2] = c[5];
+    all_aligned = all_aligned && (aligned != nullptr && aligned[idx] != 0);
+  }
+  const int n = dev::p6l_estimate_octet(o, lines, all_aligned, points,
+                                        models_out + (size_t)t * 96);
+  if (o.sub == 0) num_models_out[t] = n;
+}
+
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
                       int lanes_per_warp, int threads_per_cta) {
   if (num_trials <= 0) return;
+  if (lanes_per_warp == kSolveOctet) {
+    const int per_cta = kOctetThreads / 8;
+    p6l_solve_octet_kernel<<<(num_trials + per_cta - 1) / per_cta, kOctetThreads, 0, s>>>(
+        corr6, aligned, samples, num_trials, models_out, num_models_out);
+    return;
+  }
   const int threads = std::max(32, std::min(256, threads_per_cta)) / 32 * 32;
   const int lanes = std::max(1, std::min(32, lanes_per_warp));
   const int warps = (num_trials + lanes - 1) / lanes;

@@ -11,7 +11,9 @@ namespace ppsfm {
 // corr6f (device, ceil(n/2) x 12 floats): the set rounded to float, two correspondences per record
 void launch_pack_corr(const double* lines, const double* points, size_t n, double* corr6,
                       float* corr6f, double* bounds, cudaStream_t s);
-// lanes_per_warp: how many lanes of each warp take a hypothesis (divergence vs. warp count)
+// lanes_per_warp: how many lanes of each warp take a hypothesis (divergence vs. warp count);
+// kSolveOctet: the eight-lanes-per-hypothesis kernel (shortest latency, twice the issue slots)
+constexpr int kSolveOctet = -8;
 void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_t* samples,
                       int num_trials, double* models_out, int* num_models_out, cudaStream_t s,
                       int lanes_per_warp = 32, int threads_per_cta = 64);

@@ -56,7 +56,11 @@ def test_line_residuals_empty_and_ragged(ctx, oracle):
         assert (int(cnt[0]), sm[0]) == oracle.inlier_support(r, 1e-4)
 
 
-def test_p6l_solve_batch_bit_exact(ctx, oracle):
+@pytest.mark.parametrize("octet", [0, 2])
+def test_p6l_solve_batch_bit_exact(ctx, oracle, monkeypatch, octet):
+    """Both solve kernels — one thread per hypothesis, and eight lanes per hypothesis
+    (p6l_octet.cuh, the kernel at the head of every RANSAC call) — against the oracle."""
+    monkeypatch.setenv("PPSFM_SOLVE_OCTET", str(octet))
     sc = S.make_abs_pose_scene(n=3000, seed=7)
     ctx.set_prng_seed(1)
     table = ctx.sample_table(3000, 600)
@@ -69,6 +73,36 @@ def test_p6l_solve_batch_bit_exact(ctx, oracle):
         assert np.array_equal(models[t, :nm[t]], ref), f"trial {t}"
         tot += nm[t]
     assert tot > 1000
+
+
+def test_p6l_solve_kernels_agree_on_degenerate_samples(ctx, monkeypatch):
+    """Samples that take the rare branches (all lines aligned; a singular translation block ->
+    fixed mixing matrix; repeated correspondences -> near-singular elimination and the affine
+    change of variables): the two solve kernels must still agree bit for bit."""
+    sc = S.make_abs_pose_scene(n=400, seed=17)
+    lines, pts, al = sc["lines"].copy(), sc["points"].copy(), sc["aligned"].copy()
+    lines[:3] = lines[0]                      # det(l0 l1 l2) = 0
+    pts[10:16] = pts[10]                      # six identical points
+    lines[20:26, :2] = [1.0, 0.0]             # parallel lines
+    al[30:36] = 1                             # all aligned -> no model
+    rng = np.random.default_rng(3)
+    table = np.stack([rng.permutation(400)[:6] for _ in range(300)]).astype(np.uint32)
+    table[0] = [0, 1, 2, 50, 51, 52]
+    table[1] = [10, 11, 12, 13, 14, 15]
+    table[2] = [20, 21, 22, 23, 24, 25]
+    table[3] = [30, 31, 32, 33, 34, 35]
+    table[4] = [0, 1, 2, 10, 11, 12]
+    table[5] = [7, 7, 7, 7, 7, 7]
+    outs = []
+    for octet in (0, 2):
+        monkeypatch.setenv("PPSFM_SOLVE_OCTET", str(octet))
+        models, nm = ctx.p6l_solve_batch(lines, al, pts, table)
+        outs.append((models.copy(), nm.copy()))
+    assert np.array_equal(outs[0][1], outs[1][1])
+    assert outs[0][1][3] == 0
+    for t in range(len(table)):
+        a, b = outs[0][0][t, :outs[0][1][t]], outs[1][0][t, :outs[1][1][t]]
+        assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), t   # NaNs compare by bits
 
 
 def test_p6l_recovers_generating_pose(ctx):
