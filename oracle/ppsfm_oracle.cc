@@ -140,6 +140,7 @@ void SolvePartialPiv3(double A[3][3], double B[3][NC]) {
 // Only the active window is updated (sufficient for eigenvalues; window values are identical).
 // ---------------------------------------------------------------------------------------------
 constexpr int kN = 8;
+thread_local int g_last_qr_sweeps = 0;  // diagnostics only (orc_poly8_sweeps)
 
 struct Hqr8 {
   double T[kN][kN];
@@ -359,6 +360,7 @@ struct Hqr8 {
     }
     for (int i = 0; i < kN; ++i)
       for (int j = 0; j < kN; ++j) T[i][j] = T[i][j] * scale;
+    g_last_qr_sweeps = total_iter;
     return ok;
   }
 
@@ -853,6 +855,9 @@ int orc_poly8_all_roots(const double* c, double* re_im_out) {
   }
   return ok ? 8 : -1;
 }
+
+/* diagnostics: Francis sweeps the eigenvalue step of the last P6L / re3q3 / poly8 call took */
+int orc_last_qr_sweeps(void) { return g_last_qr_sweeps; }
 
 void orc_re3q3_resultant(const double* P, double* a_out, double* c_out) {
   double Pm[3][7], a[33], c[9];

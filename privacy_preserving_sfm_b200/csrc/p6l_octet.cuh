@@ -34,8 +34,13 @@ struct Octet {
 };
 
 // Hqr8::reduce of p6l_device.cuh, cooperatively.  Returns false if the iteration limit is hit.
+// (The member mask is a run-time value: a variant templated on the octet's position in its warp
+// — constant masks, single-instruction __syncwarp — was measured TWICE as slow, 0.25 against
+// 0.12 ms: the four octets of a warp then run four copies of the code and can never issue
+// together, whereas in this shared-code form they are converged most of the time.)
 __device__ inline bool hqr8_reduce_octet(const Octet& o) {
   const int sub = o.sub;
+  const unsigned oct_shift = (threadIdx.x & 31u) & ~7u;  // first lane of the octet in its warp
   // scale = max |T| (the comparator of the serial code ignores NaNs: any order gives the same)
   double scale = 0.0;
 #pragma unroll
@@ -67,11 +72,17 @@ __device__ inline bool hqr8_reduce_octet(const Octet& o) {
   bool ok = true;
   if (norm_nonzero) {
     while (iu >= 0) {
-      int il = iu;
-      while (il > 0) {
-        const double s = fabs(o.at(il - 1, il - 1)) + fabs(o.at(il, il));
-        if (fabs(o.at(il, il - 1)) <= eps * s) break;
-        --il;
+      // findSmallSubdiagEntry: the serial loop stops at the largest i <= iu whose sub-diagonal
+      // entry is negligible; lane i tests entry i, a ballot picks the largest
+      int il;
+      {
+        bool small = false;
+        if (sub >= 1 && sub <= iu) {
+          const double s = fabs(o.at(sub - 1, sub - 1)) + fabs(o.at(sub, sub));
+          small = fabs(o.at(sub, sub - 1)) <= eps * s;
+        }
+        const unsigned bits = (__ballot_sync(o.mask, small) & o.mask) >> oct_shift;
+        il = bits ? 31 - __clz((int)bits) : 0;
       }
       if (il == iu) {
         if (sub == 0) {
@@ -168,20 +179,35 @@ __device__ inline bool hqr8_reduce_octet(const Octet& o) {
           ok = false;
           break;
         }
+        // initFrancisQRStep: the serial search walks im = iu-2 ... il and stops at the first im
+        // that passes the test (im == il always does); every candidate only reads the matrix, so
+        // lane m evaluates candidate m and the largest passing one wins
         int im;
         double v0 = 0.0, v1 = 0.0, v2 = 0.0;
-        for (im = iu - 2; im >= il; --im) {
-          const double Tmm = o.at(im, im);
-          const double r = sh0 - Tmm;
-          const double s = sh1 - Tmm;
-          v0 = (r * s - sh2) / o.at(im + 1, im) + o.at(im, im + 1);
-          v1 = o.at(im + 1, im + 1) - Tmm - r - s;
-          v2 = o.at(im + 2, im + 1);
-          if (im == il) break;
-          const double lhs = o.at(im, im - 1) * (fabs(v1) + fabs(v2));
-          const double rhs =
-              v0 * (fabs(o.at(im - 1, im - 1)) + fabs(Tmm) + fabs(o.at(im + 1, im + 1)));
-          if (fabs(lhs) < eps * rhs) break;
+        {
+          bool pass = false;
+          if (sub >= il && sub <= iu - 2) {
+            const double Tmm = o.at(sub, sub);
+            const double r = sh0 - Tmm;
+            const double s = sh1 - Tmm;
+            v0 = (r * s - sh2) / o.at(sub + 1, sub) + o.at(sub, sub + 1);
+            v1 = o.at(sub + 1, sub + 1) - Tmm - r - s;
+            v2 = o.at(sub + 2, sub + 1);
+            if (sub == il) {
+              pass = true;
+            } else {
+              const double lhs = o.at(sub, sub - 1) * (fabs(v1) + fabs(v2));
+              const double rhs =
+                  v0 * (fabs(o.at(sub - 1, sub - 1)) + fabs(Tmm) + fabs(o.at(sub + 1, sub + 1)));
+              pass = fabs(lhs) < eps * rhs;
+            }
+          }
+          const unsigned bits = (__ballot_sync(o.mask, pass) & o.mask) >> oct_shift;
+          im = 31 - __clz((int)bits);  // bit il is always set
+          const int src = (int)oct_shift + im;
+          v0 = __shfl_sync(o.mask, v0, src);
+          v1 = __shfl_sync(o.mask, v1, src);
+          v2 = __shfl_sync(o.mask, v2, src);
         }
         o.sync();  // all reads of the search are done before the sweep writes
         for (int k = im; k <= iu - 2; ++k) {

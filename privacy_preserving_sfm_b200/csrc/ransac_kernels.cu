@@ -19,6 +19,7 @@
 
 #include "p6l_octet.cuh"
 #include "ransac_kernels.h"
+#include "common.h"
 
 namespace ppsfm {
 
@@ -117,10 +118,16 @@ constexpr int kOctetThreads = 64;
 __global__ void __launch_bounds__(kOctetThreads)
 p6l_solve_octet_kernel(const double* __restrict__ corr6, const uint8_t* __restrict__ aligned,
                        const uint32_t* __restrict__ samples, int num_trials,
-                       double* __restrict__ models_out, int* __restrict__ num_models_out) {
+                       double* __restrict__ models_out, int* __restrict__ num_models_out,
+                       int octets_per_warp) {
   __shared__ double Tsm[kOctetThreads / 8][8 * dev::Octet::kLd];
   const int oct = threadIdx.x >> 3;
-  const int t = blockIdx.x * (kOctetThreads / 8) + oct;
+  // octets of a warp follow different control paths; with fewer than four octets per warp the
+  // other lanes of the warp stay idle (octets_per_warp: measured trade-off, see launch)
+  const int oct_in_warp = oct & 3;
+  if (oct_in_warp >= octets_per_warp) return;
+  const int warp = (blockIdx.x * kOctetThreads + threadIdx.x) >> 5;
+  const int t = warp * octets_per_warp + oct_in_warp;
   if (t >= num_trials) return;  // whole octets leave
   dev::Octet o;
   o.T = Tsm[oct];
@@ -146,9 +153,10 @@ void launch_p6l_solve(const double* corr6, const uint8_t* aligned, const uint32_
                       int lanes_per_warp, int threads_per_cta) {
   if (num_trials <= 0) return;
   if (lanes_per_warp == kSolveOctet) {
-    const int per_cta = kOctetThreads / 8;
+    static const int opw = std::max(1, std::min(4, tune_int("PPSFM_OCTETS_PER_WARP", 4)));
+    const int per_cta = (kOctetThreads / 32) * opw;
     p6l_solve_octet_kernel<<<(num_trials + per_cta - 1) / per_cta, kOctetThreads, 0, s>>>(
-        corr6, aligned, samples, num_trials, models_out, num_models_out);
+        corr6, aligned, samples, num_trials, models_out, num_models_out, opw);
     return;
   }
   const int threads = std::max(32, std::min(256, threads_per_cta)) / 32 * 32;
