@@ -231,9 +231,10 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.J, ba_j_doubles(K)));
   BA_TRY(DevAlloc(st, &d.cam_scale, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.pt_scale, 3 * (size_t)P));
-  BA_TRY(DevAlloc(st, &d.U, 36 * (size_t)NB));
+  // U and g_c in ONE allocation: the sharded solve sums both over the ranks with one all-reduce
+  BA_TRY(DevAlloc(st, &d.U, 42 * (size_t)NB));
+  d.gc = d.U + 36 * (size_t)NB;
   BA_TRY(DevAlloc(st, &d.Upart, 4 * 27 * (size_t)NB));
-  BA_TRY(DevAlloc(st, &d.gc, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.V, 6 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.Vinv, 6 * (size_t)P));
@@ -275,7 +276,6 @@ namespace {
 
 // Sum-reduction across ranks (NCCL all-reduce over NVLink); identity for a single GPU.
 int AllReduceSum(BaState* st, double* dev, size_t count);
-int AllReduceMax(BaState* st, double* dev, size_t count);
 
 struct Scalars {
   double v[kNumScalars];
@@ -338,8 +338,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   auto normal_equations = [&]() -> int {
     st->launches += launch_normal_equations(d, s);
     if (st->world > 1) {  // cameras are replicated: U, g_c are sums over all ranks' observations
-      int rc = AllReduceSum(st, d.U, 36 * (size_t)d.NB);
-      if (rc == PPSFM_OK) rc = AllReduceSum(st, d.gc, 6 * (size_t)d.NB);
+      const int rc = AllReduceSum(st, d.U, 42 * (size_t)d.NB);  // U and g_c are contiguous
       if (rc != PPSFM_OK) return rc;
     }
     return PPSFM_OK;
@@ -347,8 +346,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   auto cost_and_gradient = [&](double* cost, double* gmax) -> int {
     st->launches += launch_gradient_max_norm(d, s);
     if (st->world > 1) {
-      int rc = AllReduceSum(st, d.scalars + kCost, 1);
-      if (rc == PPSFM_OK) rc = AllReduceMax(st, d.scalars + kGradMax, 1);
+      const int rc = CommAllReduceSumAndMax(st->ctx, d.scalars + kCost, 1, d.scalars + kGradMax, 1);
       if (rc != PPSFM_OK) return rc;
     }
     int rc = FetchScalars(st, &sc);
@@ -436,14 +434,12 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[2], s));
     st->launches += launch_backsubstitute_and_update(d, st->rank == 0, s);
-    if (st->world > 1) {
-      rc = AllReduceSum(st, d.scalars + kModelChange, 3);  // model change, step^2, x^2
-      if (rc != PPSFM_OK) return rc;
-    }
     // candidate cost
     st->launches += launch_linearize(d, d.qn, d.tn, d.Xn, false, loss, s);
     if (st->world > 1) {
-      rc = AllReduceSum(st, d.scalars + kCost, 1);
+      // candidate cost, model cost change, step^2, x^2: four adjacent scalars, one all-reduce
+      static_assert(kCost == 0 && kModelChange == 1 && kStepSq == 2 && kXSq == 3, "adjacent");
+      rc = AllReduceSum(st, d.scalars + kCost, 4);
       if (rc != PPSFM_OK) return rc;
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[3], s));
@@ -565,9 +561,6 @@ int BaReset(BaState* st) {
 namespace {
 int AllReduceSum(BaState* st, double* dev, size_t count) {
   return CommAllReduce(st->ctx, dev, count, false);
-}
-int AllReduceMax(BaState* st, double* dev, size_t count) {
-  return CommAllReduce(st->ctx, dev, count, true);
 }
 }  // namespace
 

@@ -26,6 +26,8 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) =
       nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
   bool ok = false;
 };
@@ -51,6 +53,8 @@ NcclApi* Api() {
   api.AllReduce = (decltype(api.AllReduce))dlsym(api.handle, "ncclAllReduce");
   api.CommDestroy = (decltype(api.CommDestroy))dlsym(api.handle, "ncclCommDestroy");
   api.GetErrorString = (decltype(api.GetErrorString))dlsym(api.handle, "ncclGetErrorString");
+  api.GroupStart = (decltype(api.GroupStart))dlsym(api.handle, "ncclGroupStart");
+  api.GroupEnd = (decltype(api.GroupEnd))dlsym(api.handle, "ncclGroupEnd");
   api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.CommDestroy;
   return &api;
 }
@@ -70,6 +74,28 @@ int CommAllReduce(ppsfm_ctx* ctx, double* dev, size_t count, bool max_op) {
   const ncclResult_t r = a->AllReduce(dev, dev, count, kNcclFloat64, max_op ? kNcclMax : kNcclSum,
                                       (ncclComm_t)ctx->comm, ctx->stream);
   if (r != 0) return NcclFail(ctx, "ncclAllReduce", r);
+  return PPSFM_OK;
+}
+
+// A sum all-reduce and a max all-reduce issued as ONE NCCL group (one launch): the cost and the
+// gradient max-norm of an accepted LM step.
+int CommAllReduceSumAndMax(ppsfm_ctx* ctx, double* sum_dev, size_t sum_count, double* max_dev,
+                           size_t max_count) {
+  if (ctx->world <= 1) return PPSFM_OK;
+  NcclApi* a = Api();
+  if (!a->ok || !ctx->comm) return fail(ctx, PPSFM_ERR_NCCL, "communicator not initialised");
+  const bool group = a->GroupStart && a->GroupEnd;
+  if (group) a->GroupStart();
+  ncclResult_t r = a->AllReduce(sum_dev, sum_dev, sum_count, kNcclFloat64, kNcclSum,
+                                (ncclComm_t)ctx->comm, ctx->stream);
+  if (r == 0)
+    r = a->AllReduce(max_dev, max_dev, max_count, kNcclFloat64, kNcclMax, (ncclComm_t)ctx->comm,
+                     ctx->stream);
+  if (group) {
+    const ncclResult_t r2 = a->GroupEnd();
+    if (r == 0) r = r2;
+  }
+  if (r != 0) return NcclFail(ctx, "ncclAllReduce (group)", r);
   return PPSFM_OK;
 }
 

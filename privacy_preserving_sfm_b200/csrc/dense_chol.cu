@@ -91,6 +91,20 @@ __device__ __forceinline__ double shfl_d(double v, int src) {
   return __hiloint2double(hi, lo);
 }
 
+// 1 / x to full double precision without the IEEE division sequence: the 20-bit hardware seed
+// (MUFU.RCP64H) and two Newton steps (2^-20 -> 2^-40 -> 2^-80), four dependent DFMAs.  The pivot
+// reciprocal sits on the factorisation's dependency chain (one per pivot, 3000 pivots in a row at
+// 500 cameras); x is a positive, normal pivot here.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  r = fma(r, e, r);
+  return r;
+}
+
 // (optional per-tile event trace: PPSFM_CHOL_TRACE=<file>, 16 timestamp slots per tile)
 __device__ __forceinline__ unsigned long long global_ns() {
   unsigned long long t;
@@ -169,7 +183,7 @@ __device__ __forceinline__ bool factor8(double* Cs, int k1, double* rdiag, int l
       l1 = e1;
       pv = piv;
     }
-    const double sc = u * (1.0 / piv);
+    const double sc = u * fast_rcp(piv);
     e0 -= t0 * sc;
     e1 -= t1 * sc;
   }
