@@ -405,6 +405,14 @@ int ppsfm_estimate_triangulation_batch(ppsfm_ctx* ctx, const ppsfm_filter_proble
                                        uint8_t* success, uint8_t* inlier_mask,
                                        uint32_t* num_trials);
 
+/* CameraModel::ImageToWorldThreshold (src/base/camera_models.h:533-543): pixel threshold / mean
+ * focal length of the model (host arithmetic).  PPSFM_ERR_INVALID for an unsupported model id. */
+int ppsfm_image_to_world_threshold(int camera_model, const double* camera_params, double threshold,
+                                   double* out);
+/* RotationMatrixToQuaternion (src/base/pose.cc:41-44 = Eigen::Quaterniond(R)); R column-major
+ * 3x3, qvec (w, x, y, z).  Host arithmetic. */
+void ppsfm_rotation_matrix_to_quaternion(const double* R, double* qvec);
+
 /* ---- measurement helpers (bench.py only; not part of the reference surface) ------------------
  * FP64 issue rate in 1e12 thread-instructions/s: fused (DFMA) and unfused (DMUL/DADD mix). */
 int ppsfm_bench_fp64_peak(ppsfm_ctx* ctx, double* dfma_tips, double* dmuladd_tips);

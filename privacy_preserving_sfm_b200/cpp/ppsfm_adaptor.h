@@ -14,6 +14,11 @@
 //   RefineAbsolutePoseFromLines     estimators/pose.h:117    ppsfm::RefineAbsolutePoseFromLines
 //   BundleAdjustmentOptions/Config  optim/bundle_adjustment.h ppsfm::BundleAdjustment{Options,Config}
 //   BundleAdjuster::Solve/Summary   optim/bundle_adjustment.h ppsfm::BundleAdjuster<Reconstruction>
+//   EstimateTriangulation           estimators/triangulation.h:143  ppsfm::EstimateTriangulation
+//                                   (+ EstimateTriangulationBatch: all tracks of an image at once)
+//   Reconstruction::FilterPoints3D, FilterObservationsWithNegativeDepth
+//                                   base/reconstruction.cc:425-460  ppsfm::FilterPoints3D, ...
+//   Camera::ImageToWorldThreshold   base/camera_models.h:533-543    ppsfm::ImageToWorldThreshold
 //
 // Vector types: with -DPPSFM_WITH_EIGEN the Eigen types of the reference are used
 // (Eigen::Vector3d, Eigen::Vector4d, Eigen::Matrix3x4d); otherwise std::array stand-ins with the
@@ -31,6 +36,7 @@
 #include <limits>
 #include <unordered_map>
 #include <unordered_set>
+#include <utility>
 #include <vector>
 
 #include "ppsfm_b200.h"
@@ -303,6 +309,307 @@ inline bool RefineAbsolutePoseFromLines(const AbsolutePoseRefinementOptions& opt
                 summary.num_successful_steps + summary.num_unsuccessful_steps,
                 summary.initial_cost, summary.final_cost);
   return rc == PPSFM_OK;
+}
+
+
+// ---- src/base/camera_models.h:533-543 (through Camera::ImageToWorldThreshold, camera.cc) -------
+// CameraT: .ModelId(), .ParamsData()
+template <class CameraT>
+inline double ImageToWorldThreshold(const CameraT& camera, double threshold) {
+  double out = 0.0;
+  PPSFM_CHECK(ppsfm_image_to_world_threshold(camera.ModelId(), camera.ParamsData(), threshold,
+                                             &out) == PPSFM_OK);
+  return out;
+}
+
+// ---- src/estimators/triangulation.h:57-147 ---------------------------------------------------
+// EstimateTriangulation: LORANSAC over the 3-combinations of the views of ONE track.  The GPU
+// entry point takes many tracks at once (ppsfm_estimate_triangulation_batch); this is the
+// reference's per-track signature on top of it, and EstimateTriangulationBatch the form the
+// triangulator should call once per image.  CameraT: .ModelId(), .NumParams(), .ParamsData(),
+// .Width(), .Height().
+struct TriangulationEstimator {
+  enum class ResidualType { ANGULAR_ERROR, REPROJECTION_ERROR };
+  struct PointData {
+    PointData() = default;
+    explicit PointData(const Vector3d& l) : line(l) {}
+    Vector3d line{};
+  };
+  template <class CameraT>
+  struct PoseData {
+    PoseData() = default;
+    PoseData(const Matrix3x4d& P, const Vector3d& c, const CameraT* cam)
+        : proj_matrix(P), proj_center(c), camera(cam) {}
+    Matrix3x4d proj_matrix{};  // [R | t], column-major
+    Vector3d proj_center{};
+    const CameraT* camera = nullptr;
+  };
+  static const int kMinNumSamples = 3;
+};
+
+struct EstimateTriangulationOptions {
+  double min_tri_angle = 0.0;  // radians
+  TriangulationEstimator::ResidualType residual_type =
+      TriangulationEstimator::ResidualType::ANGULAR_ERROR;
+  RANSACOptions ransac_options;
+  // tracks up to this length sample all C(n, 3) combinations
+  // (src/sfm/incremental_triangulator.cc:527-531 sets min_num_trials that way per track)
+  int exhaustive_threshold = 0;
+  void Check() const {
+    PPSFM_CHECK(min_tri_angle >= 0.0);
+    ransac_options.Check();
+  }
+};
+
+namespace internal {
+// a batch of tracks as the flat problem of the C-ABI
+template <class CameraT>
+struct TrackBatch {
+  std::vector<double> qvecs, tvecs, params, lines;
+  std::vector<int32_t> image_camera, model, width, height, obs_image;
+  std::vector<int64_t> track_start{0};
+  std::vector<uint8_t> aligned;
+  std::unordered_map<const CameraT*, int> camera_index;
+  void AddView(const Vector3d& line, const Matrix3x4d& P, const CameraT* camera) {
+    PPSFM_CHECK(camera != nullptr);
+    auto it = camera_index.find(camera);
+    if (it == camera_index.end()) {
+      it = camera_index.emplace(camera, (int)model.size()).first;
+      model.push_back(camera->ModelId());
+      width.push_back((int32_t)camera->Width());
+      height.push_back((int32_t)camera->Height());
+      const size_t base = params.size();
+      params.resize(base + 12, 0.0);
+      for (size_t k = 0; k < camera->NumParams() && k < 12; ++k)
+        params[base + k] = camera->ParamsData()[k];
+    }
+    double q[4];
+    ppsfm_rotation_matrix_to_quaternion(P.data(), q);  // first 9 doubles = R, column-major
+    obs_image.push_back((int32_t)image_camera.size());
+    image_camera.push_back(it->second);
+    for (int k = 0; k < 4; ++k) qvecs.push_back(q[k]);
+    for (int k = 0; k < 3; ++k) tvecs.push_back(P.data()[9 + k]);
+    for (int k = 0; k < 3; ++k) lines.push_back(line.data()[k]);
+    aligned.push_back(0);
+  }
+  void EndTrack() { track_start.push_back((int64_t)obs_image.size()); }
+  ppsfm_filter_problem Problem() const {
+    ppsfm_filter_problem pb{};
+    pb.num_images = (int32_t)image_camera.size();
+    pb.qvecs = qvecs.data();
+    pb.tvecs = tvecs.data();
+    pb.image_camera = image_camera.data();
+    pb.num_cameras = (int32_t)model.size();
+    pb.camera_model = model.data();
+    pb.camera_params = params.data();
+    pb.camera_width = width.data();
+    pb.camera_height = height.data();
+    pb.num_points = (int32_t)track_start.size() - 1;
+    pb.points = nullptr;
+    pb.track_start = track_start.data();
+    pb.num_obs = (int64_t)obs_image.size();
+    pb.obs_image = obs_image.data();
+    pb.obs_line = lines.data();
+    pb.obs_aligned = aligned.data();
+    return pb;
+  }
+};
+inline ppsfm_triangulation_options ToC(const EstimateTriangulationOptions& o) {
+  ppsfm_triangulation_options c;
+  ppsfm_triangulation_options_default(&c);
+  c.min_tri_angle = o.min_tri_angle;
+  c.residual_type = o.residual_type == TriangulationEstimator::ResidualType::ANGULAR_ERROR ? 0 : 1;
+  c.max_error = o.ransac_options.max_error;
+  c.min_inlier_ratio = o.ransac_options.min_inlier_ratio;
+  c.confidence = o.ransac_options.confidence;
+  c.dyn_num_trials_multiplier = o.ransac_options.dyn_num_trials_multiplier;
+  c.min_num_trials = o.ransac_options.min_num_trials;
+  c.max_num_trials = o.ransac_options.max_num_trials;
+  c.exhaustive_threshold = o.exhaustive_threshold;
+  return c;
+}
+}  // namespace internal
+
+// All tracks of a batch in ONE GPU call: point_data[t] / pose_data[t] are the views of track t.
+template <class CameraT>
+inline void EstimateTriangulationBatch(
+    const EstimateTriangulationOptions& options,
+    const std::vector<std::vector<TriangulationEstimator::PointData>>& point_data,
+    const std::vector<std::vector<TriangulationEstimator::PoseData<CameraT>>>& pose_data,
+    std::vector<char>* success, std::vector<std::vector<char>>* inlier_masks,
+    std::vector<Vector3d>* xyz) {
+  options.Check();
+  PPSFM_CHECK(point_data.size() == pose_data.size());
+  internal::TrackBatch<CameraT> batch;
+  for (size_t t = 0; t < point_data.size(); ++t) {
+    PPSFM_CHECK(point_data[t].size() == pose_data[t].size());
+    for (size_t i = 0; i < point_data[t].size(); ++i)
+      batch.AddView(point_data[t][i].line, pose_data[t][i].proj_matrix, pose_data[t][i].camera);
+    batch.EndTrack();
+  }
+  const size_t T = point_data.size(), O = batch.obs_image.size();
+  std::vector<double> x(3 * (T ? T : 1));
+  std::vector<uint8_t> ok(T ? T : 1), mask(O ? O : 1);
+  const ppsfm_filter_problem pb = batch.Problem();
+  const ppsfm_triangulation_options o = internal::ToC(options);
+  internal::CheckRc(ppsfm_estimate_triangulation_batch(ThreadContext(), &pb, &o, x.data(),
+                                                       ok.data(), mask.data(), nullptr));
+  success->assign(T, 0);
+  inlier_masks->assign(T, {});
+  xyz->assign(T, Vector3d{});
+  for (size_t t = 0; t < T; ++t) {
+    (*success)[t] = (char)ok[t];
+    for (int k = 0; k < 3; ++k) (*xyz)[t].data()[k] = x[3 * t + k];
+    for (int64_t k = batch.track_start[t]; k < batch.track_start[t + 1]; ++k)
+      (*inlier_masks)[t].push_back((char)mask[k]);
+  }
+}
+
+// bool EstimateTriangulation(options, point_data, pose_data, &inlier_mask, &xyz)
+// (src/estimators/triangulation.h:143-147)
+template <class CameraT>
+inline bool EstimateTriangulation(
+    const EstimateTriangulationOptions& options,
+    const std::vector<TriangulationEstimator::PointData>& point_data,
+    const std::vector<TriangulationEstimator::PoseData<CameraT>>& pose_data,
+    std::vector<char>* inlier_mask, Vector3d* xyz) {
+  PPSFM_CHECK(point_data.size() >= 3);  // CHECK_GE(point_data.size(), 3), triangulation.cc:124
+  std::vector<char> ok;
+  std::vector<std::vector<char>> masks;
+  std::vector<Vector3d> pts;
+  EstimateTriangulationBatch<CameraT>(options, {point_data}, {pose_data}, &ok, &masks, &pts);
+  if (!ok[0]) return false;
+  *inlier_mask = masks[0];
+  *xyz = pts[0];
+  return true;
+}
+
+// ---- src/base/reconstruction.cc:425-460, 594-719 ---------------------------------------------
+// Reconstruction::FilterPoints3D / FilterObservationsWithNegativeDepth as free functions over a
+// Reconstruction-like object: the tracks of `point3D_ids` go to the GPU as one problem, the
+// delete masks come back and are applied through the reconstruction's own DeleteObservation /
+// DeletePoint3D / Point3D::SetError.  ReconstructionT needs, beyond what BundleAdjuster uses:
+//   ExistsPoint3D(id), DeleteObservation(image_id, line_idx), DeletePoint3D(id),
+//   Point3D(id).SetError(e), Image(id).Lines()[i].IsAligned(), Camera(id).Width() / .Height().
+namespace internal {
+template <class ReconstructionT>
+struct TrackProblem {
+  std::vector<double> qvecs, tvecs, params, points, lines;
+  std::vector<int32_t> image_camera, model, width, height, obs_image;
+  std::vector<int64_t> track_start{0};
+  std::vector<uint8_t> aligned;
+  std::vector<point3D_t> point_ids;
+  std::vector<image_t> image_ids;
+  std::vector<std::pair<image_t, uint32_t>> obs_ref;
+  std::unordered_map<image_t, int> image_index;
+  std::unordered_map<camera_t, int> camera_index;
+  TrackProblem(ReconstructionT* rec, const std::vector<point3D_t>& ids) {
+    for (const point3D_t pid : ids) {
+      if (!rec->ExistsPoint3D(pid)) continue;
+      auto& point3D = rec->Point3D(pid);
+      point_ids.push_back(pid);
+      for (int k = 0; k < 3; ++k) points.push_back(point3D.XYZ().data()[k]);
+      for (const auto& el : point3D.Track().Elements()) {
+        auto it = image_index.find(el.image_id);
+        if (it == image_index.end()) {
+          auto& image = rec->Image(el.image_id);
+          it = image_index.emplace(el.image_id, (int)image_ids.size()).first;
+          image_ids.push_back(el.image_id);
+          for (int k = 0; k < 4; ++k) qvecs.push_back(image.Qvec().data()[k]);
+          for (int k = 0; k < 3; ++k) tvecs.push_back(image.Tvec().data()[k]);
+          const camera_t cid = image.CameraId();
+          auto ct = camera_index.find(cid);
+          if (ct == camera_index.end()) {
+            auto& camera = rec->Camera(cid);
+            ct = camera_index.emplace(cid, (int)model.size()).first;
+            model.push_back(camera.ModelId());
+            width.push_back((int32_t)camera.Width());
+            height.push_back((int32_t)camera.Height());
+            const size_t base = params.size();
+            params.resize(base + 12, 0.0);
+            for (size_t k = 0; k < camera.NumParams() && k < 12; ++k)
+              params[base + k] = camera.ParamsData()[k];
+          }
+          image_camera.push_back(ct->second);
+        }
+        const auto& line = rec->Image(el.image_id).Lines()[el.line_idx];
+        obs_image.push_back(it->second);
+        for (int k = 0; k < 3; ++k) lines.push_back(line.Line().data()[k]);
+        aligned.push_back(line.IsAligned() ? 1 : 0);
+        obs_ref.emplace_back(el.image_id, el.line_idx);
+      }
+      track_start.push_back((int64_t)obs_image.size());
+    }
+  }
+  ppsfm_filter_problem Problem() const {
+    ppsfm_filter_problem pb{};
+    pb.num_images = (int32_t)image_ids.size();
+    pb.qvecs = qvecs.data();
+    pb.tvecs = tvecs.data();
+    pb.image_camera = image_camera.data();
+    pb.num_cameras = (int32_t)model.size();
+    pb.camera_model = model.data();
+    pb.camera_params = params.data();
+    pb.camera_width = width.data();
+    pb.camera_height = height.data();
+    pb.num_points = (int32_t)point_ids.size();
+    pb.points = points.data();
+    pb.track_start = track_start.data();
+    pb.num_obs = (int64_t)obs_image.size();
+    pb.obs_image = obs_image.data();
+    pb.obs_line = lines.data();
+    pb.obs_aligned = aligned.data();
+    return pb;
+  }
+  // applies the masks: whole points first, then single observations of the survivors
+  void Apply(ReconstructionT* rec, const std::vector<uint8_t>& obs_deleted,
+             const std::vector<uint8_t>& point_deleted, const double* point_error) const {
+    for (size_t p = 0; p < point_ids.size(); ++p) {
+      if (point_deleted[p]) {
+        rec->DeletePoint3D(point_ids[p]);
+        continue;
+      }
+      for (int64_t k = track_start[p]; k < track_start[p + 1]; ++k)
+        if (obs_deleted[k]) rec->DeleteObservation(obs_ref[k].first, obs_ref[k].second);
+      if (point_error) rec->Point3D(point_ids[p]).SetError(point_error[p]);
+    }
+  }
+};
+}  // namespace internal
+
+template <class ReconstructionT, class IdContainer>
+inline size_t FilterPoints3D(ReconstructionT* rec, double max_reproj_error, double min_tri_angle,
+                             const IdContainer& point3D_ids) {
+  const std::vector<point3D_t> ids(point3D_ids.begin(), point3D_ids.end());
+  internal::TrackProblem<ReconstructionT> tp(rec, ids);
+  const size_t P = tp.point_ids.size(), O = tp.obs_image.size();
+  if (P == 0) return 0;
+  std::vector<uint8_t> od(O ? O : 1), pd(P);
+  std::vector<double> err(P, -1.0);
+  size_t num_filtered = 0;
+  const ppsfm_filter_problem pb = tp.Problem();
+  internal::CheckRc(ppsfm_filter_points3d(ThreadContext(), &pb, max_reproj_error, min_tri_angle,
+                                          od.data(), pd.data(), err.data(), &num_filtered));
+  tp.Apply(rec, od, pd, err.data());
+  return num_filtered;
+}
+
+// `point3D_ids`: every point of the reconstruction (the reference walks the registered images;
+// the set of observations visited is the same)
+template <class ReconstructionT, class IdContainer>
+inline size_t FilterObservationsWithNegativeDepth(ReconstructionT* rec,
+                                                  const IdContainer& point3D_ids) {
+  const std::vector<point3D_t> ids(point3D_ids.begin(), point3D_ids.end());
+  internal::TrackProblem<ReconstructionT> tp(rec, ids);
+  const size_t P = tp.point_ids.size(), O = tp.obs_image.size();
+  if (P == 0) return 0;
+  std::vector<uint8_t> od(O ? O : 1), pd(P);
+  size_t num_filtered = 0;
+  const ppsfm_filter_problem pb = tp.Problem();
+  internal::CheckRc(ppsfm_filter_observations_with_negative_depth(
+      ThreadContext(), &pb, od.data(), pd.data(), &num_filtered));
+  tp.Apply(rec, od, pd, nullptr);
+  return num_filtered;
 }
 
 // ---- src/optim/bundle_adjustment.h:49-100 --------------------------------------------------------------

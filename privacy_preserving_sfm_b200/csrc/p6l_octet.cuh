@@ -83,6 +83,7 @@ __device__ inline bool hqr8_reduce_octet(const Octet& o) {
         }
         const unsigned bits = (__ballot_sync(o.mask, small) & o.mask) >> oct_shift;
         il = bits ? 31 - __clz((int)bits) : 0;
+        o.sync();  // the search's reads are ordered before the writes of the branch taken below
       }
       if (il == iu) {
         if (sub == 0) {
@@ -134,6 +135,7 @@ __device__ inline bool hqr8_reduce_octet(const Octet& o) {
           a11 = s * r10 + c * r11;
           a10 = 0.0;
         }
+        o.sync();  // every lane has read the block
         if (sub == 0) {
           o.at(iu - 1, iu - 1) = a00;
           o.at(iu - 1, iu) = a01;

@@ -884,6 +884,32 @@ void ppsfm_corr_free(ppsfm_ctx* ctx, ppsfm_corr* corr) {
   FreeCorr(corr);
 }
 
+int ppsfm_image_to_world_threshold(int camera_model, const double* camera_params, double threshold,
+                                   double* out) {
+  if (!camera_params || !out) return PPSFM_ERR_INVALID;
+  // focal_length_idxs of src/base/camera_models.h:263-420
+  double mean_focal_length = 0;
+  switch (camera_model) {
+    case 0: case 2: case 3:  // SIMPLE_PINHOLE, SIMPLE_RADIAL, RADIAL: {0}
+      mean_focal_length += camera_params[0];
+      mean_focal_length /= 1;
+      break;
+    case 1: case 4:          // PINHOLE, OPENCV: {0, 1}
+      mean_focal_length += camera_params[0];
+      mean_focal_length += camera_params[1];
+      mean_focal_length /= 2;
+      break;
+    default:
+      return PPSFM_ERR_INVALID;
+  }
+  *out = threshold / mean_focal_length;
+  return PPSFM_OK;
+}
+
+void ppsfm_rotation_matrix_to_quaternion(const double* R, double* qvec) {
+  RotationMatrixToQuaternion(R, qvec);
+}
+
 int ppsfm_ransac_p6l_resident(ppsfm_ctx* ctx, const ppsfm_corr* corr,
                               const ppsfm_ransac_options* options, ppsfm_ransac_report* report,
                               uint8_t* inlier_mask) {

@@ -84,3 +84,99 @@ def test_adaptor_bundle_adjuster_matches_oracle(oracle, tmp_path):
     assert int(iters) == s2.num_successful_steps + s2.num_unsuccessful_steps
     assert np.abs(q - b.qvecs).max() < 1e-8 and np.abs(t - b.tvecs).max() < 1e-8
     assert np.abs(X - b.points).max() < 1e-7
+
+
+def _scene_file(tmp_path, sc, aligned=None):
+    fin = str(tmp_path / "scene.bin")
+    with open(fin, "wb") as f:
+        np.array([sc["num_cams"], sc["num_points"], len(sc["obs_cam"])], dtype=np.int64).tofile(f)
+        for a in (sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"].astype(np.float64),
+                  sc["obs_pt"].astype(np.float64), sc["obs_line"], sc["cam_params"]):
+            np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+        if aligned is not None:
+            np.ascontiguousarray(aligned, dtype=np.float64).tofile(f)
+    return fin
+
+
+def _filter_scene(seed):
+    """Point-major scene with corrupted lines, far / behind points and all-aligned tracks."""
+    from privacy_preserving_sfm_b200 import filters as F
+    sc = S.make_ba_scene(num_cams=10, num_points=300, obs_per_point=6, seed=seed)
+    rng = np.random.default_rng(seed + 1)
+    O = len(sc["obs_cam"])
+    sc["qvecs"], sc["tvecs"] = sc["qvecs_gt"], sc["tvecs_gt"]
+    pts = sc["points_gt"].copy()
+    line = sc["obs_line"].copy()
+    bad = rng.uniform(size=O) < 0.12
+    line[bad, 2] += rng.normal(scale=0.02, size=bad.sum())
+    pts[rng.choice(300, 12, replace=False)] *= 400.0
+    pts[rng.choice(300, 30, replace=False)] += 30.0 * np.array([0.0, 0.0, 1.0])
+    aligned = (rng.uniform(size=O) < 0.4).astype(np.uint8)
+    track_start = np.searchsorted(sc["obs_pt"], np.arange(301)).astype(np.int64)
+    for p in rng.choice(300, 8, replace=False):
+        aligned[track_start[p]:track_start[p + 1]] = 1
+    sc["points"], sc["obs_line"] = pts, line
+    pb = F.FilterProblem(sc["qvecs"], sc["tvecs"], np.zeros(10, np.int32), [1],
+                         [list(sc["cam_params"])], [(1000, 1000)], pts, track_start,
+                         sc["obs_cam"], line, aligned)
+    return sc, aligned, pb
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["filter", "depth"])
+def test_adaptor_filters_match_oracle(oracle, tmp_path, mode):
+    """ppsfm::FilterPoints3D / FilterObservationsWithNegativeDepth applied to a Reconstruction-like
+    object through DeleteObservation / DeletePoint3D / SetError end in the state the oracle's
+    masks describe."""
+    exe = _build()
+    sc, aligned, pb = _filter_scene(41)
+    fin, fout = _scene_file(tmp_path, sc, aligned), str(tmp_path / "out.bin")
+    subprocess.check_call([exe, mode, fin, fout])
+    out = np.fromfile(fout, dtype=np.float64)
+    P, O = 300, len(sc["obs_cam"])
+    nf, thr = out[0], out[1]
+    alive, err = out[2:2 + 2 * P:2], out[3:3 + 2 * P:2]
+    attached = out[2 + 2 * P:]
+    assert thr == 12.0 / 1000.0                       # ImageToWorldThreshold, PINHOLE f = 1000
+    if mode == "filter":
+        nf2, od2, pd2, pe2, _ = oracle.filter_points3d(pb, 4.0, 1.5)
+        assert np.array_equal(err[alive > 0], pe2[pd2 == 0])
+    else:
+        nf2, od2, pd2 = oracle.filter_negative_depth(pb)
+    assert int(nf) == nf2 and 0 < nf2
+    assert np.array_equal(alive > 0, pd2 == 0) and 0 < (pd2 == 0).sum() < P
+    assert np.array_equal(attached > 0, od2 == 0)
+
+
+@pytest.mark.gpu
+def test_adaptor_triangulation_matches_oracle(oracle, tmp_path, ctx):
+    """ppsfm::EstimateTriangulationBatch / EstimateTriangulation (projection matrices in, the
+    reference's signature) against the oracle's EstimateTriangulation on the same tracks."""
+    from privacy_preserving_sfm_b200 import filters as F, triangulation as T
+    exe = _build()
+    sc = S.make_ba_scene(num_cams=9, num_points=150, obs_per_point=6, seed=52)
+    sc["qvecs"], sc["tvecs"] = sc["qvecs_gt"], sc["tvecs_gt"]
+    rng = np.random.default_rng(3)
+    bad = rng.uniform(size=len(sc["obs_cam"])) < 0.1
+    sc["obs_line"] = sc["obs_line"].copy()
+    sc["obs_line"][bad, 2] += rng.normal(scale=0.05, size=bad.sum())
+    fin, fout = _scene_file(tmp_path, sc), str(tmp_path / "out.bin")
+    subprocess.check_call([exe, "tri", fin, fout])
+    out = np.fromfile(fout, dtype=np.float64)
+    assert out[1] == 1.0                              # per-track call == batch on track 0
+    P, O = 150, len(sc["obs_cam"])
+    ok, xyz = out[2:2 + 4 * P].reshape(P, 4)[:, 0] > 0, out[2:2 + 4 * P].reshape(P, 4)[:, 1:]
+    mask = out[2 + 4 * P:] > 0
+    track_start = np.searchsorted(sc["obs_pt"], np.arange(P + 1)).astype(np.int64)
+    pb = F.FilterProblem(sc["qvecs"], sc["tvecs"], np.zeros(9, np.int32), [1],
+                         [list(sc["cam_params"])], [(1000, 1000)], sc["points_gt"], track_start,
+                         sc["obs_cam"], sc["obs_line"], np.zeros(O, np.uint8))
+    opt = T.EstimateTriangulationOptions(
+        min_tri_angle=np.deg2rad(1.5), residual_type=T.ANGULAR_ERROR, max_error=np.deg2rad(2.0),
+        confidence=0.9999, min_inlier_ratio=0.02, max_num_trials=10000, exhaustive_threshold=15)
+    ok2, xyz2, mask2, _ = oracle.estimate_triangulation_batch(pb, opt)
+    assert np.array_equal(ok, ok2) and ok.sum() > 100
+    assert np.array_equal(mask[np.repeat(ok, 6)], mask2[np.repeat(ok, 6)])
+    # (rotation matrix -> quaternion -> rotation matrix on the way in: 1e-8, not bits)
+    assert np.abs(xyz[ok] - xyz2[ok]).max() < 1e-8 * max(1.0, np.abs(xyz2[ok]).max())
+    assert np.abs(xyz[ok] - sc["points_gt"][ok]).max() < 0.05
