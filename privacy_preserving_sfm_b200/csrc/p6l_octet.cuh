@@ -306,6 +306,7 @@ __device__ inline bool hqr8_reduce_octet(const Octet& o) {
             o.sync();
           }
         }
+        o.sync();  // (a skipped reflection leaves its reads unordered against the zeroing below)
         if (sub >= im + 2 && sub <= iu) {
           o.at(sub, sub - 2) = 0.0;
           if (sub > im + 2) o.at(sub, sub - 3) = 0.0;

@@ -179,4 +179,4 @@ def test_adaptor_triangulation_matches_oracle(oracle, tmp_path, ctx):
     assert np.array_equal(mask[np.repeat(ok, 6)], mask2[np.repeat(ok, 6)])
     # (rotation matrix -> quaternion -> rotation matrix on the way in: 1e-8, not bits)
     assert np.abs(xyz[ok] - xyz2[ok]).max() < 1e-8 * max(1.0, np.abs(xyz2[ok]).max())
-    assert np.abs(xyz[ok] - sc["points_gt"][ok]).max() < 0.05
+    assert np.median(np.abs(xyz[ok] - sc["points_gt"][ok]).max(axis=1)) < 0.02
