@@ -245,7 +245,7 @@ class BaProblem(C.Structure):
                 ("image_camera", _i32p), ("num_cameras", C.c_int32), ("camera_model", _i32p),
                 ("camera_params", _dp), ("num_points", C.c_int32), ("points", _dp),
                 ("point_const", _u8p), ("num_obs", C.c_int64), ("obs_image", _i32p),
-                ("obs_point", _i32p), ("obs_line", _dp)]
+                ("obs_point", _i32p), ("obs_line", _dp), ("camera_const", _u8p)]
 
 
 class BaOptions(C.Structure):
@@ -257,7 +257,8 @@ class BaOptions(C.Structure):
                 ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
                 ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
-                ("num_threads", C.c_int32)]
+                ("num_threads", C.c_int32), ("refine_focal_length", C.c_int32),
+                ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32)]
 
 
 class BaSummary(C.Structure):
@@ -310,7 +311,7 @@ class BaArrays:
 
     def __init__(self, qvecs, tvecs, points, obs_image, obs_point, obs_line, camera_model,
                  camera_params, image_camera=None, pose_flags=None, point_const=None,
-                 struct_cls=None):
+                 struct_cls=None, camera_const=None):
         self.qvecs = np.ascontiguousarray(qvecs, dtype=np.float64).copy()
         self.tvecs = np.ascontiguousarray(tvecs, dtype=np.float64).copy()
         self.points = np.ascontiguousarray(points, dtype=np.float64).copy()
@@ -328,6 +329,9 @@ class BaArrays:
             pose_flags if pose_flags is not None else np.zeros(ni), dtype=np.uint8)
         self.point_const = np.ascontiguousarray(
             point_const if point_const is not None else np.zeros(npnt), dtype=np.uint8)
+        self.camera_const = np.ascontiguousarray(
+            camera_const if camera_const is not None else np.zeros(self.camera_model.shape[0]),
+            dtype=np.uint8)
         cls = struct_cls or BaProblem
         p = cls()
         p.num_images = ni
@@ -345,6 +349,8 @@ class BaArrays:
         p.obs_image = self.obs_image.ctypes.data_as(_i32p)
         p.obs_point = self.obs_point.ctypes.data_as(_i32p)
         p.obs_line = self.obs_line.ctypes.data_as(_dp)
+        if hasattr(p, "camera_const"):
+            p.camera_const = self.camera_const.ctypes.data_as(_u8p)
         self.struct = p
 
 

@@ -18,6 +18,7 @@
 #include <limits>
 #include <mutex>
 #include <thread>
+#include <type_traits>
 #include <vector>
 
 namespace {
@@ -68,47 +69,52 @@ void UnitQuaternionRotatePoint(const T q[4], const T pt[3], T result[3]) {
   result[2] = two * ((t7 - t3) * pt[0] + (t2 + t9) * pt[1] + (t5 + t8) * pt[2]) + pt[2];
 }
 
-// CameraModel::WorldToImage<T> (src/base/camera_models.h); intrinsics are constants here
-// (refine_focal_length / principal_point / extra_params default to false,
-//  src/optim/bundle_adjustment.h:57-63).
-template <typename T>
-bool WorldToImage(int model, const double* p, const T u, const T v, T* x, T* y) {
+// CameraModel::WorldToImage<T> (src/base/camera_models.h).  The intrinsics `p` are either plain
+// doubles (constant camera: refine_* = false, the defaults of src/optim/bundle_adjustment.h:57-63)
+// or jets like everything else (camera_params is the fourth parameter block of the functor,
+// cost_functions.h:56-58).
+template <typename T> inline T AsT(const T& x) { return x; }
+template <typename T, typename = typename std::enable_if<!std::is_same<T, double>::value>::type>
+inline T AsT(double x) { return Lift<T>::C(x); }
+template <typename T, typename PT>
+bool WorldToImage(int model, const PT* p, const T u, const T v, T* x, T* y) {
+  auto P = [&](int k) { return AsT<T>(p[k]); };
   auto C = [](double c) { return Lift<T>::C(c); };
   switch (model) {
     case 0: {  // SIMPLE_PINHOLE f, cx, cy                      (:615-627)
-      *x = C(p[0]) * u + C(p[1]);
-      *y = C(p[0]) * v + C(p[2]);
+      *x = P(0) * u + P(1);
+      *y = P(0) * v + P(2);
       return true;
     }
     case 1: {  // PINHOLE fx, fy, cx, cy                        (:664-676)
-      *x = C(p[0]) * u + C(p[2]);
-      *y = C(p[1]) * v + C(p[3]);
+      *x = P(0) * u + P(2);
+      *y = P(1) * v + P(3);
       return true;
     }
     case 2: {  // SIMPLE_RADIAL f, cx, cy, k                    (:715-757)
       const T u2 = u * u, v2 = v * v, r2 = u2 + v2;
-      const T radial = C(p[3]) * r2;
+      const T radial = P(3) * r2;
       const T xx = u + u * radial, yy = v + v * radial;
-      *x = C(p[0]) * xx + C(p[1]);
-      *y = C(p[0]) * yy + C(p[2]);
+      *x = P(0) * xx + P(1);
+      *y = P(0) * yy + P(2);
       return true;
     }
     case 3: {  // RADIAL f, cx, cy, k1, k2                      (:784-829)
       const T u2 = u * u, v2 = v * v, r2 = u2 + v2;
-      const T radial = C(p[3]) * r2 + C(p[4]) * r2 * r2;
+      const T radial = P(3) * r2 + P(4) * r2 * r2;
       const T xx = u + u * radial, yy = v + v * radial;
-      *x = C(p[0]) * xx + C(p[1]);
-      *y = C(p[0]) * yy + C(p[2]);
+      *x = P(0) * xx + P(1);
+      *y = P(0) * yy + P(2);
       return true;
     }
     case 4: {  // OPENCV fx, fy, cx, cy, k1, k2, p1, p2          (:854-904)
       const T u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2;
-      const T radial = C(p[4]) * r2 + C(p[5]) * r2 * r2;
-      const T du = u * radial + C(2.0) * C(p[6]) * uv + C(p[7]) * (r2 + C(2.0) * u2);
-      const T dv = v * radial + C(2.0) * C(p[7]) * uv + C(p[6]) * (r2 + C(2.0) * v2);
+      const T radial = P(4) * r2 + P(5) * r2 * r2;
+      const T du = u * radial + C(2.0) * P(6) * uv + P(7) * (r2 + C(2.0) * u2);
+      const T dv = v * radial + C(2.0) * P(7) * uv + P(6) * (r2 + C(2.0) * v2);
       const T xx = u + du, yy = v + dv;
-      *x = C(p[0]) * xx + C(p[2]);
-      *y = C(p[1]) * yy + C(p[3]);
+      *x = P(0) * xx + P(2);
+      *y = P(1) * yy + P(3);
       return true;
     }
   }
@@ -116,8 +122,8 @@ bool WorldToImage(int model, const double* p, const T u, const T v, T* x, T* y) 
 }
 
 // BundleAdjustmentLineCostFunction::operator() (src/base/cost_functions.h:62-100).
-template <typename T>
-bool LineCost(int model, const double* cam, const double* line, const T* qvec, const T* tvec,
+template <typename T, typename PT>
+bool LineCost(int model, const PT* cam, const double* line, const T* qvec, const T* tvec,
               const T* point3D, T* residuals) {
   T projection[3];
   UnitQuaternionRotatePoint(qvec, point3D, projection);
@@ -159,6 +165,30 @@ void LineCostAutoDiff(int model, const double* cam, const double* line, const do
   }
 }
 
+// AutoDiff of the block (2; 4, 3, 3, kNumParams): additionally the 2 x 8 Jacobian with respect to
+// camera_params (columns >= NumParams stay zero).
+constexpr int kIntrWidth = 8;  // widest supported model (OPENCV)
+const int kNumParams[5] = {3, 4, 4, 5, 8};
+void LineCostAutoDiffIntr(int model, const double* cam, const double* line, const double* q,
+                          const double* t, const double* X, double* r, double* Jq, double* Jt,
+                          double* JX, double* Jcam) {
+  typedef Jet<10 + kIntrWidth> J;
+  J jq[4], jt[3], jX[3], jc[kIntrWidth], res[2];
+  for (int i = 0; i < 4; ++i) jq[i] = J(q[i], i);
+  for (int i = 0; i < 3; ++i) jt[i] = J(t[i], 4 + i);
+  for (int i = 0; i < 3; ++i) jX[i] = J(X[i], 7 + i);
+  for (int i = 0; i < kIntrWidth; ++i)
+    jc[i] = i < kNumParams[model] ? J(cam[i], 10 + i) : J(0.0);
+  LineCost<J, J>(model, jc, line, jq, jt, jX, res);
+  for (int k = 0; k < 2; ++k) {
+    r[k] = res[k].a;
+    for (int i = 0; i < 4; ++i) Jq[4 * k + i] = res[k].v[i];
+    for (int i = 0; i < 3; ++i) Jt[3 * k + i] = res[k].v[4 + i];
+    for (int i = 0; i < 3; ++i) JX[3 * k + i] = res[k].v[7 + i];
+    for (int i = 0; i < kIntrWidth; ++i) Jcam[kIntrWidth * k + i] = res[k].v[10 + i];
+  }
+}
+
 // ceres::QuaternionParameterization::ComputeJacobian (4x3, row-major)
 void QuaternionPlusJacobian(const double* x, double* j) {
   j[0] = -x[1]; j[1] = -x[2]; j[2] = -x[3];
@@ -185,9 +215,11 @@ void QuaternionPlus(const double* x, const double* delta, double* out) {
 }
 
 void LineCostTangent(int model, const double* cam, const double* line, const double* q,
-                     const double* t, const double* X, double* r, double* Jc, double* JX) {
+                     const double* t, const double* X, double* r, double* Jc, double* JX,
+                     double* Jcam = nullptr) {
   double Jq[8], Jt[6], pj[12];
-  LineCostAutoDiff(model, cam, line, q, t, X, r, Jq, Jt, JX);
+  if (Jcam) LineCostAutoDiffIntr(model, cam, line, q, t, X, r, Jq, Jt, JX, Jcam);
+  else LineCostAutoDiff(model, cam, line, q, t, X, r, Jq, Jt, JX);
   QuaternionPlusJacobian(q, pj);
   for (int k = 0; k < 2; ++k) {
     for (int c = 0; c < 3; ++c) {
@@ -350,6 +382,14 @@ struct Solver {
   std::vector<double> r, Jc, Jp;          // 2, 12, 6 per obs
   std::vector<double> cam_scale, pt_scale;  // 6 per block, 3 per point
   int threads;
+  // intrinsics (ParameterizeCameras, bundle_adjustment.cc:490-528): cameras with at least one
+  // variable parameter get a reduced block of kIntrWidth columns after the pose blocks
+  std::vector<double> params;             // current Camera::Params(), 12 per camera
+  std::vector<int> intr_block;            // camera -> block index or -1 (constant intrinsics)
+  std::vector<uint8_t> intr_mask;         // per camera: bit k = parameter k is variable
+  int nintr = 0;
+  std::vector<double> Ji;                 // 2 x kIntrWidth per obs (only if nintr > 0)
+  std::vector<double> intr_scale;         // kIntrWidth per intrinsics block
 
   Solver(const orc_ba_problem& p, const orc_ba_options& o) : pb(p), opt(o) {
     C = p.num_images; P = p.num_points; O = p.num_obs;
@@ -363,13 +403,32 @@ struct Solver {
     cam_mask.assign(C, 0);
     pt_var.assign(P, 1);
     if (p.point_const) for (int i = 0; i < P; ++i) pt_var[i] = p.point_const[i] ? 0 : 1;
+    // ParameterizeCameras: constant unless a refine_* flag is set and the camera is not in
+    // config.ConstantCameras(); the groups that are not refined stay constant
+    // (SubsetParameterization).  Parameter groups per model: camera_models.h:597-846.
+    params.assign(p.camera_params, p.camera_params + 12 * (size_t)p.num_cameras);
+    intr_block.assign(p.num_cameras, -1);
+    intr_mask.assign(p.num_cameras, 0);
+    std::vector<uint8_t> intr_candidate(p.num_cameras, 0);
+    for (int c = 0; c < p.num_cameras; ++c) {
+      static const uint8_t kFocal[5] = {0x01, 0x03, 0x01, 0x01, 0x03};
+      static const uint8_t kPP[5] = {0x06, 0x0c, 0x06, 0x06, 0x0c};
+      static const uint8_t kExtra[5] = {0x00, 0x00, 0x08, 0x18, 0xf0};
+      const int m = p.camera_model[c];
+      uint8_t mask = 0;
+      if (o.refine_focal_length) mask |= kFocal[m];
+      if (o.refine_principal_point) mask |= kPP[m];
+      if (o.refine_extra_params) mask |= kExtra[m];
+      if (p.camera_const && p.camera_const[c]) mask = 0;
+      intr_candidate[c] = mask;
+    }
     // keep observations that touch at least one variable block (Ceres drops the rest)
     std::vector<int64_t> cnt(P + 1, 0);
     std::vector<uint8_t> cam_used(C, 0);
     for (int64_t o2 = 0; o2 < O; ++o2) {
       const int ci = p.obs_image[o2], pi = p.obs_point[o2];
       const bool cam_const = p.pose_flags && (p.pose_flags[ci] & 1);
-      if (cam_const && !pt_var[pi]) continue;
+      if (cam_const && !pt_var[pi] && !intr_candidate[p.image_camera[ci]]) continue;
       cnt[pi + 1]++;
       cam_used[ci] = 1;
     }
@@ -380,8 +439,15 @@ struct Solver {
     for (int64_t o2 = 0; o2 < O; ++o2) {
       const int ci = p.obs_image[o2], pi = p.obs_point[o2];
       const bool cam_const = p.pose_flags && (p.pose_flags[ci] & 1);
-      if (cam_const && !pt_var[pi]) continue;
+      if (cam_const && !pt_var[pi] && !intr_candidate[p.image_camera[ci]]) continue;
       obs[fill[pi]++] = o2;
+    }
+    for (int i = 0; i < C; ++i) {  // cameras of images that are part of the problem
+      const int c = p.image_camera[i];
+      if (cam_used[i] && intr_candidate[c] && intr_block[c] < 0) {
+        intr_block[c] = nintr++;
+        intr_mask[c] = intr_candidate[c];
+      }
     }
     for (int i = 0; i < C; ++i) {
       const uint8_t f = p.pose_flags ? p.pose_flags[i] : 0;
@@ -400,18 +466,24 @@ struct Solver {
     for (int i = 0; i < P; ++i) if (pt_start[i + 1] == pt_start[i]) pt_var[i] = 0;
     const size_t K = obs.size();
     r.resize(2 * K); Jc.resize(12 * K); Jp.resize(6 * K);
+    if (nintr > 0) Ji.assign(2 * kIntrWidth * K, 0.0);
+    intr_scale.assign(kIntrWidth * (size_t)nintr, 1.0);
     cam_scale.assign(6 * (size_t)nblocks, 1.0);
     pt_scale.assign(3 * (size_t)P, 1.0);
   }
 
-  const double* CamParams(int img) const {
-    return pb.camera_params + 12 * (size_t)pb.image_camera[img];
+  const double* CamParams(int img, const std::vector<double>& prm) const {
+    return prm.data() + 12 * (size_t)pb.image_camera[img];
   }
   int CamModel(int img) const { return pb.camera_model[pb.image_camera[img]]; }
 
   // residuals (+ Jacobians) at (q_, t_, X_); returns cost = 0.5 sum rho(s)
   double Evaluate(const std::vector<double>& q_, const std::vector<double>& t_,
                   const std::vector<double>& X_, bool jac) {
+    return Evaluate(q_, t_, X_, params, jac);
+  }
+  double Evaluate(const std::vector<double>& q_, const std::vector<double>& t_,
+                  const std::vector<double>& X_, const std::vector<double>& prm, bool jac) {
     std::vector<double> partial(threads, 0.0);
     ParallelFor(threads, P, [&](int tid, int64_t lo, int64_t hi) {
       double cost = 0.0;
@@ -419,35 +491,45 @@ struct Solver {
         for (int64_t k = pt_start[pi]; k < pt_start[pi + 1]; ++k) {
           const int64_t o2 = obs[k];
           const int ci = pb.obs_image[o2];
-          double rr[2], jc[12], jp[6];
+          double rr[2], jc[12], jp[6], ji[2 * kIntrWidth];
+          const int ib = intr_block[pb.image_camera[ci]];
           if (jac) {
-            LineCostTangent(CamModel(ci), CamParams(ci), pb.obs_line + 3 * o2, &q_[4 * ci],
-                            &t_[3 * ci], &X_[3 * pi], rr, jc, jp);
+            LineCostTangent(CamModel(ci), CamParams(ci, prm), pb.obs_line + 3 * o2, &q_[4 * ci],
+                            &t_[3 * ci], &X_[3 * pi], rr, jc, jp, ib >= 0 ? ji : nullptr);
           } else {
-            LineCost<double>(CamModel(ci), CamParams(ci), pb.obs_line + 3 * o2, &q_[4 * ci],
-                             &t_[3 * ci], &X_[3 * pi], rr);
+            LineCost<double, double>(CamModel(ci), CamParams(ci, prm), pb.obs_line + 3 * o2,
+                                     &q_[4 * ci], &t_[3 * ci], &X_[3 * pi], rr);
           }
           const double s = rr[0] * rr[0] + rr[1] * rr[1];
           double rho[3];
           EvaluateLoss(opt.loss_type, opt.loss_scale, s, rho);
           cost += 0.5 * rho[0];
           if (!jac) continue;
-          // corrector on the block [jc | jp] (2 x 9)
-          double blk[18];
+          // corrector on the block [jc | jp | ji] (2 x 17; ji = 0 for a constant camera)
+          constexpr int kW = 9 + kIntrWidth;
+          double blk[2 * kW];
           for (int row = 0; row < 2; ++row) {
-            for (int c = 0; c < 6; ++c) blk[9 * row + c] = jc[6 * row + c];
-            for (int c = 0; c < 3; ++c) blk[9 * row + 6 + c] = jp[3 * row + c];
+            for (int c = 0; c < 6; ++c) blk[kW * row + c] = jc[6 * row + c];
+            for (int c = 0; c < 3; ++c) blk[kW * row + 6 + c] = jp[3 * row + c];
+            for (int c = 0; c < kIntrWidth; ++c)
+              blk[kW * row + 9 + c] = ib >= 0 ? ji[kIntrWidth * row + c] : 0.0;
           }
-          ApplyCorrector(s, rho, rr, blk, 9);
+          ApplyCorrector(s, rho, rr, blk, kW);
           const int b = cam_block[ci];
           for (int row = 0; row < 2; ++row) {
             for (int c = 0; c < 6; ++c) {
               const bool on = b >= 0 && ((cam_mask[ci] >> c) & 1);
-              Jc[12 * k + 6 * row + c] = on ? blk[9 * row + c] * cam_scale[6 * b + c] : 0.0;
+              Jc[12 * k + 6 * row + c] = on ? blk[kW * row + c] * cam_scale[6 * b + c] : 0.0;
             }
             for (int c = 0; c < 3; ++c)
               Jp[6 * k + 3 * row + c] =
-                  pt_var[pi] ? blk[9 * row + 6 + c] * pt_scale[3 * pi + c] : 0.0;
+                  pt_var[pi] ? blk[kW * row + 6 + c] * pt_scale[3 * pi + c] : 0.0;
+            if (ib >= 0)
+              for (int c = 0; c < kIntrWidth; ++c) {
+                const bool on = (intr_mask[pb.image_camera[ci]] >> c) & 1;
+                Ji[2 * kIntrWidth * k + kIntrWidth * row + c] =
+                    on ? blk[kW * row + 9 + c] * intr_scale[kIntrWidth * ib + c] : 0.0;
+              }
           }
           r[2 * k] = rr[0];
           r[2 * k + 1] = rr[1];
@@ -461,8 +543,30 @@ struct Solver {
   }
 
   // diag(J^T J) per camera block (6) and per point (3), and gradient J^T r
+  // intrinsics part of J^T J and J^T r (only with nintr > 0): Uii 8x8 per intrinsics block,
+  // Uic 8x6 per pose block (coupling with the block of the image's own camera), gi
+  std::vector<double> Uii, Uic, gi;
   void Normal(std::vector<double>& U, std::vector<double>& gc, std::vector<double>& V,
               std::vector<double>& gp) {
+    if (nintr > 0) {
+      constexpr int W = kIntrWidth;
+      Uii.assign(W * W * (size_t)nintr, 0.0);
+      Uic.assign(W * 6 * (size_t)nblocks, 0.0);
+      gi.assign(W * (size_t)nintr, 0.0);
+      for (size_t k = 0; k < obs.size(); ++k) {
+        const int img = pb.obs_image[obs[k]];
+        const int ib = intr_block[pb.image_camera[img]], b = cam_block[img];
+        if (ib < 0) continue;
+        const double* ji = &Ji[2 * W * k];
+        const double* jc = &Jc[12 * k];
+        for (int a = 0; a < W; ++a) {
+          for (int c = 0; c < W; ++c) Uii[W * W * (size_t)ib + W * a + c] += ji[a] * ji[c] + ji[W + a] * ji[W + c];
+          gi[W * (size_t)ib + a] += ji[a] * r[2 * k] + ji[W + a] * r[2 * k + 1];
+          if (b >= 0)
+            for (int c = 0; c < 6; ++c) Uic[W * 6 * (size_t)b + 6 * a + c] += ji[a] * jc[c] + ji[W + a] * jc[6 + c];
+        }
+      }
+    }
     U.assign(36 * (size_t)nblocks, 0.0);
     gc.assign(6 * (size_t)nblocks, 0.0);
     V.assign(9 * (size_t)P, 0.0);
@@ -497,10 +601,14 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
   sum->num_residuals = 2 * pb.num_obs;
   sum->num_residuals_reduced = 2 * (int64_t)S.obs.size();
   if (pb.num_obs == 0) return 0;  // bundle_adjustment.cc:269-271
-  const int nb = S.nblocks, n = 6 * nb, P = S.P;
+  constexpr int IW = kIntrWidth;
+  const int nb = S.nblocks, ni = S.nintr, n = 6 * nb + IW * ni, P = S.P;
+  const int ioff = 6 * nb;  // first reduced index of the intrinsics blocks
   int eff = 0;
   for (int i = 0; i < S.C; ++i) eff += __builtin_popcount(S.cam_mask[i]);
   for (int i = 0; i < P; ++i) eff += S.pt_var[i] ? 3 : 0;
+  for (int c = 0; c < pb.num_cameras; ++c)
+    if (S.intr_block[c] >= 0) eff += __builtin_popcount(S.intr_mask[c]);
   sum->num_effective_parameters_reduced = eff;
 
   auto secs = [](std::chrono::steady_clock::time_point a) {
@@ -510,6 +618,7 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
     std::memcpy(pb.qvecs, S.q.data(), sizeof(double) * S.q.size());
     std::memcpy(pb.tvecs, S.t.data(), sizeof(double) * S.t.size());
     std::memcpy(pb.points, S.X.data(), sizeof(double) * S.X.size());
+    if (ni > 0) std::memcpy(pb.camera_params, S.params.data(), sizeof(double) * S.params.size());
   };
   if (S.obs.empty() || eff == 0) {
     sum->termination_type = 0;
@@ -529,6 +638,9 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
     for (int p = 0; p < P; ++p)
       for (int a = 0; a < 3; ++a)
         S.pt_scale[3 * p + a] = 1.0 / (1.0 + std::sqrt(V[9 * (size_t)p + 4 * a]));
+    for (int ib = 0; ib < ni; ++ib)
+      for (int a = 0; a < IW; ++a)
+        S.intr_scale[IW * ib + a] = 1.0 / (1.0 + std::sqrt(S.Uii[IW * IW * (size_t)ib + (IW + 1) * a]));
     cost = S.Evaluate(S.q, S.t, S.X, true);
     S.Normal(U, gc, V, gp);
   }
@@ -551,6 +663,8 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
     }
     for (int p = 0; p < P; ++p)
       for (int a = 0; a < 3; ++a) m = std::max(m, std::fabs(gp[3 * p + a] / S.pt_scale[3 * p + a]));
+    for (int ib = 0; ib < ni; ++ib)  // SubsetParameterization: Plus(x, d) = x + d
+      for (int a = 0; a < IW; ++a) m = std::max(m, std::fabs(S.gi[IW * ib + a] / S.intr_scale[IW * ib + a]));
     return m;
   };
 
@@ -588,6 +702,23 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
         rhs[6 * b + a] = -gc[6 * b + a];
       }
     }
+    for (int ib = 0; ib < ni; ++ib)
+      for (int a = 0; a < IW; ++a) {
+        const int ra = ioff + IW * ib + a;
+        for (int c = 0; c < IW; ++c) Smat[(size_t)ra * n + ioff + IW * ib + c] = S.Uii[IW * IW * (size_t)ib + IW * a + c];
+        const double d = std::min(std::max(S.Uii[IW * IW * (size_t)ib + (IW + 1) * a], opt.min_lm_diagonal),
+                                  opt.max_lm_diagonal);
+        Smat[(size_t)ra * n + ra] += d / radius;
+        rhs[ra] = -S.gi[IW * ib + a];
+      }
+    if (ni > 0)
+      for (int i = 0; i < S.C; ++i) {
+        const int b = S.cam_block[i], ib = S.intr_block[pb.image_camera[i]];
+        if (b < 0 || ib < 0) continue;
+        for (int a = 0; a < IW; ++a)
+          for (int c = 0; c < 6; ++c)
+            Smat[(size_t)(ioff + IW * ib + a) * n + 6 * b + c] = S.Uic[IW * 6 * (size_t)b + 6 * a + c];
+      }
     for (int p = 0; p < P; ++p) {
       double Vd[9];
       for (int k = 0; k < 9; ++k) Vd[k] = V[9 * (size_t)p + k];
@@ -602,9 +733,10 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
     {
       const int nlocks = 256;
       std::vector<std::mutex> locks(nlocks);
+      std::mutex intr_lock;
       ParallelFor(S.threads, P, [&](int, int64_t lo, int64_t hi) {
-        std::vector<double> Wb, Zb;
-        std::vector<int> blk;
+        std::vector<double> Wb, Zb, Wi, Zi;
+        std::vector<int> blk, iblk;
         for (int64_t p = lo; p < hi; ++p) {
           if (!S.pt_var[p]) continue;
           const int64_t k0 = S.pt_start[p], k1 = S.pt_start[p + 1];
@@ -612,6 +744,11 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
           Wb.assign(18 * (size_t)m, 0.0);
           Zb.assign(18 * (size_t)m, 0.0);
           blk.assign(m, -1);
+          if (ni > 0) {
+            Wi.assign(3 * IW * (size_t)m, 0.0);
+            Zi.assign(3 * IW * (size_t)m, 0.0);
+            iblk.assign(m, -1);
+          }
           const double* vi = &Vinv[9 * (size_t)p];
           double vg[3];
           for (int a = 0; a < 3; ++a)
@@ -620,6 +757,23 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
             const int64_t k = k0 + e;
             const int b = S.cam_block[pb.obs_image[S.obs[k]]];
             blk[e] = b;
+            if (ni > 0) {
+              const int ib = S.intr_block[pb.image_camera[pb.obs_image[S.obs[k]]]];
+              iblk[e] = ib;
+              if (ib >= 0) {
+                const double* ji = &S.Ji[2 * IW * k];
+                const double* jp = &S.Jp[6 * k];
+                for (int a = 0; a < IW; ++a)
+                  for (int c = 0; c < 3; ++c) {
+                    Wi[3 * IW * (size_t)e + 3 * a + c] = ji[a] * jp[c] + ji[IW + a] * jp[3 + c];
+                  }
+                for (int a = 0; a < IW; ++a)
+                  for (int c = 0; c < 3; ++c) {
+                    const double* w = &Wi[3 * IW * (size_t)e + 3 * a];
+                    Zi[3 * IW * (size_t)e + 3 * a + c] = w[0] * vi[c] + w[1] * vi[3 + c] + w[2] * vi[6 + c];
+                  }
+              }
+            }
             if (b < 0) continue;
             const double* jc = &S.Jc[12 * k];
             const double* jp = &S.Jp[6 * k];
@@ -630,6 +784,33 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
             for (int a = 0; a < 6; ++a)
               for (int c = 0; c < 3; ++c)
                 Z[3 * a + c] = W[3 * a] * vi[c] + W[3 * a + 1] * vi[3 + c] + W[3 * a + 2] * vi[6 + c];
+          }
+          if (ni > 0) {  // rows of the intrinsics blocks: (intr, pose) and (intr, intr) products
+            std::lock_guard<std::mutex> g(intr_lock);
+            for (int e = 0; e < m; ++e) {
+              const int ie = iblk[e];
+              if (ie < 0) continue;
+              const double* Z = &Zi[3 * IW * (size_t)e];
+              const double* We = &Wi[3 * IW * (size_t)e];
+              for (int a = 0; a < IW; ++a)
+                rhs[ioff + IW * ie + a] += We[3 * a] * vg[0] + We[3 * a + 1] * vg[1] + We[3 * a + 2] * vg[2];
+              for (int f = 0; f < m; ++f) {
+                if (blk[f] >= 0) {
+                  const double* W2 = &Wb[18 * (size_t)f];
+                  for (int a = 0; a < IW; ++a)
+                    for (int c = 0; c < 6; ++c)
+                      Smat[(size_t)(ioff + IW * ie + a) * n + 6 * blk[f] + c] -=
+                          Z[3 * a] * W2[3 * c] + Z[3 * a + 1] * W2[3 * c + 1] + Z[3 * a + 2] * W2[3 * c + 2];
+                }
+                if (iblk[f] >= 0 && iblk[f] <= ie) {
+                  const double* W2 = &Wi[3 * IW * (size_t)f];
+                  for (int a = 0; a < IW; ++a)
+                    for (int c = 0; c < IW; ++c)
+                      Smat[(size_t)(ioff + IW * ie + a) * n + ioff + IW * iblk[f] + c] -=
+                          Z[3 * a] * W2[3 * c] + Z[3 * a + 1] * W2[3 * c + 1] + Z[3 * a + 2] * W2[3 * c + 2];
+                }
+              }
+            }
           }
           for (int e = 0; e < m; ++e) {
             const int bi = blk[e];
@@ -662,6 +843,15 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
           rhs[6 * b + a] = 0.0;
         }
     }
+    for (int c = 0; c < pb.num_cameras; ++c) {  // constant parameters of a variable camera
+      const int ib = S.intr_block[c];
+      if (ib < 0) continue;
+      for (int a = 0; a < IW; ++a)
+        if (!((S.intr_mask[c] >> a) & 1)) {
+          Smat[(size_t)(ioff + IW * ib + a) * n + ioff + IW * ib + a] = 1.0;
+          rhs[ioff + IW * ib + a] = 0.0;
+        }
+    }
     bool ok = n == 0 || CholeskyLower(Smat, n, S.threads);
     dc = rhs;
     if (ok && n > 0) CholeskySolve(Smat, n, dc);
@@ -672,11 +862,18 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
         double acc[3] = {gp[3 * p], gp[3 * p + 1], gp[3 * p + 2]};
         for (int64_t k = S.pt_start[p]; k < S.pt_start[p + 1]; ++k) {
           const int b = S.cam_block[pb.obs_image[S.obs[k]]];
-          if (b < 0) continue;
+          const int ib = ni > 0 ? S.intr_block[pb.image_camera[pb.obs_image[S.obs[k]]]] : -1;
+          if (b < 0 && ib < 0) continue;
           const double* jc = &S.Jc[12 * k];
           const double* jp = &S.Jp[6 * k];
           double u0 = 0, u1 = 0;
-          for (int a = 0; a < 6; ++a) { u0 += jc[a] * dc[6 * b + a]; u1 += jc[6 + a] * dc[6 * b + a]; }
+          if (b >= 0)
+            for (int a = 0; a < 6; ++a) { u0 += jc[a] * dc[6 * b + a]; u1 += jc[6 + a] * dc[6 * b + a]; }
+          if (ib >= 0)
+            for (int a = 0; a < IW; ++a) {
+              u0 += S.Ji[2 * IW * k + a] * dc[ioff + IW * ib + a];
+              u1 += S.Ji[2 * IW * k + IW + a] * dc[ioff + IW * ib + a];
+            }
           for (int c = 0; c < 3; ++c) acc[c] += jp[c] * u0 + jp[3 + c] * u1;
         }
         const double* vi = &Vinv[9 * (size_t)p];
@@ -691,6 +888,14 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
           const double* jp = &S.Jp[6 * k];
           double m0 = 0, m1 = 0;
           if (b >= 0) for (int a = 0; a < 6; ++a) { m0 += jc[a] * dc[6 * b + a]; m1 += jc[6 + a] * dc[6 * b + a]; }
+          if (ni > 0) {
+            const int ib = S.intr_block[pb.image_camera[pb.obs_image[S.obs[k]]]];
+            if (ib >= 0)
+              for (int a = 0; a < IW; ++a) {
+                m0 += S.Ji[2 * IW * k + a] * dc[ioff + IW * ib + a];
+                m1 += S.Ji[2 * IW * k + IW + a] * dc[ioff + IW * ib + a];
+              }
+          }
           for (int c = 0; c < 3; ++c) { m0 += jp[c] * dp[3 * p + c]; m1 += jp[3 + c] * dp[3 * p + c]; }
           model_cost_change -= m0 * (S.r[2 * k] + m0 / 2.0) + m1 * (S.r[2 * k + 1] + m1 / 2.0);
         }
@@ -741,7 +946,18 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
         x_sq += S.X[3 * p + a] * S.X[3 * p + a];
       }
     }
-    cost_new = S.Evaluate(qn, tn, Xn, false);
+    std::vector<double> prm_n = S.params;
+    for (int c = 0; c < pb.num_cameras; ++c) {
+      const int ib = S.intr_block[c];
+      if (ib < 0) continue;
+      for (int a = 0; a < kNumParams[pb.camera_model[c]]; ++a) {
+        const double d = ((S.intr_mask[c] >> a) & 1) ? dc[ioff + IW * ib + a] * S.intr_scale[IW * ib + a] : 0.0;
+        prm_n[12 * (size_t)c + a] = S.params[12 * (size_t)c + a] + d;
+        step_sq += d * d;
+        x_sq += S.params[12 * (size_t)c + a] * S.params[12 * (size_t)c + a];
+      }
+    }
+    cost_new = S.Evaluate(qn, tn, Xn, prm_n, false);
     if (std::sqrt(step_sq) <= opt.parameter_tolerance * (std::sqrt(x_sq) + opt.parameter_tolerance)) {
       sum->termination_type = 0;  // parameter tolerance: the candidate is not applied
       break;
@@ -759,6 +975,7 @@ int SolveBA(const orc_ba_problem& pb, const orc_ba_options& opt, orc_ba_summary*
       radius = std::min(opt.max_trust_region_radius, radius);
       decrease_factor = 2.0;
       S.q.swap(qn); S.t.swap(tn); S.X.swap(Xn);
+      S.params.swap(prm_n);
       tj = std::chrono::steady_clock::now();
       cost = S.Evaluate(S.q, S.t, S.X, true);
       S.Normal(U, gc, V, gp);
@@ -804,6 +1021,9 @@ void orc_ba_options_default(orc_ba_options* o) {
   o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1;
   o->num_threads = -1;
+  o->refine_focal_length = 0;  // intrinsics constant (the pose-refinement / test default; the
+  o->refine_principal_point = 0;  // mapper sets them per its options)
+  o->refine_extra_params = 0;
 }
 
 int orc_ba_solve(const orc_ba_problem* problem, const orc_ba_options* options,
@@ -862,6 +1082,7 @@ int orc_refine_absolute_pose(const double* lines, const double* points, const ui
   pb.num_cameras = 1; pb.camera_model = &model; pb.camera_params = params;
   pb.num_points = np; pb.points = pts.data(); pb.point_const = pc.data();
   pb.num_obs = np; pb.obs_image = oi.data(); pb.obs_point = op.data(); pb.obs_line = ol.data();
+  pb.camera_const = nullptr;
   orc_ba_options o;
   orc_ba_options_default(&o);
   o.loss_type = 2;

@@ -38,7 +38,7 @@ typedef struct {
   const int32_t* image_camera; /* index into cameras */
   int32_t num_cameras;
   const int32_t* camera_model; /* COLMAP model ids (camera_models.h:189-248) */
-  const double* camera_params; /* num_cameras x 12, zero padded */
+  double* camera_params;       /* num_cameras x 12, zero padded; in/out when intrinsics are refined */
   int32_t num_points;
   double* points;              /* num_points x 3, in/out */
   const uint8_t* point_const;  /* may be NULL */
@@ -46,6 +46,8 @@ typedef struct {
   const int32_t* obs_image;
   const int32_t* obs_point;
   const double* obs_line;      /* num_obs x 3 */
+  const uint8_t* camera_const; /* config.IsConstantCamera per camera (bundle_adjustment.cc:497);
+                                  may be NULL (= none) */
 } orc_ba_problem;
 
 typedef struct {
@@ -64,6 +66,11 @@ typedef struct {
   double max_lm_diagonal;
   int32_t jacobi_scaling;
   int32_t num_threads;
+  /* BundleAdjustmentOptions::refine_* (bundle_adjustment.h:57-63) -> ParameterizeCameras
+   * (bundle_adjustment.cc:490-528): which groups of Camera::Params() are variable */
+  int32_t refine_focal_length;
+  int32_t refine_principal_point;
+  int32_t refine_extra_params;
 } orc_ba_options;
 
 typedef struct {
