@@ -16,9 +16,24 @@ given as tracks (one lifted line per image that sees the point):
                               constant, second image tvec[0] constant), then FilterPoints3D
                               (sfm/incremental_mapper.cc:893-945, controllers/...:102-130)
 
-It is a driver for tests and for the full-loop configuration of BASELINE.json, not a
-re-implementation of COLMAP's bookkeeping (no local BA, re-triangulation or track merging).
+  AdjustLocalBundle           the new image + the 5 images sharing most points, last one constant,
+                              second-to-last tvec[0] constant, short-track points of the new image
+                              variable, their views outside the bundle through constant poses,
+                              SOFT_L1, then CompleteTracks + FilterPoints3D of the touched points
+                              (sfm/incremental_mapper.cc:781-891)
+  schedule                    local BA after every registration, global BA when the model has
+                              grown by ba_global_{images,points}_{ratio,freq}
+                              (controllers/incremental_mapper.cc:490-510)
+  WriteText / ReadText        cameras.txt / images.txt / points3D.txt of this fork
+                              (base/reconstruction.cc:963-1095: images carry LINES2D[] as
+                              (A, B, C, is_aligned, POINT3D_ID))
+
+It is a driver for tests and for the full-loop configuration of BASELINE.json (configs[4]) over the
+GPU operators, not a re-implementation of COLMAP's bookkeeping: tracks are given (no
+correspondence search, hence no track merging), one shared camera, intrinsics constant (the
+fork's defaults, controllers/incremental_mapper.h:81-83).
 """
+import os
 import numpy as np
 
 from . import bundle_adjustment as ba
@@ -46,7 +61,20 @@ class Scene:
 
 class IncrementalMapper:
     def __init__(self, ctx, scene, max_reproj_error_px=12.0, filter_max_reproj_error=4.0,
-                 filter_min_tri_angle=1.5, ba_every=4, verbose=False):
+                 filter_min_tri_angle=1.5, ba_every=4, verbose=False, local_ba=False,
+                 ba_global_images_ratio=1.1, ba_global_points_ratio=1.1,
+                 ba_global_images_freq=500, ba_global_points_freq=250000,
+                 ba_local_num_images=6, ba_ctx=None):
+        """local_ba = False: global BA every `ba_every` images (the small-scene mode of the
+        tests); True: the controller's schedule — local BA after every image, global BA when the
+        model has grown by the ba_global_* ratios.  ba_ctx: context for the GLOBAL adjustments
+        (e.g. one with a communicator: sharded over the GPUs); default ctx."""
+        self.local_ba = local_ba
+        self.ba_global = (ba_global_images_ratio, ba_global_points_ratio, ba_global_images_freq,
+                          ba_global_points_freq)
+        self.ba_local_num_images = ba_local_num_images
+        self.ba_ctx = ba_ctx if ba_ctx is not None else ctx
+        self.timing = {}
         self.ctx, self.scene = ctx, scene
         n, p = scene.visible.shape
         self.qvec = np.zeros((n, 4))
@@ -175,7 +203,7 @@ class IncrementalMapper:
                              [sc.camera_params], pose_flags=flags)
         opts = ba.default_solver_options(loss_type=0, max_num_iterations=max_num_iterations,
                                          gradient_tolerance=1.0)   # controllers/...:221-243
-        ok, s = ba.solve_arrays(self.ctx, arrays, opts)
+        ok, s = ba.solve_arrays(self.ba_ctx, arrays, opts)
         if ok:
             self.qvec[reg], self.tvec[reg] = arrays.qvecs[reg], arrays.tvecs[reg]
             self.points[pid] = arrays.points
@@ -189,26 +217,219 @@ class IncrementalMapper:
         self.points[pid[pd]] = np.nan
         self.log.append(("global_ba", float(s.initial_cost), float(s.final_cost), int(nf)))
 
+    # ---- AdjustLocalBundle (sfm/incremental_mapper.cc:781-891) ----------------------------------
+    def adjust_local_bundle(self, i, max_num_iterations=25):
+        sc = self.scene
+        reg = np.array(self.registered)
+        seen = self.obs_on[i] & self.has_point                    # points of the new image
+        if not seen.any():
+            return
+        # FindLocalBundle: the images sharing most points with image i
+        shared = (self.obs_on[reg][:, seen]).sum(axis=1)
+        shared[reg == i] = -1
+        order = np.argsort(-shared, kind="stable")[:self.ba_local_num_images - 1]
+        local = [int(reg[k]) for k in order if shared[k] > 0]
+        if not local:
+            return
+        bundle = [i] + local
+        in_bundle = np.zeros(len(self.qvec), bool)
+        in_bundle[bundle] = True
+        is_reg = np.zeros(len(self.qvec), bool)
+        is_reg[reg] = True
+        # variable points: those of the new image with a short track (kMaxTrackLength = 15)
+        track_len = (self.obs_on[reg]).sum(axis=0)
+        variable = seen & (track_len <= 15)
+        # observations: everything the bundle images see (AddImageToProblem), plus the views of
+        # the variable points from registered images outside the bundle (AddPointToProblem)
+        pts_any = np.flatnonzero(((self.obs_on[bundle]) & self.has_point[None, :]).any(axis=0))
+        img_ids = np.flatnonzero(is_reg)
+        sub = self.obs_on[np.ix_(img_ids, pts_any)]
+        keep = in_bundle[img_ids][:, None] | variable[pts_any][None, :]
+        ii, pp = np.nonzero(sub & keep)
+        obs_image, obs_point = img_ids[ii], pts_any[pp]
+        flags = np.ones(len(self.qvec), np.uint8)                 # outside the bundle: constant
+        flags[bundle] = 0
+        if len(local) == 1:                                       # (:828-839)
+            flags[local[0]] = 1
+            flags[i] = 2
+        else:
+            flags[local[-1]] = 1
+            flags[local[-2]] = 2
+        local_pt = np.searchsorted(pts_any, obs_point)
+        # points whose track is not completely inside the problem are constant (ParameterizePoints)
+        arrays = ba.BaArrays(self.qvec, self.tvec, self.points[pts_any], obs_image, local_pt,
+                             sc.lines[obs_image, obs_point], [sc.camera_model],
+                             [sc.camera_params], pose_flags=flags,
+                             point_const=(~variable[pts_any]).astype(np.uint8))
+        opts = ba.default_solver_options(loss_type=1, loss_scale=1.0,   # controllers/...:196-219
+                                         max_num_iterations=max_num_iterations,
+                                         gradient_tolerance=10.0)
+        ok, s = ba.solve_arrays(self.ctx, arrays, opts)
+        if ok:
+            self.qvec[bundle], self.tvec[bundle] = arrays.qvecs[bundle], arrays.tvecs[bundle]
+            self.points[pts_any] = arrays.points
+        touched = np.flatnonzero(variable)
+        completed = self.complete_tracks(touched)
+        # FilterPoints3D of the changed points (:882-888)
+        nf = 0
+        if len(touched):
+            pb, obs_image, obs_point = self._track_problem(touched, self.points[touched].copy())
+            nf, od, pd, _ = F.FilterPoints3D(self.ctx, pb, self.filter_max_reproj_error,
+                                             self.filter_min_tri_angle)
+            od, pd = od.astype(bool), pd.astype(bool)
+            self.obs_on[obs_image[od], obs_point[od]] = False
+            self.has_point[touched[pd]] = False
+            self.points[touched[pd]] = np.nan
+        self.log.append(("local_ba", i, len(bundle), float(s.initial_cost), float(s.final_cost),
+                         int(completed), int(nf)))
+
+    # ---- CompleteTracks (sfm/incremental_triangulator.cc, CompleteTracks / CompleteImage) --------
+    def complete_tracks(self, point_ids):
+        """Views of a triangulated point that were dropped earlier (RANSAC outlier at registration
+        time, filtered) re-join the track if the point now reprojects within the filter
+        threshold and in front of the camera."""
+        sc = self.scene
+        reg = np.array(self.registered)
+        if len(point_ids) == 0:
+            return 0
+        cand = sc.visible[np.ix_(reg, point_ids)] & ~self.obs_on[np.ix_(reg, point_ids)] & \
+            self.has_point[point_ids][None, :]
+        ri, pi = np.nonzero(cand)
+        if len(ri) == 0:
+            return 0
+        from .synthetic import quat_to_rotmat
+        img, pts = reg[ri], point_ids[pi]
+        Rm = np.stack([quat_to_rotmat(self.qvec[k]) for k in reg])[ri]
+        pc = np.einsum("nij,nj->ni", Rm, self.points[pts]) + self.tvec[img]
+        ok = pc[:, 2] > 1e-9
+        uv = pc[:, :2] / np.where(ok, pc[:, 2], 1.0)[:, None]
+        l = sc.lines[img, pts]
+        dist_px = np.abs((l[:, 0] * uv[:, 0] + l[:, 1] * uv[:, 1] + l[:, 2])) * sc.mean_focal
+        good = ok & (dist_px < self.filter_max_reproj_error)
+        self.obs_on[img[good], pts[good]] = True
+        return int(good.sum())
+
+    # ---- WriteText / ReadText (base/reconstruction.cc:963-1095) -----------------------------------
+    MODEL_NAMES = {0: "SIMPLE_PINHOLE", 1: "PINHOLE", 2: "SIMPLE_RADIAL", 3: "RADIAL", 4: "OPENCV"}
+
+    def write_text(self, path):
+        """cameras.txt, images.txt (LINES2D[] as (A, B, C, is_aligned, POINT3D_ID)) and
+        points3D.txt (TRACK[] as (IMAGE_ID, line_idx)) with 17 significant digits.  Image ids are
+        index + 1, the lines of an image are its visible tracks in point order, point ids are
+        point index + 1."""
+        sc = self.scene
+        os.makedirs(path, exist_ok=True)
+        nparams = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8}[sc.camera_model]
+        with open(os.path.join(path, "cameras.txt"), "w") as f:
+            f.write("# Camera list with one line of data per camera:\n")
+            f.write("#   CAMERA_ID, MODEL, WIDTH, HEIGHT, PARAMS[]\n# Number of cameras: 1\n")
+            f.write("1 %s %d %d %s\n" % (self.MODEL_NAMES[sc.camera_model], sc.camera_size[0],
+                                         sc.camera_size[1],
+                                         " ".join(repr(float(x)) for x in sc.camera_params[:nparams])))
+        line_idx = {}
+        with open(os.path.join(path, "images.txt"), "w") as f:
+            f.write("# Image list with two lines of data per image:\n")
+            f.write("#   IMAGE_ID, QW, QX, QY, QZ, TX, TY, TZ, CAMERA_ID, NAME\n")
+            f.write("#   LINES2D[] as (A, B, C, is_aligned, POINT3D_ID)\n")
+            f.write("# Number of images: %d\n" % len(self.registered))
+            for i in sorted(self.registered):
+                q = self.qvec[i] / np.linalg.norm(self.qvec[i])
+                f.write("%d %s %s 1 image%06d.jpg\n" % (
+                    i + 1, " ".join(repr(float(x)) for x in q),
+                    " ".join(repr(float(x)) for x in self.tvec[i]), i))
+                vis = np.flatnonzero(sc.visible[i])
+                parts = []
+                for k, p in enumerate(vis):
+                    line_idx[(i, int(p))] = k
+                    has = self.obs_on[i, p] and self.has_point[p]
+                    a, b, c = sc.lines[i, p]
+                    parts.append("%r %r %r %d %d" % (float(a), float(b), float(c),
+                                                     1 if sc.aligned[p] else 0, p + 1 if has else -1))
+                f.write(" ".join(parts) + "\n")
+        reg = set(self.registered)
+        with open(os.path.join(path, "points3D.txt"), "w") as f:
+            f.write("# 3D point list with one line of data per point:\n")
+            f.write("#   POINT3D_ID, X, Y, Z, R, G, B, ERROR, TRACK[] as (IMAGE_ID, line_idx)\n")
+            f.write("# Number of points: %d\n" % int(self.has_point.sum()))
+            for p in np.flatnonzero(self.has_point):
+                imgs = [i for i in np.flatnonzero(self.obs_on[:, p]) if int(i) in reg]
+                track = " ".join("%d %d" % (i + 1, line_idx[(int(i), int(p))]) for i in imgs)
+                x, y, z = self.points[p]
+                f.write("%d %r %r %r 0 0 0 -1 %s\n" % (p + 1, float(x), float(y), float(z), track))
+
+    @staticmethod
+    def read_text(path):
+        """Reads the three files back: dict(cameras {id: (model, w, h, params)}, images {id:
+        (qvec, tvec, camera_id, name, lines [n, 5])}, points {id: (xyz, error, track [m, 2])})."""
+        cams, images, points = {}, {}, {}
+        with open(os.path.join(path, "cameras.txt")) as f:
+            for ln in f:
+                if ln.startswith("#") or not ln.strip():
+                    continue
+                t = ln.split()
+                cams[int(t[0])] = (t[1], int(t[2]), int(t[3]), np.array(t[4:], np.float64))
+        with open(os.path.join(path, "images.txt")) as f:
+            rows = [ln for ln in f if not ln.startswith("#")]
+        for k in range(0, len(rows) - 1, 2):
+            t = rows[k].split()
+            vals = np.array(rows[k + 1].split(), np.float64).reshape(-1, 5)
+            images[int(t[0])] = (np.array(t[1:5], np.float64), np.array(t[5:8], np.float64),
+                                 int(t[8]), t[9], vals)
+        with open(os.path.join(path, "points3D.txt")) as f:
+            for ln in f:
+                if ln.startswith("#") or not ln.strip():
+                    continue
+                t = ln.split()
+                points[int(t[0])] = (np.array(t[1:4], np.float64), float(t[7]),
+                                     np.array(t[8:], np.int64).reshape(-1, 2))
+        return dict(cameras=cams, images=images, points=points)
+
     # ---- the loop (controllers/incremental_mapper.cc:438-591) -------------------------------------
-    def run(self, initial_images):
+    def run(self, initial_images, max_images=None):
+        import time
+        t0 = time.perf_counter()
+        tm = self.timing
+        for k in ("register", "triangulate", "local_ba", "global_ba", "find_next"):
+            tm.setdefault(k, 0.0)
+
+        def timed(key, fn, *a):
+            t = time.perf_counter()
+            r = fn(*a)
+            tm[key] += time.perf_counter() - t
+            return r
+
         if not self.register_initial(initial_images):
             return False
         since_ba = 0
-        while True:
-            i = self.find_next_image()
+        prev_images, prev_points = len(self.registered), int(self.has_point.sum())
+        while max_images is None or len(self.registered) < max_images:
+            i = timed("find_next", self.find_next_image)
             if i is None:
                 break
-            if not self.register_next_image(i):
+            if not timed("register", self.register_next_image, i):
                 # give up on this image (the reference retries other candidates)
                 self.obs_on[i, :] = False
                 continue
-            self.triangulate_new()
-            since_ba += 1
-            if since_ba >= self.ba_every:
-                self.adjust_global_bundle()
-                self.triangulate_new()
-                since_ba = 0
-        self.adjust_global_bundle()
+            timed("triangulate", self.triangulate_new)
+            if self.local_ba:
+                # controllers/incremental_mapper.cc:484-510: local BA, then global BA when the
+                # model has grown enough since the last one
+                timed("local_ba", self.adjust_local_bundle, i)
+                ri, rp, fi, fp = self.ba_global
+                n_img, n_pts = len(self.registered), int(self.has_point.sum())
+                if (n_img >= ri * prev_images or n_img >= fi + prev_images or
+                        n_pts >= rp * prev_points or n_pts >= fp + prev_points):
+                    timed("global_ba", self.adjust_global_bundle)
+                    timed("triangulate", self.triangulate_new)
+                    prev_images, prev_points = len(self.registered), int(self.has_point.sum())
+            else:
+                since_ba += 1
+                if since_ba >= self.ba_every:
+                    timed("global_ba", self.adjust_global_bundle)
+                    timed("triangulate", self.triangulate_new)
+                    since_ba = 0
+        timed("global_ba", self.adjust_global_bundle)
+        tm["total"] = time.perf_counter() - t0
         return True
 
 
@@ -219,7 +440,7 @@ def _rotmat_to_quat(R):
 
 
 def make_mapper_scene(num_images=12, num_points=600, aligned_fraction=0.4, noise_px=0.3,
-                      focal=1000.0, seed=1, visibility=0.8):
+                      focal=1000.0, seed=1, visibility=0.8, rings=1):
     """Upright cameras on an arc looking at a cloud of points; every point is seen by a random
     subset of the images; the four initial images see everything.  Returns (Scene, gt) with
     gt = dict(R [N,3,3], t [N,3], points [P,3])."""
@@ -228,7 +449,10 @@ def make_mapper_scene(num_images=12, num_points=600, aligned_fraction=0.4, noise
     R = np.zeros((num_images, 3, 3))
     t = np.zeros((num_images, 3))
     for i, a in enumerate(ang):
-        c = np.array([4.0 * np.sin(a), 0.15 * rng.normal(), -4.0 * np.cos(a)])   # camera centre
+        ring = i % max(1, rings)                 # multi-ring trajectory: radius / height per ring
+        rad = 4.0 + 0.8 * ring
+        c = np.array([rad * np.sin(a), 0.15 * rng.normal() + 0.5 * ring,
+                      -rad * np.cos(a)])                                          # camera centre
         yaw = a + 0.05 * rng.normal()
         R[i] = np.array([[np.cos(yaw), 0, np.sin(yaw)], [0, 1, 0], [-np.sin(yaw), 0, np.cos(yaw)]])
         t[i] = -R[i] @ c

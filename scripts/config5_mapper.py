@@ -1,0 +1,60 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[4]: the incremental-mapper loop (register -> triangulate -> local /
+global bundle adjustment -> filters) on a synthetic 1000-image scene, every operator on the GPU.
+
+  python scripts/config5_mapper.py [images] [points] [visibility]
+  torchrun --nproc-per-node N scripts/config5_mapper.py ...   (global BA sharded over N GPUs)
+
+Prints one JSON line: wall time of the loop, its split, registered images, final pose error
+against the generating scene (after a similarity alignment)."""
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import privacy_preserving_sfm_b200 as pp                      # noqa: E402
+from privacy_preserving_sfm_b200 import mapper as M           # noqa: E402
+
+n_img = int(sys.argv[1]) if len(sys.argv) > 1 else 1000
+n_pts = int(sys.argv[2]) if len(sys.argv) > 2 else 30000
+vis = float(sys.argv[3]) if len(sys.argv) > 3 else 0.03
+world = int(os.environ.get("WORLD_SIZE", "1"))
+rank = int(os.environ.get("RANK", "0"))
+local = int(os.environ.get("LOCAL_RANK", "0"))
+ctx = pp.Context(local)
+ba_ctx = None
+if world > 1:
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl")
+    ba_ctx = pp.Context(local)          # a second context with the communicator: every rank runs
+    ba_ctx.comm_init_from_torch(dist)   # the same deterministic loop, global BA is collective
+t0 = time.perf_counter()
+scene, gt = M.make_mapper_scene(num_images=n_img, num_points=n_pts, seed=20201017,
+                                visibility=vis, noise_px=0.5, rings=3)
+t_scene = time.perf_counter() - t0
+m = M.IncrementalMapper(ctx, scene, local_ba=True, ba_ctx=ba_ctx)
+t0 = time.perf_counter()
+ok = m.run([0, 1, 2, 3])
+wall = time.perf_counter() - t0
+rot_err, centre_err = M.pose_errors(m, gt)
+if rank == 0:
+    kinds = [e[0] for e in m.log]
+    print(json.dumps({
+        "metric": "incremental mapper loop wall time (BASELINE.json configs[4])", "value": wall,
+        "unit": "s", "higher_is_better": False, "n_gpus": world, "ok": bool(ok),
+        "config": {"images": n_img, "points": n_pts, "observations": int(scene.visible.sum()),
+                   "visibility": vis, "noise_px": 0.5},
+        "registered_images": len(m.registered), "points3D": int(m.has_point.sum()),
+        "images_per_s": len(m.registered) / wall,
+        "split_s": {k: round(v, 3) for k, v in m.timing.items()},
+        "calls": {k: kinds.count(k) for k in ("register", "triangulate", "local_ba", "global_ba")},
+        "max_rotation_error_rad": rot_err, "max_centre_error_rel": centre_err,
+        "scene_generation_s": t_scene,
+        "note": "Python driver over the GPU operators; one shared PINHOLE camera, tracks given"}))
+if world > 1:
+    dist.destroy_process_group()
