@@ -70,6 +70,7 @@ class IncrementalMapper:
         model has grown by the ba_global_* ratios.  ba_ctx: context for the GLOBAL adjustments
         (e.g. one with a communicator: sharded over the GPUs); default ctx."""
         self.local_ba = local_ba
+        self.max_init_tracks = 2000
         self.ba_global = (ba_global_images_ratio, ba_global_points_ratio, ba_global_images_freq,
                           ba_global_points_freq)
         self.ba_local_num_images = ba_local_num_images
@@ -93,6 +94,9 @@ class IncrementalMapper:
         sc = self.scene
         ids = list(image_ids)
         common = np.flatnonzero(sc.visible[ids].all(axis=0))
+        # (the four-view LO-MSAC is host code whose models carry every track, SURVEY.md A18: a few
+        # thousand tracks are what a real four-view match set holds)
+        common = common[:self.max_init_tracks]
         lines = sc.lines[ids][:, common]
         aligned = np.repeat(sc.aligned[common][None, :].astype(np.uint8), 4, axis=0)
         ok, poses, ratio, rep = I.initialize_reconstruction(lines, aligned, sc.gravity[ids])
@@ -389,7 +393,7 @@ class IncrementalMapper:
         import time
         t0 = time.perf_counter()
         tm = self.timing
-        for k in ("register", "triangulate", "local_ba", "global_ba", "find_next"):
+        for k in ("init", "register", "triangulate", "local_ba", "global_ba", "find_next"):
             tm.setdefault(k, 0.0)
 
         def timed(key, fn, *a):
@@ -398,7 +402,7 @@ class IncrementalMapper:
             tm[key] += time.perf_counter() - t
             return r
 
-        if not self.register_initial(initial_images):
+        if not timed("init", self.register_initial, initial_images):
             return False
         since_ba = 0
         prev_images, prev_points = len(self.registered), int(self.has_point.sum())
