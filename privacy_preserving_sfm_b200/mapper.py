@@ -146,7 +146,7 @@ class IncrementalMapper:
     def _track_problem(self, point_ids, use_points=None):
         sc = self.scene
         reg = np.array(self.registered)
-        vis = self.obs_on[reg][:, point_ids]                        # [R, T]
+        vis = self.obs_on[np.ix_(reg, point_ids)]                   # [R, T]
         counts = vis.sum(axis=0)
         track_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
         r_idx, t_idx = np.nonzero(vis.T)[::-1]                      # track-major order
@@ -163,9 +163,10 @@ class IncrementalMapper:
 
     def triangulate_new(self):
         reg = np.array(self.registered)
-        views = self.obs_on[reg].sum(axis=0)
         # tracks need a non-aligned line (incremental_triangulator.cc:512-515) and >= 3 views
-        cand = np.flatnonzero(~self.has_point & (views >= 3) & ~self.scene.aligned)
+        open_pts = np.flatnonzero(~self.has_point & ~self.scene.aligned)
+        views = self.obs_on[np.ix_(reg, open_pts)].sum(axis=0)
+        cand = open_pts[views >= 3]
         if len(cand) == 0:
             return 0
         pb, _, _ = self._track_problem(cand)
@@ -229,7 +230,9 @@ class IncrementalMapper:
         if not seen.any():
             return
         # FindLocalBundle: the images sharing most points with image i
-        shared = (self.obs_on[reg][:, seen]).sum(axis=1)
+        seen_idx = np.flatnonzero(seen)
+        sub_seen = self.obs_on[np.ix_(reg, seen_idx)]             # [R, points of image i]
+        shared = sub_seen.sum(axis=1)
         shared[reg == i] = -1
         order = np.argsort(-shared, kind="stable")[:self.ba_local_num_images - 1]
         local = [int(reg[k]) for k in order if shared[k] > 0]
@@ -241,8 +244,8 @@ class IncrementalMapper:
         is_reg = np.zeros(len(self.qvec), bool)
         is_reg[reg] = True
         # variable points: those of the new image with a short track (kMaxTrackLength = 15)
-        track_len = (self.obs_on[reg]).sum(axis=0)
-        variable = seen & (track_len <= 15)
+        variable = np.zeros(len(seen), bool)
+        variable[seen_idx[sub_seen.sum(axis=0) <= 15]] = True
         # observations: everything the bundle images see (AddImageToProblem), plus the views of
         # the variable points from registered images outside the bundle (AddPointToProblem)
         pts_any = np.flatnonzero(((self.obs_on[bundle]) & self.has_point[None, :]).any(axis=0))
