@@ -304,9 +304,13 @@ class IncrementalMapper:
         ri, pi = np.nonzero(cand)
         if len(ri) == 0:
             return 0
-        from .synthetic import quat_to_rotmat
         img, pts = reg[ri], point_ids[pi]
-        Rm = np.stack([quat_to_rotmat(self.qvec[k]) for k in reg])[ri]
+        q = self.qvec[img] / np.linalg.norm(self.qvec[img], axis=1, keepdims=True)
+        w, x, y, z = q[:, 0], q[:, 1], q[:, 2], q[:, 3]
+        Rm = np.stack([np.stack([1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)], 1),
+                       np.stack([2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)], 1),
+                       np.stack([2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)], 1)],
+                      axis=1)
         pc = np.einsum("nij,nj->ni", Rm, self.points[pts]) + self.tvec[img]
         ok = pc[:, 2] > 1e-9
         uv = pc[:, :2] / np.where(ok, pc[:, 2], 1.0)[:, None]
