@@ -21,6 +21,8 @@
 #include <type_traits>
 #include <vector>
 
+#include "camera_models_ext.h"
+
 namespace {
 
 // ---------------------------------------------------------------------------------------------
@@ -48,6 +50,15 @@ template <int N> Jet<N> operator/(const Jet<N>& x, const Jet<N>& y) {
 template <int N> Jet<N>& operator+=(Jet<N>& x, const Jet<N>& y) { x = x + y; return x; }
 template <int N> Jet<N>& operator/=(Jet<N>& x, const Jet<N>& y) { x = x / y; return x; }
 
+template <int N> Jet<N> sqrt(const Jet<N>& x) {
+  Jet<N> r; r.a = std::sqrt(x.a); const double d = 1.0 / (2.0 * r.a);
+  for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * d; return r; }
+template <int N> Jet<N> atan(const Jet<N>& x) {
+  Jet<N> r; r.a = std::atan(x.a); const double d = 1.0 / (1.0 + x.a * x.a);
+  for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * d; return r; }
+template <int N> Jet<N> tan(const Jet<N>& x) {
+  Jet<N> r; r.a = std::tan(x.a); const double d = 1.0 + r.a * r.a;
+  for (int i = 0; i < N; ++i) r.v[i] = x.v[i] * d; return r; }
 template <typename T> struct Lift { static T C(double x) { return T(x); } };
 template <> struct Lift<double> { static double C(double x) { return x; } };
 
@@ -118,7 +129,8 @@ bool WorldToImage(int model, const PT* p, const T u, const T v, T* x, T* y) {
       return true;
     }
   }
-  return false;
+  // OPENCV_FISHEYE, FULL_OPENCV, FOV, SIMPLE_RADIAL_FISHEYE, RADIAL_FISHEYE, THIN_PRISM_FISHEYE
+  return orc_cam::WorldToImageExt(model, p, u, v, x, y, C, P);
 }
 
 // BundleAdjustmentLineCostFunction::operator() (src/base/cost_functions.h:62-100).
@@ -167,8 +179,8 @@ void LineCostAutoDiff(int model, const double* cam, const double* line, const do
 
 // AutoDiff of the block (2; 4, 3, 3, kNumParams): additionally the 2 x 8 Jacobian with respect to
 // camera_params (columns >= NumParams stay zero).
-constexpr int kIntrWidth = 8;  // widest supported model (OPENCV)
-const int kNumParams[5] = {3, 4, 4, 5, 8};
+constexpr int kIntrWidth = 12;  // widest model (FULL_OPENCV, THIN_PRISM_FISHEYE)
+const int kNumParams[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
 void LineCostAutoDiffIntr(int model, const double* cam, const double* line, const double* q,
                           const double* t, const double* X, double* r, double* Jq, double* Jt,
                           double* JX, double* Jcam) {
@@ -386,7 +398,7 @@ struct Solver {
   // variable parameter get a reduced block of kIntrWidth columns after the pose blocks
   std::vector<double> params;             // current Camera::Params(), 12 per camera
   std::vector<int> intr_block;            // camera -> block index or -1 (constant intrinsics)
-  std::vector<uint8_t> intr_mask;         // per camera: bit k = parameter k is variable
+  std::vector<uint16_t> intr_mask;        // per camera: bit k = parameter k is variable
   int nintr = 0;
   std::vector<double> Ji;                 // 2 x kIntrWidth per obs (only if nintr > 0)
   std::vector<double> intr_scale;         // kIntrWidth per intrinsics block
@@ -409,13 +421,14 @@ struct Solver {
     params.assign(p.camera_params, p.camera_params + 12 * (size_t)p.num_cameras);
     intr_block.assign(p.num_cameras, -1);
     intr_mask.assign(p.num_cameras, 0);
-    std::vector<uint8_t> intr_candidate(p.num_cameras, 0);
+    std::vector<uint16_t> intr_candidate(p.num_cameras, 0);
     for (int c = 0; c < p.num_cameras; ++c) {
-      static const uint8_t kFocal[5] = {0x01, 0x03, 0x01, 0x01, 0x03};
-      static const uint8_t kPP[5] = {0x06, 0x0c, 0x06, 0x06, 0x0c};
-      static const uint8_t kExtra[5] = {0x00, 0x00, 0x08, 0x18, 0xf0};
+      static const uint16_t kFocal[11] = {0x1, 0x3, 0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x1, 0x1, 0x3};
+      static const uint16_t kPP[11] = {0x6, 0xc, 0x6, 0x6, 0xc, 0xc, 0xc, 0xc, 0x6, 0x6, 0xc};
+      static const uint16_t kExtra[11] = {0x0, 0x0, 0x8, 0x18, 0xf0, 0xf0, 0xff0, 0x10, 0x8, 0x18,
+                                          0xff0};
       const int m = p.camera_model[c];
-      uint8_t mask = 0;
+      uint16_t mask = 0;
       if (o.refine_focal_length) mask |= kFocal[m];
       if (o.refine_principal_point) mask |= kPP[m];
       if (o.refine_extra_params) mask |= kExtra[m];
@@ -1072,7 +1085,7 @@ int orc_refine_absolute_pose(const double* lines, const double* points, const ui
   uint8_t flags = 0;
   int32_t icam = 0;
   double params[12] = {0};
-  const int nparams[5] = {3, 4, 4, 5, 8};
+  const int nparams[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
   for (int k = 0; k < nparams[model]; ++k) params[k] = cam[k];
   // *qvec = NormalizeQuaternion(*qvec) (pose.cc:143)
   double nrm = std::sqrt(qvec[0] * qvec[0] + qvec[1] * qvec[1] + qvec[2] * qvec[2] + qvec[3] * qvec[3]);

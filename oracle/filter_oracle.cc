@@ -9,6 +9,7 @@
 // The reference's hash-map Reconstruction is replaced by a track-major SoA view (the loops visit a
 // point's track in Track::Elements() order, as here).  Parity unpinned at the Eigen boundary
 // (dot-product association); the reference has no test for these functions.
+#include "camera_models_ext.h"
 #include <cfloat>
 #include <cmath>
 #include <cstdint>
@@ -48,6 +49,11 @@ void RotationOf(const double* qv, double R[9]) {
 }
 
 void WorldToImage(int model, const double* p, double u, double v, double* x, double* y) {
+  if (model >= 5) {  // the fisheye / FOV / full-OpenCV / thin-prism models (camera_models_ext.h)
+    orc_cam::WorldToImageExt(model, p, u, v, x, y, [](double c) { return c; },
+                             [&](int k) { return p[k]; });
+    return;
+  }
   switch (model) {
     case 0: *x = p[0] * u + p[1]; *y = p[0] * v + p[2]; break;           // SIMPLE_PINHOLE
     case 1: *x = p[0] * u + p[2]; *y = p[1] * v + p[3]; break;           // PINHOLE

@@ -11,6 +11,7 @@
 //   RANSAC ctor cap / ComputeNumTrials                src/optim/ransac.h:144-176
 // Eigen::JacobiSVD is replaced by a one-sided Jacobi SVD of the full n x 4 system (parity
 // unpinned at the Eigen boundary; the reference has no test for this path).
+#include "camera_models_ext.h"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -53,6 +54,11 @@ Pose MakePose(const double* qv, const double* t) {
 }
 
 void WorldToImage(int model, const double* p, double u, double v, double* x, double* y) {
+  if (model >= 5) {  // the fisheye / FOV / full-OpenCV / thin-prism models (camera_models_ext.h)
+    orc_cam::WorldToImageExt(model, p, u, v, x, y, [](double c) { return c; },
+                             [&](int k) { return p[k]; });
+    return;
+  }
   switch (model) {
     case 0: *x = p[0] * u + p[1]; *y = p[0] * v + p[2]; break;
     case 1: *x = p[0] * u + p[2]; *y = p[1] * v + p[3]; break;

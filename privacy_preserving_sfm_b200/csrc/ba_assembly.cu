@@ -20,14 +20,14 @@ namespace ppsfm {
 
 namespace {
 
-// key = point index for kept observations, P for dropped ones (they sort to the end)
+// key = LOCAL point index for kept observations, P_local for dropped ones (they sort to the end)
 __global__ void asm_classify_kernel(BaRaw raw, int rank, int world, uint32_t* __restrict__ keys,
                                     int* __restrict__ vals, uint8_t* __restrict__ cam_used,
                                     unsigned long long* __restrict__ err /* [2] first bad obs */) {
   const int64_t o = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= raw.O) return;
   const int ci = raw.obs_image[o], pi = raw.obs_point[o];
-  uint32_t key = (uint32_t)raw.P;
+  uint32_t key = (uint32_t)raw.P_local;
   if (ci < 0 || ci >= raw.C || pi < 0 || pi >= raw.P) {
     atomicMin(&err[0], (unsigned long long)o);
   } else {
@@ -38,7 +38,8 @@ __global__ void asm_classify_kernel(BaRaw raw, int rank, int world, uint32_t* __
     const bool cc = raw.pose_flags[ci] & 1, pc = raw.point_const[pi] != 0;
     if (!(cc && pc)) {
       cam_used[ci] = 1;  // global property: identical on every rank
-      if (world == 1 || (pi % world) == rank) key = (uint32_t)pi;
+      if (world == 1) key = (uint32_t)pi;
+      else if ((pi % world) == rank) key = (uint32_t)(pi / world);
     }
   }
   keys[o] = key;
@@ -75,8 +76,9 @@ __global__ void asm_gather_kernel(BaRaw raw, const uint32_t* __restrict__ keys,
 __global__ void asm_point_var_kernel(BaRaw raw, const int64_t* __restrict__ pt_start,
                                      uint8_t* __restrict__ pt_var) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= raw.P) return;
-  pt_var[p] = (!raw.point_const[p] && pt_start[p + 1] > pt_start[p]) ? 1 : 0;
+  if (p >= raw.P_local) return;
+  const int64_t pg = (int64_t)p * raw.world + raw.rank;  // the caller's index of local point p
+  pt_var[p] = (!raw.point_const[pg] && pt_start[p + 1] > pt_start[p]) ? 1 : 0;
 }
 
 __global__ void asm_camera_keys_kernel(const int* __restrict__ obs_cam,
@@ -123,7 +125,7 @@ cudaError_t ba_assemble_points(BaDev& d, const BaRaw& raw, int rank, int world,
                                uint8_t* cam_used_host, int64_t* first_bad_index,
                                int64_t* first_bad_norm) {
   const int64_t O = raw.O;
-  const int P = raw.P, C = raw.C;
+  const int P = raw.P_local, C = raw.C;  // per-point arrays are local
   cudaError_t e = cudaSuccess;
   auto tmp_alloc = [&](void** p, size_t bytes) {
     if (e == cudaSuccess) e = cudaMallocAsync(p, bytes < 16 ? 16 : bytes, s);

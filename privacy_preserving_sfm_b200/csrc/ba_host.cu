@@ -27,9 +27,12 @@ struct BaState {
   ppsfm_ba_options opt{};
   std::vector<void*> allocs;
   // host copies needed to write results back in the caller's order
-  int C = 0, P = 0;
+  int C = 0, P = 0;       // P: points resident on this rank (all of them on a single GPU)
+  int P_global = 0;       // points of the caller's problem
   int64_t num_obs_in = 0;
   double *q0 = nullptr, *t0 = nullptr, *X0 = nullptr;  // initial state (for reset)
+  double* Xg = nullptr;              // sharded solve: whole-problem displacement buffer (download)
+  std::vector<double> points_in;     // sharded solve: the caller's points as handed in
   PinBuf h_scalars;
   int64_t launches = 0;
   double lin_ms = 0, lin_launches = 0;
@@ -105,18 +108,21 @@ void BaFree(BaState* st) {
 int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options* opt,
              int rank, int world, BaState** out) {
   if (!ctx || !pb || !opt || !out) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
-  const int C = pb->num_images, P = pb->num_points;
+  const int C = pb->num_images, P_global = pb->num_points;
   const int64_t O = pb->num_obs;
-  if (C < 0 || P < 0 || O < 0) return fail(ctx, PPSFM_ERR_INVALID, "negative size");
+  if (C < 0 || P_global < 0 || O < 0) return fail(ctx, PPSFM_ERR_INVALID, "negative size");
+  // sharded solve: the points p with p % world == rank live here, numbered p / world; every
+  // per-point array (and every per-point kernel) is sized by the local count
+  const int P = world <= 1 ? P_global
+                           : (P_global > rank ? (P_global - rank + world - 1) / world : 0);
   for (int i = 0; i < C; ++i) {
     const int cam = pb->image_camera[i];
     if (cam < 0 || cam >= pb->num_cameras)
       return fail(ctx, PPSFM_ERR_INVALID, "image %d references a missing camera", i);
     const int m = pb->camera_model[cam];
-    if (m < 0 || m > 4)
+    if (m < 0 || m > 10)
       return fail(ctx, PPSFM_ERR_INVALID,
-                  "camera model %d not supported (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL, "
-                  "RADIAL, OPENCV are)", m);
+                  "camera model id %d unknown (COLMAP ids 0..10)", m);
   }
   static const bool timing = tune_int("PPSFM_BA_TIMING", 0) != 0;
   const auto t_create = std::chrono::steady_clock::now();
@@ -125,6 +131,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   st->opt = *opt;
   st->C = C;
   st->P = P;
+  st->P_global = P_global;
   st->num_obs_in = O;
   st->rank = rank;
   st->world = world;
@@ -136,11 +143,12 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
 #define BA_TRY(x) do { if (e == cudaSuccess) e = (x); } while (0)
   // ---- raw arrays to HBM, assembly on the device (ba_assembly.cu)
   BaRaw raw;
-  raw.C = C; raw.P = P; raw.O = O;
-  std::vector<uint8_t> flags_h(std::max(C, 1), 0), pconst_h(std::max(P, 1), 0);
+  raw.C = C; raw.P = P_global; raw.O = O;
+  raw.P_local = P; raw.rank = world <= 1 ? 0 : rank; raw.world = world <= 1 ? 1 : world;
+  std::vector<uint8_t> flags_h(std::max(C, 1), 0), pconst_h(std::max(P_global, 1), 0);
   if (pb->pose_flags) std::copy(pb->pose_flags, pb->pose_flags + C, flags_h.begin());
   if (pb->point_const)
-    for (int i = 0; i < P; ++i) pconst_h[i] = pb->point_const[i] ? 1 : 0;
+    for (int i = 0; i < P_global; ++i) pconst_h[i] = pb->point_const[i] ? 1 : 0;
   std::vector<void*> raw_tmp;
   auto raw_upload = [&](const void* src, size_t bytes) -> void* {
     void* p = nullptr;
@@ -154,7 +162,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   raw.obs_point = (const int*)raw_upload(pb->obs_point, sizeof(int32_t) * (size_t)O);
   raw.obs_line = (const double*)raw_upload(pb->obs_line, sizeof(double) * 3 * (size_t)O);
   raw.pose_flags = (const uint8_t*)raw_upload(flags_h.data(), (size_t)C);
-  raw.point_const = (const uint8_t*)raw_upload(pconst_h.data(), (size_t)P);
+  raw.point_const = (const uint8_t*)raw_upload(pconst_h.data(), (size_t)P_global);
   std::vector<uint8_t> cam_used(std::max(C, 1), 0);
   int64_t bad_index = -1, bad_norm = -1;
   BA_TRY(ba_assemble_points(d, raw, rank, world, &StateAlloc, st, s, cam_used.data(), &bad_index,
@@ -204,7 +212,15 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     cudaStreamSynchronize(s);
     std::fprintf(stderr, "[ba] upload + device assembly %.2f ms\n", 1e3 * Secs(t_create));
   }
-  std::vector<double> X(pb->points, pb->points + 3 * (size_t)P);
+  std::vector<double> X(3 * (size_t)P);
+  for (int p = 0; p < P; ++p) {
+    const size_t pg = (size_t)p * raw.world + raw.rank;
+    for (int k = 0; k < 3; ++k) X[3 * (size_t)p + k] = pb->points[3 * pg + k];
+  }
+  if (world > 1) {
+    BA_TRY(DevAlloc(st, &st->Xg, 3 * (size_t)std::max(P_global, 1)));
+    st->points_in.assign(pb->points, pb->points + 3 * (size_t)P_global);
+  }
   BA_TRY(Upload(st, &d.block_img, block_img));
   BA_TRY(Upload(st, &d.cam_mask, cam_mask));
   BA_TRY(Upload(st, &d.img_model, img_model));
@@ -535,12 +551,19 @@ int BaDownload(BaState* st, const ppsfm_ba_problem* pb) {
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->qvecs, d.q, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToHost, s));
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->tvecs, d.t, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToHost, s));
   if (st->world > 1) {
-    // every rank moved only its own points: sum the displacements so that all ranks return the
-    // complete point set (X = X0 + sum_r (X_r - X0))
-    launch_axpby(d.Xn, d.X, st->X0, -1.0, 3 * (size_t)d.P, s);
-    const int rc = CommAllReduce(ctx, d.Xn, 3 * (size_t)d.P, false);
+    // every rank moved only its own points (local index p = the caller's p * world + rank):
+    // scatter the displacements into a zeroed whole-problem buffer and sum it over the ranks, so
+    // that all ranks return the complete point set (once per solve, not per iteration)
+    const size_t ng = 3 * (size_t)st->P_global;
+    PPSFM_CUDA(ctx, cudaMemsetAsync(st->Xg, 0, sizeof(double) * std::max<size_t>(ng, 1), s));
+    launch_scatter_displacement(st->Xg, d.X, st->X0, d.P, st->world, st->rank, s);
+    const int rc = CommAllReduce(ctx, st->Xg, ng, false);
     if (rc != PPSFM_OK) return rc;
-    launch_axpby(d.X, st->X0, d.Xn, 1.0, 3 * (size_t)d.P, s);
+    std::vector<double> disp(ng);
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(disp.data(), st->Xg, sizeof(double) * ng, cudaMemcpyDeviceToHost, s));
+    PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
+    for (size_t i = 0; i < ng; ++i) pb->points[i] = st->points_in[i] + disp[i];
+    return PPSFM_OK;
   }
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->points, d.X, sizeof(double) * 3 * d.P, cudaMemcpyDeviceToHost, s));
   PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
@@ -796,7 +819,7 @@ int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_
                                           ppsfm_ba_summary* summary) {
   if (!ctx || !inlier_mask || !lines || !points || !qvec || !tvec || !camera_params)
     return fail(ctx, PPSFM_ERR_INVALID, "null argument");
-  if (camera_model < 0 || camera_model > 4)
+  if (camera_model < 0 || camera_model > 10)
     return fail(ctx, PPSFM_ERR_INVALID, "camera model %d not supported", camera_model);
   // AbsolutePoseRefinementOptions::Check (pose.h:103-107)
   if (gradient_tolerance < 0 || max_num_iterations < 0 || loss_function_scale < 0)
@@ -824,7 +847,7 @@ int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_
   uint8_t flags = 0;
   int32_t icam = 0, model = camera_model;
   double params[12] = {0};
-  const int nparams[5] = {3, 4, 4, 5, 8};
+  const int nparams[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
   for (int k = 0; k < nparams[camera_model]; ++k) params[k] = camera_params[k];
   ppsfm_ba_problem pb;
   pb.num_images = 1; pb.qvecs = qvec; pb.tvecs = tvec; pb.pose_flags = &flags;

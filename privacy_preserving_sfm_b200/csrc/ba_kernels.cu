@@ -92,7 +92,7 @@ __device__ __forceinline__ void eval_loss(BaLoss loss, double s, double& rho0, d
 // Odd stride: lanes that read different images mostly hit different banks.  Intrinsics are
 // staged per CAMERA (8 doubles = OPENCV, the largest supported model) next to it.
 constexpr int kCamRec = 13;
-constexpr int kIntrRec = 9;  // 8 parameters + model id (stored as a double)
+constexpr int kIntrRec = 13;  // 12 parameters + model id (stored as a double)
 
 template <bool JAC, bool SMEM>
 __global__ void __launch_bounds__(kThreads, 2)  // ~100 live registers: 2 CTAs / SM, no spills
@@ -132,7 +132,7 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     }
     for (int idx = threadIdx.x; idx < d.num_cameras * kIntrRec; idx += kThreads) {
       const int cam = idx / kIntrRec, f = idx - cam * kIntrRec;
-      intr_tab[idx] = (f < 8) ? d.cam_params[12 * (size_t)cam + f] : (double)d.cam_model[cam];
+      intr_tab[idx] = (f < 12) ? d.cam_params[12 * (size_t)cam + f] : (double)d.cam_model[cam];
     }
     for (int ci = threadIdx.x; ci < d.C; ci += kThreads) tab_cam[ci] = d.img_cam[ci];
     __syncthreads();
@@ -171,6 +171,7 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     }
     if (!valid) continue;
     double qw, qx, qy, qz, tx, ty, tz, cs[6], prm[8];
+    const double* prm_all;
     int model;
     if (SMEM) {
       const double* rec = cam_tab + (size_t)ci * kCamRec;
@@ -181,7 +182,8 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
       const double* irec = intr_tab + (size_t)tab_cam[ci] * kIntrRec;
 #pragma unroll
       for (int j = 0; j < 8; ++j) prm[j] = irec[j];
-      model = (int)irec[8];
+      model = (int)irec[12];
+      prm_all = irec;
     } else {
       const double4 qq = *reinterpret_cast<const double4*>(q + 4 * (size_t)ci);
       qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
@@ -194,6 +196,7 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) prm[j] = d.img_params[12 * (size_t)ci + j];
       model = d.img_model[ci];
+      prm_all = d.img_params + 12 * (size_t)ci;
     }
     // ceres::UnitQuaternionRotatePoint
     const double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy;
@@ -211,8 +214,14 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     const double lu = u - alpha * a, lv = v - alpha * b;
     double x1, y1, x2, y2, d1xu = 0, d1xv = 0, d1yu = 0, d1yv = 0, d2xu = 0, d2xv = 0, d2yu = 0,
                            d2yv = 0;
-    world_to_image<JAC>(model, prm, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
-    world_to_image<JAC>(model, prm, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+    if (model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out of line, up to 12
+                       // parameters read where they lie (the common models keep 8 in registers)
+      world_to_image_ext<JAC>(model, prm_all, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
+      world_to_image_ext<JAC>(model, prm_all, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+    } else {
+      world_to_image<JAC>(model, prm, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
+      world_to_image<JAC>(model, prm, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+    }
     const double r0 = x1 - x2, r1 = y1 - y2;
     const double sq = r0 * r0 + r1 * r1;
     double rho0, rho1;
@@ -691,6 +700,22 @@ void launch_pack_lower(const double* S, int n, int ld, double* packed, cudaStrea
 }
 void launch_unpack_lower(double* S, int n, int ld, const double* packed, cudaStream_t s) {
   if (n > 0) ba_unpack_lower_kernel<<<n + 1, kThreads, 0, s>>>(S, n, ld, packed);
+}
+
+// Xg[3 (p world + rank) + k] = X[3 p + k] - X0[3 p + k]: this rank's point displacements at the
+// caller's indices (download of a sharded solve)
+__global__ void ba_scatter_displacement_kernel(double* __restrict__ Xg, const double* __restrict__ X,
+                                               const double* __restrict__ X0, int P, int world,
+                                               int rank) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 3 * P) return;
+  const int p = i / 3, k = i - 3 * p;
+  Xg[3 * ((size_t)p * world + rank) + k] = X[i] - X0[i];
+}
+void launch_scatter_displacement(double* Xg, const double* X, const double* X0, int P, int world,
+                                 int rank, cudaStream_t s) {
+  if (P > 0)
+    ba_scatter_displacement_kernel<<<(3 * P + 255) / 256, 256, 0, s>>>(Xg, X, X0, P, world, rank);
 }
 
 void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,

@@ -75,7 +75,10 @@ struct BaDev {
 
 // Device copies of the caller's arrays (input order), consumed by the assembly (ba_assembly.cu).
 struct BaRaw {
-  int C = 0, P = 0;
+  int C = 0, P = 0;  // P: points of the WHOLE problem (the caller's indices)
+  // sharded solve: this rank owns the points p with p % world == rank and numbers them p / world;
+  // every per-point array on the device has P_local entries (world == 1: P_local == P)
+  int P_local = 0, rank = 0, world = 1;
   int64_t O = 0;
   const int* obs_image = nullptr;       // [O]
   const int* obs_point = nullptr;       // [O]
@@ -128,6 +131,8 @@ size_t packed_lower_doubles(int n);
 void launch_pack_lower(const double* S, int n, int ld, double* packed, cudaStream_t s);
 void launch_unpack_lower(double* S, int n, int ld, const double* packed, cudaStream_t s);
 // out = a + beta * b
+void launch_scatter_displacement(double* Xg, const double* X, const double* X0, int P, int world,
+                                 int rank, cudaStream_t s);
 void launch_axpby(double* out, const double* a, const double* b, double beta, size_t n,
                   cudaStream_t s);
 // max |x - Plus(x, -g)| over all blocks -> scalars[kGradMax]

@@ -2,14 +2,178 @@
 // (src/base/camera_models.h:615-904) as a device function, shared by the bundle adjustment and the
 // observation filters.
 #pragma once
+#include <cfloat>
 
 namespace ppsfm {
+
+// ------------------------------------------------------------------------------------------
+// The six remaining COLMAP models (src/base/camera_models.h: OPENCV_FISHEYE :929-986,
+// FULL_OPENCV :1024-1080, FOV :1103-1166, SIMPLE_RADIAL_FISHEYE :1238-1290, RADIAL_FISHEYE
+// :1318-1366, THIN_PRISM_FISHEYE :1405-1481).  Each model is written ONCE, expression by
+// expression as the reference, over a scalar type S that is either double or a two-direction dual
+// number (value, d/du, d/dv): the 2x2 Jacobian the bundle adjustment needs is then the forward-mode
+// derivative of exactly the expressions the reference differentiates with ceres::Jet.  Not
+// inlined: the pinhole / radial / OpenCV path of the callers keeps its register budget.
+// ------------------------------------------------------------------------------------------
+struct Dual2 {
+  double v, a, b;  // value, d/du, d/dv
+};
+__device__ __forceinline__ Dual2 operator+(Dual2 x, Dual2 y) { return {x.v + y.v, x.a + y.a, x.b + y.b}; }
+__device__ __forceinline__ Dual2 operator-(Dual2 x, Dual2 y) { return {x.v - y.v, x.a - y.a, x.b - y.b}; }
+__device__ __forceinline__ Dual2 operator*(Dual2 x, Dual2 y) {
+  return {x.v * y.v, x.v * y.a + x.a * y.v, x.v * y.b + x.b * y.v};
+}
+__device__ __forceinline__ Dual2 operator/(Dual2 x, Dual2 y) {
+  const double inv = 1.0 / y.v, q = x.v * inv;
+  return {q, (x.a - q * y.a) * inv, (x.b - q * y.b) * inv};
+}
+__device__ __forceinline__ Dual2 cm_sqrt(Dual2 x) {
+  const double r = sqrt(x.v), d = 1.0 / (2.0 * r);
+  return {r, x.a * d, x.b * d};
+}
+__device__ __forceinline__ Dual2 cm_atan(Dual2 x) {
+  const double d = 1.0 / (1.0 + x.v * x.v);
+  return {atan(x.v), x.a * d, x.b * d};
+}
+__device__ __forceinline__ double cm_sqrt(double x) { return sqrt(x); }
+__device__ __forceinline__ double cm_atan(double x) { return atan(x); }
+__device__ __forceinline__ double cm_value(double x) { return x; }
+__device__ __forceinline__ double cm_value(Dual2 x) { return x.v; }
+template <typename S> __device__ __forceinline__ S cm_const(double c);
+template <> __device__ __forceinline__ double cm_const<double>(double c) { return c; }
+template <> __device__ __forceinline__ Dual2 cm_const<Dual2>(double c) { return {c, 0.0, 0.0}; }
+
+template <typename S, typename F>
+__device__ __forceinline__ void cm_fisheye(S u, S v, F thetad_of_theta, S& du, S& dv) {
+  const S r = cm_sqrt(u * u + v * v);
+  if (cm_value(r) > DBL_EPSILON) {
+    const S theta = cm_atan(r);
+    const S thetad = thetad_of_theta(theta);
+    du = u * thetad / r - u;
+    dv = v * thetad / r - v;
+  } else {
+    du = cm_const<S>(0.0);
+    dv = cm_const<S>(0.0);
+  }
+}
+
+template <typename S>
+__device__ void world_to_image_ext_t(int model, const double* __restrict__ p, S u, S v, S& x, S& y) {
+  auto C = [](double c) { return cm_const<S>(c); };
+  auto P = [&](int k) { return cm_const<S>(p[k]); };
+  switch (model) {
+    case 5: {  // OPENCV_FISHEYE fx, fy, cx, cy, k1, k2, k3, k4
+      S du, dv;
+      cm_fisheye(u, v, [&](S theta) {
+        const S theta2 = theta * theta;
+        const S theta4 = theta2 * theta2;
+        const S theta6 = theta4 * theta2;
+        const S theta8 = theta4 * theta4;
+        return theta * (C(1.0) + P(4) * theta2 + P(5) * theta4 + P(6) * theta6 + P(7) * theta8);
+      }, du, dv);
+      x = u + du;
+      y = v + dv;
+      x = P(0) * x + P(2);
+      y = P(1) * y + P(3);
+      break;
+    }
+    case 6: {  // FULL_OPENCV fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, k5, k6
+      const S u2 = u * u, uv = u * v, v2 = v * v, r2 = u2 + v2, r4 = r2 * r2, r6 = r4 * r2;
+      const S radial = (C(1.0) + P(4) * r2 + P(5) * r4 + P(8) * r6) /
+                       (C(1.0) + P(9) * r2 + P(10) * r4 + P(11) * r6);
+      const S du = u * radial + C(2.0) * P(6) * uv + P(7) * (r2 + C(2.0) * u2) - u;
+      const S dv = v * radial + C(2.0) * P(7) * uv + P(6) * (r2 + C(2.0) * v2) - v;
+      x = u + du;
+      y = v + dv;
+      x = P(0) * x + P(2);
+      y = P(1) * y + P(3);
+      break;
+    }
+    case 7: {  // FOV fx, fy, cx, cy, omega  (omega is a constant here: plain double branches)
+      const double omega = p[4], omega2 = omega * omega;
+      const S radius2 = u * u + v * v;
+      S factor;
+      if (omega2 < 1e-4) {
+        factor = (C(omega2) * radius2) / C(3.0) - C(omega2 / 12.0) + C(1.0);
+      } else if (cm_value(radius2) < 1e-4) {
+        const double tan_half_omega = tan(omega / 2.0);
+        factor = (C(-2.0 * tan_half_omega) *
+                  (C(4.0) * radius2 * C(tan_half_omega) * C(tan_half_omega) - C(3.0))) /
+                 C(3.0 * omega);
+      } else {
+        const S radius = cm_sqrt(radius2);
+        const S numerator = cm_atan(radius * C(2.0) * C(tan(omega / 2.0)));
+        factor = numerator / (radius * C(omega));
+      }
+      x = u * factor;
+      y = v * factor;
+      x = P(0) * x + P(2);
+      y = P(1) * y + P(3);
+      break;
+    }
+    case 8:    // SIMPLE_RADIAL_FISHEYE f, cx, cy, k
+    case 9: {  // RADIAL_FISHEYE f, cx, cy, k1, k2
+      S du, dv;
+      cm_fisheye(u, v, [&](S theta) {
+        const S theta2 = theta * theta;
+        if (model == 8) return theta * (C(1.0) + P(3) * theta2);
+        const S theta4 = theta2 * theta2;
+        return theta * (C(1.0) + P(3) * theta2 + P(4) * theta4);
+      }, du, dv);
+      x = u + du;
+      y = v + dv;
+      x = P(0) * x + P(1);
+      y = P(0) * y + P(2);
+      break;
+    }
+    default: {  // 10: THIN_PRISM_FISHEYE fx, fy, cx, cy, k1, k2, p1, p2, k3, k4, sx1, sy1
+      const S r = cm_sqrt(u * u + v * v);
+      S uu, vv;
+      if (cm_value(r) > DBL_EPSILON) {
+        const S theta = cm_atan(r);
+        uu = theta * u / r;
+        vv = theta * v / r;
+      } else {
+        uu = u;
+        vv = v;
+      }
+      const S u2 = uu * uu, uv = uu * vv, v2 = vv * vv, r2 = u2 + v2, r4 = r2 * r2, r6 = r4 * r2,
+              r8 = r6 * r2;
+      const S radial = P(4) * r2 + P(5) * r4 + P(8) * r6 + P(9) * r8;
+      const S du = uu * radial + C(2.0) * P(6) * uv + P(7) * (r2 + C(2.0) * u2) + P(10) * r2;
+      const S dv = vv * radial + C(2.0) * P(7) * uv + P(6) * (r2 + C(2.0) * v2) + P(11) * r2;
+      x = uu + du;
+      y = vv + dv;
+      x = P(0) * x + P(2);
+      y = P(1) * y + P(3);
+      break;
+    }
+  }
+}
+
+template <bool JAC>
+__device__ __noinline__ void world_to_image_ext(int model, const double* __restrict__ p, double u,
+                                                double v, double& x, double& y, double& xu,
+                                                double& xv, double& yu, double& yv) {
+  if (JAC) {
+    Dual2 X, Y;
+    world_to_image_ext_t<Dual2>(model, p, Dual2{u, 1.0, 0.0}, Dual2{v, 0.0, 1.0}, X, Y);
+    x = X.v; xu = X.a; xv = X.b;
+    y = Y.v; yu = Y.a; yv = Y.b;
+  } else {
+    world_to_image_ext_t<double>(model, p, u, v, x, y);
+  }
+}
 
 // CameraModel::WorldToImage (src/base/camera_models.h) and its 2x2 Jacobian d(x,y)/d(u,v).
 template <bool JAC>
 __device__ __forceinline__ void world_to_image(int model, const double* __restrict__ p, double u,
                                                double v, double& x, double& y, double& xu,
                                                double& xv, double& yu, double& yv) {
+  if (model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out-of-line
+    world_to_image_ext<JAC>(model, p, u, v, x, y, xu, xv, yu, yv);
+    return;
+  }
   switch (model) {
     case 0: {  // SIMPLE_PINHOLE f, cx, cy
       x = p[0] * u + p[1];

@@ -224,7 +224,7 @@ int validate(ppsfm_ctx* ctx, const ppsfm_filter_problem* pb) {
     const int cam = pb->image_camera[i];
     if (cam < 0 || cam >= pb->num_cameras)
       return fail(ctx, PPSFM_ERR_INVALID, "image %d references a missing camera", i);
-    if (pb->camera_model[cam] < 0 || pb->camera_model[cam] > 4)
+    if (pb->camera_model[cam] < 0 || pb->camera_model[cam] > 10)
       return fail(ctx, PPSFM_ERR_INVALID, "camera model %d not supported", pb->camera_model[cam]);
   }
   if (pb->track_start[0] != 0 || pb->track_start[pb->num_points] != pb->num_obs)

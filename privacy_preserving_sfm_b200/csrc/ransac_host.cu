@@ -890,11 +890,11 @@ int ppsfm_image_to_world_threshold(int camera_model, const double* camera_params
   // focal_length_idxs of src/base/camera_models.h:263-420
   double mean_focal_length = 0;
   switch (camera_model) {
-    case 0: case 2: case 3:  // SIMPLE_PINHOLE, SIMPLE_RADIAL, RADIAL: {0}
+    case 0: case 2: case 3: case 8: case 9:  // SIMPLE_PINHOLE, SIMPLE_RADIAL, RADIAL, *_FISHEYE: {0}
       mean_focal_length += camera_params[0];
       mean_focal_length /= 1;
       break;
-    case 1: case 4:          // PINHOLE, OPENCV: {0, 1}
+    case 1: case 4: case 5: case 6: case 7: case 10:  // PINHOLE, OPENCV*, FOV, THIN_PRISM: {0, 1}
       mean_focal_length += camera_params[0];
       mean_focal_length += camera_params[1];
       mean_focal_length /= 2;

@@ -381,7 +381,7 @@ int ppsfm_estimate_triangulation_batch(ppsfm_ctx* ctx, const ppsfm_filter_proble
     return fail(ctx, PPSFM_ERR_INVALID, "negative size");
   for (int i = 0; i < pb->num_images; ++i) {
     const int cam = pb->image_camera[i];
-    if (cam < 0 || cam >= pb->num_cameras || pb->camera_model[cam] < 0 || pb->camera_model[cam] > 4)
+    if (cam < 0 || cam >= pb->num_cameras || pb->camera_model[cam] < 0 || pb->camera_model[cam] > 10)
       return fail(ctx, PPSFM_ERR_INVALID, "image %d: missing camera or unsupported model", i);
   }
   const int T = pb->num_points;

@@ -56,7 +56,8 @@ class Scene:
         self.gravity = np.asarray(gravity, np.float64)      # [N, 3]
         self.camera_model, self.camera_params = int(camera_model), list(camera_params)
         self.camera_size = tuple(camera_size)
-        self.mean_focal = float(np.mean(camera_params[:2] if camera_model in (1, 4) else camera_params[:1]))
+        self.mean_focal = float(np.mean(camera_params[:2] if camera_model in (1, 4, 5, 6, 7, 10)
+                                        else camera_params[:1]))
 
 
 class IncrementalMapper:
@@ -321,7 +322,9 @@ class IncrementalMapper:
         return int(good.sum())
 
     # ---- WriteText / ReadText (base/reconstruction.cc:963-1095) -----------------------------------
-    MODEL_NAMES = {0: "SIMPLE_PINHOLE", 1: "PINHOLE", 2: "SIMPLE_RADIAL", 3: "RADIAL", 4: "OPENCV"}
+    MODEL_NAMES = {0: "SIMPLE_PINHOLE", 1: "PINHOLE", 2: "SIMPLE_RADIAL", 3: "RADIAL", 4: "OPENCV",
+                   5: "OPENCV_FISHEYE", 6: "FULL_OPENCV", 7: "FOV", 8: "SIMPLE_RADIAL_FISHEYE",
+                   9: "RADIAL_FISHEYE", 10: "THIN_PRISM_FISHEYE"}
 
     def write_text(self, path):
         """cameras.txt, images.txt (LINES2D[] as (A, B, C, is_aligned, POINT3D_ID)) and
@@ -330,7 +333,7 @@ class IncrementalMapper:
         point index + 1."""
         sc = self.scene
         os.makedirs(path, exist_ok=True)
-        nparams = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8}[sc.camera_model]
+        nparams = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12}[sc.camera_model]
         with open(os.path.join(path, "cameras.txt"), "w") as f:
             f.write("# Camera list with one line of data per camera:\n")
             f.write("#   CAMERA_ID, MODEL, WIDTH, HEIGHT, PARAMS[]\n# Number of cameras: 1\n")

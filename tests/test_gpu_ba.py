@@ -11,7 +11,14 @@ pytestmark = pytest.mark.gpu
 
 MODELS = [(0, [900.0, 500, 480]), (1, [1000.0, 990, 500, 480]), (2, [900.0, 500, 480, 0.05]),
           (3, [900.0, 500, 480, 0.05, -0.01]),
-          (4, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003])]
+          (4, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003]),
+          (5, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003]),                  # OPENCV_FISHEYE
+          (6, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003, 0.004, 0.02, -0.005, 0.001]),  # FULL_OPENCV
+          (7, [1000.0, 990, 500, 480, 0.3]),                                         # FOV
+          (7, [1000.0, 990, 500, 480, 0.003]),                                       # FOV, small omega
+          (8, [900.0, 500, 480, 0.05]),                                              # SIMPLE_RADIAL_FISHEYE
+          (9, [900.0, 500, 480, 0.05, -0.01]),                                       # RADIAL_FISHEYE
+          (10, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003, 0.004, -0.002, 0.001, -0.001])]  # THIN_PRISM_FISHEYE
 
 
 def _scene(num_cams=8, num_points=300, obs=5, seed=3, **kw):

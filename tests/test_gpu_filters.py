@@ -10,11 +10,19 @@ pytestmark = pytest.mark.gpu
 
 MODELS = [(0, [900.0, 500, 480]), (1, [1000.0, 990, 500, 480]), (2, [900.0, 500, 480, 0.05]),
           (3, [900.0, 500, 480, 0.05, -0.01]),
-          (4, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003])]
+          (4, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003]),
+          (5, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003]),                  # OPENCV_FISHEYE
+          (6, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003, 0.004, 0.02, -0.005, 0.001]),  # FULL_OPENCV
+          (7, [1000.0, 990, 500, 480, 0.3]),                                         # FOV
+          (7, [1000.0, 990, 500, 480, 0.003]),                                       # FOV, small omega
+          (8, [900.0, 500, 480, 0.05]),                                              # SIMPLE_RADIAL_FISHEYE
+          (9, [900.0, 500, 480, 0.05, -0.01]),                                       # RADIAL_FISHEYE
+          (10, [1000.0, 990, 500, 480, 0.05, -0.01, 0.002, -0.003, 0.004, -0.002, 0.001, -0.001])]  # THIN_PRISM_FISHEYE
 
 
 def _problem(num_cams, num_points, obs, seed, model=1, params=(1000.0, 1000.0, 500.0, 500.0),
              corrupt=0.15):
+    seed = int(seed)
     sc = S.make_ba_scene(num_cams=num_cams, num_points=num_points, obs_per_point=obs, seed=seed)
     rng = np.random.default_rng(seed + 1)
     order = np.argsort(sc["obs_pt"], kind="stable")
@@ -44,7 +52,10 @@ def test_filter_points3d_matches_oracle(ctx, oracle, model, params):
     assert nf == nf2 and nf > 0
     assert np.array_equal(od, od2) and np.array_equal(pd, pd2)
     assert 0 < pd.sum() < len(pd) and 0 < od.sum() < len(od)
-    assert np.array_equal(pe, pe2)         # same operations in the same order: bit-identical
+    if model <= 4:
+        assert np.array_equal(pe, pe2)     # same operations in the same order: bit-identical
+    else:                                  # atan / tan: CUDA's and glibc's differ in the last bits
+        assert np.allclose(pe, pe2, rtol=1e-12, atol=1e-12)
 
 
 def test_filter_points3d_short_and_empty_tracks(ctx, oracle):
