@@ -203,6 +203,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   for (int i = 0; i < C; ++i) {
     const int cam = pb->image_camera[i];
     img_model[i] = pb->camera_model[cam];
+    if (img_model[i] >= 5) d.has_ext_models = 1;
     std::memcpy(&img_params[12 * (size_t)i], pb->camera_params + 12 * (size_t)cam, 12 * sizeof(double));
   }
   d.NB = NB; d.n = 6 * NB; d.ld = chol_ld(6 * NB);

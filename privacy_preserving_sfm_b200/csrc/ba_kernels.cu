@@ -94,7 +94,9 @@ __device__ __forceinline__ void eval_loss(BaLoss loss, double s, double& rho0, d
 constexpr int kCamRec = 13;
 constexpr int kIntrRec = 13;  // 12 parameters + model id (stored as a double)
 
-template <bool JAC, bool SMEM>
+// EXT: the problem holds a camera of the fisheye / FOV / full-OpenCV / thin-prism family; those
+// models are evaluated out of line, and the instance without them is the unchanged hot kernel.
+template <bool JAC, bool SMEM, bool EXT = false>
 __global__ void __launch_bounds__(kThreads, 2)  // ~100 live registers: 2 CTAs / SM, no spills
 ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restrict__ t,
                     const double* __restrict__ X, BaLoss loss, double* __restrict__ partials,
@@ -171,7 +173,6 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     }
     if (!valid) continue;
     double qw, qx, qy, qz, tx, ty, tz, cs[6], prm[8];
-    const double* prm_all;
     int model;
     if (SMEM) {
       const double* rec = cam_tab + (size_t)ci * kCamRec;
@@ -183,7 +184,6 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) prm[j] = irec[j];
       model = (int)irec[12];
-      prm_all = irec;
     } else {
       const double4 qq = *reinterpret_cast<const double4*>(q + 4 * (size_t)ci);
       qw = qq.x; qx = qq.y; qy = qq.z; qz = qq.w;
@@ -196,7 +196,6 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
 #pragma unroll
       for (int j = 0; j < 8; ++j) prm[j] = d.img_params[12 * (size_t)ci + j];
       model = d.img_model[ci];
-      prm_all = d.img_params + 12 * (size_t)ci;
     }
     // ceres::UnitQuaternionRotatePoint
     const double t2 = qw * qx, t3 = qw * qy, t4 = qw * qz, t5 = -qx * qx, t6 = qx * qy;
@@ -214,13 +213,20 @@ ba_linearize_kernel(BaDev d, const double* __restrict__ q, const double* __restr
     const double lu = u - alpha * a, lv = v - alpha * b;
     double x1, y1, x2, y2, d1xu = 0, d1xv = 0, d1yu = 0, d1yv = 0, d2xu = 0, d2xv = 0, d2yu = 0,
                            d2yv = 0;
-    if (model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out of line, up to 12
+    if (EXT && model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out of line, up to 12
                        // parameters read where they lie (the common models keep 8 in registers)
-      world_to_image_ext<JAC>(model, prm_all, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
-      world_to_image_ext<JAC>(model, prm_all, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+      const double* prm_all = SMEM ? intr_tab + (size_t)tab_cam[ci] * kIntrRec
+                                   : d.img_params + 12 * (size_t)ci;
+      const WorldToImageResult w1 = world_to_image_ext<JAC>(model, prm_all, u, v);
+      const WorldToImageResult w2 = world_to_image_ext<JAC>(model, prm_all, lu, lv);
+      x1 = w1.x; y1 = w1.y; x2 = w2.x; y2 = w2.y;
+      if (JAC) {
+        d1xu = w1.xu; d1xv = w1.xv; d1yu = w1.yu; d1yv = w1.yv;
+        d2xu = w2.xu; d2xv = w2.xv; d2yu = w2.yu; d2yv = w2.yv;
+      }
     } else {
-      world_to_image<JAC>(model, prm, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
-      world_to_image<JAC>(model, prm, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
+      world_to_image<JAC, false>(model, prm, u, v, x1, y1, d1xu, d1xv, d1yu, d1yv);
+      world_to_image<JAC, false>(model, prm, lu, lv, x2, y2, d2xu, d2xv, d2yu, d2yv);
     }
     const double r0 = x1 - x2, r1 = y1 - y2;
     const double sq = r0 * r0 + r1 * r1;
@@ -628,13 +634,17 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
   static PerDevice<> per_device;
   static const int store_mode = tune_int("PPSFM_BA_J_STREAM", 0);
   const auto& dev = per_device.get([](const DeviceFacts& f, int&) {
-    cudaError_t e = cudaFuncSetAttribute(ba_linearize_kernel<true, true>,
-                                         cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         f.max_smem_optin - 1024);
-    if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(ba_linearize_kernel<false, true>,
-                                cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                f.max_smem_optin - 1024);
+    cudaError_t e = cudaSuccess;
+    auto optin = [&](auto kernel) {
+      if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 f.max_smem_optin - 1024);
+    };
+    optin(ba_linearize_kernel<true, true, false>);
+    optin(ba_linearize_kernel<false, true, false>);
+    optin(ba_linearize_kernel<true, true, true>);
+    optin(ba_linearize_kernel<false, true, true>);
+    return e;
   });
   // (a failed attribute call surfaces as a launch error at the caller's next CUDA check)
   const int num_sms = dev.facts.num_sms, max_smem = dev.facts.max_smem_optin;
@@ -649,20 +659,19 @@ int launch_linearize(const BaDev& d, const double* q, const double* t, const dou
     if (blocks > chunks) blocks = chunks;
   }
   if (blocks > d.num_partials) blocks = d.num_partials;
-  if (use_smem) {
-    if (jacobians)
-      ba_linearize_kernel<true, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
-                                                                          d.partials, chunks, store_mode);
-    else
-      ba_linearize_kernel<false, true><<<blocks, kThreads, tab_bytes, s>>>(d, q, t, X, loss,
-                                                                           d.partials, chunks, store_mode);
-  } else {
-    if (jacobians)
-      ba_linearize_kernel<true, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
-                                                                   chunks, store_mode);
-    else
-      ba_linearize_kernel<false, false><<<blocks, kThreads, 0, s>>>(d, q, t, X, loss, d.partials,
-                                                                    chunks, store_mode);
+  auto launch = [&](auto kernel, size_t smem) {
+    kernel<<<blocks, kThreads, smem, s>>>(d, q, t, X, loss, d.partials, chunks, store_mode);
+  };
+  const int variant = (jacobians ? 4 : 0) | (use_smem ? 2 : 0) | (d.has_ext_models ? 1 : 0);
+  switch (variant) {
+    case 7: launch(ba_linearize_kernel<true, true, true>, tab_bytes); break;
+    case 6: launch(ba_linearize_kernel<true, true, false>, tab_bytes); break;
+    case 5: launch(ba_linearize_kernel<true, false, true>, 0); break;
+    case 4: launch(ba_linearize_kernel<true, false, false>, 0); break;
+    case 3: launch(ba_linearize_kernel<false, true, true>, tab_bytes); break;
+    case 2: launch(ba_linearize_kernel<false, true, false>, tab_bytes); break;
+    case 1: launch(ba_linearize_kernel<false, false, true>, 0); break;
+    default: launch(ba_linearize_kernel<false, false, false>, 0); break;
   }
   reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials, blocks, d.num_partials, 1, d.scalars,
                                             kCost, 0);

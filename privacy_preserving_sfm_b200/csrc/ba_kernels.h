@@ -10,6 +10,7 @@ namespace ppsfm {
 // NB = camera blocks (images with a variable pose that have observations).
 struct BaDev {
   int C = 0, P = 0, NB = 0, n = 0, ld = 0;
+  int has_ext_models = 0;  // a camera of model id >= 5 is present (out-of-line model evaluation)
   int64_t K = 0;
   // static structure
   int* obs_cam = nullptr;       // [K] image index

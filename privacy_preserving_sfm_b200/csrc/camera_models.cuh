@@ -151,27 +151,40 @@ __device__ void world_to_image_ext_t(int model, const double* __restrict__ p, S 
   }
 }
 
+// Result by value: the caller's own variables never have their address taken, so its fast path
+// (pinhole / radial / OpenCV, inlined) keeps them in registers.
+struct WorldToImageResult {
+  double x, y, xu, xv, yu, yv;
+};
 template <bool JAC>
-__device__ __noinline__ void world_to_image_ext(int model, const double* __restrict__ p, double u,
-                                                double v, double& x, double& y, double& xu,
-                                                double& xv, double& yu, double& yv) {
+__device__ __noinline__ WorldToImageResult world_to_image_ext(int model,
+                                                              const double* __restrict__ p,
+                                                              double u, double v) {
+  WorldToImageResult r;
   if (JAC) {
     Dual2 X, Y;
     world_to_image_ext_t<Dual2>(model, p, Dual2{u, 1.0, 0.0}, Dual2{v, 0.0, 1.0}, X, Y);
-    x = X.v; xu = X.a; xv = X.b;
-    y = Y.v; yu = Y.a; yv = Y.b;
+    r.x = X.v; r.xu = X.a; r.xv = X.b;
+    r.y = Y.v; r.yu = Y.a; r.yv = Y.b;
   } else {
+    double x, y;
     world_to_image_ext_t<double>(model, p, u, v, x, y);
+    r.x = x; r.y = y;
+    r.xu = r.xv = r.yu = r.yv = 0.0;
   }
+  return r;
 }
 
 // CameraModel::WorldToImage (src/base/camera_models.h) and its 2x2 Jacobian d(x,y)/d(u,v).
-template <bool JAC>
+// EXT = false: models 0..4 only (the caller has dealt with the others)
+template <bool JAC, bool EXT = true>
 __device__ __forceinline__ void world_to_image(int model, const double* __restrict__ p, double u,
                                                double v, double& x, double& y, double& xu,
                                                double& xv, double& yu, double& yv) {
-  if (model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out-of-line
-    world_to_image_ext<JAC>(model, p, u, v, x, y, xu, xv, yu, yv);
+  if (EXT && model >= 5) {  // fisheye / FOV / full-OpenCV / thin-prism: out of line
+    const WorldToImageResult r = world_to_image_ext<JAC>(model, p, u, v);
+    x = r.x; y = r.y;
+    if (JAC) { xu = r.xu; xv = r.xv; yu = r.yu; yv = r.yv; }
     return;
   }
   switch (model) {
