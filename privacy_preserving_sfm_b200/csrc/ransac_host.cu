@@ -201,7 +201,10 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
   // cut into waves (next_wave_range) so that the pipeline has something to overlap.
   const size_t kWaveFloor = 1024;
   const size_t kWaveCap = 1u << 17;
-  const size_t kChunks = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", 4));
+  // (a call sharded over >= 4 GPUs keeps every plan whole: its scoring is too short to hide the
+  // next wave's solve, so a second wave would only add a solve latency and a collective)
+  const size_t kChunks =
+      (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_CHUNKS", shard.world >= 4 ? 1 : 4));
   const size_t kFirst = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_FIRST", 3));
   const size_t kGrowth = (size_t)std::max(1, ppsfm::tune_int("PPSFM_RANSAC_GROWTH", 100));
   // Hypotheses per warp of the solve kernel: as few as keep all warps resident at once (the
