@@ -184,9 +184,12 @@ typedef struct ppsfm_ba ppsfm_ba; /* a BA problem resident in HBM */
  *                  by AddPointToProblem :450-487); bit1..3 = tvec[0..2] constant
  *                  (config.ConstantTvec -> SubsetParameterization :425-432)
  *   point_const[p]: ParameterizePoints :530-542 (partial tracks, ConstantPoints)
- *   camera_model:  COLMAP ids 0 SIMPLE_PINHOLE, 1 PINHOLE, 2 SIMPLE_RADIAL, 3 RADIAL, 4 OPENCV
- *                  (src/base/camera_models.h:189-248); intrinsics are constant (refine_* = false,
- *                  the defaults of src/optim/bundle_adjustment.h:57-63). */
+ *   camera_model:  COLMAP ids 0 SIMPLE_PINHOLE, 1 PINHOLE, 2 SIMPLE_RADIAL, 3 RADIAL, 4 OPENCV,
+ *                  5 OPENCV_FISHEYE, 6 FULL_OPENCV, 7 FOV, 8 SIMPLE_RADIAL_FISHEYE,
+ *                  9 RADIAL_FISHEYE, 10 THIN_PRISM_FISHEYE (src/base/camera_models.h:189-248)
+ *   camera_params / camera_const: intrinsics are constant unless an options.refine_* flag is
+ *                  set and camera_const[c] == 0 (ParameterizeCameras :490-528); only then is
+ *                  camera_params written (Camera::Params() updated in place). */
 typedef struct {
   int32_t num_images;
   double* qvecs;               /* num_images x 4 (w,x,y,z) */
@@ -195,7 +198,7 @@ typedef struct {
   const int32_t* image_camera; /* index into cameras */
   int32_t num_cameras;
   const int32_t* camera_model;
-  const double* camera_params; /* num_cameras x 12, zero padded */
+  double* camera_params;       /* num_cameras x 12, zero padded */
   int32_t num_points;
   double* points;              /* num_points x 3 */
   const uint8_t* point_const;  /* may be NULL */
@@ -203,6 +206,7 @@ typedef struct {
   const int32_t* obs_image;
   const int32_t* obs_point;
   const double* obs_line;      /* num_obs x 3, ||(a,b)|| = 1 */
+  const uint8_t* camera_const; /* config.IsConstantCamera per camera; may be NULL (= none) */
 } ppsfm_ba_problem;
 
 /* BundleAdjustmentOptions (src/optim/bundle_adjustment.h:49-100) + the ceres::Solver::Options
@@ -223,6 +227,12 @@ typedef struct {
   double max_lm_diagonal;
   int32_t jacobi_scaling;
   int32_t num_threads; /* ignored (kept for layout parity with the CPU oracle) */
+  /* BundleAdjustmentOptions::refine_focal_length / refine_principal_point / refine_extra_params
+   * (src/optim/bundle_adjustment.h:57-63); all 0 = constant cameras, what the reference's mapper
+   * runs with (src/controllers/incremental_mapper.h:81-83) */
+  int32_t refine_focal_length;
+  int32_t refine_principal_point;
+  int32_t refine_extra_params;
 } ppsfm_ba_options;
 
 /* The fields of ceres::Solver::Summary the reference reads / prints
@@ -268,13 +278,22 @@ int ppsfm_ba_download(ppsfm_ba* ba, const ppsfm_ba_problem* problem);
 void ppsfm_ba_free(ppsfm_ba* ba);
 
 /* RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213, options pose.h:84-108) with constant
- * intrinsics.  Returns PPSFM_OK when summary.IsSolutionUsable(), else PPSFM_NO_SOLUTION. */
+ * intrinsics (the defaults).  Returns PPSFM_OK when summary.IsSolutionUsable(), else
+ * PPSFM_NO_SOLUTION.  The _ex variant takes AbsolutePoseRefinementOptions::refine_focal_length /
+ * refine_extra_params (pose.cc:149-183) and updates camera_params in place. */
 int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
                                           const double* lines, const double* points, size_t n,
                                           int camera_model, const double* camera_params,
                                           double gradient_tolerance, int max_num_iterations,
                                           double loss_function_scale, double* qvec, double* tvec,
                                           ppsfm_ba_summary* summary);
+int ppsfm_refine_absolute_pose_from_lines_ex(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
+                                             const double* lines, const double* points, size_t n,
+                                             int camera_model, double* camera_params,
+                                             int refine_focal_length, int refine_extra_params,
+                                             double gradient_tolerance, int max_num_iterations,
+                                             double loss_function_scale, double* qvec,
+                                             double* tvec, ppsfm_ba_summary* summary);
 
 /* Test hooks (parity tests only).
  * ppsfm_ba_linearize: per observation residual[2], tangent Jacobians jac_cam[2x6] (rotation via

@@ -20,8 +20,11 @@ from . import binding
 from .binding import PpsfmError, _dp, _u8p, _i32p
 
 BA_MAX_TRACE = 128
-CAMERA_MODEL_IDS = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4}
-CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8}
+# src/base/camera_models.h:189-248
+CAMERA_MODEL_IDS = {"SIMPLE_PINHOLE": 0, "PINHOLE": 1, "SIMPLE_RADIAL": 2, "RADIAL": 3, "OPENCV": 4,
+                    "OPENCV_FISHEYE": 5, "FULL_OPENCV": 6, "FOV": 7, "SIMPLE_RADIAL_FISHEYE": 8,
+                    "RADIAL_FISHEYE": 9, "THIN_PRISM_FISHEYE": 10}
+CAMERA_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12}
 
 
 class LossFunctionType(IntEnum):
@@ -35,7 +38,7 @@ class BaProblem(C.Structure):
                 ("image_camera", _i32p), ("num_cameras", C.c_int32), ("camera_model", _i32p),
                 ("camera_params", _dp), ("num_points", C.c_int32), ("points", _dp),
                 ("point_const", _u8p), ("num_obs", C.c_int64), ("obs_image", _i32p),
-                ("obs_point", _i32p), ("obs_line", _dp)]
+                ("obs_point", _i32p), ("obs_line", _dp), ("camera_const", _u8p)]
 
 
 class BaOptions(C.Structure):
@@ -47,7 +50,8 @@ class BaOptions(C.Structure):
                 ("max_trust_region_radius", C.c_double), ("min_trust_region_radius", C.c_double),
                 ("min_relative_decrease", C.c_double), ("min_lm_diagonal", C.c_double),
                 ("max_lm_diagonal", C.c_double), ("jacobi_scaling", C.c_int32),
-                ("num_threads", C.c_int32)]
+                ("num_threads", C.c_int32), ("refine_focal_length", C.c_int32),
+                ("refine_principal_point", C.c_int32), ("refine_extra_params", C.c_int32)]
 
 
 class BaSummary(C.Structure):
@@ -95,6 +99,9 @@ def _lib():
         L.ppsfm_refine_absolute_pose_from_lines.argtypes = [
             vp, _u8p, _dp, _dp, C.c_size_t, C.c_int, _dp, C.c_double, C.c_int, C.c_double, _dp,
             _dp, C.POINTER(BaSummary)]
+        L.ppsfm_refine_absolute_pose_from_lines_ex.argtypes = [
+            vp, _u8p, _dp, _dp, C.c_size_t, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
+            C.c_double, _dp, _dp, C.POINTER(BaSummary)]
         L.ppsfm_ba_linearize.argtypes = [vp, C.POINTER(BaProblem), C.POINTER(BaOptions), _dp, _dp,
                                          _dp, _dp]
         L.ppsfm_dense_cholesky_solve.argtypes = [vp, _dp, C.c_int, _dp, _dp]
@@ -116,7 +123,8 @@ class BaArrays:
     """Contiguous numpy buffers of a flattened BA problem + the ctypes struct over them."""
 
     def __init__(self, qvecs, tvecs, points, obs_image, obs_point, obs_line, camera_model,
-                 camera_params, image_camera=None, pose_flags=None, point_const=None, copy=True):
+                 camera_params, image_camera=None, pose_flags=None, point_const=None, copy=True,
+                 camera_const=None):
         f64 = dict(dtype=np.float64)
         self.qvecs = np.array(qvecs, **f64) if copy else np.ascontiguousarray(qvecs, **f64)
         self.tvecs = np.array(tvecs, **f64) if copy else np.ascontiguousarray(tvecs, **f64)
@@ -135,7 +143,12 @@ class BaArrays:
             pose_flags if pose_flags is not None else np.zeros(ni), dtype=np.uint8)
         self.point_const = np.ascontiguousarray(
             point_const if point_const is not None else np.zeros(npnt), dtype=np.uint8)
+        # config.IsConstantCamera per camera (only read when an options.refine_* flag is set)
+        self.camera_const = np.ascontiguousarray(
+            camera_const if camera_const is not None else np.zeros(self.camera_model.shape[0]),
+            dtype=np.uint8)
         p = BaProblem()
+        p.camera_const = self.camera_const.ctypes.data_as(_u8p)
         p.num_images = ni
         p.qvecs = self.qvecs.ctypes.data_as(_dp)
         p.tvecs = self.tvecs.ctypes.data_as(_dp)
@@ -391,9 +404,6 @@ class BundleAdjuster:
     def __init__(self, options, config, ctx=None):
         if not options.Check():
             raise PpsfmError("CHECK(options_.Check())")
-        if options.refine_focal_length or options.refine_principal_point or \
-                options.refine_extra_params:
-            raise PpsfmError("intrinsics refinement is not built yet (SURVEY.md §7: later option)")
         self._options, self._config = options, config
         self._ctx = ctx or binding.default_context()
         self._summary = None
@@ -406,13 +416,21 @@ class BundleAdjuster:
         if self._used:
             raise PpsfmError("Cannot use the same BundleAdjuster multiple times")
         self._used = True
-        arrays, img_ids, pt_ids = self._SetUp(reconstruction)
+        arrays, img_ids, pt_ids, cam_ids = self._SetUp(reconstruction)
         if arrays.obs_image.shape[0] == 0:  # problem_->NumResiduals() == 0 -> false
             return False
         o = self._options.solver_options
         o.loss_type = int(self._options.loss_function_type)
         o.loss_scale = self._options.loss_function_scale
+        # ParameterizeCameras (:490-528)
+        o.refine_focal_length = int(bool(self._options.refine_focal_length))
+        o.refine_principal_point = int(bool(self._options.refine_principal_point))
+        o.refine_extra_params = int(bool(self._options.refine_extra_params))
         ok, self._summary = solve_arrays(self._ctx, arrays, o)
+        if o.refine_focal_length or o.refine_principal_point or o.refine_extra_params:
+            for i, cid in enumerate(cam_ids):  # camera.ParamsData() updated in place
+                cam = reconstruction.Camera(cid)
+                cam.params[:] = arrays.camera_params[i, :len(cam.params)]
         # results in place (image.Qvec().data(), image.Tvec().data(), point3D.XYZ().data())
         for i, iid in enumerate(img_ids):
             img = reconstruction.Image(iid)
@@ -502,17 +520,22 @@ class BundleAdjuster:
         for pid in cfg.ConstantPoints():
             if pid in pt_index:
                 point_const[pt_index[pid]] = 1
+        cam_ids = [None] * len(cmodel)
+        for cid, i in cam_index.items():
+            cam_ids[i] = cid
         z = lambda rows, w: np.array(rows, dtype=np.float64).reshape(-1, w)
         arrays = BaArrays(z(qv, 4), z(tv, 3), z(pts, 3), oi, op, z(ol, 3),
                           cmodel if cmodel else [1], z(cparams, 12) if cparams else np.zeros((1, 12)),
-                          image_camera=icam, pose_flags=flags, point_const=point_const)
+                          image_camera=icam, pose_flags=flags, point_const=point_const,
+                          camera_const=[1 if cfg.IsConstantCamera(c) else 0 for c in cam_ids]
+                          if cam_ids else None)
         img_ids = [None] * len(qv)
         for iid, i in img_index.items():
             img_ids[i] = iid
         pt_ids = [None] * len(pts)
         for pid, i in pt_index.items():
             pt_ids[i] = pid
-        return arrays, img_ids, pt_ids
+        return arrays, img_ids, pt_ids, cam_ids
 
 
 class AbsolutePoseRefinementOptions:
@@ -538,8 +561,6 @@ def RefineAbsolutePoseFromLines(options, inlier_mask, lines2D, points3D, qvec, t
     reference's bool (summary.IsSolutionUsable())."""
     ctx = ctx or binding.default_context()
     options.Check()
-    if options.refine_focal_length or options.refine_extra_params:
-        raise PpsfmError("intrinsics refinement is not built yet")
     lines2D = np.ascontiguousarray(lines2D, dtype=np.float64)
     points3D = np.ascontiguousarray(points3D, dtype=np.float64)
     inlier_mask = np.ascontiguousarray(inlier_mask, dtype=np.uint8)
@@ -550,14 +571,19 @@ def RefineAbsolutePoseFromLines(options, inlier_mask, lines2D, points3D, qvec, t
     params = np.zeros(12)
     params[:len(camera.params)] = camera.params
     s = BaSummary()
-    rc = ctx._check(_lib().ppsfm_refine_absolute_pose_from_lines(
+    refine = bool(options.refine_focal_length or options.refine_extra_params)
+    rc = ctx._check(_lib().ppsfm_refine_absolute_pose_from_lines_ex(
         ctx._h, inlier_mask.ctypes.data_as(_u8p), lines2D.ctypes.data_as(_dp),
         points3D.ctypes.data_as(_dp), lines2D.shape[0], camera.ModelId(),
-        params.ctypes.data_as(_dp), options.gradient_tolerance, options.max_num_iterations,
-        options.loss_function_scale, q.ctypes.data_as(_dp), t.ctypes.data_as(_dp), C.byref(s)),
+        params.ctypes.data_as(_dp), int(bool(options.refine_focal_length)),
+        int(bool(options.refine_extra_params)), options.gradient_tolerance,
+        options.max_num_iterations, options.loss_function_scale, q.ctypes.data_as(_dp),
+        t.ctypes.data_as(_dp), C.byref(s)),
         allow_no_solution=True)
     qvec[:] = q
     tvec[:] = t
+    if refine:  # camera->ParamsData() is a parameter block of the problem (pose.cc:108, 138)
+        camera.params[:] = params[:len(camera.params)]
     RefineAbsolutePoseFromLines.last_summary = s
     return rc == binding.PPSFM_OK
 

@@ -292,15 +292,16 @@ inline bool RefineAbsolutePoseFromLines(const AbsolutePoseRefinementOptions& opt
   PPSFM_CHECK(inlier_mask.size() == lines2D.size());
   PPSFM_CHECK(lines2D.size() == points3D.size());
   options.Check();
-  PPSFM_CHECK(!options.refine_focal_length && !options.refine_extra_params);  // not built yet
   std::vector<double> l, p;
   internal::Flatten(lines2D, &l);
   internal::Flatten(points3D, &p);
   std::vector<uint8_t> mask(inlier_mask.begin(), inlier_mask.end());
   ppsfm_ba_summary summary;
-  const int rc = ppsfm_refine_absolute_pose_from_lines(
+  // (camera->ParamsData() is written only when a refine_* flag is set, pose.cc:149-183)
+  const int rc = ppsfm_refine_absolute_pose_from_lines_ex(
       ThreadContext(), mask.data(), l.data(), p.data(), lines2D.size(), camera->ModelId(),
-      camera->ParamsData(), options.gradient_tolerance, options.max_num_iterations,
+      camera->ParamsData(), options.refine_focal_length ? 1 : 0,
+      options.refine_extra_params ? 1 : 0, options.gradient_tolerance, options.max_num_iterations,
       options.loss_function_scale, qvec->data(), tvec->data(), &summary);
   internal::CheckRc(rc);
   if (options.print_summary)
@@ -708,9 +709,6 @@ class BundleAdjuster {
   BundleAdjuster(const BundleAdjustmentOptions& options, const BundleAdjustmentConfig& config)
       : options_(options), config_(config) {
     PPSFM_CHECK(options_.Check());
-    // intrinsics refinement is not built yet (defaults are false, bundle_adjustment.h:57-63)
-    PPSFM_CHECK(!options_.refine_focal_length && !options_.refine_principal_point &&
-                !options_.refine_extra_params);
   }
 
   const ppsfm_ba_summary& Summary() const { return summary_; }
@@ -737,7 +735,15 @@ class BundleAdjuster {
     pb.obs_image = obs_image_.data();
     pb.obs_point = obs_point_.data();
     pb.obs_line = obs_line_.data();
+    // ParameterizeCameras (bundle_adjustment.cc:490-528)
+    std::vector<uint8_t> camera_const(camera_ids_.size(), 0);
+    for (size_t c = 0; c < camera_ids_.size(); ++c)
+      camera_const[c] = config_.IsConstantCamera(camera_ids_[c]) ? 1 : 0;
+    pb.camera_const = camera_const.data();
     ppsfm_ba_options o = options_.solver_options;
+    o.refine_focal_length = options_.refine_focal_length ? 1 : 0;
+    o.refine_principal_point = options_.refine_principal_point ? 1 : 0;
+    o.refine_extra_params = options_.refine_extra_params ? 1 : 0;
     o.loss_type = (int32_t)options_.loss_function_type;
     o.loss_scale = options_.loss_function_scale;
     const int rc = ppsfm_ba_solve(ThreadContext(), &pb, &o, &summary_);
@@ -752,6 +758,12 @@ class BundleAdjuster {
       double* xyz = reconstruction->Point3D(point_ids_[i]).XYZ().data();
       for (int k = 0; k < 3; ++k) xyz[k] = points_[3 * i + k];
     }
+    if (o.refine_focal_length || o.refine_principal_point || o.refine_extra_params)
+      for (size_t c = 0; c < camera_ids_.size(); ++c) {  // camera.ParamsData() updated in place
+        auto& camera = reconstruction->Camera(camera_ids_[c]);
+        for (size_t k = 0; k < camera.NumParams() && k < 12; ++k)
+          camera.ParamsData()[k] = camera_params_[12 * c + k];
+      }
     if (options_.print_summary)
       std::printf("Bundle adjustment report: residuals %lld, iterations %d, cost %g -> %g\n",
                   (long long)summary_.num_residuals_reduced,
@@ -779,6 +791,7 @@ class BundleAdjuster {
     if (ct == camera_index_.end()) {
       auto& camera = rec->Camera(cid);
       ct = camera_index_.emplace(cid, (int)camera_model_.size()).first;
+      camera_ids_.push_back(cid);
       camera_model_.push_back(camera.ModelId());
       const size_t base = camera_params_.size();
       camera_params_.resize(base + 12, 0.0);
@@ -850,6 +863,7 @@ class BundleAdjuster {
   std::unordered_map<camera_t, int> camera_index_;
   std::unordered_map<point3D_t, int> point_index_;
   std::vector<image_t> image_ids_;
+  std::vector<camera_t> camera_ids_;
   std::vector<point3D_t> point_ids_;
   std::vector<double> qvecs_, tvecs_, points_, camera_params_, obs_line_;
   std::vector<uint8_t> pose_flags_, point_const_;

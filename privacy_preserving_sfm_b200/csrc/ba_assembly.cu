@@ -35,8 +35,10 @@ __global__ void asm_classify_kernel(BaRaw raw, int rank, int world, uint32_t* __
     const double n2 = l0 * l0 + l1 * l1;
     if (!(n2 > 0.999998 && n2 < 1.000002) && fabs(sqrt(n2) - 1.0) > 1e-6)
       atomicMin(&err[1], (unsigned long long)o);
+    // (bit 4 of the device copy of pose_flags: the image's camera has variable intrinsics)
     const bool cc = raw.pose_flags[ci] & 1, pc = raw.point_const[pi] != 0;
-    if (!(cc && pc)) {
+    const bool ic = raw.pose_flags[ci] & 16;
+    if (!(cc && pc && !ic)) {
       cam_used[ci] = 1;  // global property: identical on every rank
       if (world == 1) key = (uint32_t)pi;
       else if ((pi % world) == rank) key = (uint32_t)(pi / world);

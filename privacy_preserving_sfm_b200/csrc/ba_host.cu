@@ -32,6 +32,12 @@ struct BaState {
   int64_t num_obs_in = 0;
   double *q0 = nullptr, *t0 = nullptr, *X0 = nullptr;  // initial state (for reset)
   double* Xg = nullptr;              // sharded solve: whole-problem displacement buffer (download)
+  // intrinsics refinement: candidate parameters, initial parameters, overflow flag of the
+  // intrinsics Schur kernel, number of variable intrinsics
+  double *cam_params_n = nullptr, *img_params_n = nullptr;
+  double *cam_params0 = nullptr, *img_params0 = nullptr;
+  int* intr_overflow = nullptr;
+  int intr_eff = 0;
   std::vector<double> points_in;     // sharded solve: the caller's points as handed in
   PinBuf h_scalars;
   int64_t launches = 0;
@@ -74,6 +80,26 @@ cudaError_t Upload(BaState* st, T** p, const std::vector<T>& h) {
 }
 
 // allocation callback for build_schur_lists
+// Parameter groups of the camera models (FocalLengthIdxs / PrincipalPointIdxs / ExtraParamsIdxs,
+// src/base/camera_models.h:597-846) as bit masks over Camera::Params().
+const unsigned kFocalMask[11] = {0x1, 0x3, 0x1, 0x1, 0x3, 0x3, 0x3, 0x3, 0x1, 0x1, 0x3};
+const unsigned kPrincipalMask[11] = {0x6, 0xc, 0x6, 0x6, 0xc, 0xc, 0xc, 0xc, 0x6, 0x6, 0xc};
+const unsigned kExtraMask[11] = {0x0, 0x0, 0x8, 0x18, 0xf0, 0xf0, 0xff0, 0x10, 0x8, 0x18, 0xff0};
+const int kNumParams[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
+
+// BundleAdjuster::ParameterizeCameras (bundle_adjustment.cc:490-528): the variable parameters of
+// camera `cam` (0 = constant camera).
+unsigned VariableIntrinsics(const ppsfm_ba_problem* pb, const ppsfm_ba_options* opt, int cam) {
+  const int m = pb->camera_model[cam];
+  if (m < 0 || m > 10) return 0;
+  unsigned mask = 0;
+  if (opt->refine_focal_length) mask |= kFocalMask[m];
+  if (opt->refine_principal_point) mask |= kPrincipalMask[m];
+  if (opt->refine_extra_params) mask |= kExtraMask[m];
+  if (pb->camera_const && pb->camera_const[cam]) mask = 0;
+  return mask;
+}
+
 void* StateAlloc(void* state, size_t bytes) {
   char* p = nullptr;
   return DevAlloc(static_cast<BaState*>(state), &p, bytes) == cudaSuccess ? p : nullptr;
@@ -149,6 +175,14 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   if (pb->pose_flags) std::copy(pb->pose_flags, pb->pose_flags + C, flags_h.begin());
   if (pb->point_const)
     for (int i = 0; i < P_global; ++i) pconst_h[i] = pb->point_const[i] ? 1 : 0;
+  // images whose camera has variable intrinsics keep their residuals even with a constant pose
+  // and a constant point (bit 4 of the device copy of the flags)
+  std::vector<unsigned> intr_candidate(std::max(pb->num_cameras, 1), 0u);
+  for (int c = 0; c < pb->num_cameras; ++c) intr_candidate[c] = VariableIntrinsics(pb, opt, c);
+  for (int i = 0; i < C; ++i) {
+    flags_h[i] &= 0x0f;
+    if (intr_candidate[pb->image_camera[i]]) flags_h[i] |= 16;
+  }
   std::vector<void*> raw_tmp;
   auto raw_upload = [&](const void* src, size_t bytes) -> void* {
     void* p = nullptr;
@@ -206,7 +240,28 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
     if (img_model[i] >= 5) d.has_ext_models = 1;
     std::memcpy(&img_params[12 * (size_t)i], pb->camera_params + 12 * (size_t)cam, 12 * sizeof(double));
   }
-  d.NB = NB; d.n = 6 * NB; d.ld = chol_ld(6 * NB);
+  // intrinsics blocks: cameras of the images that are part of the problem, in image order
+  std::vector<int> cam_intr_block(std::max(pb->num_cameras, 1), -1), cam_nparams(std::max(pb->num_cameras, 1), 0);
+  std::vector<unsigned> intr_mask;
+  for (int c = 0; c < pb->num_cameras; ++c) {
+    const int m = pb->camera_model[c];
+    cam_nparams[c] = (m >= 0 && m <= 10) ? kNumParams[m] : 0;
+  }
+  for (int i = 0; i < C; ++i) {
+    const int cam = pb->image_camera[i];
+    if (cam_used[i] && intr_candidate[cam] && cam_intr_block[cam] < 0) {
+      cam_intr_block[cam] = (int)intr_mask.size();
+      intr_mask.push_back(intr_candidate[cam]);
+      st->intr_eff += __builtin_popcount(intr_candidate[cam]);
+    }
+  }
+  const int NCv = (int)intr_mask.size();
+  if (NCv > kMaxVarCams) {
+    BaFree(st);
+    return fail(ctx, PPSFM_ERR_INVALID, "%d cameras with variable intrinsics (limit %d)", NCv,
+                kMaxVarCams);
+  }
+  d.NB = NB; d.NCv = NCv; d.n = 6 * NB + kIntrW * NCv; d.ld = chol_ld(d.n);
   BA_TRY(Upload(st, &d.cam_block, cam_block));
   BA_TRY(ba_assemble_cameras(d, &StateAlloc, st, s));
   if (timing) {
@@ -248,9 +303,27 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.J, ba_j_doubles(K)));
   BA_TRY(DevAlloc(st, &d.cam_scale, 6 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.pt_scale, 3 * (size_t)P));
-  // U and g_c in ONE allocation: the sharded solve sums both over the ranks with one all-reduce
-  BA_TRY(DevAlloc(st, &d.U, 42 * (size_t)NB));
+  // U and g_c (and the intrinsics blocks U_ii, U_ic, g_i behind them) in ONE allocation: the
+  // sharded solve sums them over the ranks with one all-reduce
+  BA_TRY(DevAlloc(st, &d.U, 42 * (size_t)NB + intr_normal_doubles(NB, NCv)));
   d.gc = d.U + 36 * (size_t)NB;
+  if (NCv > 0) {
+    d.Uii = d.U + 42 * (size_t)NB;
+    d.Uic = d.Uii + (size_t)NCv * kIntrW * kIntrW;
+    d.gi = d.Uic + (size_t)NB * kIntrW * 6;
+    BA_TRY(Upload(st, &d.cam_intr_block, cam_intr_block));
+    BA_TRY(Upload(st, &d.intr_mask, intr_mask));
+    BA_TRY(Upload(st, &d.cam_nparams, cam_nparams));
+    BA_TRY(DevAlloc(st, &d.intr_scale, (size_t)NCv * kIntrW));
+    BA_TRY(DevAlloc(st, &d.Ji, 2 * (size_t)kIntrW * (size_t)std::max<int64_t>(K, 1)));
+    BA_TRY(DevAlloc(st, &st->cam_params_n, 12 * (size_t)pb->num_cameras));
+    BA_TRY(DevAlloc(st, &st->img_params_n, 12 * (size_t)std::max(C, 1)));
+    std::vector<double> cp0(pb->camera_params, pb->camera_params + 12 * (size_t)pb->num_cameras);
+    BA_TRY(Upload(st, &st->cam_params0, cp0));
+    BA_TRY(Upload(st, &st->img_params0, img_params));
+    BA_TRY(DevAlloc(st, &st->intr_overflow, 1));
+    BA_TRY(cudaMemsetAsync(st->intr_overflow, 0, sizeof(int), s));
+  }
   BA_TRY(DevAlloc(st, &d.Upart, 4 * 27 * (size_t)NB));
   BA_TRY(DevAlloc(st, &d.V, 6 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.gp, 3 * (size_t)P));
@@ -269,7 +342,7 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.dp, 3 * (size_t)P));
   BA_TRY(DevAlloc(st, &d.u, 2 * (size_t)K));
   BA_TRY(DevAlloc(st, &d.chol_status, 1));
-  BA_TRY(DevAlloc(st, &d.chol_work, chol_work_doubles(6 * NB)));
+  BA_TRY(DevAlloc(st, &d.chol_work, chol_work_doubles(d.n)));
   d.num_partials = (int)std::max<int64_t>((K + 255) / 256, (P + 255) / 256) + 1;
   BA_TRY(DevAlloc(st, &d.partials, 3 * (size_t)d.num_partials));
   BA_TRY(DevAlloc(st, &d.scalars, kNumScalars));
@@ -350,18 +423,22 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     }
     st->launches += launch_linearize(d, q, t, X, jac, loss, s);
     if (jac) PPSFM_CUDA(ctx, cudaEventRecord(st->lin_ev[2 * slot + 1], s));
+    if (jac) st->launches += launch_intr_jacobian(d, q, t, X, loss, s);
     return PPSFM_OK;
   };
   auto normal_equations = [&]() -> int {
     st->launches += launch_normal_equations(d, s);
+    st->launches += launch_intr_normal(d, s);
     if (st->world > 1) {  // cameras are replicated: U, g_c are sums over all ranks' observations
-      const int rc = AllReduceSum(st, d.U, 42 * (size_t)d.NB);  // U and g_c are contiguous
+      // (U, g_c and the intrinsics blocks are contiguous)
+      const int rc = AllReduceSum(st, d.U, 42 * (size_t)d.NB + intr_normal_doubles(d.NB, d.NCv));
       if (rc != PPSFM_OK) return rc;
     }
     return PPSFM_OK;
   };
   auto cost_and_gradient = [&](double* cost, double* gmax) -> int {
     st->launches += launch_gradient_max_norm(d, s);
+    st->launches += launch_intr_gradient(d, s);
     if (st->world > 1) {
       const int rc = CommAllReduceSumAndMax(st->ctx, d.scalars + kCost, 1, d.scalars + kGradMax, 1);
       if (rc != PPSFM_OK) return rc;
@@ -381,6 +458,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     for (uint8_t m : mask) eff += __builtin_popcount(m);
     for (uint8_t v : pv) eff += v ? 3 : 0;
   }
+  eff += st->intr_eff;
   sum->num_effective_parameters_reduced = eff;
 
   // unit scales, first linearisation
@@ -392,12 +470,14 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
                                     cudaMemcpyHostToDevice, s));
     PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
   }
+  st->launches += launch_intr_scales(d, false, s);
   int rc = linearize(d.q, d.t, d.X, true);
   if (rc != PPSFM_OK) return rc;
   rc = normal_equations();
   if (rc != PPSFM_OK) return rc;
   if (opt.jacobi_scaling) {
     st->launches += launch_jacobi_scales(d, s);
+    st->launches += launch_intr_scales(d, true, s);
     rc = linearize(d.q, d.t, d.X, true);
     if (rc != PPSFM_OK) return rc;
     rc = normal_equations();
@@ -432,6 +512,8 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[0], s));
     st->launches += launch_build_reduced_system(d, radius, opt.min_lm_diagonal,
                                                 opt.max_lm_diagonal, st->rank == 0, s);
+    st->launches += launch_intr_reduced_rows(d, radius, opt.min_lm_diagonal, opt.max_lm_diagonal,
+                                             st->rank == 0, st->intr_overflow, s);
     if (st->world > 1) {
       // rank 0 contributed blockdiag(U + D) and -g_c; every rank its points' Schur products
       // (only the lower triangle and the rhs row are referenced: pack, reduce half the bytes)
@@ -442,7 +524,10 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       st->launches += 2;
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[1], s));
-    int chol_failed = 0;
+    int chol_failed = 0, intr_overflow = 0;
+    if (d.NCv > 0)
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(&intr_overflow, st->intr_overflow, sizeof(int),
+                                      cudaMemcpyDeviceToHost, s));
     if (d.n > 0) {
       st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_work, d.chol_status, s);
       PPSFM_CUDA(ctx, cudaGetLastError());  // a refused launch must not read as "factorised"
@@ -451,8 +536,16 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[2], s));
     st->launches += launch_backsubstitute_and_update(d, st->rank == 0, s);
+    st->launches += launch_intr_update(d, st->cam_params_n, st->img_params_n, st->rank == 0, s);
     // candidate cost
-    st->launches += launch_linearize(d, d.qn, d.tn, d.Xn, false, loss, s);
+    if (d.NCv > 0) {
+      BaDev dn = d;  // the candidate intrinsics
+      dn.cam_params = st->cam_params_n;
+      dn.img_params = st->img_params_n;
+      st->launches += launch_linearize(dn, d.qn, d.tn, d.Xn, false, loss, s);
+    } else {
+      st->launches += launch_linearize(d, d.qn, d.tn, d.Xn, false, loss, s);
+    }
     if (st->world > 1) {
       // candidate cost, model cost change, step^2, x^2: four adjacent scalars, one all-reduce
       static_assert(kCost == 0 && kModelChange == 1 && kStepSq == 2 && kXSq == 3, "adjacent");
@@ -463,6 +556,9 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     rc = FetchScalars(st, &sc);
     if (rc != PPSFM_OK) return rc;
     solver_s += Secs(t_lin);
+    if (intr_overflow)
+      return fail(ctx, PPSFM_ERR_INVALID,
+                  "a point is seen by more distinct cameras with variable intrinsics than supported");
     {
       float m01 = 0, m12 = 0, m23 = 0;
       cudaEventElapsedTime(&m01, st->evp[0], st->evp[1]);
@@ -507,6 +603,10 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       std::swap(d.q, d.qn);
       std::swap(d.t, d.tn);
       std::swap(d.X, d.Xn);
+      if (d.NCv > 0) {
+        std::swap(d.cam_params, st->cam_params_n);
+        std::swap(d.img_params, st->img_params_n);
+      }
       rc = linearize(d.q, d.t, d.X, true);
       if (rc != PPSFM_OK) return rc;
       rc = normal_equations();
@@ -551,6 +651,9 @@ int BaDownload(BaState* st, const ppsfm_ba_problem* pb) {
   // poses of every image (constant ones come back unchanged); points owned by this rank
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->qvecs, d.q, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToHost, s));
   PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->tvecs, d.t, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToHost, s));
+  if (d.NCv > 0)  // Camera::Params() of the refined cameras (replicated on every rank)
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(pb->camera_params, d.cam_params,
+                                    sizeof(double) * 12 * d.num_cameras, cudaMemcpyDeviceToHost, s));
   if (st->world > 1) {
     // every rank moved only its own points (local index p = the caller's p * world + rank):
     // scatter the displacements into a zeroed whole-problem buffer and sum it over the ranks, so
@@ -578,6 +681,12 @@ int BaReset(BaState* st) {
   PPSFM_CUDA(ctx, cudaMemcpyAsync(d.q, st->q0, sizeof(double) * 4 * d.C, cudaMemcpyDeviceToDevice, s));
   PPSFM_CUDA(ctx, cudaMemcpyAsync(d.t, st->t0, sizeof(double) * 3 * d.C, cudaMemcpyDeviceToDevice, s));
   PPSFM_CUDA(ctx, cudaMemcpyAsync(d.X, st->X0, sizeof(double) * 3 * d.P, cudaMemcpyDeviceToDevice, s));
+  if (d.NCv > 0) {
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(d.cam_params, st->cam_params0,
+                                    sizeof(double) * 12 * d.num_cameras, cudaMemcpyDeviceToDevice, s));
+    PPSFM_CUDA(ctx, cudaMemcpyAsync(d.img_params, st->img_params0, sizeof(double) * 12 * d.C,
+                                    cudaMemcpyDeviceToDevice, s));
+  }
   PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
   return PPSFM_OK;
 }
@@ -615,6 +724,9 @@ void ppsfm_ba_options_default(ppsfm_ba_options* o) {
   o->max_lm_diagonal = 1e32;
   o->jacobi_scaling = 1;
   o->num_threads = -1;
+  o->refine_focal_length = 0;     // intrinsics constant: what the mapper of the reference runs
+  o->refine_principal_point = 0;  // with (controllers/incremental_mapper.h:81-83) and the default
+  o->refine_extra_params = 0;     // of the pose refinement (estimators/pose.h:84-101)
 }
 
 int ppsfm_ba_create(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
@@ -745,7 +857,8 @@ int ppsfm_ba_linearize(ppsfm_ctx* ctx, const ppsfm_ba_problem* problem,
       const int ci = problem->obs_image[o], pi = problem->obs_point[o];
       const bool cc = problem->pose_flags && (problem->pose_flags[ci] & 1);
       const bool pc = problem->point_const && problem->point_const[pi];
-      return !(cc && pc);
+      const bool ic = VariableIntrinsics(problem, options, problem->image_camera[ci]) != 0;
+      return !(cc && pc && !ic);
     };
     for (int64_t o = 0; o < O; ++o)
       if (kept(o)) pt_start[problem->obs_point[o] + 1]++;
@@ -810,14 +923,16 @@ int ppsfm_dense_cholesky_solve(ppsfm_ctx* ctx, const double* A, int n, const dou
   return rc;
 }
 
-// RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213) with constant intrinsics
-// (refine_focal_length = refine_extra_params = false, the defaults of pose.h:84-101).
-int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
-                                          const double* lines, const double* points, size_t n,
-                                          int camera_model, const double* camera_params,
-                                          double gradient_tolerance, int max_num_iterations,
-                                          double loss_function_scale, double* qvec, double* tvec,
-                                          ppsfm_ba_summary* summary) {
+// RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213).  refine_focal_length /
+// refine_extra_params select the variable groups of camera->Params() (pose.cc:149-183; the
+// principal point always stays fixed); camera_params is updated in place when one is set.
+int ppsfm_refine_absolute_pose_from_lines_ex(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
+                                             const double* lines, const double* points, size_t n,
+                                             int camera_model, double* camera_params,
+                                             int refine_focal_length, int refine_extra_params,
+                                             double gradient_tolerance, int max_num_iterations,
+                                             double loss_function_scale, double* qvec,
+                                             double* tvec, ppsfm_ba_summary* summary) {
   if (!ctx || !inlier_mask || !lines || !points || !qvec || !tvec || !camera_params)
     return fail(ctx, PPSFM_ERR_INVALID, "null argument");
   if (camera_model < 0 || camera_model > 10)
@@ -848,14 +963,15 @@ int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_
   uint8_t flags = 0;
   int32_t icam = 0, model = camera_model;
   double params[12] = {0};
-  const int nparams[11] = {3, 4, 4, 5, 8, 8, 12, 5, 4, 5, 12};
-  for (int k = 0; k < nparams[camera_model]; ++k) params[k] = camera_params[k];
+  const int np_model = kNumParams[camera_model];
+  for (int k = 0; k < np_model; ++k) params[k] = camera_params[k];
   ppsfm_ba_problem pb;
   pb.num_images = 1; pb.qvecs = qvec; pb.tvecs = tvec; pb.pose_flags = &flags;
   pb.image_camera = &icam; pb.num_cameras = 1; pb.camera_model = &model;
   pb.camera_params = params; pb.num_points = np; pb.points = pts.data();
   pb.point_const = pc.data(); pb.num_obs = np; pb.obs_image = oi.data();
   pb.obs_point = op.data(); pb.obs_line = ol.data();
+  pb.camera_const = nullptr;
   ppsfm_ba_options o;
   ppsfm_ba_options_default(&o);
   o.loss_type = 2;  // ceres::CauchyLoss(options.loss_function_scale)  (pose.cc:106-107)
@@ -864,9 +980,31 @@ int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_
   o.max_num_iterations = max_num_iterations;
   o.function_tolerance = 1e-6;   // ceres::Solver::Options defaults: pose.cc:187-190 overrides
   o.parameter_tolerance = 1e-8;  // only gradient_tolerance / max_num_iterations / solver type
+  o.refine_focal_length = refine_focal_length ? 1 : 0;
+  o.refine_extra_params = refine_extra_params ? 1 : 0;
   const int rc = ppsfm_ba_solve(ctx, &pb, &o, sum);
   if (rc != PPSFM_OK) return rc;
+  if (o.refine_focal_length || o.refine_extra_params)
+    for (int k = 0; k < np_model; ++k) camera_params[k] = params[k];
   return sum->termination_type != 2 ? PPSFM_OK : PPSFM_NO_SOLUTION;  // IsSolutionUsable()
+}
+
+// The same with constant intrinsics (refine_focal_length = refine_extra_params = false, the
+// defaults of pose.h:84-101).
+int ppsfm_refine_absolute_pose_from_lines(ppsfm_ctx* ctx, const uint8_t* inlier_mask,
+                                          const double* lines, const double* points, size_t n,
+                                          int camera_model, const double* camera_params,
+                                          double gradient_tolerance, int max_num_iterations,
+                                          double loss_function_scale, double* qvec, double* tvec,
+                                          ppsfm_ba_summary* summary) {
+  if (!camera_params) return fail(ctx, PPSFM_ERR_INVALID, "null argument");
+  double params[12] = {0};
+  if (camera_model >= 0 && camera_model <= 10)
+    for (int k = 0; k < kNumParams[camera_model]; ++k) params[k] = camera_params[k];
+  return ppsfm_refine_absolute_pose_from_lines_ex(ctx, inlier_mask, lines, points, n, camera_model,
+                                                  params, 0, 0, gradient_tolerance,
+                                                  max_num_iterations, loss_function_scale, qvec,
+                                                  tvec, summary);
 }
 
 }  // extern "C"

@@ -742,6 +742,7 @@ int launch_backsubstitute_and_update(const BaDev& d, bool count_camera_norms, cu
   if (pblocks > 0 && oblocks > 0) {
     cudaMemcpyAsync(d.dp, d.gp, sizeof(double) * 3 * (size_t)d.P, cudaMemcpyDeviceToDevice, s);
     ba_backsub_accum_kernel<<<oblocks, kThreads, 0, s>>>(d);
+    n += launch_intr_backsub(d, s);  // (variable intrinsics only)
     ba_point_step_kernel<<<pblocks, kThreads, 0, s>>>(d, d.partials, d.num_partials);
     // step / x norms accumulate on top of the camera part written by ba_camera_update_kernel
     reduce_partials_kernel<<<1, 1024, 0, s>>>(d.partials + d.num_partials, pblocks,

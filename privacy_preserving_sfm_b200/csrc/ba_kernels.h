@@ -29,6 +29,16 @@ struct BaDev {
   int* cam_model = nullptr;     // [num_cameras]
   double* cam_params = nullptr; // [num_cameras][12]
   uint8_t* pt_var = nullptr;    // [P]
+  // intrinsics refinement (ba_intrinsics.cu); NCv = 0: every camera constant, nothing below is used
+  int NCv = 0;                      // cameras with at least one variable parameter
+  int* cam_intr_block = nullptr;    // [num_cameras] intrinsics block of a camera or -1
+  unsigned* intr_mask = nullptr;    // [NCv] bit a = parameter a is variable
+  int* cam_nparams = nullptr;       // [num_cameras] CameraModel::kNumParams
+  double* intr_scale = nullptr;     // [NCv][12] Jacobi scales
+  double* Ji = nullptr;             // [K][2][12] d r / d params (scaled, loss-corrected, masked)
+  double* Uii = nullptr;            // [NCv][12][12]   (Uii | Uic | gi are contiguous behind U | gc)
+  double* Uic = nullptr;            // [NB][12][6] coupling with the pose block of the image
+  double* gi = nullptr;             // [NCv][12]
   // state
   double* q = nullptr;   // [C][4]
   double* t = nullptr;   // [C][3]
@@ -94,6 +104,13 @@ cudaError_t ba_assemble_points(BaDev& d, const BaRaw& raw, int rank, int world,
 cudaError_t ba_assemble_cameras(BaDev& d, void* (*alloc)(void*, size_t), void* alloc_ctx,
                                 cudaStream_t s);
 
+// reduced-system width of one intrinsics block (the widest models have 12 parameters)
+constexpr int kIntrW = 12;
+constexpr int kMaxVarCams = 64;
+inline size_t intr_normal_doubles(int NB, int NCv) {
+  return (size_t)NCv * kIntrW * kIntrW + (size_t)NB * kIntrW * 6 + (size_t)NCv * kIntrW;
+}
+
 constexpr int kJFields = 20;
 __host__ __device__ inline size_t ba_jidx(int field, int64_t k) {
   return ((size_t)(k >> 8) * kJFields + (size_t)field) * 256 + (size_t)(k & 255);
@@ -138,5 +155,20 @@ void launch_axpby(double* out, const double* a, const double* b, double beta, si
                   cudaStream_t s);
 // max |x - Plus(x, -g)| over all blocks -> scalars[kGradMax]
 int launch_gradient_max_norm(const BaDev& d, cudaStream_t s);
+
+// Intrinsics refinement (ba_intrinsics.cu); every launcher is a no-op returning 0 when d.NCv == 0.
+int launch_intr_jacobian(const BaDev& d, const double* q, const double* t, const double* X,
+                         BaLoss loss, cudaStream_t s);
+int launch_intr_normal(const BaDev& d, cudaStream_t s);           // Uii, Uic, gi (zeroed first)
+int launch_intr_scales(const BaDev& d, bool jacobi, cudaStream_t s);
+// intrinsics rows of S (after launch_build_reduced_system); *overflow = 1 if a point sees more
+// distinct variable cameras than the kernel holds
+int launch_intr_reduced_rows(const BaDev& d, double radius, double min_diag, double max_diag,
+                             bool include_camera_terms, int* overflow, cudaStream_t s);
+int launch_intr_backsub(const BaDev& d, cudaStream_t s);          // u += J_i d_i, acc_p += J_p^T (J_i d_i)
+// candidate parameters (per camera and expanded per image); adds to scalars[kStepSq / kXSq]
+int launch_intr_update(const BaDev& d, double* cam_params_n, double* img_params_n,
+                       bool count_norms, cudaStream_t s);
+int launch_intr_gradient(const BaDev& d, cudaStream_t s);
 
 }  // namespace ppsfm

@@ -279,7 +279,9 @@ static int RunPose(const char* in, const char* out) {
   return 0;
 }
 
-static int RunBA(const char* in, const char* out) {
+// refine: ParameterizeCameras with refine_extra_params on a SIMPLE_RADIAL camera (id 1) next to a
+// second, constant camera (id 2, config.SetConstantCamera) that the odd images use
+static int RunBA(const char* in, const char* out, bool refine = false) {
   FILE* f = fopen(in, "rb");
   if (!f) return 2;
   const int C = (int)ReadI64(f), P = (int)ReadI64(f);
@@ -290,8 +292,14 @@ static int RunBA(const char* in, const char* out) {
   fclose(f);
   TestReconstruction rec;
   rec.cameras[1].params = cam;
+  if (refine) {
+    rec.cameras[1].model_id = 2;
+    rec.cameras[1].params = {cam[0], cam[2], cam[3], 0.08};
+    rec.cameras[2] = rec.cameras[1];
+  }
   for (int i = 0; i < C; ++i) {
     TestImage& im = rec.images[i + 1];
+    if (refine) im.camera_id = 1 + i % 2;
     im.qvec = Vector4d{q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]};
     im.tvec = Vector3d{t[3 * i], t[3 * i + 1], t[3 * i + 2]};
   }
@@ -304,10 +312,12 @@ static int RunBA(const char* in, const char* out) {
   }
   // IncrementalMapper::AdjustGlobalBundle (src/sfm/incremental_mapper.cc:893-939)
   BundleAdjustmentOptions options;
-  options.solver_options.max_num_iterations = 20;
+  options.solver_options.max_num_iterations = refine ? 6 : 20;
   options.solver_options.gradient_tolerance = 1e-4;
   options.print_summary = false;
+  options.refine_extra_params = refine;
   BundleAdjustmentConfig config;
+  if (refine) config.SetConstantCamera(2);
   for (int i = 0; i < C; ++i) config.AddImage(i + 1);
   config.SetConstantPose(1);
   config.SetConstantTvec(2, {0});
@@ -322,6 +332,10 @@ static int RunBA(const char* in, const char* out) {
   for (int i = 0; i < C; ++i) fwrite(rec.images[i + 1].qvec.data(), sizeof(double), 4, g);
   for (int i = 0; i < C; ++i) fwrite(rec.images[i + 1].tvec.data(), sizeof(double), 3, g);
   for (int p = 0; p < P; ++p) fwrite(rec.points[p + 100].xyz.data(), sizeof(double), 3, g);
+  if (refine) {
+    fwrite(rec.cameras[1].params.data(), sizeof(double), 4, g);
+    fwrite(rec.cameras[2].params.data(), sizeof(double), 4, g);
+  }
   fclose(g);
   return 0;
 }
@@ -330,6 +344,7 @@ int main(int argc, char** argv) {
   if (argc != 4) return 1;
   if (std::string(argv[1]) == "pose") return RunPose(argv[2], argv[3]);
   if (std::string(argv[1]) == "ba") return RunBA(argv[2], argv[3]);
+  if (std::string(argv[1]) == "ba_refine") return RunBA(argv[2], argv[3], true);
   if (std::string(argv[1]) == "filter") return RunFilter(argv[2], argv[3], false);
   if (std::string(argv[1]) == "depth") return RunFilter(argv[2], argv[3], true);
   if (std::string(argv[1]) == "tri") return RunTri(argv[2], argv[3]);

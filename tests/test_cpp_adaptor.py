@@ -86,6 +86,45 @@ def test_adaptor_bundle_adjuster_matches_oracle(oracle, tmp_path):
     assert np.abs(X - b.points).max() < 1e-7
 
 
+@pytest.mark.gpu
+def test_adaptor_bundle_adjuster_refines_intrinsics(oracle, tmp_path):
+    """BundleAdjustmentOptions::refine_extra_params + config.SetConstantCamera through the C++
+    adaptor (ParameterizeCameras, bundle_adjustment.cc:490-528): camera.ParamsData() of the
+    variable camera is updated in place, the constant camera stays."""
+    exe = _build()
+    sc = S.make_ba_scene(num_cams=7, num_points=200, obs_per_point=4, seed=81, noise_px=2.0)
+    fin, fout = str(tmp_path / "in.bin"), str(tmp_path / "out.bin")
+    with open(fin, "wb") as f:
+        np.array([7, 200, len(sc["obs_cam"])], dtype=np.int64).tofile(f)
+        for a in (sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"].astype(np.float64),
+                  sc["obs_pt"].astype(np.float64), sc["obs_line"], sc["cam_params"]):
+            np.ascontiguousarray(a, dtype=np.float64).tofile(f)
+    subprocess.check_call([exe, "ba_refine", fin, fout])
+    out = np.fromfile(fout, dtype=np.float64)
+    ok, c0, c1, iters = out[:4]
+    q = out[4:4 + 28].reshape(7, 4)
+    t = out[32:32 + 21].reshape(7, 3)
+    X = out[53:53 + 600].reshape(200, 3)
+    cams = out[653:661].reshape(2, 4)
+    flags = np.zeros(7, np.uint8)
+    flags[0], flags[1] = 1, 2
+    cp = sc["cam_params"]
+    prm = [cp[0], cp[2], cp[3], 0.08]
+    b = oracle.BaArrays(sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                        sc["obs_line"], [2, 2], [prm, prm], image_camera=np.arange(7) % 2,
+                        pose_flags=flags, camera_const=[0, 1])
+    ok2, s2 = oracle.ba_solve(b, oracle.ba_default_options(
+        num_threads=1, max_num_iterations=6, gradient_tolerance=1e-4, refine_extra_params=1))
+    assert bool(ok) and ok2
+    assert abs(c1 - s2.final_cost) <= 1e-8 * s2.final_cost
+    assert int(iters) == s2.num_successful_steps + s2.num_unsuccessful_steps
+    assert np.abs(q - b.qvecs).max() < 1e-7 and np.abs(t - b.tvecs).max() < 1e-7
+    assert np.abs(X - b.points).max() < 1e-6
+    assert np.array_equal(cams[1], prm) and cams[0, 3] != 0.08
+    assert np.array_equal(cams[0, :3], prm[:3])
+    assert abs(cams[0, 3] - b.camera_params[0, 3]) <= 1e-6 * max(1e-3, abs(b.camera_params[0, 3]))
+
+
 def _scene_file(tmp_path, sc, aligned=None):
     fin = str(tmp_path / "scene.bin")
     with open(fin, "wb") as f:
