@@ -57,6 +57,20 @@ else:
     np.save(os.path.join(sys.argv[2], f"X{{rank}}.npy"), arr.points)
     np.save(os.path.join(sys.argv[2], f"c{{rank}}.npy"),
             np.array([s.initial_cost, s.final_cost, s.num_successful_steps, s.num_unsuccessful_steps]))
+    # intrinsics refinement, sharded: the intrinsics blocks are replicated like the pose blocks
+    sn = S.make_ba_scene(num_cams=9, num_points=401, obs_per_point=5, seed=7, noise_px=2.0)
+    prm = [[1000.0, 500, 500, 0.08], [1000.0, 500, 500, 0.05]]
+    ai = ba.BaArrays(sn["qvecs"], sn["tvecs"], sn["points"], sn["obs_cam"], sn["obs_pt"],
+                     sn["obs_line"], [2, 2], prm, image_camera=np.arange(9) % 2, pose_flags=flags,
+                     point_const=pc)
+    ok, si = ba.solve_arrays(ctx, ai, ba.default_solver_options(max_num_iterations=6,
+                                                                refine_extra_params=1))
+    np.save(os.path.join(sys.argv[2], f"iq{{rank}}.npy"), ai.qvecs)
+    np.save(os.path.join(sys.argv[2], f"iX{{rank}}.npy"), ai.points)
+    np.save(os.path.join(sys.argv[2], f"ip{{rank}}.npy"), ai.camera_params)
+    np.save(os.path.join(sys.argv[2], f"ic{{rank}}.npy"),
+            np.array([si.initial_cost, si.final_cost, si.num_successful_steps,
+                      si.num_unsuccessful_steps]))
     dist.barrier()
     if rank == 0:
         print("NCCL_OK")
@@ -211,3 +225,21 @@ def test_sharded_ba_matches_single_gpu(tmp_path, ctx):
         assert np.abs(np.load(out / f"q{rank}.npy") - arr.qvecs).max() < 1e-8
         assert np.abs(np.load(out / f"t{rank}.npy") - arr.tvecs).max() < 1e-8
         assert np.abs(np.load(out / f"X{rank}.npy") - arr.points).max() < 1e-7
+    # the sharded solve with intrinsics refinement (two variable SIMPLE_RADIAL cameras)
+    sn = S.make_ba_scene(num_cams=9, num_points=401, obs_per_point=5, seed=7, noise_px=2.0)
+    prm = [[1000.0, 500, 500, 0.08], [1000.0, 500, 500, 0.05]]
+    ai = ba.BaArrays(sn["qvecs"], sn["tvecs"], sn["points"], sn["obs_cam"], sn["obs_pt"],
+                     sn["obs_line"], [2, 2], prm, image_camera=np.arange(9) % 2, pose_flags=flags,
+                     point_const=pc)
+    ok, si = ba.solve_arrays(ctx, ai, ba.default_solver_options(max_num_iterations=6,
+                                                                refine_extra_params=1))
+    assert ai.camera_params[0, 3] != 0.08 and ai.camera_params[1, 3] != 0.05
+    for rank in range(2):
+        c = np.load(out / f"ic{rank}.npy")
+        assert abs(c[0] - si.initial_cost) <= 1e-12 * si.initial_cost
+        assert abs(c[1] - si.final_cost) <= 1e-8 * si.final_cost
+        assert (int(c[2]), int(c[3])) == (si.num_successful_steps, si.num_unsuccessful_steps)
+        pr = np.load(out / f"ip{rank}.npy")
+        assert (np.abs(pr - ai.camera_params) / np.maximum(np.abs(ai.camera_params), 1e-3)).max() < 1e-6
+        assert np.abs(np.load(out / f"iq{rank}.npy") - ai.qvecs).max() < 1e-7
+        assert np.abs(np.load(out / f"iX{rank}.npy") - ai.points).max() < 1e-6
