@@ -376,7 +376,7 @@ typedef struct ppsfm_filter_problem {
   const double* tvecs;           /* [num_images][3] */
   const int32_t* image_camera;   /* [num_images] */
   int32_t num_cameras;
-  const int32_t* camera_model;   /* COLMAP model id (0..4) */
+  const int32_t* camera_model;   /* COLMAP model id (0..10) */
   const double* camera_params;   /* [num_cameras][12] */
   const int32_t* camera_width;   /* Camera::Width() */
   const int32_t* camera_height;
