@@ -43,7 +43,9 @@ constexpr int kKS = 36;  // row stride (doubles) of a 64x32 chunk in shared memo
 constexpr int kStages = 3;
 constexpr int kStageDoubles = 64 * kKS;
 constexpr int kFactorSmem = kStages * 2 * kStageDoubles * (int)sizeof(double);  // 110 592 B
-static_assert(3 * 64 * kCS * (int)sizeof(double) <= kFactorSmem, "walker needs three tiles");
+// the walker: three tiles, then 8 x (8x8) block inverses and 4 x (8x8) scratch blocks
+constexpr int kWalkerInv = 3 * 64 * kCS;
+static_assert((kWalkerInv + 12 * 64) * (int)sizeof(double) <= kFactorSmem, "walker's shared memory");
 
 // ---- PTX helpers ---------------------------------------------------------------------------
 __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
@@ -60,6 +62,9 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   return v;
 }
 __device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ void st_relaxed(int* p, int v) {
+  asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ void st_release(int* p, int v) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
@@ -85,10 +90,16 @@ __device__ __forceinline__ double ld_cg(const double* p) {
 // warp shuffle of a double without the convergence bookkeeping nvcc adds around __shfl_sync in
 // warp-specialised code
 __device__ __forceinline__ double shfl_d(double v, int src) {
-  int lo = __double2loint(v), hi = __double2hiint(v);
-  asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(lo) : "r"(src));
-  asm volatile("shfl.sync.idx.b32 %0, %0, %1, 0x1f, 0xffffffff;" : "+r"(hi) : "r"(src));
-  return __hiloint2double(hi, lo);
+  double out;  // (one asm block: ptxas shuffles the halves in place in the result's register pair)
+  asm volatile(
+      "{ .reg .b32 lo, hi;\n"
+      "  mov.b64 {lo, hi}, %1;\n"
+      "  shfl.sync.idx.b32 lo, lo, %2, 0x1f, 0xffffffff;\n"
+      "  shfl.sync.idx.b32 hi, hi, %2, 0x1f, 0xffffffff;\n"
+      "  mov.b64 %0, {lo, hi}; }"
+      : "=d"(out)
+      : "d"(v), "r"(src));
+  return out;
 }
 
 // 1 / x to full double precision without the IEEE division sequence: the 20-bit hardware seed
@@ -104,6 +115,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
   r = fma(r, e, r);
   return r;
 }
+
+// tile t of a lower triangle of 8x8 blocks, row-major ((0,0), (1,0), (1,1), (2,0), ...): row << 4 | col
+__constant__ unsigned char kTriRow[28] = {
+    0x00, 0x10, 0x11, 0x20, 0x21, 0x22, 0x30, 0x31, 0x32, 0x33, 0x40, 0x41, 0x42, 0x43,
+    0x44, 0x50, 0x51, 0x52, 0x53, 0x54, 0x55, 0x60, 0x61, 0x62, 0x63, 0x64, 0x65, 0x66};
 
 // (optional per-tile event trace: PPSFM_CHOL_TRACE=<file>, 16 timestamp slots per tile)
 __device__ __forceinline__ unsigned long long global_ns() {
@@ -147,16 +163,22 @@ __device__ __forceinline__ void wait_flag(const int* f) {
 }
 
 // ------------------------------------------------------------------------------------------
-// 8x8 Cholesky of the diagonal sub-block at (k1, k1) of the tile in shared memory, by ONE warp.
+// 8x8 Cholesky of the diagonal sub-block at (k1, k1) of the tile in shared memory, by ONE warp,
+// together with the inverse of its factor.
 // The symmetric block is spread over the warp, two elements per lane: lane (r, c) = (lane >> 3,
 // lane & 7) holds A[r][c] and A[r+4][c].  A pivot step then needs only four shuffles (pivot,
 // row element a_jc, column elements a_rj and a_(r+4)j) and two FMAs per lane, so the warp's
 // instruction stream stays far below the length of the dependency chain
 // shuffle -> reciprocal -> multiply -> FMA (~110 cycles per pivot; measured on B200: DFMA 8,
 // SHFL.64 26, reciprocal 58 cycles).  Square roots are taken once, after the eight steps.
-// Writes L (lower) back, and rdiag[k1 + j] = 1 / l_jj.
+// The same elimination is applied to an identity block held the same way (one more shuffle, a
+// multiply and two predicated FMAs per pivot, none of them on the chain): A = L_u D L_u^T leaves
+// L_u^-1 there, and inv(L) = D^-1/2 L_u^-1.  The panel below the block is then ONE small matrix
+// product on the tensor cores instead of an eight-step substitution per row, and the 16x16
+// inverses of the tile need no 8x8 substitutions either.
+// Writes L (lower) to Cs and inv(L) (lower, zeros above the diagonal) to iv (8 x 8, row-major).
 // ------------------------------------------------------------------------------------------
-__device__ __forceinline__ bool factor8(double* Cs, int k1, double* rdiag, int lane) {
+__device__ __forceinline__ bool factor8(double* Cs, int k1, double* iv, int lane) {
   const int r = lane >> 3, c = lane & 7;
   double e0, e1;
   {
@@ -165,40 +187,55 @@ __device__ __forceinline__ bool factor8(double* Cs, int k1, double* rdiag, int l
     e0 = Cs[(k1 + r0) * kCS + k1 + c0];
     e1 = Cs[(k1 + r1) * kCS + k1 + c1];
   }
+  double i0 = (r == c) ? 1.0 : 0.0, i1 = (r + 4 == c) ? 1.0 : 0.0;  // the identity, same layout
   __syncwarp();
-  bool bad = false;
-  double l0 = 0.0, l1 = 0.0, pv = 1.0;  // column c of the factor (unscaled) and its pivot
+  // The warp is alone on its scheduler while it factors, so the step is bound by its instruction
+  // count as much as by the chain: columns <= j are simply left alone (their lanes then end up
+  // holding the unscaled factor column, no copies), and non-positive pivots are detected once, at
+  // the end (they turn the later pivots into NaN).
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int jl = (j & 3) << 3;
     const double src = (j < 4) ? e0 : e1;  // row j lives in slot j >> 2 of lanes (j & 3, *)
-    double piv = shfl_d(src, jl | j);
+    const double isrc = (j < 4) ? i0 : i1;
+    const double piv = shfl_d(src, jl | j);
     const double u = shfl_d(src, jl | c);          // a_jc
     const double t0 = shfl_d(e0, (r << 3) | j);    // a_rj
     const double t1 = shfl_d(e1, (r << 3) | j);    // a_(r+4)j
-    bad = bad || !(piv > 0.0);
-    piv = (piv > 0.0) ? piv : 1.0;
-    if (c == j) {
-      l0 = e0;
-      l1 = e1;
-      pv = piv;
-    }
-    const double sc = u * fast_rcp(piv);
+    const double ij = shfl_d(isrc, jl | c);        // row j of the inverse so far
+    const double rp = fast_rcp(piv);
+    const double sc = (c > j) ? u * rp : 0.0;
     e0 -= t0 * sc;
     e1 -= t1 * sc;
+    const double si = ij * rp;
+    if (r > j) i0 -= t0 * si;      // rows <= j of the inverse are final
+    if (r + 4 > j) i1 -= t1 * si;
   }
+  // pivot of this lane's column: element (c, c), slot c >> 2 of lane (c & 3, c)
+  const double p0 = shfl_d(e0, ((c & 3) << 3) | c), p1 = shfl_d(e1, ((c & 3) << 3) | c);
+  const double pv = (c < 4) ? p0 : p1;
+  const bool bad = __any_sync(0xffffffffu, !(pv > 0.0));
+  const double l0 = e0, l1 = e1;
   const double rs = rsqrt(pv);
+  const double rs0 = shfl_d(rs, r), rs1 = shfl_d(rs, r + 4);  // lanes 0..7 hold columns 0..7
   if (r >= c) Cs[(k1 + r) * kCS + k1 + c] = l0 * rs;
   Cs[(k1 + r + 4) * kCS + k1 + c] = l1 * rs;  // r + 4 >= c for the rows that matter; the
-  if (r == 0) rdiag[k1 + c] = rs;             // entries above the diagonal are never read
+                                              // entries above the diagonal are never read
+  iv[8 * r + c] = i0 * rs0;
+  iv[8 * (r + 4) + c] = i1 * rs1;
   return bad;
 }
 
 // ------------------------------------------------------------------------------------------
 // In-place factorisation of the 64x64 tile in Cs (lower triangle valid): L overwrites the lower
-// triangle, the inverses of the four 16x16 diagonal sub-blocks go to the diagonal blocks of Tm.
-// Eight rounds: 8x8 factor (warp 0) -> panel rows by forward substitution -> trailing update on
-// the tensor cores.  All 256 threads call it.
+// triangle, the inverses of the four 16x16 diagonal sub-blocks go to the diagonal blocks of Tm
+// (written only at the very end).  Eight rounds: 8x8 factor + inverse (warp 0) -> panel
+// X = A inv(L_8)^T and trailing update, both on the tensor cores.  All 256 threads call it.
+// Iv: 12 x 64 doubles of scratch (the 8x8 inverses and the 16x16 assembly).
+// Xd (optional): the tile still lacks the update C -= Xd Xd^T in its column blocks >= 2 (the
+// caller applied column blocks 0 and 1); column block b + 2 gets it in round b, by the warps that
+// wait for warp 0's factor step anyway, so that only 15 of the 36 blocks of that update are on
+// the walker's dependency chain.  Xd (stride kCS) may be Tm.
 // ------------------------------------------------------------------------------------------
 // 64x64 tile global (leading dimension ld) -> shared (stride kCS), asynchronously
 __device__ __forceinline__ void tile_prefetch(double* dst, const double* src, int ld) {
@@ -218,10 +255,17 @@ struct PrefetchHook {
   const double* src = nullptr;
   int ld = 0;
   bool issued = false;
+  // a second flag that is only WATCHED (the tile that follows into the same buffer later):
+  // *seen2 is set once it is up, so that the caller need not poll global memory on its own path
+  const int* flag2 = nullptr;
+  int* seen2 = nullptr;
 };
 
-__device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int* s_bad,
-                                     PrefetchHook* hook) {
+// tr (optional): trace slots 8..14 of the diagonal tile (after the first 8x8 factor, after the
+// panel / the update of round 0, after rounds 3 and 6, after the 8x8 inverses, at the end)
+__device__ __noinline__ void potrf64(double* Cs, double* Tm, double* Iv, const double* Xd,
+                                     int* s_bad, PrefetchHook* hook,
+                                     unsigned long long* tr = nullptr) {
   __shared__ int s_hook;
   const int tid = threadIdx.x, lane = tid & 31;
   // warp index broadcast from lane 0: the compiler then knows the warp-specialised branches
@@ -229,15 +273,17 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int*
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int g = lane >> 2, q = lane & 3;  // mma fragment coordinates
   if (warp == 0) {
-    const bool bad = factor8(Cs, 0, rdiag, lane);
+    const bool bad = factor8(Cs, 0, Iv, lane);
     if (bad && lane == 0) *s_bad = 1;
   }
   const bool want = hook->flag != nullptr && !hook->issued;
+  const bool watch2 = hook->flag2 != nullptr;
   if (want && tid == 32) {  // (warp 1 idles during the first 8x8 factor)
     s_hook = ld_relaxed(hook->flag) != 0;
     if (s_hook) fence_acquire();
   }
   __syncthreads();
+  if (tr && tid == 0) tr[8] = global_ns();
 #pragma unroll 1
   for (int bk = 0; bk < 7; ++bk) {
     const int k1 = 8 * bk;
@@ -246,27 +292,32 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int*
       tile_prefetch(hook->dst, hook->src, hook->ld);
       hook->issued = true;
     }
-    // panel: row r of X = A_r L^-T by forward substitution, one thread per row
-    if (tid < below) {
-      double* rowp = Cs + (k1 + 8 + tid) * kCS + k1;
-      double x[8];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) x[c] = rowp[c];
-#pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        x[c] *= rdiag[k1 + c];
-#pragma unroll
-        for (int p = c + 1; p < 8; ++p) x[p] -= x[c] * Cs[(k1 + p) * kCS + k1 + c];
-      }
-#pragma unroll
-      for (int c = 0; c < 8; ++c) rowp[c] = x[c];
+    // panel: X = A inv(L_8)^T, one 8x8 block of rows per warp (two m8n8k4 steps, in place)
+    if (warp < (below >> 3)) {
+      double* ab = Cs + (k1 + 8 + 8 * warp + g) * kCS + k1;
+      const double* ib = Iv + 64 * bk + 8 * g;
+      const double a0 = ab[q], a1 = ab[4 + q];
+      const double b0 = ib[q], b1 = ib[4 + q];
+      double x0 = 0.0, x1 = 0.0;
+      dmma_m8n8k4(x0, x1, a0, b0);
+      dmma_m8n8k4(x0, x1, a1, b1);
+      __syncwarp();  // every lane has its operands: the block may be overwritten
+      *reinterpret_cast<double2*>(ab + 2 * q) = make_double2(x0, x1);
     }
     __syncthreads();
+    if (tr && tid == 0 && bk == 0) tr[9] = global_ns();
     // (s_hook is only written between the two barriers of a round and read after the second one,
     // so every thread takes the same prefetch decision)
-    if (want && !hook->issued && tid == 255) {
-      s_hook = ld_relaxed(hook->flag) != 0;
-      if (s_hook) fence_acquire();
+    if (tid == 255) {
+      if (want && !hook->issued) {
+        s_hook = ld_relaxed(hook->flag) != 0;
+        if (s_hook) fence_acquire();
+      } else if (watch2 && !*hook->seen2) {
+        if (ld_relaxed(hook->flag2) != 0) {
+          fence_acquire();
+          *hook->seen2 = 1;
+        }
+      }
     }
     // trailing update inside the tile on the FP64 tensor cores: 8x8 output tiles (lower part),
     // C -= X_ti X_tj^T with k = 8 (two m8n8k4 steps).  Look-ahead: warp 0 updates the next
@@ -274,11 +325,16 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int*
     const int nb = below >> 3;
     const int ntile = nb * (nb + 1) / 2;
     const double* X = Cs + (k1 + 8) * kCS + k1;
+    // tile t of the lower triangle -> (ti, tj): a table instead of a square root (t < 28)
+    auto tile_rc = [](int t, int& ti, int& tj) {
+      const unsigned v = (unsigned)kTriRow[t];
+      ti = (int)(v >> 4);
+      tj = (int)(v & 15u);
+    };
     auto update_tile = [&](int t) {
-      int ti = (int)((sqrtf(8.0f * t + 1.0f) - 1.0f) * 0.5f);
-      while ((ti + 1) * (ti + 2) / 2 <= t) ++ti;
-      while (ti * (ti + 1) / 2 > t) --ti;
-      const int tj = t - ti * (ti + 1) / 2;
+      int ti, tj;
+      tile_rc(t, ti, tj);
+      if (Xd && tj == 1 && ti >= 1) return;  // with the deferred update: heavy_tile below
       double* cp = Cs + (k1 + 8 + 8 * ti + g) * kCS + k1 + 8 + 8 * tj + 2 * q;
       double2 cv = *reinterpret_cast<double2*>(cp);
       const double a0 = -X[(8 * ti + g) * kCS + q], a1 = -X[(8 * ti + g) * kCS + 4 + q];
@@ -287,66 +343,77 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* rdiag, int*
       dmma_m8n8k4(cv.x, cv.y, a1, b1);
       *reinterpret_cast<double2*>(cp) = cv;
     };
+    // tile (ti, 1) of the trailing part = block (bk + 1 + ti, bk + 2) of the 64x64 tile: this
+    // round's update and the deferred C -= Xd Xd^T of column block bk + 2, one load and one store
+    auto heavy_tile = [&](int ti) {
+      double* cp = Cs + (k1 + 8 + 8 * ti + g) * kCS + k1 + 16 + 2 * q;
+      double2 cv = *reinterpret_cast<double2*>(cp);
+      // four accumulators: chains of 5, 5, 4 and 4 tensor-core steps instead of one of 18
+      double2 c2 = make_double2(0.0, 0.0), c3 = c2, c4 = c2;
+      const double a0 = -X[(8 * ti + g) * kCS + q], a1 = -X[(8 * ti + g) * kCS + 4 + q];
+      const double b0 = X[(8 + g) * kCS + q], b1 = X[(8 + g) * kCS + 4 + q];
+      dmma_m8n8k4(cv.x, cv.y, a0, b0);
+      dmma_m8n8k4(c2.x, c2.y, a1, b1);
+      const double* xa = Xd + (8 * (bk + 1 + ti) + g) * kCS + q;
+      const double* xb = Xd + (8 * (bk + 2) + g) * kCS + q;
+#pragma unroll
+      for (int kk = 0; kk < NB; kk += 16) {
+        dmma_m8n8k4(cv.x, cv.y, -xa[kk], xb[kk]);
+        dmma_m8n8k4(c2.x, c2.y, -xa[kk + 4], xb[kk + 4]);
+        dmma_m8n8k4(c3.x, c3.y, -xa[kk + 8], xb[kk + 8]);
+        dmma_m8n8k4(c4.x, c4.y, -xa[kk + 12], xb[kk + 12]);
+      }
+      cv.x += (c2.x + c3.x) + c4.x;
+      cv.y += (c2.y + c3.y) + c4.y;
+      *reinterpret_cast<double2*>(cp) = cv;
+    };
     if (warp == 0) {
-      update_tile(0);
+      {  // tile (0, 0): the next diagonal 8x8 block
+        double* cp = Cs + (k1 + 8 + g) * kCS + k1 + 8 + 2 * q;
+        double2 cv = *reinterpret_cast<double2*>(cp);
+        const double a0 = X[g * kCS + q], a1 = X[g * kCS + 4 + q];
+        dmma_m8n8k4(cv.x, cv.y, -a0, a0);
+        dmma_m8n8k4(cv.x, cv.y, -a1, a1);
+        *reinterpret_cast<double2*>(cp) = cv;
+      }
       __syncwarp();
-      const bool bad = factor8(Cs, k1 + 8, rdiag, lane);
+      const bool bad = factor8(Cs, k1 + 8, Iv + 64 * (bk + 1), lane);
       if (bad && lane == 0) *s_bad = 1;
     } else {
+      if (Xd && warp < nb) heavy_tile(warp);  // ti = 1 .. nb - 1, one per warp (the long one first)
       for (int t = warp; t < ntile; t += 7) update_tile(t);
     }
     __syncthreads();
+    if (tr && tid == 0 && (bk == 0 || bk == 3 || bk == 6)) tr[bk == 0 ? 10 : (bk == 3 ? 11 : 12)] = global_ns();
   }
   if (want && !hook->issued && s_hook) {
     tile_prefetch(hook->dst, hook->src, hook->ld);
     hook->issued = true;
   }
   // Inverses of the 16x16 diagonal sub-blocks (what the triangular solves of the tiles below
-  // use): 8x8 inverses by forward substitution, one thread per column, then
-  // inv([A 0; B C]) = [inv A, 0; -inv(C) B inv(A), inv C].
-  if (tid < 64) {
-    const int blk = tid >> 3, c = tid & 7, o = 8 * blk;
-    double m[8];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) m[i] = 0.0;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      if (i >= c) {
-        double acc = (i == c) ? 1.0 : 0.0;
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-          if (k < i && k >= c) acc -= Cs[(o + i) * kCS + o + k] * m[k];
-        m[i] = acc * rdiag[o + i];
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < 8; ++i) Tm[(o + i) * kCS + o + c] = m[i];
-    // upper-right 8x8 of the 16-block this 8-block belongs to is zero
-    if ((blk & 1) == 0) {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) Tm[(o + i) * kCS + o + 8 + c] = 0.0;
-    }
-  }
-  __syncthreads();
+  // use) from the 8x8 inverses of the factor steps:
+  // inv([A 0; B C]) = [inv A, 0; -inv(C) B inv(A), inv C].  (Xd, if it is Tm, is dead by now.)
+  if (tr && tid == 0) tr[13] = global_ns();
   {
-    // lower-left 8x8 of each 16-block: T = B inv(A) (into scratch right of the tile's 16-block
-    // row, Tm columns [48, 56) are free until the dense inverse is assembled), then -inv(C) T
     const int blk = tid >> 6, r = (tid >> 3) & 7, c = tid & 7, o = 16 * blk;
-    double acc = 0.0;
+    const double* iA = Iv + 64 * (2 * blk);
+    const double* iC = Iv + 64 * (2 * blk + 1);
+    double* Ts = Iv + 64 * (8 + blk);
+    double acc = 0.0;  // T = B inv(A)
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc += Cs[(o + 8 + r) * kCS + o + k] * Tm[(o + k) * kCS + o + c];
+    for (int k = 0; k < 8; ++k) acc += Cs[(o + 8 + r) * kCS + o + k] * iA[8 * k + c];
+    Ts[8 * r + c] = acc;
     __syncthreads();
-    double* scratch = Tm + (size_t)(o + r) * kCS + ((blk == 3) ? 0 : 56);  // outside block `blk`
-    scratch[c] = acc;
-    __syncthreads();
-    double res = 0.0;
+    double res = 0.0;  // - inv(C) T
 #pragma unroll
-    for (int k = 0; k < 8; ++k)
-      res -= Tm[(o + 8 + r) * kCS + o + 8 + k] * Tm[(size_t)(o + k) * kCS + ((blk == 3) ? 0 : 56) + c];
-    __syncthreads();
+    for (int k = 0; k < 8; ++k) res -= iC[8 * r + k] * Ts[8 * k + c];
+    Tm[(o + r) * kCS + o + c] = iA[8 * r + c];
+    Tm[(o + r) * kCS + o + 8 + c] = 0.0;
     Tm[(o + 8 + r) * kCS + o + c] = res;
+    Tm[(o + 8 + r) * kCS + o + 8 + c] = iC[8 * r + c];
   }
   __syncthreads();
+  if (tr && tid == 0) tr[14] = global_ns();
 }
 
 // ------------------------------------------------------------------------------------------
@@ -414,16 +481,22 @@ __device__ __forceinline__ void frag_load_smem(double (&acc)[8][2], const double
 // ------------------------------------------------------------------------------------------
 // The walker: diagonal and sub-diagonal tiles, one column after the other.
 // Shared memory: Cs (current diagonal tile -> L -> Lpack), Tm (block inverses, then X of the
-// sub-diagonal tile), Ps (prefetch buffer for the pre-accumulated tiles the helpers hand over).
+// sub-diagonal tile), Ps (prefetch buffer for the pre-accumulated tiles the helpers hand over;
+// the next diagonal tile is updated in place there and the two buffers swap roles), Iv (scratch
+// of the diagonal factorisation).
 // ------------------------------------------------------------------------------------------
-__device__ void walker(double* __restrict__ A, int ld, int n, double* smem, const Work& w, int T,
+__device__ __noinline__ void walker(double* __restrict__ A, int ld, int n, double* smem, const Work& w, int T,
                        int ncols, int* __restrict__ status,
                        unsigned long long* __restrict__ trace) {
-  double* Cs = smem;
-  double* Tm = smem + 64 * kCS;
-  double* Ps = smem + 2 * 64 * kCS;
-  __shared__ double rdiag[NB], rhs_row[NB];
-  __shared__ int s_bad, s_poll;
+  // Cs / Ps swap roles every column: one parity bit instead of two more live pointers
+  int par = 0;
+#define Cs (smem + (par ? 2 * 64 * kCS : 0))
+#define Ps (smem + (par ? 0 : 2 * 64 * kCS))
+  double* const Tm = smem + 64 * kCS;
+  double* const Iv = smem + kWalkerInv;
+  bool deferred = false;  // Cs still lacks C -= X X^T (X in Tm) in its column blocks >= 2
+  __shared__ double rhs_row[NB];
+  __shared__ int s_bad, s_poll, s_seen2;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int g = lane >> 2, q = lane & 3;
   if (tid == 0) s_bad = 0;
@@ -448,12 +521,18 @@ __device__ void walker(double* __restrict__ A, int ld, int n, double* smem, cons
       hook.dst = Ps;
       hook.src = A + (size_t)(k0 + NB) * ld + k0;
       hook.ld = ld;
+      if (has_next) {  // watched during the factorisation, fetched after the triangular solve
+        hook.flag2 = w.pre + (j + 1) * T + (j + 1);
+        hook.seen2 = &s_seen2;
+      }
     }
+    if (tid == 0) s_seen2 = 0;  // (ordered before its use by the barriers inside potrf64)
     // raise the flags of the previous column now: warp 1 idles during the first 8x8 factor anyway
+    // (one fence, then relaxed stores: a release pattern without a second and third membar)
     if (warp == 1 && lane == 0 && (pending_diag >= 0 || pending_tile >= 0)) {
       __threadfence();
-      if (pending_diag >= 0) st_release(w.tile + pending_diag, 1);
-      if (pending_tile >= 0) st_release(w.tile + pending_tile, 1);
+      if (pending_diag >= 0) st_relaxed(w.tile + pending_diag, 1);
+      if (pending_tile >= 0) st_relaxed(w.tile + pending_tile, 1);
     }
     pending_diag = pending_tile = -1;
     if (kb < NB) {
@@ -466,7 +545,9 @@ __device__ void walker(double* __restrict__ A, int ld, int n, double* smem, cons
       }
       __syncthreads();
     }
-    potrf64(Cs, Tm, rdiag, &s_bad, &hook);
+    potrf64(Cs, Tm, Iv, deferred ? Tm : nullptr, &s_bad, &hook,
+            trace ? trace + 16 * (size_t)(j * T + j) : nullptr);
+    deferred = false;
     // Cs := Lpack (diagonal 16x16 blocks <- their inverses)
     for (int idx = tid; idx < 4 * 256; idx += 256) {
       const int b = idx >> 8, r = 16 * b + ((idx >> 4) & 15), c = 16 * b + (idx & 15);
@@ -529,7 +610,7 @@ __device__ void walker(double* __restrict__ A, int ld, int n, double* smem, cons
     // membar of latency inside the solve below) instead of at the top of the next iteration
     if (tid == 32 && pending_diag >= 0) {
       __threadfence();
-      st_release(w.tile + pending_diag, 1);
+      st_relaxed(w.tile + pending_diag, 1);
     }
     pending_diag = -1;
     double acc[8][2];
@@ -538,9 +619,13 @@ __device__ void walker(double* __restrict__ A, int ld, int n, double* smem, cons
     // the helpers are done with it, otherwise right after
     bool next_issued = false;
     if (has_next) {
+      // (usually seen already by the watcher inside potrf64: no global load on this path then)
       if (tid == 0) {
-        s_poll = ld_relaxed(w.pre + (j + 1) * T + (j + 1)) != 0;
-        if (s_poll) fence_acquire();
+        s_poll = s_seen2;
+        if (!s_poll) {
+          s_poll = ld_relaxed(w.pre + (j + 1) * T + (j + 1)) != 0;
+          if (s_poll) fence_acquire();
+        }
       }
       __syncthreads();  // (also: every warp has its fragments, Ps may be overwritten)
       if (s_poll) {
@@ -561,29 +646,48 @@ __device__ void walker(double* __restrict__ A, int ld, int n, double* smem, cons
       __syncthreads();
       tile_prefetch(Ps, A + (size_t)(k0 + NB) * ld + k0 + NB, ld);
     }
-    // next diagonal tile: C -= X X^T (the one term the helpers could not pre-accumulate); only
-    // the 36 lower 8x8 blocks, dealt round-robin to the warps
+    // next diagonal tile: C -= X X^T (the one term the helpers could not pre-accumulate), in
+    // place in Ps.  Only column blocks 0 and 1 (15 of the 36 lower 8x8 blocks) are needed before
+    // its factorisation can start; the others are applied inside potrf64, off the dependency
+    // chain.  A partial last block takes all of it now (its right-hand-side row is read first).
     cp_async_wait<0>();
     __syncthreads();  // X complete in Tm, pre-accumulated tile complete in Ps, Lpack stores issued
     if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 6] = global_ns();
+    const bool defer = n - (k0 + NB) >= NB;
+    const int nblk = defer ? 15 : 36;
 #pragma unroll 1
-    for (int e = warp; e < 36; e += 8) {
-      int bi = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
-      while ((bi + 1) * (bi + 2) / 2 <= e) ++bi;
-      while (bi * (bi + 1) / 2 > e) --bi;
-      const int bj = e - bi * (bi + 1) / 2;
-      double2 cv = *reinterpret_cast<const double2*>(Ps + (8 * bi + g) * kCS + 8 * bj + 2 * q);
-#pragma unroll
-      for (int kk = 0; kk < NB; kk += 4) {
-        const double a = -Tm[(8 * bi + g) * kCS + kk + q];
-        const double b = Tm[(8 * bj + g) * kCS + kk + q];
-        dmma_m8n8k4(cv.x, cv.y, a, b);
+    for (int e = warp; e < nblk; e += 8) {
+      int bi, bj;
+      if (defer) {
+        bi = e < 8 ? e : e - 7;
+        bj = e < 8 ? 0 : 1;
+      } else {
+        bi = (int)((sqrtf(8.0f * e + 1.0f) - 1.0f) * 0.5f);
+        while ((bi + 1) * (bi + 2) / 2 <= e) ++bi;
+        while (bi * (bi + 1) / 2 > e) --bi;
+        bj = e - bi * (bi + 1) / 2;
       }
-      *reinterpret_cast<double2*>(Cs + (8 * bi + g) * kCS + 8 * bj + 2 * q) = cv;
+      double* cp = Ps + (8 * bi + g) * kCS + 8 * bj + 2 * q;
+      double2 cv = *reinterpret_cast<const double2*>(cp);
+      double2 c2 = make_double2(0.0, 0.0);
+      const double* xa = Tm + (8 * bi + g) * kCS + q;
+      const double* xb = Tm + (8 * bj + g) * kCS + q;
+#pragma unroll
+      for (int kk = 0; kk < NB; kk += 8) {
+        dmma_m8n8k4(cv.x, cv.y, -xa[kk], xb[kk]);
+        dmma_m8n8k4(c2.x, c2.y, -xa[kk + 4], xb[kk + 4]);
+      }
+      cv.x += c2.x;
+      cv.y += c2.y;
+      *reinterpret_cast<double2*>(cp) = cv;
     }
     __syncthreads();
+    par ^= 1;  // the updated tile becomes the current one; the old one (Lpack_j, stored) is free
+    deferred = defer;
     if (trace && tid == 0) trace[16 * (size_t)(j * T + j) + 7] = global_ns();
   }
+#undef Cs
+#undef Ps
   // flags of the last column
   if (tid == 0) {
     if (s_bad) atomicExch(status, 1);

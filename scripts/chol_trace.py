@@ -20,3 +20,21 @@ for j in range(ncols):
 print("sums (us): potrf %.0f, wait-sub %.0f, trsm %.0f, wait-diag %.0f, syrk %.0f" % tuple(tot))
 last = max(v[7] for v in ev.values())
 print("walker total us", (max(max(v[2], v[5], v[7]) for (i, j), v in ev.items() if i == j) - t0) / 1e3)
+
+# inside the diagonal factorisation (slots 8..14), averaged over the columns
+names = ["first 8x8 factor", "panel 0", "update 0 + factor 1", "rounds 1-3", "rounds 4-6",
+         "8x8 inverses", "16x16 inverses"]
+acc = np.zeros(7)
+cnt = 0
+for j in range(ncols - 1):
+    d = ev[(j, j)]
+    if len(d) < 15 or d[8] <= 0 or d[14] <= 0:
+        continue
+    marks = [d[1], d[8], d[9], d[10], d[11], d[12], d[13], d[14]]
+    acc += np.diff(marks) / 1e3
+    cnt += 1
+if cnt:
+    print("inside potrf (us, mean of %d columns): " % cnt +
+          ", ".join(f"{n} {v:.2f}" for n, v in zip(names, acc / cnt)) +
+          f"; packing after it {np.mean([(ev[(j, j)][2] - ev[(j, j)][14]) / 1e3 for j in range(ncols - 1)]):.2f}")
+
