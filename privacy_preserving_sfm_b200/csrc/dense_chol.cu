@@ -61,6 +61,15 @@ __device__ __forceinline__ int ld_relaxed(const int* p) {
   asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+constexpr unsigned long long kXPending = ~0ull;  // x entries not yet solved (back-substitution)
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ void fence_acquire() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
 __device__ __forceinline__ void st_relaxed(int* p, int v) {
   asm volatile("st.relaxed.gpu.global.s32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
@@ -869,6 +878,10 @@ chol_factor_kernel(double* __restrict__ A, int ld, int n, double* __restrict__ w
 // ticket).  CTA j streams the tiles L[b][j], b > j, through a cp.async double buffer, applies
 // y_j -= L[b][j]^T x_b as soon as x_b is published, then x_j = L_jj^-T y_j with the dense inverse
 // it assembled from the blocked factor Lpack_j while it was waiting.
+// x is its own flag: the host fills it with an all-ones NaN pattern, a consumer spins on the 64
+// values it needs, and a producer never stores that pattern (NaNs are made canonical first).  The
+// chain x_(j+1) -> x_j is then one global round trip per step — no flag store behind a fence and no
+// second dependent load (2.4 -> 1.4 us per step).
 // ------------------------------------------------------------------------------------------
 constexpr int kBackSmem = 4 * NB * NB * (int)sizeof(double);
 
@@ -880,7 +893,6 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   __shared__ int s_ticket;
   const Work w = work_layout(work_base, n);
   const int nblk = (n + NB - 1) / NB;
-  int* xflags = w.xf;
   const int tid = threadIdx.x, c = tid & 63, part = tid >> 6;
   if (tid == 0) s_ticket = atomicAdd(w.flags + 1, 1);
   __syncthreads();
@@ -958,12 +970,20 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
   }
   for (int b = nblk - 1; b > j; --b) {
     const int st = (nblk - 1 - b) & 1;
-    if (tid == 0) wait_flag(xflags + b);
+    const int kbb = min(NB, n - b * NB);
+    if (tid < NB) {
+      double v = 0.0;
+      if (tid < kbb) {
+        const unsigned long long* src = reinterpret_cast<const unsigned long long*>(x + b * NB + tid);
+        unsigned long long bits;
+        while ((bits = ld_relaxed_u64(src)) == kXPending) {
+        }
+        v = __longlong_as_double((long long)bits);
+      }
+      xb[tid] = v;
+    }
     // tile b has been issued; at most one younger group is in flight
     if (issued_b < b - 1) cp_async_wait<1>(); else cp_async_wait<0>();
-    __syncthreads();
-    const int kbb = min(NB, n - b * NB);
-    if (tid < NB) xb[tid] = (tid < kbb) ? ld_cg(x + b * NB + tid) : 0.0;
     __syncthreads();
     const double* Lt = stage0 + (size_t)st * NB * NB;
     double s = 0.0;
@@ -990,11 +1010,11 @@ chol_backsolve_kernel(const double* __restrict__ A, int ld, int n, double* __res
     red[part][c] = s;
   }
   __syncthreads();
-  if (tid < kb) x[k0 + tid] = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
-  __syncthreads();
-  if (tid == 0) {
-    __threadfence();
-    st_release(xflags + j, 1);
+  if (tid < kb) {
+    double v = red[0][tid] + red[1][tid] + red[2][tid] + red[3][tid];
+    if (v != v) v = __longlong_as_double(0x7ff8000000000000ll);  // never the "pending" pattern
+    st_relaxed_u64(reinterpret_cast<unsigned long long*>(x + k0 + tid),
+                   (unsigned long long)__double_as_longlong(v));
   }
 }
 
@@ -1022,6 +1042,7 @@ int chol_solve_bordered(double* A, int n, int ld, double* x, double* work, int* 
   const Work w = work_layout(work, n);
   cudaMemsetAsync(status, 0, sizeof(int), s);
   cudaMemsetAsync(w.flags, 0, sizeof(int) * work_flag_ints(n), s);
+  cudaMemsetAsync(x, 0xff, sizeof(double) * (size_t)n, s);  // "pending" (see chol_backsolve_kernel)
   const int T = ld / NB;
   const int ncols = (n + NB - 1) / NB;
   const int ntiles = ncols * T - ncols * (ncols - 1) / 2;
