@@ -2,7 +2,7 @@
 """Small invocations of the hand-synchronised kernels for compute-sanitizer
 (memcheck / racecheck / synccheck): the scoring kernel (bulk-copy + mbarrier pipeline, pruned
 two-phase path), the octet solve kernel, the dataflow Cholesky (walker + helpers, flag polling)
-and the tensor-core Schur gather inside a small BA solve.
+and the tensor-core Schur gather inside a small BA solve, with and without intrinsics refinement.
   compute-sanitizer --tool racecheck python scripts/sanitize_probe.py"""
 import os
 import sys
@@ -38,4 +38,12 @@ a = ba.BaArrays(sb["qvecs"], sb["tvecs"], sb["points"], sb["obs_cam"], sb["obs_p
 ok, s = ba.solve_arrays(ctx, a, ba.default_solver_options(max_num_iterations=3,
                                                           gradient_tolerance=1e-6))
 print("ba:", ok, s.initial_cost, s.final_cost, flush=True)
+# intrinsics refinement (two cameras, both variable): the kernels of ba_intrinsics.cu
+sn = S.make_ba_scene(num_cams=12, num_points=500, obs_per_point=5, seed=5, noise_px=2.0)
+ai = ba.BaArrays(sn["qvecs"], sn["tvecs"], sn["points"], sn["obs_cam"], sn["obs_pt"],
+                 sn["obs_line"], [2, 2], [[1000.0, 500, 500, 0.08], [1000.0, 500, 500, 0.05]],
+                 image_camera=np.arange(12) % 2, pose_flags=flags)
+ok, s = ba.solve_arrays(ctx, ai, ba.default_solver_options(max_num_iterations=3,
+                                                           refine_extra_params=1))
+print("ba intrinsics:", ok, s.initial_cost, s.final_cost, ai.camera_params[:, 3], flush=True)
 ctx.close()
