@@ -355,6 +355,21 @@ int ppsfm_initialize_reconstruction(const double* lines, const uint8_t* aligned,
                                     const double* gravity, const ppsfm_init_options* options,
                                     double* poses_out, double* inlier_ratio,
                                     ppsfm_init_report* report);
+/* The same run with the data-parallel part of both LO-MSAC loops on the GPU:
+ * every candidate model of FourView2dEstimator (src/init/sfm2d.cc:302-444) and
+ * PlanarOffsetEstimator (src/init/initializer.cc:219-333) is scored by one kernel launch per
+ * minimal sample — all tracks triangulated and evaluated, MSAC sum in track order — with scores
+ * bit-identical to the host's, so the result equals ppsfm_initialize_reconstruction's.
+ * gpu_launches (optional): kernels launched. */
+int ppsfm_initialize_reconstruction_gpu(ppsfm_ctx* ctx, const double* lines,
+                                        const uint8_t* aligned, size_t n, const double* gravity,
+                                        const ppsfm_init_options* options, double* poses_out,
+                                        double* inlier_ratio, ppsfm_init_report* report,
+                                        int64_t* gpu_launches);
+/* Test hook: the generic and the fixed-size least-squares routine of the initialisation on one
+ * m x n system ((3, 2) or (4, 3)); both must return the same bits. */
+int ppsfm_init_test_qr(const double* A, int m, int n, const double* b, double* x_generic,
+                       double* x_fixed);
 
 /* =============================================================================================
  * Observation / point filters that follow every bundle adjustment, on a

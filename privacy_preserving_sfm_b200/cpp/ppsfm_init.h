@@ -23,6 +23,7 @@
 #include <limits>
 #include <vector>
 
+#include "ppsfm_init_math.h"
 #include "ppsfm_lomsac.h"
 
 namespace ppsfm {
@@ -522,18 +523,11 @@ inline void metric_upgrade(const Pose2d& P2, const Pose2d& P3, double H[3][3]) {
 inline void three_view_triangulate2d(const Pose2d& P1, const Pose2d& P2, const Pose2d& P3,
                                      const std::vector<Vec2>& x1, const std::vector<Vec2>& x2,
                                      const std::vector<Vec2>& x3, std::vector<Vec2>* X) {
-  const Pose2d* P[3] = {&P1, &P2, &P3};
-  const std::vector<Vec2>* x[3] = {&x1, &x2, &x3};
-  std::vector<double> A(6), b(3);
+  // (per point: hd::triangulate2d_point, the arithmetic the GPU scoring kernel shares)
   for (size_t i = 0; i < x1.size(); ++i) {
-    for (int v = 0; v < 3; ++v) {
-      const Vec2& xi = (*x[v])[i];
-      A[2 * v] = xi[0] * P[v]->m[1][0] - xi[1] * P[v]->m[0][0];
-      A[2 * v + 1] = xi[0] * P[v]->m[1][1] - xi[1] * P[v]->m[0][1];
-      b[v] = xi[1] * P[v]->m[0][2] - xi[0] * P[v]->m[1][2];
-    }
     Vec2 sol;
-    la::qr_solve(A, 3, 2, b, sol.data());
+    hd::triangulate2d_point(&P1.m[0][0], &P2.m[0][0], &P3.m[0][0], x1[i].data(), x2[i].data(),
+                            x3[i].data(), sol.data());
     X->push_back(sol);
   }
 }
@@ -650,27 +644,46 @@ class FourView2dEstimator {
 
   // sfm2d.cc:302-319: max over the four views of the 1-D reprojection error
   double EvaluateModelOnPoint(const Reconstruction& model, int i) const {
-    const std::vector<Vec2>* xs[4] = {&x1_, &x2_, &x3_, &x4_};
-    Vec2 z[4];
-    for (int v = 0; v < 4; ++v) z[v] = la::apply(model.cams[v], model.X[i]);
-    if (z[0][1] < 0 || z[1][1] < 0 || z[2][1] < 0 || z[3][1] < 0) return 1000000.0;
-    double err = 0;
-    for (int v = 0; v < 4; ++v) {
-      const Vec2& x = (*xs[v])[i];
-      err = std::max(err, std::fabs(x[0] / x[1] - z[v][0] / z[v][1]));
-    }
-    return err;
+    static_assert(sizeof(Pose2d) == 6 * sizeof(double), "cams[] is 4 x 6 contiguous doubles");
+    const double* cams = &model.cams[0].m[0][0];
+    return hd::fourview2d_error(cams, x1_[i].data(), x2_[i].data(), x3_[i].data(), x4_[i].data(),
+                                model.X[i].data());
   }
 
-  // sfm2d.cc:321-361
+  // ---- batched scoring (optional; the GPU path of ppsfm_initialize_reconstruction_gpu) --------
+  // With a scorer attached, MinimalSolver leaves X empty ("lazy" models: only the cameras are
+  // known), ScoreModels scores all candidates of a sample in one call — every track triangulated
+  // and evaluated on the device, the sums in track order like LocallyOptimizedMSAC::Score — and
+  // Materialize triangulates the tracks of the one model that is kept.
+  void set_batch_scorer(const BatchScorer* scorer) { scorer_ = scorer; }
+  static void PackCams(const Reconstruction& model, double* cams) {
+    for (int v = 0; v < 4; ++v)
+      for (int r = 0; r < 2; ++r)
+        for (int c = 0; c < 3; ++c) cams[6 * v + 3 * r + c] = model.cams[v].m[r][c];
+  }
+  bool ScoreModels(const ReconstructionVector& models, int num_models, double threshold,
+                   double* scores, bool threshold_first = false) const {
+    if (!scorer_ || num_models <= 0) return false;
+    std::vector<double> cams(24 * static_cast<size_t>(num_models));
+    for (int m = 0; m < num_models; ++m) PackCams(models[m], &cams[24 * static_cast<size_t>(m)]);
+    return scorer_->ScoreFourView2d(cams.data(), num_models, threshold, threshold_first, scores);
+  }
+  void Materialize(Reconstruction* model) const {
+    if (!model->X.empty()) return;
+    detail::three_view_triangulate2d(model->cams[0], model->cams[1], model->cams[2], x1_, x2_, x3_,
+                                     &model->X);
+  }
+
+  // sfm2d.cc:321-361.  compact: X_ holds only the sample's points, in sample order (lazy models)
   int AbsPoseSolver(const std::vector<int>& sample, const std::vector<Vec2>& x_,
-                    const std::vector<Vec2>& X_, Pose2d* model) const {
+                    const std::vector<Vec2>& X_, Pose2d* model, bool compact = false) const {
     const int n = static_cast<int>(sample.size());
     std::vector<double> A(2 * n), B(2 * n);
     double btb[3] = {0, 0, 0}, bta[4] = {0, 0, 0, 0};
     for (int i = 0; i < n; ++i) {
       const double x1 = x_[sample[i]][0], x2 = x_[sample[i]][1];
-      const double X1 = X_[sample[i]][0], X2 = X_[sample[i]][1];
+      const Vec2& Xi = X_[compact ? i : sample[i]];
+      const double X1 = Xi[0], X2 = Xi[1];
       A[2 * i] = X1 * x2 - X2 * x1;
       A[2 * i + 1] = -X1 * x1 - X2 * x2;
       B[2 * i] = x2;
@@ -702,7 +715,7 @@ class FourView2dEstimator {
     model->m[0][0] = ab[0]; model->m[1][1] = ab[0];
     model->m[0][1] = -ab[1]; model->m[1][0] = ab[1];
     model->m[0][2] = t[0]; model->m[1][2] = t[1];
-    const Vec2& X0 = X_[sample[0]];
+    const Vec2& X0 = X_[compact ? 0 : sample[0]];
     if (model->m[1][0] * X0[0] + model->m[1][1] * X0[1] + model->m[1][2] < 0)
       for (auto& row : model->m)
         for (double& e : row) e *= -1.0;
@@ -780,8 +793,17 @@ class FourView2dEstimator {
               }
             if (flip2) scale_all(&rec.cams[1], -1.0);
             if (flip3) scale_all(&rec.cams[2], -1.0);
-            detail::three_view_triangulate2d(rec.cams[0], rec.cams[1], rec.cams[2], x1_, x2_, x3_, &rec.X);
-            AbsPoseSolver(sample, x4_, rec.X, &rec.cams[3]);
+            if (scorer_) {  // lazy: only the sample's points, for the fourth camera
+              std::vector<Vec2> Xs(sample.size());
+              for (size_t i = 0; i < sample.size(); ++i)
+                hd::triangulate2d_point(&rec.cams[0].m[0][0], &rec.cams[1].m[0][0],
+                                        &rec.cams[2].m[0][0], x1_[sample[i]].data(),
+                                        x2_[sample[i]].data(), x3_[sample[i]].data(), Xs[i].data());
+              AbsPoseSolver(sample, x4_, Xs, &rec.cams[3], true);
+            } else {
+              detail::three_view_triangulate2d(rec.cams[0], rec.cams[1], rec.cams[2], x1_, x2_, x3_, &rec.X);
+              AbsPoseSolver(sample, x4_, rec.X, &rec.cams[3]);
+            }
             models->push_back(rec);
           }
     }
@@ -793,15 +815,26 @@ class FourView2dEstimator {
     ReconstructionVector models;
     MinimalSolver(sample, &models);
     double best = std::numeric_limits<double>::max();
-    for (const Reconstruction& m : models) {
+    std::vector<double> scores(models.size());
+    // (std::min(threshold, error) here, std::min(error, threshold) in the driver)
+    const bool batched = ScoreModels(models, static_cast<int>(models.size()), inlier_threshold_,
+                                     scores.data(), true);
+    for (size_t mi = 0; mi < models.size(); ++mi) {
+      if (!batched) Materialize(&models[mi]);
+      const Reconstruction& m = models[mi];
       double score = 0;
-      for (int j = 0, nd = num_data(); j < nd; ++j)
-        score += std::min(inlier_threshold_, EvaluateModelOnPoint(m, j));
+      if (batched) {
+        score = scores[mi];
+      } else {
+        for (int j = 0, nd = num_data(); j < nd; ++j)
+          score += std::min(inlier_threshold_, EvaluateModelOnPoint(m, j));
+      }
       if (score < best) {
         best = score;
         *model = m;
       }
     }
+    if (!models.empty()) Materialize(model);
     return models.empty() ? 0 : 1;
   }
 
@@ -827,6 +860,7 @@ class FourView2dEstimator {
  private:
   std::vector<Vec2> x1_, x2_, x3_, x4_;
   const double inlier_threshold_;
+  const BatchScorer* scorer_ = nullptr;
 };
 
 class AbsolutePose2dEstimator {  // sfm2d.h:102-148
@@ -892,16 +926,14 @@ class AbsolutePose2dEstimator {  // sfm2d.h:102-148
 // initializer.cc:219-232
 inline void four_view_triangulate(const std::vector<Pose>& cams,
                                   const std::vector<std::vector<Vec3>>& lines, std::vector<Vec3>* X) {
-  std::vector<double> A(12), b(4);
+  double P[48];  // (per track: hd::triangulate3d_point, shared with the GPU scoring kernel)
+  for (int j = 0; j < 4; ++j)
+    for (int r = 0; r < 3; ++r)
+      for (int c = 0; c < 4; ++c) P[12 * j + 4 * r + c] = cams[j].m[r][c];
   for (size_t i = 0; i < lines[0].size(); ++i) {
-    for (int j = 0; j < 4; ++j) {
-      const Vec3& l = lines[j][i];
-      for (int c = 0; c < 3; ++c)
-        A[3 * j + c] = l[0] * cams[j].m[0][c] + l[1] * cams[j].m[1][c] + l[2] * cams[j].m[2][c];
-      b[j] = -(l[0] * cams[j].m[0][3] + l[1] * cams[j].m[1][3] + l[2] * cams[j].m[2][3]);
-    }
     Vec3 sol;
-    la::qr_solve(A, 4, 3, b, sol.data());
+    hd::triangulate3d_point(P, lines[0][i].data(), lines[1][i].data(), lines[2][i].data(),
+                            lines[3][i].data(), sol.data());
     X->push_back(sol);
   }
 }
@@ -955,10 +987,28 @@ class PlanarOffsetEstimator {  // initializer.h:62-101
         for (int c = 0; c < 4; ++c)
           rec.cams[i].m[r][c] = Rg_[i].m[0][r] * P.m[0][c] + Rg_[i].m[1][r] * P.m[1][c] + Rg_[i].m[2][r] * P.m[2][c];
     }
-    four_view_triangulate(rec.cams, lines_, &rec.X);
+    if (!scorer_) four_view_triangulate(rec.cams, lines_, &rec.X);  // (else lazy: see Materialize)
     models->clear();
     models->push_back(rec);
     return 1;
+  }
+
+  // batched scoring, as in FourView2dEstimator
+  void set_batch_scorer(const BatchScorer* scorer) { scorer_ = scorer; }
+  static void PackCams(const Reconstruction& model, double* cams) {
+    for (int v = 0; v < 4; ++v)
+      for (int r = 0; r < 3; ++r)
+        for (int c = 0; c < 4; ++c) cams[12 * v + 4 * r + c] = model.cams[v].m[r][c];
+  }
+  bool ScoreModels(const ReconstructionVector& models, int num_models, double threshold,
+                   double* scores, bool threshold_first = false) const {
+    if (!scorer_ || num_models <= 0) return false;
+    std::vector<double> cams(48 * static_cast<size_t>(num_models));
+    for (int m = 0; m < num_models; ++m) PackCams(models[m], &cams[48 * static_cast<size_t>(m)]);
+    return scorer_->ScorePlanarOffset(cams.data(), num_models, threshold, threshold_first, scores);
+  }
+  void Materialize(Reconstruction* model) const {
+    if (model->X.empty()) four_view_triangulate(model->cams, lines_, &model->X);
   }
 
   // initializer.cc:283-308
@@ -966,33 +1016,36 @@ class PlanarOffsetEstimator {  // initializer.h:62-101
     ReconstructionVector models;
     MinimalSolver(sample, &models);
     double best = std::numeric_limits<double>::max();
-    for (const Reconstruction& m : models) {
+    std::vector<double> scores(models.size());
+    const bool batched = ScoreModels(models, static_cast<int>(models.size()), inlier_threshold_,
+                                     scores.data());
+    for (size_t mi = 0; mi < models.size(); ++mi) {
+      if (!batched) Materialize(&models[mi]);
+      const Reconstruction& m = models[mi];
       double score = 0;
-      for (int j = 0, nd = num_data(); j < nd; ++j)
-        score += std::min(EvaluateModelOnPoint(m, j), inlier_threshold_);
+      if (batched) {
+        score = scores[mi];
+      } else {
+        for (int j = 0, nd = num_data(); j < nd; ++j)
+          score += std::min(EvaluateModelOnPoint(m, j), inlier_threshold_);
+      }
       if (score < best) {
         best = score;
         *model = m;
       }
     }
     if (models.empty()) return 0;
+    Materialize(model);
     LeastSquares(sample, model);
     return 1;
   }
 
   // initializer.cc:310-333: max over the views of the point-to-line distance (normalised plane)
   double EvaluateModelOnPoint(const Reconstruction& model, int i) const {
-    double err = 0;
-    Vec3 z[4];
-    for (int v = 0; v < 4; ++v) z[v] = la::apply(model.cams[v], model.X[i]);
-    if (z[0][2] < 0 || z[1][2] < 0 || z[2][2] < 0 || z[3][2] < 0) return 100000.0;
-    for (int v = 0; v < 4; ++v) {
-      const Vec3& l = lines_[v][i];
-      const double d = (l[0] * z[v][0] / z[v][2] + l[1] * z[v][1] / z[v][2] + l[2]) /
-                       std::sqrt(l[0] * l[0] + l[1] * l[1]);
-      err = std::max(err, std::fabs(d));
-    }
-    return err;
+    static_assert(sizeof(Pose) == 12 * sizeof(double), "cams[] is 4 x 12 contiguous doubles");
+    const double* cams = &model.cams[0].m[0][0];
+    return hd::planar_offset_error(cams, lines_[0][i].data(), lines_[1][i].data(),
+                                   lines_[2][i].data(), lines_[3][i].data(), model.X[i].data());
   }
 
   // the reference returns before doing anything (initializer.cc:450-451)
@@ -1003,6 +1056,7 @@ class PlanarOffsetEstimator {  // initializer.h:62-101
   std::vector<std::vector<Vec3>> lines_;
   std::vector<Mat3> Rg_;
   const double inlier_threshold_;
+  const BatchScorer* scorer_ = nullptr;
 };
 
 inline void lift_camera(const Pose2d& p, Pose* out) {  // initializer.cc:45-55
@@ -1035,7 +1089,8 @@ template <class LomsacTraits>
 inline bool initialize_reconstruction_t(const std::vector<ImageLines>& lines,
                                         const std::vector<Vec3>& gravity, const InitOptions& options,
                                         std::vector<Pose>* output, double* inlier_ratio,
-                                        InitReport* report = nullptr, const char** error = nullptr) {
+                                        InitReport* report = nullptr, const char** error = nullptr,
+                                        BatchScorerFactory* scorers = nullptr) {
   *inlier_ratio = 0;
   if (error) *error = nullptr;
   auto fail = [&](const char* msg) {
@@ -1078,6 +1133,13 @@ inline bool initialize_reconstruction_t(const std::vector<ImageLines>& lines,
   ransac_options.min_num_iterations_ = 1000;
   ransac_options.squared_inlier_threshold_ = options.max_error;
   FourView2dEstimator solver(x[0], x[1], x[2], x[3], ransac_options.squared_inlier_threshold_);
+  if (scorers && !x[0].empty()) {  // (the estimator's own, normalised, observations)
+    const double* obs[4];
+    for (int v = 0; v < 4; ++v) obs[v] = solver.x(v).data()->data();
+    const BatchScorer* sc = scorers->FourView2d(obs, static_cast<int>(x[0].size()));
+    if (!sc) return fail("GPU scorer of the four-view solver could not be set up");
+    solver.set_batch_scorer(sc);
+  }
   typename LomsacTraits::template Driver<FourView2dEstimator::Reconstruction,
                                          FourView2dEstimator::ReconstructionVector,
                                          FourView2dEstimator> fourview_ransac;
@@ -1119,6 +1181,13 @@ inline bool initialize_reconstruction_t(const std::vector<ImageLines>& lines,
   planar_options.min_num_iterations_ = 1000;
   planar_options.squared_inlier_threshold_ = options.max_error;
   PlanarOffsetEstimator planar_solver(poses, lines_r, Rg, planar_options.squared_inlier_threshold_);
+  if (scorers && !lines_r[0].empty()) {
+    const double* obs[4];
+    for (int v = 0; v < 4; ++v) obs[v] = lines_r[v].data()->data();
+    const BatchScorer* sc = scorers->PlanarOffset(obs, static_cast<int>(lines_r[0].size()));
+    if (!sc) return fail("GPU scorer of the planar-offset solver could not be set up");
+    planar_solver.set_batch_scorer(sc);
+  }
   typename LomsacTraits::template Driver<PlanarOffsetEstimator::Reconstruction,
                                          PlanarOffsetEstimator::ReconstructionVector,
                                          PlanarOffsetEstimator> planar_ransac;
@@ -1142,9 +1211,10 @@ struct PpsfmLomsac {
 inline bool initialize_reconstruction(const std::vector<ImageLines>& lines,
                                       const std::vector<Vec3>& gravity, const InitOptions& options,
                                       std::vector<Pose>* output, double* inlier_ratio,
-                                      InitReport* report = nullptr, const char** error = nullptr) {
+                                      InitReport* report = nullptr, const char** error = nullptr,
+                                      BatchScorerFactory* scorers = nullptr) {
   return initialize_reconstruction_t<PpsfmLomsac>(lines, gravity, options, output, inlier_ratio,
-                                                  report, error);
+                                                  report, error, scorers);
 }
 
 }  // namespace init

@@ -112,6 +112,27 @@ class MinimalSampler {
 
 }  // namespace lomsac_detail
 
+namespace lomsac_detail {
+// Optional members of a Solver (not part of the RansacLib concept): ScoreModels scores all the
+// models of one minimal sample at once (e.g. on a GPU) and returns false if it cannot; Materialize
+// completes a model that MinimalSolver left "lazy" before it is stored or refined.
+template <class S, class MV>
+auto batch_score(const S& s, const MV& models, int n, double thr, double* out, int)
+    -> decltype(s.ScoreModels(models, n, thr, out)) {
+  return s.ScoreModels(models, n, thr, out);
+}
+template <class S, class MV>
+bool batch_score(const S&, const MV&, int, double, double*, long) {
+  return false;
+}
+template <class S, class M>
+auto materialize(const S& s, M* m, int) -> decltype(s.Materialize(m), void()) {
+  s.Materialize(m);
+}
+template <class S, class M>
+void materialize(const S&, M*, long) {}
+}  // namespace lomsac_detail
+
 template <class Model, class ModelVector, class Solver>
 class LocallyOptimizedMSAC {
  public:
@@ -130,6 +151,7 @@ class LocallyOptimizedMSAC {
     double best_minimal_score = kInf;
     std::vector<int> sample(k);
     ModelVector models;
+    std::vector<double> batch_scores;
 
     auto refresh = [&]() {  // inliers of the best model and the adaptive iteration bound
       st.best_num_inliers = Inliers(solver, *best_model, thr, &st.inlier_indices);
@@ -155,8 +177,12 @@ class LocallyOptimizedMSAC {
       if (num_models <= 0) continue;
       double local_score = kInf;
       int local_id = 0;
+      batch_scores.resize(num_models);
+      const bool batched =
+          lomsac_detail::batch_score(solver, models, num_models, thr, batch_scores.data(), 0);
       for (int m = 0; m < num_models; ++m) {
-        const double s = Score(solver, models[m], thr);
+        if (!batched) lomsac_detail::materialize(solver, &models[m], 0);
+        const double s = batched ? batch_scores[m] : Score(solver, models[m], thr);
         if (s < local_score) {
           local_score = s;
           local_id = m;
@@ -167,6 +193,7 @@ class LocallyOptimizedMSAC {
       if (improved) {
         best_minimal_score = local_score;
         best_minimal = models[local_id];
+        lomsac_detail::materialize(solver, &best_minimal, 0);
         KeepBetter(best_minimal_score, best_minimal, &st.best_model_score, best_model);
       }
       const bool run_lo =

@@ -1,5 +1,8 @@
-"""Four-view initialisation from lifted lines (host code): Python mirror of
-``init::initialize_reconstruction`` (src/init/initializer.h:103-108) over the C-ABI."""
+"""Four-view initialisation from lifted lines: Python mirror of
+``init::initialize_reconstruction`` (src/init/initializer.h:103-108) over the C-ABI.  With a
+context the candidate models of both LO-MSAC loops are scored on the GPU
+(``ppsfm_initialize_reconstruction_gpu``, identical results); without one everything runs on the
+host."""
 import ctypes as C
 
 import numpy as np
@@ -38,12 +41,18 @@ def _declare(L):
                                                   C.POINTER(InitOptions), _dp, _dp,
                                                   C.POINTER(InitReport)]
     L.ppsfm_initialize_reconstruction.restype = C.c_int
+    L.ppsfm_initialize_reconstruction_gpu.argtypes = [C.c_void_p, _dp, _u8p, C.c_size_t, _dp,
+                                                      C.POINTER(InitOptions), _dp, _dp,
+                                                      C.POINTER(InitReport),
+                                                      C.POINTER(C.c_int64)]
+    L.ppsfm_initialize_reconstruction_gpu.restype = C.c_int
     L._init_declared = True
 
 
-def initialize_reconstruction(lines, aligned, gravity, options=None):
+def initialize_reconstruction(lines, aligned, gravity, options=None, ctx=None):
     """lines [4, n, 3], aligned [4, n], gravity [4, 3] -> (ok, poses [4, 3, 4], inlier_ratio,
-    report).  Raises ValueError where the reference CHECK-aborts."""
+    report).  Raises ValueError where the reference CHECK-aborts.  ctx: a Context -> models are
+    scored on its GPU (report.gpu_launches = kernels launched)."""
     L = binding.load_library()
     _declare(L)
     lines = np.ascontiguousarray(lines, np.float64)
@@ -58,9 +67,18 @@ def initialize_reconstruction(lines, aligned, gravity, options=None):
     poses = np.zeros((4, 3, 4))
     ratio = C.c_double(0.0)
     rep = InitReport()
-    rc = L.ppsfm_initialize_reconstruction(
-        lines.ctypes.data_as(_dp), aligned.ctypes.data_as(_u8p), n, gravity.ctypes.data_as(_dp),
-        C.byref(opt), poses.ctypes.data_as(_dp), C.byref(ratio), C.byref(rep))
+    args = (lines.ctypes.data_as(_dp), aligned.ctypes.data_as(_u8p), n,
+            gravity.ctypes.data_as(_dp), C.byref(opt), poses.ctypes.data_as(_dp), C.byref(ratio),
+            C.byref(rep))
+    if ctx is not None:
+        launches = C.c_int64(0)
+        rc = L.ppsfm_initialize_reconstruction_gpu(ctx._h, *args, C.byref(launches))
+        rep.gpu_launches = int(launches.value)
+        if rc == -2:  # PPSFM_ERR_CUDA
+            raise binding.PpsfmError("initialize_reconstruction: CUDA error "
+                                     + ctx._L.ppsfm_last_error(ctx._h).decode())
+    else:
+        rc = L.ppsfm_initialize_reconstruction(*args)
     if rc < 0:
         raise ValueError("initialize_reconstruction: contract violation (the reference aborts)")
     return rc == binding.PPSFM_OK, poses, ratio.value, rep

@@ -95,12 +95,14 @@ class IncrementalMapper:
         sc = self.scene
         ids = list(image_ids)
         common = np.flatnonzero(sc.visible[ids].all(axis=0))
-        # (the four-view LO-MSAC is host code whose models carry every track, SURVEY.md A18: a few
-        # thousand tracks are what a real four-view match set holds)
+        # (the LO-MSAC control flow is host code, its candidate models are scored on the GPU —
+        # every model carries every track; a few thousand tracks are what a real
+        # four-view match set holds)
         common = common[:self.max_init_tracks]
         lines = sc.lines[ids][:, common]
         aligned = np.repeat(sc.aligned[common][None, :].astype(np.uint8), 4, axis=0)
-        ok, poses, ratio, rep = I.initialize_reconstruction(lines, aligned, sc.gravity[ids])
+        ok, poses, ratio, rep = I.initialize_reconstruction(lines, aligned, sc.gravity[ids],
+                                                            ctx=self.ctx)
         if not ok:
             return False
         for k, i in enumerate(ids):

@@ -119,3 +119,31 @@ def test_lomsac_bit_identical_to_reference_driver(n, n_al, n_out, seed):
         [int(v) for v in rep2[2:6]]
     assert ratio == ratio2.value
     assert np.array_equal(poses, poses2)
+
+
+@pytest.mark.parametrize("m,n", [(3, 2), (4, 3)])
+def test_fixed_size_least_squares_equals_the_generic_routine(m, n):
+    """hd::qr_solve_fixed (cpp/ppsfm_init_math.h: what the triangulations and the GPU scoring
+    kernel run) is la::qr_solve operation for operation: same bits on random, rank-deficient and
+    badly scaled systems."""
+    from privacy_preserving_sfm_b200 import binding
+    L = binding.load_library()
+    dp = C.POINTER(C.c_double)
+    L.ppsfm_init_test_qr.argtypes = [dp, C.c_int, C.c_int, dp, dp, dp]
+    rng = np.random.default_rng(m * 10 + n)
+    for k in range(500):
+        A = rng.normal(size=(m, n))
+        b = rng.normal(size=m)
+        if k % 5 == 1:
+            A[:, 1] = 2.0 * A[:, 0]                 # rank deficient
+        if k % 5 == 2:
+            A *= 10.0 ** rng.integers(-8, 8)        # badly scaled
+        if k % 5 == 3:
+            A[:, n - 1] *= 1e-15                    # negligible pivot
+        xg, xf = np.zeros(n), np.zeros(n)
+        rc = L.ppsfm_init_test_qr(np.ascontiguousarray(A).ctypes.data_as(dp), m, n,
+                                  b.ctypes.data_as(dp), xg.ctypes.data_as(dp),
+                                  xf.ctypes.data_as(dp))
+        assert rc == 0 and np.array_equal(xg, xf)
+        if k % 5 == 0:
+            assert np.allclose(xg, np.linalg.lstsq(A, b, rcond=None)[0], atol=1e-9)
