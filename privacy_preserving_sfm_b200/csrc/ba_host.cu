@@ -347,7 +347,10 @@ int BaCreate(ppsfm_ctx* ctx, const ppsfm_ba_problem* pb, const ppsfm_ba_options*
   BA_TRY(DevAlloc(st, &d.partials, 3 * (size_t)d.num_partials));
   BA_TRY(DevAlloc(st, &d.scalars, kNumScalars));
   BA_TRY(cudaMemsetAsync(d.scalars, 0, sizeof(double) * kNumScalars, s));
-  BA_TRY(st->h_scalars.reserve(sizeof(double) * kNumScalars));
+  // (+ two ints behind the scalars: the Cholesky status and the intrinsics overflow flag, so that
+  // their device -> host copies are truly asynchronous — a copy to pageable memory blocks the host
+  // until the stream has drained, i.e. until the factorisation is over)
+  BA_TRY(st->h_scalars.reserve(sizeof(double) * kNumScalars + 2 * sizeof(int)));
   BA_TRY(cudaEventCreate(&st->ev0));
   BA_TRY(cudaEventCreate(&st->ev1));
   for (auto& ev : st->evp) BA_TRY(cudaEventCreate(&ev));
@@ -524,14 +527,15 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       st->launches += 2;
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[1], s));
-    int chol_failed = 0, intr_overflow = 0;
+    int* h_flags = reinterpret_cast<int*>(st->h_scalars.as<double>() + kNumScalars);
+    h_flags[0] = h_flags[1] = 0;  // [0] Cholesky failed, [1] intrinsics overflow (pinned memory)
     if (d.NCv > 0)
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(&intr_overflow, st->intr_overflow, sizeof(int),
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(h_flags + 1, st->intr_overflow, sizeof(int),
                                       cudaMemcpyDeviceToHost, s));
     if (d.n > 0) {
       st->launches += chol_solve_bordered(d.S, d.n, d.ld, d.dc, d.chol_work, d.chol_status, s);
       PPSFM_CUDA(ctx, cudaGetLastError());  // a refused launch must not read as "factorised"
-      PPSFM_CUDA(ctx, cudaMemcpyAsync(&chol_failed, d.chol_status, sizeof(int),
+      PPSFM_CUDA(ctx, cudaMemcpyAsync(h_flags, d.chol_status, sizeof(int),
                                       cudaMemcpyDeviceToHost, s));
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[2], s));
@@ -556,6 +560,7 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
     rc = FetchScalars(st, &sc);
     if (rc != PPSFM_OK) return rc;
     solver_s += Secs(t_lin);
+    const int chol_failed = h_flags[0], intr_overflow = h_flags[1];  // (the stream is drained)
     if (intr_overflow)
       return fail(ctx, PPSFM_ERR_INVALID,
                   "a point is seen by more distinct cameras with variable intrinsics than supported");
