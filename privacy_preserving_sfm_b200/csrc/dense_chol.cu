@@ -198,34 +198,45 @@ __device__ __forceinline__ bool factor8(double* Cs, int k1, double* iv, int lane
   }
   double i0 = (r == c) ? 1.0 : 0.0, i1 = (r + 4 == c) ? 1.0 : 0.0;  // the identity, same layout
   __syncwarp();
-  // The warp is alone on its scheduler while it factors, so the step is bound by its instruction
-  // count as much as by the chain: columns <= j are simply left alone (their lanes then end up
-  // holding the unscaled factor column, no copies), and non-positive pivots are detected once, at
-  // the end (they turn the later pivots into NaN).
+  // Fraction-free (Bareiss) elimination: with B_j the j-th leading minor (B_-1 = 1),
+  //   b_rc <- (B_j b_rc - b_rj b_jc) / B_(j-1)      (b = true Schur complement x B_(j-1)),
+  // so the reciprocal a step needs is that of the PREVIOUS pivot and leaves the dependency chain
+  // (shuffle -> multiply -> FMA -> multiply, ~50 cycles, instead of shuffle -> reciprocal [58 +
+  // Newton] -> multiply -> FMA).  The warp is alone on its scheduler while it factors, so the
+  // step is bound by this chain and by its instruction count: columns <= j are simply left alone
+  // (their lanes end up holding column j of the factor, scaled — no copies), non-positive pivots
+  // are detected once at the end.  Magnitudes grow with the product of the pivots of ONE 8x8
+  // block (<= 8 factors: far inside the double range for any matrix the factorisation survives).
+  double rprev = 1.0;
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     const int jl = (j & 3) << 3;
     const double src = (j < 4) ? e0 : e1;  // row j lives in slot j >> 2 of lanes (j & 3, *)
     const double isrc = (j < 4) ? i0 : i1;
-    const double piv = shfl_d(src, jl | j);
-    const double u = shfl_d(src, jl | c);          // a_jc
-    const double t0 = shfl_d(e0, (r << 3) | j);    // a_rj
-    const double t1 = shfl_d(e1, (r << 3) | j);    // a_(r+4)j
-    const double ij = shfl_d(isrc, jl | c);        // row j of the inverse so far
-    const double rp = fast_rcp(piv);
-    const double sc = (c > j) ? u * rp : 0.0;
-    e0 -= t0 * sc;
-    e1 -= t1 * sc;
-    const double si = ij * rp;
-    if (r > j) i0 -= t0 * si;      // rows <= j of the inverse are final
-    if (r + 4 > j) i1 -= t1 * si;
+    const double piv = shfl_d(src, jl | j);        // B_j
+    const double u = shfl_d(src, jl | c);          // b_jc
+    const double t0 = shfl_d(e0, (r << 3) | j);    // b_rj
+    const double t1 = shfl_d(e1, (r << 3) | j);    // b_(r+4)j
+    const double ij = shfl_d(isrc, jl | c);        // row j of the (scaled) inverse so far
+    if (c > j) {
+      e0 = (piv * e0 - t0 * u) * rprev;
+      e1 = (piv * e1 - t1 * u) * rprev;
+    }
+    if (r > j) i0 = (piv * i0 - t0 * ij) * rprev;      // rows <= j of the inverse are final
+    if (r + 4 > j) i1 = (piv * i1 - t1 * ij) * rprev;
+    rprev = fast_rcp(piv);  // for the next step: off the chain
   }
-  // pivot of this lane's column: element (c, c), slot c >> 2 of lane (c & 3, c)
-  const double p0 = shfl_d(e0, ((c & 3) << 3) | c), p1 = shfl_d(e1, ((c & 3) << 3) | c);
-  const double pv = (c < 4) ? p0 : p1;
-  const bool bad = __any_sync(0xffffffffu, !(pv > 0.0));
+  // lane (r, c) now holds b_rc at step c and J_rc = B_(r-1) x (unit-lower inverse)_rc.  With
+  // s_k = 1 / sqrt(B_(k-1) B_k):  L_rc = b_rc s_c,  inv(L)_rc = J_rc s_r.
+  const int dl = ((c & 3) << 3) | c;  // lane of element (c, c); its slot is c >> 2
+  const double d0 = shfl_d(e0, dl), d1 = shfl_d(e1, dl);
+  const double Bc = (c < 4) ? d0 : d1;  // B_c
+  const int dlp = (((c + 7) & 3) << 3) | ((c + 7) & 7);  // element (c - 1, c - 1)
+  const double q0 = shfl_d(e0, dlp), q1 = shfl_d(e1, dlp);
+  const double Bp = (c == 0) ? 1.0 : ((c - 1 < 4) ? q0 : q1);  // B_(c-1)
+  const bool bad = __any_sync(0xffffffffu, !(Bc > 0.0));
   const double l0 = e0, l1 = e1;
-  const double rs = rsqrt(pv);
+  const double rs = rsqrt(Bp) * rsqrt(Bc);  // s_c (two factors: the product could overflow)
   const double rs0 = shfl_d(rs, r), rs1 = shfl_d(rs, r + 4);  // lanes 0..7 hold columns 0..7
   if (r >= c) Cs[(k1 + r) * kCS + k1 + c] = l0 * rs;
   Cs[(k1 + r + 4) * kCS + k1 + c] = l1 * rs;  // r + 4 >= c for the rows that matter; the
@@ -287,8 +298,9 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* Iv, const d
   }
   const bool want = hook->flag != nullptr && !hook->issued;
   const bool watch2 = hook->flag2 != nullptr;
-  if (want && tid == 32) {  // (warp 1 idles during the first 8x8 factor)
-    s_hook = ld_relaxed(hook->flag) != 0;
+  int poll_kind = 0, poll_val = 0;  // (thread 255) the poll in flight: 1 = flag, 2 = flag2
+  if (tid == 32) {  // (warp 1 idles during the first 8x8 factor)
+    s_hook = want ? (ld_relaxed(hook->flag) != 0) : 0;
     if (s_hook) fence_acquire();
   }
   __syncthreads();
@@ -317,15 +329,24 @@ __device__ __noinline__ void potrf64(double* Cs, double* Tm, double* Iv, const d
     if (tr && tid == 0 && bk == 0) tr[9] = global_ns();
     // (s_hook is only written between the two barriers of a round and read after the second one,
     // so every thread takes the same prefetch decision)
+    // Split-phase polling: the load issued in one round is looked at in the next, so its
+    // ~800 cycles of global latency never sit between two barriers of a round (a warp that waits
+    // for it there holds up all eight; in the late rounds the other warps have little else to do).
     if (tid == 255) {
-      if (want && !hook->issued) {
-        s_hook = ld_relaxed(hook->flag) != 0;
-        if (s_hook) fence_acquire();
+      if (poll_kind == 1 && poll_val) {
+        fence_acquire();
+        s_hook = 1;
+      } else if (poll_kind == 2 && poll_val) {
+        fence_acquire();
+        *hook->seen2 = 1;
+      }
+      poll_kind = 0;
+      if (want && !hook->issued && !s_hook) {
+        poll_val = ld_relaxed(hook->flag);
+        poll_kind = 1;
       } else if (watch2 && !*hook->seen2) {
-        if (ld_relaxed(hook->flag2) != 0) {
-          fence_acquire();
-          *hook->seen2 = 1;
-        }
+        poll_val = ld_relaxed(hook->flag2);
+        poll_kind = 2;
       }
     }
     // trailing update inside the tile on the FP64 tensor cores: 8x8 output tiles (lower part),

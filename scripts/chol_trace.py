@@ -38,3 +38,4 @@ if cnt:
           ", ".join(f"{n} {v:.2f}" for n, v in zip(names, acc / cnt)) +
           f"; packing after it {np.mean([(ev[(j, j)][2] - ev[(j, j)][14]) / 1e3 for j in range(ncols - 1)]):.2f}")
 
+
