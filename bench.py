@@ -8,7 +8,8 @@ distinct scenes per GPU (weak scaling: every rank registers its own images).  Se
 `ransac_sharded_call` (ONE call sharded over the GPUs, strong scaling),
 `ransac_mapper_call` (the mapper's adaptive settings on 2 000 correspondences), `ba` (config 4:
 500 cameras / 200 k points / 2 M observations, LM iterations/s, strong scaling over NCCL) and
-`ba_config3` (100 cameras / 30 k points / 300 k observations, one GPU).
+`ba_config3` (100 cameras / 30 k points / 300 k observations, one GPU), `init_config1` (config 1:
+the four-view initialisation on 2 000 tracks, host vs candidate models scored on the GPU).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
@@ -330,6 +331,7 @@ def run_b200(args):
     sharded = run_sharded_call(args, ctx, world, rank, dist, scenes[0] if rank == 0 else make_scene(),
                                opts)
     mapper = run_mapper_call(args, ctx, rank)
+    init1 = run_init_config1(args, ctx) if rank == 0 else None
     for corr in corrs:
         corr.free()
 
@@ -415,6 +417,7 @@ def run_b200(args):
         "host_cores": os.cpu_count(),
         "ransac_sharded_call": sharded,
         "ransac_mapper_call": mapper,
+        "init_config1": init1,
     }
     if ba_out is not None:
         out["ba"] = ba_out
@@ -504,6 +507,39 @@ def run_sharded_call(args, ctx, world, rank, dist, sc, opts):
 # The mapper's call shape (src/sfm/incremental_mapper.cc:673-681): a few thousand correspondences,
 # min 100 / max 10 000 trials, adaptive abort.  Latency bound: the solve kernel is the cost.
 # ------------------------------------------------------------------------------------------------
+def run_init_config1(args, ctx):
+    """BASELINE.json configs[0] (SURVEY.md 8 f4): init::initialize_reconstruction on 2 000 lifted-line
+    tracks (1 000 aligned), 10 % outliers, max_error 0.005: the host run (the reference's CPU path,
+    restated) against the run whose candidate models are scored on the GPU; the two must agree
+    bit for bit."""
+    from privacy_preserving_sfm_b200 import initializer as I, synthetic as S
+    lines, aligned, gravity, gt = S.make_init_scene(2000, 1000, 200, seed=S.SCENE_SEED)
+    opt = I.InitOptions(max_error=0.005)
+    I.initialize_reconstruction(lines[:, :200], aligned[:, :200], gravity, opt, ctx=ctx)  # warm-up
+    t0 = time.perf_counter()
+    okg, pg, rg, repg = I.initialize_reconstruction(lines, aligned, gravity, opt, ctx=ctx)
+    t1 = time.perf_counter()
+    out = {"metric": "four-view initialisation (config 1), wall time per run", "unit": "ms",
+           "gpu_scored_ms": 1e3 * (t1 - t0), "gpu_launches": int(repg.gpu_launches),
+           "iterations": [int(repg.iterations_2d), int(repg.iterations_3d)],
+           "inlier_ratio": rg,
+           "max_pose_error": float(np.abs(_normalise_init(pg) - gt).max()) if okg else None,
+           "config": {"tracks": 2000, "aligned": 1000, "outliers": 200, "max_error": 0.005}}
+    if not args.no_cpu_baseline:
+        t0 = time.perf_counter()
+        okh, ph, rh, reph = I.initialize_reconstruction(lines, aligned, gravity, opt)
+        out["host_ms"] = 1e3 * (time.perf_counter() - t0)
+        out["identical_to_host_run"] = bool(okh == okg and rh == rg and np.array_equal(ph, pg))
+        assert out["identical_to_host_run"], "GPU-scored initialisation differs from the host run"
+    return out
+
+
+def _normalise_init(poses):
+    p = poses.copy()
+    p[:, :, 3] /= np.linalg.norm(p[1, :, 3])
+    return p
+
+
 def run_mapper_call(args, ctx, rank):
     import privacy_preserving_sfm_b200 as pp
     from privacy_preserving_sfm_b200 import synthetic as S
