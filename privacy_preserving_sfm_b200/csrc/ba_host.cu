@@ -509,6 +509,9 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
   if (done) sum->termination_type = 0;
   double solver_s = 0;
 
+  static const bool gap_trace = tune_int("PPSFM_BA_GAPS", 0) != 0;
+  double g_enq1 = 0, g_wait1 = 0, g_enq2 = 0, g_wait2 = 0;
+  int g_n = 0;
   for (int iter = 0; !done && iter < opt.max_num_iterations; ++iter) {
     const auto t_lin = std::chrono::steady_clock::now();
     // --- reduced camera system + dense Cholesky
@@ -557,9 +560,12 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       if (rc != PPSFM_OK) return rc;
     }
     PPSFM_CUDA(ctx, cudaEventRecord(st->evp[3], s));
+    const double t_enq1 = Secs(t_lin);
     rc = FetchScalars(st, &sc);
     if (rc != PPSFM_OK) return rc;
     solver_s += Secs(t_lin);
+    g_enq1 += t_enq1;
+    g_wait1 += Secs(t_lin) - t_enq1;
     const int chol_failed = h_flags[0], intr_overflow = h_flags[1];  // (the stream is drained)
     if (intr_overflow)
       return fail(ctx, PPSFM_ERR_INVALID,
@@ -612,12 +618,17 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
         std::swap(d.cam_params, st->cam_params_n);
         std::swap(d.img_params, st->img_params_n);
       }
+      const auto t_acc = std::chrono::steady_clock::now();
       rc = linearize(d.q, d.t, d.X, true);
       if (rc != PPSFM_OK) return rc;
       rc = normal_equations();
       if (rc != PPSFM_OK) return rc;
+      const double t_enq2 = Secs(t_acc);
       rc = cost_and_gradient(&cost, &gmax);
       if (rc != PPSFM_OK) return rc;
+      g_enq2 += t_enq2;
+      g_wait2 += Secs(t_acc) - t_enq2;
+      ++g_n;
       ++sum->num_successful_steps;
       trace(cost, radius, 1);
       if (gmax <= opt.gradient_tolerance) {
@@ -635,6 +646,10 @@ int BaRun(BaState* st, ppsfm_ba_summary* sum) {
       }
     }
   }
+  if (gap_trace && g_n > 0)
+    std::fprintf(stderr, "[ba gaps] per iteration (us): enqueue solve batch %.0f, wait %.0f | "
+                 "enqueue linearise batch %.0f, wait (incl. gradient launch) %.0f\n",
+                 1e6 * g_enq1 / g_n, 1e6 * g_wait1 / g_n, 1e6 * g_enq2 / g_n, 1e6 * g_wait2 / g_n);
   PPSFM_CUDA(ctx, cudaStreamSynchronize(s));
   PPSFM_CUDA(ctx, cudaGetLastError());
   drain_lin_events();
