@@ -433,22 +433,33 @@ int RansacResident(ppsfm_ctx* ctx, const ppsfm_corr* corr, const ppsfm_ransac_op
       cand_sum.resize(EE);
       PPSFM_CUDA(ctx, ctx->h_esum.reserve(sizeof(double) * (size_t)EE));
       PPSFM_CUDA(ctx, ctx->h_ecnt.reserve(sizeof(unsigned long long) * (size_t)EE));
-      const int kBatch = 32;
-      PPSFM_CUDA(ctx, ctx->d_emodels.reserve(sizeof(double) * 12 * kBatch));
-      PPSFM_CUDA(ctx, ctx->d_rbuf.reserve(sizeof(double) * (size_t)kBatch * n));
-      PPSFM_CUDA(ctx, ctx->d_ecnt.reserve(sizeof(unsigned long long) * kBatch));
-      PPSFM_CUDA(ctx, ctx->d_esum.reserve(sizeof(double) * kBatch));
+      // Batches of up to 64 MB of residuals.  With a high inlier ratio (the mapper's registration
+      // calls) most good models TIE at the full inlier count, so a wave can hold thousands of
+      // candidates: they are gathered by one kernel from an index list, not copied one by one.
+      const int kBatch = (int)std::min<size_t>(8192, std::max<size_t>(32, (64u << 20) / (8 * n)));
+      const int cap = std::min(kBatch, EE);
+      PPSFM_CUDA(ctx, ctx->d_emodels.reserve(sizeof(double) * 12 * cap));
+      PPSFM_CUDA(ctx, ctx->d_rbuf.reserve(sizeof(double) * (size_t)cap * n));
+      PPSFM_CUDA(ctx, ctx->d_ecnt.reserve(sizeof(unsigned long long) * cap));
+      PPSFM_CUDA(ctx, ctx->d_esum.reserve(sizeof(double) * cap));
+      PPSFM_CUDA(ctx, ctx->d_eidx.reserve(sizeof(long long) * cap));
+      PPSFM_CUDA(ctx, ctx->h_eidx.reserve(sizeof(long long) * (size_t)EE));
+      long long* h_idx = ctx->h_eidx.as<long long>();
+      for (int e = 0; e < E; ++e) h_idx[e] = (long long)model_src(cand[e]);
       for (int e0 = 0; e0 < EE; e0 += kBatch) {
         const int ne = std::min(kBatch, EE - e0);
-        for (int e = e0; e < e0 + ne; ++e) {
-          double* dst = ctx->d_emodels.as<double>() + (size_t)(e - e0) * 12;
-          if (e < E)
-            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, sl.d_models.as<double>() + model_src(cand[e]),
-                                            sizeof(double) * 12, cudaMemcpyDeviceToDevice, hi));
-          else
-            PPSFM_CUDA(ctx, cudaMemcpyAsync(dst, best_model, sizeof(double) * 12,
-                                            cudaMemcpyHostToDevice, hi));
+        const int ng = std::min(ne, E - e0);  // gathered from the wave; the last one may be the carried best
+        if (ng > 0) {
+          PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_eidx.p, h_idx + e0, sizeof(long long) * ng,
+                                          cudaMemcpyHostToDevice, hi));
+          launch_gather_models(sl.d_models.as<double>(), ctx->d_eidx.as<long long>(), ng,
+                               ctx->d_emodels.as<double>(), hi);
+          ++ctx->timing.kernel_launches;
         }
+        if (ne > std::max(ng, 0))
+          PPSFM_CUDA(ctx, cudaMemcpyAsync(ctx->d_emodels.as<double>() + (size_t)std::max(ng, 0) * 12,
+                                          best_model, sizeof(double) * 12, cudaMemcpyHostToDevice,
+                                          hi));
         PPSFM_CUDA(ctx, cudaEventRecord(ctx->ev[3], hi));
         launch_exact(corr->corr6, (int)n, ctx->d_emodels.as<double>(), ne, max_residual,
                      ctx->d_rbuf.as<double>(), nullptr, ctx->d_ecnt.as<unsigned long long>(),

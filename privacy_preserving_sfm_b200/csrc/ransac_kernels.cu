@@ -757,7 +757,9 @@ __global__ void exact_residual_kernel(const double* __restrict__ corr6, int n,
   const double* c = corr6 + (size_t)i * 6;
   const double l_0 = c[0], l_1 = c[1], l_2 = c[2];
   const double X_0 = c[3], X_1 = c[4], X_2 = c[5];
-  for (int e = 0; e < num_e; ++e) {
+  // blockIdx.y strides over the models (few correspondences x many tied candidates — the
+  // mapper's registration calls — would otherwise run on a couple of CTAs)
+  for (int e = blockIdx.y; e < num_e; e += gridDim.y) {
     const double* P = emodels + (size_t)e * 12;
     const double px_2 = P[2] * X_0 + P[5] * X_1 + P[8] * X_2 + P[11];
     double r2;
@@ -839,12 +841,29 @@ seq_support_kernel(const double* __restrict__ rbuf, int n, int num_e, double max
   }
 }
 
+// dst[e] = the 12 doubles at src + off[e] (candidate models of a wave -> a dense batch)
+__global__ void gather_models_kernel(const double* __restrict__ src,
+                                     const long long* __restrict__ off, int ne,
+                                     double* __restrict__ dst) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= 12 * ne) return;
+  const int e = i / 12, j = i - 12 * e;
+  dst[i] = src[off[e] + j];
+}
+void launch_gather_models(const double* src, const long long* off, int ne, double* dst,
+                          cudaStream_t s) {
+  if (ne > 0) gather_models_kernel<<<(12 * ne + 255) / 256, 256, 0, s>>>(src, off, ne, dst);
+}
+
 void launch_exact(const double* corr6, int n, const double* emodels, int num_e,
                   double max_residual, double* rbuf, uint8_t* mask, unsigned long long* ecnt,
                   double* esum, cudaStream_t s) {
   if (num_e <= 0 || n <= 0) return;
-  exact_residual_kernel<<<(n + 255) / 256, 256, 0, s>>>(corr6, n, emodels, num_e, max_residual,
-                                                        rbuf, mask);
+  const int bx = (n + 255) / 256;
+  int by = 1;  // ~ 4 CTAs per SM in total
+  while (by < num_e && bx * by < 592) by *= 2;
+  exact_residual_kernel<<<dim3(bx, by), 256, 0, s>>>(corr6, n, emodels, num_e, max_residual,
+                                                     rbuf, mask);
   if (ecnt != nullptr) {
     seq_support_kernel<<<num_e, kSeqThreads, 0, s>>>(rbuf, n, num_e, max_residual, ecnt, esum);
   }

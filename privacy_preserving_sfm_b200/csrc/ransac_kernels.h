@@ -50,6 +50,9 @@ void launch_score(const double* corr6, const float* corr6f, const double* bounds
 // best_lb = max(best_lb, max of the first K counts): after the all-reduce of a sharded wave
 void launch_raise_best_lb(const unsigned* cnt, const int* offsets, int num_trials,
                           unsigned* best_lb, cudaStream_t s);
+// dst[e * 12 + j] = src[off[e] + j], e < ne (off on the device)
+void launch_gather_models(const double* src, const long long* off, int ne, double* dst,
+                          cudaStream_t s);
 // Largest double r with fl(r*r) <= max_residual.
 double inlier_abs_threshold(double max_residual);
 // rbuf: num_e x n residuals; mask (optional): num_e x n; ecnt/esum (optional): num_e.

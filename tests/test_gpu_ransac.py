@@ -154,6 +154,26 @@ def test_ransac_matches_oracle(ctx, oracle, n, opts, cases):
         assert ctx.prng_peek() == oracle.prng_peek(), tag   # same number of PRNG draws
 
 
+def test_ransac_many_tied_candidates_stay_cheap(ctx, oracle):
+    """The mapper's registration calls: few hundred correspondences, almost all inliers, so most
+    good models TIE at the full inlier count and a wave holds thousands of candidates for the
+    index-order support pass.  They are gathered and evaluated in a few launches (this call took
+    108 launches / 9.5 ms when candidates were copied one by one in batches of 32), and the result
+    is the oracle's."""
+    sc = S.make_abs_pose_scene(n=500, inlier_ratio=0.95, noise_px=0.5, aligned_fraction=0.4, seed=5)
+    o = RANSACOptions(max_error=0.012, min_inlier_ratio=0.25, confidence=0.99999,
+                      min_num_trials=100, max_num_trials=10000)
+    ctx.set_prng_seed(0)
+    oracle.set_prng_seed(0)
+    rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+    tm = ctx.ransac_timing()
+    oref, omask = oracle.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], _oracle_opts(oracle, o))
+    assert rep.success and oref.success and rep.num_trials == oref.num_trials
+    assert (rep.best_trial, rep.best_model_idx) == (oref.best_trial, oref.best_model_idx)
+    assert rep.residual_sum == oref.residual_sum and np.array_equal(mask, omask)
+    assert tm.kernel_launches <= 16, tm.kernel_launches
+
+
 @pytest.mark.parametrize("first,growth,chunks,prune_min", [
     (10, 2, 4, 2048), (3, 100, 4, 2048), (4, 3, 4, 2048), (3, 100, 1, 2048),
     (10, 2, 4, 128), (3, 100, 4, 128), (5, 2, 4, 256)])
