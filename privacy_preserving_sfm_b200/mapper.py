@@ -85,6 +85,14 @@ class IncrementalMapper:
         self.points = np.full((p, 3), np.nan)
         self.has_point = np.zeros(p, bool)
         self.obs_on = scene.visible.copy()       # observation (i, p) still part of its track
+        # sparse view of the (static) visibility: the images that see point p, ascending
+        pi, ii = np.nonzero(scene.visible.T)
+        self._csc_ptr = np.concatenate([[0], np.cumsum(np.bincount(pi, minlength=p))]).astype(np.int64)
+        self._csc_img = ii.astype(np.int64)
+        # find_next_image: visible-point counts of the unregistered images, kept up to date from
+        # the changes of has_point (their obs_on rows do not change before they are registered)
+        self._score = np.zeros(n, np.int64)
+        self._score_has_point = np.zeros(p, bool)
         self.max_reproj_error_px = max_reproj_error_px
         self.filter_max_reproj_error, self.filter_min_tri_angle = filter_max_reproj_error, filter_min_tri_angle
         self.ba_every, self.verbose = ba_every, verbose
@@ -116,11 +124,40 @@ class IncrementalMapper:
 
     # ---- RegisterNextImage ------------------------------------------------------------------
     def find_next_image(self):
-        sc = self.scene
-        score = (self.obs_on & self.has_point[None, :]).sum(axis=1).astype(float)
+        # score[i] = number of triangulated points image i sees; only needed for unregistered
+        # images, whose rows of obs_on still equal the scene's visibility: update the counts by
+        # the points whose has_point flag changed since the last call
+        changed = np.flatnonzero(self.has_point != self._score_has_point)
+        if len(changed):
+            gained = changed[self.has_point[changed]]
+            lost = changed[~self.has_point[changed]]
+            if len(gained):
+                self._score += self.scene.visible[:, gained].sum(axis=1)
+            if len(lost):
+                self._score -= self.scene.visible[:, lost].sum(axis=1)
+            self._score_has_point[changed] = self.has_point[changed]
+        score = self._score.astype(float)
         score[self.registered] = -1
         i = int(np.argmax(score))
         return i if score[i] >= 6 else None
+
+    def _views(self, point_ids):
+        """Active observations of the given points from registered images: (image, index into
+        point_ids), track-major, the views of a track in registration order."""
+        n = len(self.qvec)
+        rank = np.full(n, -1, np.int64)
+        rank[self.registered] = np.arange(len(self.registered))
+        point_ids = np.asarray(point_ids, np.int64)
+        starts = self._csc_ptr[point_ids]
+        lens = self._csc_ptr[point_ids + 1] - starts
+        total = int(lens.sum())
+        t_idx = np.repeat(np.arange(len(point_ids)), lens)
+        offs = np.arange(total) - np.repeat(np.cumsum(lens) - lens, lens) + np.repeat(starts, lens)
+        img = self._csc_img[offs]
+        keep = (rank[img] >= 0) & self.obs_on[img, point_ids[t_idx]]
+        img, t_idx = img[keep], t_idx[keep]
+        order = np.lexsort((rank[img], t_idx))
+        return img[order], t_idx[order]
 
     def register_next_image(self, i):
         sc = self.scene
@@ -148,14 +185,10 @@ class IncrementalMapper:
     # ---- TriangulateImage -------------------------------------------------------------------
     def _track_problem(self, point_ids, use_points=None):
         sc = self.scene
-        reg = np.array(self.registered)
-        vis = self.obs_on[np.ix_(reg, point_ids)]                   # [R, T]
-        counts = vis.sum(axis=0)
+        point_ids = np.asarray(point_ids, np.int64)
+        obs_image, t_idx = self._views(point_ids)                   # track-major order
+        counts = np.bincount(t_idx, minlength=len(point_ids))
         track_start = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-        r_idx, t_idx = np.nonzero(vis.T)[::-1]                      # track-major order
-        order = np.lexsort((r_idx, t_idx))
-        r_idx, t_idx = r_idx[order], t_idx[order]
-        obs_image = reg[r_idx]
         obs_line = sc.lines[obs_image, point_ids[t_idx]]
         obs_aligned = sc.aligned[point_ids[t_idx]].astype(np.uint8)
         pts = np.zeros((len(point_ids), 3)) if use_points is None else use_points
@@ -168,7 +201,7 @@ class IncrementalMapper:
         reg = np.array(self.registered)
         # tracks need a non-aligned line (incremental_triangulator.cc:512-515) and >= 3 views
         open_pts = np.flatnonzero(~self.has_point & ~self.scene.aligned)
-        views = self.obs_on[np.ix_(reg, open_pts)].sum(axis=0)
+        views = np.bincount(self._views(open_pts)[1], minlength=len(open_pts))
         cand = open_pts[views >= 3]
         if len(cand) == 0:
             return 0
@@ -234,8 +267,9 @@ class IncrementalMapper:
             return
         # FindLocalBundle: the images sharing most points with image i
         seen_idx = np.flatnonzero(seen)
-        sub_seen = self.obs_on[np.ix_(reg, seen_idx)]             # [R, points of image i]
-        shared = sub_seen.sum(axis=1)
+        img_s, t_s = self._views(seen_idx)                        # registered views of its points
+        shared_all = np.bincount(img_s, minlength=len(self.qvec))
+        shared = shared_all[reg]
         shared[reg == i] = -1
         order = np.argsort(-shared, kind="stable")[:self.ba_local_num_images - 1]
         local = [int(reg[k]) for k in order if shared[k] > 0]
@@ -244,19 +278,25 @@ class IncrementalMapper:
         bundle = [i] + local
         in_bundle = np.zeros(len(self.qvec), bool)
         in_bundle[bundle] = True
-        is_reg = np.zeros(len(self.qvec), bool)
-        is_reg[reg] = True
         # variable points: those of the new image with a short track (kMaxTrackLength = 15)
         variable = np.zeros(len(seen), bool)
-        variable[seen_idx[sub_seen.sum(axis=0) <= 15]] = True
+        track_len = np.bincount(t_s, minlength=len(seen_idx))
+        variable[seen_idx[track_len <= 15]] = True
         # observations: everything the bundle images see (AddImageToProblem), plus the views of
-        # the variable points from registered images outside the bundle (AddPointToProblem)
-        pts_any = np.flatnonzero(((self.obs_on[bundle]) & self.has_point[None, :]).any(axis=0))
-        img_ids = np.flatnonzero(is_reg)
-        sub = self.obs_on[np.ix_(img_ids, pts_any)]
-        keep = in_bundle[img_ids][:, None] | variable[pts_any][None, :]
-        ii, pp = np.nonzero(sub & keep)
-        obs_image, obs_point = img_ids[ii], pts_any[pp]
+        # the variable points from registered images outside the bundle (AddPointToProblem);
+        # ordered by (image, point)
+        oi, op = [], []
+        for b_img in bundle:
+            pts_b = np.flatnonzero(self.obs_on[b_img] & self.has_point)
+            oi.append(np.full(len(pts_b), b_img, np.int64))
+            op.append(pts_b)
+        out = variable[seen_idx[t_s]] & ~in_bundle[img_s]
+        oi.append(img_s[out])
+        op.append(seen_idx[t_s[out]])
+        obs_image, obs_point = np.concatenate(oi), np.concatenate(op)
+        order = np.lexsort((obs_point, obs_image))
+        obs_image, obs_point = obs_image[order], obs_point[order]
+        pts_any = np.unique(np.concatenate(op[:len(bundle)]))
         flags = np.ones(len(self.qvec), np.uint8)                 # outside the bundle: constant
         flags[bundle] = 0
         if len(local) == 1:                                       # (:828-839)
