@@ -261,14 +261,15 @@ __device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, do
 }
 
 constexpr int kGThreads = 256;
-constexpr int kUnroll = 8;  // entries whose record loads are in flight together, per warp
+constexpr int kUnroll = 4;  // entries whose record loads are in flight together, per warp
 
-// Three CTAs (24 warps) per SM: the kernel is bound by the latency of its scattered 192-byte
-// record reads, and warps in flight are what hides it — measured at config 4: 16 warps / SM 0.90 ms,
-// 24 warps 0.70 ms, 32 warps (64 registers, spills) 0.70 ms; 8 -> 16 entries per batch at 16 warps
-// gains 4 %, a second accumulator chain nothing, staging the records through shared memory with
-// cp.async (3 stages x 8 entries per warp in flight, 16 warps) nothing (profiles/r02_gather_variants.txt).
-__global__ void __launch_bounds__(kGThreads, 3)
+// Five CTAs (40 warps) per SM with four entries per batch (40 registers): the kernel is bound by
+// the latency of its scattered 192-byte record reads, and WARPS in flight are what hides it — at
+// config 4: 16 warps x 8 entries 0.90 ms, 24 x 8 0.70 ms, 40 x 4 0.62 ms, 64 x 2 0.61 ms (spills),
+// 32 x 8 (spills) 0.70 ms; 16 entries per batch at 16 warps gains 4 %, a second accumulator
+// chain nothing, staging the records through shared memory with cp.async (3 stages x 8 entries
+// per warp in flight, 16 warps) nothing (profiles/r02_gather_variants.txt).
+__global__ void __launch_bounds__(kGThreads, 5)
 ba_schur_gather_kernel(BaDev d, double radius, double min_diag, double max_diag,
                        int include_cam) {
   const int w = (int)(((int64_t)blockIdx.x * kGThreads + threadIdx.x) >> 5);
