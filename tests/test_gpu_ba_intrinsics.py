@@ -201,9 +201,9 @@ def test_resident_problem_reset_restores_the_intrinsics(ctx):
     ok, s2 = rp.run()
     rp.download()
     rp.free()
-    assert k1 != 0.08 and abs(a.camera_params[0, 3] - k1) <= 1e-9 * abs(k1)
+    assert k1 != 0.08 and abs(a.camera_params[0, 3] - k1) <= 1e-6 * abs(k1)
     assert s1.initial_cost == s2.initial_cost      # the run after reset starts from k = 0.08 again
-    assert abs(s1.final_cost - s2.final_cost) <= 1e-10 * s1.final_cost
+    assert abs(s1.final_cost - s2.final_cost) <= 1e-8 * s1.final_cost
 
 
 def test_pose_refinement_with_focal_length(ctx, oracle):
