@@ -147,3 +147,24 @@ def test_fixed_size_least_squares_equals_the_generic_routine(m, n):
         assert rc == 0 and np.array_equal(xg, xf)
         if k % 5 == 0:
             assert np.allclose(xg, np.linalg.lstsq(A, b, rcond=None)[0], atol=1e-9)
+
+
+@pytest.mark.parametrize("n,n_al,n_out,seed", [(100, 50, 10, 4), (160, 90, 30, 15)])
+def test_batched_scoring_hooks_reproduce_the_plain_run(tmp_path, n, n_al, n_out, seed):
+    """The optional Solver members ScoreModels / Materialize (lazy candidate models scored in one
+    batch — what csrc/init_kernels.cu does on the GPU) with a HOST scorer built on the shared
+    arithmetic of cpp/ppsfm_init_math.h: initialize_reconstruction must return exactly what the
+    plain run returns (tests/cpp/init_scorer_test.cc; no GPU involved)."""
+    import subprocess
+    root = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..")
+    exe = str(tmp_path / "init_scorer_test")
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall",
+                           "-I" + os.path.join(root, "privacy_preserving_sfm_b200", "cpp"),
+                           os.path.join(root, "tests", "cpp", "init_scorer_test.cc"), "-o", exe])
+    lines, aligned, gravity, _ = S.make_init_scene(n, n_al, n_out, seed=seed)
+    blob = np.concatenate([np.ascontiguousarray(lines, np.float64).ravel(),
+                           np.ascontiguousarray(aligned, np.float64).ravel(),
+                           np.ascontiguousarray(gravity, np.float64).ravel()]).tobytes()
+    r = subprocess.run([exe, str(n)], input=blob, capture_output=True)
+    assert r.returncode == 0, r.stdout.decode() + r.stderr.decode()
+    assert b"identical 1" in r.stdout
