@@ -85,12 +85,36 @@ def ba_case():
             "state_sha256": hashlib.sha256(state.astype(np.float64).tobytes()).hexdigest()}
 
 
+def ba_intrinsics_case():
+    """refine_extra_params on two SIMPLE_RADIAL cameras, the second in ConstantCameras()
+    (ParameterizeCameras, src/optim/bundle_adjustment.cc:490-528); noisy scene, 5 LM iterations."""
+    sb = S.make_ba_scene(num_cams=6, num_points=200, obs_per_point=4, seed=107, noise_px=2.0)
+    flags = np.zeros(6, np.uint8)
+    flags[0], flags[1] = 1, 2
+    prm = [[1000.0, 500.0, 500.0, 0.08], [1000.0, 500.0, 500.0, 0.05]]
+    a = O.BaArrays(sb["qvecs"], sb["tvecs"], sb["points"], sb["obs_cam"], sb["obs_pt"],
+                   sb["obs_line"], [2, 2], prm, image_camera=np.arange(6) % 2, pose_flags=flags,
+                   camera_const=[0, 1])
+    ok, s = O.ba_solve(a, O.ba_default_options(num_threads=1, max_num_iterations=5,
+                                               refine_extra_params=1))
+    state = np.concatenate([a.qvecs.ravel(), a.tvecs.ravel(), a.points.ravel(),
+                            a.camera_params.ravel()])
+    return {"ok": bool(ok), "successful_steps": int(s.num_successful_steps),
+            "unsuccessful_steps": int(s.num_unsuccessful_steps),
+            "effective_parameters": int(s.num_effective_parameters_reduced),
+            "initial_cost": float(s.initial_cost).hex(), "final_cost": float(s.final_cost).hex(),
+            "k_camera0": float(a.camera_params[0, 3]).hex(),
+            "k_camera1": float(a.camera_params[1, 3]).hex(),
+            "state_sha256": hashlib.sha256(state.astype(np.float64).tobytes()).hexdigest()}
+
+
 def main():
     O.build()
     gold = {"ransac": {name: dict(scene=kw, options=list(opt), expect=ransac_case(kw, opt))
                        for name, kw, opt in RANSAC_CASES},
             "line_residuals": residual_case(), "p6l_estimate": p6l_case(),
-            "ba_solve_single_thread": ba_case()}
+            "ba_solve_single_thread": ba_case(),
+            "ba_intrinsics_single_thread": ba_intrinsics_case()}
     with open(os.path.join(HERE, "oracle_vectors.json"), "w") as f:
         json.dump(gold, f, indent=1)
     print("wrote", os.path.join(HERE, "oracle_vectors.json"))

@@ -81,3 +81,26 @@ def test_gpu_ba_reproduces_golden(ctx):
     ic, fc = float.fromhex(g["initial_cost"]), float.fromhex(g["final_cost"])
     assert abs(s.initial_cost - ic) <= 1e-11 * ic       # floating-point path: tolerance, not bits
     assert abs(s.final_cost - fc) <= 1e-9 * fc
+
+
+def test_gpu_ba_intrinsics_reproduces_golden(ctx):
+    g = _gold()["ba_intrinsics_single_thread"]
+    sb = S.make_ba_scene(num_cams=6, num_points=200, obs_per_point=4, seed=107, noise_px=2.0)
+    flags = np.zeros(6, np.uint8)
+    flags[0], flags[1] = 1, 2
+    prm = [[1000.0, 500.0, 500.0, 0.08], [1000.0, 500.0, 500.0, 0.05]]
+    a = ba.BaArrays(sb["qvecs"], sb["tvecs"], sb["points"], sb["obs_cam"], sb["obs_pt"],
+                    sb["obs_line"], [2, 2], prm, image_camera=np.arange(6) % 2, pose_flags=flags,
+                    camera_const=[0, 1])
+    ok, s = ba.solve_arrays(ctx, a, ba.default_solver_options(max_num_iterations=5,
+                                                              refine_extra_params=1))
+    assert ok == g["ok"]
+    assert (s.num_successful_steps, s.num_unsuccessful_steps) == \
+        (g["successful_steps"], g["unsuccessful_steps"])
+    assert s.num_effective_parameters_reduced == g["effective_parameters"]
+    ic, fc = float.fromhex(g["initial_cost"]), float.fromhex(g["final_cost"])
+    assert abs(s.initial_cost - ic) <= 1e-11 * ic       # floating-point path: tolerance, not bits
+    assert abs(s.final_cost - fc) <= 1e-8 * fc
+    k0, k1 = float.fromhex(g["k_camera0"]), float.fromhex(g["k_camera1"])
+    assert abs(a.camera_params[0, 3] - k0) <= 1e-6 * abs(k0)
+    assert a.camera_params[1, 3] == k1 == 0.05          # the constant camera
