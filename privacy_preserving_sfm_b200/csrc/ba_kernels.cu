@@ -422,28 +422,57 @@ __global__ void ba_jacobi_scales_kernel(BaDev d) {
 // Back-substitution, model cost change, candidate state.
 // ------------------------------------------------------------------------------------------
 // (1) one thread per observation: u = J_c dc (kept for the model-cost pass), and the point-side
-//     accumulation acc_p += J_p^T u by atomics (acc is pre-loaded with g_p; lives in d.dp).
+//     sums s_p = sum_e J_p,e^T u_e (into d.dp, zeroed before).  The observations of a point are
+//     contiguous, so this is the segmented warp reduction of ba_point_normal_kernel: segments
+//     inside one warp batch are stored, the (at most two per batch) that cross a batch boundary
+//     are added atomically to zero — two partials commute, so the sums, and with them the whole
+//     solve, are reproducible run to run for tracks of <= 32 observations.
 __global__ void __launch_bounds__(kThreads) ba_backsub_accum_kernel(BaDev d) {
   const int64_t K = d.K;
   const int64_t k = (int64_t)blockIdx.x * kThreads + threadIdx.x;
-  if (k >= K) return;
-  const int b = d.cam_block[d.obs_cam[k]];
-  double u0 = 0.0, u1 = 0.0;
-  if (b >= 0) {
+  const int lane = threadIdx.x & 31;
+  int pid = -1;
+  double v[3] = {0.0, 0.0, 0.0};
+  if (k < K) {
+    pid = d.obs_pt[k];
+    const int b = d.cam_block[d.obs_cam[k]];
+    double u0 = 0.0, u1 = 0.0;
+    if (b >= 0) {
 #pragma unroll
-    for (int a = 0; a < 6; ++a) {
-      const double dca = d.dc[6 * b + a];
-      u0 += JC(a, k) * dca;
-      u1 += JC((6 + a), k) * dca;
+      for (int a = 0; a < 6; ++a) {
+        const double dca = d.dc[6 * b + a];
+        u0 += JC(a, k) * dca;
+        u1 += JC((6 + a), k) * dca;
+      }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) v[c] = JP(c, k) * u0 + JP((3 + c), k) * u1;
     }
-    const int p = d.obs_pt[k];
-    const int P = d.P;
-#pragma unroll
-    for (int c = 0; c < 3; ++c)
-      atomicAdd(&d.dp[(size_t)c * P + p], JP(c, k) * u0 + JP((3 + c), k) * u1);
+    d.u[k] = u0;
+    d.u[K + k] = u1;
   }
-  d.u[k] = u0;
-  d.u[K + k] = u1;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int other = __shfl_down_sync(0xffffffffu, pid, off);
+    const bool take = (lane + off < 32) && (other == pid);
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      const double t = __shfl_down_sync(0xffffffffu, v[i], off);
+      if (take) v[i] += t;
+    }
+  }
+  const int prev = __shfl_up_sync(0xffffffffu, pid, 1);
+  const bool head = pid >= 0 && (lane == 0 || prev != pid);
+  if (!head) return;
+  const int64_t batch_end = (k - lane) + 32;
+  const bool whole = d.pt_start[pid] == k && d.pt_start[pid + 1] <= batch_end;
+  const int P = d.P;
+  if (whole) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) d.dp[(size_t)c * P + pid] = v[c];
+  } else {
+#pragma unroll
+    for (int c = 0; c < 3; ++c) atomicAdd(&d.dp[(size_t)c * P + pid], v[c]);
+  }
 }
 
 // (2) one thread per point: dp = -V^-1 acc, candidate point, step / x norm partials.
@@ -454,7 +483,9 @@ ba_point_step_kernel(BaDev d, double* __restrict__ partials, int stride) {
   const int P = d.P;
   double step_sq = 0.0, x_sq = 0.0;
   if (p < P) {
-    const double acc0 = d.dp[p], acc1 = d.dp[P + p], acc2 = d.dp[2 * P + p];
+    // acc = g_p + sum_e J_p,e^T u_e
+    const double acc0 = d.gp[p] + d.dp[p], acc1 = d.gp[P + p] + d.dp[P + p],
+                 acc2 = d.gp[2 * P + p] + d.dp[2 * P + p];
     const double w00 = d.Vinv[p], w01 = d.Vinv[P + p], w02 = d.Vinv[2 * P + p];
     const double w11 = d.Vinv[3 * P + p], w12 = d.Vinv[4 * P + p], w22 = d.Vinv[5 * P + p];
     const double dp0 = -(w00 * acc0 + w01 * acc1 + w02 * acc2);
@@ -740,7 +771,7 @@ int launch_backsubstitute_and_update(const BaDev& d, bool count_camera_norms, cu
   const int pblocks = (d.P + kThreads - 1) / kThreads;
   const int oblocks = (int)((d.K + kThreads - 1) / kThreads);
   if (pblocks > 0 && oblocks > 0) {
-    cudaMemcpyAsync(d.dp, d.gp, sizeof(double) * 3 * (size_t)d.P, cudaMemcpyDeviceToDevice, s);
+    cudaMemsetAsync(d.dp, 0, sizeof(double) * 3 * (size_t)d.P, s);
     ba_backsub_accum_kernel<<<oblocks, kThreads, 0, s>>>(d);
     n += launch_intr_backsub(d, s);  // (variable intrinsics only)
     ba_point_step_kernel<<<pblocks, kThreads, 0, s>>>(d, d.partials, d.num_partials);

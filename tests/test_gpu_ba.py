@@ -324,3 +324,24 @@ def test_bundle_adjuster_out_of_set_observations(ctx):
     assert any(not np.array_equal(rec.images[i].tvec, before[i][1]) for i in (2, 3))
     moved = [pid for pid in pts_before if not np.array_equal(rec.points3D[pid].xyz, pts_before[pid])]
     assert moved and all(100 <= pid < 160 for pid in moved)   # only configured points move
+
+
+def test_ba_solve_is_reproducible_run_to_run(ctx):
+    """No floating-point atomics whose order matters on the default path (segmented reductions,
+    ordered partial sums, a dataflow factorisation with a fixed summation order): two solves of
+    the same problem return the same bits (tracks of <= 32 observations)."""
+    sc = _scene(num_cams=12, num_points=3000, obs=6, seed=77)
+    outs = []
+    for _ in range(3):
+        a, _unused = ba.BaArrays(sc["qvecs"], sc["tvecs"], sc["points"], sc["obs_cam"], sc["obs_pt"],
+                                 sc["obs_line"], [1], [sc["cam_params"]],
+                                 pose_flags=_gauge_flags(12)), None
+        ok, s = ba.solve_arrays(ctx, a, ba.default_solver_options(max_num_iterations=12,
+                                                                  loss_type=1, loss_scale=1.0))
+        assert ok
+        outs.append((a.qvecs.copy(), a.tvecs.copy(), a.points.copy(), s.final_cost,
+                     s.num_successful_steps, s.num_unsuccessful_steps))
+    for o in outs[1:]:
+        assert o[3] == outs[0][3] and o[4:] == outs[0][4:]
+        assert np.array_equal(o[0], outs[0][0]) and np.array_equal(o[1], outs[0][1])
+        assert np.array_equal(o[2], outs[0][2])
