@@ -188,15 +188,73 @@ def workload_config(world):
                            "no data-path collective"}
 
 
-def cpu_reference_run(sc, num_trials):
-    """Oracle restatement of the reference's serial CPU loop (1 thread, as the reference)."""
+def cpu_arm():
+    """The CPU implementation the baselines time: ("reference", module) when oracle/_ref/
+    libref_p6l.so exists — the reference's OWN RANSAC loop / P6L / re3q3 / scoring sources,
+    compiled in the build container by oracle/build_ref.sh against Eigen / glog stand-ins and
+    shipped as a git-ignored file — else ("port", module): the oracle's restatement."""
     import oracle as O
-    O.set_prng_seed(0)
+    try:
+        import oracle.reference as R
+        if os.path.exists(R.LIB_PATH):
+            R.lib()
+            return "reference", R
+    except (OSError, RuntimeError):
+        pass
+    return "port", O
+
+
+CPU_ARM_TEXT = {
+    "reference": "the reference's own sources (src/optim/ransac.h, src/estimators/absolute_pose.cc, "
+                 "lib/re3q3, src/estimators/utils.cc) compiled by oracle/build_ref.sh against "
+                 "stand-ins for Eigen / glog (absent in this image); serial loop, 1 thread, as the "
+                 "reference runs it",
+    "port": "oracle restatement of the reference's serial RANSAC loop, 1 thread like the "
+            "reference (oracle/_ref/libref_p6l.so not present)",
+}
+
+
+def cpu_reference_run(sc, num_trials, seed=0):
+    """`num_trials` trials of the reference's serial CPU loop (1 thread, as the reference) on
+    the whole correspondence set.  min_inlier_ratio 0.01 keeps the constructor's cap
+    (src/optim/ransac.h:144-156) far above num_trials; min = max = num_trials disables the
+    dynamic abort, as in config 2."""
+    import oracle as O
+    kind, impl = cpu_arm()
+    impl.set_prng_seed(seed)
+    opt = O.make_options(MAX_ERROR, 0.01, 0.99999, 3.0, num_trials, num_trials)
     t0 = time.perf_counter()
-    scored, rep = O.ransac_p6l_fixed_trials(sc["lines"], sc["aligned"], sc["points"], MAX_ERROR,
-                                            num_trials)
+    rep, _ = impl.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], opt)
     dt = time.perf_counter() - t0
-    return num_trials / dt, dt, scored
+    assert rep.num_trials == num_trials
+    return num_trials / dt, dt, kind
+
+
+def cpu_all_cores_run(sc, trials_per_thread):
+    """For information: the same serial loop on every host core at once, each thread on its own
+    slice of trials (its own thread-local generator) — the ceiling of an embarrassingly parallel
+    CPU version the reference does not have.  Needs the reference build (its PRNG is
+    thread_local; the oracle's is one global)."""
+    import threading
+    kind, impl = cpu_arm()
+    if kind != "reference":
+        return None
+    cores = os.cpu_count() or 1
+    done = []
+
+    def work(tid):
+        done.append(cpu_reference_run(sc, trials_per_thread, seed=tid + 1)[1])
+
+    th = [threading.Thread(target=work, args=(i,)) for i in range(cores)]
+    t0 = time.perf_counter()
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    dt = time.perf_counter() - t0
+    return {"value": cores * trials_per_thread / dt, "unit": "hypotheses/s", "cores": cores,
+            "sample": f"{trials_per_thread} trials per thread on all {N_CORR} correspondences, "
+                      f"{dt:.1f} s; NOT a reference code path (its loop is serial)"}
 
 
 def run_reference(args):
@@ -210,8 +268,9 @@ def run_reference(args):
     for _ in range(args.warmup):
         cpu_reference_run(sc, 100)
     total_t, total_h = 0.0, 0
+    kind = "port"
     for _ in range(args.steps):
-        hps, dt, _ = cpu_reference_run(sc, sample_trials)
+        hps, dt, kind = cpu_reference_run(sc, sample_trials)
         total_t += dt
         total_h += sample_trials
     value = total_h / total_t
@@ -221,16 +280,17 @@ def run_reference(args):
         "ms_per_step": 1e3 * total_t / max(1, args.steps), "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(args.gpus),
-        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": 1, "kind": "port",
+        "cpu_baseline": {"value": value, "unit": "hypotheses/s", "cores": 1, "kind": kind,
                          "sample": f"{sample_trials} of the {N_HYP * CALLS_PER_STEP} hypotheses "
                                    f"of a step (first call, all {N_CORR} correspondences) per "
-                                   "timed step; oracle restatement of the reference's serial "
-                                   "RANSAC loop, 1 thread like the reference (Eigen / Ceres are "
-                                   "absent: the reference itself cannot be compiled here)"},
+                                   "timed step; " + CPU_ARM_TEXT[kind]},
         "e2e": {"value": value, "unit": "hypotheses/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
         "host_cores": os.cpu_count(),
     }
+    allc = cpu_all_cores_run(sc, 200)
+    if allc is not None:
+        out["cpu_baseline"]["all_cores_for_information"] = allc
     print(json.dumps(out), flush=True)
 
 
@@ -426,13 +486,14 @@ def run_b200(args):
     if ba_weak is not None:
         out["ba_weak_scaling"] = ba_weak
     if not args.no_cpu_baseline and world == 1:
-        hps, dt, scored = cpu_reference_run(scenes[0], 2000)
+        hps, dt, kind = cpu_reference_run(scenes[0], 2000)
         out["cpu_baseline"] = {
-            "value": hps, "unit": "hypotheses/s", "cores": 1, "kind": "port",
-            "sample": f"2000 of the {N_HYP} hypotheses of one call ({scored} models) on all "
-                      f"{N_CORR} correspondences, {dt:.1f} s; oracle restatement of the "
-                      "reference's serial RANSAC loop (the reference needs Eigen/Ceres, absent "
-                      "here)"}
+            "value": hps, "unit": "hypotheses/s", "cores": 1, "kind": kind,
+            "sample": f"2000 of the {N_HYP} hypotheses of one call on all {N_CORR} "
+                      f"correspondences, {dt:.1f} s; " + CPU_ARM_TEXT[kind]}
+        allc = cpu_all_cores_run(scenes[0], 200)
+        if allc is not None:
+            out["cpu_baseline"]["all_cores_for_information"] = allc
     print(json.dumps(out), flush=True)
 
 

@@ -1,0 +1,185 @@
+// ref_p6l.cc — TEST INFRASTRUCTURE.  C entry points around the REFERENCE's own sources of the
+// absolute-pose RANSAC path, compiled from where they lie under /root/reference (never copied):
+//   src/estimators/absolute_pose.cc   P6LEstimator::Estimate / Residuals        
+//   lib/re3q3/re3q3/re3q3.h           re3q3                                     (A4)
+//   src/estimators/utils.cc           ComputeSquaredLineReprojectionError       (A5)
+//   src/optim/ransac.h                RANSAC<Estimator, SupportMeasurer, Sampler>::Estimate (A6)
+//   src/optim/random_sampler.cc, src/util/random.{h,cc}   sampler + PRNG        (A7)
+//   src/optim/support_measurement.cc  Inlier / MEstimator support               (A8)
+// Eigen and glog are absent in this image: the sources compile against the stand-ins under
+// oracle/ref/shim/ (minieigen.h: the Eigen calls are the restatements of oracle/eigen_restated.h,
+// shared with the oracle; glog/logging.h: CHECK* = print + abort).  So what tests/test_ref_p6l.py
+// pins is the reference's SOURCE TEXT against the oracle's restatement of it, bit for bit; the
+// inside of Eigen (determinant, PartialPivLU, EigenSolver, product association) stays unpinned.
+// Built by oracle/build_ref.sh into oracle/_ref/libref_p6l.so.  Signatures mirror the orc_*
+// functions of oracle/ppsfm_oracle.h.
+#include <cstdint>
+#include <cstring>
+#include <random>
+#include <vector>
+
+#include "estimators/absolute_pose.h"
+#include "estimators/utils.h"
+#include "feature/types.h"
+#include "optim/random_sampler.h"
+#include "optim/ransac.h"
+#include "optim/support_measurement.h"
+#include "util/random.h"
+
+// defined (non-inline) by lib/re3q3/re3q3/re3q3.h inside the absolute_pose.cc translation unit
+int re3q3(Eigen::Matrix<double, 3, 10> coeffs, Eigen::Matrix<double, 3, 8>* solutions,
+          bool try_random_var_change);
+
+namespace {
+
+struct Options {  // == orc_ransac_options
+  double max_error, min_inlier_ratio, confidence, dyn_num_trials_multiplier;
+  uint64_t min_num_trials, max_num_trials;
+};
+struct Report {  // == orc_ransac_report
+  int32_t success;
+  uint64_t num_trials, num_inliers;
+  double residual_sum;
+  double model[12];
+  int64_t best_trial;
+  int32_t best_model_idx;
+  uint64_t num_models_scored;
+};
+
+void Gather(const double* lines, const uint8_t* aligned, const double* points, size_t n,
+            colmap::FeatureLines* X, std::vector<Eigen::Vector3d>* Y) {
+  X->clear();
+  Y->clear();
+  for (size_t i = 0; i < n; ++i) {
+    X->emplace_back(Eigen::Vector3d(lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]),
+                    aligned != nullptr && aligned[i] != 0);
+    Y->emplace_back(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+void ref_set_prng_seed(uint32_t seed) { colmap::SetPRNGSeed(seed); }
+
+// the next 32-bit output of the generator, without consuming it (== orc_prng_peek)
+uint32_t ref_prng_peek(void) {
+  if (colmap::PRNG == nullptr) colmap::SetPRNGSeed();
+  std::mt19937 copy = *colmap::PRNG;
+  return static_cast<uint32_t>(copy());
+}
+
+void ref_line_residuals(const double* lines, const double* points, size_t n, const double* model,
+                        double* residuals_out) {
+  std::vector<Eigen::Vector3d> l, p;
+  for (size_t i = 0; i < n; ++i) {
+    l.emplace_back(lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]);
+    p.emplace_back(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+  }
+  Eigen::Matrix3x4d m;
+  std::memcpy(m.data(), model, sizeof(double) * 12);  // column-major 3x4, like Eigen's storage
+  std::vector<double> r;
+  colmap::ComputeSquaredLineReprojectionError(l, p, m, &r);
+  std::memcpy(residuals_out, r.data(), sizeof(double) * n);
+}
+
+void ref_inlier_support(const double* residuals, size_t n, double max_residual,
+                        uint64_t* num_inliers, double* residual_sum) {
+  colmap::InlierSupportMeasurer m;
+  const auto s = m.Evaluate(std::vector<double>(residuals, residuals + n), max_residual);
+  *num_inliers = s.num_inliers;
+  *residual_sum = s.residual_sum;
+}
+
+// 1 if support (n1, s1) is better than (n2, s2): InlierSupportMeasurer::Compare
+int ref_inlier_support_compare(uint64_t n1, double s1, uint64_t n2, double s2) {
+  colmap::InlierSupportMeasurer m;
+  colmap::InlierSupportMeasurer::Support a, b;
+  a.num_inliers = n1;
+  a.residual_sum = s1;
+  b.num_inliers = n2;
+  b.residual_sum = s2;
+  return m.Compare(a, b) ? 1 : 0;
+}
+
+void ref_mestimator_support(const double* residuals, size_t n, double max_residual,
+                            uint64_t* num_inliers, double* score) {
+  colmap::MEstimatorSupportMeasurer m;
+  const auto s = m.Evaluate(std::vector<double>(residuals, residuals + n), max_residual);
+  *num_inliers = s.num_inliers;
+  *score = s.score;
+}
+
+uint64_t ref_compute_num_trials(uint64_t num_inliers, uint64_t num_samples, double confidence,
+                                double num_trials_multiplier) {
+  return colmap::RANSAC<colmap::P6LEstimator>::ComputeNumTrials(num_inliers, num_samples,
+                                                                 confidence, num_trials_multiplier);
+}
+
+void ref_sample_table(size_t n, size_t num_trials, uint32_t* table_out) {
+  colmap::RandomSampler sampler(colmap::P6LEstimator::kMinNumSamples);
+  sampler.Initialize(n);
+  for (size_t t = 0; t < num_trials; ++t) {
+    const std::vector<size_t> idx = sampler.Sample();
+    for (int i = 0; i < 6; ++i) table_out[6 * t + i] = static_cast<uint32_t>(idx[i]);
+  }
+}
+
+// coeffs: 3 x 10 row-major; solutions: 8 x 3 (solution-major) like orc_re3q3
+int ref_re3q3(const double* coeffs, double* solutions) {
+  Eigen::Matrix<double, 3, 10> c;
+  for (int k = 0; k < 3; ++k)
+    for (int j = 0; j < 10; ++j) c(k, j) = coeffs[10 * k + j];
+  Eigen::Matrix<double, 3, 8> s;
+  for (int k = 0; k < 8; ++k)
+    for (int i = 0; i < 3; ++i) s(i, k) = 0.0;
+  const int n = re3q3(c, &s, true);
+  for (int k = 0; k < 8; ++k)
+    for (int i = 0; i < 3; ++i) solutions[3 * k + i] = s(i, k);
+  return n;
+}
+
+// lines6 / points6: 6 x 3 row-major; models_out: up to 8 column-major 3x4 matrices
+int ref_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double* points6,
+                     double* models_out) {
+  colmap::FeatureLines X;
+  std::vector<Eigen::Vector3d> Y;
+  Gather(lines6, aligned6, points6, 6, &X, &Y);
+  const std::vector<colmap::P6LEstimator::M_t> models = colmap::P6LEstimator::Estimate(X, Y);
+  for (size_t k = 0; k < models.size(); ++k)
+    std::memcpy(models_out + 12 * k, models[k].data(), sizeof(double) * 12);
+  return static_cast<int>(models.size());
+}
+
+// colmap::RANSAC<P6LEstimator>(options).Estimate(X, Y) — the serial loop the GPU path replaces.
+// best_trial / best_model_idx / num_models_scored are not observable from outside the loop: -1 / 0.
+void ref_ransac_p6l(const double* lines, const uint8_t* aligned, const double* points, size_t n,
+                    const Options* options, Report* report, uint8_t* inlier_mask) {
+  colmap::RANSACOptions o;
+  o.max_error = options->max_error;
+  o.min_inlier_ratio = options->min_inlier_ratio;
+  o.confidence = options->confidence;
+  o.dyn_num_trials_multiplier = options->dyn_num_trials_multiplier;
+  o.min_num_trials = options->min_num_trials;
+  o.max_num_trials = options->max_num_trials;
+  colmap::FeatureLines X;
+  std::vector<Eigen::Vector3d> Y;
+  Gather(lines, aligned, points, n, &X, &Y);
+  colmap::RANSAC<colmap::P6LEstimator> ransac(o);
+  const auto r = ransac.Estimate(X, Y);
+  std::memset(report, 0, sizeof(*report));
+  report->success = r.success ? 1 : 0;
+  report->num_trials = r.num_trials;
+  report->num_inliers = r.support.num_inliers;
+  report->residual_sum = r.support.residual_sum;
+  std::memcpy(report->model, r.model.data(), sizeof(double) * 12);
+  report->best_trial = -1;
+  report->best_model_idx = -1;
+  if (inlier_mask != nullptr) {
+    std::memset(inlier_mask, 0, n);
+    for (size_t i = 0; i < r.inlier_mask.size(); ++i) inlier_mask[i] = r.inlier_mask[i] ? 1 : 0;
+  }
+}
+
+}  // extern "C"

@@ -1,0 +1,518 @@
+// minieigen.h — TEST INFRASTRUCTURE ONLY.  A stand-in for the handful of Eigen 3 calls the
+// reference's P6L / re3q3 / RANSAC / cost-functor sources make, so that those sources compile
+// HERE from where they lie under /root/reference (oracle/build_ref.sh -> oracle/_ref/), with no
+// Eigen in the image.  It is NOT Eigen: fixed-size, eager (every expression is evaluated to a
+// value at once), no vectorisation, and only the members those files use.
+//
+// Arithmetic contract (what makes the comparison with the restatement meaningful):
+//   * element-wise operators do one IEEE operation per element, products sum left to right
+//     (k = 0, 1, 2, ...) — what Eigen's unrolled, non-vectorised small fixed-size kernels do;
+//   * determinant(), lu()/partialPivLu().solve(), EigenSolver: the restatements of
+//     oracle/eigen_restated.h (the SAME functions the oracle calls) — the Eigen boundary stays
+//     unpinned, everything else in the compiled reference sources is the reference's own text;
+//   * setRandom() / Quaternion::UnitRandom() return FIXED generic values (the ones the oracle
+//     uses) instead of C rand(): the two degenerate fallbacks stay reproducible.
+#pragma once
+#include <cmath>
+#include <complex>
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <memory>
+#include <type_traits>
+#include <vector>
+
+#include "../../eigen_restated.h"
+
+#define EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+namespace Eigen {
+
+constexpr int Dynamic = -1;
+enum StorageOptions { ColMajor = 0, RowMajor = 1 };
+enum TransformTraits { Affine = 2 };
+
+template <class T>
+struct aligned_allocator {
+  using value_type = T;
+  aligned_allocator() = default;
+  template <class U>
+  aligned_allocator(const aligned_allocator<U>&) {}
+  T* allocate(std::size_t n) { return static_cast<T*>(::operator new(n * sizeof(T))); }
+  void deallocate(T* p, std::size_t) { ::operator delete(p); }
+  template <class U>
+  struct rebind {
+    using other = aligned_allocator<U>;
+  };
+  bool operator==(const aligned_allocator&) const { return true; }
+  bool operator!=(const aligned_allocator&) const { return false; }
+};
+
+template <class S, int R, int C, int Opt = ColMajor>
+class Matrix;
+template <class Xpr, int BR, int BC>
+class Block;
+template <class M>
+class Map;
+
+template <class D>
+struct traits;
+template <class S, int R, int C, int Opt>
+struct traits<Matrix<S, R, C, Opt>> {
+  using Scalar = S;
+  static constexpr int Rows = R, Cols = C;
+};
+template <class Xpr, int BR, int BC>
+struct traits<Block<Xpr, BR, BC>> {
+  using Scalar = typename traits<std::remove_const_t<Xpr>>::Scalar;
+  static constexpr int Rows = BR, Cols = BC;
+};
+template <class M>
+struct traits<Map<M>> {
+  using Scalar = typename traits<std::remove_const_t<M>>::Scalar;
+  static constexpr int Rows = traits<std::remove_const_t<M>>::Rows;
+  static constexpr int Cols = traits<std::remove_const_t<M>>::Cols;
+};
+
+template <class Target>
+class CommaInitializer;
+template <class S>
+class PartialPivLU3;
+
+// ---------------------------------------------------------------------------------------------
+// Everything dense derives from this: Derived supplies coeff(i, j) (and coeffRef for writes).
+// ---------------------------------------------------------------------------------------------
+template <class D>
+class MatrixBase {
+ public:
+  using Scalar = typename traits<D>::Scalar;
+  static constexpr int Rows = traits<D>::Rows, Cols = traits<D>::Cols;
+  using Plain = Matrix<Scalar, Rows, Cols>;
+
+  const D& derived() const { return *static_cast<const D*>(this); }
+  D& derived() { return *static_cast<D*>(this); }
+
+  Scalar operator()(int i, int j) const { return derived().coeff(i, j); }
+  Scalar& operator()(int i, int j) { return derived().coeffRef(i, j); }
+  // vectors (either orientation)
+  Scalar operator()(int i) const { return Cols == 1 ? derived().coeff(i, 0) : derived().coeff(0, i); }
+  Scalar& operator()(int i) { return Cols == 1 ? derived().coeffRef(i, 0) : derived().coeffRef(0, i); }
+  Scalar operator[](int i) const { return (*this)(i); }
+  Scalar& operator[](int i) { return (*this)(i); }
+  Scalar x() const { return (*this)(0); }
+  Scalar y() const { return (*this)(1); }
+  Scalar z() const { return (*this)(2); }
+
+  Plain eval() const {
+    Plain r;
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) r.coeffRef(i, j) = derived().coeff(i, j);
+    return r;
+  }
+  Matrix<Scalar, Cols, Rows> transpose() const {
+    Matrix<Scalar, Cols, Rows> r;
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) r.coeffRef(j, i) = derived().coeff(i, j);
+    return r;
+  }
+
+  template <class O>
+  D& assign(const MatrixBase<O>& o) {
+    static_assert(O::Rows == Rows && O::Cols == Cols, "minieigen: size mismatch");
+    const typename O::Plain v = o.eval();  // (aliasing-safe)
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = v.coeff(i, j);
+    return derived();
+  }
+  template <class O>
+  D& operator+=(const MatrixBase<O>& o) {
+    const typename O::Plain v = o.eval();
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = derived().coeff(i, j) + v.coeff(i, j);
+    return derived();
+  }
+  template <class O>
+  D& operator-=(const MatrixBase<O>& o) {
+    const typename O::Plain v = o.eval();
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = derived().coeff(i, j) - v.coeff(i, j);
+    return derived();
+  }
+  D& operator/=(Scalar s) {
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = derived().coeff(i, j) / s;
+    return derived();
+  }
+  D& operator*=(Scalar s) {
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = derived().coeff(i, j) * s;
+    return derived();
+  }
+  template <class O>
+  void swap(MatrixBase<O>&& o) { swap(o); }
+  template <class O>
+  void swap(MatrixBase<O>& o) {
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) {
+        const Scalar t = derived().coeff(i, j);
+        derived().coeffRef(i, j) = o.derived().coeff(i, j);
+        o.derived().coeffRef(i, j) = t;
+      }
+  }
+
+  // Eigen's "random" fills of the two degenerate fallbacks, fixed (see the header comment).
+  D& setRandom() {
+    static_assert(std::is_same<Scalar, double>::value && Rows == 3 && (Cols == 3 || Cols == 1),
+                  "minieigen: setRandom() only for the reference's 3x3 / 3x1 uses");
+    if (Cols == 3) {  // absolute_pose.cc:131 — the oracle's kMixA
+      static const double k[3][3] = {{0.680375, -0.211234, 0.566198},
+                                     {0.596880, 0.823295, -0.604897},
+                                     {-0.329554, 0.536459, -0.444451}};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) derived().coeffRef(i, j) = k[i][j];
+    } else {  // re3q3.h:42 — normalised by the caller
+      static const double k[3] = {0.3, -0.5, 0.8};
+      for (int i = 0; i < 3; ++i) derived().coeffRef(i, 0) = k[i];
+    }
+    return derived();
+  }
+  Scalar squaredNorm() const {
+    Scalar s = derived().coeff(0, 0) * derived().coeff(0, 0);
+    for (int j = 0; j < Cols; ++j)
+      for (int i = (j == 0 ? 1 : 0); i < Rows; ++i) s = s + derived().coeff(i, j) * derived().coeff(i, j);
+    return s;
+  }
+  Scalar norm() const { return std::sqrt(squaredNorm()); }
+  void normalize() { *this /= norm(); }
+  template <class O>
+  Scalar dot(const MatrixBase<O>& o) const {
+    static_assert(Cols == 1 && O::Cols == 1 && O::Rows == Rows, "minieigen: dot of column vectors");
+    Scalar s = derived().coeff(0, 0) * o.derived().coeff(0, 0);
+    for (int i = 1; i < Rows; ++i) s = s + derived().coeff(i, 0) * o.derived().coeff(i, 0);
+    return s;
+  }
+
+  // Matrix3d::determinant()
+  Scalar determinant() const {
+    static_assert(std::is_same<Scalar, double>::value && Rows == 3 && Cols == 3,
+                  "minieigen: determinant() is 3x3 only");
+    double m[3][3];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) m[i][j] = derived().coeff(i, j);
+    return eigen_restated::Det3(m);
+  }
+  PartialPivLU3<Scalar> partialPivLu() const { return PartialPivLU3<Scalar>(eval()); }
+  PartialPivLU3<Scalar> lu() const { return partialPivLu(); }  // Eigen 3: lu() == partialPivLu()
+
+  template <int BR, int BC>
+  Block<D, BR, BC> block(int i, int j) { return Block<D, BR, BC>(derived(), i, j); }
+  template <int BR, int BC>
+  Block<const D, BR, BC> block(int i, int j) const { return Block<const D, BR, BC>(derived(), i, j); }
+  Block<D, Rows, 1> col(int j) { return Block<D, Rows, 1>(derived(), 0, j); }
+  Block<const D, Rows, 1> col(int j) const { return Block<const D, Rows, 1>(derived(), 0, j); }
+  Block<D, 1, Cols> row(int i) { return Block<D, 1, Cols>(derived(), i, 0); }
+  Block<const D, 1, Cols> row(int i) const { return Block<const D, 1, Cols>(derived(), i, 0); }
+};
+
+// ---------------------------------------------------------------------------------------------
+template <class S, int R, int C, int Opt>
+class Matrix : public MatrixBase<Matrix<S, R, C, Opt>> {
+  static_assert(R > 0 && C > 0, "minieigen: fixed sizes only");
+  S d_[R * C];  // column-major like Eigen's default
+
+ public:
+  using Base = MatrixBase<Matrix>;
+  Matrix() {}
+  template <class O>
+  Matrix(const MatrixBase<O>& o) { Base::assign(o); }
+  Matrix(const S& x, const S& y) {
+    static_assert(R * C == 2, "minieigen: 2-vector constructor");
+    d_[0] = x; d_[1] = y;
+  }
+  Matrix(const S& x, const S& y, const S& z) {
+    static_assert(R * C == 3, "minieigen: 3-vector constructor");
+    d_[0] = x; d_[1] = y; d_[2] = z;
+  }
+  Matrix(const S& x, const S& y, const S& z, const S& w) {
+    static_assert(R * C == 4, "minieigen: 4-vector constructor");
+    d_[0] = x; d_[1] = y; d_[2] = z; d_[3] = w;
+  }
+  template <class O>
+  Matrix& operator=(const MatrixBase<O>& o) { return Base::assign(o); }
+
+  static Matrix Zero() {
+    Matrix m;
+    for (int i = 0; i < R * C; ++i) m.d_[i] = S(0);
+    return m;
+  }
+  static Matrix Identity() {
+    Matrix m = Zero();
+    for (int i = 0; i < (R < C ? R : C); ++i) m.coeffRef(i, i) = S(1);
+    return m;
+  }
+
+  const S& coeff(int i, int j) const { return d_[j * R + i]; }
+  S& coeffRef(int i, int j) { return d_[j * R + i]; }
+  const S* data() const { return d_; }
+  S* data() { return d_; }
+
+  // comma initialisation: `M << a, b, c, ...;`
+  template <class T>
+  CommaInitializer<Matrix> operator<<(const T& first) {
+    CommaInitializer<Matrix> ci(*this);
+    ci, first;
+    return ci;
+  }
+};
+
+template <class Xpr, int BR, int BC>
+class Block : public MatrixBase<Block<Xpr, BR, BC>> {
+  Xpr& x_;
+  int i0_, j0_;
+
+ public:
+  using Base = MatrixBase<Block>;
+  using S = typename Base::Scalar;
+  Block(Xpr& x, int i0, int j0) : x_(x), i0_(i0), j0_(j0) {}
+  Block(const Block&) = default;
+  S coeff(int i, int j) const { return x_.coeff(i0_ + i, j0_ + j); }
+  S& coeffRef(int i, int j) { return x_.coeffRef(i0_ + i, j0_ + j); }
+  template <class O>
+  Block& operator=(const MatrixBase<O>& o) { return Base::assign(o); }
+  Block& operator=(const Block& o) { return Base::assign(o); }
+};
+
+template <class M>
+class Map : public MatrixBase<Map<M>> {
+  using Base = MatrixBase<Map>;
+  using S = typename Base::Scalar;
+  using Ptr = std::conditional_t<std::is_const<M>::value, const S*, S*>;
+  Ptr p_;
+
+ public:
+  explicit Map(Ptr p) : p_(p) {}
+  S coeff(int i, int j) const { return p_[j * Base::Rows + i]; }
+  S& coeffRef(int i, int j) { return const_cast<S*>(p_)[j * Base::Rows + i]; }
+  template <class O>
+  Map& operator=(const MatrixBase<O>& o) { return Base::assign(o); }
+};
+
+// `M << ...`: scalars and blocks, filled left to right, top to bottom (Eigen's CommaInitializer)
+template <class Target>
+class CommaInitializer {
+  Target& t_;
+  int row_ = 0, col_ = 0, h_ = 1;
+  void Advance(int h, int w) {
+    h_ = h;
+    col_ += w;
+    if (col_ >= Target::Cols) {
+      col_ = 0;
+      row_ += h_;
+    }
+  }
+
+ public:
+  explicit CommaInitializer(Target& t) : t_(t) {}
+  template <class T, std::enable_if_t<std::is_arithmetic<T>::value, int> = 0>
+  CommaInitializer& operator,(const T& s) {
+    t_.coeffRef(row_, col_) = static_cast<typename Target::Scalar>(s);
+    Advance(1, 1);
+    return *this;
+  }
+  template <class O>
+  CommaInitializer& operator,(const MatrixBase<O>& b) {
+    for (int j = 0; j < O::Cols; ++j)
+      for (int i = 0; i < O::Rows; ++i) t_.coeffRef(row_ + i, col_ + j) = b.derived().coeff(i, j);
+    Advance(O::Rows, O::Cols);
+    return *this;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// operators (eager)
+// ---------------------------------------------------------------------------------------------
+template <class A, class B>
+Matrix<typename A::Scalar, A::Rows, B::Cols> operator*(const MatrixBase<A>& a, const MatrixBase<B>& b) {
+  static_assert(A::Cols == B::Rows, "minieigen: inner dimensions");
+  Matrix<typename A::Scalar, A::Rows, B::Cols> r;
+  for (int j = 0; j < B::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) {
+      typename A::Scalar s = a.derived().coeff(i, 0) * b.derived().coeff(0, j);
+      for (int k = 1; k < A::Cols; ++k) s = s + a.derived().coeff(i, k) * b.derived().coeff(k, j);
+      r.coeffRef(i, j) = s;
+    }
+  return r;
+}
+template <class A>
+typename A::Plain operator*(const MatrixBase<A>& a, typename A::Scalar s) {
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = a.derived().coeff(i, j) * s;
+  return r;
+}
+template <class A>
+typename A::Plain operator*(typename A::Scalar s, const MatrixBase<A>& a) {
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = s * a.derived().coeff(i, j);
+  return r;
+}
+template <class A>
+typename A::Plain operator/(const MatrixBase<A>& a, typename A::Scalar s) {
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = a.derived().coeff(i, j) / s;
+  return r;
+}
+template <class A, class B>
+typename A::Plain operator+(const MatrixBase<A>& a, const MatrixBase<B>& b) {
+  static_assert(A::Rows == B::Rows && A::Cols == B::Cols, "minieigen: size mismatch");
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = a.derived().coeff(i, j) + b.derived().coeff(i, j);
+  return r;
+}
+template <class A, class B>
+typename A::Plain operator-(const MatrixBase<A>& a, const MatrixBase<B>& b) {
+  static_assert(A::Rows == B::Rows && A::Cols == B::Cols, "minieigen: size mismatch");
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = a.derived().coeff(i, j) - b.derived().coeff(i, j);
+  return r;
+}
+template <class A>
+typename A::Plain operator-(const MatrixBase<A>& a) {
+  typename A::Plain r;
+  for (int j = 0; j < A::Cols; ++j)
+    for (int i = 0; i < A::Rows; ++i) r.coeffRef(i, j) = -a.derived().coeff(i, j);
+  return r;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PartialPivLU<Matrix3d>::solve  (eigen_restated::SolvePartialPiv3)
+// ---------------------------------------------------------------------------------------------
+template <class S>
+class PartialPivLU3 {
+  Matrix<S, 3, 3> a_;
+
+ public:
+  explicit PartialPivLU3(const Matrix<S, 3, 3>& a) : a_(a) {}
+  template <class B>
+  typename B::Plain solve(const MatrixBase<B>& rhs) const {
+    static_assert(std::is_same<S, double>::value && B::Rows == 3, "minieigen: 3x3 double systems");
+    double A[3][3], X[3][B::Cols];
+    for (int i = 0; i < 3; ++i) {
+      for (int j = 0; j < 3; ++j) A[i][j] = a_.coeff(i, j);
+      for (int j = 0; j < B::Cols; ++j) X[i][j] = rhs.derived().coeff(i, j);
+    }
+    eigen_restated::SolvePartialPiv3<B::Cols>(A, X);
+    typename B::Plain r;
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < B::Cols; ++j) r.coeffRef(i, j) = X[i][j];
+    return r;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+// EigenSolver<Matrix<double,8,8>>: eigenvalues only, of an upper-Hessenberg input (the companion
+// matrix of re3q3.h:152-165) — eigen_restated::Hqr8.
+// ---------------------------------------------------------------------------------------------
+template <class M>
+class EigenSolver {
+  Matrix<std::complex<double>, 8, 1> ev_;
+
+ public:
+  EigenSolver(const M& m, bool compute_eigenvectors = true) {
+    static_assert(M::Rows == 8 && M::Cols == 8, "minieigen: EigenSolver is 8x8 only");
+    if (compute_eigenvectors) std::abort();  // not provided
+    eigen_restated::Hqr8 h;
+    for (int i = 0; i < 8; ++i)
+      for (int j = 0; j < 8; ++j) {
+        h.T[i][j] = m.coeff(i, j);
+        if (i > j + 1 && m.coeff(i, j) != 0.0) std::abort();  // Hessenberg inputs only
+      }
+    h.Reduce();
+    double re[8], im[8];
+    h.Eigenvalues(re, im);
+    for (int i = 0; i < 8; ++i) ev_.coeffRef(i, 0) = std::complex<double>(re[i], im[i]);
+  }
+  const Matrix<std::complex<double>, 8, 1>& eigenvalues() const { return ev_; }
+};
+
+// ---------------------------------------------------------------------------------------------
+// Geometry stubs: only what the reference's headers name.
+// ---------------------------------------------------------------------------------------------
+template <class S>
+class Quaternion {
+  S w_, x_, y_, z_;
+  bool fixed_generic_ = false;  // the UnitRandom() stand-in
+
+ public:
+  Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
+  Quaternion(S w, S x, S y, S z) : w_(w), x_(x), y_(y), z_(z) {}
+  S w() const { return w_; }
+  S x() const { return x_; }
+  S y() const { return y_; }
+  S z() const { return z_; }
+  // re3q3.h:41 draws a random rotation; fixed here: the rotation of the oracle's kVarChangeA
+  static Quaternion UnitRandom() {
+    Quaternion q;
+    q.fixed_generic_ = true;
+    return q;
+  }
+  Matrix<S, 3, 3> toRotationMatrix() const {
+    Matrix<S, 3, 3> r;
+    if (fixed_generic_) {
+      static const double k[3][3] = {
+          {-0.45264637943155561, -0.88862107060359552, 0.073917846740986226},
+          {0.19122225569950785, -0.015767801546650473, 0.98142010645776834},
+          {-0.8709450637742292, 0.45837099527970276, 0.1770613638646179}};
+      for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) r.coeffRef(i, j) = S(k[i][j]);
+      return r;
+    }
+    const S tx = S(2) * x_, ty = S(2) * y_, tz = S(2) * z_;
+    const S twx = tx * w_, twy = ty * w_, twz = tz * w_;
+    const S txx = tx * x_, txy = ty * x_, txz = tz * x_;
+    const S tyy = ty * y_, tyz = tz * y_, tzz = tz * z_;
+    r.coeffRef(0, 0) = S(1) - (tyy + tzz); r.coeffRef(0, 1) = txy - twz; r.coeffRef(0, 2) = txz + twy;
+    r.coeffRef(1, 0) = txy + twz; r.coeffRef(1, 1) = S(1) - (txx + tzz); r.coeffRef(1, 2) = tyz - twx;
+    r.coeffRef(2, 0) = txz - twy; r.coeffRef(2, 1) = tyz + twx; r.coeffRef(2, 2) = S(1) - (txx + tyy);
+    return r;
+  }
+};
+template <class S, int Dim, int Mode>
+class Transform {};
+
+// the one dynamic type the compiled headers name (base/polynomial.h, included but unused by
+// absolute_pose.cc): size() and element access only
+class VectorXd {
+  std::vector<double> v_;
+
+ public:
+  typedef std::ptrdiff_t Index;
+  VectorXd() {}
+  explicit VectorXd(Index n) : v_(static_cast<std::size_t>(n)) {}
+  Index size() const { return static_cast<Index>(v_.size()); }
+  double operator()(Index i) const { return v_[static_cast<std::size_t>(i)]; }
+  double& operator()(Index i) { return v_[static_cast<std::size_t>(i)]; }
+};
+
+typedef Matrix<double, 2, 1> Vector2d;
+typedef Matrix<double, 3, 1> Vector3d;
+typedef Matrix<double, 4, 1> Vector4d;
+typedef Matrix<float, 2, 1> Vector2f;
+typedef Matrix<float, 3, 1> Vector3f;
+typedef Matrix<float, 4, 1> Vector4f;
+typedef Matrix<double, 2, 2> Matrix2d;
+typedef Matrix<double, 3, 3> Matrix3d;
+typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<float, 2, 2> Matrix2f;
+typedef Matrix<float, 3, 3> Matrix3f;
+typedef Matrix<float, 4, 4> Matrix4f;
+typedef Quaternion<double> Quaterniond;
+typedef Quaternion<float> Quaternionf;
+typedef Transform<double, 3, Affine> Affine3d;
+typedef Transform<float, 3, Affine> Affine3f;
+
+}  // namespace Eigen

@@ -1,0 +1,152 @@
+"""ctypes binding of oracle/_ref/libref_p6l.so: the REFERENCE's own sources of the absolute-pose
+RANSAC path (P6LEstimator, re3q3, ComputeSquaredLineReprojectionError, RANSAC<>::Estimate,
+RandomSampler, support measurers) compiled from /root/reference by oracle/build_ref.sh against the
+Eigen / glog stand-ins of oracle/ref/shim/.
+
+TEST INFRASTRUCTURE ONLY (same rule as the oracle: tests/, smoke() and bench.py's CPU arms).  The
+library is built in the container that has /root/reference and travels to the GPU box as a
+git-ignored file; nothing here reads /root/reference at run time.  Same call surface as the
+matching functions of ``oracle/__init__.py`` so that a test can run both side by side.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from . import RansacOptions, RansacReport, make_options  # noqa: F401  (same C structs)
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_ref", "libref_p6l.so")
+_dp = C.POINTER(C.c_double)
+_u8p = C.POINTER(C.c_uint8)
+_u32p = C.POINTER(C.c_uint32)
+_lib = None
+
+
+def build(reference_root="/root/reference"):
+    """Compile oracle/_ref/ where the reference tree exists; returns True if the library is there."""
+    srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "shim", "minieigen.h"),
+            os.path.join(_HERE, "eigen_restated.h"), os.path.join(_HERE, "build_ref.sh")]
+    fresh = os.path.exists(LIB_PATH) and all(
+        os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)
+    if not fresh and os.path.isdir(os.path.join(reference_root, "src", "estimators")):
+        subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")],
+                              stdout=subprocess.DEVNULL)
+    return os.path.exists(LIB_PATH)
+
+
+def available():
+    return build()
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libref_p6l.so is not built (needs /root/reference)")
+        L = C.CDLL(LIB_PATH)
+        L.ref_set_prng_seed.argtypes = [C.c_uint32]
+        L.ref_prng_peek.restype = C.c_uint32
+        L.ref_line_residuals.argtypes = [_dp, _dp, C.c_size_t, _dp, _dp]
+        L.ref_inlier_support.argtypes = [_dp, C.c_size_t, C.c_double, C.POINTER(C.c_uint64), _dp]
+        L.ref_inlier_support_compare.argtypes = [C.c_uint64, C.c_double, C.c_uint64, C.c_double]
+        L.ref_inlier_support_compare.restype = C.c_int
+        L.ref_mestimator_support.argtypes = [_dp, C.c_size_t, C.c_double,
+                                             C.POINTER(C.c_uint64), _dp]
+        L.ref_compute_num_trials.argtypes = [C.c_uint64, C.c_uint64, C.c_double, C.c_double]
+        L.ref_compute_num_trials.restype = C.c_uint64
+        L.ref_sample_table.argtypes = [C.c_size_t, C.c_size_t, _u32p]
+        L.ref_re3q3.argtypes = [_dp, _dp]
+        L.ref_re3q3.restype = C.c_int
+        L.ref_p6l_estimate.argtypes = [_dp, _u8p, _dp, _dp]
+        L.ref_p6l_estimate.restype = C.c_int
+        L.ref_ransac_p6l.argtypes = [_dp, _u8p, _dp, C.c_size_t, C.POINTER(RansacOptions),
+                                     C.POINTER(RansacReport), _u8p]
+        _lib = L
+    return _lib
+
+
+def _d(a):
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    return a, a.ctypes.data_as(_dp)
+
+
+def _u8(a):
+    a = np.ascontiguousarray(a, dtype=np.uint8)
+    return a, a.ctypes.data_as(_u8p)
+
+
+def set_prng_seed(seed):
+    lib().ref_set_prng_seed(seed)
+
+
+def prng_peek():
+    return int(lib().ref_prng_peek())
+
+
+def line_residuals(lines, points, model):
+    lines, lp = _d(lines)
+    points, pp = _d(points)
+    model, mp = _d(model)
+    out = np.empty(lines.shape[0], dtype=np.float64)
+    lib().ref_line_residuals(lp, pp, lines.shape[0], mp, out.ctypes.data_as(_dp))
+    return out
+
+
+def inlier_support(residuals, max_residual):
+    residuals, rp = _d(residuals)
+    cnt, s = C.c_uint64(), C.c_double()
+    lib().ref_inlier_support(rp, residuals.shape[0], max_residual, C.byref(cnt), C.byref(s))
+    return int(cnt.value), float(s.value)
+
+
+def inlier_support_compare(n1, s1, n2, s2):
+    return bool(lib().ref_inlier_support_compare(n1, s1, n2, s2))
+
+
+def mestimator_support(residuals, max_residual):
+    residuals, rp = _d(residuals)
+    cnt, s = C.c_uint64(), C.c_double()
+    lib().ref_mestimator_support(rp, residuals.shape[0], max_residual, C.byref(cnt), C.byref(s))
+    return int(cnt.value), float(s.value)
+
+
+def compute_num_trials(num_inliers, num_samples, confidence, multiplier):
+    return int(lib().ref_compute_num_trials(num_inliers, num_samples, confidence, multiplier))
+
+
+def sample_table(n, num_trials):
+    out = np.empty((num_trials, 6), dtype=np.uint32)
+    lib().ref_sample_table(n, num_trials, out.ctypes.data_as(_u32p))
+    return out
+
+
+def re3q3(coeffs):
+    coeffs, cp = _d(coeffs)
+    assert coeffs.shape == (3, 10)
+    sol = np.zeros(24, dtype=np.float64)
+    n = lib().ref_re3q3(cp, sol.ctypes.data_as(_dp))
+    return sol.reshape(8, 3)[:n].copy()
+
+
+def p6l_estimate(lines6, aligned6, points6):
+    lines6, lp = _d(lines6)
+    points6, pp = _d(points6)
+    aligned6, ap = _u8(aligned6)
+    out = np.zeros((8, 12), dtype=np.float64)
+    n = lib().ref_p6l_estimate(lp, ap, pp, out.ctypes.data_as(_dp))
+    return out[:n].copy()
+
+
+def ransac_p6l(lines, aligned, points, options):
+    """colmap::RANSAC<P6LEstimator>(options).Estimate.  best_trial / best_model_idx /
+    num_models_scored of the report are not observable from outside the loop (-1 / 0)."""
+    lines, lp = _d(lines)
+    points, pp = _d(points)
+    aligned, ap = _u8(aligned)
+    n = lines.shape[0]
+    rep = RansacReport()
+    mask = np.zeros(n, dtype=np.uint8)
+    lib().ref_ransac_p6l(lp, ap, pp, n, C.byref(options), C.byref(rep), mask.ctypes.data_as(_u8p))
+    return rep, mask

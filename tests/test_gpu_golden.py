@@ -48,6 +48,30 @@ def test_gpu_ransac_reproduces_golden(ctx):
         assert got == case["expect"], name
 
 
+def test_gpu_config2_reproduces_the_reference_run(ctx):
+    """BASELINE config 2 exactly as bench.py times it, against tests/golden/config2_reference.json
+    — written by the REFERENCE's own RANSAC / P6L / re3q3 / scoring sources compiled in the build
+    container (tests/golden/make_config2_reference.py): trial count, support, the winning pose,
+    the 50 000-entry inlier mask and the generator state after the call, bit for bit."""
+    with open(os.path.join(HERE, "golden", "config2_reference.json")) as f:
+        gold = json.load(f)
+    sc = S.make_abs_pose_scene(**gold["scene"])
+    me, mir, conf, mult, tmin, tmax = gold["options"]
+    o = RANSACOptions(max_error=me, min_inlier_ratio=mir, confidence=conf,
+                      dyn_num_trials_multiplier=mult, min_num_trials=int(tmin),
+                      max_num_trials=int(tmax))
+    ctx.set_prng_seed(gold["prng_seed"])
+    rep, mask = ctx.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], o)
+    got = {
+        "success": int(rep.success), "num_trials": int(rep.num_trials),
+        "num_inliers": int(rep.num_inliers), "residual_sum": float(rep.residual_sum).hex(),
+        "model": _hexes(list(rep.model)),
+        "mask_sha256": hashlib.sha256(np.asarray(mask, np.uint8).tobytes()).hexdigest(),
+        "prng_peek_after": int(ctx.prng_peek()),
+    }
+    assert got == gold["expect"]
+
+
 def test_gpu_residuals_and_p6l_reproduce_golden(ctx):
     gold = _gold()
     sc = S.make_abs_pose_scene(n=500, inlier_ratio=0.5, seed=105)

@@ -1,0 +1,270 @@
+"""The oracle against the REFERENCE'S OWN SOURCES of the absolute-pose RANSAC path (CPU).
+
+oracle/build_ref.sh compiles, from where they lie under /root/reference,
+  src/estimators/absolute_pose.cc (P6LEstimator), lib/re3q3/re3q3/re3q3.h (re3q3),
+  src/estimators/utils.cc (ComputeSquaredLineReprojectionError), src/optim/ransac.h
+  (RANSAC<>::Estimate), src/optim/random_sampler.cc + src/util/random.{h,cc} (sampler, PRNG),
+  src/optim/support_measurement.cc (support measurers)
+into oracle/_ref/libref_p6l.so.  Eigen and glog are absent in this image, so those sources are
+compiled against the stand-ins of oracle/ref/shim/, whose Eigen calls (determinant, PartialPivLU,
+EigenSolver, left-to-right products) are the SAME functions the oracle uses (oracle/
+eigen_restated.h).  What these tests pin, bit for bit, is therefore the reference's source text —
+every statement of P6L, re3q3 (variable choice, column permutations, resultant, root filter,
+back-substitution, row swaps), scoring, support, sampling and the RANSAC loop with its abort rule
+— against the oracle's restatement; the inside of Eigen stays unpinned.
+The GPU path is pinned to the oracle by the `-m gpu` tests, and the committed golden vectors are
+reproduced by BOTH here.
+
+Skipped where neither oracle/_ref/libref_p6l.so nor /root/reference exists."""
+import importlib.util
+import json
+import os
+
+import numpy as np
+import pytest
+
+from privacy_preserving_sfm_b200 import synthetic as S
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def ref():
+    import oracle.reference as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref_p6l.so not built and /root/reference absent")
+    return R
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float64).view(np.uint64)
+
+
+def _same_bits(a, b):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    return a.shape == b.shape and np.array_equal(_bits(a), _bits(b))
+
+
+def test_p6l_estimate_bit_identical(oracle, ref):
+    # absolute_pose.cc:77-162 + re3q3.h on generic samples: random geometry and real minimal problems
+    rng = np.random.default_rng(7)
+    n_models = 0
+    for it in range(3000):
+        lines = rng.normal(size=(6, 3))
+        lines[:, :2] /= np.linalg.norm(lines[:, :2], axis=1, keepdims=True)
+        pts = rng.normal(size=(6, 3)) * 2
+        al = (rng.random(6) < 0.3).astype(np.uint8)
+        a, b = oracle.p6l_estimate(lines, al, pts), ref.p6l_estimate(lines, al, pts)
+        assert _same_bits(a, b), it
+        n_models += len(a)
+    assert n_models > 9000
+    for p in S.make_p6l_minimal_problems(500, seed=8):
+        al = np.zeros(6, np.uint8)
+        a, b = oracle.p6l_estimate(p["lines"], al, p["points"]), ref.p6l_estimate(p["lines"], al, p["points"])
+        assert len(a) >= 2 and _same_bits(a, b)
+
+
+def test_p6l_branches_bit_identical(oracle, ref):
+    p = S.make_p6l_minimal_problems(1, seed=3)[0]
+    # all lines gravity-aligned -> no model (absolute_pose.cc:87-97)
+    assert len(ref.p6l_estimate(p["lines"], np.ones(6, np.uint8), p["points"])) == 0
+    assert len(oracle.p6l_estimate(p["lines"], np.ones(6, np.uint8), p["points"])) == 0
+    # singular translation block (first three lines parallel): the `A.setRandom()` mix of
+    # absolute_pose.cc:126-134, with the same fixed A on both sides
+    rng = np.random.default_rng(9)
+    for q in S.make_p6l_minimal_problems(50, seed=10):
+        lines = q["lines"].copy()
+        pc = q["points"] @ q["R"].T + q["t"]
+        th = rng.uniform(0, 2 * np.pi)
+        for i in range(3):
+            uv = pc[i, :2] / pc[i, 2]
+            lines[i] = [np.cos(th), np.sin(th), -(np.cos(th) * uv[0] + np.sin(th) * uv[1])]
+        al = np.zeros(6, np.uint8)
+        a, b = oracle.p6l_estimate(lines, al, q["points"]), ref.p6l_estimate(lines, al, q["points"])
+        assert len(a) > 0 and _same_bits(a, b)
+
+
+def test_re3q3_bit_identical_on_generic_systems(oracle, ref):
+    # lib/re3q3/test_re3q3.cpp:33-44 style inputs; all three elimination variables occur
+    rng = np.random.default_rng(11)
+    n_sol = 0
+    for _ in range(2000):
+        co = rng.uniform(-1, 1, (3, 10))
+        a, b = oracle.re3q3(co), ref.re3q3(co)
+        assert _same_bits(a, b)
+        n_sol += len(a)
+    assert n_sol > 4000
+    # pure squares -> the 8 corners of the cube (test_re3q3.cpp:98-121)
+    co = np.zeros((3, 10))
+    co[0, 0] = co[1, 3] = co[2, 5] = 1.0
+    co[:, 9] = -1.0
+    a, b = oracle.re3q3(co), ref.re3q3(co)
+    assert len(b) == 8 and _same_bits(a, b)
+
+
+def test_re3q3_variable_change_branch_agrees(oracle, ref):
+    """det < 1e-10 for every elimination variable -> the affine change of variables of
+    re3q3.h:39-64.  The reference multiplies the coefficients by an explicit 10x10 matrix, the
+    oracle (and the CUDA solver) form G^T Q G per quadric: the same polynomial in another
+    association, so this one branch is compared by solution sets, not bits.  Both use the same
+    fixed A instead of C rand()."""
+    rng = np.random.default_rng(12)
+    hit = 0
+    for _ in range(100):
+        # columns x^2 = y^2 = a, z^2 = c, yz and xz in span(a, c): det[y^2 z^2 yz] = det[x^2 z^2 xz]
+        # = det[y^2 x^2 xy] = 0, but the three quadratic parts are independent forms, so a generic
+        # change of variables makes the blocks regular
+        a, c, d = rng.uniform(-1, 1, (3, 3))
+        co = rng.uniform(-1, 1, (3, 10))
+        co[:, 0], co[:, 3], co[:, 5], co[:, 1] = a, a, c, d
+        co[:, 4] = rng.uniform(-1, 1) * a + rng.uniform(-1, 1) * c
+        co[:, 2] = rng.uniform(-1, 1) * a + rng.uniform(-1, 1) * c
+        so, sr = oracle.re3q3(co), ref.re3q3(co)
+        assert len(so) == len(sr)
+        if len(sr) == 0:
+            continue
+        hit += 1
+        x, y, z = sr.T
+        mons = np.stack([x * x, x * y, x * z, y * y, y * z, z * z, x, y, z, np.ones_like(x)])
+        assert np.abs(co @ mons).max() < 1e-6          # the reference's solutions solve the system
+        for s_ in sr:
+            assert np.abs(so - s_).max(axis=1).min() <= 1e-6 * max(1.0, np.abs(s_).max())
+    assert hit >= 30        # (systems with no real solution agree on the count only)
+
+
+def test_line_residuals_bit_identical(oracle, ref):
+    # utils.cc:40-89 including the behind-the-camera branch (DBL_MAX)
+    sc = S.make_abs_pose_scene(n=4000, inlier_ratio=0.5, seed=13)
+    rng = np.random.default_rng(14)
+    behind = 0
+    for k in range(20):
+        R = S.random_rotation(rng) if k else sc["R"]
+        t = rng.uniform(-1, 1, 3) if k else sc["t"]
+        m = S.model_from_pose(R, t)
+        a, b = oracle.line_residuals(sc["lines"], sc["points"], m), ref.line_residuals(sc["lines"], sc["points"], m)
+        assert _same_bits(a, b)
+        behind += int((b == np.finfo(np.float64).max).sum())
+    assert behind > 1000
+
+
+def test_support_and_trial_count_identical(oracle, ref):
+    rng = np.random.default_rng(15)
+    r = rng.uniform(0, 3e-4, 5000)
+    r[rng.random(5000) < 0.1] = np.finfo(np.float64).max
+    thr = 0.012 ** 2
+    assert oracle.inlier_support(r, thr) == ref.inlier_support(r, thr)
+    assert oracle.mestimator_support(r, thr) == ref.mestimator_support(r, thr)
+    # Compare: more inliers wins, ties by the smaller residual sum (support_measurement.cc:52-60)
+    assert ref.inlier_support_compare(11, 5.0, 10, 1.0)
+    assert ref.inlier_support_compare(10, 1.0, 10, 2.0)
+    assert not ref.inlier_support_compare(10, 2.0, 10, 2.0)
+    assert not ref.inlier_support_compare(9, 0.0, 10, 2.0)
+    # SURVEY 8(c) known answer (5) (the survey's 141 453 is the floor; ceil() gives ...454), a sweep
+    assert ref.compute_num_trials(25000, 100000, 0.99999, 3.0) == 141454
+    for ninl in [0, 1, 5, 6, 100, 2500, 14999, 15000, 49999, 50000]:
+        for conf, mult in [(0.99999, 3.0), (0.99, 3.0), (0.5, 1.0), (1.0, 3.0)]:
+            if ninl == 0 and conf < 1.0:
+                continue      # log(1) = 0 in the denominator: +inf -> size_t is UB in the reference
+            assert oracle.compute_num_trials(ninl, 50000, conf, mult) == \
+                ref.compute_num_trials(ninl, 50000, conf, mult), (ninl, conf, mult)
+
+
+def test_sample_table_and_generator_state_identical(oracle, ref):
+    for seed, n, trials in [(0, 50000, 3000), (1, 7, 500), (12345, 6, 50), (7, 1000, 2000)]:
+        oracle.set_prng_seed(seed)
+        ref.set_prng_seed(seed)
+        assert np.array_equal(oracle.sample_table(n, trials), ref.sample_table(n, trials))
+        assert oracle.prng_peek() == ref.prng_peek()
+        # a second sampler on the SAME generator continues the stream (thread-local PRNG)
+        assert np.array_equal(oracle.sample_table(n, 10), ref.sample_table(n, 10))
+
+
+RANSAC_CASES = [
+    # scene, (max_error, min_inlier_ratio, confidence, multiplier, min_trials, max_trials)
+    (dict(n=2000, inlier_ratio=0.3, seed=201), (0.012, 0.25, 0.99999, 3.0, 100, 10000)),   # mapper
+    (dict(n=3000, inlier_ratio=0.35, seed=202), (0.012, 0.25, 0.99999, 3.0, 1500, 1500)),  # fixed
+    (dict(n=1500, inlier_ratio=0.7, seed=203), (0.012, 0.1, 0.99, 3.0, 0, 2 ** 64 - 1)),   # abort
+    (dict(n=800, inlier_ratio=0.05, seed=204), (0.004, 0.25, 0.99999, 3.0, 0, 300)),       # poor
+    (dict(n=500, inlier_ratio=0.95, noise_px=0.0, seed=205), (0.012, 0.25, 0.99999, 3.0, 100, 10000)),
+]
+
+
+def _report_tuple(rep, mask, peek):
+    return (int(rep.success), int(rep.num_trials), int(rep.num_inliers),
+            float(rep.residual_sum).hex(), [float(x).hex() for x in rep.model] if rep.success else None,
+            mask.tobytes(), peek)
+
+
+@pytest.mark.parametrize("case", range(len(RANSAC_CASES)))
+def test_ransac_loop_bit_identical(oracle, ref, case):
+    """colmap::RANSAC<P6LEstimator>::Estimate (ransac.h:144-278) against the oracle's loop:
+    trial count (dynamic abort rule included), support, winning model, inlier mask and the
+    generator state after the call."""
+    scene_kw, opt = RANSAC_CASES[case]
+    sc = S.make_abs_pose_scene(**scene_kw)
+    for seed in (0, 1):
+        oracle.set_prng_seed(seed)
+        ref.set_prng_seed(seed)
+        ro, mo = oracle.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], oracle.make_options(*opt))
+        rr, mr = ref.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], oracle.make_options(*opt))
+        assert _report_tuple(ro, mo, oracle.prng_peek()) == _report_tuple(rr, mr, ref.prng_peek())
+        if case in (0, 1, 2, 4):
+            assert rr.success and rr.num_inliers > 0.2 * scene_kw["n"]
+
+
+def test_ransac_edge_cases_identical(oracle, ref):
+    sc = S.make_abs_pose_scene(n=40, inlier_ratio=0.9, seed=206)
+    opt = oracle.make_options(0.012, 0.25, 0.99999, 3.0, 10, 100)
+    # fewer than kMinNumSamples correspondences: no trial, no success (ransac.h:188-190)
+    for n in (0, 5):
+        rr, mr = ref.ransac_p6l(sc["lines"][:n], sc["aligned"][:n], sc["points"][:n], opt)
+        ro, mo = oracle.ransac_p6l(sc["lines"][:n], sc["aligned"][:n], sc["points"][:n], opt)
+        assert (rr.success, rr.num_trials) == (ro.success, ro.num_trials) == (0, 0)
+    # every line gravity-aligned: every sample yields no model, the loop runs to max_num_trials
+    al = np.ones(40, np.uint8)
+    oracle.set_prng_seed(3)
+    ref.set_prng_seed(3)
+    ro, mo = oracle.ransac_p6l(sc["lines"], al, sc["points"], opt)
+    rr, mr = ref.ransac_p6l(sc["lines"], al, sc["points"], opt)
+    assert (rr.success, rr.num_trials, rr.num_inliers) == (ro.success, ro.num_trials, ro.num_inliers) == (0, 100, 0)
+    assert oracle.prng_peek() == ref.prng_peek()
+    # exactly six correspondences
+    oracle.set_prng_seed(4)
+    ref.set_prng_seed(4)
+    ro, mo = oracle.ransac_p6l(sc["lines"][:6], sc["aligned"][:6] * 0, sc["points"][:6], opt)
+    rr, mr = ref.ransac_p6l(sc["lines"][:6], sc["aligned"][:6] * 0, sc["points"][:6], opt)
+    assert _report_tuple(ro, mo, oracle.prng_peek()) == _report_tuple(rr, mr, ref.prng_peek())
+
+
+def test_reference_reproduces_the_golden_vectors(ref):
+    """tests/golden/oracle_vectors.json was written by the oracle; the reference's own loop gives
+    the same trial counts, supports, models, masks and generator states on those scenes, so the
+    file the CUDA path is pinned to (tests/test_gpu_golden.py) is also the reference's answer."""
+    import hashlib
+    with open(os.path.join(HERE, "golden", "oracle_vectors.json")) as f:
+        gold = json.load(f)
+    import oracle as O
+    for name, case in gold["ransac"].items():
+        sc = S.make_abs_pose_scene(**case["scene"])
+        ref.set_prng_seed(0)
+        rep, mask = ref.ransac_p6l(sc["lines"], sc["aligned"], sc["points"],
+                                   O.make_options(*case["options"]))
+        e = case["expect"]
+        assert int(rep.success) == e["success"] and int(rep.num_trials) == e["num_trials"], name
+        assert int(rep.num_inliers) == e["num_inliers"], name
+        assert float(rep.residual_sum).hex() == e["residual_sum"], name
+        assert [float(x).hex() for x in rep.model] == e["model"], name
+        assert hashlib.sha256(mask.tobytes()).hexdigest() == e["mask_sha256"], name
+        assert ref.prng_peek() == e["prng_peek_after"], name
+    # line residuals and P6L solutions of the golden file
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(HERE, "golden", "make_golden.py"))
+    gen = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(gen)
+    sc = S.make_abs_pose_scene(n=500, inlier_ratio=0.5, seed=105)
+    P = np.concatenate([sc["R"].T.reshape(9), sc["t"]])
+    r = ref.line_residuals(sc["lines"], sc["points"], P)
+    assert hashlib.sha256(r.tobytes()).hexdigest() == gold["line_residuals"]["residuals_sha256"]
+    probs = S.make_p6l_minimal_problems(8, seed=106)
+    got = [[gen.hexes(s) for s in ref.p6l_estimate(p["lines"], np.zeros(6, np.uint8), p["points"])]
+           for p in probs]
+    assert got == gold["p6l_estimate"]
