@@ -286,6 +286,7 @@ def _ba_lib():
                                    C.POINTER(BaSummary)]
         L.orc_ba_solve.restype = C.c_int
         L.orc_line_cost.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
+        L.orc_line_cost_intr.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.orc_line_cost_tangent.argtypes = [C.c_int, _dp, _dp, _dp, _dp, _dp, _dp, _dp, _dp]
         L.orc_ba_cost.argtypes = [C.POINTER(BaProblem), C.POINTER(BaOptions)]
         L.orc_ba_cost.restype = C.c_double
@@ -376,6 +377,23 @@ def line_cost(model, cam_params, line, q, t, X):
                             r.ctypes.data_as(_dp), jq.ctypes.data_as(_dp),
                             jt.ctypes.data_as(_dp), jx.ctypes.data_as(_dp))
     return r, jq, jt, jx
+
+
+def line_cost_intr(model, cam_params, line, q, t, X):
+    """The block (2; 4, 3, 3, k) of intrinsics refinement: r, Jq, Jt, JX, Jcamera[2 x 12]."""
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r, jq, jt, jx = np.zeros(2), np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 3))
+    jc = np.zeros((2, 12))
+    _ba_lib().orc_line_cost_intr(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                                 r.ctypes.data_as(_dp), jq.ctypes.data_as(_dp),
+                                 jt.ctypes.data_as(_dp), jx.ctypes.data_as(_dp),
+                                 jc.ctypes.data_as(_dp))
+    return r, jq, jt, jx, jc
 
 
 def line_cost_tangent(model, cam_params, line, q, t, X):

@@ -1050,6 +1050,12 @@ void orc_line_cost(int model, const double* cam, const double* line, const doubl
   LineCostAutoDiff(model, cam, line, q, t, X, r, jq, jt, jX);
 }
 
+void orc_line_cost_intr(int model, const double* cam, const double* line, const double* q,
+                        const double* t, const double* X, double* r, double* jq, double* jt,
+                        double* jX, double* jcam) {
+  LineCostAutoDiffIntr(model, cam, line, q, t, X, r, jq, jt, jX, jcam);
+}
+
 void orc_line_cost_tangent(int model, const double* cam, const double* line, const double* q,
                            const double* t, const double* X, double* r, double* jc, double* jX) {
   LineCostTangent(model, cam, line, q, t, X, r, jc, jX);

@@ -5,11 +5,13 @@
  * PARITY UNPINNED at the Ceres boundary: the reference hands the problem to ceres::Solve
  * (src/optim/bundle_adjustment.cc:306, src/estimators/pose.cc:201) and Ceres is neither in
  * /root/reference nor installed; no reference test constructs a BundleAdjuster or the line cost
- * functors.  This oracle restates
+ * functors.  PINNED against the reference's own sources: the two cost functors and the camera
+ * models — src/base/cost_functions.h and src/base/camera_models.{h,cc} compiled from
+ * /root/reference against stand-ins (oracle/build_ref.sh -> oracle/_ref/libref_cost.so) give
+ * bit-identical residuals and Jacobian blocks (tests/test_ref_cost.py).  This oracle restates
  *   - the residual functors of src/base/cost_functions.h:46-191 evaluated on forward-mode dual
  *     numbers (what ceres::AutoDiffCostFunction does),
- *   - the camera models of src/base/camera_models.h (SIMPLE_PINHOLE, PINHOLE, SIMPLE_RADIAL,
- *     RADIAL, OPENCV),
+ *   - the camera models of src/base/camera_models.h (all 11),
  *   - problem assembly / gauge rules of src/optim/bundle_adjustment.cc:326-542,
  *   - Ceres' documented trust-region Levenberg-Marquardt with Jacobi scaling, loss-function
  *     corrector and Schur elimination of the points,
@@ -103,6 +105,12 @@ int orc_ba_solve(const orc_ba_problem* problem, const orc_ba_options* options,
 void orc_line_cost(int camera_model, const double* camera_params, const double* line,
                    const double* qvec, const double* tvec, const double* point, double* residual,
                    double* jac_q, double* jac_t, double* jac_X);
+/* The block (2; 4, 3, 3, kNumParams) of intrinsics refinement: additionally jac_camera[2x12]
+ * (row-major, columns >= kNumParams zero). */
+void orc_line_cost_intr(int camera_model, const double* camera_params, const double* line,
+                        const double* qvec, const double* tvec, const double* point,
+                        double* residual, double* jac_q, double* jac_t, double* jac_X,
+                        double* jac_camera);
 /* Same block in the tangent space used by the solver: jac_cam[2x6] = [rotation(3) via
  * QuaternionParameterization | translation(3)], jac_X[2x3]. */
 void orc_line_cost_tangent(int camera_model, const double* camera_params, const double* line,

@@ -9,6 +9,9 @@
 #                    support_measurement.cc}, src/util/random.cc) behind C entry points
 #                    (oracle/ref/ref_p6l.cc), compiled against the Eigen / glog stand-ins of
 #                    oracle/ref/shim/ (both libraries are absent in this image)
+#   libref_cost.so : the reference's OWN line cost functors (src/base/cost_functions.h) and
+#                    camera models (src/base/camera_models.{h,cc}) behind C entry points
+#                    (oracle/ref/ref_cost.cc), against the Ceres / Eigen / glog / Boost stand-ins
 set -e
 here="$(cd "$(dirname "$0")" && pwd)"
 ref="${PPSFM_REFERENCE:-/root/reference}"
@@ -24,3 +27,8 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$ref/src/optim/random_sampler.cc" "$ref/src/optim/support_measurement.cc" \
     "$ref/src/util/random.cc" -o "$here/_ref/libref_p6l.so"
 echo "built $here/_ref/libref_p6l.so"
+
+g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
+    -I"$here/ref/shim" -I"$ref/src" \
+    "$here/ref/ref_cost.cc" "$ref/src/base/camera_models.cc" -o "$here/_ref/libref_cost.so"
+echo "built $here/_ref/libref_cost.so"

@@ -11,7 +11,9 @@
 // P6L + re3q3 call Eigen in the reference (absent here): elimination, LU and the companion-matrix
 // eigenvalue step are restated from the published algorithms (Francis double-shift QR on the
 // Hessenberg companion matrix, EISPACK `hqr` lineage, as used by Eigen::RealSchur) — pinned by the
-// reference's known-answer properties only; bit-level parity with an Eigen build is UNPINNED.
+// reference's known-answer properties only; bit-level parity with an Eigen build is UNPINNED
+// (eigen_restated.h).  Everything else is pinned bit for bit against the reference's own sources
+// compiled here against stand-ins (oracle/build_ref.sh, tests/test_ref_p6l.py).
 // The two `rand()`-driven degenerate fallbacks (absolute_pose.cc:128-134, re3q3.h:39-64) use a
 // FIXED generic matrix instead of C rand() so that results are reproducible.
 

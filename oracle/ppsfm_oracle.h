@@ -17,8 +17,18 @@
  *     (3x3 determinant, PartialPivLU::solve, the 3x3 * 3x9 products, EigenSolver<8x8>) is NOT in
  *     /root/reference and not installed: restated from Eigen 3.3's algorithms; pinned by the
  *     reference's known-answer properties (lib/re3q3/test_re3q3.cpp) and numpy.roots; bit-level
- *     parity with an Eigen build is UNPINNED for exactly those calls.
- *   - BA / pose refinement: Ceres is not in /root/reference; parity UNPINNED (see ba_oracle.h).
+ *     parity with an Eigen build is UNPINNED for exactly those calls (they live in
+ *     eigen_restated.h).
+ *   - Pinned against the reference's OWN SOURCES: oracle/build_ref.sh compiles
+ *     absolute_pose.cc, re3q3.h, utils.cc, ransac.h, random_sampler.cc, random.cc and
+ *     support_measurement.cc from /root/reference against Eigen / glog stand-ins
+ *     (oracle/ref/shim/, whose Eigen calls are eigen_restated.h) into oracle/_ref/libref_p6l.so;
+ *     tests/test_ref_p6l.py requires this library and the reference build to agree bit for bit
+ *     (P6L, re3q3, residuals, supports, sample tables, whole RANSAC calls incl. BASELINE
+ *     config 2 at full size).
+ *   - BA / pose refinement: Ceres is not in /root/reference; the SOLVER is parity-UNPINNED (see
+ *     ba_oracle.h); the cost functors and camera models are pinned the same way
+ *     (oracle/_ref/libref_cost.so, tests/test_ref_cost.py).
  *
  * Layout conventions (shared with include/ppsfm_b200.h):
  *   lines  : N x 3 doubles, row-major (a, b, c) per correspondence  (FeatureLine::Line())

@@ -54,3 +54,4 @@ T* NotNull(const char* file, int line, const char* what, T* p) {
 #define DCHECK_GE(a, b) CHECK_GE(a, b)
 #define LOG(severity) glog_shim::Null()
 #define VLOG(n) glog_shim::Null()
+#define CHECK_NEAR(a, b, eps) CHECK(((a) > (b) ? (a) - (b) : (b) - (a)) <= (eps))

@@ -201,6 +201,19 @@ class MatrixBase {
       for (int j = 0; j < 3; ++j) m[i][j] = derived().coeff(i, j);
     return eigen_restated::Det3(m);
   }
+  // Matrix2d::inverse() (adjugate times 1 / det, Eigen's size-2 kernel).  Only
+  // BaseCameraModel::IterativeUndistortion names it; nothing on the tested path evaluates it.
+  Plain inverse() const {
+    static_assert(Rows == 2 && Cols == 2, "minieigen: inverse() is 2x2 only");
+    const D& m = derived();
+    const Scalar invdet = Scalar(1) / (m.coeff(0, 0) * m.coeff(1, 1) - m.coeff(1, 0) * m.coeff(0, 1));
+    Plain r;
+    r.coeffRef(0, 0) = m.coeff(1, 1) * invdet;
+    r.coeffRef(1, 0) = -m.coeff(1, 0) * invdet;
+    r.coeffRef(0, 1) = -m.coeff(0, 1) * invdet;
+    r.coeffRef(1, 1) = m.coeff(0, 0) * invdet;
+    return r;
+  }
   PartialPivLU3<Scalar> partialPivLu() const { return PartialPivLU3<Scalar>(eval()); }
   PartialPivLU3<Scalar> lu() const { return partialPivLu(); }  // Eigen 3: lu() == partialPivLu()
 

@@ -18,6 +18,7 @@ from . import RansacOptions, RansacReport, make_options  # noqa: F401  (same C s
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref_p6l.so")
+COST_LIB_PATH = os.path.join(_HERE, "_ref", "libref_cost.so")
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -26,14 +27,17 @@ _lib = None
 
 def build(reference_root="/root/reference"):
     """Compile oracle/_ref/ where the reference tree exists; returns True if the library is there."""
-    srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "shim", "minieigen.h"),
+    srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "ref_cost.cc"),
+            os.path.join(_HERE, "ref", "shim", "minieigen.h"),
+            os.path.join(_HERE, "ref", "shim", "ceres", "ceres.h"),
+            os.path.join(_HERE, "ref", "shim", "glog", "logging.h"),
             os.path.join(_HERE, "eigen_restated.h"), os.path.join(_HERE, "build_ref.sh")]
-    fresh = os.path.exists(LIB_PATH) and all(
-        os.path.getmtime(LIB_PATH) >= os.path.getmtime(s) for s in srcs)
+    fresh = all(os.path.exists(lp) and all(os.path.getmtime(lp) >= os.path.getmtime(s)
+                                           for s in srcs) for lp in (LIB_PATH, COST_LIB_PATH))
     if not fresh and os.path.isdir(os.path.join(reference_root, "src", "estimators")):
         subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")],
                               stdout=subprocess.DEVNULL)
-    return os.path.exists(LIB_PATH)
+    return os.path.exists(LIB_PATH) and os.path.exists(COST_LIB_PATH)
 
 
 def available():
@@ -150,3 +154,99 @@ def ransac_p6l(lines, aligned, points, options):
     mask = np.zeros(n, dtype=np.uint8)
     lib().ref_ransac_p6l(lp, ap, pp, n, C.byref(options), C.byref(rep), mask.ctypes.data_as(_u8p))
     return rep, mask
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref/libref_cost.so: the reference's line cost functors and camera models
+# ---------------------------------------------------------------------------------------------
+_cost = None
+_ip = C.POINTER(C.c_int)
+
+
+def cost_lib():
+    global _cost
+    if _cost is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libref_cost.so is not built (needs /root/reference)")
+        L = C.CDLL(COST_LIB_PATH)
+        L.ref_camera_num_params.argtypes = [C.c_int]
+        L.ref_camera_param_idxs.argtypes = [C.c_int, C.c_int, _ip]
+        L.ref_world_to_image.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp]
+        L.ref_image_to_world_threshold.argtypes = [C.c_int, _dp, C.c_double]
+        L.ref_image_to_world_threshold.restype = C.c_double
+        L.ref_line_cost.argtypes = [C.c_int] + [_dp] * 10
+        L.ref_constant_pose_line_cost.argtypes = [C.c_int] + [_dp] * 8
+        _cost = L
+    return _cost
+
+
+def camera_num_params(model):
+    return int(cost_lib().ref_camera_num_params(model))
+
+
+def camera_param_idxs(model, group):
+    """group 0: focal length, 1: principal point, 2: extra parameters."""
+    out = (C.c_int * 12)()
+    n = cost_lib().ref_camera_param_idxs(model, group, out)
+    return [int(out[i]) for i in range(n)]
+
+
+def world_to_image(model, params, u, v):
+    params, pp = _d(params)
+    xy = np.zeros(2)
+    cost_lib().ref_world_to_image(model, pp, u, v, xy.ctypes.data_as(_dp))
+    return xy
+
+
+def image_to_world_threshold(model, params, threshold):
+    params, pp = _d(params)
+    return float(cost_lib().ref_image_to_world_threshold(model, pp, threshold))
+
+
+def line_cost_intr(model, cam_params, line, q, t, X):
+    """BundleAdjustmentLineCostFunction<Model>: r, Jq[2x4], Jt[2x3], JX[2x3], Jcamera[2x12]."""
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r, jq, jt, jx = np.zeros(2), np.zeros((2, 4)), np.zeros((2, 3)), np.zeros((2, 3))
+    jc = np.zeros((2, 12))
+    ok = cost_lib().ref_line_cost(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                                  r.ctypes.data_as(_dp), jq.ctypes.data_as(_dp),
+                                  jt.ctypes.data_as(_dp), jx.ctypes.data_as(_dp),
+                                  jc.ctypes.data_as(_dp))
+    assert ok == 1
+    return r, jq, jt, jx, jc
+
+
+def line_residual(model, cam_params, line, q, t, X):
+    """The functor on plain doubles (no Jacobians): r[2]."""
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r = np.zeros(2)
+    ok = cost_lib().ref_line_cost(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                                  r.ctypes.data_as(_dp), None, None, None, None)
+    assert ok == 1
+    return r
+
+
+def constant_pose_line_cost(model, cam_params, line, q, t, X):
+    """BundleAdjustmentConstantPoseLineCostFunction<Model>: r, JX[2x3], Jcamera[2x12]."""
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    line, lp = _d(line)
+    q, qp = _d(q)
+    t, tp = _d(t)
+    X, xp = _d(X)
+    r, jx, jc = np.zeros(2), np.zeros((2, 3)), np.zeros((2, 12))
+    ok = cost_lib().ref_constant_pose_line_cost(model, cam.ctypes.data_as(_dp), lp, qp, tp, xp,
+                                                r.ctypes.data_as(_dp), jx.ctypes.data_as(_dp),
+                                                jc.ctypes.data_as(_dp))
+    assert ok == 1
+    return r, jx, jc

@@ -4,10 +4,14 @@ of the CPU oracle on them, stored bit-exactly (doubles as hex strings).
 
   python tests/golden/make_golden.py
 
-The reference itself cannot be built in this environment (Eigen / Ceres / glog absent, see
-DESIGN.md section 4), so the vectors pin the ORACLE: tests/test_golden.py checks on the CPU that
-the oracle still reproduces them and, on the GPU, that the CUDA path does — a drift of either
-shows up against a fixed, committed answer instead of only against each other."""
+The vectors are written by the ORACLE: tests/test_golden.py checks on the CPU that the oracle
+still reproduces them and, on the GPU, that the CUDA path does — a drift of either shows up
+against a fixed, committed answer instead of only against each other.  The RANSAC, residual and
+P6L entries are ALSO what the reference's own sources give (compiled against Eigen / glog
+stand-ins by oracle/build_ref.sh; tests/test_ref_p6l.py::
+test_reference_reproduces_the_golden_vectors); config2_reference.json is written by that
+reference build directly (make_config2_reference.py).  The BA entries stay oracle-only (Ceres'
+solver cannot be built here)."""
 import hashlib
 import json
 import os
