@@ -9,6 +9,9 @@
 #                    support_measurement.cc}, src/util/random.cc) behind C entry points
 #                    (oracle/ref/ref_p6l.cc), compiled against the Eigen / glog stand-ins of
 #                    oracle/ref/shim/ (both libraries are absent in this image)
+#   libref_tri.so  : the reference's OWN LORANSAC / CombinationSampler / NChooseK sources
+#                    (src/optim/loransac.h, combination_sampler.cc, src/util/math.cc) driving the
+#                    oracle's per-track triangulation estimator (oracle/ref/ref_triangulation.cc)
 #   libref_cost.so : the reference's OWN line cost functors (src/base/cost_functions.h) and
 #                    camera models (src/base/camera_models.{h,cc}) behind C entry points
 #                    (oracle/ref/ref_cost.cc), against the Ceres / Eigen / glog / Boost stand-ins
@@ -32,3 +35,10 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -I"$here/ref/shim" -I"$ref/src" \
     "$here/ref/ref_cost.cc" "$ref/src/base/camera_models.cc" -o "$here/_ref/libref_cost.so"
 echo "built $here/_ref/libref_cost.so"
+
+g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
+    -I"$here/ref/shim" -I"$ref/src" \
+    "$here/ref/ref_triangulation.cc" "$ref/src/optim/combination_sampler.cc" \
+    "$ref/src/optim/support_measurement.cc" "$ref/src/util/math.cc" \
+    -o "$here/_ref/libref_tri.so"
+echo "built $here/_ref/libref_tri.so"

@@ -19,6 +19,7 @@ from . import RansacOptions, RansacReport, make_options  # noqa: F401  (same C s
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref_p6l.so")
 COST_LIB_PATH = os.path.join(_HERE, "_ref", "libref_cost.so")
+TRI_LIB_PATH = os.path.join(_HERE, "_ref", "libref_tri.so")
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -28,16 +29,18 @@ _lib = None
 def build(reference_root="/root/reference"):
     """Compile oracle/_ref/ where the reference tree exists; returns True if the library is there."""
     srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "ref_cost.cc"),
+            os.path.join(_HERE, "ref", "ref_triangulation.cc"),
+            os.path.join(_HERE, "triangulation_oracle.cc"),
             os.path.join(_HERE, "ref", "shim", "minieigen.h"),
             os.path.join(_HERE, "ref", "shim", "ceres", "ceres.h"),
             os.path.join(_HERE, "ref", "shim", "glog", "logging.h"),
             os.path.join(_HERE, "eigen_restated.h"), os.path.join(_HERE, "build_ref.sh")]
     fresh = all(os.path.exists(lp) and all(os.path.getmtime(lp) >= os.path.getmtime(s)
-                                           for s in srcs) for lp in (LIB_PATH, COST_LIB_PATH))
+                                           for s in srcs) for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH))
     if not fresh and os.path.isdir(os.path.join(reference_root, "src", "estimators")):
         subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")],
                               stdout=subprocess.DEVNULL)
-    return os.path.exists(LIB_PATH) and os.path.exists(COST_LIB_PATH)
+    return all(os.path.exists(lp) for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH))
 
 
 def available():
@@ -250,3 +253,30 @@ def constant_pose_line_cost(model, cam_params, line, q, t, X):
                                                 jc.ctypes.data_as(_dp))
     assert ok == 1
     return r, jx, jc
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref/libref_tri.so: the reference's LORANSAC / CombinationSampler around the oracle's
+# per-track triangulation estimator
+# ---------------------------------------------------------------------------------------------
+_tri = None
+
+
+def estimate_triangulation_batch(tracks, options):
+    """Same call as oracle.estimate_triangulation_batch (tracks: filters.FilterProblem, options:
+    triangulation.EstimateTriangulationOptions)."""
+    global _tri
+    if _tri is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libref_tri.so is not built (needs /root/reference)")
+        _tri = C.CDLL(TRI_LIB_PATH)
+        _tri.ref_estimate_triangulation_batch.argtypes = [C.c_void_p, C.c_void_p, _dp, _u8p, _u8p,
+                                                          _u32p]
+    T, O = len(tracks.points), len(tracks.obs_image)
+    xyz = np.zeros((max(T, 1), 3))
+    ok, mask = np.zeros(max(T, 1), np.uint8), np.zeros(max(O, 1), np.uint8)
+    nt = np.zeros(max(T, 1), np.uint32)
+    _tri.ref_estimate_triangulation_batch(C.byref(tracks.struct), C.byref(options),
+                                          xyz.ctypes.data_as(_dp), ok.ctypes.data_as(_u8p),
+                                          mask.ctypes.data_as(_u8p), nt.ctypes.data_as(_u32p))
+    return ok[:T].astype(bool), xyz[:T], mask[:O].astype(bool), nt[:T]
