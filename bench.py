@@ -648,15 +648,17 @@ def run_mapper_call(args, ctx, rank):
         import oracle as O
         oo = O.make_options(o.max_error, o.min_inlier_ratio, o.confidence,
                             o.dyn_num_trials_multiplier, o.min_num_trials, o.max_num_trials)
+        kind, impl = cpu_arm()
         tc = []
         for i in range(20):
-            O.set_prng_seed(i)
+            impl.set_prng_seed(i)
             t0 = time.perf_counter()
-            orep, omask = O.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], oo)
+            orep, omask = impl.ransac_p6l(sc["lines"], sc["aligned"], sc["points"], oo)
             tc.append(time.perf_counter() - t0)
         out["cpu_baseline"] = {"value": len(tc) / sum(tc), "unit": "calls/s", "cores": 1,
-                               "kind": "port", "ms_per_call": 1e3 * sum(tc) / len(tc),
-                               "sample": "20 whole calls (seeds 0..19) of the oracle's serial loop"}
+                               "kind": kind, "ms_per_call": 1e3 * sum(tc) / len(tc),
+                               "sample": "20 whole calls (seeds 0..19) of the serial loop; "
+                                         + CPU_ARM_TEXT[kind]}
     return out
 
 
