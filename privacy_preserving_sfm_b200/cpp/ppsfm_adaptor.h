@@ -474,7 +474,13 @@ inline bool EstimateTriangulation(
     const std::vector<TriangulationEstimator::PointData>& point_data,
     const std::vector<TriangulationEstimator::PoseData<CameraT>>& pose_data,
     std::vector<char>* inlier_mask, Vector3d* xyz) {
-  PPSFM_CHECK(point_data.size() >= 3);  // CHECK_GE(point_data.size(), 3), triangulation.cc:124
+  // src/estimators/triangulation.cc:122-130: two views are a contract violation only below 2;
+  // exactly two return false
+  PPSFM_CHECK(inlier_mask != nullptr && xyz != nullptr);
+  PPSFM_CHECK(point_data.size() >= 2);
+  PPSFM_CHECK(point_data.size() == pose_data.size());
+  options.Check();
+  if (point_data.size() < 3) return false;
   std::vector<char> ok;
   std::vector<std::vector<char>> masks;
   std::vector<Vector3d> pts;
