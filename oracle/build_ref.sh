@@ -12,6 +12,11 @@
 #   libref_tri.so  : the reference's OWN LORANSAC / CombinationSampler / NChooseK sources
 #                    (src/optim/loransac.h, combination_sampler.cc, src/util/math.cc) driving the
 #                    oracle's per-track triangulation estimator (oracle/ref/ref_triangulation.cc)
+#   libref_ba_setup.so : the reference's OWN bundle-adjustment assembly (src/optim/
+#                    bundle_adjustment.cc + the classes it reads) against a RECORDING ceres::Problem,
+#                    and the product's adaptor on the same colmap::Reconstruction
+#                    (oracle/ref/ref_ba_setup.cc); links libppsfm_b200.so for the adaptor's option
+#                    defaults (host-only entry points)
 #   libref_cost.so : the reference's OWN line cost functors (src/base/cost_functions.h) and
 #                    camera models (src/base/camera_models.{h,cc}) behind C entry points
 #                    (oracle/ref/ref_cost.cc), against the Ceres / Eigen / glog / Boost stand-ins
@@ -42,3 +47,15 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$ref/src/optim/support_measurement.cc" "$ref/src/util/math.cc" \
     -o "$here/_ref/libref_tri.so"
 echo "built $here/_ref/libref_tri.so"
+
+lib="$here/../privacy_preserving_sfm_b200"
+if [ -f "$lib/libppsfm_b200.so" ]; then
+g++ -O1 -std=c++17 -fPIC -w -shared -fvisibility=hidden -ffunction-sections -fdata-sections \
+    -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" -I"$here/../include" -I"$lib/cpp" \
+    "$here/ref/ref_ba_setup.cc" "$ref/src/optim/bundle_adjustment.cc" "$ref/src/base/image.cc" \
+    "$ref/src/base/point3d.cc" "$ref/src/base/track.cc" "$ref/src/base/camera.cc" \
+    "$ref/src/base/camera_models.cc" "$ref/src/util/string.cc" "$ref/src/util/misc.cc" \
+    "$ref/src/util/threading.cc" "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
+    -Wl,--gc-sections -L"$lib" -lppsfm_b200 -Wl,-rpath,"$lib" -o "$here/_ref/libref_ba_setup.so"
+echo "built $here/_ref/libref_ba_setup.so"
+fi

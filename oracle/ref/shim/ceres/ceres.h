@@ -10,6 +10,9 @@
 #pragma once
 #include <cmath>
 #include <memory>
+#include <string>
+#include <utility>
+#include <vector>
 
 #include <glog/logging.h>  // (real Ceres headers pull glog in; cost_functions.h relies on it for CHECK_NEAR)
 
@@ -178,18 +181,166 @@ inline void UnitQuaternionRotatePoint(const T q[4], const T pt[3], T result[3]) 
   result[2] = T(2) * ((t7 - t3) * pt[0] + (t2 + t9) * pt[1] + (t5 + t8) * pt[2]) + pt[2];
 }
 
-// the class names of the functors' Create() factories (never evaluated through here)
+// ---------------------------------------------------------------------------------------------
+// The solver-facing classes, as a RECORDER: ceres::Problem keeps what the reference's
+// BundleAdjuster::SetUp adds to it (residual blocks with their cost-function kind and parameter
+// blocks, constant blocks, parameterisations), ceres::Solve stores the options it was handed and
+// solves nothing.  oracle/ref/ref_ba_setup.cc reads the record back; tests/test_ref_ba_setup.py
+// compares it with what the oracle and the product assemble for the same configuration.
+// ---------------------------------------------------------------------------------------------
+#define CERES_VERSION_MAJOR 2
+#define CERES_VERSION_MINOR 0
+
+enum LinearSolverType { DENSE_NORMAL_CHOLESKY, DENSE_QR, SPARSE_NORMAL_CHOLESKY, DENSE_SCHUR,
+                        SPARSE_SCHUR, ITERATIVE_SCHUR, CGNR };
+enum PreconditionerType { IDENTITY, JACOBI, SCHUR_JACOBI, CLUSTER_JACOBI, CLUSTER_TRIDIAGONAL };
+enum TerminationType { CONVERGENCE, NO_CONVERGENCE, FAILURE, USER_SUCCESS, USER_FAILURE };
+
+class LossFunction {
+ public:
+  virtual ~LossFunction() {}
+  virtual int Kind() const = 0;  // 0 trivial, 1 soft-L1, 2 Cauchy (the recorder's numbering)
+  virtual double Scale() const { return 0.0; }
+};
+class TrivialLoss : public LossFunction {
+ public:
+  int Kind() const override { return 0; }
+};
+class SoftLOneLoss : public LossFunction {
+  double a_;
+
+ public:
+  explicit SoftLOneLoss(double a) : a_(a) {}
+  int Kind() const override { return 1; }
+  double Scale() const override { return a_; }
+};
+class CauchyLoss : public LossFunction {
+  double a_;
+
+ public:
+  explicit CauchyLoss(double a) : a_(a) {}
+  int Kind() const override { return 2; }
+  double Scale() const override { return a_; }
+};
+
+class LocalParameterization {
+ public:
+  virtual ~LocalParameterization() {}
+  virtual int GlobalSize() const = 0;
+  virtual int LocalSize() const = 0;
+  virtual const std::vector<int>* ConstantIndices() const { return nullptr; }
+};
+class QuaternionParameterization : public LocalParameterization {
+ public:
+  int GlobalSize() const override { return 4; }
+  int LocalSize() const override { return 3; }
+};
+class SubsetParameterization : public LocalParameterization {
+  int size_;
+  std::vector<int> constant_;
+
+ public:
+  SubsetParameterization(int size, const std::vector<int>& constant_parameters)
+      : size_(size), constant_(constant_parameters) {}
+  int GlobalSize() const override { return size_; }
+  int LocalSize() const override { return size_ - static_cast<int>(constant_.size()); }
+  const std::vector<int>* ConstantIndices() const override { return &constant_; }
+};
+
 class CostFunction {
  public:
   virtual ~CostFunction() {}
+  virtual int NumResiduals() const = 0;
+  virtual const std::vector<int>& ParameterBlockSizes() const = 0;
+  virtual const void* FunctorAddress() const = 0;
 };
 template <typename Functor, int kNumResiduals, int... Ns>
 class AutoDiffCostFunction : public CostFunction {
   std::unique_ptr<Functor> functor_;
+  std::vector<int> sizes_;
 
  public:
-  explicit AutoDiffCostFunction(Functor* functor) : functor_(functor) {}
+  explicit AutoDiffCostFunction(Functor* functor) : functor_(functor), sizes_{Ns...} {}
+  int NumResiduals() const override { return kNumResiduals; }
+  const std::vector<int>& ParameterBlockSizes() const override { return sizes_; }
+  const void* FunctorAddress() const override { return functor_.get(); }
   const Functor& functor() const { return *functor_; }
 };
+
+class Problem {
+ public:
+  struct ResidualBlock {
+    std::unique_ptr<CostFunction> cost;
+    const LossFunction* loss;
+    std::vector<double*> blocks;
+  };
+  std::vector<ResidualBlock> residual_blocks;
+  std::vector<double*> constant_blocks;
+  std::vector<std::pair<double*, std::unique_ptr<LocalParameterization>>> parameterizations;
+  std::vector<std::unique_ptr<const LossFunction>> owned_losses;
+
+  template <typename... Ts>
+  void AddResidualBlock(CostFunction* cost, LossFunction* loss, Ts*... blocks) {
+    ResidualBlock rb;
+    rb.cost.reset(cost);
+    rb.loss = loss;
+    rb.blocks = {blocks...};
+    bool owned = false;
+    for (const auto& l : owned_losses) owned = owned || l.get() == loss;
+    if (!owned && loss != nullptr) owned_losses.emplace_back(loss);  // Ceres takes ownership
+    residual_blocks.push_back(std::move(rb));
+  }
+  void SetParameterBlockConstant(double* block) { constant_blocks.push_back(block); }
+  void SetParameterization(double* block, LocalParameterization* p) {
+    parameterizations.emplace_back(block, std::unique_ptr<LocalParameterization>(p));
+  }
+  int NumResidualBlocks() const { return static_cast<int>(residual_blocks.size()); }
+  int NumResiduals() const {
+    int n = 0;
+    for (const auto& rb : residual_blocks) n += rb.cost->NumResiduals();
+    return n;
+  }
+};
+
+class Solver {
+ public:
+  struct Options {
+    double function_tolerance = 1e-6;
+    double gradient_tolerance = 1e-10;
+    double parameter_tolerance = 1e-8;
+    bool minimizer_progress_to_stdout = false;
+    int max_num_iterations = 50;
+    int max_linear_solver_iterations = 500;
+    int max_num_consecutive_invalid_steps = 5;
+    int max_consecutive_nonmonotonic_steps = 5;
+    int num_threads = 1;
+    LinearSolverType linear_solver_type = SPARSE_NORMAL_CHOLESKY;
+    PreconditionerType preconditioner_type = JACOBI;
+    bool IsValid(std::string*) const { return true; }
+  };
+  struct Summary {
+    int num_residuals_reduced = 0;
+    int num_effective_parameters_reduced = 0;
+    int num_successful_steps = 0;
+    int num_unsuccessful_steps = 0;
+    double total_time_in_seconds = 0.0;
+    double initial_cost = 0.0;
+    double final_cost = 0.0;
+    TerminationType termination_type = NO_CONVERGENCE;
+    std::string BriefReport() const { return "recorder: nothing solved"; }
+    std::string FullReport() const { return BriefReport(); }
+    bool IsSolutionUsable() const { return false; }
+  };
+};
+
+// what the last ceres::Solve call was handed (one per thread)
+inline Solver::Options& LastSolveOptions() {
+  static thread_local Solver::Options o;
+  return o;
+}
+inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
+  LastSolveOptions() = options;
+  summary->num_residuals_reduced = problem->NumResiduals();
+}
 
 }  // namespace ceres

@@ -4,8 +4,16 @@
 #pragma once
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <string>
 #include <iostream>
 #include <sstream>
+
+namespace google {
+inline void InitGoogleLogging(const char*) {}
+inline void InstallFailureSignalHandler() {}
+}  // namespace google
 
 namespace glog_shim {
 struct Fatal {

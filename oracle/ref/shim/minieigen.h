@@ -13,6 +13,7 @@
 //   * setRandom() / Quaternion::UnitRandom() return FIXED generic values (the ones the oracle
 //     uses) instead of C rand(): the two degenerate fallbacks stay reproducible.
 #pragma once
+#include <cassert>
 #include <cmath>
 #include <complex>
 #include <cstddef>
@@ -118,10 +119,13 @@ class MatrixBase {
 
   template <class O>
   D& assign(const MatrixBase<O>& o) {
-    static_assert(O::Rows == Rows && O::Cols == Cols, "minieigen: size mismatch");
+    constexpr bool same = O::Rows == Rows && O::Cols == Cols;
+    // Eigen transposes implicitly when a row vector is assigned to a column vector (and back)
+    constexpr bool vec_t = O::Rows == Cols && O::Cols == Rows && (Rows == 1 || Cols == 1);
+    static_assert(same || vec_t, "minieigen: size mismatch");
     const typename O::Plain v = o.eval();  // (aliasing-safe)
     for (int j = 0; j < Cols; ++j)
-      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = v.coeff(i, j);
+      for (int i = 0; i < Rows; ++i) derived().coeffRef(i, j) = same ? v.coeff(i, j) : v.coeff(j, i);
     return derived();
   }
   template <class O>
@@ -183,6 +187,19 @@ class MatrixBase {
     return s;
   }
   Scalar norm() const { return std::sqrt(squaredNorm()); }
+  Scalar sum() const {
+    Scalar s = derived().coeff(0, 0);
+    for (int j = 0; j < Cols; ++j)
+      for (int i = (j == 0 ? 1 : 0); i < Rows; ++i) s = s + derived().coeff(i, j);
+    return s;
+  }
+  Plain normalized() const { return eval() / norm(); }
+  bool hasNaN() const {
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i)
+        if (derived().coeff(i, j) != derived().coeff(i, j)) return true;
+    return false;
+  }
   void normalize() { *this /= norm(); }
   template <class O>
   Scalar dot(const MatrixBase<O>& o) const {
@@ -221,6 +238,11 @@ class MatrixBase {
   Block<D, BR, BC> block(int i, int j) { return Block<D, BR, BC>(derived(), i, j); }
   template <int BR, int BC>
   Block<const D, BR, BC> block(int i, int j) const { return Block<const D, BR, BC>(derived(), i, j); }
+  // head<N>() of a column vector
+  template <int N>
+  Block<D, N, 1> head() { return Block<D, N, 1>(derived(), 0, 0); }
+  template <int N>
+  Block<const D, N, 1> head() const { return Block<const D, N, 1>(derived(), 0, 0); }
   Block<D, Rows, 1> col(int j) { return Block<D, Rows, 1>(derived(), 0, j); }
   Block<const D, Rows, 1> col(int j) const { return Block<const D, Rows, 1>(derived(), 0, j); }
   Block<D, 1, Cols> row(int i) { return Block<D, 1, Cols>(derived(), i, 0); }

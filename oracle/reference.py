@@ -20,6 +20,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "_ref", "libref_p6l.so")
 COST_LIB_PATH = os.path.join(_HERE, "_ref", "libref_cost.so")
 TRI_LIB_PATH = os.path.join(_HERE, "_ref", "libref_tri.so")
+BA_SETUP_LIB_PATH = os.path.join(_HERE, "_ref", "libref_ba_setup.so")
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -30,17 +31,21 @@ def build(reference_root="/root/reference"):
     """Compile oracle/_ref/ where the reference tree exists; returns True if the library is there."""
     srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "ref_cost.cc"),
             os.path.join(_HERE, "ref", "ref_triangulation.cc"),
+            os.path.join(_HERE, "ref", "ref_ba_setup.cc"),
+            os.path.join(_HERE, "..", "privacy_preserving_sfm_b200", "cpp", "ppsfm_adaptor.h"),
             os.path.join(_HERE, "triangulation_oracle.cc"),
             os.path.join(_HERE, "ref", "shim", "minieigen.h"),
             os.path.join(_HERE, "ref", "shim", "ceres", "ceres.h"),
             os.path.join(_HERE, "ref", "shim", "glog", "logging.h"),
             os.path.join(_HERE, "eigen_restated.h"), os.path.join(_HERE, "build_ref.sh")]
     fresh = all(os.path.exists(lp) and all(os.path.getmtime(lp) >= os.path.getmtime(s)
-                                           for s in srcs) for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH))
+                                           for s in srcs)
+                for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH))
     if not fresh and os.path.isdir(os.path.join(reference_root, "src", "estimators")):
         subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")],
                               stdout=subprocess.DEVNULL)
-    return all(os.path.exists(lp) for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH))
+    return all(os.path.exists(lp)
+               for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH))
 
 
 def available():
@@ -280,3 +285,92 @@ def estimate_triangulation_batch(tracks, options):
                                           xyz.ctypes.data_as(_dp), ok.ctypes.data_as(_u8p),
                                           mask.ctypes.data_as(_u8p), nt.ctypes.data_as(_u32p))
     return ok[:T].astype(bool), xyz[:T], mask[:O].astype(bool), nt[:T]
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref/libref_ba_setup.so: the reference's BundleAdjuster::SetUp against a recording
+# ceres::Problem, and the product's adaptor on the same colmap::Reconstruction
+# ---------------------------------------------------------------------------------------------
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class _BaScene(C.Structure):
+    _fields_ = [("num_cameras", C.c_int32), ("camera_model", _i32p), ("camera_params", _dp),
+                ("num_images", C.c_int32), ("image_camera", _i32p), ("qvecs", _dp), ("tvecs", _dp),
+                ("num_points", C.c_int32), ("points", _dp), ("num_lines", C.c_int64),
+                ("image_line_start", _i64p), ("lines", _dp), ("line_point", _i32p)]
+
+
+class _BaConfig(C.Structure):
+    _fields_ = [("num_config_images", C.c_int32), ("config_images", _i32p),
+                ("num_constant_poses", C.c_int32), ("constant_poses", _i32p),
+                ("num_constant_tvecs", C.c_int32), ("constant_tvec_image", _i32p),
+                ("constant_tvec_mask", _i32p),
+                ("num_variable_points", C.c_int32), ("variable_points", _i32p),
+                ("num_constant_points", C.c_int32), ("constant_points", _i32p),
+                ("num_constant_cameras", C.c_int32), ("constant_cameras", _i32p),
+                ("loss_type", C.c_int32), ("loss_scale", C.c_double),
+                ("refine_focal_length", C.c_int32), ("refine_principal_point", C.c_int32),
+                ("refine_extra_params", C.c_int32), ("refine_extrinsics", C.c_int32)]
+
+
+_ba_setup = None
+
+
+def ba_setup_compare(scene, config):
+    """scene: dict(camera_model [C], camera_params [C, 12], image_camera [I], qvecs [I, 4],
+    tvecs [I, 3], points [P, 3], image_line_start [I + 1], lines [L, 3], line_point [L] (-1: no
+    3-D point)); config: dict(images, constant_poses, constant_tvecs {image: [idx]},
+    variable_points, constant_points, constant_cameras, loss_type, loss_scale, refine_focal_length,
+    refine_principal_point, refine_extra_params, refine_extrinsics), all indices 0-based.
+    Returns (rc, reference_text, product_text): the canonical descriptions of what the reference's
+    BundleAdjuster::SetUp hands to Ceres and of what the product's adaptor assembles."""
+    global _ba_setup
+    if _ba_setup is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libref_ba_setup.so is not built (needs /root/reference)")
+        _ba_setup = C.CDLL(BA_SETUP_LIB_PATH)
+        _ba_setup.ref_ba_setup_compare.argtypes = [C.POINTER(_BaScene), C.POINTER(_BaConfig),
+                                                   C.c_char_p, C.c_char_p, C.c_size_t]
+    keep = []
+
+    def i32(a):
+        a = np.ascontiguousarray(a, dtype=np.int32)
+        keep.append(a)
+        return len(a), a.ctypes.data_as(_i32p)
+
+    def f64(a):
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        keep.append(a)
+        return a.ctypes.data_as(_dp)
+
+    s = _BaScene()
+    s.num_cameras, s.camera_model = i32(scene["camera_model"])
+    s.camera_params = f64(scene["camera_params"])
+    s.num_images, s.image_camera = i32(scene["image_camera"])
+    s.qvecs, s.tvecs, s.points = f64(scene["qvecs"]), f64(scene["tvecs"]), f64(scene["points"])
+    s.num_points = len(scene["points"])
+    ils = np.ascontiguousarray(scene["image_line_start"], dtype=np.int64)
+    keep.append(ils)
+    s.image_line_start = ils.ctypes.data_as(_i64p)
+    s.lines = f64(scene["lines"])
+    s.num_lines, s.line_point = i32(scene["line_point"])
+    c = _BaConfig()
+    c.num_config_images, c.config_images = i32(config.get("images", []))
+    c.num_constant_poses, c.constant_poses = i32(config.get("constant_poses", []))
+    tv = config.get("constant_tvecs", {})
+    c.num_constant_tvecs, c.constant_tvec_image = i32(list(tv.keys()))
+    _, c.constant_tvec_mask = i32([sum(1 << k for k in idxs) for idxs in tv.values()])
+    c.num_variable_points, c.variable_points = i32(config.get("variable_points", []))
+    c.num_constant_points, c.constant_points = i32(config.get("constant_points", []))
+    c.num_constant_cameras, c.constant_cameras = i32(config.get("constant_cameras", []))
+    c.loss_type, c.loss_scale = config.get("loss_type", 0), config.get("loss_scale", 1.0)
+    c.refine_focal_length = int(config.get("refine_focal_length", False))
+    c.refine_principal_point = int(config.get("refine_principal_point", False))
+    c.refine_extra_params = int(config.get("refine_extra_params", False))
+    c.refine_extrinsics = int(config.get("refine_extrinsics", True))
+    cap = 1 << 22
+    a, b = C.create_string_buffer(cap), C.create_string_buffer(cap)
+    rc = _ba_setup.ref_ba_setup_compare(C.byref(s), C.byref(c), a, b, cap)
+    return rc, a.value.decode(), b.value.decode()

@@ -451,6 +451,7 @@ class BundleAdjuster:
         qv, tv, flags, icam, cmodel, cparams, pts = [], [], [], [], [], [], []
         oi, op, ol = [], [], []
         num_obs_of_point = {}
+        config_cameras, outside_cameras = set(), set()
 
         def cam_idx(camera_id):
             if camera_id not in cam_index:
@@ -498,6 +499,7 @@ class BundleAdjuster:
                 oi.append(img_idx(image_id, constant_pose))
                 op.append(pt_idx(line.point3D_id))
                 ol.append(line.line)
+                config_cameras.add(img.camera_id)         # camera_ids_.insert (:432-434)
         # AddPointToProblem (:437-488): observations of configured points in images outside the
         # image set enter through the constant-pose functor
         for pid in list(sorted(cfg.VariablePoints())) + list(sorted(cfg.ConstantPoints())):
@@ -509,6 +511,10 @@ class BundleAdjuster:
                     continue
                 num_obs_of_point[pid] = num_obs_of_point.get(pid, 0) + 1
                 img = rec.Image(image_id)
+                # a camera that enters only through images outside the configuration is
+                # constant (config_.SetConstantCamera, :476-479)
+                if img.camera_id not in config_cameras:
+                    outside_cameras.add(img.camera_id)
                 oi.append(img_idx(image_id, True))
                 op.append(pt_idx(pid))
                 ol.append(img.lines[line_idx].line)
@@ -527,7 +533,8 @@ class BundleAdjuster:
         arrays = BaArrays(z(qv, 4), z(tv, 3), z(pts, 3), oi, op, z(ol, 3),
                           cmodel if cmodel else [1], z(cparams, 12) if cparams else np.zeros((1, 12)),
                           image_camera=icam, pose_flags=flags, point_const=point_const,
-                          camera_const=[1 if cfg.IsConstantCamera(c) else 0 for c in cam_ids]
+                          camera_const=[1 if (cfg.IsConstantCamera(c) or c in outside_cameras)
+                                        else 0 for c in cam_ids]
                           if cam_ids else None)
         img_ids = [None] * len(qv)
         for iid, i in img_index.items():

@@ -719,6 +719,28 @@ class BundleAdjuster {
 
   const ppsfm_ba_summary& Summary() const { return summary_; }
 
+  // The assembly alone (what SetUp, bundle_adjustment.cc:326-542, decides), without a solve: the
+  // flat problem Solve() would hand to ppsfm_ba_solve.  For tests of the assembly rules against
+  // the reference's own SetUp (tests/test_ref_ba_setup.py); uses up the adjuster like Solve().
+  struct Assembly {
+    std::vector<image_t> image_ids;      // problem order
+    std::vector<camera_t> camera_ids;
+    std::vector<point3D_t> point_ids;
+    std::vector<uint8_t> pose_flags;     // per image: 1 constant pose, 2 << k: tvec[k] constant
+    std::vector<uint8_t> point_const;    // per point
+    std::vector<uint8_t> camera_const;   // per camera
+    std::vector<int32_t> image_camera, obs_image, obs_point;
+    std::vector<double> obs_line;
+  };
+  Assembly AssembleOnly(ReconstructionT* reconstruction) {
+    PPSFM_CHECK(reconstruction != nullptr);
+    PPSFM_CHECK(!used_);
+    used_ = true;
+    SetUp(reconstruction);
+    return Assembly{image_ids_,  camera_ids_,   point_ids_, pose_flags_, point_const_,
+                    camera_const_, image_camera_, obs_image_, obs_point_,  obs_line_};
+  }
+
   bool Solve(ReconstructionT* reconstruction) {
     PPSFM_CHECK(reconstruction != nullptr);
     PPSFM_CHECK(!used_);  // "Cannot use the same BundleAdjuster multiple times"
@@ -741,11 +763,7 @@ class BundleAdjuster {
     pb.obs_image = obs_image_.data();
     pb.obs_point = obs_point_.data();
     pb.obs_line = obs_line_.data();
-    // ParameterizeCameras (bundle_adjustment.cc:490-528)
-    std::vector<uint8_t> camera_const(camera_ids_.size(), 0);
-    for (size_t c = 0; c < camera_ids_.size(); ++c)
-      camera_const[c] = config_.IsConstantCamera(camera_ids_[c]) ? 1 : 0;
-    pb.camera_const = camera_const.data();
+    pb.camera_const = camera_const_.data();  // ParameterizeCameras (bundle_adjustment.cc:490-528)
     ppsfm_ba_options o = options_.solver_options;
     o.refine_focal_length = options_.refine_focal_length ? 1 : 0;
     o.refine_principal_point = options_.refine_principal_point ? 1 : 0;
@@ -826,6 +844,7 @@ class BundleAdjuster {
   // bundle_adjustment.cc:326-542
   void SetUp(ReconstructionT* rec) {
     std::unordered_map<point3D_t, size_t> num_obs;
+    std::unordered_set<camera_t> config_cameras, outside_cameras;
     for (const image_t image_id : config_.Images()) {  // AddImageToProblem (:348-435)
       auto& image = rec->Image(image_id);
       image.NormalizeQvec();
@@ -835,6 +854,7 @@ class BundleAdjuster {
         num_obs[line.Point3DId()] += 1;
         const int ii = ImageIndex(rec, image_id, constant_pose);
         AddObservation(ii, PointIndex(rec, line.Point3DId()), line.Line().data());
+        config_cameras.insert(image.CameraId());  // camera_ids_.insert (:432-434)
       }
     }
     auto add_point = [&](point3D_t pid) {  // AddPointToProblem (:437-488)
@@ -844,6 +864,9 @@ class BundleAdjuster {
         if (config_.HasImage(el.image_id)) continue;
         num_obs[pid] += 1;
         auto& image = rec->Image(el.image_id);
+        // a camera that enters only through images outside the configuration is constant
+        // (config_.SetConstantCamera, :476-479)
+        if (config_cameras.count(image.CameraId()) == 0) outside_cameras.insert(image.CameraId());
         const int ii = ImageIndex(rec, el.image_id, /*constant=*/true);
         AddObservation(ii, PointIndex(rec, pid), image.Lines()[el.line_idx].Line().data());
       }
@@ -859,6 +882,11 @@ class BundleAdjuster {
       auto it = point_index_.find(pid);
       if (it != point_index_.end()) point_const_[it->second] = 1;
     }
+    // ParameterizeCameras (:490-528): constant if the config says so or AddPointToProblem did
+    camera_const_.assign(camera_ids_.size(), 0);
+    for (size_t c = 0; c < camera_ids_.size(); ++c)
+      camera_const_[c] = (config_.IsConstantCamera(camera_ids_[c]) ||
+                          outside_cameras.count(camera_ids_[c]) > 0) ? 1 : 0;
   }
 
   BundleAdjustmentOptions options_;
@@ -872,7 +900,7 @@ class BundleAdjuster {
   std::vector<camera_t> camera_ids_;
   std::vector<point3D_t> point_ids_;
   std::vector<double> qvecs_, tvecs_, points_, camera_params_, obs_line_;
-  std::vector<uint8_t> pose_flags_, point_const_;
+  std::vector<uint8_t> pose_flags_, point_const_, camera_const_;
   std::vector<int32_t> image_camera_, camera_model_, obs_image_, obs_point_;
 };
 
