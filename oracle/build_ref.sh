@@ -4,7 +4,8 @@
 #   libref_init.so : ransac_lib::LocallyOptimizedMSAC (lib/RansacLib, header-only) driving the
 #                    product's init estimators — see oracle/ref/ref_init.cc
 #   libref_p6l.so  : the reference's OWN P6L / re3q3 / line residual / RANSAC loop / sampler /
-#                    support sources (src/estimators/absolute_pose.cc, lib/re3q3/re3q3/re3q3.h,
+#                    support sources and the EstimateAbsolutePoseFromLines wrapper
+#                    (src/estimators/{absolute_pose,pose}.cc, lib/re3q3/re3q3/re3q3.h,
 #                    src/estimators/utils.cc, src/optim/{ransac.h,random_sampler.cc,
 #                    support_measurement.cc}, src/util/random.cc) behind C entry points
 #                    (oracle/ref/ref_p6l.cc), compiled against the Eigen / glog stand-ins of
@@ -30,10 +31,12 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared \
 echo "built $here/_ref/libref_init.so"
 
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
-    -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib/re3q3" \
+    -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
+    -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" -I"$ref/lib/re3q3" \
     "$here/ref/ref_p6l.cc" "$ref/src/estimators/absolute_pose.cc" "$ref/src/estimators/utils.cc" \
-    "$ref/src/optim/random_sampler.cc" "$ref/src/optim/support_measurement.cc" \
-    "$ref/src/util/random.cc" -o "$here/_ref/libref_p6l.so"
+    "$ref/src/estimators/pose.cc" "$ref/src/optim/random_sampler.cc" \
+    "$ref/src/optim/support_measurement.cc" "$ref/src/util/random.cc" \
+    -o "$here/_ref/libref_p6l.so"
 echo "built $here/_ref/libref_p6l.so"
 
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \

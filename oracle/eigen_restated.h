@@ -6,6 +6,7 @@
 //   * Matrix3d::determinant()                 (re3q3.h:24-26, absolute_pose.cc:126)
 //   * PartialPivLU<Matrix3d>::solve           (absolute_pose.cc:137, re3q3.h:71,75,79)
 //   * EigenSolver<Matrix<double,8,8>>         (re3q3.h:164-165)
+//   * Quaterniond(Matrix3d)                   (base/pose.cc:41-44, used by estimators/pose.cc:86)
 // Included by ppsfm_oracle.cc (the restatement) AND by the Eigen stand-in under oracle/ref/shim/
 // that lets the reference's own sources compile (oracle/build_ref.sh -> oracle/_ref/libref_p6l.so),
 // so both sides of tests/test_ref_p6l.py share exactly these operations and everything ELSE the
@@ -350,6 +351,38 @@ inline bool Poly8Roots(const double* c, double* re, double* im) {
   const bool ok = h.Reduce();
   h.Eigenvalues(re, im);
   return ok;
+}
+
+// Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl):
+// Ken Shoemake's trace-branch algorithm.  R is column-major: R(r,c) = R[3c + r]; q = (w, x, y, z).
+inline void QuaternionFromRotationMatrix(const double* R, double* q) {
+  auto at = [&](int r, int c) { return R[3 * c + r]; };
+  double t = at(0, 0) + at(1, 1) + at(2, 2);
+  double w, v[3];
+  if (t > 0.0) {
+    t = std::sqrt(t + 1.0);
+    w = 0.5 * t;
+    t = 0.5 / t;
+    v[0] = (at(2, 1) - at(1, 2)) * t;
+    v[1] = (at(0, 2) - at(2, 0)) * t;
+    v[2] = (at(1, 0) - at(0, 1)) * t;
+  } else {
+    int i = 0;
+    if (at(1, 1) > at(0, 0)) i = 1;
+    if (at(2, 2) > at(i, i)) i = 2;
+    const int j = (i + 1) % 3;
+    const int k = (j + 1) % 3;
+    t = std::sqrt(at(i, i) - at(j, j) - at(k, k) + 1.0);
+    v[i] = 0.5 * t;
+    t = 0.5 / t;
+    w = (at(k, j) - at(j, k)) * t;
+    v[j] = (at(j, i) + at(i, j)) * t;
+    v[k] = (at(k, i) + at(i, k)) * t;
+  }
+  q[0] = w;
+  q[1] = v[0];
+  q[2] = v[1];
+  q[3] = v[2];
 }
 
 }  // namespace eigen_restated

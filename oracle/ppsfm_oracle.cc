@@ -572,35 +572,7 @@ int orc_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double
 }
 
 void orc_rotation_matrix_to_quaternion(const double* R, double* q) {
-  // Eigen::Quaterniond(Matrix3d) (Eigen/src/Geometry/Quaternion.h, quaternionbase_assign_impl):
-  // Ken Shoemake's trace-branch algorithm.  R is column-major: R(r,c) = R[3c + r].
-  auto at = [&](int r, int c) { return R[3 * c + r]; };
-  double t = at(0, 0) + at(1, 1) + at(2, 2);
-  double w, v[3];
-  if (t > 0.0) {
-    t = std::sqrt(t + 1.0);
-    w = 0.5 * t;
-    t = 0.5 / t;
-    v[0] = (at(2, 1) - at(1, 2)) * t;
-    v[1] = (at(0, 2) - at(2, 0)) * t;
-    v[2] = (at(1, 0) - at(0, 1)) * t;
-  } else {
-    int i = 0;
-    if (at(1, 1) > at(0, 0)) i = 1;
-    if (at(2, 2) > at(i, i)) i = 2;
-    const int j = (i + 1) % 3;
-    const int k = (j + 1) % 3;
-    t = std::sqrt(at(i, i) - at(j, j) - at(k, k) + 1.0);
-    v[i] = 0.5 * t;
-    t = 0.5 / t;
-    w = (at(k, j) - at(j, k)) * t;
-    v[j] = (at(j, i) + at(i, j)) * t;
-    v[k] = (at(k, i) + at(i, k)) * t;
-  }
-  q[0] = w;
-  q[1] = v[0];
-  q[2] = v[1];
-  q[3] = v[2];
+  QuaternionFromRotationMatrix(R, q);  // Eigen::Quaterniond(Matrix3d): eigen_restated.h
 }
 
 void orc_ransac_p6l(const double* lines, const uint8_t* aligned, const double* points, size_t n,

@@ -6,6 +6,7 @@
 //   src/optim/ransac.h                RANSAC<Estimator, SupportMeasurer, Sampler>::Estimate (A6)
 //   src/optim/random_sampler.cc, src/util/random.{h,cc}   sampler + PRNG        (A7)
 //   src/optim/support_measurement.cc  Inlier / MEstimator support               (A8)
+//   src/estimators/pose.cc            EstimateAbsolutePoseFromLines             (A9)
 // Eigen and glog are absent in this image: the sources compile against the stand-ins under
 // oracle/ref/shim/ (minieigen.h: the Eigen calls are the restatements of oracle/eigen_restated.h,
 // shared with the oracle; glog/logging.h: CHECK* = print + abort).  So what tests/test_ref_p6l.py
@@ -18,7 +19,9 @@
 #include <random>
 #include <vector>
 
+#include "base/pose.h"
 #include "estimators/absolute_pose.h"
+#include "estimators/pose.h"
 #include "estimators/utils.h"
 #include "feature/types.h"
 #include "optim/random_sampler.h"
@@ -29,6 +32,26 @@
 // defined (non-inline) by lib/re3q3/re3q3/re3q3.h inside the absolute_pose.cc translation unit
 int re3q3(Eigen::Matrix<double, 3, 10> coeffs, Eigen::Matrix<double, 3, 8>* solutions,
           bool try_random_var_change);
+
+#define REF_API extern "C" __attribute__((visibility("default")))
+
+// base/pose.cc needs more of Eigen than the stand-in has; the two of its functions that
+// estimators/pose.cc calls are restated here (pose.cc:41-44, :53-62).  Quaterniond(Matrix3d) is
+// eigen_restated::QuaternionFromRotationMatrix, the function the oracle uses.
+namespace colmap {
+Eigen::Vector4d RotationMatrixToQuaternion(const Eigen::Matrix3d& rot_mat) {
+  const Eigen::Quaterniond quat(rot_mat);
+  return Eigen::Vector4d(quat.w(), quat.x(), quat.y(), quat.z());
+}
+Eigen::Vector4d NormalizeQuaternion(const Eigen::Vector4d& qvec) {
+  const double norm = qvec.norm();
+  if (norm == 0) {
+    return Eigen::Vector4d(1.0, qvec(1), qvec(2), qvec(3));
+  } else {
+    return qvec / norm;
+  }
+}
+}  // namespace colmap
 
 namespace {
 
@@ -59,18 +82,17 @@ void Gather(const double* lines, const uint8_t* aligned, const double* points, s
 
 }  // namespace
 
-extern "C" {
 
-void ref_set_prng_seed(uint32_t seed) { colmap::SetPRNGSeed(seed); }
+REF_API void ref_set_prng_seed(uint32_t seed) { colmap::SetPRNGSeed(seed); }
 
 // the next 32-bit output of the generator, without consuming it (== orc_prng_peek)
-uint32_t ref_prng_peek(void) {
+REF_API uint32_t ref_prng_peek(void) {
   if (colmap::PRNG == nullptr) colmap::SetPRNGSeed();
   std::mt19937 copy = *colmap::PRNG;
   return static_cast<uint32_t>(copy());
 }
 
-void ref_line_residuals(const double* lines, const double* points, size_t n, const double* model,
+REF_API void ref_line_residuals(const double* lines, const double* points, size_t n, const double* model,
                         double* residuals_out) {
   std::vector<Eigen::Vector3d> l, p;
   for (size_t i = 0; i < n; ++i) {
@@ -84,7 +106,7 @@ void ref_line_residuals(const double* lines, const double* points, size_t n, con
   std::memcpy(residuals_out, r.data(), sizeof(double) * n);
 }
 
-void ref_inlier_support(const double* residuals, size_t n, double max_residual,
+REF_API void ref_inlier_support(const double* residuals, size_t n, double max_residual,
                         uint64_t* num_inliers, double* residual_sum) {
   colmap::InlierSupportMeasurer m;
   const auto s = m.Evaluate(std::vector<double>(residuals, residuals + n), max_residual);
@@ -93,7 +115,7 @@ void ref_inlier_support(const double* residuals, size_t n, double max_residual,
 }
 
 // 1 if support (n1, s1) is better than (n2, s2): InlierSupportMeasurer::Compare
-int ref_inlier_support_compare(uint64_t n1, double s1, uint64_t n2, double s2) {
+REF_API int ref_inlier_support_compare(uint64_t n1, double s1, uint64_t n2, double s2) {
   colmap::InlierSupportMeasurer m;
   colmap::InlierSupportMeasurer::Support a, b;
   a.num_inliers = n1;
@@ -103,7 +125,7 @@ int ref_inlier_support_compare(uint64_t n1, double s1, uint64_t n2, double s2) {
   return m.Compare(a, b) ? 1 : 0;
 }
 
-void ref_mestimator_support(const double* residuals, size_t n, double max_residual,
+REF_API void ref_mestimator_support(const double* residuals, size_t n, double max_residual,
                             uint64_t* num_inliers, double* score) {
   colmap::MEstimatorSupportMeasurer m;
   const auto s = m.Evaluate(std::vector<double>(residuals, residuals + n), max_residual);
@@ -111,13 +133,13 @@ void ref_mestimator_support(const double* residuals, size_t n, double max_residu
   *score = s.score;
 }
 
-uint64_t ref_compute_num_trials(uint64_t num_inliers, uint64_t num_samples, double confidence,
+REF_API uint64_t ref_compute_num_trials(uint64_t num_inliers, uint64_t num_samples, double confidence,
                                 double num_trials_multiplier) {
   return colmap::RANSAC<colmap::P6LEstimator>::ComputeNumTrials(num_inliers, num_samples,
                                                                  confidence, num_trials_multiplier);
 }
 
-void ref_sample_table(size_t n, size_t num_trials, uint32_t* table_out) {
+REF_API void ref_sample_table(size_t n, size_t num_trials, uint32_t* table_out) {
   colmap::RandomSampler sampler(colmap::P6LEstimator::kMinNumSamples);
   sampler.Initialize(n);
   for (size_t t = 0; t < num_trials; ++t) {
@@ -127,7 +149,7 @@ void ref_sample_table(size_t n, size_t num_trials, uint32_t* table_out) {
 }
 
 // coeffs: 3 x 10 row-major; solutions: 8 x 3 (solution-major) like orc_re3q3
-int ref_re3q3(const double* coeffs, double* solutions) {
+REF_API int ref_re3q3(const double* coeffs, double* solutions) {
   Eigen::Matrix<double, 3, 10> c;
   for (int k = 0; k < 3; ++k)
     for (int j = 0; j < 10; ++j) c(k, j) = coeffs[10 * k + j];
@@ -141,7 +163,7 @@ int ref_re3q3(const double* coeffs, double* solutions) {
 }
 
 // lines6 / points6: 6 x 3 row-major; models_out: up to 8 column-major 3x4 matrices
-int ref_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double* points6,
+REF_API int ref_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double* points6,
                      double* models_out) {
   colmap::FeatureLines X;
   std::vector<Eigen::Vector3d> Y;
@@ -154,7 +176,7 @@ int ref_p6l_estimate(const double* lines6, const uint8_t* aligned6, const double
 
 // colmap::RANSAC<P6LEstimator>(options).Estimate(X, Y) — the serial loop the GPU path replaces.
 // best_trial / best_model_idx / num_models_scored are not observable from outside the loop: -1 / 0.
-void ref_ransac_p6l(const double* lines, const uint8_t* aligned, const double* points, size_t n,
+REF_API void ref_ransac_p6l(const double* lines, const uint8_t* aligned, const double* points, size_t n,
                     const Options* options, Report* report, uint8_t* inlier_mask) {
   colmap::RANSACOptions o;
   o.max_error = options->max_error;
@@ -182,4 +204,34 @@ void ref_ransac_p6l(const double* lines, const uint8_t* aligned, const double* p
   }
 }
 
-}  // extern "C"
+
+// colmap::EstimateAbsolutePoseFromLines (src/estimators/pose.cc:52-94): the RANSAC call, the
+// rejection of mostly-aligned inlier sets, the quaternion conversion and the NaN check.
+// Returns the function's bool; inlier_mask is what the function leaves in *inlier_mask.
+REF_API int ref_estimate_absolute_pose_from_lines(const double* lines, const uint8_t* aligned,
+                                                  const double* points, size_t n,
+                                                  const Options* options, double* qvec,
+                                                  double* tvec, uint64_t* num_inliers,
+                                                  uint8_t* inlier_mask) {
+  colmap::RANSACOptions o;
+  o.max_error = options->max_error;
+  o.min_inlier_ratio = options->min_inlier_ratio;
+  o.confidence = options->confidence;
+  o.dyn_num_trials_multiplier = options->dyn_num_trials_multiplier;
+  o.min_num_trials = options->min_num_trials;
+  o.max_num_trials = options->max_num_trials;
+  colmap::FeatureLines X;
+  std::vector<Eigen::Vector3d> Y;
+  Gather(lines, aligned, points, n, &X, &Y);
+  Eigen::Vector4d q(0, 0, 0, 0);
+  Eigen::Vector3d t(0, 0, 0);
+  size_t ninl = 0;
+  std::vector<char> mask;
+  const bool ok = colmap::EstimateAbsolutePoseFromLines(o, X, Y, &q, &t, &ninl, &mask);
+  for (int k = 0; k < 4; ++k) qvec[k] = q(k);
+  for (int k = 0; k < 3; ++k) tvec[k] = t(k);
+  *num_inliers = ninl;
+  std::memset(inlier_mask, 0, n);
+  for (size_t i = 0; i < mask.size(); ++i) inlier_mask[i] = mask[i] ? 1 : 0;
+  return ok ? 1 : 0;
+}

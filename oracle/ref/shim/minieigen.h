@@ -238,6 +238,29 @@ class MatrixBase {
   Block<D, BR, BC> block(int i, int j) { return Block<D, BR, BC>(derived(), i, j); }
   template <int BR, int BC>
   Block<const D, BR, BC> block(int i, int j) const { return Block<const D, BR, BC>(derived(), i, j); }
+  template <int N>
+  Block<D, Rows, N> leftCols() { return Block<D, Rows, N>(derived(), 0, 0); }
+  template <int N>
+  Block<const D, Rows, N> leftCols() const { return Block<const D, Rows, N>(derived(), 0, 0); }
+  template <int N>
+  Block<D, Rows, N> rightCols() { return Block<D, Rows, N>(derived(), 0, Cols - N); }
+  template <int N>
+  Block<const D, Rows, N> rightCols() const { return Block<const D, Rows, N>(derived(), 0, Cols - N); }
+  // x.array() == y.array() ... .all(): only what util/matrix.h's IsNaN / IsInf write
+  struct BoolArray {
+    bool all_;
+    bool all() const { return all_; }
+  };
+  struct ArrayView {
+    Plain v;
+    BoolArray operator==(const ArrayView& o) const {
+      bool a = true;
+      for (int j = 0; j < Cols; ++j)
+        for (int i = 0; i < Rows; ++i) a = a && (v.coeff(i, j) == o.v.coeff(i, j));
+      return BoolArray{a};
+    }
+  };
+  ArrayView array() const { return ArrayView{eval()}; }
   // head<N>() of a column vector
   template <int N>
   Block<D, N, 1> head() { return Block<D, N, 1>(derived(), 0, 0); }
@@ -474,6 +497,9 @@ class EigenSolver {
   const Matrix<std::complex<double>, 8, 1>& eigenvalues() const { return ev_; }
 };
 
+template <class M>
+class HouseholderQR;  // named by an uninstantiated template of util/matrix.h
+
 // ---------------------------------------------------------------------------------------------
 // Geometry stubs: only what the reference's headers name.
 // ---------------------------------------------------------------------------------------------
@@ -485,6 +511,16 @@ class Quaternion {
  public:
   Quaternion() : w_(1), x_(0), y_(0), z_(0) {}
   Quaternion(S w, S x, S y, S z) : w_(w), x_(x), y_(y), z_(z) {}
+  // Quaterniond(Matrix3d): eigen_restated::QuaternionFromRotationMatrix
+  template <class O>
+  explicit Quaternion(const MatrixBase<O>& rot) {
+    static_assert(O::Rows == 3 && O::Cols == 3 && std::is_same<S, double>::value,
+                  "minieigen: quaternion from a 3x3 double matrix");
+    const Matrix<double, 3, 3> r = rot.eval();
+    double q[4];
+    eigen_restated::QuaternionFromRotationMatrix(r.data(), q);
+    w_ = q[0]; x_ = q[1]; y_ = q[2]; z_ = q[3];
+  }
   S w() const { return w_; }
   S x() const { return x_; }
   S y() const { return y_; }

@@ -75,6 +75,10 @@ def lib():
         L.ref_p6l_estimate.restype = C.c_int
         L.ref_ransac_p6l.argtypes = [_dp, _u8p, _dp, C.c_size_t, C.POINTER(RansacOptions),
                                      C.POINTER(RansacReport), _u8p]
+        L.ref_estimate_absolute_pose_from_lines.argtypes = [
+            _dp, _u8p, _dp, C.c_size_t, C.POINTER(RansacOptions), _dp, _dp,
+            C.POINTER(C.c_uint64), _u8p]
+        L.ref_estimate_absolute_pose_from_lines.restype = C.c_int
         _lib = L
     return _lib
 
@@ -162,6 +166,22 @@ def ransac_p6l(lines, aligned, points, options):
     mask = np.zeros(n, dtype=np.uint8)
     lib().ref_ransac_p6l(lp, ap, pp, n, C.byref(options), C.byref(rep), mask.ctypes.data_as(_u8p))
     return rep, mask
+
+
+def estimate_absolute_pose_from_lines(lines, aligned, points, options):
+    """colmap::EstimateAbsolutePoseFromLines (src/estimators/pose.cc:52-94):
+    (ok, qvec, tvec, num_inliers, inlier_mask)."""
+    lines, lp = _d(lines)
+    points, pp = _d(points)
+    aligned, ap = _u8(aligned)
+    n = lines.shape[0]
+    q, t = np.zeros(4), np.zeros(3)
+    ninl = C.c_uint64()
+    mask = np.zeros(n, dtype=np.uint8)
+    ok = lib().ref_estimate_absolute_pose_from_lines(
+        lp, ap, pp, n, C.byref(options), q.ctypes.data_as(_dp), t.ctypes.data_as(_dp),
+        C.byref(ninl), mask.ctypes.data_as(_u8p))
+    return bool(ok), q, t, int(ninl.value), mask
 
 
 # ---------------------------------------------------------------------------------------------

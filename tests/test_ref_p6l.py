@@ -236,6 +236,36 @@ def test_ransac_edge_cases_identical(oracle, ref):
     assert _report_tuple(ro, mo, oracle.prng_peek()) == _report_tuple(rr, mr, ref.prng_peek())
 
 
+def test_estimate_absolute_pose_wrapper_identical(oracle, ref):
+    """colmap::EstimateAbsolutePoseFromLines (src/estimators/pose.cc:52-94) — RANSAC call,
+    rejection of inlier sets that are more than 90 % gravity-aligned, quaternion conversion, NaN
+    check — against the oracle's wrapper (what the C-ABI's ppsfm_estimate_absolute_pose_from_lines
+    is tested against).  Quaterniond(Matrix3d) is the shared restatement of Eigen's algorithm."""
+    opt = oracle.make_options(0.012, 0.25, 0.99999, 3.0, 100, 3000)
+    seen = set()
+    for seed, kw in [(301, dict(n=2000, inlier_ratio=0.4)), (302, dict(n=1200, inlier_ratio=0.6)),
+                     (303, dict(n=600, inlier_ratio=0.03)),            # nothing found
+                     (304, dict(n=1500, inlier_ratio=0.5, aligned_fraction=0.97)),   # mostly aligned
+                     (305, dict(n=900, inlier_ratio=0.5, aligned_fraction=0.0))]:
+        sc = S.make_abs_pose_scene(seed=seed, **kw)
+        oracle.set_prng_seed(0)
+        ref.set_prng_seed(0)
+        ok, q, t, ninl, mask, _ = oracle.estimate_absolute_pose_from_lines(
+            sc["lines"], sc["aligned"], sc["points"], opt)
+        ok2, q2, t2, ninl2, mask2 = ref.estimate_absolute_pose_from_lines(
+            sc["lines"], sc["aligned"], sc["points"], opt)
+        assert (ok, ninl) == (ok2, ninl2), seed
+        assert np.array_equal(mask, mask2), seed
+        if ok2:
+            assert _same_bits(q, q2) and _same_bits(t, t2), seed
+            assert abs(np.linalg.norm(q2) - 1.0) < 1e-9
+        aligned_inliers = int((mask2 & sc["aligned"]).sum())
+        seen.add((ok2, ninl2 > 0, aligned_inliers > 0.9 * ninl2 if ninl2 else None))
+        assert oracle.prng_peek() == ref.prng_peek()
+    # a found pose, the aligned-inlier rejection (inliers but `false`), and a run without a model
+    assert (True, True, False) in seen and (False, True, True) in seen
+
+
 def test_reference_reproduces_the_golden_vectors(ref):
     """tests/golden/oracle_vectors.json was written by the oracle; the reference's own loop gives
     the same trial counts, supports, models, masks and generator states on those scenes, so the
