@@ -10,9 +10,11 @@
 #                    support_measurement.cc}, src/util/random.cc) behind C entry points
 #                    (oracle/ref/ref_p6l.cc), compiled against the Eigen / glog stand-ins of
 #                    oracle/ref/shim/ (both libraries are absent in this image)
-#   libref_tri.so  : the reference's OWN LORANSAC / CombinationSampler / NChooseK sources
-#                    (src/optim/loransac.h, combination_sampler.cc, src/util/math.cc) driving the
-#                    oracle's per-track triangulation estimator (oracle/ref/ref_triangulation.cc)
+#   libref_tri.so  : the reference's OWN robust line triangulation (src/estimators/
+#                    triangulation.cc, src/base/{triangulation,projection,camera}.cc,
+#                    src/optim/{loransac.h,combination_sampler.cc}, src/util/math.cc) behind a C
+#                    entry point (oracle/ref/ref_triangulation.cc); only the n x 4 JacobiSVD is
+#                    the stand-in's (eigen_restated::NullVectorNx4)
 #   libref_ba_setup.so : the reference's OWN bundle-adjustment assembly (src/optim/
 #                    bundle_adjustment.cc + the classes it reads) against a RECORDING ceres::Problem,
 #                    and the product's adaptor on the same colmap::Reconstruction
@@ -45,8 +47,11 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
 echo "built $here/_ref/libref_cost.so"
 
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
-    -I"$here/ref/shim" -I"$ref/src" \
-    "$here/ref/ref_triangulation.cc" "$ref/src/optim/combination_sampler.cc" \
+    -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
+    -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" \
+    "$here/ref/ref_triangulation.cc" "$ref/src/estimators/triangulation.cc" \
+    "$ref/src/base/triangulation.cc" "$ref/src/base/projection.cc" "$ref/src/base/camera.cc" \
+    "$ref/src/base/camera_models.cc" "$ref/src/optim/combination_sampler.cc" \
     "$ref/src/optim/support_measurement.cc" "$ref/src/util/math.cc" \
     -o "$here/_ref/libref_tri.so"
 echo "built $here/_ref/libref_tri.so"

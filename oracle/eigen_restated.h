@@ -7,6 +7,7 @@
 //   * PartialPivLU<Matrix3d>::solve           (absolute_pose.cc:137, re3q3.h:71,75,79)
 //   * EigenSolver<Matrix<double,8,8>>         (re3q3.h:164-165)
 //   * Quaterniond(Matrix3d)                   (base/pose.cc:41-44, used by estimators/pose.cc:86)
+//   * JacobiSVD<Matrix<double,Dynamic,4>>     (base/triangulation.cc:51-53: only matrixV().col(3))
 // Included by ppsfm_oracle.cc (the restatement) AND by the Eigen stand-in under oracle/ref/shim/
 // that lets the reference's own sources compile (oracle/build_ref.sh -> oracle/_ref/libref_p6l.so),
 // so both sides of tests/test_ref_p6l.py share exactly these operations and everything ELSE the
@@ -16,7 +17,9 @@
 #include <algorithm>
 #include <cmath>
 #include <limits>
+#include <cfloat>
 #include <utility>
+#include <vector>
 
 namespace eigen_restated {
 
@@ -383,6 +386,51 @@ inline void QuaternionFromRotationMatrix(const double* R, double* q) {
   q[1] = v[0];
   q[2] = v[1];
   q[3] = v[2];
+}
+
+// The right singular vector of the smallest singular value of an n x 4 matrix W (row-major,
+// overwritten): one-sided Jacobi rotations of the columns until they are orthogonal, then the
+// column of the accumulated V whose W-column is shortest.  (Eigen's JacobiSVD is two-sided with a
+// QR preconditioner: same vector up to rounding and sign; UNPINNED like the rest of this file.)
+inline void NullVectorNx4(std::vector<double>& W, int n, double v[4]) {
+  double V[16];
+  for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    bool rotated = false;
+    for (int p = 0; p < 3; ++p)
+      for (int q = p + 1; q < 4; ++q) {
+        double alpha = 0, beta = 0, gamma = 0;
+        for (int r = 0; r < n; ++r) {
+          alpha += W[4 * r + p] * W[4 * r + p];
+          beta += W[4 * r + q] * W[4 * r + q];
+          gamma += W[4 * r + p] * W[4 * r + q];
+        }
+        if (std::fabs(gamma) <= 1e-300 || std::fabs(gamma) <= 2.3e-16 * std::sqrt(alpha * beta)) continue;
+        rotated = true;
+        const double zeta = (beta - alpha) / (2.0 * gamma);
+        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
+        const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
+        for (int r = 0; r < n; ++r) {
+          const double wp = W[4 * r + p], wq = W[4 * r + q];
+          W[4 * r + p] = c * wp - s * wq;
+          W[4 * r + q] = s * wp + c * wq;
+        }
+        for (int r = 0; r < 4; ++r) {
+          const double vp = V[4 * r + p], vq = V[4 * r + q];
+          V[4 * r + p] = c * vp - s * vq;
+          V[4 * r + q] = s * vp + c * vq;
+        }
+      }
+    if (!rotated) break;
+  }
+  int best = 0;
+  double best_norm = DBL_MAX;
+  for (int j = 0; j < 4; ++j) {
+    double s2 = 0;
+    for (int r = 0; r < n; ++r) s2 += W[4 * r + j] * W[4 * r + j];
+    if (s2 < best_norm) { best_norm = s2; best = j; }
+  }
+  for (int r = 0; r < 4; ++r) v[r] = V[4 * r + best];
 }
 
 }  // namespace eigen_restated

@@ -202,12 +202,50 @@ class MatrixBase {
   }
   void normalize() { *this /= norm(); }
   template <class O>
-  Scalar dot(const MatrixBase<O>& o) const {
-    static_assert(Cols == 1 && O::Cols == 1 && O::Rows == Rows, "minieigen: dot of column vectors");
-    Scalar s = derived().coeff(0, 0) * o.derived().coeff(0, 0);
-    for (int i = 1; i < Rows; ++i) s = s + derived().coeff(i, 0) * o.derived().coeff(i, 0);
+  Scalar dot(const MatrixBase<O>& o) const {  // vectors of either orientation
+    static_assert((Cols == 1 || Rows == 1) && (O::Cols == 1 || O::Rows == 1) &&
+                      Rows * Cols == O::Rows * O::Cols,
+                  "minieigen: dot of two vectors of one length");
+    Scalar s = (*this)(0) * o(0);
+    for (int i = 1; i < Rows * Cols; ++i) s = s + (*this)(i) * o(i);
     return s;
   }
+  // (x, 1) and x / x_last for column vectors
+  Matrix<Scalar, Rows + 1, 1> homogeneous() const {
+    static_assert(Cols == 1, "minieigen: homogeneous() of a column vector");
+    Matrix<Scalar, Rows + 1, 1> r;
+    for (int i = 0; i < Rows; ++i) r.coeffRef(i, 0) = derived().coeff(i, 0);
+    r.coeffRef(Rows, 0) = Scalar(1);
+    return r;
+  }
+  Matrix<Scalar, Rows - 1, 1> hnormalized() const {
+    static_assert(Cols == 1 && Rows > 1, "minieigen: hnormalized() of a column vector");
+    Matrix<Scalar, Rows - 1, 1> r;
+    for (int i = 0; i < Rows - 1; ++i) r.coeffRef(i, 0) = derived().coeff(i, 0) / derived().coeff(Rows - 1, 0);
+    return r;
+  }
+  int rows() const { return Rows; }
+  int cols() const { return Cols; }
+  // Members that only OFF-PATH functions of the compiled reference files name
+  // (DecomposeProjectionMatrix, ComputeClosestRotationMatrix, DecomposeMatrixRQ): they exist so
+  // that those translation units compile, and abort if anything ever runs them.
+  struct OffPathReverse {
+    Plain reverse() const {
+      std::abort();
+      return Plain();
+    }
+  };
+  OffPathReverse rowwise() const { return OffPathReverse(); }
+  OffPathReverse colwise() const { return OffPathReverse(); }
+  struct OffPathTriangular {
+    template <class B>
+    typename B::Plain solve(const MatrixBase<B>&) const {
+      std::abort();
+      return typename B::Plain();
+    }
+  };
+  template <int Mode>
+  OffPathTriangular triangularView() const { return OffPathTriangular(); }
 
   // Matrix3d::determinant()
   Scalar determinant() const {
@@ -308,6 +346,10 @@ class Matrix : public MatrixBase<Matrix<S, R, C, Opt>> {
     for (int i = 0; i < (R < C ? R : C); ++i) m.coeffRef(i, i) = S(1);
     return m;
   }
+
+  // a 1 x 1 product is a scalar (std::acos(a.transpose() * b))
+  template <int RR = R, int CC = C, std::enable_if_t<RR == 1 && CC == 1, int> = 0>
+  operator S() const { return d_[0]; }
 
   const S& coeff(int i, int j) const { return d_[j * R + i]; }
   S& coeffRef(int i, int j) { return d_[j * R + i]; }
@@ -497,8 +539,69 @@ class EigenSolver {
   const Matrix<std::complex<double>, 8, 1>& eigenvalues() const { return ev_; }
 };
 
+enum { Lower = 1, Upper = 2 };
+enum { ComputeFullU = 4, ComputeThinU = 8, ComputeFullV = 16, ComputeThinV = 32 };
+
+// off-path (see MatrixBase): util/matrix.h DecomposeMatrixRQ, projection.cc
 template <class M>
-class HouseholderQR;  // named by an uninstantiated template of util/matrix.h
+class HouseholderQR {
+ public:
+  explicit HouseholderQR(const M&) { std::abort(); }
+  M householderQ() const { return M(); }
+  M matrixQR() const { return M(); }
+};
+template <class M>
+class JacobiSVD {
+ public:
+  JacobiSVD(const M&, unsigned = 0) { std::abort(); }
+  M matrixU() const { return M(); }
+  M matrixV() const { return M(); }
+};
+
+// The ONE dynamically sized matrix of the compiled sources: the n x 4 system of
+// TriangulateMultiViewPoint (src/base/triangulation.cc:41-57) — `A(n, 4)`, `A.row(i) = ...`,
+// `JacobiSVD<decltype(A)> svd(A, ComputeFullV)`, `svd.matrixV().col(3)`.
+template <class S, int Opt>
+class Matrix<S, Dynamic, 4, Opt> {
+  std::vector<S> d_;  // row-major n x 4
+  int rows_;
+
+ public:
+  Matrix(std::size_t rows, int cols) : d_(rows * 4), rows_(static_cast<int>(rows)) {
+    if (cols != 4) std::abort();
+  }
+  int rows() const { return rows_; }
+  int cols() const { return 4; }
+  const std::vector<S>& storage() const { return d_; }
+  struct RowRef {
+    S* p;
+    template <class O>
+    RowRef& operator=(const MatrixBase<O>& o) {
+      static_assert(O::Rows == 1 && O::Cols == 4, "minieigen: a 1 x 4 row");
+      for (int j = 0; j < 4; ++j) p[j] = o.derived().coeff(0, j);
+      return *this;
+    }
+  };
+  RowRef row(int i) { return RowRef{d_.data() + 4 * static_cast<std::size_t>(i)}; }
+};
+// JacobiSVD of that system: only the right singular vector of the smallest singular value is
+// provided (column 3 of matrixV(), the one the reference reads), by the one-sided Jacobi
+// iteration of eigen_restated::NullVectorNx4 — the function the oracle uses.  Eigen's own
+// JacobiSVD (two-sided, QR-preconditioned) gives the same vector up to rounding and sign.
+template <class S, int Opt>
+class JacobiSVD<Matrix<S, Dynamic, 4, Opt>> {
+  Matrix<S, 4, 4> v_;
+
+ public:
+  JacobiSVD(const Matrix<S, Dynamic, 4, Opt>& a, unsigned = 0) {
+    std::vector<double> w(a.storage().begin(), a.storage().end());
+    double x[4];
+    eigen_restated::NullVectorNx4(w, a.rows(), x);
+    v_ = Matrix<S, 4, 4>::Zero();
+    for (int i = 0; i < 4; ++i) v_.coeffRef(i, 3) = x[i];
+  }
+  const Matrix<S, 4, 4>& matrixV() const { return v_; }
+};
 
 // ---------------------------------------------------------------------------------------------
 // Geometry stubs: only what the reference's headers name.

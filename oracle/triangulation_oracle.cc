@@ -12,6 +12,7 @@
 // Eigen::JacobiSVD is replaced by a one-sided Jacobi SVD of the full n x 4 system (parity
 // unpinned at the Eigen boundary; the reference has no test for this path).
 #include "camera_models_ext.h"
+#include "eigen_restated.h"
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -90,45 +91,9 @@ void MultiViewPoint(const std::vector<const double*>& lines, const std::vector<c
     for (int c = 0; c < 4; ++c)
       W[4 * i + c] = lines[i][0] * poses[i]->P[c] + lines[i][1] * poses[i]->P[4 + c] +
                      lines[i][2] * poses[i]->P[8 + c];
-  double V[16];
-  for (int i = 0; i < 16; ++i) V[i] = (i % 5 == 0) ? 1.0 : 0.0;
-  for (int sweep = 0; sweep < 60; ++sweep) {
-    bool rotated = false;
-    for (int p = 0; p < 3; ++p)
-      for (int q = p + 1; q < 4; ++q) {
-        double alpha = 0, beta = 0, gamma = 0;
-        for (int r = 0; r < n; ++r) {
-          alpha += W[4 * r + p] * W[4 * r + p];
-          beta += W[4 * r + q] * W[4 * r + q];
-          gamma += W[4 * r + p] * W[4 * r + q];
-        }
-        if (std::fabs(gamma) <= 1e-300 || std::fabs(gamma) <= 2.3e-16 * std::sqrt(alpha * beta)) continue;
-        rotated = true;
-        const double zeta = (beta - alpha) / (2.0 * gamma);
-        const double t = (zeta >= 0 ? 1.0 : -1.0) / (std::fabs(zeta) + std::sqrt(1.0 + zeta * zeta));
-        const double c = 1.0 / std::sqrt(1.0 + t * t), s = c * t;
-        for (int r = 0; r < n; ++r) {
-          const double wp = W[4 * r + p], wq = W[4 * r + q];
-          W[4 * r + p] = c * wp - s * wq;
-          W[4 * r + q] = s * wp + c * wq;
-        }
-        for (int r = 0; r < 4; ++r) {
-          const double vp = V[4 * r + p], vq = V[4 * r + q];
-          V[4 * r + p] = c * vp - s * vq;
-          V[4 * r + q] = s * vp + c * vq;
-        }
-      }
-    if (!rotated) break;
-  }
-  int best = 0;
-  double best_norm = DBL_MAX;
-  for (int j = 0; j < 4; ++j) {
-    double s2 = 0;
-    for (int r = 0; r < n; ++r) s2 += W[4 * r + j] * W[4 * r + j];
-    if (s2 < best_norm) { best_norm = s2; best = j; }
-  }
-  const double w = V[12 + best];
-  X[0] = V[best] / w; X[1] = V[4 + best] / w; X[2] = V[8 + best] / w;
+  double v[4];
+  eigen_restated::NullVectorNx4(W, n, v);  // JacobiSVD(A, ComputeFullV).matrixV().col(3)
+  X[0] = v[0] / v[3]; X[1] = v[1] / v[3]; X[2] = v[2] / v[3];  // hnormalized()
 }
 
 double TriAngle(const double* c1, const double* c2, const double* X) {

@@ -1,16 +1,21 @@
-"""Robust line triangulation: the oracle's inline restatement of the
-LORANSAC loop against the REFERENCE'S OWN loop sources (CPU).
+"""Robust line triangulation: the oracle against the REFERENCE'S OWN sources
+(CPU).
 
-oracle/build_ref.sh compiles src/optim/loransac.h, src/optim/ransac.h,
+oracle/build_ref.sh compiles src/estimators/triangulation.cc (EstimateTriangulation,
+TriangulationEstimator), src/base/triangulation.cc (TriangulateMultiViewPoint,
+CalculateTriangulationAngle), src/base/projection.cc (CalculateNormalizedLineAngularError,
+CalculateSquaredLineReprojectionError with the in-image test, HasPointPositiveDepth),
+src/base/camera.cc + camera_models.cc, src/optim/loransac.h + ransac.h,
 src/optim/combination_sampler.cc, src/util/math.{h,cc} and src/optim/support_measurement.cc from
-where they lie under /root/reference into oracle/_ref/libref_tri.so, where they drive the oracle's
-per-track estimator (Track::Estimate / Track::Residual of oracle/triangulation_oracle.cc) the way
-EstimateTriangulation (src/estimators/triangulation.cc:117-149) and its caller
-(src/sfm/incremental_triangulator.cc:518-533) drive TriangulationEstimator.  Pinned bit for bit:
-sampling order, support comparison, when the local optimisation runs and wins, the dynamic trial
-bound and abort, the final mask.  The estimator's arithmetic (JacobiSVD, projection.cc) needs more
-of Eigen than the stand-in provides and stays an oracle restatement.  The CUDA kernel is compared
-with the oracle in tests/test_gpu_triangulation.py.
+where they lie under /root/reference into oracle/_ref/libref_tri.so (stand-ins of
+oracle/ref/shim/ for Eigen / glog / Ceres / Boost).  The one piece that is not the reference's
+text is the n x 4 JacobiSVD inside TriangulateMultiViewPoint: the stand-in returns the null vector
+of eigen_restated::NullVectorNx4, the iteration the oracle uses (Eigen's own JacobiSVD gives the
+same vector up to rounding).  Everything else — the residuals of both types, cheirality and
+angle tests, sampling order, support comparison, local optimisation, the dynamic trial bound, the
+final mask — is pinned bit for bit: success flags, points, inlier masks and trial counts of
+oracle/triangulation_oracle.cc equal the reference's.  The CUDA kernel is compared with the oracle
+in tests/test_gpu_triangulation.py.
 
 Skipped where neither oracle/_ref/libref_tri.so nor /root/reference exists."""
 import numpy as np
