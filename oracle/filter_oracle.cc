@@ -7,8 +7,14 @@
 //   ProjectionCenterFromPose / QuaternionToRotationMatrix     src/base/pose.cc:46-62, 94-101
 //   CameraModel::WorldToImage                                 src/base/camera_models.h:615-904
 // The reference's hash-map Reconstruction is replaced by a track-major SoA view (the loops visit a
-// point's track in Track::Elements() order, as here).  Parity unpinned at the Eigen boundary
-// (dot-product association); the reference has no test for these functions.
+// point's track in Track::Elements() order, as here).  The per-observation functions the loops
+// call — CalculateSquaredLineReprojectionError with its cheirality and in-image tests,
+// CalculateTriangulationAngle, WorldToImage — are the restatements pinned bit for bit against the
+// reference's own projection.cc / triangulation.cc / camera_models.h by
+// tests/test_ref_triangulation.py and tests/test_ref_cost.py (same arithmetic as in
+// triangulation_oracle.cc); the LOOPS themselves (reconstruction.cc needs the whole
+// Reconstruction class) follow the reference by reading only, and the reference has no test
+// for them.
 #include "camera_models_ext.h"
 #include <cfloat>
 #include <cmath>

@@ -9,8 +9,12 @@
 //   CombinationSampler, NChooseK, NextCombination     src/optim/combination_sampler.cc:41-70,
 //                                                     src/util/math.cc:36-42, math.h:140-176
 //   RANSAC ctor cap / ComputeNumTrials                src/optim/ransac.h:144-176
-// Eigen::JacobiSVD is replaced by a one-sided Jacobi SVD of the full n x 4 system (parity
-// unpinned at the Eigen boundary; the reference has no test for this path).
+// Eigen::JacobiSVD is replaced by a one-sided Jacobi iteration for the null vector of the n x 4
+// system (eigen_restated.h; parity unpinned at that Eigen boundary).  Everything else is PINNED
+// against the reference's own sources: oracle/build_ref.sh compiles triangulation.cc,
+// base/triangulation.cc, base/projection.cc, camera.cc, loransac.h, combination_sampler.cc and
+// math.cc from /root/reference (oracle/_ref/libref_tri.so) and tests/test_ref_triangulation.py
+// requires success flags, points, inlier masks and trial counts to be bit-identical.
 #include "camera_models_ext.h"
 #include "eigen_restated.h"
 #include <algorithm>
