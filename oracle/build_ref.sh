@@ -38,6 +38,9 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$here/ref/ref_p6l.cc" "$ref/src/estimators/absolute_pose.cc" "$ref/src/estimators/utils.cc" \
     "$ref/src/estimators/pose.cc" "$ref/src/optim/random_sampler.cc" \
     "$ref/src/optim/support_measurement.cc" "$ref/src/util/random.cc" \
+    "$ref/src/base/camera.cc" "$ref/src/base/camera_models.cc" "$ref/src/optim/bundle_adjustment.cc" \
+    "$ref/src/util/misc.cc" "$ref/src/util/string.cc" "$ref/src/util/threading.cc" \
+    "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
     -o "$here/_ref/libref_p6l.so"
 echo "built $here/_ref/libref_p6l.so"
 

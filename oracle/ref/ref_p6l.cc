@@ -7,6 +7,7 @@
 //   src/optim/random_sampler.cc, src/util/random.{h,cc}   sampler + PRNG        (A7)
 //   src/optim/support_measurement.cc  Inlier / MEstimator support               (A8)
 //   src/estimators/pose.cc            EstimateAbsolutePoseFromLines             (A9)
+//                                     RefineAbsolutePoseFromLines: the problem it builds (A10)
 // Eigen and glog are absent in this image: the sources compile against the stand-ins under
 // oracle/ref/shim/ (minieigen.h: the Eigen calls are the restatements of oracle/eigen_restated.h,
 // shared with the oracle; glog/logging.h: CHECK* = print + abort).  So what tests/test_ref_p6l.py
@@ -19,6 +20,7 @@
 #include <random>
 #include <vector>
 
+#include "base/camera.h"
 #include "base/pose.h"
 #include "estimators/absolute_pose.h"
 #include "estimators/pose.h"
@@ -234,4 +236,88 @@ REF_API int ref_estimate_absolute_pose_from_lines(const double* lines, const uin
   std::memset(inlier_mask, 0, n);
   for (size_t i = 0; i < mask.size(); ++i) inlier_mask[i] = mask[i] ? 1 : 0;
   return ok ? 1 : 0;
+}
+
+// colmap::RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213) against the RECORDING
+// ceres::Problem of the stand-in: what the reference hands to Ceres for a pose refinement.
+// out[0] residual blocks, [1] all blocks are (2; 4, 3, 3, k) on the same qvec / tvec / camera
+// pointers, [2] loss kind (2 = Cauchy) and [3] its scale, [4] constant 3-blocks (the points),
+// [5] the residual blocks' points are exactly the inlier points in order, [6] qvec has a 4 -> 3
+// parameterisation, [7] tvec is neither constant nor parameterised, [8] variable mask of the
+// camera parameters, [9] linear solver type (1 = DENSE_QR), [10] gradient_tolerance,
+// [11] max_num_iterations, [12] num_threads, [13..16] qvec after the call (normalised in place).
+REF_API int ref_refine_absolute_pose_setup(const double* lines, const double* points,
+                                           const uint8_t* inlier_mask, size_t n, int camera_model,
+                                           const double* camera_params, int refine_focal_length,
+                                           int refine_extra_params, double gradient_tolerance,
+                                           int max_num_iterations, double loss_scale,
+                                           const double* qvec_in, const double* tvec_in,
+                                           double* out) {
+  colmap::AbsolutePoseRefinementOptions o;
+  o.gradient_tolerance = gradient_tolerance;
+  o.max_num_iterations = max_num_iterations;
+  o.loss_function_scale = loss_scale;
+  o.refine_focal_length = refine_focal_length != 0;
+  o.refine_extra_params = refine_extra_params != 0;
+  o.print_summary = false;
+  colmap::Camera camera;
+  camera.SetModelId(camera_model);
+  camera.SetWidth(1000);
+  camera.SetHeight(1000);
+  camera.SetParams(std::vector<double>(camera_params, camera_params + camera.NumParams()));
+  std::vector<Eigen::Vector3d> l, p;
+  std::vector<char> mask(inlier_mask, inlier_mask + n);
+  for (size_t i = 0; i < n; ++i) {
+    l.emplace_back(lines[3 * i], lines[3 * i + 1], lines[3 * i + 2]);
+    p.emplace_back(points[3 * i], points[3 * i + 1], points[3 * i + 2]);
+  }
+  Eigen::Vector4d q(qvec_in[0], qvec_in[1], qvec_in[2], qvec_in[3]);
+  Eigen::Vector3d t(tvec_in[0], tvec_in[1], tvec_in[2]);
+  const bool usable = colmap::RefineAbsolutePoseFromLines(o, mask, l, p, &q, &t, &camera);
+
+  const ceres::SolveRecord& r = ceres::LastSolveRecord();
+  out[0] = r.num_residual_blocks;
+  bool uniform = true, points_in_order = true;
+  size_t next = 0;
+  for (int b = 0; b < r.num_residual_blocks; ++b) {
+    const auto& sz = r.block_sizes[b];
+    uniform = uniform && sz.size() == 4 && sz[0] == 4 && sz[1] == 3 && sz[2] == 3 &&
+              sz[3] == static_cast<int>(camera.NumParams()) && r.blocks[b][0] == q.data() &&
+              r.blocks[b][1] == t.data() && r.blocks[b][3] == camera.ParamsData() &&
+              r.loss_kind[b] == r.loss_kind[0] && r.loss_scale[b] == r.loss_scale[0];
+    while (next < n && !mask[next]) ++next;
+    // block3_values: tvec (3) then the point (3) (then the camera if it has three parameters)
+    points_in_order = points_in_order && next < n && r.block3_values[b].size() >= 6 &&
+                      r.block3_values[b][3] == p[next](0) && r.block3_values[b][4] == p[next](1) &&
+                      r.block3_values[b][5] == p[next](2);
+    ++next;
+  }
+  out[1] = uniform ? 1 : 0;
+  out[2] = r.num_residual_blocks ? r.loss_kind[0] : -1;
+  out[3] = r.num_residual_blocks ? r.loss_scale[0] : 0.0;
+  int const_points = 0;
+  bool camera_const = false, tvec_touched = false, quat = false;
+  for (const double* c : r.constant_blocks) {
+    if (c == camera.ParamsData()) camera_const = true;
+    else if (c == t.data() || c == q.data()) tvec_touched = true;
+    else ++const_points;
+  }
+  unsigned variable = camera_const ? 0u : (1u << camera.NumParams()) - 1;
+  for (const auto& pr : r.parameterizations) {
+    if (pr.block == q.data()) quat = pr.global_size == 4 && pr.local_size == 3;
+    else if (pr.block == t.data()) tvec_touched = true;
+    else if (pr.block == camera.ParamsData())
+      for (int k : pr.constant) variable &= ~(1u << k);
+  }
+  out[4] = const_points;
+  out[5] = points_in_order ? 1 : 0;
+  out[6] = quat ? 1 : 0;
+  out[7] = tvec_touched ? 0 : 1;
+  out[8] = variable;
+  out[9] = static_cast<int>(r.options.linear_solver_type);
+  out[10] = r.options.gradient_tolerance;
+  out[11] = r.options.max_num_iterations;
+  out[12] = r.options.num_threads;
+  for (int k = 0; k < 4; ++k) out[13 + k] = q(k);
+  return usable ? 1 : 0;
 }

@@ -333,13 +333,56 @@ class Solver {
   };
 };
 
-// what the last ceres::Solve call was handed (one per thread)
-inline Solver::Options& LastSolveOptions() {
-  static thread_local Solver::Options o;
-  return o;
+// what the last ceres::Solve call was handed (one per thread): the options, and a structural
+// snapshot of the problem (some callers build it on their stack: estimators/pose.cc)
+struct SolveRecord {
+  Solver::Options options;
+  int num_residual_blocks = 0;
+  int num_residuals = 0;
+  std::vector<std::vector<int>> block_sizes;        // per residual block
+  std::vector<std::vector<const double*>> blocks;   // per residual block: parameter pointers
+  std::vector<std::vector<double>> block3_values;   // per residual block: values of its 3-vectors
+  std::vector<int> loss_kind;
+  std::vector<double> loss_scale;
+  std::vector<const double*> constant_blocks;
+  struct Param {
+    const double* block;
+    int global_size, local_size;
+    std::vector<int> constant;
+  };
+  std::vector<Param> parameterizations;
+};
+inline SolveRecord& LastSolveRecord() {
+  static thread_local SolveRecord r;
+  return r;
 }
+inline Solver::Options& LastSolveOptions() { return LastSolveRecord().options; }
 inline void Solve(const Solver::Options& options, Problem* problem, Solver::Summary* summary) {
-  LastSolveOptions() = options;
+  SolveRecord& r = LastSolveRecord();
+  r = SolveRecord();
+  r.options = options;
+  r.num_residual_blocks = problem->NumResidualBlocks();
+  r.num_residuals = problem->NumResiduals();
+  for (const auto& rb : problem->residual_blocks) {
+    r.block_sizes.push_back(rb.cost->ParameterBlockSizes());
+    r.blocks.emplace_back(rb.blocks.begin(), rb.blocks.end());
+    std::vector<double> v3;
+    for (size_t b = 0; b < rb.blocks.size(); ++b)
+      if (rb.cost->ParameterBlockSizes()[b] == 3)
+        for (int k = 0; k < 3; ++k) v3.push_back(rb.blocks[b][k]);
+    r.block3_values.push_back(v3);
+    r.loss_kind.push_back(rb.loss ? rb.loss->Kind() : -1);
+    r.loss_scale.push_back(rb.loss ? rb.loss->Scale() : 0.0);
+  }
+  r.constant_blocks.assign(problem->constant_blocks.begin(), problem->constant_blocks.end());
+  for (const auto& p : problem->parameterizations) {
+    SolveRecord::Param q;
+    q.block = p.first;
+    q.global_size = p.second->GlobalSize();
+    q.local_size = p.second->LocalSize();
+    if (p.second->ConstantIndices()) q.constant = *p.second->ConstantIndices();
+    r.parameterizations.push_back(q);
+  }
   summary->num_residuals_reduced = problem->NumResiduals();
 }
 

@@ -79,6 +79,10 @@ def lib():
             _dp, _u8p, _dp, C.c_size_t, C.POINTER(RansacOptions), _dp, _dp,
             C.POINTER(C.c_uint64), _u8p]
         L.ref_estimate_absolute_pose_from_lines.restype = C.c_int
+        L.ref_refine_absolute_pose_setup.argtypes = [
+            _dp, _dp, _u8p, C.c_size_t, C.c_int, _dp, C.c_int, C.c_int, C.c_double, C.c_int,
+            C.c_double, _dp, _dp, _dp]
+        L.ref_refine_absolute_pose_setup.restype = C.c_int
         _lib = L
     return _lib
 
@@ -182,6 +186,32 @@ def estimate_absolute_pose_from_lines(lines, aligned, points, options):
         lp, ap, pp, n, C.byref(options), q.ctypes.data_as(_dp), t.ctypes.data_as(_dp),
         C.byref(ninl), mask.ctypes.data_as(_u8p))
     return bool(ok), q, t, int(ninl.value), mask
+
+
+def refine_absolute_pose_setup(lines, points, mask, model, cam_params, qvec, tvec,
+                               refine_focal_length=False, refine_extra_params=False,
+                               gradient_tolerance=1.0, max_num_iterations=100, loss_scale=1.0):
+    """What colmap::RefineAbsolutePoseFromLines (src/estimators/pose.cc:96-213) hands to Ceres,
+    as recorded by the stand-in ceres::Problem / ceres::Solve.  Returns a dict."""
+    lines, lp = _d(lines)
+    points, pp = _d(points)
+    mask, mp = _u8(mask)
+    cam = np.zeros(12)
+    cam[:len(cam_params)] = cam_params
+    q, qp = _d(qvec)
+    t, tp = _d(tvec)
+    out = np.zeros(17)
+    lib().ref_refine_absolute_pose_setup(lp, pp, mp, lines.shape[0], model,
+                                         cam.ctypes.data_as(_dp), int(refine_focal_length),
+                                         int(refine_extra_params), gradient_tolerance,
+                                         max_num_iterations, loss_scale, qp, tp,
+                                         out.ctypes.data_as(_dp))
+    return dict(residual_blocks=int(out[0]), uniform_blocks=bool(out[1]), loss_kind=int(out[2]),
+                loss_scale=float(out[3]), constant_points=int(out[4]),
+                points_in_inlier_order=bool(out[5]), quaternion_parameterization=bool(out[6]),
+                tvec_free=bool(out[7]), camera_variable_mask=int(out[8]),
+                linear_solver_type=int(out[9]), gradient_tolerance=float(out[10]),
+                max_num_iterations=int(out[11]), num_threads=int(out[12]), qvec=out[13:17].copy())
 
 
 # ---------------------------------------------------------------------------------------------

@@ -237,3 +237,51 @@ def test_python_mirror_assembles_like_the_reference(ref):
         rc, a, _ = ref.ba_setup_compare(scene, config)
         assert rc == 0
         assert _c_hex(a) == _python_assembly_text(scene, config)
+
+
+# ---------------------------------------------------------------------------------------------
+# RefineAbsolutePoseFromLines (row A10): what the reference hands to Ceres, against what
+# ppsfm_refine_absolute_pose_from_lines_ex builds (csrc/ba_host.cu)
+# ---------------------------------------------------------------------------------------------
+def test_pose_refinement_problem_of_the_reference(ref):
+    """src/estimators/pose.cc:96-213 run against the recording ceres::Problem: one (2; 4, 3, 3, k)
+    block per inlier in index order, Cauchy loss of the given scale, every point constant, the
+    quaternion parameterised, the translation free, DENSE_QR on one thread, qvec normalised in
+    place — and the variable intrinsics: none by default, otherwise the focal-length and / or
+    extra-parameter groups, never the principal point.  The library builds the same problem
+    (loss_type 2, point_const all 1, refine_principal_point 0, the group masks of kFocalMask /
+    kExtraMask), which the last assertions tie to its source."""
+    import os
+    import re
+    import test_ref_cost as TC
+    sc = S.make_abs_pose_scene(n=400, inlier_ratio=0.5, seed=41)
+    rng = np.random.default_rng(41)
+    mask = (rng.random(400) < 0.6).astype(np.uint8)
+    q = np.array([0.9, 0.1, -0.3, 0.2]) * 2.5                  # not normalised
+    src = open(os.path.join(TC.ROOT, "privacy_preserving_sfm_b200", "csrc", "ba_host.cu")).read()
+    body = src[src.index("int ppsfm_refine_absolute_pose_from_lines_ex("):]
+    body = body[:body.index("\n}\n")]
+    assert "o.loss_type = 2;" in body and "std::vector<uint8_t> pc(np, 1);" in body
+    assert "refine_principal_point" not in body                # stays at its default 0
+    assert re.search(r"o->refine_principal_point = 0;", src)
+    focal, extra = TC._mask_table("privacy_preserving_sfm_b200/csrc/ba_host.cu", "kFocalMask"), \
+        TC._mask_table("privacy_preserving_sfm_b200/csrc/ba_host.cu", "kExtraMask")
+    for model, params in TC.MODELS.items():
+        for rf, re_ in [(False, False), (True, False), (False, True), (True, True)]:
+            r = ref.refine_absolute_pose_setup(sc["lines"], sc["points"], mask, model, params, q,
+                                               sc["t"], rf, re_, gradient_tolerance=0.5,
+                                               max_num_iterations=37, loss_scale=0.7)
+            assert r["residual_blocks"] == int(mask.sum()) and r["uniform_blocks"]
+            assert r["points_in_inlier_order"] and r["constant_points"] == int(mask.sum())
+            assert (r["loss_kind"], r["loss_scale"]) == (2, 0.7)
+            assert r["quaternion_parameterization"] and r["tvec_free"]
+            assert (r["linear_solver_type"], r["num_threads"]) == (1, 1)       # DENSE_QR
+            assert (r["gradient_tolerance"], r["max_num_iterations"]) == (0.5, 37)
+            assert np.array_equal(r["qvec"], q / np.linalg.norm(q))
+            want = (focal[model] if rf else 0) | (extra[model] if re_ else 0)
+            assert r["camera_variable_mask"] == want, (model, rf, re_)
+    # no inlier: nothing is added, nothing parameterised
+    r = ref.refine_absolute_pose_setup(sc["lines"], sc["points"], np.zeros(400, np.uint8), 1,
+                                       TC.MODELS[1], q, sc["t"])
+    assert r["residual_blocks"] == 0 and not r["quaternion_parameterization"]
+    assert np.array_equal(r["qvec"], q)
