@@ -20,6 +20,10 @@
 #                    and the product's adaptor on the same colmap::Reconstruction
 #                    (oracle/ref/ref_ba_setup.cc); links libppsfm_b200.so for the adaptor's option
 #                    defaults (host-only entry points)
+#   libref_filter.so : the reference's OWN Reconstruction::FilterPoints3D /
+#                    FilterObservationsWithNegativeDepth (src/base/reconstruction.cc and the classes
+#                    it uses) on a reconstruction built through its own Add* members
+#                    (oracle/ref/ref_filter.cc)
 #   libref_cost.so : the reference's OWN line cost functors (src/base/cost_functions.h) and
 #                    camera models (src/base/camera_models.{h,cc}) behind C entry points
 #                    (oracle/ref/ref_cost.cc), against the Ceres / Eigen / glog / Boost stand-ins
@@ -38,7 +42,8 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$here/ref/ref_p6l.cc" "$ref/src/estimators/absolute_pose.cc" "$ref/src/estimators/utils.cc" \
     "$ref/src/estimators/pose.cc" "$ref/src/optim/random_sampler.cc" \
     "$ref/src/optim/support_measurement.cc" "$ref/src/util/random.cc" \
-    "$ref/src/base/camera.cc" "$ref/src/base/camera_models.cc" "$ref/src/optim/bundle_adjustment.cc" \
+    "$ref/src/base/camera.cc" "$ref/src/base/camera_models.cc" "$ref/src/base/pose.cc" \
+    "$ref/src/optim/bundle_adjustment.cc" \
     "$ref/src/util/misc.cc" "$ref/src/util/string.cc" "$ref/src/util/threading.cc" \
     "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
     -o "$here/_ref/libref_p6l.so"
@@ -63,10 +68,24 @@ lib="$here/../privacy_preserving_sfm_b200"
 if [ -f "$lib/libppsfm_b200.so" ]; then
 g++ -O1 -std=c++17 -fPIC -w -shared -fvisibility=hidden -ffunction-sections -fdata-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" -I"$here/../include" -I"$lib/cpp" \
-    "$here/ref/ref_ba_setup.cc" "$ref/src/optim/bundle_adjustment.cc" "$ref/src/base/image.cc" \
+    "$here/ref/ref_ba_setup.cc" "$ref/src/optim/bundle_adjustment.cc" \
+    "$ref/src/base/reconstruction.cc" "$ref/src/base/image.cc" \
     "$ref/src/base/point3d.cc" "$ref/src/base/track.cc" "$ref/src/base/camera.cc" \
-    "$ref/src/base/camera_models.cc" "$ref/src/util/string.cc" "$ref/src/util/misc.cc" \
+    "$ref/src/base/camera_models.cc" "$ref/src/base/pose.cc" "$ref/src/base/projection.cc" \
+    "$ref/src/base/triangulation.cc" "$ref/src/util/math.cc" \
+    "$ref/src/util/string.cc" "$ref/src/util/misc.cc" \
     "$ref/src/util/threading.cc" "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
     -Wl,--gc-sections -L"$lib" -lppsfm_b200 -Wl,-rpath,"$lib" -o "$here/_ref/libref_ba_setup.so"
 echo "built $here/_ref/libref_ba_setup.so"
 fi
+
+g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
+    -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
+    -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" \
+    "$here/ref/ref_filter.cc" "$ref/src/base/reconstruction.cc" "$ref/src/base/image.cc" \
+    "$ref/src/base/point3d.cc" "$ref/src/base/track.cc" "$ref/src/base/camera.cc" \
+    "$ref/src/base/camera_models.cc" "$ref/src/base/pose.cc" "$ref/src/base/projection.cc" \
+    "$ref/src/base/triangulation.cc" "$ref/src/util/math.cc" "$ref/src/util/misc.cc" \
+    "$ref/src/util/string.cc" "$ref/src/util/logging.cc" \
+    -o "$here/_ref/libref_filter.so"
+echo "built $here/_ref/libref_filter.so"

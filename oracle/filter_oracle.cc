@@ -7,14 +7,11 @@
 //   ProjectionCenterFromPose / QuaternionToRotationMatrix     src/base/pose.cc:46-62, 94-101
 //   CameraModel::WorldToImage                                 src/base/camera_models.h:615-904
 // The reference's hash-map Reconstruction is replaced by a track-major SoA view (the loops visit a
-// point's track in Track::Elements() order, as here).  The per-observation functions the loops
-// call — CalculateSquaredLineReprojectionError with its cheirality and in-image tests,
-// CalculateTriangulationAngle, WorldToImage — are the restatements pinned bit for bit against the
-// reference's own projection.cc / triangulation.cc / camera_models.h by
-// tests/test_ref_triangulation.py and tests/test_ref_cost.py (same arithmetic as in
-// triangulation_oracle.cc); the LOOPS themselves (reconstruction.cc needs the whole
-// Reconstruction class) follow the reference by reading only, and the reference has no test
-// for them.
+// point's track in Track::Elements() order, as here).  PINNED against the reference's own
+// sources: oracle/build_ref.sh compiles src/base/reconstruction.cc and the classes it uses into
+// oracle/_ref/libref_filter.so; tests/test_ref_filters.py requires num_filtered, the deleted
+// observations / points and Point3D::Error() to be identical (the projection centres differ in
+// the last bits: Eigen's quaternion-vector product there, -R^T t here).
 #include "camera_models_ext.h"
 #include <cfloat>
 #include <cmath>

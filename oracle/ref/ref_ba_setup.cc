@@ -3,8 +3,9 @@
 //   src/optim/bundle_adjustment.cc   BundleAdjustmentOptions / BundleAdjustmentConfig,
 //                                    BundleAdjuster::Solve -> SetUp -> AddImageToProblem,
 //                                    AddPointToProblem, ParameterizeCameras, ParameterizePoints
-//   src/base/{image,point3d,track,camera,camera_models}.cc, src/util/{string,misc,threading,
-//   timer,logging}.cc                 the classes SetUp reads
+//   src/base/{reconstruction,image,point3d,track,camera,camera_models,pose,projection,
+//   triangulation}.cc, src/util/{string,misc,threading,timer,logging,math}.cc
+//                                    the classes SetUp reads
 // against the stand-ins of oracle/ref/shim/.  ceres::Problem is a RECORDER there (it keeps the
 // residual blocks, constant blocks and parameterisations SetUp creates; ceres::Solve keeps the
 // options and solves nothing), so one call of the reference's BundleAdjuster::Solve yields what
@@ -12,10 +13,11 @@
 // product's adaptor (ppsfm::BundleAdjuster<colmap::Reconstruction>::AssembleOnly, the flat problem
 // of the C-ABI) and both are written out in one canonical form for tests/test_ref_ba_setup.py.
 //
-// Two one-line definitions live in translation units that need too much of Eigen to compile
-// here and are restated below: Reconstruction's default constructor (reconstruction.cc:48-49)
-// and NormalizeQuaternion (pose.cc:53-62).  The Reconstruction is filled through its private
-// maps (its Add* members are in reconstruction.cc too).
+// The colmap::Reconstruction is built through the reference's own AddCamera / AddImage /
+// RegisterImage / AddPoint3D (src/base/reconstruction.cc).  The access hack below opens the
+// reference's classes only to READ what SetUp produced (BundleAdjuster::problem_, the functors'
+// line / pose members); base/database.cc (SQLite) is not built: its one constant that the compiled
+// code names is defined here.
 #include <algorithm>
 #include <array>
 #include <atomic>
@@ -68,6 +70,7 @@
 #undef protected
 
 #include "base/camera_models.h"
+#include "base/database.h"
 #include "base/pose.h"
 
 #ifndef PPSFM_WITH_EIGEN
@@ -75,16 +78,8 @@
 #endif
 #include "ppsfm_adaptor.h"
 
-namespace colmap {
-Reconstruction::Reconstruction() : correspondence_graph_(nullptr), num_added_points3D_(0) {}
-Eigen::Vector4d NormalizeQuaternion(const Eigen::Vector4d& qvec) {
-  const double norm = qvec.norm();
-  if (norm == 0) {
-    return Eigen::Vector4d(1.0, qvec(1), qvec(2), qvec(3));
-  } else {
-    return qvec / norm;
-  }
-}
+namespace colmap {  // database.cc:229-230
+const size_t Database::kMaxNumImages = static_cast<size_t>(std::numeric_limits<int32_t>::max());
 }  // namespace colmap
 
 namespace {
@@ -116,9 +111,8 @@ struct Config {
   int32_t refine_focal_length, refine_principal_point, refine_extra_params, refine_extrinsics;
 };
 
-// ids are index + 1 (0 is never a valid id in the tests; kInvalid* stay out of the way)
-colmap::Reconstruction BuildReconstruction(const Scene& s) {
-  colmap::Reconstruction rec;
+// ids are index + 1 (AddPoint3D hands out 1, 2, ... in the order of the calls)
+void BuildReconstruction(const Scene& s, colmap::Reconstruction* rec) {
   for (int c = 0; c < s.num_cameras; ++c) {
     colmap::Camera cam;
     cam.SetCameraId(c + 1);
@@ -127,36 +121,30 @@ colmap::Reconstruction BuildReconstruction(const Scene& s) {
     cam.SetHeight(1000);
     cam.SetParams(std::vector<double>(s.camera_params + 12 * c,
                                       s.camera_params + 12 * c + cam.NumParams()));
-    rec.cameras_.emplace(cam.CameraId(), cam);
+    rec->AddCamera(cam);
   }
   std::vector<colmap::Track> tracks(s.num_points);
   for (int i = 0; i < s.num_images; ++i) {
     colmap::Image img;
     img.SetImageId(i + 1);
     img.SetCameraId(s.image_camera[i] + 1);
-    img.SetRegistered(true);
     img.Qvec() = Eigen::Vector4d(s.qvecs[4 * i], s.qvecs[4 * i + 1], s.qvecs[4 * i + 2], s.qvecs[4 * i + 3]);
     img.Tvec() = Eigen::Vector3d(s.tvecs[3 * i], s.tvecs[3 * i + 1], s.tvecs[3 * i + 2]);
     colmap::FeatureLines lines;
     for (int64_t k = s.image_line_start[i]; k < s.image_line_start[i + 1]; ++k) {
-      const Eigen::Vector3d l(s.lines[3 * k], s.lines[3 * k + 1], s.lines[3 * k + 2]);
-      if (s.line_point[k] >= 0) {
-        lines.emplace_back(l, false, static_cast<colmap::point3D_t>(s.line_point[k] + 1));
+      lines.emplace_back(Eigen::Vector3d(s.lines[3 * k], s.lines[3 * k + 1], s.lines[3 * k + 2]), false);
+      if (s.line_point[k] >= 0)
         tracks[s.line_point[k]].AddElement(i + 1, static_cast<colmap::point2D_t>(k - s.image_line_start[i]));
-      } else {
-        lines.emplace_back(l, false);
-      }
     }
-    img.lines_ = lines;  // (Image::SetLines also sets up the correspondence counters, unused here)
-    rec.images_.emplace(img.ImageId(), img);
+    img.SetLines(lines);
+    rec->AddImage(img);
+    rec->RegisterImage(i + 1);
   }
   for (int p = 0; p < s.num_points; ++p) {
-    colmap::Point3D pt;
-    pt.SetXYZ(Eigen::Vector3d(s.points[3 * p], s.points[3 * p + 1], s.points[3 * p + 2]));
-    pt.SetTrack(tracks[p]);
-    rec.points3D_.emplace(static_cast<colmap::point3D_t>(p + 1), pt);
+    const colmap::point3D_t id = rec->AddPoint3D(
+        Eigen::Vector3d(s.points[3 * p], s.points[3 * p + 1], s.points[3 * p + 2]), tracks[p]);
+    if (id != static_cast<colmap::point3D_t>(p + 1)) std::abort();
   }
-  return rec;
 }
 
 template <class ConfigT>
@@ -219,7 +207,8 @@ unsigned GroupMask(const std::vector<size_t>& idxs) {
 extern "C" __attribute__((visibility("default"))) int ref_ba_setup_compare(const Scene* scene, const Config* config, char* ref_out,
                                     char* prod_out, size_t cap) {
   // ------------------------------------------------------------------ the reference's SetUp
-  colmap::Reconstruction rec = BuildReconstruction(*scene);
+  colmap::Reconstruction rec;
+  BuildReconstruction(*scene, &rec);
   colmap::BundleAdjustmentOptions opt;
   opt.loss_function_type = static_cast<colmap::BundleAdjustmentOptions::LossFunctionType>(config->loss_type);
   opt.loss_function_scale = config->loss_scale;
@@ -325,7 +314,8 @@ extern "C" __attribute__((visibility("default"))) int ref_ba_setup_compare(const
   }
 
   // ------------------------------------------------------------------ the product's assembly
-  colmap::Reconstruction rec2 = BuildReconstruction(*scene);
+  colmap::Reconstruction rec2;
+  BuildReconstruction(*scene, &rec2);
   ppsfm::BundleAdjustmentOptions popt;
   popt.loss_function_type = static_cast<ppsfm::BundleAdjustmentOptions::LossFunctionType>(config->loss_type);
   popt.loss_function_scale = config->loss_scale;

@@ -7,6 +7,7 @@
 //   src/optim/random_sampler.cc, src/util/random.{h,cc}   sampler + PRNG        (A7)
 //   src/optim/support_measurement.cc  Inlier / MEstimator support               (A8)
 //   src/estimators/pose.cc            EstimateAbsolutePoseFromLines             (A9)
+//   src/base/pose.cc                  RotationMatrixToQuaternion, NormalizeQuaternion
 //                                     RefineAbsolutePoseFromLines: the problem it builds (A10)
 // Eigen and glog are absent in this image: the sources compile against the stand-ins under
 // oracle/ref/shim/ (minieigen.h: the Eigen calls are the restatements of oracle/eigen_restated.h,
@@ -36,24 +37,6 @@ int re3q3(Eigen::Matrix<double, 3, 10> coeffs, Eigen::Matrix<double, 3, 8>* solu
           bool try_random_var_change);
 
 #define REF_API extern "C" __attribute__((visibility("default")))
-
-// base/pose.cc needs more of Eigen than the stand-in has; the two of its functions that
-// estimators/pose.cc calls are restated here (pose.cc:41-44, :53-62).  Quaterniond(Matrix3d) is
-// eigen_restated::QuaternionFromRotationMatrix, the function the oracle uses.
-namespace colmap {
-Eigen::Vector4d RotationMatrixToQuaternion(const Eigen::Matrix3d& rot_mat) {
-  const Eigen::Quaterniond quat(rot_mat);
-  return Eigen::Vector4d(quat.w(), quat.x(), quat.y(), quat.z());
-}
-Eigen::Vector4d NormalizeQuaternion(const Eigen::Vector4d& qvec) {
-  const double norm = qvec.norm();
-  if (norm == 0) {
-    return Eigen::Vector4d(1.0, qvec(1), qvec(2), qvec(3));
-  } else {
-    return qvec / norm;
-  }
-}
-}  // namespace colmap
 
 namespace {
 

@@ -226,6 +226,13 @@ class MatrixBase {
   }
   int rows() const { return Rows; }
   int cols() const { return Cols; }
+  template <class T>
+  Matrix<T, Rows, Cols> cast() const {
+    Matrix<T, Rows, Cols> r;
+    for (int j = 0; j < Cols; ++j)
+      for (int i = 0; i < Rows; ++i) r.coeffRef(i, j) = static_cast<T>(derived().coeff(i, j));
+    return r;
+  }
   // Members that only OFF-PATH functions of the compiled reference files name
   // (DecomposeProjectionMatrix, ComputeClosestRotationMatrix, DecomposeMatrixRQ): they exist so
   // that those translation units compile, and abort if anything ever runs them.
@@ -628,6 +635,30 @@ class Quaternion {
   S x() const { return x_; }
   S y() const { return y_; }
   S z() const { return z_; }
+  // Eigen's quaternion product and rotation of a vector (Quaternion.h: quat_product,
+  // _transformVector: v + w * 2 (u x v) + u x 2 (u x v), u = (x, y, z))
+  Quaternion operator*(const Quaternion& b) const {
+    return Quaternion(w_ * b.w_ - x_ * b.x_ - y_ * b.y_ - z_ * b.z_,
+                      w_ * b.x_ + x_ * b.w_ + y_ * b.z_ - z_ * b.y_,
+                      w_ * b.y_ + y_ * b.w_ + z_ * b.x_ - x_ * b.z_,
+                      w_ * b.z_ + z_ * b.w_ + x_ * b.y_ - y_ * b.x_);
+  }
+  template <class O>
+  Matrix<S, 3, 1> operator*(const MatrixBase<O>& vec) const {
+    static_assert(O::Rows == 3 && O::Cols == 1, "minieigen: quaternion times a 3-vector");
+    const S v0 = vec.derived().coeff(0, 0), v1 = vec.derived().coeff(1, 0), v2 = vec.derived().coeff(2, 0);
+    S u0 = y_ * v2 - z_ * v1, u1 = z_ * v0 - x_ * v2, u2 = x_ * v1 - y_ * v0;
+    u0 = u0 + u0; u1 = u1 + u1; u2 = u2 + u2;
+    Matrix<S, 3, 1> r;
+    r.coeffRef(0, 0) = v0 + w_ * u0 + (y_ * u2 - z_ * u1);
+    r.coeffRef(1, 0) = v1 + w_ * u1 + (z_ * u0 - x_ * u2);
+    r.coeffRef(2, 0) = v2 + w_ * u2 + (x_ * u1 - y_ * u0);
+    return r;
+  }
+  Quaternion slerp(const S&, const Quaternion&) const {  // off-path (InterpolatePose)
+    std::abort();
+    return *this;
+  }
   // re3q3.h:41 draws a random rotation; fixed here: the rotation of the oracle's kVarChangeA
   static Quaternion UnitRandom() {
     Quaternion q;

@@ -21,6 +21,7 @@ LIB_PATH = os.path.join(_HERE, "_ref", "libref_p6l.so")
 COST_LIB_PATH = os.path.join(_HERE, "_ref", "libref_cost.so")
 TRI_LIB_PATH = os.path.join(_HERE, "_ref", "libref_tri.so")
 BA_SETUP_LIB_PATH = os.path.join(_HERE, "_ref", "libref_ba_setup.so")
+FILTER_LIB_PATH = os.path.join(_HERE, "_ref", "libref_filter.so")
 _dp = C.POINTER(C.c_double)
 _u8p = C.POINTER(C.c_uint8)
 _u32p = C.POINTER(C.c_uint32)
@@ -32,6 +33,7 @@ def build(reference_root="/root/reference"):
     srcs = [os.path.join(_HERE, "ref", "ref_p6l.cc"), os.path.join(_HERE, "ref", "ref_cost.cc"),
             os.path.join(_HERE, "ref", "ref_triangulation.cc"),
             os.path.join(_HERE, "ref", "ref_ba_setup.cc"),
+            os.path.join(_HERE, "ref", "ref_filter.cc"),
             os.path.join(_HERE, "..", "privacy_preserving_sfm_b200", "cpp", "ppsfm_adaptor.h"),
             os.path.join(_HERE, "triangulation_oracle.cc"),
             os.path.join(_HERE, "ref", "shim", "minieigen.h"),
@@ -40,12 +42,14 @@ def build(reference_root="/root/reference"):
             os.path.join(_HERE, "eigen_restated.h"), os.path.join(_HERE, "build_ref.sh")]
     fresh = all(os.path.exists(lp) and all(os.path.getmtime(lp) >= os.path.getmtime(s)
                                            for s in srcs)
-                for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH))
+                for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH,
+                           FILTER_LIB_PATH))
     if not fresh and os.path.isdir(os.path.join(reference_root, "src", "estimators")):
         subprocess.check_call(["bash", os.path.join(_HERE, "build_ref.sh")],
                               stdout=subprocess.DEVNULL)
     return all(os.path.exists(lp)
-               for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH))
+               for lp in (LIB_PATH, COST_LIB_PATH, TRI_LIB_PATH, BA_SETUP_LIB_PATH,
+                          FILTER_LIB_PATH))
 
 
 def available():
@@ -424,3 +428,43 @@ def ba_setup_compare(scene, config):
     a, b = C.create_string_buffer(cap), C.create_string_buffer(cap)
     rc = _ba_setup.ref_ba_setup_compare(C.byref(s), C.byref(c), a, b, cap)
     return rc, a.value.decode(), b.value.decode()
+
+
+# ---------------------------------------------------------------------------------------------
+# oracle/_ref/libref_filter.so: the reference's Reconstruction::FilterPoints3D /
+# FilterObservationsWithNegativeDepth on a Reconstruction built through its own Add* members
+# ---------------------------------------------------------------------------------------------
+_filter = None
+
+
+def _filter_lib():
+    global _filter
+    if _filter is None:
+        if not build():
+            raise RuntimeError("oracle/_ref/libref_filter.so is not built (needs /root/reference)")
+        _filter = C.CDLL(FILTER_LIB_PATH)
+        _filter.ref_filter_points3d.argtypes = [C.c_void_p, C.c_double, C.c_double, _u8p, _u8p, _dp,
+                                                C.POINTER(C.c_uint64)]
+        _filter.ref_filter_negative_depth.argtypes = [C.c_void_p, _u8p, _u8p, C.POINTER(C.c_uint64)]
+    return _filter
+
+
+def filter_points3d(problem, max_reproj_error, min_tri_angle):
+    """Same call as oracle.filter_points3d: (num_filtered, obs_deleted, point_deleted, point_error)."""
+    O, P = len(problem.obs_image), len(problem.points)
+    od, pd = np.zeros(max(O, 1), np.uint8), np.zeros(max(P, 1), np.uint8)
+    pe = np.full(max(P, 1), -1.0)
+    nf = C.c_uint64(0)
+    _filter_lib().ref_filter_points3d(C.byref(problem.struct), max_reproj_error, min_tri_angle,
+                                      od.ctypes.data_as(_u8p), pd.ctypes.data_as(_u8p),
+                                      pe.ctypes.data_as(_dp), C.byref(nf))
+    return nf.value, od[:O], pd[:P], pe[:P]
+
+
+def filter_negative_depth(problem):
+    O, P = len(problem.obs_image), len(problem.points)
+    od, pd = np.zeros(max(O, 1), np.uint8), np.zeros(max(P, 1), np.uint8)
+    nf = C.c_uint64(0)
+    _filter_lib().ref_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p),
+                                            pd.ctypes.data_as(_u8p), C.byref(nf))
+    return nf.value, od[:O], pd[:P]
