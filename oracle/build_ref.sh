@@ -32,10 +32,15 @@ here="$(cd "$(dirname "$0")" && pwd)"
 ref="${PPSFM_REFERENCE:-/root/reference}"
 [ -d "$ref/lib/RansacLib/RansacLib" ] || { echo "reference tree not found: $ref"; exit 0; }
 mkdir -p "$here/_ref"
+pids=""   # the libraries are independent: build them side by side
+(
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared \
     -I"$ref/lib/RansacLib" "$here/ref/ref_init.cc" -o "$here/_ref/libref_init.so"
 echo "built $here/_ref/libref_init.so"
+) &
+pids="$pids $!"
 
+(
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" -I"$ref/lib/re3q3" \
@@ -48,12 +53,18 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
     -o "$here/_ref/libref_p6l.so"
 echo "built $here/_ref/libref_p6l.so"
+) &
+pids="$pids $!"
 
+(
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -I"$here/ref/shim" -I"$ref/src" \
     "$here/ref/ref_cost.cc" "$ref/src/base/camera_models.cc" -o "$here/_ref/libref_cost.so"
 echo "built $here/_ref/libref_cost.so"
+) &
+pids="$pids $!"
 
+(
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" \
@@ -63,9 +74,12 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$ref/src/optim/support_measurement.cc" "$ref/src/util/math.cc" \
     -o "$here/_ref/libref_tri.so"
 echo "built $here/_ref/libref_tri.so"
+) &
+pids="$pids $!"
 
 lib="$here/../privacy_preserving_sfm_b200"
 if [ -f "$lib/libppsfm_b200.so" ]; then
+(
 g++ -O1 -std=c++17 -fPIC -w -shared -fvisibility=hidden -ffunction-sections -fdata-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" -I"$here/../include" -I"$lib/cpp" \
     "$here/ref/ref_ba_setup.cc" "$ref/src/optim/bundle_adjustment.cc" \
@@ -77,8 +91,11 @@ g++ -O1 -std=c++17 -fPIC -w -shared -fvisibility=hidden -ffunction-sections -fda
     "$ref/src/util/threading.cc" "$ref/src/util/timer.cc" "$ref/src/util/logging.cc" \
     -Wl,--gc-sections -L"$lib" -lppsfm_b200 -Wl,-rpath,"$lib" -o "$here/_ref/libref_ba_setup.so"
 echo "built $here/_ref/libref_ba_setup.so"
+) &
+pids="$pids $!"
 fi
 
+(
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" \
@@ -89,3 +106,8 @@ g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     "$ref/src/util/string.cc" "$ref/src/util/logging.cc" \
     -o "$here/_ref/libref_filter.so"
 echo "built $here/_ref/libref_filter.so"
+) &
+pids="$pids $!"
+rc=0
+for p in $pids; do wait "$p" || rc=1; done
+exit $rc
