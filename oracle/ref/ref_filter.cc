@@ -124,3 +124,143 @@ extern "C" __attribute__((visibility("default"))) int ref_filter_negative_depth(
   ReadBack(*pb, b, obs_deleted, point_deleted, nullptr);
   return 0;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Text model format: the reference's own Reconstruction::WriteText / ReadText
+// (src/base/reconstruction.cc:543-553, 721-1095) — cameras.txt, images.txt with
+// LINES2D[] as (A, B, C, is_aligned, POINT3D_ID), points3D.txt with TRACK[] as (IMAGE_ID, line_idx).
+// ref_model_write_text builds the reconstruction of a FilterProblem through the reference's own
+// members (optionally runs its FilterPoints3D first, so that lines without a point and deleted
+// points appear) and lets the reference write it; ref_model_read_text lets the reference read a
+// directory and hands the result back as flat arrays sorted by id.
+// ---------------------------------------------------------------------------------------------
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+
+namespace {
+
+struct ReadModel {
+  colmap::Reconstruction rec;
+  std::vector<colmap::camera_t> cams;
+  std::vector<colmap::image_t> imgs;
+  std::vector<colmap::point3D_t> pts;
+  int64_t num_lines = 0, num_track = 0;
+};
+
+void Index(ReadModel* m) {
+  for (const auto& c : m->rec.Cameras()) m->cams.push_back(c.first);
+  for (const auto& i : m->rec.Images()) {
+    m->imgs.push_back(i.first);
+    m->num_lines += static_cast<int64_t>(i.second.Lines().size());
+  }
+  for (const auto& p : m->rec.Points3D()) {
+    m->pts.push_back(p.first);
+    m->num_track += static_cast<int64_t>(p.second.Track().Length());
+  }
+  std::sort(m->cams.begin(), m->cams.end());
+  std::sort(m->imgs.begin(), m->imgs.end());
+  std::sort(m->pts.begin(), m->pts.end());
+}
+
+}  // namespace
+
+extern "C" __attribute__((visibility("default"))) int ref_model_write_text(
+    const FilterProblem* pb, int apply_filter, double max_reproj_error, double min_tri_angle_deg,
+    const char* path) {
+  Built b;
+  Build(*pb, &b);
+  for (int i = 0; i < pb->num_images; ++i) {
+    char name[32];
+    std::snprintf(name, sizeof(name), "image%06d.jpg", i);
+    b.rec.Image(i + 1).SetName(name);
+  }
+  if (apply_filter) {
+    std::unordered_set<colmap::point3D_t> ids;
+    for (const auto id : b.point_id)
+      if (id != 0) ids.insert(id);
+    b.rec.FilterPoints3D(max_reproj_error, min_tri_angle_deg, ids);
+  }
+  b.rec.WriteText(path);
+  return 0;
+}
+
+extern "C" __attribute__((visibility("default"))) void* ref_model_read_text(const char* path) {
+  auto* m = new ReadModel;
+  m->rec.ReadText(path);
+  Index(m);
+  return m;
+}
+
+// the reference writes what it has read: text -> Reconstruction -> text
+extern "C" __attribute__((visibility("default"))) void ref_model_rewrite_text(void* h, const char* path) {
+  static_cast<ReadModel*>(h)->rec.WriteText(path);
+}
+
+extern "C" __attribute__((visibility("default"))) void ref_model_free(void* h) {
+  delete static_cast<ReadModel*>(h);
+}
+
+// sizes: cameras, images, lines (all images), points, track elements (all points), registered images
+extern "C" __attribute__((visibility("default"))) void ref_model_sizes(void* h, int64_t* sizes) {
+  const auto* m = static_cast<ReadModel*>(h);
+  sizes[0] = static_cast<int64_t>(m->cams.size());
+  sizes[1] = static_cast<int64_t>(m->imgs.size());
+  sizes[2] = m->num_lines;
+  sizes[3] = static_cast<int64_t>(m->pts.size());
+  sizes[4] = m->num_track;
+  sizes[5] = static_cast<int64_t>(m->rec.NumRegImages());
+}
+
+extern "C" __attribute__((visibility("default"))) void ref_model_dump(
+    void* h, int64_t* cam_id, int32_t* cam_model, int64_t* cam_size, int32_t* cam_num_params,
+    double* cam_params /* 12 per camera */, int64_t* img_id, double* img_qvec, double* img_tvec,
+    int64_t* img_camera, char* img_name /* 64 per image */, int64_t* line_start /* images + 1 */,
+    double* lines, uint8_t* aligned, int64_t* line_point /* -1: none */, int64_t* pt_id,
+    double* pt_xyz, uint8_t* pt_color, double* pt_error, int64_t* track_start /* points + 1 */,
+    int64_t* track_image, int64_t* track_line) {
+  const auto* m = static_cast<ReadModel*>(h);
+  for (size_t c = 0; c < m->cams.size(); ++c) {
+    const auto& cam = m->rec.Camera(m->cams[c]);
+    cam_id[c] = cam.CameraId();
+    cam_model[c] = cam.ModelId();
+    cam_size[2 * c] = static_cast<int64_t>(cam.Width());
+    cam_size[2 * c + 1] = static_cast<int64_t>(cam.Height());
+    cam_num_params[c] = static_cast<int32_t>(cam.NumParams());
+    for (size_t k = 0; k < cam.NumParams() && k < 12; ++k) cam_params[12 * c + k] = cam.Params()[k];
+  }
+  int64_t l = 0;
+  for (size_t i = 0; i < m->imgs.size(); ++i) {
+    const auto& img = m->rec.Image(m->imgs[i]);
+    img_id[i] = img.ImageId();
+    for (int k = 0; k < 4; ++k) img_qvec[4 * i + k] = img.Qvec(k);
+    for (int k = 0; k < 3; ++k) img_tvec[3 * i + k] = img.Tvec(k);
+    img_camera[i] = img.CameraId();
+    std::strncpy(img_name + 64 * i, img.Name().c_str(), 63);
+    line_start[i] = l;
+    for (const auto& fl : img.Lines()) {
+      for (int k = 0; k < 3; ++k) lines[3 * l + k] = fl.Line()(k);
+      aligned[l] = fl.IsAligned() ? 1 : 0;
+      line_point[l] = fl.HasPoint3D() ? static_cast<int64_t>(fl.Point3DId()) : -1;
+      ++l;
+    }
+  }
+  line_start[m->imgs.size()] = l;
+  int64_t e = 0;
+  for (size_t p = 0; p < m->pts.size(); ++p) {
+    const auto& pt = m->rec.Point3D(m->pts[p]);
+    pt_id[p] = static_cast<int64_t>(m->pts[p]);
+    for (int k = 0; k < 3; ++k) {
+      pt_xyz[3 * p + k] = pt.XYZ()(k);
+      pt_color[3 * p + k] = pt.Color(k);
+    }
+    pt_error[p] = pt.Error();
+    track_start[p] = e;
+    for (const auto& el : pt.Track().Elements()) {
+      track_image[e] = el.image_id;
+      track_line[e] = el.line_idx;
+      ++e;
+    }
+  }
+  track_start[m->pts.size()] = e;
+}

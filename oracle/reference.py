@@ -446,6 +446,13 @@ def _filter_lib():
         _filter.ref_filter_points3d.argtypes = [C.c_void_p, C.c_double, C.c_double, _u8p, _u8p, _dp,
                                                 C.POINTER(C.c_uint64)]
         _filter.ref_filter_negative_depth.argtypes = [C.c_void_p, _u8p, _u8p, C.POINTER(C.c_uint64)]
+        _filter.ref_model_write_text.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double, C.c_char_p]
+        _filter.ref_model_read_text.argtypes = [C.c_char_p]
+        _filter.ref_model_read_text.restype = C.c_void_p
+        _filter.ref_model_rewrite_text.argtypes = [C.c_void_p, C.c_char_p]
+        _filter.ref_model_free.argtypes = [C.c_void_p]
+        _filter.ref_model_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
+        _filter.ref_model_dump.argtypes = [C.c_void_p] * 22
     return _filter
 
 
@@ -468,3 +475,46 @@ def filter_negative_depth(problem):
     _filter_lib().ref_filter_negative_depth(C.byref(problem.struct), od.ctypes.data_as(_u8p),
                                             pd.ctypes.data_as(_u8p), C.byref(nf))
     return nf.value, od[:O], pd[:P]
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's Reconstruction::WriteText / ReadText (text model format, row f3), same library
+# ---------------------------------------------------------------------------------------------
+def model_write_text(problem, path, filter_thresholds=None):
+    """The reference builds the reconstruction of a filters.FilterProblem through its own members
+    (ids = index + 1, names image%06d.jpg), optionally runs its own FilterPoints3D
+    (filter_thresholds = (max_reproj_error, min_tri_angle)), and writes it with WriteText."""
+    os.makedirs(path, exist_ok=True)
+    mx, ang = filter_thresholds if filter_thresholds is not None else (0.0, 0.0)
+    _filter_lib().ref_model_write_text(C.byref(problem.struct), int(filter_thresholds is not None),
+                                       mx, ang, path.encode())
+
+
+def model_read_text(path, rewrite_to=None):
+    """The reference's ReadText on directory ``path``, handed back as a dict of flat arrays sorted
+    by id; ``rewrite_to``: the reference also writes what it has read into that directory."""
+    L = _filter_lib()
+    h = L.ref_model_read_text(path.encode())
+    try:
+        sz = (C.c_int64 * 6)()
+        L.ref_model_sizes(h, sz)
+        nc, ni, nl, npt, nt, nreg = (int(v) for v in sz)
+        m = dict(
+            cam_id=np.zeros(nc, np.int64), cam_model=np.zeros(nc, np.int32),
+            cam_size=np.zeros((nc, 2), np.int64), cam_num_params=np.zeros(nc, np.int32),
+            cam_params=np.zeros((nc, 12)), img_id=np.zeros(ni, np.int64), img_qvec=np.zeros((ni, 4)),
+            img_tvec=np.zeros((ni, 3)), img_camera=np.zeros(ni, np.int64),
+            img_name=np.zeros((ni, 64), np.uint8), line_start=np.zeros(ni + 1, np.int64),
+            lines=np.zeros((nl, 3)), aligned=np.zeros(nl, np.uint8), line_point=np.zeros(nl, np.int64),
+            pt_id=np.zeros(npt, np.int64), pt_xyz=np.zeros((npt, 3)), pt_color=np.zeros((npt, 3), np.uint8),
+            pt_error=np.zeros(npt), track_start=np.zeros(npt + 1, np.int64),
+            track_image=np.zeros(nt, np.int64), track_line=np.zeros(nt, np.int64))
+        L.ref_model_dump(h, *[C.c_void_p(a.ctypes.data) for a in m.values()])
+        m["num_reg_images"] = nreg
+        m["img_name"] = [bytes(r).split(b"\0")[0].decode() for r in m["img_name"]]
+        if rewrite_to is not None:
+            os.makedirs(rewrite_to, exist_ok=True)
+            L.ref_model_rewrite_text(h, rewrite_to.encode())
+    finally:
+        L.ref_model_free(h)
+    return m

@@ -39,6 +39,7 @@ import numpy as np
 from . import bundle_adjustment as ba
 from . import filters as F
 from . import initializer as I
+from . import model_io
 from . import triangulation as T
 from .binding import RANSACOptions
 from .estimators import EstimateAbsolutePoseFromLines
@@ -363,81 +364,51 @@ class IncrementalMapper:
         self.obs_on[img[good], pts[good]] = True
         return int(good.sum())
 
-    # ---- WriteText / ReadText (base/reconstruction.cc:963-1095) -----------------------------------
-    MODEL_NAMES = {0: "SIMPLE_PINHOLE", 1: "PINHOLE", 2: "SIMPLE_RADIAL", 3: "RADIAL", 4: "OPENCV",
-                   5: "OPENCV_FISHEYE", 6: "FULL_OPENCV", 7: "FOV", 8: "SIMPLE_RADIAL_FISHEYE",
-                   9: "RADIAL_FISHEYE", 10: "THIN_PRISM_FISHEYE"}
+    # ---- WriteText / ReadText (base/reconstruction.cc:543-553, 721-1095; model_io.py) -------------
+    def to_model(self):
+        """The reconstruction as model_io.Model: image ids are index + 1, the lines of an image are
+        its visible tracks in point order, point ids are point index + 1."""
+        sc = self.scene
+        nparams = model_io.CAMERA_MODEL_NUM_PARAMS[sc.camera_model]
+        cams = {1: model_io.Camera(sc.camera_model, sc.camera_size[0], sc.camera_size[1],
+                                   sc.camera_params[:nparams])}
+        reg = sorted(self.registered)
+        images = {}
+        for i in reg:
+            vis = np.flatnonzero(sc.visible[i])
+            has = self.obs_on[i, vis] & self.has_point[vis]
+            images[i + 1] = model_io.Image(self.qvec[i], self.tvec[i], 1, "image%06d.jpg" % i,
+                                           sc.lines[i, vis], sc.aligned[vis],
+                                           np.where(has, vis + 1, -1))
+        row = {i: k for k, i in enumerate(reg)}                  # rank of a point among an image's lines
+        line_idx = np.cumsum(sc.visible[reg], axis=1, dtype=np.int32) - 1
+        points = {}
+        for p in np.flatnonzero(self.has_point):
+            imgs = np.array([i for i in reg if self.obs_on[i, p]], np.int64)
+            points[int(p) + 1] = model_io.Point3D(self.points[p],
+                                                  np.stack([imgs + 1, line_idx[[row[i] for i in imgs], p]], 1))
+        return model_io.Model(cams, images, points)
 
     def write_text(self, path):
         """cameras.txt, images.txt (LINES2D[] as (A, B, C, is_aligned, POINT3D_ID)) and
-        points3D.txt (TRACK[] as (IMAGE_ID, line_idx)) with 17 significant digits.  Image ids are
-        index + 1, the lines of an image are its visible tracks in point order, point ids are
-        point index + 1."""
-        sc = self.scene
-        os.makedirs(path, exist_ok=True)
-        nparams = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4, 9: 5, 10: 12}[sc.camera_model]
-        with open(os.path.join(path, "cameras.txt"), "w") as f:
-            f.write("# Camera list with one line of data per camera:\n")
-            f.write("#   CAMERA_ID, MODEL, WIDTH, HEIGHT, PARAMS[]\n# Number of cameras: 1\n")
-            f.write("1 %s %d %d %s\n" % (self.MODEL_NAMES[sc.camera_model], sc.camera_size[0],
-                                         sc.camera_size[1],
-                                         " ".join(repr(float(x)) for x in sc.camera_params[:nparams])))
-        line_idx = {}
-        with open(os.path.join(path, "images.txt"), "w") as f:
-            f.write("# Image list with two lines of data per image:\n")
-            f.write("#   IMAGE_ID, QW, QX, QY, QZ, TX, TY, TZ, CAMERA_ID, NAME\n")
-            f.write("#   LINES2D[] as (A, B, C, is_aligned, POINT3D_ID)\n")
-            f.write("# Number of images: %d\n" % len(self.registered))
-            for i in sorted(self.registered):
-                q = self.qvec[i] / np.linalg.norm(self.qvec[i])
-                f.write("%d %s %s 1 image%06d.jpg\n" % (
-                    i + 1, " ".join(repr(float(x)) for x in q),
-                    " ".join(repr(float(x)) for x in self.tvec[i]), i))
-                vis = np.flatnonzero(sc.visible[i])
-                parts = []
-                for k, p in enumerate(vis):
-                    line_idx[(i, int(p))] = k
-                    has = self.obs_on[i, p] and self.has_point[p]
-                    a, b, c = sc.lines[i, p]
-                    parts.append("%r %r %r %d %d" % (float(a), float(b), float(c),
-                                                     1 if sc.aligned[p] else 0, p + 1 if has else -1))
-                f.write(" ".join(parts) + "\n")
-        reg = set(self.registered)
-        with open(os.path.join(path, "points3D.txt"), "w") as f:
-            f.write("# 3D point list with one line of data per point:\n")
-            f.write("#   POINT3D_ID, X, Y, Z, R, G, B, ERROR, TRACK[] as (IMAGE_ID, line_idx)\n")
-            f.write("# Number of points: %d\n" % int(self.has_point.sum()))
-            for p in np.flatnonzero(self.has_point):
-                imgs = [i for i in np.flatnonzero(self.obs_on[:, p]) if int(i) in reg]
-                track = " ".join("%d %d" % (i + 1, line_idx[(int(i), int(p))]) for i in imgs)
-                x, y, z = self.points[p]
-                f.write("%d %r %r %r 0 0 0 -1 %s\n" % (p + 1, float(x), float(y), float(z), track))
+        points3D.txt (TRACK[] as (IMAGE_ID, line_idx)) in the record layout of the reference's
+        WriteText, with 17 significant digits everywhere (the reference itself keeps six digits of
+        poses, lines and camera parameters: model_io.write_model_text)."""
+        model_io.write_model_text(path, self.to_model(), reference_precision=False)
 
     @staticmethod
     def read_text(path):
-        """Reads the three files back: dict(cameras {id: (model, w, h, params)}, images {id:
-        (qvec, tvec, camera_id, name, lines [n, 5])}, points {id: (xyz, error, track [m, 2])})."""
-        cams, images, points = {}, {}, {}
-        with open(os.path.join(path, "cameras.txt")) as f:
-            for ln in f:
-                if ln.startswith("#") or not ln.strip():
-                    continue
-                t = ln.split()
-                cams[int(t[0])] = (t[1], int(t[2]), int(t[3]), np.array(t[4:], np.float64))
-        with open(os.path.join(path, "images.txt")) as f:
-            rows = [ln for ln in f if not ln.startswith("#")]
-        for k in range(0, len(rows) - 1, 2):
-            t = rows[k].split()
-            vals = np.array(rows[k + 1].split(), np.float64).reshape(-1, 5)
-            images[int(t[0])] = (np.array(t[1:5], np.float64), np.array(t[5:8], np.float64),
-                                 int(t[8]), t[9], vals)
-        with open(os.path.join(path, "points3D.txt")) as f:
-            for ln in f:
-                if ln.startswith("#") or not ln.strip():
-                    continue
-                t = ln.split()
-                points[int(t[0])] = (np.array(t[1:4], np.float64), float(t[7]),
-                                     np.array(t[8:], np.int64).reshape(-1, 2))
+        """Reads the three files back WITHOUT the float narrowing of the reference's reader
+        (model_io.read_model_text(path, reference_precision=False)): dict(cameras {id: (model, w,
+        h, params)}, images {id: (qvec, tvec, camera_id, name, lines [n, 5])}, points {id: (xyz,
+        error, track [m, 2])})."""
+        m = model_io.read_model_text(path, reference_precision=False)
+        cams = {c: (cam.model_name, cam.width, cam.height, cam.params) for c, cam in m.cameras.items()}
+        images = {i: (im.qvec, im.tvec, im.camera_id, im.name,
+                      np.column_stack([im.lines, im.aligned.astype(np.float64),
+                                       im.point3D_ids.astype(np.float64)]).reshape(-1, 5))
+                  for i, im in m.images.items()}
+        points = {p: (pt.xyz, pt.error, pt.track) for p, pt in m.points3D.items()}
         return dict(cameras=cams, images=images, points=points)
 
     # ---- the loop (controllers/incremental_mapper.cc:438-591) -------------------------------------

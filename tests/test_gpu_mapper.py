@@ -5,6 +5,7 @@ import numpy as np
 import pytest
 
 from privacy_preserving_sfm_b200 import mapper as M
+from privacy_preserving_sfm_b200 import model_io
 
 pytestmark = pytest.mark.gpu
 
@@ -58,7 +59,7 @@ def test_mapper_controller_schedule_with_local_ba(ctx, tmp_path):
     assert len(model["points"]) == int(m.has_point.sum())
     for img_id, (q, t, cam_id, name, lines) in model["images"].items():
         i = img_id - 1
-        assert np.array_equal(q, m.qvec[i] / np.linalg.norm(m.qvec[i])) and np.array_equal(t, m.tvec[i])
+        assert np.array_equal(q, model_io.normalize_quaternion(m.qvec[i])) and np.array_equal(t, m.tvec[i])
         vis = np.flatnonzero(scene.visible[i])
         assert np.array_equal(lines[:, :3], scene.lines[i, vis])          # 17 digits: exact
         has = m.obs_on[i, vis] & m.has_point[vis]
