@@ -22,8 +22,10 @@
 #                    defaults (host-only entry points)
 #   libref_filter.so : the reference's OWN Reconstruction::FilterPoints3D /
 #                    FilterObservationsWithNegativeDepth (src/base/reconstruction.cc and the classes
-#                    it uses) on a reconstruction built through its own Add* members
-#                    (oracle/ref/ref_filter.cc)
+#                    it uses) on a reconstruction built through its own Add* members, its
+#                    ReadText / WriteText (text model format) (oracle/ref/ref_filter.cc), and
+#                    the reference's CorrespondenceGraph (src/base/correspondence_graph.cc,
+#                    oracle/ref/ref_corr_graph.cc)
 #   libref_cost.so : the reference's OWN line cost functors (src/base/cost_functions.h) and
 #                    camera models (src/base/camera_models.{h,cc}) behind C entry points
 #                    (oracle/ref/ref_cost.cc), against the Ceres / Eigen / glog / Boost stand-ins
@@ -99,7 +101,8 @@ fi
 g++ -O2 -std=c++17 -fPIC -ffp-contract=off -fno-fast-math -shared -w \
     -fvisibility=hidden -ffunction-sections -fdata-sections -Wl,--gc-sections \
     -I"$here/ref/shim" -I"$ref/src" -I"$ref/lib" \
-    "$here/ref/ref_filter.cc" "$ref/src/base/reconstruction.cc" "$ref/src/base/image.cc" \
+    "$here/ref/ref_filter.cc" "$here/ref/ref_corr_graph.cc" \
+    "$ref/src/base/reconstruction.cc" "$ref/src/base/correspondence_graph.cc" "$ref/src/base/image.cc" \
     "$ref/src/base/point3d.cc" "$ref/src/base/track.cc" "$ref/src/base/camera.cc" \
     "$ref/src/base/camera_models.cc" "$ref/src/base/pose.cc" "$ref/src/base/projection.cc" \
     "$ref/src/base/triangulation.cc" "$ref/src/util/math.cc" "$ref/src/util/misc.cc" \

@@ -34,6 +34,7 @@ def build(reference_root="/root/reference"):
             os.path.join(_HERE, "ref", "ref_triangulation.cc"),
             os.path.join(_HERE, "ref", "ref_ba_setup.cc"),
             os.path.join(_HERE, "ref", "ref_filter.cc"),
+            os.path.join(_HERE, "ref", "ref_corr_graph.cc"),
             os.path.join(_HERE, "..", "privacy_preserving_sfm_b200", "cpp", "ppsfm_adaptor.h"),
             os.path.join(_HERE, "triangulation_oracle.cc"),
             os.path.join(_HERE, "ref", "shim", "minieigen.h"),
@@ -518,3 +519,111 @@ def model_read_text(path, rewrite_to=None):
     finally:
         L.ref_model_free(h)
     return m
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's CorrespondenceGraph (src/base/correspondence_graph.cc), same library
+# ---------------------------------------------------------------------------------------------
+class CorrespondenceGraph:
+    """The reference's own class behind the member names of
+    privacy_preserving_sfm_b200.correspondence_graph.CorrespondenceGraph."""
+
+    def __init__(self):
+        L = self._L = _filter_lib()
+        if not getattr(L, "_cg_declared", False):
+            u32, u64 = C.c_uint32, C.c_uint64
+            L.ref_cg_new.restype = C.c_void_p
+            L.ref_cg_free.argtypes = [C.c_void_p]
+            L.ref_cg_add_image.argtypes = [C.c_void_p, u32, u64]
+            L.ref_cg_add_correspondences.argtypes = [C.c_void_p, u32, u32, C.c_void_p, u64]
+            L.ref_cg_finalize.argtypes = [C.c_void_p]
+            L.ref_cg_sizes.argtypes = [C.c_void_p, C.POINTER(u64)]
+            L.ref_cg_image.argtypes = [C.c_void_p, u32, C.POINTER(u64)]
+            L.ref_cg_num_between.argtypes = [C.c_void_p, u32, u32]
+            L.ref_cg_num_between.restype = u64
+            L.ref_cg_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, u64]
+            L.ref_cg_pairs.restype = u64
+            L.ref_cg_find.argtypes = [C.c_void_p, u32, u32, u64, C.c_void_p, u64]
+            L.ref_cg_find.restype = u64
+            L.ref_cg_between.argtypes = [C.c_void_p, u32, u32, C.c_void_p, u64]
+            L.ref_cg_between.restype = u64
+            L.ref_cg_line.argtypes = [C.c_void_p, u32, u32, C.POINTER(u64)]
+            L._cg_declared = True
+        self._h = L.ref_cg_new()
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ref_cg_free(self._h)
+            self._h = None
+
+    def AddImage(self, image_id, num_lines):
+        self._L.ref_cg_add_image(self._h, image_id, num_lines)
+
+    def AddCorrespondences(self, image_id1, image_id2, matches):
+        m = np.ascontiguousarray(matches, np.uint32).reshape(-1, 2)
+        self._L.ref_cg_add_correspondences(self._h, image_id1, image_id2, m.ctypes.data, len(m))
+
+    def Finalize(self):
+        self._L.ref_cg_finalize(self._h)
+
+    def _sizes(self):
+        out = (C.c_uint64 * 2)()
+        self._L.ref_cg_sizes(self._h, out)
+        return int(out[0]), int(out[1])
+
+    def NumImages(self):
+        return self._sizes()[0]
+
+    def NumImagePairs(self):
+        return self._sizes()[1]
+
+    def _image(self, image_id):
+        out = (C.c_uint64 * 3)()
+        self._L.ref_cg_image(self._h, image_id, out)
+        return [int(v) for v in out]
+
+    def ExistsImage(self, image_id):
+        return bool(self._image(image_id)[0])
+
+    def NumObservationsForImage(self, image_id):
+        return self._image(image_id)[1]
+
+    def NumCorrespondencesForImage(self, image_id):
+        return self._image(image_id)[2]
+
+    def NumCorrespondencesBetweenImages(self, image_id1=None, image_id2=None):
+        if image_id1 is not None:
+            return int(self._L.ref_cg_num_between(self._h, image_id1, image_id2))
+        n = self.NumImagePairs()
+        ids, num = np.zeros(max(n, 1), np.uint64), np.zeros(max(n, 1), np.uint32)
+        self._L.ref_cg_pairs(self._h, ids.ctypes.data, num.ctypes.data, n)
+        return {int(i): int(c) for i, c in zip(ids[:n], num[:n])}
+
+    def FindTransitiveCorrespondences(self, image_id, line_idx, transitivity):
+        cap = 4096
+        while True:
+            out = np.zeros((cap, 2), np.uint32)
+            n = int(self._L.ref_cg_find(self._h, image_id, line_idx, transitivity, out.ctypes.data, cap))
+            if n <= cap:
+                return [tuple(r) for r in out[:n].tolist()]
+            cap = n
+
+    def FindCorrespondences(self, image_id, line_idx):
+        return self.FindTransitiveCorrespondences(image_id, line_idx, 1)
+
+    def FindCorrespondencesBetweenImages(self, image_id1, image_id2):
+        cap = max(1, self.NumCorrespondencesBetweenImages(image_id1, image_id2))
+        out = np.zeros((cap, 2), np.uint32)
+        n = int(self._L.ref_cg_between(self._h, image_id1, image_id2, out.ctypes.data, cap))
+        return [tuple(r) for r in out[:n].tolist()]
+
+    def _line(self, image_id, line_idx):
+        out = (C.c_uint64 * 2)()
+        self._L.ref_cg_line(self._h, image_id, line_idx, out)
+        return bool(out[0]), bool(out[1])
+
+    def HasCorrespondences(self, image_id, line_idx):
+        return self._line(image_id, line_idx)[0]
+
+    def IsTwoViewObservation(self, image_id, line_idx):
+        return self._line(image_id, line_idx)[1]

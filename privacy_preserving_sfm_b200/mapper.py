@@ -60,6 +60,29 @@ class Scene:
         self.mean_focal = float(np.mean(camera_params[:2] if camera_model in (1, 4, 5, 6, 7, 10)
                                         else camera_params[:1]))
 
+    @classmethod
+    def from_correspondence_graph(cls, graph, image_lines, image_aligned, gravity, camera_model,
+                                  camera_params, camera_size, min_track_length=2):
+        """The scene of a matched image set: ``graph`` is a correspondence_graph.CorrespondenceGraph
+        over image ids index + 1 (what ``CorrespondenceGraph`` holds after the database's matches
+        were added, controllers/incremental_mapper.cc:424-436 / base/database_cache.cc),
+        ``image_lines[i]`` [n_i, 3] and ``image_aligned[i]`` [n_i] the lifted lines of image i.
+        Tracks are the connected components of the graph (``graph.Tracks``); a component with two
+        lines of one image is ambiguous and left out, a track must be aligned in all of its views
+        or in none (one flag per track in this driver).  Returns (scene, tracks)."""
+        tracks = [t for t in graph.Tracks(min_track_length)
+                  if len({image_id for image_id, _ in t}) == len(t)]
+        lines = np.full((len(image_lines), len(tracks), 3), np.nan)
+        aligned = np.zeros(len(tracks), bool)
+        for k, t in enumerate(tracks):
+            flags = [bool(image_aligned[image_id - 1][line_idx]) for image_id, line_idx in t]
+            if any(flags) != all(flags):
+                raise ValueError("track %d mixes gravity-aligned and free lines" % k)
+            aligned[k] = flags[0]
+            for image_id, line_idx in t:
+                lines[image_id - 1, k] = image_lines[image_id - 1][line_idx]
+        return cls(lines, aligned, gravity, camera_model, camera_params, camera_size), tracks
+
 
 class IncrementalMapper:
     def __init__(self, ctx, scene, max_reproj_error_px=12.0, filter_max_reproj_error=4.0,
