@@ -110,6 +110,13 @@ void ref_world_to_image(int model, const double* params, double u, double v, dou
                                   u, v, &xy[0], &xy[1]);
 }
 
+// CameraModelImageToWorld (src/base/camera_models.cc) on n pixels: xy [n, 2] -> uv [n, 2]
+void ref_image_to_world(int model, const double* params, int n, const double* xy, double* uv) {
+  const std::vector<double> p(params, params + ref_camera_num_params(model));
+  for (int i = 0; i < n; ++i)
+    colmap::CameraModelImageToWorld(model, p, xy[2 * i], xy[2 * i + 1], &uv[2 * i], &uv[2 * i + 1]);
+}
+
 double ref_image_to_world_threshold(int model, const double* params, double threshold) {
   return colmap::CameraModelImageToWorldThreshold(
       model, std::vector<double>(params, params + ref_camera_num_params(model)), threshold);

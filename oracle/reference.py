@@ -236,6 +236,7 @@ def cost_lib():
         L.ref_camera_param_idxs.argtypes = [C.c_int, C.c_int, _ip]
         L.ref_world_to_image.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp]
         L.ref_image_to_world_threshold.argtypes = [C.c_int, _dp, C.c_double]
+        L.ref_image_to_world.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp]
         L.ref_image_to_world_threshold.restype = C.c_double
         L.ref_line_cost.argtypes = [C.c_int] + [_dp] * 10
         L.ref_constant_pose_line_cost.argtypes = [C.c_int] + [_dp] * 8
@@ -259,6 +260,15 @@ def world_to_image(model, params, u, v):
     xy = np.zeros(2)
     cost_lib().ref_world_to_image(model, pp, u, v, xy.ctypes.data_as(_dp))
     return xy
+
+
+def image_to_world(model, params, xy):
+    """The reference's CameraModelImageToWorld on pixels [n, 2]."""
+    params, pp = _d(params)
+    xy = np.ascontiguousarray(xy, np.float64).reshape(-1, 2)
+    uv = np.zeros_like(xy)
+    cost_lib().ref_image_to_world(model, pp, len(xy), xy.ctypes.data_as(_dp), uv.ctypes.data_as(_dp))
+    return uv
 
 
 def image_to_world_threshold(model, params, threshold):
