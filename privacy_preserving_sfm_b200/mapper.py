@@ -483,6 +483,98 @@ class IncrementalMapper:
         return True
 
 
+_COMBOS3 = {}
+
+
+def _combos3(c):
+    """All 3-subsets of range(c) in the order of the reference's i < j < k loops."""
+    if c not in _COMBOS3:
+        i, j, k = np.meshgrid(np.arange(c), np.arange(c), np.arange(c), indexing="ij")
+        keep = (i < j) & (j < k)
+        _COMBOS3[c] = np.stack([i[keep], j[keep], k[keep]], 1)
+    return _COMBOS3[c]
+
+
+def find_initial_image_sets(graph, image_aligned, check_image_ids, min_num_aligned_tracks=20,
+                            min_num_random_tracks=20):
+    """The candidate search of ``IncrementalMapper::RegisterInitialLineImages``
+    (src/sfm/incremental_mapper.cc:192-421) on a correspondence_graph.CorrespondenceGraph
+    (image ids index + 1, ``image_aligned[i]`` the is_aligned flags of image i's lines).
+
+    For every line of every check image (the reference draws up to ten of them at random,
+    :296-306: here they are an argument) its correspondences of the SAME alignment are taken; with
+    three or more of them every 3-subset plus the line itself is a four-view track, keyed by its
+    image set (ids ascending) and stored once (:253-283, :336-358).  An image set qualifies with at
+    least 20 aligned and 20 unaligned tracks (:398-412); the qualifying sets are returned by
+    descending number of aligned tracks (:421-426: the unaligned weight is zero; ties, which
+    ``std::sort`` leaves unspecified, in ascending image-set order).
+
+    Returns [dict(image_set (4 ids), aligned_tracks [na, 4], unaligned_tracks [nu, 4])]: line
+    indices per image of the set, rows in lexicographic order (the order of the reference's
+    ``std::set``) — aligned rows then unaligned rows are the ``lines`` the reference hands to
+    ``init::initialize_reconstruction`` (:459-481)."""
+    rows = []
+    for image_id in check_image_ids:
+        flags = np.asarray(image_aligned[image_id - 1], bool)
+        for line_idx in range(len(flags)):
+            di, dl = graph._corrs(image_id, line_idx)
+            if len(di) < 3:
+                continue
+            same = np.array([bool(image_aligned[int(i) - 1][int(l)]) for i, l in zip(di, dl)]) == flags[line_idx]
+            di, dl = di[same], dl[same]
+            if len(di) < 3:
+                continue
+            c3 = _combos3(len(di))
+            img = np.concatenate([np.full((len(c3), 1), image_id, np.int64), di[c3]], 1)
+            idx = np.concatenate([np.full((len(c3), 1), line_idx, np.int64), dl[c3]], 1)
+            order = np.argsort(img, axis=1, kind="stable")
+            img, idx = np.take_along_axis(img, order, 1), np.take_along_axis(idx, order, 1)
+            distinct = (np.diff(img, axis=1) > 0).all(axis=1)          # track_candidate.size() == 4
+            al = np.full((int(distinct.sum()), 1), int(flags[line_idx]), np.int64)
+            rows.append(np.concatenate([al, img[distinct], idx[distinct]], 1))
+    if not rows:
+        return []
+    rows = np.unique(np.concatenate(rows), axis=0)                      # std::set: every track once
+    sets, start, count = np.unique(rows[:, :5], axis=0, return_index=True, return_counts=True)
+    by_set = {}
+    for key, s, c in zip(sets, start, count):
+        by_set.setdefault(tuple(int(v) for v in key[1:]), {})[int(key[0])] = rows[s:s + c, 5:]
+    out = []
+    for image_set in sorted(by_set):
+        tracks = by_set[image_set]
+        if len(tracks.get(1, ())) >= min_num_aligned_tracks and len(tracks.get(0, ())) >= min_num_random_tracks:
+            out.append(dict(image_set=image_set, aligned_tracks=tracks[1], unaligned_tracks=tracks[0]))
+    out.sort(key=lambda d: -len(d["aligned_tracks"]))                  # stable
+    return out
+
+
+def select_initial_images(graph, image_lines, image_aligned, gravity, check_image_ids, options=None,
+                          init_min_num_inliers=0, max_num_init_tries=10, ctx=None):
+    """The selection loop of ``RegisterInitialLineImages`` (:428-541): the first ten candidate sets
+    go through ``init::initialize_reconstruction`` (models scored on the GPU of ``ctx`` if given,
+    else the library's host estimators), the one with the best inlier ratio wins; fails without a
+    success or with fewer than ``init_min_num_inliers`` inliers (:536-539).
+
+    Returns (ok, image_set, poses [4, 3, 4], inlier_ratio, tried [(image_set, ok, ratio)])."""
+    best = (False, None, None, 0.0)
+    best_inliers, tried = 0, []
+    for cand in find_initial_image_sets(graph, image_aligned, check_image_ids)[:max_num_init_tries]:
+        ids = cand["image_set"]
+        tracks = np.concatenate([cand["aligned_tracks"], cand["unaligned_tracks"]])
+        lines = np.stack([np.asarray(image_lines[i - 1], np.float64)[tracks[:, k]] for k, i in enumerate(ids)])
+        aligned = np.zeros((4, len(tracks)), np.uint8)
+        aligned[:, :len(cand["aligned_tracks"])] = 1
+        ok, poses, ratio, _ = I.initialize_reconstruction(
+            lines, aligned, np.asarray(gravity, np.float64)[[i - 1 for i in ids]], options, ctx=ctx)
+        tried.append((ids, bool(ok), float(ratio)))
+        if ok and ratio > best[3]:
+            best = (True, ids, poses, float(ratio))
+            best_inliers = int(ratio * len(tracks))
+    if not best[0] or best_inliers < init_min_num_inliers:
+        return False, None, None, 0.0, tried
+    return best + (tried,)
+
+
 def _rotmat_to_quat(R):
     from .synthetic import rotmat_to_quat
     q = rotmat_to_quat(np.asarray(R))

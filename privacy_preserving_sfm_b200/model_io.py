@@ -312,3 +312,15 @@ def read_model_text(path, reference_precision=True):
         points[int(t[0])] = Point3D([num(x) for x in t[1:4]], track, num(t[7]),
                                     [int(x) & 0xFF for x in t[4:7]])
     return Model(cameras, images, points)
+
+
+def Read(path, reference_precision=True):
+    """Reconstruction::Read (:527-536): this fork reads the text files only and fails without them."""
+    if not all(os.path.exists(os.path.join(path, n)) for n in ("cameras.txt", "images.txt", "points3D.txt")):
+        raise FileNotFoundError("cameras, images, points3D files do not exist at " + path)
+    return read_model_text(path, reference_precision)
+
+
+def Write(path, model, reference_precision=True):
+    """Reconstruction::Write (:538-540): text."""
+    write_model_text(path, model, reference_precision)

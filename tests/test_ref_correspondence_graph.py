@@ -9,8 +9,10 @@ match) and must answer every query identically: image / pair / observation / cor
 counts before and after Finalize, the per-pair counts, every line's correspondences IN ORDER, the
 transitive closure at every transitivity (the reference's removal of the query line by
 overwriting the first entry with the last one included), the matches between two images and the
-two-view test.  Then the tracks (connected components) against the generating tracks, and a
-mapper scene rebuilt from pairwise matches.
+two-view test.  Then the tracks (connected components) against the generating tracks, a mapper
+scene rebuilt from pairwise matches, and the initial image-set search of
+RegisterInitialLineImages (src/sfm/incremental_mapper.cc:192-541) against a literal restatement,
+with the selection loop run on the library's host estimators.
 
 Skipped where neither oracle/_ref/libref_filter.so nor /root/reference exists."""
 import numpy as np
@@ -193,3 +195,74 @@ def test_mapper_scene_from_pairwise_matches():
     assert np.array_equal(rebuilt.visible, scene.visible[:, point_of])
     assert np.array_equal(rebuilt.lines[rebuilt.visible], scene.lines[:, point_of][rebuilt.visible])
     assert np.array_equal(rebuilt.aligned, scene.aligned[point_of])
+
+
+def _initial_sets_literal(g, image_aligned, check_image_ids, min_al=20, min_un=20):
+    """incremental_mapper.cc:253-426 statement by statement (sets of tuples, itertools)."""
+    from itertools import combinations
+    all_tracks = {True: {}, False: {}}
+    for image_id in check_image_ids:
+        for line_idx, flag in enumerate(image_aligned[image_id - 1]):
+            corrs = [c for c in g.FindCorrespondences(image_id, line_idx)
+                     if bool(image_aligned[c[0] - 1][c[1]]) == bool(flag)]
+            if len(corrs) < 3:
+                continue
+            for trio in combinations(corrs, 3):
+                cand = {}
+                for image, line in ((image_id, line_idx),) + trio:       # std::set keyed by image id
+                    cand.setdefault(image, line)
+                if len(cand) == 4:
+                    key = tuple(sorted(cand))
+                    all_tracks[bool(flag)].setdefault(key, set()).add(tuple(cand[i] for i in key))
+    numbers = [(key, len(tr), len(all_tracks[False][key])) for key, tr in sorted(all_tracks[True].items())
+               if len(tr) >= min_al and len(all_tracks[False].get(key, ())) >= min_un]
+    numbers.sort(key=lambda t: -t[1])
+    return numbers, all_tracks
+
+
+def test_initial_image_sets_and_selection():
+    """mapper.find_initial_image_sets against a literal restatement of the reference's candidate
+    search; mapper.select_initial_images (host estimators, no GPU) picks the tried set with the
+    best inlier ratio and its poses explain the tracks."""
+    from privacy_preserving_sfm_b200 import mapper as M
+    scene, gt = M.make_mapper_scene(num_images=7, num_points=260, seed=6, visibility=0.75, noise_px=0.2)
+    rng = np.random.default_rng(2)
+    n, p = scene.visible.shape
+    line_of = -np.ones((n, p), np.int64)
+    image_lines, image_aligned = [], []
+    for i in range(n):
+        vis = np.flatnonzero(scene.visible[i])
+        perm = rng.permutation(len(vis))
+        line_of[i, vis[perm]] = np.arange(len(vis))
+        image_lines.append(scene.lines[i, vis[perm]])
+        image_aligned.append(scene.aligned[vis[perm]])
+    g = CorrespondenceGraph()
+    for i in range(n):
+        g.AddImage(i + 1, len(image_lines[i]))
+    for i in range(n):
+        for j in range(i + 1, n):
+            both = np.flatnonzero(scene.visible[i] & scene.visible[j])
+            both = both[rng.uniform(size=len(both)) < 0.9]
+            g.AddCorrespondences(i + 1, j + 1, np.stack([line_of[i, both], line_of[j, both]], 1))
+    g.Finalize()
+    check = [2, 5, 6]
+    got = M.find_initial_image_sets(g, image_aligned, check)
+    want, all_tracks = _initial_sets_literal(g, image_aligned, check)
+    assert len(got) == len(want) > 3
+    assert [(d["image_set"], len(d["aligned_tracks"]), len(d["unaligned_tracks"])) for d in got] == want
+    for d in got[:5]:
+        assert [tuple(r) for r in d["aligned_tracks"].tolist()] == sorted(all_tracks[True][d["image_set"]])
+        assert [tuple(r) for r in d["unaligned_tracks"].tolist()] == sorted(all_tracks[False][d["image_set"]])
+        assert any(i in check for i in d["image_set"])                    # every track holds its reference line
+    ok, image_set, poses, ratio, tried = M.select_initial_images(
+        g, image_lines, image_aligned, scene.gravity, check, max_num_init_tries=3)
+    assert ok and len(tried) == 3 and [t[0] for t in tried] == [d["image_set"] for d in got[:3]]
+    assert ratio == max(t[2] for t in tried if t[1])
+    assert image_set == next(t[0] for t in tried if t[1] and t[2] == ratio)   # first best: ">" at :505
+    assert ratio > 0.9 and poses.shape == (4, 3, 4)
+    # the poses explain the four-view tracks: relative rotations equal the generating ones
+    ids = [i - 1 for i in image_set]
+    for k in range(1, 4):
+        rel = poses[k, :, :3] @ poses[0, :, :3].T
+        rel_gt = gt["R"][ids[k]] @ gt["R"][ids[0]].T
+        assert np.degrees(np.arccos(np.clip((np.trace(rel @ rel_gt.T) - 1) / 2, -1, 1))) < 0.5

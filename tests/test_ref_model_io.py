@@ -208,7 +208,9 @@ def test_reader_rejects_what_the_reference_rejects(tmp_path):
                 f.write(text)
 
     write()
-    assert len(IO.read_model_text(path).images[1].lines) == 1
+    assert len(IO.read_model_text(path).images[1].lines) == 1 and len(IO.Read(path).cameras) == 1
+    with pytest.raises(FileNotFoundError):                                   # Reconstruction::Read: LOG(FATAL)
+        IO.Read(str(tmp_path / "nothing"))
     write(**{"cameras.txt": "1 PINHOLE 640 480 500 500 320\n"})              # CHECK(VerifyParams)
     with pytest.raises(ValueError):
         IO.read_model_text(path)
