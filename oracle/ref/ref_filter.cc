@@ -264,3 +264,22 @@ extern "C" __attribute__((visibility("default"))) void ref_model_dump(
   }
   track_start[m->pts.size()] = e;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Reconstruction::Normalize (src/base/reconstruction.cc:302-398), called by the mapper after
+// every global bundle adjustment (src/sfm/incremental_mapper.cc:934-936): the reference's own
+// member on the reconstruction of a FilterProblem; translations and points are handed back.
+// ---------------------------------------------------------------------------------------------
+extern "C" __attribute__((visibility("default"))) int ref_normalize(
+    const FilterProblem* pb, double extent, double p0, double p1, int use_images, double* tvecs,
+    double* points) {
+  Built b;
+  Build(*pb, &b);
+  b.rec.Normalize(extent, p0, p1, use_images != 0);
+  for (int i = 0; i < pb->num_images; ++i)
+    for (int k = 0; k < 3; ++k) tvecs[3 * i + k] = b.rec.Image(i + 1).Tvec(k);
+  for (int p = 0; p < pb->num_points; ++p)
+    for (int k = 0; k < 3; ++k)
+      points[3 * p + k] = b.point_id[p] != 0 ? b.rec.Point3D(b.point_id[p]).XYZ()(k) : pb->points[3 * p + k];
+  return 0;
+}

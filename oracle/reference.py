@@ -464,6 +464,7 @@ def _filter_lib():
         _filter.ref_model_free.argtypes = [C.c_void_p]
         _filter.ref_model_sizes.argtypes = [C.c_void_p, C.POINTER(C.c_int64)]
         _filter.ref_model_dump.argtypes = [C.c_void_p] * 22
+        _filter.ref_normalize.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_int, _dp, _dp]
     return _filter
 
 
@@ -499,6 +500,15 @@ def model_write_text(problem, path, filter_thresholds=None):
     mx, ang = filter_thresholds if filter_thresholds is not None else (0.0, 0.0)
     _filter_lib().ref_model_write_text(C.byref(problem.struct), int(filter_thresholds is not None),
                                        mx, ang, path.encode())
+
+
+def normalize(problem, extent=10.0, p0=0.1, p1=0.9, use_images=True):
+    """The reference's Reconstruction::Normalize on the reconstruction of a FilterProblem:
+    (tvecs [n, 3], points [p, 3]) afterwards (points with an empty track are not part of it)."""
+    tv, pts = np.zeros_like(problem.tvecs), np.zeros_like(problem.points)
+    _filter_lib().ref_normalize(C.byref(problem.struct), extent, p0, p1, int(use_images),
+                                tv.ctypes.data_as(_dp), pts.ctypes.data_as(_dp))
+    return tv, pts
 
 
 def model_read_text(path, rewrite_to=None):

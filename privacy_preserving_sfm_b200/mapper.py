@@ -89,7 +89,7 @@ class IncrementalMapper:
                  filter_min_tri_angle=1.5, ba_every=4, verbose=False, local_ba=False,
                  ba_global_images_ratio=1.1, ba_global_points_ratio=1.1,
                  ba_global_images_freq=500, ba_global_points_freq=250000,
-                 ba_local_num_images=6, ba_ctx=None):
+                 ba_local_num_images=6, ba_ctx=None, normalize=False):
         """local_ba = False: global BA every `ba_every` images (the small-scene mode of the
         tests); True: the controller's schedule — local BA after every image, global BA when the
         model has grown by the ba_global_* ratios.  ba_ctx: context for the GLOBAL adjustments
@@ -120,6 +120,10 @@ class IncrementalMapper:
         self.max_reproj_error_px = max_reproj_error_px
         self.filter_max_reproj_error, self.filter_min_tri_angle = filter_max_reproj_error, filter_min_tri_angle
         self.ba_every, self.verbose = ba_every, verbose
+        # Reconstruction::Normalize after every global adjustment (sfm/incremental_mapper.cc:934-936):
+        # off by default — a similarity of the whole model, it changes no residual, only the gauge
+        # the result is reported in (pose_errors aligns by a similarity anyway)
+        self.normalize = normalize
         self.log = []
 
     # ---- RegisterInitialLineImages --------------------------------------------------------
@@ -272,6 +276,8 @@ class IncrementalMapper:
         if ok:
             self.qvec[reg], self.tvec[reg] = arrays.qvecs[reg], arrays.tvecs[reg]
             self.points[pid] = arrays.points
+        if self.normalize:
+            self.normalize_scene()
         # FilterPoints3D after the adjustment (controllers/incremental_mapper.cc:120-128)
         pb, obs_image, obs_point = self._track_problem(pid, self.points[pid].copy())
         nf, od, pd, _ = F.FilterPoints3D(self.ctx, pb, self.filter_max_reproj_error,
@@ -281,6 +287,15 @@ class IncrementalMapper:
         self.has_point[pid[pd]] = False
         self.points[pid[pd]] = np.nan
         self.log.append(("global_ba", float(s.initial_cost), float(s.final_cost), int(nf)))
+
+    def normalize_scene(self):
+        """Reconstruction::Normalize (base/reconstruction.cc:302-398; model_io.normalize_scene):
+        registered images' centres to extent 10 around their robust mean, points with them."""
+        reg = np.array(self.registered)
+        pid = np.flatnonzero(self.has_point)
+        tvec, pts, scale, _ = model_io.normalize_scene(self.qvec[reg], self.tvec[reg], self.points[pid])
+        self.tvec[reg], self.points[pid] = tvec, pts
+        return scale
 
     # ---- AdjustLocalBundle (sfm/incremental_mapper.cc:781-891) ----------------------------------
     def adjust_local_bundle(self, i, max_num_iterations=25):

@@ -247,6 +247,53 @@ def normalize_quaternion(qvec):
     return q / norm
 
 
+def _rotate(q, v):
+    """Eigen's quaternion * vector (Quaternion.h, _transformVector): v + w 2(u x v) + u x 2(u x v)."""
+    w, x, y, z = q[..., 0], q[..., 1], q[..., 2], q[..., 3]
+    v0, v1, v2 = v[..., 0], v[..., 1], v[..., 2]
+    u0, u1, u2 = y * v2 - z * v1, z * v0 - x * v2, x * v1 - y * v0
+    u0, u1, u2 = u0 + u0, u1 + u1, u2 + u2
+    return np.stack([v0 + w * u0 + (y * u2 - z * u1), v1 + w * u1 + (z * u0 - x * u2),
+                     v2 + w * u2 + (x * u1 - y * u0)], -1)
+
+
+def projection_centers(qvecs, tvecs):
+    """ProjectionCenterFromPose (src/base/pose.cc:94-101): conj(q / |q|) * (-t)."""
+    q = np.asarray(qvecs, np.float64).reshape(-1, 4)
+    norm = np.sqrt(q[:, 0] * q[:, 0] + q[:, 1] * q[:, 1] + q[:, 2] * q[:, 2] + q[:, 3] * q[:, 3])
+    qn = np.where(norm[:, None] == 0, np.concatenate([np.ones((len(q), 1)), q[:, 1:]], 1),
+                  q / np.where(norm == 0, 1.0, norm)[:, None])
+    return _rotate(qn * np.array([1.0, -1.0, -1.0, -1.0]), -np.asarray(tvecs, np.float64).reshape(-1, 3))
+
+
+def normalize_scene(qvecs, tvecs, points, extent=10.0, p0=0.1, p1=0.9, use_images=True):
+    """Reconstruction::Normalize (src/base/reconstruction.cc:302-398) on arrays: the registered
+    images' (qvecs [n, 4], tvecs [n, 3]) and the points [p, 3] -> (tvecs, points, scale,
+    translation).  The mapper calls it after every global bundle adjustment
+    (src/sfm/incremental_mapper.cc:934-936).  As the reference: coordinates (projection centres,
+    or points with ``use_images=False``) are cast to FLOAT and every axis is sorted on its own;
+    the box spans the p0 / p1 percentiles, the translation is the mean of the sorted values
+    between them, the scale ``extent`` over the box diagonal; a new tvec is q * (-(c - t) s) with
+    the image's quaternion as stored."""
+    q = np.asarray(qvecs, np.float64).reshape(-1, 4)
+    t = np.array(tvecs, np.float64).reshape(-1, 3)
+    X = np.array(points, np.float64).reshape(-1, 3)
+    if (use_images and len(q) < 2) or (not use_images and len(X) < 2):
+        return t, X, 1.0, np.zeros(3)
+    centers = projection_centers(q, t)
+    coords = np.sort((centers if use_images else X).astype(np.float32), axis=0)
+    n = len(coords)
+    P0 = int(p0 * (n - 1)) if n > 3 else 0
+    P1 = int(p1 * (n - 1)) if n > 3 else n - 1
+    bbox_min, bbox_max = coords[P0].astype(np.float64), coords[P1].astype(np.float64)
+    translation = np.cumsum(coords[P0:P1 + 1].astype(np.float64), axis=0)[-1] / float(P1 - P0 + 1)
+    d = bbox_max - bbox_min
+    old_extent = float(np.sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]))
+    scale = 1.0 if old_extent < np.finfo(np.float64).eps else extent / old_extent
+    new_t = _rotate(q, -((centers - translation) * scale))
+    return new_t, (X - translation) * scale, scale, translation
+
+
 def _rows(path):
     with open(path) as f:
         for ln in f:

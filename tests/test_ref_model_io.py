@@ -240,10 +240,22 @@ def test_mapper_text_round_trip_on_a_hand_made_state(tmp_path):
     m.scene = scene
     m.registered = [0, 2, 3, 5, 6]
     m.qvec = rng.normal(size=(7, 4))
+    m.qvec /= np.linalg.norm(m.qvec, axis=1)[:, None]               # unit, as the mapper keeps them
     m.tvec = rng.normal(size=(7, 3))
     m.points = rng.normal(size=(60, 3))
     m.has_point = rng.uniform(size=60) < 0.7
     m.obs_on = scene.visible & (rng.uniform(size=scene.visible.shape) < 0.8)
+    # Reconstruction::Normalize on the mapper's state: registered images and points move together
+    before = IO.projection_centers(m.qvec[m.registered], m.tvec[m.registered])
+    pts_before, t_unreg = m.points.copy(), m.tvec[[1, 4]].copy()
+    scale = m.normalize_scene()
+    after = IO.projection_centers(m.qvec[m.registered], m.tvec[m.registered])
+    d0, d1 = np.linalg.norm(before[0] - before[1]), np.linalg.norm(after[0] - after[1])
+    assert abs(d1 - scale * d0) < 1e-9 * d1 and np.array_equal(m.tvec[[1, 4]], t_unreg)
+    has = m.has_point
+    assert np.array_equal(m.points[~has], pts_before[~has])
+    assert abs(np.linalg.norm(m.points[has][0] - m.points[has][1])
+               - scale * np.linalg.norm(pts_before[has][0] - pts_before[has][1])) < 1e-9 * scale
     out = str(tmp_path / "model")
     m.write_text(out)
     model = M.IncrementalMapper.read_text(out)
@@ -263,3 +275,26 @@ def test_mapper_text_round_trip_on_a_hand_made_state(tmp_path):
         assert [i - 1 for i in track[:, 0]] == [i for i in m.registered if m.obs_on[i, pid - 1]]
         for img_id, line_idx in track:                                       # track elements point back
             assert model["images"][img_id][4][line_idx, 4] == pid
+
+
+@pytest.mark.parametrize("num_cams,use_images,p", [(12, True, (0.1, 0.9)), (3, True, (0.1, 0.9)),
+                                                   (12, False, (0.1, 0.9)), (9, True, (0.0, 1.0)),
+                                                   (30, True, (0.25, 0.6))])
+def test_normalize_is_the_references(ref, num_cams, use_images, p):
+    """model_io.normalize_scene against the reference's own Reconstruction::Normalize (what the
+    mapper applies after every global bundle adjustment): bit for bit."""
+    pb = _problem(num_cams, 200, min(4, num_cams), seed=90 + num_cams)
+    tv, pts, scale, translation = IO.normalize_scene(pb.qvecs, pb.tvecs, pb.points, 10.0, p[0], p[1],
+                                                     use_images)
+    tv_ref, pts_ref = ref.normalize(pb, 10.0, p[0], p[1], use_images)
+    assert np.array_equal(tv.view(np.uint64), tv_ref.view(np.uint64))
+    assert np.array_equal(pts.view(np.uint64), pts_ref.view(np.uint64))
+    # a similarity: line residuals of the model are unchanged (up to rounding), the extent is 10
+    c = IO.projection_centers(pb.qvecs, tv)
+    if use_images and p == (0.0, 1.0):
+        assert abs(np.linalg.norm(c.max(axis=0) - c.min(axis=0)) - 10.0) < 1e-5
+    c0 = IO.projection_centers(pb.qvecs, pb.tvecs)
+    assert np.abs((c0 - translation) * scale - c).max() < 1e-9 * max(1.0, scale)
+    # fewer than two images: untouched
+    one = IO.normalize_scene(pb.qvecs[:1], pb.tvecs[:1], pb.points)
+    assert np.array_equal(one[0], pb.tvecs[:1]) and one[2] == 1.0
