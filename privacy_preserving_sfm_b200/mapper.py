@@ -418,13 +418,16 @@ class IncrementalMapper:
             images[i + 1] = model_io.Image(self.qvec[i], self.tvec[i], 1, "image%06d.jpg" % i,
                                            sc.lines[i, vis], sc.aligned[vis],
                                            np.where(has, vis + 1, -1))
-        row = {i: k for k, i in enumerate(reg)}                  # rank of a point among an image's lines
+        is_reg = np.zeros(len(self.qvec), bool)
+        is_reg[reg] = True
+        row = np.cumsum(is_reg) - 1                              # image -> row of line_idx
+        # line_idx: rank of a point among an image's lines
         line_idx = np.cumsum(sc.visible[reg], axis=1, dtype=np.int32) - 1
         points = {}
         for p in np.flatnonzero(self.has_point):
-            imgs = np.array([i for i in reg if self.obs_on[i, p]], np.int64)
+            imgs = np.flatnonzero(self.obs_on[:, p] & is_reg)
             points[int(p) + 1] = model_io.Point3D(self.points[p],
-                                                  np.stack([imgs + 1, line_idx[[row[i] for i in imgs], p]], 1))
+                                                  np.stack([imgs + 1, line_idx[row[imgs], p]], 1))
         return model_io.Model(cams, images, points)
 
     def write_text(self, path):
