@@ -38,6 +38,12 @@ def ImagePairToPairId(image_id1, image_id2):
     return K_MAX_NUM_IMAGES * image_id1 + image_id2
 
 
+def _all_distinct(v):
+    if len(v) < 256:
+        return len(set(v.tolist())) == len(v)
+    return len(np.unique(v)) == len(v)
+
+
 class CorrespondenceGraph:
     def __init__(self):
         self._num_lines = {}                         # image_id -> number of lines
@@ -66,10 +72,11 @@ class CorrespondenceGraph:
         m = np.asarray(matches, np.int64).reshape(-1, 2)
         pair_id = ImagePairToPairId(image_id1, image_id2)
         self._pairs.setdefault(pair_id, 0)
-        m = m[(m[:, 0] >= 0) & (m[:, 0] < n1) & (m[:, 1] >= 0) & (m[:, 1] < n2)]
+        if len(m) and (m.min() < 0 or m[:, 0].max() >= n1 or m[:, 1].max() >= n2):
+            m = m[(m[:, 0] >= 0) & (m[:, 0] < n1) & (m[:, 1] >= 0) & (m[:, 1] < n2)]
         swap = image_id1 > image_id2
         earlier = self._kept.setdefault(pair_id, [])
-        if not earlier and len(np.unique(m[:, 0])) == len(m) and len(np.unique(m[:, 1])) == len(m):
+        if not earlier and _all_distinct(m[:, 0]) and _all_distinct(m[:, 1]):
             keep = m                                                          # no duplicate possible
         else:
             used1, used2 = set(), set()
@@ -96,15 +103,18 @@ class CorrespondenceGraph:
 
     def Finalize(self):
         idx = self._build()
+        erased = False
         for image_id in list(self._num_lines):
             start = idx["start"][image_id]
             obs = int((np.diff(start) > 0).sum())
             if obs == 0:
                 for d in (self._num_lines, self._num_corrs, self._num_obs):
                     del d[image_id]
+                erased = True
             else:
                 self._num_obs[image_id] = obs
-        self._index = None
+        if erased:
+            self._index = None
 
     # ---- CSR index: per image, start[line] .. start[line + 1] into (dst_image, dst_line) ------------
     def _build(self):
@@ -116,22 +126,24 @@ class CorrespondenceGraph:
         for i in ids:
             base[i] = total
             total += self._num_lines[i]
-        src, dst_img, dst_line = [], [], []
-        for id1, id2, m in self._edges:
-            if id1 not in base or id2 not in base:
-                continue                              # erased by Finalize: nothing points to them
+        if self._edges and ids:
+            ids_arr = np.array(ids, np.int64)
+            base_arr = np.array([base[i] for i in ids], np.int64)
+            lens = np.array([len(m) for _, _, m in self._edges], np.int64)
+            id1 = np.repeat(np.array([e[0] for e in self._edges], np.int64), lens)
+            id2 = np.repeat(np.array([e[1] for e in self._edges], np.int64), lens)
+            m = np.concatenate([e[2] for e in self._edges])
+            k1 = np.minimum(np.searchsorted(ids_arr, id1), len(ids) - 1)
+            k2 = np.minimum(np.searchsorted(ids_arr, id2), len(ids) - 1)
+            alive = (ids_arr[k1] == id1) & (ids_arr[k2] == id2)   # erased by Finalize: nothing points to them
+            id1, id2, m, k1, k2 = id1[alive], id2[alive], m[alive], k1[alive], k2[alive]
             # corrs1.emplace_back(image_id2, idx2); corrs2.emplace_back(image_id1, idx1) per match
-            s = np.empty(2 * len(m), np.int64)
-            s[0::2], s[1::2] = base[id1] + m[:, 0], base[id2] + m[:, 1]
-            di = np.empty(2 * len(m), np.int64)
-            di[0::2], di[1::2] = id2, id1
-            dl = np.empty(2 * len(m), np.int64)
-            dl[0::2], dl[1::2] = m[:, 1], m[:, 0]
-            src.append(s)
-            dst_img.append(di)
-            dst_line.append(dl)
-        if src:
-            src, dst_img, dst_line = np.concatenate(src), np.concatenate(dst_img), np.concatenate(dst_line)
+            src = np.empty(2 * len(m), np.int64)
+            src[0::2], src[1::2] = base_arr[k1] + m[:, 0], base_arr[k2] + m[:, 1]
+            dst_img = np.empty(2 * len(m), np.int64)
+            dst_img[0::2], dst_img[1::2] = id2, id1
+            dst_line = np.empty(2 * len(m), np.int64)
+            dst_line[0::2], dst_line[1::2] = m[:, 1], m[:, 0]
             order = np.argsort(src, kind="stable")    # insertion order within every line
             src, dst_img, dst_line = src[order], dst_img[order], dst_line[order]
         else:
@@ -227,25 +239,34 @@ class CorrespondenceGraph:
         for i in ids:
             base[i] = total
             total += self._num_lines[i]
-        parent = np.arange(total)
         img_of = np.repeat(np.array(ids, np.int64), [self._num_lines[i] for i in ids]) if ids else np.zeros(0, np.int64)
         base_arr = np.array([base[i] for i in ids], np.int64)
         ids_arr = np.array(ids, np.int64)
-        # edges (node -> node); label propagation by pointer jumping on the minimum label
+        # edges (node -> node): the CSR arrays are ordered by source node
         src = np.concatenate([np.repeat(np.arange(base[i], base[i] + self._num_lines[i]),
                                         np.diff(idx["start"][i])) for i in ids]) if ids else np.zeros(0, np.int64)
+        parent = np.arange(total)
         if len(src):
-            # the CSR arrays are ordered by source node: same order as src
             dst = base_arr[np.searchsorted(ids_arr, idx["dst_img"])] + idx["dst_line"]
-            while True:
-                m = np.minimum(parent[src], parent[dst])
-                new = parent.copy()
-                np.minimum.at(new, src, m)
-                np.minimum.at(new, dst, m)
-                new = new[new]
-                if np.array_equal(new, parent):
-                    break
-                parent = new
+            try:
+                from scipy.sparse import coo_matrix
+                from scipy.sparse.csgraph import connected_components
+                adj = coo_matrix((np.ones(len(src), np.int8), (src, dst)), shape=(total, total))
+                _, label = connected_components(adj, directed=False)
+                # label every node by the smallest node of its component (order of first element)
+                first = np.full(label.max() + 1, total, np.int64)
+                np.minimum.at(first, label, np.arange(total))
+                parent = first[label]
+            except ImportError:                       # label propagation by pointer jumping
+                while True:
+                    m = np.minimum(parent[src], parent[dst])
+                    new = parent.copy()
+                    np.minimum.at(new, src, m)
+                    np.minimum.at(new, dst, m)
+                    new = new[new]
+                    if np.array_equal(new, parent):
+                        break
+                    parent = new
         order = np.argsort(parent, kind="stable")
         labels = parent[order]
         cuts = np.flatnonzero(np.diff(labels)) + 1
@@ -254,3 +275,43 @@ class CorrespondenceGraph:
             if len(comp) >= min_length:
                 tracks.append([(int(img_of[n]), int(n - base[int(img_of[n])])) for n in comp])
         return tracks
+
+
+def graph_from_visibility(visible, line_of=None, finalize=True):
+    """The synthetic correspondence graph of a generated scene ("synthetic
+    CorrespondenceGraph from ground-truth visibility"): image ids index + 1, every pair of images
+    matched on the points both see.  visible [n_images, n_points] bool; line_of [n_images,
+    n_points]: the line index of a point in an image (default: its rank among the image's visible
+    points).  Returns (graph, line_of, num_lines)."""
+    visible = np.asarray(visible, bool)
+    n, _ = visible.shape
+    if line_of is None:
+        line_of = np.where(visible, np.cumsum(visible, axis=1) - 1, -1)
+    num_lines = [int(line_of[i][visible[i]].max()) + 1 if visible[i].any() else 0 for i in range(n)]
+    g = CorrespondenceGraph()
+    for i in range(n):
+        g.AddImage(i + 1, num_lines[i])
+    # all (point, view a < view b) triples, grouped by image pair
+    pt, img = np.nonzero(visible.T)                      # sorted by point, then image
+    start = np.searchsorted(pt, np.arange(visible.shape[1] + 1))
+    length = np.diff(start)
+    a_list, b_list = [], []
+    for L in np.unique(length[length >= 2]):
+        pts = np.flatnonzero(length == L)
+        views = img[start[pts][:, None] + np.arange(L)[None, :]]        # [points of this length, L]
+        ia, ib = np.triu_indices(L, 1)
+        a_list.append(np.stack([views[:, ia].ravel(), views[:, ib].ravel(),
+                                np.repeat(pts, len(ia))], 1))
+    if a_list:
+        tri = np.concatenate(a_list)
+        order = np.argsort((tri[:, 0] * n + tri[:, 1]) * visible.shape[1] + tri[:, 2], kind="stable")
+        tri = tri[order]                              # by image pair, then point
+        matches = np.stack([line_of[tri[:, 0], tri[:, 2]], line_of[tri[:, 1], tri[:, 2]]], 1)
+        key = tri[:, 0] * n + tri[:, 1]
+        cuts = np.concatenate([[0], np.flatnonzero(np.diff(key)) + 1, [len(tri)]])
+        first = tri[cuts[:-1], :2] + 1
+        for (i, j), lo, hi in zip(first.tolist(), cuts[:-1].tolist(), cuts[1:].tolist()):
+            g.AddCorrespondences(i, j, matches[lo:hi])
+    if finalize:
+        g.Finalize()
+    return g, line_of, num_lines
