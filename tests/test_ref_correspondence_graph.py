@@ -266,3 +266,26 @@ def test_initial_image_sets_and_selection():
         rel = poses[k, :, :3] @ poses[0, :, :3].T
         rel_gt = gt["R"][ids[k]] @ gt["R"][ids[0]].T
         assert np.degrees(np.arccos(np.clip((np.trace(rel @ rel_gt.T) - 1) / 2, -1, 1))) < 0.5
+
+
+def test_graph_from_visibility_is_the_pairwise_graph(ref):
+    """correspondence_graph.graph_from_visibility (config 5: "synthetic CorrespondenceGraph from
+    ground-truth visibility") == the reference's class fed pair by pair with the same matches."""
+    from privacy_preserving_sfm_b200.correspondence_graph import graph_from_visibility
+    visible, line_of, _ = _scene(9, 70, 0.4, seed=31, extra_lines=0)
+    visible[8] = False                                                     # an image that sees nothing
+    g, line_of2, num_lines = graph_from_visibility(visible, np.where(visible, line_of, -1))
+    b = ref.CorrespondenceGraph()
+    for i, n in enumerate(num_lines):
+        b.AddImage(i + 1, n)
+    for i in range(9):
+        for j in range(i + 1, 9):
+            both = np.flatnonzero(visible[i] & visible[j])
+            if len(both):
+                b.AddCorrespondences(i + 1, j + 1, np.stack([line_of[i, both], line_of[j, both]], 1))
+    b.Finalize()
+    _same_answers(g, b, num_lines, transitivities=(1, 3))
+    assert not g.ExistsImage(9)
+    g2, default_line_of, _ = graph_from_visibility(visible)                # default: rank among visible
+    assert np.array_equal(default_line_of[0][visible[0]], np.arange(visible[0].sum()))
+    assert len(g2.Tracks()) == int((visible.sum(axis=0) >= 2).sum())
