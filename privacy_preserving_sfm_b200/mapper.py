@@ -532,14 +532,22 @@ def find_initial_image_sets(graph, image_aligned, check_image_ids, min_num_align
     ``std::set``) — aligned rows then unaligned rows are the ``lines`` the reference hands to
     ``init::initialize_reconstruction`` (:459-481)."""
     rows = []
+    csr = graph._build()
+    # is_aligned of the line every correspondence points to (one lookup for the whole graph)
+    ids = np.array(sorted(csr["start"]), np.int64)
+    sizes = np.array([len(image_aligned[i - 1]) for i in ids], np.int64)
+    base = np.concatenate([[0], np.cumsum(sizes)[:-1]])
+    flat = np.concatenate([np.asarray(image_aligned[i - 1], bool) for i in ids]) if len(ids) else np.zeros(0, bool)
+    dst_aligned = flat[base[np.searchsorted(ids, csr["dst_img"])] + csr["dst_line"]]
     for image_id in check_image_ids:
         flags = np.asarray(image_aligned[image_id - 1], bool)
+        start = csr["start"][image_id]                                  # images_.at(image_id)
         for line_idx in range(len(flags)):
-            di, dl = graph._corrs(image_id, line_idx)
-            if len(di) < 3:
+            lo, hi = start[line_idx], start[line_idx + 1]
+            if hi - lo < 3:
                 continue
-            same = np.array([bool(image_aligned[int(i) - 1][int(l)]) for i, l in zip(di, dl)]) == flags[line_idx]
-            di, dl = di[same], dl[same]
+            same = dst_aligned[lo:hi] == flags[line_idx]
+            di, dl = csr["dst_img"][lo:hi][same], csr["dst_line"][lo:hi][same]
             if len(di) < 3:
                 continue
             c3 = _combos3(len(di))
@@ -552,11 +560,15 @@ def find_initial_image_sets(graph, image_aligned, check_image_ids, min_num_align
             rows.append(np.concatenate([al, img[distinct], idx[distinct]], 1))
     if not rows:
         return []
-    rows = np.unique(np.concatenate(rows), axis=0)                      # std::set: every track once
-    sets, start, count = np.unique(rows[:, :5], axis=0, return_index=True, return_counts=True)
+    rows = np.concatenate(rows)
+    rows = rows[np.lexsort(rows.T[::-1])]                               # lexicographic by row
+    rows = rows[np.concatenate([[True], (np.diff(rows, axis=0) != 0).any(axis=1)])]   # std::set: every track once
+    start = np.flatnonzero(np.concatenate([[True], (np.diff(rows[:, :5], axis=0) != 0).any(axis=1)]))
+    stop = np.concatenate([start[1:], [len(rows)]])
     by_set = {}
-    for key, s, c in zip(sets, start, count):
-        by_set.setdefault(tuple(int(v) for v in key[1:]), {})[int(key[0])] = rows[s:s + c, 5:]
+    for s, e in zip(start.tolist(), stop.tolist()):
+        key = rows[s, :5].tolist()
+        by_set.setdefault(tuple(key[1:]), {})[key[0]] = rows[s:e, 5:]
     out = []
     for image_set in sorted(by_set):
         tracks = by_set[image_set]

@@ -10,10 +10,11 @@ config 5: "synthetic CorrespondenceGraph from ground-truth visibility"): pairwis
 generated visibility -> correspondence_graph.CorrespondenceGraph -> tracks (connected components)
 -> mapper.Scene, and the four initial images are searched and selected as
 RegisterInitialLineImages does (mapper.select_initial_images, ten check images drawn with seed 0)
-instead of being given.  (Building the graph of 1 000 images / 13 M correspondences takes ~30 s
-of host time and is reported separately; written in the round's last session, which had no GPU
-time left: the host side is covered by tests/test_ref_correspondence_graph.py, the GPU loop on
-a scene built this way has not been run.)
+instead of being given.  (Building the graph of 1 000 images / 13 M correspondences takes ~30 s of host time and is
+reported separately.  Added in the round's last session with under a GPU-minute left: run on a
+B200 at 16 images / 1 000 points only — profiles/r02_s7_config5_graph_small.json: the search
+finds the four initial images, all 16 images registered, 1.1e-3 rad / 7e-4 of the extent — the
+host side is covered by tests/test_ref_correspondence_graph.py.)
 
 Prints one JSON line: wall time of the loop, its split, registered images, final pose error
 against the generating scene (after a similarity alignment)."""
