@@ -289,3 +289,29 @@ def test_graph_from_visibility_is_the_pairwise_graph(ref):
     g2, default_line_of, _ = graph_from_visibility(visible)                # default: rank among visible
     assert np.array_equal(default_line_of[0][visible[0]], np.arange(visible[0].sum()))
     assert len(g2.Tracks()) == int((visible.sum(axis=0) >= 2).sum())
+
+
+@pytest.mark.parametrize("seed", range(12))
+def test_random_dirty_match_sets_identical_to_the_reference(ref, capfd, seed):
+    """Fuzz: few images, few lines, many random matches — so that duplicates, conflicting matches,
+    repeated / swapped pairs, self matches and out-of-range indices all occur together."""
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(3, 6))
+    num_lines = [int(rng.integers(1, 7)) for _ in range(n)]
+    calls = []
+    for _ in range(int(rng.integers(4, 14))):
+        i, j = (int(v) for v in rng.integers(1, n + 1, size=2))
+        k = int(rng.integers(0, 9))
+        m = np.stack([rng.integers(0, num_lines[i - 1] + 2, size=k),
+                      rng.integers(0, num_lines[j - 1] + 2, size=k)], 1)
+        calls.append((i, j, m))
+    a, b = CorrespondenceGraph(), ref.CorrespondenceGraph()
+    _feed((a, b), num_lines, calls, finalize=False)
+    for i in range(1, n + 1):
+        assert a.NumCorrespondencesForImage(i) == b.NumCorrespondencesForImage(i)
+        for line in range(num_lines[i - 1]):
+            assert a.FindCorrespondences(i, line) == b.FindCorrespondences(i, line), (seed, i, line)
+    a.Finalize()
+    b.Finalize()
+    _same_answers(a, b, num_lines, transitivities=(1, 2, 4))
+    capfd.readouterr()                                                     # the reference's warnings
