@@ -44,6 +44,7 @@ Pinned against the reference's own ``ReadText`` / ``WriteText`` compiled from
 import ctypes as C
 import ctypes.util
 import os
+import re
 
 import numpy as np
 
@@ -58,34 +59,61 @@ CAMERA_MODEL_NUM_PARAMS = {0: 3, 1: 4, 2: 4, 3: 5, 4: 8, 5: 8, 6: 12, 7: 5, 8: 4
 
 _libc = C.CDLL(ctypes.util.find_library("c") or None, use_errno=True)
 _libc.strtold.restype = C.c_longdouble
-_libc.strtold.argtypes = [C.c_char_p, C.c_void_p]
+_libc.strtold.argtypes = [C.c_void_p, C.c_void_p]
 _libc.strtof.restype = C.c_float
-_libc.strtof.argtypes = [C.c_char_p, C.c_void_p]
+_libc.strtof.argtypes = [C.c_void_p, C.c_void_p]
+
+
+def _c_parse(fn, item):
+    """strtold / strtof with the std::sto* contract: leading white space and trailing characters
+    are accepted, no conversion at all throws (std::invalid_argument), ERANGE throws
+    (std::out_of_range)."""
+    raw = item.encode()
+    buf = C.create_string_buffer(raw)
+    end = C.c_void_p()
+    C.set_errno(0)
+    value = fn(buf, C.byref(end))
+    if end.value is None or end.value == C.addressof(buf):
+        raise ValueError("sto*: no conversion of %r" % item)
+    if C.get_errno() == 34:                                       # ERANGE
+        raise ValueError("sto*: %r is out of range" % item)
+    return value
 
 
 def _stold(item):
     """double(std::stold(item)): parsed to long double, narrowed to double on assignment."""
-    if not item.strip():
-        raise ValueError("stold: no conversion")
-    return float(_libc.strtold(item.encode(), None))
+    return float(_c_parse(_libc.strtold, item))
+
+
+_INT = re.compile(r"\s*[+-]?\d+")
+
+
+def _stoi(item):
+    """std::stoul / stoll / stoi on well-formed ids: the leading integer, trailing characters ignored."""
+    m = _INT.match(item)
+    if not m:
+        raise ValueError("sto*: no conversion of %r" % item)
+    return int(m.group(0))
 
 
 def _stof_row(items):
     """double(std::stof(item)) for a row of tokens.  Vectorised as double parse + narrowing; the
     tokens whose double value sits exactly between two floats (where rounding twice and rounding
     once can differ) and the ends of the float range go through strtof itself: std::stof throws
-    std::out_of_range where strtof reports ERANGE (overflow, inexact subnormal results)."""
-    d = np.array(items, dtype=np.float64)
+    std::out_of_range where strtof reports ERANGE (overflow, inexact subnormal results).  Rows
+    with tokens numpy does not read (hexadecimal floats, trailing characters: strtof does) are
+    parsed token by token."""
+    try:
+        d = np.array(items, dtype=np.float64)
+    except ValueError:
+        return np.array([float(_c_parse(_libc.strtof, x)) for x in items], np.float64)
     with np.errstate(over="ignore"):
         f = d.astype(np.float32)
     bits = d.view(np.uint64)
     redo = ((bits & np.uint64(0x1FFFFFFF)) == np.uint64(0x10000000)) | \
            ((np.abs(d) < 1.1754943508222875e-38) & (d != 0)) | (np.abs(d) > 3.4028234e38)
     for k in np.flatnonzero(redo):
-        C.set_errno(0)
-        f[k] = _libc.strtof(items[k].encode(), None)
-        if C.get_errno() == 34:                                   # ERANGE
-            raise ValueError("stof: %r is out of the float range" % items[k])
+        f[k] = _c_parse(_libc.strtof, items[k])
     return f.astype(np.float64)
 
 
@@ -311,11 +339,11 @@ def read_model_text(path, reference_precision=True):
         t = ln.split(" ")
         if t[1] not in CAMERA_MODEL_IDS:
             raise ValueError("cameras.txt: unknown camera model %r" % t[1])
-        cam = Camera(CAMERA_MODEL_IDS[t[1]], int(t[2]), int(t[3]), [num(x) for x in t[4:]])
+        cam = Camera(CAMERA_MODEL_IDS[t[1]], _stoi(t[2]), _stoi(t[3]), [num(x) for x in t[4:]])
         if len(cam.params) != CAMERA_MODEL_NUM_PARAMS[cam.model_id]:    # CHECK(camera.VerifyParams())
             raise ValueError("cameras.txt: %s takes %d parameters, %d given"
                              % (t[1], CAMERA_MODEL_NUM_PARAMS[cam.model_id], len(cam.params)))
-        cameras[int(t[0])] = cam
+        cameras[_stoi(t[0])] = cam
     rows = _rows(os.path.join(path, "images.txt"))
     for ln in rows:
         if not ln or ln[0] == "#":
@@ -325,7 +353,7 @@ def read_model_text(path, reference_precision=True):
         if reference_precision:
             qvec = normalize_quaternion(qvec)
         tvec = np.array([num(x) for x in t[5:8]])
-        camera_id, name = int(t[8]), (t[9] if len(t) > 9 else "")
+        camera_id, name = _stoi(t[8]), (t[9] if len(t) > 9 else "")
         row = next(rows, None)                       # LINES2D: the next line, whatever it holds
         if row is None:
             break
@@ -342,22 +370,24 @@ def read_model_text(path, reference_precision=True):
                 lines = lines / np.sqrt(lines[:, 0] * lines[:, 0] + lines[:, 1] * lines[:, 1])[:, None]
             else:
                 lines = np.array(coeff, dtype=np.float64).reshape(-1, 3)
-            ids = np.array([int(x) for x in items[4::5]], np.int64)
-            images[int(t[0])] = Image(qvec, tvec, camera_id, name, lines,
+            ids = np.array([_stoi(x) for x in items[4::5]], np.int64)
+            images[_stoi(t[0])] = Image(qvec, tvec, camera_id, name, lines,
                                       [x == "1" for x in flags], ids)
         else:
-            images[int(t[0])] = Image(qvec, tvec, camera_id, name, np.zeros((0, 3)), [], [])
+            images[_stoi(t[0])] = Image(qvec, tvec, camera_id, name, np.zeros((0, 3)), [], [])
     for ln in _rows(os.path.join(path, "points3D.txt")):
         if not ln or ln[0] == "#":
             continue
         t = ln.split(" ")
         track = []
-        for k in range(8, len(t) - 1, 2):
+        for k in range(8, len(t), 2):
             if not t[k].strip():
                 break
-            track.append((int(t[k]), int(t[k + 1])))
-        points[int(t[0])] = Point3D([num(x) for x in t[1:4]], track, num(t[7]),
-                                    [int(x) & 0xFF for x in t[4:7]])
+            # a dangling IMAGE_ID: the second std::getline fails at the end of the row and leaves
+            # the item as it was, so the reference reads the id again as the line index (:944-951)
+            track.append((_stoi(t[k]), _stoi(t[k + 1] if k + 1 < len(t) else t[k])))
+        points[_stoi(t[0])] = Point3D([num(x) for x in t[1:4]], track, num(t[7]),
+                                    [_stoi(x) & 0xFF for x in t[4:7]])
     return Model(cameras, images, points)
 
 

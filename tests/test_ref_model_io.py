@@ -298,3 +298,24 @@ def test_normalize_is_the_references(ref, num_cams, use_images, p):
     # fewer than two images: untouched
     one = IO.normalize_scene(pb.qvecs[:1], pb.tvecs[:1], pb.points)
     assert np.array_equal(one[0], pb.tvecs[:1]) and one[2] == 1.0
+
+
+def test_unusual_but_valid_number_tokens_read_as_the_reference_reads_them(ref, tmp_path):
+    """std::sto* accept what strtod-style parsing accepts: signs, exponents, missing digits on one
+    side of the point, hexadecimal floats, trailing characters, nan / inf."""
+    path = str(tmp_path / "m")
+    os.makedirs(path)
+    with open(os.path.join(path, "cameras.txt"), "w") as f:
+        f.write("3 OPENCV 640 480 +5.0e2 0x1.f4p8 .32e3 240. 1e-2 -1E-3 0 0x0p0\n")
+    with open(os.path.join(path, "images.txt"), "w") as f:
+        f.write("0012 1e0 0 -0 0.0 1.5abc +2 -.5e1 3 name_with_underscore.png\n")
+        f.write("6e-1 0x1.999999999999ap-1 1 1 9 -.6 +.8 2.5E0 0 -1 3 4junk 5 0 7\n")
+        f.write("5 nan 0 0 1 inf 0 0 3 x.jpg\n\n")
+    with open(os.path.join(path, "points3D.txt"), "w") as f:
+        f.write("9 1e1 -2.E0 .5 300 -1 7 -1 12 0\n7 0 0 0 1 2 3 0x1p-3 12 2 5\n")
+    m = IO.read_model_text(path)
+    _same_as_reference_dump(m, ref.model_read_text(path))
+    assert m.cameras[3].params[1] == 500.0 and m.images[12].tvec[0] == 1.5
+    assert m.images[12].lines.shape == (3, 3) and np.isnan(m.images[5].qvec).all()
+    assert np.array_equal(m.points3D[9].color, [300 & 255, 255, 7])          # static_cast<uint8_t>
+    assert np.array_equal(m.points3D[7].track, [[12, 2], [5, 5]])             # a dangling id is read twice
