@@ -147,6 +147,42 @@ def ImageToWorld(camera_model, params, xy):
     return np.stack([u, v], 1)
 
 
+def WorldToImage(camera_model, params, uv):
+    """CameraModelWorldToImage for all 11 models: normalised camera coordinates [n, 2] -> pixels
+    (the forward model of the filters' pixel-space reprojection error, src/base/projection.cc)."""
+    p = np.asarray(params, np.float64)
+    uv = np.asarray(uv, np.float64).reshape(-1, 2)
+    u, v = uv[:, 0], uv[:, 1]
+    single = camera_model in (0, 2, 3, 8, 9)
+    if not single and camera_model not in (1, 4, 5, 6, 7, 10):
+        raise ValueError("unknown camera model %d" % camera_model)
+    f1, f2, c1, c2, extra = (p[0], p[0], p[1], p[2], p[3:]) if single else (p[0], p[1], p[2], p[3], p[4:])
+    if camera_model in (0, 1):
+        return np.stack([f1 * u + c1, f2 * v + c2], 1)
+    if camera_model == 7:                                 # FOVCameraModel::Distortion (:1136-1171)
+        omega = extra[0]
+        radius2 = u * u + v * v
+        omega2 = omega * omega
+        if omega2 < 1e-4:
+            factor = (omega2 * radius2) / 3.0 - omega2 / 12.0 + 1.0
+        else:
+            tan_half = np.tan(omega / 2.0)
+            small = radius2 < 1e-4
+            radius = np.sqrt(np.where(small, 1.0, radius2))
+            factor = np.where(small,
+                              (-2.0 * tan_half * (4.0 * radius2 * tan_half * tan_half - 3.0)) / (3.0 * omega),
+                              np.arctan(radius * 2.0 * tan_half) / (radius * omega))
+        return np.stack([f1 * (u * factor) + c1, f2 * (v * factor) + c2], 1)
+    if camera_model == 10:                                # equidistant pre-mapping (:1412-1421)
+        r = np.sqrt(u * u + v * v)
+        big = r > _EPS
+        rs = np.where(big, r, 1.0)
+        theta = np.arctan(rs)
+        u, v = np.where(big, theta * u / rs, u), np.where(big, theta * v / rs, v)
+    du, dv = _distortion(camera_model, extra, u, v)
+    return np.stack([f1 * (u + du) + c1, f2 * (v + dv) + c2], 1)
+
+
 def select_aligned_features(num_features, aligned_line_ratio, rng):
     """The reference's rule (extraction.cc:452-457): draw feature indices uniformly WITH
     replacement until the set holds at least ratio * n of them.  ``rng``: numpy Generator."""

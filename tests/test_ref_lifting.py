@@ -52,6 +52,11 @@ def test_image_to_world_matches_the_reference(ref, model, params):
     else:
         assert np.abs(uv - uv_ref).max() <= 1e-14 * max(1.0, np.abs(uv_ref).max())
     back = np.array([ref.world_to_image(model, params, u, v) for u, v in uv])
+    fwd = L.WorldToImage(model, params, uv)                 # the forward model, same pins
+    if model in EXACT:
+        assert np.array_equal(fwd.view(np.uint64), back.view(np.uint64))
+    else:
+        assert np.abs(fwd - back).max() <= 1e-12 * 1000.0
     # the Newton stop is ||step||^2 < 1e-10; the reference's FOV model at omega^2 < 1e-4 is a pair
     # of truncated series (camera_models.h:1147-1161, :1187-1193), not exact inverses of each other
     series = model == 7 and params[4] ** 2 < 1e-4
