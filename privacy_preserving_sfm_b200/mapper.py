@@ -33,7 +33,6 @@ GPU operators, not a re-implementation of COLMAP's bookkeeping: tracks are given
 correspondence search, hence no track merging), one shared camera, intrinsics constant (the
 fork's defaults, controllers/incremental_mapper.h:81-83).
 """
-import os
 import numpy as np
 
 from . import bundle_adjustment as ba
