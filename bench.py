@@ -427,8 +427,11 @@ def run_b200(args):
         # all but ~1e-5 of the pairs in its float stage: 13 packed FMAs = 26 flop per pair.
         "bound": "fp32_fma",
         "achieved": achieved, "peak": 2 * ffma_tips,
-        "unit": "TFLOP/s (EXECUTED flop: 26 per (model, correspondence) pair actually evaluated, "
-                "pruned pairs not counted)",
+        "unit": "TFLOP/s",
+        "unit_note": "EXECUTED flop: 26 per (model, correspondence) pair actually evaluated, pruned "
+                     "pairs not counted",
+        "bound_note": "CUDA-core packed-float FMA pipe (SURVEY.md 8d: the scoring is ALU-bound, "
+                      "neither HBM nor tensor pipe); the HBM view of the same kernel is under 'hbm'",
         "frac": achieved / (2 * ffma_tips),
         "peak_source": "measured in this run (ppsfm_bench_fp32_peak: packed FFMA2 issue rate x 2 "
                        "flop); not in MEASURED_PEAKS.json",
