@@ -153,6 +153,12 @@ class CorrespondenceGraph:
         self._index = dict(start=start, dst_img=dst_img, dst_line=dst_line)
         return self._index
 
+    def CSR(self):
+        """The index itself, for vectorised walks over many lines: dict(start {image_id: offsets
+        [num_lines + 1]}, dst_img, dst_line) — line l of image i corresponds to
+        (dst_img[k], dst_line[k]) for k in start[i][l] .. start[i][l + 1], in insertion order."""
+        return self._build()
+
     def _corrs(self, image_id, line_idx):
         idx = self._build()
         start = idx["start"][image_id]                                        # images_.at(image_id)

@@ -531,7 +531,7 @@ def find_initial_image_sets(graph, image_aligned, check_image_ids, min_num_align
     ``std::set``) — aligned rows then unaligned rows are the ``lines`` the reference hands to
     ``init::initialize_reconstruction`` (:459-481)."""
     rows = []
-    csr = graph._build()
+    csr = graph.CSR()
     # is_aligned of the line every correspondence points to (one lookup for the whole graph)
     ids = np.array(sorted(csr["start"]), np.int64)
     sizes = np.array([len(image_aligned[i - 1]) for i in ids], np.int64)
