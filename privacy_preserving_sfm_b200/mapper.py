@@ -88,7 +88,8 @@ class IncrementalMapper:
                  filter_min_tri_angle=1.5, ba_every=4, verbose=False, local_ba=False,
                  ba_global_images_ratio=1.1, ba_global_points_ratio=1.1,
                  ba_global_images_freq=500, ba_global_points_freq=250000,
-                 ba_local_num_images=6, ba_ctx=None, normalize=False):
+                 ba_local_num_images=6, ba_ctx=None, normalize=False,
+                 local_bundle_selection="overlap", ba_local_min_tri_angle=6.0):
         """local_ba = False: global BA every `ba_every` images (the small-scene mode of the
         tests); True: the controller's schedule — local BA after every image, global BA when the
         model has grown by the ba_global_* ratios.  ba_ctx: context for the GLOBAL adjustments
@@ -123,6 +124,10 @@ class IncrementalMapper:
         # off by default — a similarity of the whole model, it changes no residual, only the gauge
         # the result is reported in (pose_errors aligns by a similarity anyway)
         self.normalize = normalize
+        # "overlap": the images sharing most points with the new one (the mode every measured run
+        # used); "reference": IncrementalMapper::FindLocalBundle in full (find_local_bundle)
+        self.local_bundle_selection = local_bundle_selection
+        self.ba_local_min_tri_angle = ba_local_min_tri_angle
         self.log = []
 
     # ---- RegisterInitialLineImages --------------------------------------------------------
@@ -296,6 +301,69 @@ class IncrementalMapper:
         self.tvec[reg], self.points[pid] = tvec, pts
         return scale
 
+    def find_local_bundle(self, i):
+        """IncrementalMapper::FindLocalBundle (sfm/incremental_mapper.cc:993-1160): the registered
+        images sharing points with image i by descending number of shared observations; if there
+        are more than ba_local_num_images - 1 of them, those whose triangulation angle towards
+        image i (75th percentile over image i's points, base/triangulation.cc:84-118) clears a
+        threshold are preferred, over eight successively relaxed (angle, overlap) thresholds, and
+        the rest is filled with the most overlapping ones.  Returns image indices in selection
+        order.  (Ties of the overlap count, which the reference's unordered map + std::sort leave
+        unspecified, are taken in registration order.)"""
+        seen_idx = np.flatnonzero(self.obs_on[i] & self.has_point)
+        if len(seen_idx) == 0:
+            return []
+        img_s, _ = self._views(seen_idx)
+        reg = np.array(self.registered)
+        shared = np.bincount(img_s, minlength=len(self.qvec))[reg]
+        shared[reg == i] = 0
+        order = np.argsort(-shared, kind="stable")
+        order = order[shared[order] > 0]
+        overlapping, counts = reg[order], shared[order]
+        num_eff = min(self.ba_local_num_images - 1, len(overlapping))
+        if len(overlapping) == num_eff:
+            return [int(v) for v in overlapping]
+        min_tri = np.deg2rad(self.ba_local_min_tri_angle)
+        n_pts = float(len(seen_idx))
+        thresholds = [(min_tri / 1.0, 0.6 * n_pts), (min_tri / 1.5, 0.6 * n_pts), (min_tri / 2.0, 0.5 * n_pts),
+                      (min_tri / 2.5, 0.4 * n_pts), (min_tri / 3.0, 0.3 * n_pts), (min_tri / 4.0, 0.2 * n_pts),
+                      (min_tri / 5.0, 0.1 * n_pts), (min_tri / 6.0, 0.1 * n_pts)]
+        centre = model_io.projection_centers(self.qvec[[i]], self.tvec[[i]])[0]
+        pts = self.points[seen_idx]
+        ray1 = ((pts - centre) ** 2).sum(axis=1)
+        tri_angle = np.full(len(overlapping), -1.0)
+        used = np.zeros(len(overlapping), bool)
+        local = []
+        for angle_thr, overlap_thr in thresholds:
+            for k in range(len(overlapping)):
+                if counts[k] < overlap_thr:
+                    break
+                if used[k]:
+                    continue
+                if tri_angle[k] < 0.0:
+                    c2 = model_io.projection_centers(self.qvec[[overlapping[k]]], self.tvec[[overlapping[k]]])[0]
+                    ray2 = ((pts - c2) ** 2).sum(axis=1)
+                    den = 2.0 * np.sqrt(ray1 * ray2)
+                    with np.errstate(invalid="ignore", divide="ignore"):
+                        ang = np.abs(np.arccos((ray1 + ray2 - ((centre - c2) ** 2).sum()) / den))
+                    ang = np.where(den == 0.0, 0.0, np.minimum(ang, np.pi - ang))
+                    idx = max(0, min(len(ang) - 1, int(round(75 / 100 * (len(ang) - 1)))))
+                    tri_angle[k] = np.partition(ang, idx)[idx]
+                if tri_angle[k] >= angle_thr:
+                    local.append(int(overlapping[k]))
+                    used[k] = True
+                    if len(local) >= num_eff:
+                        break
+            if len(local) >= num_eff:
+                break
+        for k in range(len(overlapping)):
+            if len(local) >= num_eff:
+                break
+            if not used[k]:
+                local.append(int(overlapping[k]))
+                used[k] = True
+        return local
+
     # ---- AdjustLocalBundle (sfm/incremental_mapper.cc:781-891) ----------------------------------
     def adjust_local_bundle(self, i, max_num_iterations=25):
         sc = self.scene
@@ -311,6 +379,8 @@ class IncrementalMapper:
         shared[reg == i] = -1
         order = np.argsort(-shared, kind="stable")[:self.ba_local_num_images - 1]
         local = [int(reg[k]) for k in order if shared[k] > 0]
+        if self.local_bundle_selection == "reference":
+            local = self.find_local_bundle(i)
         if not local:
             return
         bundle = [i] + local
