@@ -86,6 +86,8 @@ if rank == 0:
         "calls": {k: kinds.count(k) for k in ("register", "triangulate", "local_ba", "global_ba")},
         "max_rotation_error_rad": rot_err, "max_centre_error_rel": centre_err,
         "scene_generation_s": t_scene, "from_correspondence_graph": graph_info,
-        "note": "Python driver over the GPU operators; one shared PINHOLE camera, tracks given"}))
+        "note": "Python driver over the GPU operators; one shared PINHOLE camera, "
+                + ("tracks = connected components of the correspondence graph, initial images searched"
+                   if graph_info else "tracks given")}))
 if world > 1:
     dist.destroy_process_group()
