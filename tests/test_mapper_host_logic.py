@@ -109,3 +109,17 @@ def test_find_local_bundle_small_and_empty_cases():
     assert sorted(m.find_local_bundle(0)) == [1, 2, 3]       # fewer overlapping images than asked: all
     m.has_point[:] = False
     assert m.find_local_bundle(0) == []
+
+
+def test_scene_mean_focal_is_the_references_threshold_scale():
+    """Scene.mean_focal turns the mapper's pixel thresholds into normalised ones (max_error =
+    12 px / mean focal, sfm/incremental_mapper.cc:673-674): Camera::ImageToWorldThreshold of the
+    reference's own camera models (base/camera_models.h:533-543) for all 11 models."""
+    import oracle.reference as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libref_cost.so not built and /root/reference absent")
+    from test_ref_lifting import MODELS
+    lines = np.full((2, 1, 3), np.nan)
+    for model, params in MODELS:
+        sc = M.Scene(lines, [False], np.zeros((2, 3)), model, params, (1000, 960))
+        assert 12.0 / sc.mean_focal == R.image_to_world_threshold(model, params, 12.0), model
