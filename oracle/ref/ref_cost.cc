@@ -13,6 +13,7 @@
 // (oracle/ba_oracle.cc) and, on the GPU, with the analytic kernel.  Built by oracle/build_ref.sh
 // into oracle/_ref/libref_cost.so.
 #include <cstring>
+#include <cstdint>
 #include <vector>
 
 #include "base/camera_models.h"
@@ -115,6 +116,16 @@ void ref_image_to_world(int model, const double* params, int n, const double* xy
   const std::vector<double> p(params, params + ref_camera_num_params(model));
   for (int i = 0; i < n; ++i)
     colmap::CameraModelImageToWorld(model, p, xy[2 * i], xy[2 * i + 1], &uv[2 * i], &uv[2 * i + 1]);
+}
+
+// CameraModelHasBogusParams (src/base/camera_models.cc:233-253)
+int ref_has_bogus_params(int model, const double* params, uint64_t width, uint64_t height,
+                         double min_focal_length_ratio, double max_focal_length_ratio,
+                         double max_extra_param) {
+  return colmap::CameraModelHasBogusParams(
+             model, std::vector<double>(params, params + ref_camera_num_params(model)), width, height,
+             min_focal_length_ratio, max_focal_length_ratio, max_extra_param)
+             ? 1 : 0;
 }
 
 double ref_image_to_world_threshold(int model, const double* params, double threshold) {

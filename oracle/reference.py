@@ -237,6 +237,8 @@ def cost_lib():
         L.ref_world_to_image.argtypes = [C.c_int, _dp, C.c_double, C.c_double, _dp]
         L.ref_image_to_world_threshold.argtypes = [C.c_int, _dp, C.c_double]
         L.ref_image_to_world.argtypes = [C.c_int, _dp, C.c_int, _dp, _dp]
+        L.ref_has_bogus_params.argtypes = [C.c_int, _dp, C.c_uint64, C.c_uint64, C.c_double,
+                                           C.c_double, C.c_double]
         L.ref_image_to_world_threshold.restype = C.c_double
         L.ref_line_cost.argtypes = [C.c_int] + [_dp] * 10
         L.ref_constant_pose_line_cost.argtypes = [C.c_int] + [_dp] * 8
@@ -269,6 +271,13 @@ def image_to_world(model, params, xy):
     uv = np.zeros_like(xy)
     cost_lib().ref_image_to_world(model, pp, len(xy), xy.ctypes.data_as(_dp), uv.ctypes.data_as(_dp))
     return uv
+
+
+def has_bogus_params(model, params, width, height, min_focal_length_ratio, max_focal_length_ratio,
+                     max_extra_param):
+    params, pp = _d(params)
+    return bool(cost_lib().ref_has_bogus_params(model, pp, width, height, min_focal_length_ratio,
+                                                max_focal_length_ratio, max_extra_param))
 
 
 def image_to_world_threshold(model, params, threshold):

@@ -183,6 +183,34 @@ def WorldToImage(camera_model, params, uv):
     return np.stack([f1 * (u + du) + c1, f2 * (v + dv) + c2], 1)
 
 
+# focal-length / principal-point / extra parameter indices of the 11 models
+# (src/base/camera_models.h: Initialize{FocalLength,PrincipalPoint,ExtraParams}Idxs)
+_PARAM_GROUPS = {0: ((0,), (1, 2), ()), 1: ((0, 1), (2, 3), ()), 2: ((0,), (1, 2), (3,)),
+                 3: ((0,), (1, 2), (3, 4)), 4: ((0, 1), (2, 3), (4, 5, 6, 7)),
+                 5: ((0, 1), (2, 3), (4, 5, 6, 7)), 6: ((0, 1), (2, 3), tuple(range(4, 12))),
+                 7: ((0, 1), (2, 3), (4,)), 8: ((0,), (1, 2), (3,)), 9: ((0,), (1, 2), (3, 4)),
+                 10: ((0, 1), (2, 3), tuple(range(4, 12)))}
+
+
+def HasBogusParams(camera_model, params, width, height, min_focal_length_ratio,
+                   max_focal_length_ratio, max_extra_param):
+    """CameraModelHasBogusParams (src/base/camera_models.h:480-531): a focal length outside
+    [min, max] x max(width, height), a principal point outside the image or an extra parameter
+    above max_extra_param in magnitude — what the mapper tests before it trusts a camera
+    (sfm/incremental_mapper.cc:684-700, 953-955; sfm/incremental_triangulator.cc:767-781)."""
+    p = np.asarray(params, np.float64)
+    focal, pp, extra = _PARAM_GROUPS[camera_model]
+    max_size = max(int(width), int(height))
+    for k in focal:
+        ratio = p[k] / max_size
+        if ratio < min_focal_length_ratio or ratio > max_focal_length_ratio:
+            return True
+    cx, cy = p[pp[0]], p[pp[1]]
+    if cx < 0 or cx > width or cy < 0 or cy > height:
+        return True
+    return any(abs(p[k]) > max_extra_param for k in extra)
+
+
 def select_aligned_features(num_features, aligned_line_ratio, rng):
     """The reference's rule (extraction.cc:452-457): draw feature indices uniformly WITH
     replacement until the set holds at least ratio * n of them.  ``rng``: numpy Generator."""

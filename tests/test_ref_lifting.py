@@ -101,3 +101,22 @@ def test_lifted_lines_are_what_the_path_consumes(oracle, ref):
     assert np.array_equal(lines2, f / np.sqrt(f[:, 0] ** 2 + f[:, 1] ** 2)[:, None])
     with pytest.raises(ValueError):
         L.feature_lines_from_blob(blob, rows=len(lines) + 1)
+
+
+def test_has_bogus_params_matches_the_reference(ref):
+    rng = np.random.default_rng(12)
+    seen = set()
+    for model, params in MODELS:
+        n = len(params)
+        for _ in range(60):
+            p = np.array(params, np.float64)
+            k = int(rng.integers(0, n))
+            p[k] = p[k] * rng.choice([-1.0, 0.05, 0.5, 1.0, 3.0, 40.0]) + rng.choice([0.0, 0.0, 1e3, -2e3, 1.5])
+            args = (1000, 960, 0.1, 10.0, 1.0)
+            got = L.HasBogusParams(model, p, *args)
+            assert got == ref.has_bogus_params(model, p, *args), (model, p.tolist())
+            seen.add(got)
+        # the parameter groups themselves (ParameterizeCameras uses the same index lists)
+        focal, pp, extra = L._PARAM_GROUPS[model]
+        assert sorted(focal + pp + extra) == list(range(n))
+    assert seen == {True, False}
