@@ -194,7 +194,7 @@ _PARAM_GROUPS = {0: ((0,), (1, 2), ()), 1: ((0, 1), (2, 3), ()), 2: ((0,), (1, 2
 
 def HasBogusParams(camera_model, params, width, height, min_focal_length_ratio,
                    max_focal_length_ratio, max_extra_param):
-    """CameraModelHasBogusParams (src/base/camera_models.h:480-531): a focal length outside
+    """CameraModelHasBogusParams (src/base/camera_models.h:471-531): a focal length outside
     [min, max] x max(width, height), a principal point outside the image or an extra parameter
     above max_extra_param in magnitude — what the mapper tests before it trusts a camera
     (sfm/incremental_mapper.cc:684-700, 953-955; sfm/incremental_triangulator.cc:767-781)."""
